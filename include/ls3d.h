@@ -1,0 +1,212 @@
+/* ls3d.h — C ABI of libls3d_b200.so, the B200 (sm_100a) implementation of LiveScan3D's per-frame
+ * point-cloud hot path.  Plain C: pointers and sizes only, no C++/torch types.
+ *
+ * Part 1 keeps the reference's own exports (what LiveScanServer P/Invokes from NativeUtils.dll), same
+ * names, argument meaning, ownership and "never throws, returns nothing" error behaviour; each entry
+ * cites the reference declaration it replaces (paths relative to the LiveScan3D tree).
+ * Part 2 adds flat-array entries for the stages that only have a C++ signature in the reference
+ * (filter) or no single entry (the whole frame pipeline), plus the error side channel.
+ * Part 3 is the device-resident API (device pointers + a cudaStream_t passed as void*): what bench.py's
+ * HBM-resident timing and the multi-GPU host (one process per GPU, torch.distributed for collectives)
+ * drive.  Nothing here ever falls back to a CPU implementation: without a CUDA device every compute
+ * entry fails and ls3d_last_error() says why.
+ */
+#ifndef LS3D_H
+#define LS3D_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- reference data types (bit-identical layouts) -------------------------------------------------- */
+
+/* include/NativeUtils/icp.h:15-18 (and include/LiveScanClient/utils.h:44-61): 12 bytes, no padding */
+typedef struct Point3f { float X, Y, Z; } Point3f;
+
+/* include/LiveScanClient/utils.h:105-111: the colour type filter() carries, 4 bytes */
+typedef struct RGB { unsigned char rgbBlue, rgbGreen, rgbRed, rgbReserved; } RGB;
+
+/* include/NativeUtils/depthprocessing.h:29-33 (C# twin LiveScanServer/Utils.cs:314-333): 16 bytes */
+typedef struct VertexC4ubV3f { unsigned char R, G, B, A; float X, Y, Z; } VertexC4ubV3f;
+
+/* include/NativeUtils/depthprocessing.h:42-48 (C# LiveScanServer/Utils.cs:335-342) */
+typedef struct Mesh {
+	int nVertices;
+	VertexC4ubV3f *vertices;   /* callee-allocated; released by deleteMesh */
+	int nTriangles;
+	int *triangles;            /* callee-allocated (never NULL after a call); released by deleteMesh */
+} Mesh;
+
+/* ---- Part 1: the reference's exports -------------------------------------------------------------- */
+
+/* Replaces include/NativeUtils/icp.h:65 (src/NativeUtils/icp.cpp:75-177); C# binding
+ * LiveScanServer/MainWindowForm.cs:42-43.  Point-to-point ICP of verts2 onto verts1: verts2 is transformed
+ * in place, R (row-major 3x3) and t are accumulated into (R = R*Rk, t += T*R^T per iteration).
+ * Returns 1.0f like the reference (its error value is never computed, icp.cpp:85,176). */
+float ICP(Point3f *verts1, Point3f *verts2, int nVerts1, int nVerts2, float *R, float *t, int maxIter);
+
+/* Replaces include/NativeUtils/depthprocessing.h:103-105 (src/NativeUtils/depthprocessing.cpp:1631-1657);
+ * C# binding LiveScanServer/KinectServer.cs:41-44.  One sensor (depth_map_index) of the packed frame:
+ * depth -> camera space -> +t -> R* -> strict bbox cull -> row-major compaction -> Mesh (no triangles).
+ * depth_maps: packed little-endian u16 images; depth_colors: packed RGB triples; intr_params: 7 floats per
+ * map (cx,cy,fx,fy,r2,r4,r6); wtransform_params: 12 floats per map (t[3], R row-major). */
+void generateVerticesFromDepthMap(unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params, Mesh *out_mesh,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int depth_map_index);
+
+/* Replaces include/NativeUtils/depthprocessing.h:108-110 (src/NativeUtils/depthprocessing.cpp:1715-1792);
+ * C# binding LiveScanServer/KinectServer.cs:35-38.  All sensors -> one merged Mesh in sensor order.
+ * Scope: the vertex path (bcolor_transfer=false); triangle generation is row N3 ("next"),
+ * so nTriangles is 0 and `triangles` is a valid empty allocation.  Both flags are read as their low byte
+ * (the C# side marshals 4-byte BOOLs, KinectServer.cs:36-38). */
+void generateMeshFromDepthMaps(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params, Mesh *out_mesh, int bcolor_transfer,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int bgenerate_triangles);
+
+/* Replace src/NativeUtils/depthprocessing.cpp:1818-1835 (C# KinectServer.cs:56-60).  deleteMesh releases the
+ * two arrays and leaves the struct itself alone, as the reference does. */
+Mesh *createMesh(void);
+void deleteMesh(Mesh *mesh);
+
+/* ---- Part 2: flat-array entries for the C++-only stages ------------------------------------------ */
+
+/* Replaces `std::unordered_map<int,int> filter(std::vector<Point3f>&, std::vector<RGB>&, int k, float maxDist)`
+ * (include/LiveScanClient/filter.h:64, src/LiveScanClient/filter.cpp:36-81).  Removes point i iff the squared
+ * distance to its k-th nearest neighbour (itself included) exceeds (float)pow(maxDist,2); verts and colors are
+ * compacted in place in their original order; old_to_new[i] (may be NULL) receives the new index or -1.
+ * k<=0 or maxDist<=0: nothing is touched, old_to_new is filled with -2 (the reference returns a map holding only
+ * its {-1:-1} sentinel) and n is returned.  Returns the surviving count, or -1 on error. */
+int ls3d_filter(Point3f *verts, RGB *colors, int n, int k, float maxDist, int *old_to_new);
+
+/* The whole per-frame path in one call: per sensor map -> world transform -> cull (createVertices,
+ * depthprocessing.cpp:122-187) -> neighbour-count filter per sensor (filter.cpp:36-81; skipped when
+ * filter_k<=0 or filter_maxDist<=0) -> merge in sensor order (formMesh, depthprocessing.cpp:1578-1629).
+ * per_map_counts (may be NULL) receives each sensor's surviving vertex count.  Returns total vertices or -1. */
+int ls3d_frame_pipeline(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params, Mesh *out_mesh,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ,
+	int filter_k, float filter_maxDist, int *per_map_counts);
+
+/* FindClosestPointForEach (src/NativeUtils/icp.cpp:18-32) as a flat entry, for stage-level parity tests:
+ * index (into verts1) and squared distance of the nearest verts1 point for every verts2 point.  Returns 0/-1. */
+int ls3d_find_closest(const Point3f *verts1, int nVerts1, const Point3f *verts2, int nVerts2,
+	unsigned long long *indices, float *distances);
+
+/* Per-iteration trace of ICP (same fields as the oracle's), filled when a trace buffer is installed. */
+typedef struct Ls3dIcpTrace {
+	int n_matched;      /* one-to-one matches before rejection (icp.cpp:95-126) */
+	int n_accepted;     /* after RejectOutlierMatches (icp.cpp:56-73) */
+	float sigma;        /* GetStandardDeviation of squared distances (icp.cpp:34-54) */
+	float T[3];         /* tempT (icp.cpp:141) */
+	float Rk[9];        /* tempR (icp.cpp:153-163) */
+} Ls3dIcpTrace;
+
+/* ICP with a per-iteration trace (trace: maxIter entries, may be NULL).  Same contract as ICP(). */
+float ls3d_icp_trace(Point3f *verts1, Point3f *verts2, int nVerts1, int nVerts2, float *R, float *t, int maxIter,
+	Ls3dIcpTrace *trace);
+
+/* Last error of the calling thread's most recent failing call ("" if none).  The reference has no error
+ * reporting at all (every export returns void or a constant); this is the side channel that replaces the
+ * C++ exceptions it would let escape into the CLR (nanoflann.h:904 on an empty target, OpenCV asserts). */
+const char *ls3d_last_error(void);
+
+/* Library/device identification: "ls3d-b200 <version> sm_100a; device: <name> (cc X.Y)" or the failure text. */
+const char *ls3d_version(void);
+
+/* Number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches). */
+long long ls3d_launch_count(void);
+void ls3d_reset_launch_count(void);
+
+/* ---- Part 3: device-resident API ---------------------------------------------------------------- */
+
+typedef struct Ls3dFrame Ls3dFrame;   /* persistent per-rig state: descriptors, scratch, voxel hash, outputs */
+typedef struct Ls3dIcp Ls3dIcp;       /* persistent ICP state: target grid, dedupe slots, partial sums */
+
+/* A frame context for n_maps sensors of the given sizes on the current CUDA device. */
+Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int *heights);
+void ls3d_frame_destroy(Ls3dFrame *f);
+
+/* Host-side parameters (intrinsics 7/map, world transforms 12/map, bounds, filter settings): copied to the
+ * device descriptors asynchronously on `stream`.  Returns 0/-1. */
+int ls3d_frame_set_params(Ls3dFrame *f, const float *intr_params, const float *wtransform_params,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ,
+	int filter_k, float filter_maxDist, void *stream);
+
+/* Enqueue the whole path on `stream` for device-resident packed inputs (same layouts as the host API).
+ * first_map/n_run select a contiguous sensor range (n_run<=0: all).  No host synchronisation.  The merged
+ * cloud is left in ls3d_frame_vertices() (16-byte VertexC4ubV3f records), its length in device memory at
+ * ls3d_frame_count_ptr().  Returns the number of kernels enqueued, or -1. */
+int ls3d_frame_run(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run, void *stream);
+
+const void *ls3d_frame_vertices(Ls3dFrame *f);        /* device pointer: merged, filtered cloud */
+const void *ls3d_frame_culled_vertices(Ls3dFrame *f); /* device pointer: mapped+culled cloud before the filter */
+const int *ls3d_frame_count_ptr(Ls3dFrame *f);        /* device int[4]: {n_final, n_culled, error_flags, n_kept} */
+const int *ls3d_frame_sensor_starts(Ls3dFrame *f);    /* device int[n_maps+1]: start of each sensor in the merged cloud */
+const int *ls3d_frame_culled_starts(Ls3dFrame *f);    /* device int[n_maps+1]: same for the culled cloud */
+const int *ls3d_frame_old_to_new(Ls3dFrame *f);       /* device int[n_culled]: culled index -> merged index or -1 */
+const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f);  /* device int[sum w*h]: pixel -> culled vertex index within its sensor, or -1 */
+
+/* Same path, writing the merged cloud to a caller-provided device buffer at record offset read from
+ * d_dst_offset (device int, may be NULL = 0): the multi-GPU merge writes peer-mapped memory through this. */
+int ls3d_frame_run_to(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run,
+	void *d_dst_vertices, const int *d_dst_offset, void *stream);
+
+/* Multi-GPU merge: as ls3d_frame_run_to, but the final compaction stores every surviving record to n_peers
+ * destination buffers (peer-mapped device pointers, one per rank; host array of n_peers <= 8 pointers) at the
+ * same record offset — compaction and all-gather in one kernel over NVLink peer stores. */
+int ls3d_frame_run_peers(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run,
+	int n_peers, void *const *peer_dst_vertices, const int *d_dst_offset, void *stream);
+
+/* The same in two stream-ordered stages, for ranks that must exchange their survivor counts in between:
+ *   ls3d_frame_run_count   : everything up to and including the neighbour count; ls3d_frame_count_ptr()[3] then
+ *                            holds this rank's survivor count (n_kept) although nothing has been compacted yet
+ *   ls3d_frame_merge_peers : the final compaction, storing to every peer buffer at *d_dst_offset. */
+int ls3d_frame_run_count(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run, void *stream);
+int ls3d_frame_merge_peers(Ls3dFrame *f, int first_map, int n_run, int n_peers, void *const *peer_dst_vertices, const int *d_dst_offset, void *stream);
+
+/* Plain device allocations that can be shared between the ranks of one node (one process per GPU) through CUDA
+ * IPC: export a 64-byte handle, open it in another process to get a peer-mapped pointer (NVLink loads/stores). */
+void *ls3d_dev_alloc(unsigned long long bytes);
+void ls3d_dev_free(void *p);
+int ls3d_ipc_export(void *p, unsigned char handle[64]);
+void *ls3d_ipc_open(const unsigned char handle[64]);
+void ls3d_ipc_close(void *p);
+
+/* ICP context sized for at most n1_max target and n2_max source points on the current device. */
+Ls3dIcp *ls3d_icp_create(int n1_max, int n2_max);
+void ls3d_icp_destroy(Ls3dIcp *c);
+
+/* Build the target grid from device points (Point3f layout) — once per ICP call (the reference rebuilds its
+ * kd-tree every iteration although verts1 never changes, icp.cpp:21-23). */
+int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, void *stream);
+/* Source cloud (device, Point3f layout, transformed in place).  [i_begin,i_end) is the slice whose nearest
+ * neighbours THIS rank searches (0,n2 on one GPU); R/t accumulators start from R0 (9 floats), t0 (3). */
+int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_begin, int i_end, const float *R0, const float *t0, void *stream);
+
+/* One iteration, in the three stream-ordered stages a multi-GPU host interleaves collectives with:
+ *   ls3d_icp_match : apply the previous iteration's (T,Rk) to verts2, NN search of the local slice, one-to-one
+ *                    dedupe by 64-bit atomicMin into the slot array (ls3d_icp_slots: int64[n1], MIN-reducible)
+ *   ls3d_icp_stats : count / sum / sum of squares of matched d2 over slots [j_begin,j_end) -> ls3d_icp_stats_buf (f64[4])
+ *   ls3d_icp_sums  : 2.5 sigma rejection + the 16 correspondence sums over slots [j_begin,j_end) -> ls3d_icp_sums_buf
+ *                    (f64[16]); resets all slots for the next iteration.
+ * ls3d_icp_finish applies the last (T,Rk), leaving R,t in ls3d_icp_Rt (device f32[12]: R[9] then t[3]). */
+int ls3d_icp_match(Ls3dIcp *c, void *stream);
+int ls3d_icp_stats(Ls3dIcp *c, int j_begin, int j_end, void *stream);
+int ls3d_icp_sums(Ls3dIcp *c, int j_begin, int j_end, void *stream);
+int ls3d_icp_finish(Ls3dIcp *c, void *stream);
+/* All maxIter iterations on one GPU, no host round trips (captured once per shape as a CUDA graph). */
+int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream);
+
+long long *ls3d_icp_slots(Ls3dIcp *c);      /* device int64[n1] */
+double *ls3d_icp_stats_buf(Ls3dIcp *c);     /* device f64[4]  : count, sum d2, sum d2^2, 0 */
+double *ls3d_icp_sums_buf(Ls3dIcp *c);      /* device f64[16] : count, sum(p-q)[3], sum p[3], sum q (x) p [9] */
+float *ls3d_icp_Rt(Ls3dIcp *c);             /* device f32[12] */
+const int *ls3d_icp_nn_index(Ls3dIcp *c);   /* device int[n2]: last NN index per source point (-1 outside the slice) */
+const float *ls3d_icp_nn_dist(Ls3dIcp *c);  /* device f32[n2] */
+Ls3dIcpTrace *ls3d_icp_trace_buf(Ls3dIcp *c); /* device trace[64]: entry i filled by iteration i (i < 64) */
+const int *ls3d_icp_status(Ls3dIcp *c);     /* device int[4]: {iterations applied, error flags, 0, 0} */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS3D_H */

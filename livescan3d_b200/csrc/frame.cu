@@ -1,0 +1,1056 @@
+// frame.cu — the per-frame path on the device: depth -> camera space -> world transform -> bbox cull ->
+// neighbour-count outlier filter -> multi-sensor merge, plus the host-buffer entry points that keep the
+// reference's signatures.
+//
+// Reference behaviour reproduced (paths relative to the LiveScan3D tree):
+//   createVertices            src/NativeUtils/depthprocessing.cpp:122-187  (+ RotatePoint :109-120)
+//   formMesh (vertex part)    src/NativeUtils/depthprocessing.cpp:1578-1629
+//   generateVerticesFromDepthMap / generateMeshFromDepthMaps   :1631-1657 / :1715-1792
+//   filter / KNNeighbors      src/LiveScanClient/filter.cpp:36-81 / :19-34
+//
+// Kernels (all sensors of a run are batched into every launch; "g" is a point's index in the culled cloud):
+//   K1 k_map_cull_compact  per 2048-pixel tile: u16 depth + RGB in, pinhole map, +t, R*, strict cull, stable
+//                          compaction through a decoupled look-back scan, 16-byte records out (HBM-bound)
+//   K2 k_voxel_insert      voxel key per point, warp-aggregated insert into a per-sensor open-addressing hash
+//                          whose 64-bit entries hold (key+1)<<24 | count; returns slot and rank per point
+//   K3 k_cell_ranges       one contiguous range of the sorted array per occupied voxel
+//   K4 k_cell_scatter      counting-sort scatter of (x,y,z,g) into voxel order
+//   K5 k_neighbour_count   one warp per occupied voxel: 27 hash look-ups by 27 lanes, candidates staged in
+//                          shared memory, count{d2 <= thr} per query by ballot/popc with warp-uniform early
+//                          exit at k (the filter keeps i  <=>  its k-th NN distance <= thr  <=>  count >= k)
+//   K6 k_filter_compact    stable compaction of the survivors (look-back scan again); sensor order is the
+//                          merge order, so the merged cloud is produced here with no extra copy; can store
+//                          to several destinations (peer-mapped buffers) for the multi-GPU merge
+#include "ls3d_common.cuh"
+#include "ls3d_internal.h"
+#include "../../include/ls3d.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace ls3d {
+
+constexpr int kCellBits = 13;                 // voxel coordinate bits per axis
+constexpr int kCellMax = (1 << kCellBits) - 1;
+constexpr unsigned long long kCountMask = 0xFFFFFFull;
+constexpr int kCountWarps = 8;                // warps per block in K5
+constexpr int kChunk = 256;                   // candidates staged per warp in K5
+constexpr int kMaxPeers = 8;
+
+struct PeerDst { int n; uint4 *ptr[kMaxPeers]; };
+
+__device__ __forceinline__ unsigned voxel_hash(unsigned long long key) {
+	return (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 32);
+}
+__device__ __forceinline__ int cell_coord(float x, float o, float inv_h) {
+	// monotone in x: fp32 subtract, fp32 multiply by a positive constant, floor, clamp
+	float u = floorf(__fmul_rn(__fsub_rn(x, o), inv_h));
+	u = fminf(fmaxf(u, 0.0f), (float)kCellMax);
+	return (int)u;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1: map + world transform + cull + stable compaction
+// ------------------------------------------------------------------------------------------------------
+template <bool kWriteD2V>
+__global__ void __launch_bounds__(kScanThreads) k_map_cull_compact(
+	const uint8_t *__restrict__ depth, const uint8_t *__restrict__ colors, const SensorDesc *__restrict__ sd,
+	int s_first, int s_end, float minX, float minY, float minZ, float maxX, float maxY, float maxZ,
+	FrameCtl *ctl, unsigned long long *status, int *culled_starts,
+	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ d2v)
+{
+	__shared__ uint4 stage[kTile];
+	__shared__ unsigned sm[16];
+	__shared__ int s_tile, s_sensor;
+
+	const int tile0 = sd[s_first].tile_begin;
+	const int ntiles = sd[s_end].tile_begin - tile0;
+	const int out_off = d_out_offset ? *d_out_offset : 0;
+	const int tid = threadIdx.x;
+
+	for (;;) {
+		if (tid == 0) {
+			const int t = (int)atomicAdd(&ctl->tile_counter_a, 1u);
+			s_tile = t;
+			if (t < ntiles) {
+				int s = s_first;
+				while (sd[s + 1].tile_begin <= t + tile0) s++;
+				s_sensor = s;
+			}
+		}
+		__syncthreads();
+		const int tile = s_tile;
+		if (tile >= ntiles) break;
+		const int s = s_sensor;
+		const int w = sd[s].w, px = sd[s].px;
+		const int p0 = (tile + tile0 - sd[s].tile_begin) * kTile + tid * 8;
+		const int rem = px - p0;
+
+		// ---- loads: 8 u16 depths (one LDG.128), 8 RGB triples (three LDG.64) ----
+		unsigned short dv[8];
+		const uint8_t *dp = depth + sd[s].depth_off + 2ll * p0;
+		if (rem >= 8 && (((uintptr_t)dp) & 15) == 0) {
+			const uint4 v = __ldg(reinterpret_cast<const uint4 *>(dp));
+			dv[0] = v.x & 0xffff; dv[1] = v.x >> 16; dv[2] = v.y & 0xffff; dv[3] = v.y >> 16;
+			dv[4] = v.z & 0xffff; dv[5] = v.z >> 16; dv[6] = v.w & 0xffff; dv[7] = v.w >> 16;
+		} else {
+#pragma unroll
+			for (int j = 0; j < 8; j++) dv[j] = (j < rem) ? __ldg(reinterpret_cast<const unsigned short *>(dp) + j) : (unsigned short)0;
+		}
+		unsigned nz = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) nz |= (dv[j] != 0 ? 1u : 0u) << j;
+
+		unsigned cw[6] = {0, 0, 0, 0, 0, 0};     // 24 colour bytes
+		const uint8_t *cp = colors + sd[s].color_off + 3ll * p0;
+		if (nz) {
+			if (rem >= 8 && (((uintptr_t)cp) & 7) == 0) {
+				const uint2 a = __ldg(reinterpret_cast<const uint2 *>(cp));
+				const uint2 b = __ldg(reinterpret_cast<const uint2 *>(cp) + 1);
+				const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cp) + 2);
+				cw[0] = a.x; cw[1] = a.y; cw[2] = b.x; cw[3] = b.y; cw[4] = c.x; cw[5] = c.y;
+			} else {
+#pragma unroll
+				for (int j = 0; j < 8; j++)
+					if ((nz >> j) & 1) {
+#pragma unroll
+						for (int c = 0; c < 3; c++) {
+							const int bi = 3 * j + c;
+							cw[bi >> 2] |= (unsigned)__ldg(cp + bi) << (8 * (bi & 3));
+						}
+					}
+			}
+		}
+
+		// ---- per-pixel arithmetic, in the reference's evaluation order (depthprocessing.cpp:148-162) ----
+		const float cx = sd[s].cx, cy = sd[s].cy, fx = sd[s].fx, fy = sd[s].fy;
+		const float t0 = sd[s].t[0], t1 = sd[s].t[1], t2 = sd[s].t[2];
+		const float r0 = sd[s].R[0], r1 = sd[s].R[1], r2 = sd[s].R[2];
+		const float r3 = sd[s].R[3], r4 = sd[s].R[4], r5 = sd[s].R[5];
+		const float r6 = sd[s].R[6], r7 = sd[s].R[7], r8 = sd[s].R[8];
+		int y = p0 / w, x = p0 - y * w;
+		float vx[8], vy[8], vz[8];
+		unsigned valid = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			if ((nz >> j) & 1) {
+				const float val = (float)dv[j];
+				float Z = __fdiv_rn(val, 1000.0f);
+				float X = __fdiv_rn(__fsub_rn((float)x, cx), fx);
+				float Y = __fdiv_rn(__fsub_rn(cy, (float)y), fy);
+				X = __fmul_rn(X, Z);
+				Y = __fmul_rn(Y, Z);
+				X = __fadd_rn(X, t0); Y = __fadd_rn(Y, t1); Z = __fadd_rn(Z, t2);
+				const float wx = __fadd_rn(__fadd_rn(__fmul_rn(X, r0), __fmul_rn(Y, r1)), __fmul_rn(Z, r2));
+				const float wy = __fadd_rn(__fadd_rn(__fmul_rn(X, r3), __fmul_rn(Y, r4)), __fmul_rn(Z, r5));
+				const float wz = __fadd_rn(__fadd_rn(__fmul_rn(X, r6), __fmul_rn(Y, r7)), __fmul_rn(Z, r8));
+				const bool outside = wx < minX || wx > maxX || wy < minY || wy > maxY || wz < minZ || wz > maxZ;
+				vx[j] = wx; vy[j] = wy; vz[j] = wz;
+				if (!outside) valid |= 1u << j;
+			}
+			if (++x == w) { x = 0; y++; }
+		}
+
+		// ---- stable compaction ----
+		const unsigned cnt = __popc(valid);
+		unsigned total, base;
+		const unsigned off = tile_scan(cnt, sm, status, tile, &ctl->err, &total, &base);
+		{
+			unsigned o = off;
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+				if ((valid >> j) & 1) {
+					const int bi = 3 * j;
+					// bytes bi, bi+1, bi+2 of the 24-byte colour block -> R,G,B,255
+					const unsigned long long lo = ((unsigned long long)cw[(bi >> 2) + ((bi >> 2) < 5 ? 1 : 0)] << 32) | cw[bi >> 2];
+					const unsigned rgb = (unsigned)(lo >> (8 * (bi & 3))) & 0xffffffu;
+					stage[o++] = make_uint4(rgb | 0xff000000u, __float_as_uint(vx[j]), __float_as_uint(vy[j]), __float_as_uint(vz[j]));
+				}
+		}
+		if (kWriteD2V) {
+			int *dst = d2v + sd[s].pix_begin + p0;
+			unsigned o = base + off;
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+				if (j < rem) dst[j] = ((valid >> j) & 1) ? (int)(o++) : -1;
+		}
+		if (tid == 0) {
+			if (tile + tile0 == sd[s].tile_begin) culled_starts[s] = (int)base;
+			if (tile == ntiles - 1) { culled_starts[s_end] = (int)(base + total); ctl->n_culled = (int)(base + total); ctl->n_final = (int)(base + total); }
+		}
+		__syncthreads();
+		uint4 *o4 = out + out_off + base;
+		for (unsigned i = tid; i < total; i += kScanThreads) o4[i] = stage[i];
+		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2: voxel hash insert
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ cloud, const SensorDesc *__restrict__ sd,
+	const int *__restrict__ culled_starts, int s_first, int s_end, FrameCtl *ctl,
+	unsigned long long *table, unsigned *__restrict__ slot_of, unsigned *__restrict__ rank_of)
+{
+	const int N = ctl->n_culled;
+	const int lane = threadIdx.x & 31;
+	for (int g0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); g0 < N; g0 += gridDim.x * blockDim.x) {
+		const int g = g0 + lane;
+		const bool active = g < N;
+		unsigned long long key = 0, tag = ~0ull - (unsigned long long)lane;
+		int s = s_first;
+		if (active) {
+			while (s + 1 < s_end && culled_starts[s + 1] <= g) s++;
+			const uint4 p = cloud[g];
+			const int cx = cell_coord(__uint_as_float(p.y), sd[s].gox, sd[s].ginv_h);
+			const int cy = cell_coord(__uint_as_float(p.z), sd[s].goy, sd[s].ginv_h);
+			const int cz = cell_coord(__uint_as_float(p.w), sd[s].goz, sd[s].ginv_h);
+			key = ((unsigned long long)cz << (2 * kCellBits)) | ((unsigned long long)cy << kCellBits) | (unsigned long long)cx;
+			tag = key | ((unsigned long long)s << 40);
+		}
+		const unsigned grp = __match_any_sync(kFull, tag);
+		const int leader = __ffs(grp) - 1;
+		unsigned slot = 0, base_rank = 0;
+		if (active && lane == leader) {
+			const unsigned n = __popc(grp);
+			const unsigned toff = sd[s].tbl_off, tmask = sd[s].tbl_mask;
+			const unsigned long long want = key + 1;
+			unsigned h = voxel_hash(key) & tmask;
+			bool found = false;
+			for (unsigned probe = 0; probe <= tmask; probe++) {
+				const unsigned long long w = table[toff + h];
+				const unsigned long long kk = w >> 24;
+				if (kk == want) { found = true; break; }
+				if (kk == 0) {
+					const unsigned long long prev = atomicCAS(&table[toff + h], 0ull, want << 24);
+					if (prev == 0 || (prev >> 24) == want) { found = true; break; }
+				}
+				h = (h + 1) & tmask;
+			}
+			if (!found) atomicOr(&ctl->err, kErrProbeLimit);
+			else {
+				const unsigned long long old = atomicAdd(&table[toff + h], (unsigned long long)n);
+				base_rank = (unsigned)(old & kCountMask);
+				if (base_rank + n > (unsigned)kCountMask) atomicOr(&ctl->err, kErrCellOverflow);
+			}
+			slot = toff + h;
+		}
+		__syncwarp();
+		slot = __shfl_sync(kFull, slot, leader);
+		base_rank = __shfl_sync(kFull, base_rank, leader);
+		if (active) {
+			slot_of[g] = slot;
+			rank_of[g] = base_rank + __popc(grp & ((1u << lane) - 1u));
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3: contiguous range of the sorted array for every occupied voxel
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_ranges(const unsigned long long *__restrict__ table, unsigned *__restrict__ cell_start,
+	unsigned slot_lo, unsigned slot_hi, FrameCtl *ctl)
+{
+	const unsigned i = slot_lo + blockIdx.x * blockDim.x + threadIdx.x;    // ranges are multiples of 32
+	const int lane = threadIdx.x & 31;
+	unsigned cnt = 0;
+	if (i < slot_hi) {
+		const unsigned long long w = table[i];
+		if (w >> 24) cnt = (unsigned)(w & kCountMask);
+	}
+	const unsigned incl = warp_incl_scan(cnt, lane);
+	const unsigned total = __shfl_sync(kFull, incl, 31);
+	if (total == 0) return;
+	unsigned base = 0;
+	if (lane == 0) base = atomicAdd(&ctl->cursor, total);
+	base = __shfl_sync(kFull, base, 0);
+	if (cnt) cell_start[i] = base + incl - cnt;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4: scatter into voxel order
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_scatter(const uint4 *__restrict__ cloud, const unsigned *__restrict__ slot_of,
+	const unsigned *__restrict__ rank_of, const unsigned *__restrict__ cell_start, const FrameCtl *ctl, float4 *__restrict__ sorted)
+{
+	const int N = ctl->n_culled;
+	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
+		const uint4 p = cloud[g];
+		const unsigned pos = cell_start[slot_of[g]] + rank_of[g];
+		sorted[pos] = make_float4(__uint_as_float(p.y), __uint_as_float(p.z), __uint_as_float(p.w), __int_as_float(g));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5: neighbour count per point, one warp per occupied voxel
+// ------------------------------------------------------------------------------------------------------
+// neighbour offsets in visiting order: home, 6 faces, 12 edges, 8 corners (nearer voxels first, so the
+// warp-uniform early exit at k fires as soon as possible)
+__constant__ signed char c_nb[27][3] = {
+	{0, 0, 0},
+	{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+	{-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1}, {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
+	{-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
+
+// Count staged candidates against the (up to 32) queries of this group.  Candidates sit in lanes, queries are
+// broadcast by shuffle, so the running count of a query is warp-uniform and the exit at k costs no divergence.
+__device__ __forceinline__ bool count_chunk(const float4 *buf, int fill, int nq, const float4 &myq, int &mycount, int k, float thr, int lane) {
+	for (int q = 0; q < nq; q++) {
+		int c = __shfl_sync(kFull, mycount, q);
+		if (c >= k) continue;
+		const float qx = __shfl_sync(kFull, myq.x, q), qy = __shfl_sync(kFull, myq.y, q), qz = __shfl_sync(kFull, myq.z, q);
+		for (int s = 0; s < fill; s += 32) {
+			const int idx = s + lane;
+			const float4 cd = buf[idx];                // idx < kChunk always; entries past `fill` are masked below
+			const float d2 = dist2_ref(qx, qy, qz, cd.x, cd.y, cd.z);
+			c += __popc(__ballot_sync(kFull, idx < fill && d2 <= thr));
+			if (c >= k) break;
+		}
+		if (lane == q) mycount = c;
+	}
+	return __all_sync(kFull, mycount >= k);
+}
+
+__global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const unsigned long long *__restrict__ table,
+	const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted, const SensorDesc *__restrict__ sd,
+	int s_first, int s_end, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep)
+{
+	__shared__ float4 sbuf[kCountWarps][kChunk];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	float4 *buf = sbuf[warp];
+	const unsigned slot_lo = sd[s_first].tbl_off, slot_hi = sd[s_end].tbl_off;
+	const unsigned nbatches = (slot_hi - slot_lo) >> 5;
+
+	for (;;) {
+		unsigned b = 0;
+		if (lane == 0) b = atomicAdd(&ctl->work_counter, 1u);
+		b = __shfl_sync(kFull, b, 0);
+		if (b >= nbatches) break;
+		const unsigned i = slot_lo + (b << 5) + lane;
+		const unsigned long long w = table[i];
+		const bool occ = (w >> 24) != 0;
+		const unsigned mystart = occ ? cell_start[i] : 0u;
+		unsigned mask = __ballot_sync(kFull, occ);
+		if (!mask) continue;
+		int s = s_first;
+		while (sd[s + 1].tbl_off <= slot_lo + (b << 5)) s++;
+		const unsigned toff = sd[s].tbl_off, tmask = sd[s].tbl_mask;
+
+		while (mask) {
+			const int j = __ffs(mask) - 1;
+			mask &= mask - 1;
+			const unsigned long long wj = __shfl_sync(kFull, w, j);
+			const unsigned sj = __shfl_sync(kFull, mystart, j);
+			const unsigned long long key = (wj >> 24) - 1;
+			const int Q = (int)(wj & kCountMask);
+			const int cx = (int)(key & kCellMax), cy = (int)((key >> kCellBits) & kCellMax), cz = (int)(key >> (2 * kCellBits));
+
+			// 27 voxel look-ups by 27 lanes
+			unsigned ncnt = 0, nstart = 0;
+			if (lane == 0) { ncnt = (unsigned)Q; nstart = sj; }
+			else if (lane < 27) {
+				const int nx = cx + c_nb[lane][0], ny = cy + c_nb[lane][1], nz = cz + c_nb[lane][2];
+				if (nx >= 0 && nx <= kCellMax && ny >= 0 && ny <= kCellMax && nz >= 0 && nz <= kCellMax) {
+					const unsigned long long nkey = ((unsigned long long)nz << (2 * kCellBits)) | ((unsigned long long)ny << kCellBits) | (unsigned long long)nx;
+					unsigned h = voxel_hash(nkey) & tmask;
+					for (unsigned probe = 0; probe <= tmask; probe++) {
+						const unsigned long long w2 = table[toff + h];
+						const unsigned long long kk = w2 >> 24;
+						if (kk == nkey + 1) { ncnt = (unsigned)(w2 & kCountMask); nstart = cell_start[toff + h]; break; }
+						if (kk == 0) break;
+						h = (h + 1) & tmask;
+					}
+				}
+			}
+			__syncwarp();
+
+			for (int qg = 0; qg < Q; qg += 32) {
+				const int nq = min(32, Q - qg);
+				float4 myq = make_float4(0.f, 0.f, 0.f, 0.f);
+				int mycount = k;                                   // lanes without a query count as done
+				if (lane < nq) { myq = sorted[sj + qg + lane]; mycount = 0; }
+				int fill = 0;
+				bool done = false;
+				for (int c = 0; c < 27 && !done; c++) {
+					const unsigned cc = __shfl_sync(kFull, ncnt, c), cs = __shfl_sync(kFull, nstart, c);
+					unsigned off = 0;
+					while (off < cc) {
+						const int take = min((int)(cc - off), kChunk - fill);
+						for (int t = lane; t < take; t += 32) buf[fill + t] = sorted[cs + off + t];
+						fill += take;
+						off += take;
+						if (fill == kChunk) {
+							__syncwarp();
+							done = count_chunk(buf, fill, nq, myq, mycount, k, thr, lane);
+							fill = 0;
+							__syncwarp();
+							if (done) break;
+						}
+					}
+					if (c == 0 && fill > 0 && !done) {       // the home voxel alone often settles every query
+						__syncwarp();
+						done = count_chunk(buf, fill, nq, myq, mycount, k, thr, lane);
+						fill = 0;
+						__syncwarp();
+					}
+				}
+				if (!done && fill > 0) {
+					__syncwarp();
+					count_chunk(buf, fill, nq, myq, mycount, k, thr, lane);
+					__syncwarp();
+				}
+				const bool kept = lane < nq && mycount >= k;
+				if (lane < nq) keep[__float_as_int(myq.w)] = (uint8_t)(kept ? 1 : 0);
+				const unsigned km = __ballot_sync(kFull, kept);
+				if (lane == 0 && km) atomicAdd(&ctl->n_kept, __popc(km));
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K6: stable compaction of the filter survivors == the merged cloud
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads) k_filter_compact(const uint4 *__restrict__ cloud, const uint8_t *__restrict__ keep,
+	const int *__restrict__ culled_starts, int s_first, int s_end, FrameCtl *ctl, unsigned long long *status, int *final_starts,
+	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ old_to_new, PeerDst peers)
+{
+	__shared__ uint4 stage[kTile];
+	__shared__ unsigned sm[16];
+	__shared__ int s_tile;
+	const int N = ctl->n_culled;
+	const int ntiles = (N + kTile - 1) / kTile;
+	const int out_off = d_out_offset ? *d_out_offset : 0;
+	const int tid = threadIdx.x;
+
+	for (;;) {
+		if (tid == 0) s_tile = (int)atomicAdd(&ctl->tile_counter_b, 1u);
+		__syncthreads();
+		const int tile = s_tile;
+		if (tile >= ntiles) break;
+		const int g0 = tile * kTile + tid * 8;
+		unsigned valid = 0;
+		if (g0 + 8 <= N) {
+			const uint2 f = *reinterpret_cast<const uint2 *>(keep + g0);
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if ((f.x >> (8 * j)) & 0xff) valid |= 1u << j;
+				if ((f.y >> (8 * j)) & 0xff) valid |= 1u << (4 + j);
+			}
+		} else {
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+				if (g0 + j < N && keep[g0 + j]) valid |= 1u << j;
+		}
+		const unsigned cnt = __popc(valid);
+		unsigned total, base;
+		const unsigned off = tile_scan(cnt, sm, status, tile, &ctl->err, &total, &base);
+		{
+			unsigned o = off;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const bool kept = (valid >> j) & 1;
+				if (kept) stage[o] = cloud[g0 + j];
+				if (g0 + j < N) old_to_new[g0 + j] = kept ? (int)(base + o) : -1;
+				if (kept) o++;
+			}
+		}
+		// sensor boundaries of the merged cloud
+		for (int s = s_first + 1; s < s_end; s++) {
+			const int bnd = culled_starts[s];
+			if (bnd >= g0 && bnd < g0 + 8 && bnd < N)
+				final_starts[s] = (int)(base + off + __popc(valid & ((1u << (bnd - g0)) - 1u)));
+		}
+		if (tid == 0 && tile == ntiles - 1) {
+			const int n_final = (int)(base + total);
+			ctl->n_final = n_final;
+			for (int s = s_first + 1; s <= s_end; s++)
+				if (culled_starts[s] >= N) final_starts[s] = n_final;
+		}
+		if (tid == 0 && tile == 0) final_starts[s_first] = 0;
+		__syncthreads();
+		if (peers.n == 0) {
+			uint4 *o4 = out + out_off + base;
+			for (unsigned i = tid; i < total; i += kScanThreads) o4[i] = stage[i];
+		} else {
+			for (int p = 0; p < peers.n; p++) {
+				uint4 *o4 = peers.ptr[p] + out_off + base;
+				for (unsigned i = tid; i < total; i += kScanThreads) o4[i] = stage[i];
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// standalone filter helpers: pack Point3f + RGB into 16-byte records (+ bounding box), grid parameters on
+// the device, unpack survivors
+// ------------------------------------------------------------------------------------------------------
+struct FilterBox { unsigned mn[3], mx[3]; };   // order-preserving encodings
+
+__global__ void __launch_bounds__(256) k_filter_pack(const float *__restrict__ verts, const unsigned *__restrict__ colors, int n,
+	uint4 *__restrict__ cloud, FilterBox *box)
+{
+	float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const float x = verts[3 * (size_t)i], y = verts[3 * (size_t)i + 1], z = verts[3 * (size_t)i + 2];
+		cloud[i] = make_uint4(colors[i], __float_as_uint(x), __float_as_uint(y), __float_as_uint(z));
+		if (isfinite(x)) { mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x); }
+		if (isfinite(y)) { mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y); }
+		if (isfinite(z)) { mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z); }
+	}
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			mn[a] = fminf(mn[a], __shfl_xor_sync(kFull, mn[a], o));
+			mx[a] = fmaxf(mx[a], __shfl_xor_sync(kFull, mx[a], o));
+		}
+	}
+	if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+		for (int a = 0; a < 3; a++) {
+			atomicMin(&box->mn[a], f2ord(mn[a]));
+			atomicMax(&box->mx[a], f2ord(mx[a]));
+		}
+	}
+}
+
+// Voxel-grid parameters from a bounding box.  Cell edge h = 1.01 r: two points with fp32 d2 <= fl(r^2) are
+// closer than r(1+1e-6) on every axis, the fp32 voxel coordinate u = fl(fl(x-o)*inv_h) carries an absolute
+// error below 2e-3 (u <= 8192), so their coordinates differ by less than 1 and their voxels by at most 1:
+// the 27-voxel neighbourhood provably contains every point that can count.  When the box would need more than
+// 2^13 voxels per axis the cells grow instead (still correct, only more candidates).
+__host__ __device__ inline void voxel_grid_params(const double lo[3], const double hi[3], double r, float origin[3], float *inv_h) {
+	double ext = 0;
+	for (int a = 0; a < 3; a++) {
+		double e = hi[a] - lo[a];
+		if (!(e >= 0)) e = 0;
+		if (e > ext) ext = e;
+	}
+	if (!(ext < 1e30)) ext = 1e30;
+	double h = r * 1.01;
+	const double hmin = ext / (double)(kCellMax - 3);
+	if (h < hmin) h = hmin * 1.0001;
+	if (!(h > 1e-30)) h = 1e-30;
+	for (int a = 0; a < 3; a++) {
+		double l = lo[a];
+		if (!(l > -1e30)) l = -1e30;
+		if (!(l < 1e30)) l = 1e30;
+		origin[a] = (float)(l - h);
+	}
+	*inv_h = (float)(1.0 / h);
+}
+
+__global__ void k_filter_grid_params(const FilterBox *box, SensorDesc *sd, FrameCtl *ctl, int *culled_starts, int n, float max_dist) {
+	double lo[3], hi[3];
+	for (int a = 0; a < 3; a++) {
+		lo[a] = (double)ord2f(box->mn[a]);
+		hi[a] = (double)ord2f(box->mx[a]);
+		if (!(lo[a] <= hi[a])) { lo[a] = 0; hi[a] = 0; }       // no finite coordinate on this axis
+	}
+	float o[3], inv_h;
+	voxel_grid_params(lo, hi, (double)max_dist, o, &inv_h);
+	sd[0].gox = o[0]; sd[0].goy = o[1]; sd[0].goz = o[2]; sd[0].ginv_h = inv_h;
+	ctl->n_culled = n;
+	ctl->n_final = n;
+	culled_starts[0] = 0;
+	culled_starts[1] = n;
+}
+
+__global__ void __launch_bounds__(256) k_filter_unpack(const uint4 *__restrict__ cloud, const FrameCtl *ctl, float *__restrict__ verts, unsigned *__restrict__ colors) {
+	const int n = ctl->n_final;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint4 p = cloud[i];
+		colors[i] = p.x;
+		verts[3 * (size_t)i] = __uint_as_float(p.y);
+		verts[3 * (size_t)i + 1] = __uint_as_float(p.z);
+		verts[3 * (size_t)i + 2] = __uint_as_float(p.w);
+	}
+}
+
+}  // namespace ls3d
+
+using namespace ls3d;
+
+// ======================================================================================================
+// Frame context
+// ======================================================================================================
+struct Ls3dFrame {
+	int device = 0;
+	int S = 0;
+	std::vector<int> w, h;
+	long long total_px = 0;
+	int total_tiles = 0;
+	size_t depth_bytes = 0, color_bytes = 0;
+	unsigned total_slots = 0;
+	std::vector<SensorDesc> h_sd;       // S+1 entries (sentinel last)
+	SensorDesc *pin_sd = nullptr;       // pinned staging for the descriptor upload
+	float bounds[6] = {0, 0, 0, 0, 0, 0};
+	int filter_k = 0;
+	float filter_max_dist = 0, filter_thr = 0;
+	bool filter_on = false;
+	bool params_set = false;
+	int sm_count = 148;
+
+	// device memory
+	DevBuf sd, zero, cloud0, sorted, final_, slot_of, rank_of, keep, map, d2v, table, cell_start, in_depth, in_colors, box;
+	// carve-outs of `zero` (re-zeroed by one memset per run)
+	FrameCtl *ctl = nullptr;
+	unsigned long long *status_a = nullptr, *status_b = nullptr;
+	int *culled_starts = nullptr, *final_starts = nullptr;
+	size_t zero_bytes = 0;
+	// pinned read-back block: FrameCtl + starts
+	int *pin_out = nullptr;
+	bool want_d2v = false;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void frame_free(Ls3dFrame *f) {
+	if (!f) return;
+	DevBuf *bufs[] = {&f->sd, &f->zero, &f->cloud0, &f->sorted, &f->final_, &f->slot_of, &f->rank_of, &f->keep, &f->map, &f->d2v,
+		&f->table, &f->cell_start, &f->in_depth, &f->in_colors, &f->box};
+	for (DevBuf *b : bufs) b->release();
+	if (f->pin_sd) cudaFreeHost(f->pin_sd);
+	if (f->pin_out) cudaFreeHost(f->pin_out);
+	delete f;
+}
+
+extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int *heights) {
+	clear_error();
+	if (!ensure_device()) return nullptr;
+	if (n_maps <= 0 || !widths || !heights) { set_error("ls3d_frame_create: n_maps must be positive"); return nullptr; }
+	Ls3dFrame *f = new Ls3dFrame();
+	cudaGetDevice(&f->device);
+	cudaDeviceGetAttribute(&f->sm_count, cudaDevAttrMultiProcessorCount, f->device);
+	f->S = n_maps;
+	f->w.assign(widths, widths + n_maps);
+	f->h.assign(heights, heights + n_maps);
+	f->h_sd.resize(n_maps + 1);
+	long long px_acc = 0, depth_off = 0, color_off = 0;
+	int tile_acc = 0;
+	unsigned long long slot_acc = 0;
+	for (int i = 0; i <= n_maps; i++) {
+		SensorDesc &d = f->h_sd[i];
+		memset(&d, 0, sizeof(d));
+		d.tile_begin = tile_acc;
+		d.depth_off = depth_off;
+		d.color_off = color_off;
+		d.pix_begin = px_acc;
+		d.tbl_off = (unsigned)slot_acc;
+		if (i == n_maps) break;
+		if (widths[i] <= 0 || heights[i] <= 0 || (long long)widths[i] * heights[i] >= (1ll << 24)) {
+			set_error("ls3d_frame_create: map %d has unsupported size %dx%d (need 0 < w*h < 2^24)", i, widths[i], heights[i]);
+			delete f;
+			return nullptr;
+		}
+		const long long px = (long long)widths[i] * heights[i];
+		d.w = widths[i]; d.h = heights[i]; d.px = (int)px;
+		unsigned long long cap = 64;
+		while (cap < (unsigned long long)px * 3 / 2) cap <<= 1;
+		d.tbl_mask = (unsigned)(cap - 1);
+		slot_acc += cap;
+		px_acc += px;
+		depth_off += px * 2;
+		color_off += px * 3;
+		tile_acc += (int)((px + kTile - 1) / kTile);
+	}
+	if (px_acc >= (1ll << 31) - kTile || slot_acc >= (1ull << 32)) { set_error("ls3d_frame_create: frame too large"); delete f; return nullptr; }
+	f->total_px = px_acc;
+	f->total_tiles = tile_acc;
+	f->depth_bytes = (size_t)depth_off;
+	f->color_bytes = (size_t)color_off;
+	f->total_slots = (unsigned)slot_acc;
+
+	const size_t n = (size_t)f->total_px;
+	const size_t ctl_b = align_up(sizeof(FrameCtl), 256);
+	const size_t st_b = align_up(sizeof(unsigned long long) * (size_t)(f->total_tiles + 1), 256);
+	const size_t starts_b = align_up(sizeof(int) * (size_t)(n_maps + 1), 256);
+	f->zero_bytes = ctl_b + 2 * st_b + 2 * starts_b;
+	bool ok = f->sd.reserve(sizeof(SensorDesc) * (n_maps + 1), "alloc descriptors") && f->zero.reserve(f->zero_bytes, "alloc control block") &&
+		f->cloud0.reserve(16 * n, "alloc culled cloud") && f->sorted.reserve(16 * n, "alloc sorted cloud") && f->final_.reserve(16 * n, "alloc merged cloud") &&
+		f->slot_of.reserve(4 * n, "alloc slots") && f->rank_of.reserve(4 * n, "alloc ranks") && f->keep.reserve(align_up(n, 16) + 16, "alloc keep flags") &&
+		f->map.reserve(4 * n, "alloc index map") && f->d2v.reserve(4 * n, "alloc pixel map") &&
+		f->table.reserve(8 * (size_t)f->total_slots, "alloc voxel hash") && f->cell_start.reserve(4 * (size_t)f->total_slots, "alloc voxel ranges") &&
+		f->box.reserve(sizeof(FilterBox), "alloc bbox");
+	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_sd, sizeof(SensorDesc) * (n_maps + 1), cudaHostAllocDefault), "alloc pinned descriptors");
+	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_out, sizeof(int) * (size_t)(16 + 2 * (n_maps + 1)), cudaHostAllocDefault), "alloc pinned read-back");
+	if (!ok) { frame_free(f); return nullptr; }
+	uint8_t *z = f->zero.as<uint8_t>();
+	f->ctl = reinterpret_cast<FrameCtl *>(z);
+	f->status_a = reinterpret_cast<unsigned long long *>(z + ctl_b);
+	f->status_b = reinterpret_cast<unsigned long long *>(z + ctl_b + st_b);
+	f->culled_starts = reinterpret_cast<int *>(z + ctl_b + 2 * st_b);
+	f->final_starts = reinterpret_cast<int *>(z + ctl_b + 2 * st_b + starts_b);
+	cudaMemset(f->zero.p, 0, f->zero_bytes);
+	return f;
+}
+
+extern "C" void ls3d_frame_destroy(Ls3dFrame *f) { frame_free(f); }
+
+// Axis-aligned bounds of everything sensor `d` can produce (any u16 depth), intersected with the cull box.
+static void sensor_world_bounds(const SensorDesc &d, const float *b, double lo[3], double hi[3]) {
+	const double zmax = 65.535;
+	const double fx = fabs((double)d.fx), fy = fabs((double)d.fy);
+	const double xr = fmax(fabs(0.0 - d.cx), fabs((double)(d.w - 1) - d.cx)) / fx * zmax;
+	const double yr = fmax(fabs((double)d.cy - 0.0), fabs((double)d.cy - (double)(d.h - 1))) / fy * zmax;
+	const double clo[3] = {-xr + d.t[0], -yr + d.t[1], 0.0 + d.t[2]};
+	const double chi[3] = {xr + d.t[0], yr + d.t[1], zmax + d.t[2]};
+	for (int i = 0; i < 3; i++) {
+		double l = 0, h = 0;
+		for (int j = 0; j < 3; j++) {
+			const double r = d.R[3 * i + j];
+			const double a = r * clo[j], c = r * chi[j];
+			l += fmin(a, c);
+			h += fmax(a, c);
+		}
+		const double pad = 1e-3 * (fabs(l) + fabs(h)) + 1e-3;
+		l -= pad; h += pad;
+		if (!(l == l) || !(h == h) || !std::isfinite(l) || !std::isfinite(h)) { l = -1e30; h = 1e30; }
+		const double bl = (double)b[i], bh = (double)b[3 + i];
+		if (bl == bl && bl > l) l = bl;
+		if (bh == bh && bh < h) h = bh;
+		if (h < l) h = l;
+		lo[i] = l; hi[i] = h;
+	}
+}
+
+// n_set: how many leading sensors intr_params / wtransform_params describe (<= f->S)
+static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, const float *wtransform_params,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int filter_k, float filter_maxDist, void *stream)
+{
+	if (!f || !intr_params || !wtransform_params) { set_error("ls3d_frame_set_params: null argument"); return -1; }
+	f->bounds[0] = minX; f->bounds[1] = minY; f->bounds[2] = minZ; f->bounds[3] = maxX; f->bounds[4] = maxY; f->bounds[5] = maxZ;
+	f->filter_on = filter_k > 0 && filter_maxDist > 0;        // filter.cpp:38-41
+	f->filter_k = filter_k;
+	f->filter_max_dist = filter_maxDist;
+	f->filter_thr = (float)pow((double)filter_maxDist, 2.0);  // filter.cpp:52: float = pow(float, int)
+	for (int i = 0; i < n_set && i < f->S; i++) {
+		SensorDesc &d = f->h_sd[i];
+		const float *ip = intr_params + 7 * i;                 // IntrinsicCameraParameters(float*), depthprocessing.h:96-97
+		d.cx = ip[0]; d.cy = ip[1]; d.fx = ip[2]; d.fy = ip[3];
+		const float *tp = wtransform_params + 12 * i;          // WorldTranformation(float*), depthprocessing.h:56-63
+		memcpy(d.t, tp, 3 * sizeof(float));
+		memcpy(d.R, tp + 3, 9 * sizeof(float));
+		if (f->filter_on) {
+			double lo[3], hi[3];
+			sensor_world_bounds(d, f->bounds, lo, hi);
+			float o[3];
+			voxel_grid_params(lo, hi, (double)filter_maxDist, o, &d.ginv_h);
+			d.gox = o[0]; d.goy = o[1]; d.goz = o[2];
+		}
+	}
+	memcpy(f->pin_sd, f->h_sd.data(), sizeof(SensorDesc) * (f->S + 1));
+	if (!cuda_ok(cudaMemcpyAsync(f->sd.p, f->pin_sd, sizeof(SensorDesc) * (f->S + 1), cudaMemcpyHostToDevice, (cudaStream_t)stream), "upload descriptors")) return -1;
+	f->params_set = true;
+	return 0;
+}
+
+extern "C" int ls3d_frame_set_params(Ls3dFrame *f, const float *intr_params, const float *wtransform_params,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int filter_k, float filter_maxDist, void *stream)
+{
+	return frame_set_params(f, f ? f->S : 0, intr_params, wtransform_params, minX, minY, minZ, maxX, maxY, maxZ, filter_k, filter_maxDist, stream);
+}
+
+enum { kStageCount = 1, kStageMerge = 2 };
+
+__global__ void __launch_bounds__(256) k_keep_all(uint8_t *keep, FrameCtl *ctl) {
+	const int N = ctl->n_culled;
+	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) keep[g] = 1;
+	if (blockIdx.x == 0 && threadIdx.x == 0) ctl->n_kept = N;
+}
+
+static int frame_merge_stage(Ls3dFrame *f, int s_first, int s_end, long long n_max, uint4 *dst, const int *d_dst_offset, const PeerDst &peers, cudaStream_t st) {
+	const int tiles = (int)((n_max + kTile - 1) / kTile);
+	k_filter_compact<<<std::max(1, std::min(tiles, f->sm_count * 6)), kScanThreads, 0, st>>>(f->cloud0.as<uint4>(), f->keep.as<uint8_t>(),
+		f->culled_starts, s_first, s_end, f->ctl, f->status_b, f->final_starts, dst, d_dst_offset, f->map.as<int>(), peers);
+	count_launch(1);
+	return cuda_ok(cudaGetLastError(), "k_filter_compact") ? 1 : -1;
+}
+
+static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n_max, uint4 *dst, const int *d_dst_offset, const PeerDst &peers, cudaStream_t st, int stages = kStageCount | kStageMerge) {
+	const SensorDesc *sd = f->sd.as<SensorDesc>();
+	const unsigned slot_lo = f->h_sd[s_first].tbl_off, slot_hi = f->h_sd[s_end].tbl_off;
+	if (!cuda_ok(cudaMemsetAsync(f->table.as<unsigned long long>() + slot_lo, 0, 8 * (size_t)(slot_hi - slot_lo), st), "clear voxel hash")) return -1;
+	const int pt_blocks = (int)std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8);
+	k_voxel_insert<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
+		f->table.as<unsigned long long>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>());
+	k_cell_ranges<<<(slot_hi - slot_lo + 255) / 256, 256, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(), slot_lo, slot_hi, f->ctl);
+	k_cell_scatter<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(),
+		f->cell_start.as<unsigned>(), f->ctl, f->sorted.as<float4>());
+	k_neighbour_count<<<f->sm_count * 6, kCountWarps * 32, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(),
+		f->sorted.as<float4>(), sd, s_first, s_end, f->ctl, f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
+	count_launch(4);
+	if (!cuda_ok(cudaGetLastError(), "filter kernels")) return -1;
+	if (!(stages & kStageMerge)) return 4;
+	return frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st) < 0 ? -1 : 5;
+}
+
+// stages: kStageCount runs map/cull (+ the filter through the neighbour count); kStageMerge runs the final
+// compaction.  `split` forces the culled cloud to stay local so a later kStageMerge call can place it.
+static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_colors, int first_map, int n_run,
+	uint4 *dst, const int *d_dst_offset, const PeerDst &peers, cudaStream_t st, int stages = kStageCount | kStageMerge)
+{
+	if (!f) { set_error("ls3d_frame_run: null frame"); return -1; }
+	if (stages == kStageMerge) {
+		if (n_run <= 0) { first_map = 0; n_run = f->S; }
+		if (first_map < 0 || first_map + n_run > f->S) { set_error("ls3d_frame_merge: sensor range outside 0..%d", f->S); return -1; }
+		const long long n_max = f->h_sd[first_map + n_run].pix_begin - f->h_sd[first_map].pix_begin;
+		return frame_merge_stage(f, first_map, first_map + n_run, n_max, dst, d_dst_offset, peers, st);
+	}
+	const bool split = !(stages & kStageMerge);
+	if (!d_depth || !d_colors) { set_error("ls3d_frame_run: null argument"); return -1; }
+	if (!f->params_set) { set_error("ls3d_frame_run: ls3d_frame_set_params has not been called"); return -1; }
+	if (n_run <= 0) { first_map = 0; n_run = f->S; }
+	if (first_map < 0 || first_map + n_run > f->S) { set_error("ls3d_frame_run: sensor range [%d,%d) outside 0..%d", first_map, first_map + n_run, f->S); return -1; }
+	const int s_first = first_map, s_end = first_map + n_run;
+	if (!cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block")) return -1;
+	const int ntiles = f->h_sd[s_end].tile_begin - f->h_sd[s_first].tile_begin;
+	const long long n_max = f->h_sd[s_end].pix_begin - f->h_sd[s_first].pix_begin;
+	const int blocks = std::max(1, std::min(ntiles, f->sm_count * 6));
+	const float *b = f->bounds;
+	uint4 *k1_out = (f->filter_on || split) ? f->cloud0.as<uint4>() : dst;
+	const int *k1_off = (f->filter_on || split) ? nullptr : d_dst_offset;
+	if (f->want_d2v)
+		k_map_cull_compact<true><<<blocks, kScanThreads, 0, st>>>((const uint8_t *)d_depth, (const uint8_t *)d_colors, f->sd.as<SensorDesc>(), s_first, s_end,
+			b[0], b[1], b[2], b[3], b[4], b[5], f->ctl, f->status_a, f->culled_starts, k1_out, k1_off, f->d2v.as<int>());
+	else
+		k_map_cull_compact<false><<<blocks, kScanThreads, 0, st>>>((const uint8_t *)d_depth, (const uint8_t *)d_colors, f->sd.as<SensorDesc>(), s_first, s_end,
+			b[0], b[1], b[2], b[3], b[4], b[5], f->ctl, f->status_a, f->culled_starts, k1_out, k1_off, nullptr);
+	count_launch(1);
+	if (!cuda_ok(cudaGetLastError(), "k_map_cull_compact")) return -1;
+	int launched = 1;
+	if (f->filter_on) {
+		const int r = frame_filter_stages(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st, stages);
+		if (r < 0) return -1;
+		launched += r;
+	} else if (split) {
+		k_keep_all<<<(int)std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8), 256, 0, st>>>(f->keep.as<uint8_t>(), f->ctl);
+		count_launch(1);
+		if (!cuda_ok(cudaGetLastError(), "k_keep_all")) return -1;
+		launched += 1;
+	}
+	return launched;
+}
+
+extern "C" int ls3d_frame_run(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run, void *stream) {
+	PeerDst none; none.n = 0;
+	if (!f) { set_error("ls3d_frame_run: null frame"); return -1; }
+	return frame_run_impl(f, d_depth_maps, d_depth_colors, first_map, n_run, f->final_.as<uint4>(), nullptr, none, (cudaStream_t)stream);
+}
+
+extern "C" int ls3d_frame_run_to(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run,
+	void *d_dst_vertices, const int *d_dst_offset, void *stream) {
+	PeerDst none; none.n = 0;
+	if (!f || !d_dst_vertices) { set_error("ls3d_frame_run_to: null argument"); return -1; }
+	return frame_run_impl(f, d_depth_maps, d_depth_colors, first_map, n_run, (uint4 *)d_dst_vertices, d_dst_offset, none, (cudaStream_t)stream);
+}
+
+extern "C" int ls3d_frame_run_count(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run, void *stream) {
+	PeerDst none; none.n = 0;
+	return frame_run_impl(f, d_depth_maps, d_depth_colors, first_map, n_run, nullptr, nullptr, none, (cudaStream_t)stream, kStageCount);
+}
+
+extern "C" int ls3d_frame_merge_peers(Ls3dFrame *f, int first_map, int n_run, int n_peers, void *const *peer_dst_vertices, const int *d_dst_offset, void *stream) {
+	if (!f || !peer_dst_vertices || n_peers <= 0 || n_peers > kMaxPeers) { set_error("ls3d_frame_merge_peers: need 1..%d destination buffers", kMaxPeers); return -1; }
+	PeerDst peers;
+	peers.n = n_peers;
+	for (int i = 0; i < kMaxPeers; i++) peers.ptr[i] = i < n_peers ? (uint4 *)peer_dst_vertices[i] : nullptr;
+	return frame_run_impl(f, nullptr, nullptr, first_map, n_run, (uint4 *)peer_dst_vertices[0], d_dst_offset, peers, (cudaStream_t)stream, kStageMerge);
+}
+
+extern "C" int ls3d_frame_run_peers(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run,
+	int n_peers, void *const *peer_dst_vertices, const int *d_dst_offset, void *stream) {
+	if (!f || !peer_dst_vertices || n_peers <= 0 || n_peers > kMaxPeers) { set_error("ls3d_frame_run_peers: need 1..%d destination buffers", kMaxPeers); return -1; }
+	if (!f->filter_on) { set_error("ls3d_frame_run_peers: the peer-store merge is fused into the filter compaction; enable the filter"); return -1; }
+	PeerDst peers;
+	peers.n = n_peers;
+	for (int i = 0; i < kMaxPeers; i++) peers.ptr[i] = i < n_peers ? (uint4 *)peer_dst_vertices[i] : nullptr;
+	return frame_run_impl(f, d_depth_maps, d_depth_colors, first_map, n_run, (uint4 *)peer_dst_vertices[0], d_dst_offset, peers, (cudaStream_t)stream);
+}
+
+extern "C" const void *ls3d_frame_vertices(Ls3dFrame *f) { return f ? f->final_.p : nullptr; }
+extern "C" const void *ls3d_frame_culled_vertices(Ls3dFrame *f) { return f ? (f->filter_on ? f->cloud0.p : f->final_.p) : nullptr; }
+extern "C" const int *ls3d_frame_count_ptr(Ls3dFrame *f) { return f ? &f->ctl->n_final : nullptr; }
+extern "C" const int *ls3d_frame_sensor_starts(Ls3dFrame *f) { return f ? (f->filter_on ? f->final_starts : f->culled_starts) : nullptr; }
+extern "C" const int *ls3d_frame_culled_starts(Ls3dFrame *f) { return f ? f->culled_starts : nullptr; }
+extern "C" const int *ls3d_frame_old_to_new(Ls3dFrame *f) { return f ? f->map.as<int>() : nullptr; }
+extern "C" const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f) {
+	if (!f) return nullptr;
+	f->want_d2v = true;      // produced from the next run on
+	return f->d2v.as<int>();
+}
+
+// ======================================================================================================
+// Host-buffer (drop-in) entry points
+// ======================================================================================================
+static Ls3dFrame *g_frame = nullptr;     // cached context for the host-buffer API, keyed by the size list
+
+static Ls3dFrame *cached_frame(int n_maps, const int *widths, const int *heights) {
+	// a context built for a longer size list serves any prefix of it (generateVerticesFromDepthMap is called once
+	// per sensor with the same arrays, KinectServer.cs:527-554)
+	if (g_frame && g_frame->S >= n_maps && !memcmp(g_frame->w.data(), widths, sizeof(int) * n_maps) && !memcmp(g_frame->h.data(), heights, sizeof(int) * n_maps))
+		return g_frame;
+	if (g_frame) { frame_free(g_frame); g_frame = nullptr; }
+	g_frame = ls3d_frame_create(n_maps, widths, heights);
+	if (g_frame) {
+		if (!g_frame->in_depth.reserve(g_frame->depth_bytes, "alloc depth input") || !g_frame->in_colors.reserve(g_frame->color_bytes, "alloc colour input")) {
+			frame_free(g_frame);
+			g_frame = nullptr;
+		}
+	}
+	return g_frame;
+}
+
+static void mesh_reset(Mesh *m) {
+	m->nVertices = 0;
+	m->vertices = nullptr;
+	m->nTriangles = 0;
+	m->triangles = (int *)malloc(sizeof(int));    // valid empty allocation, like the reference's new int[0]
+}
+
+// Shared body: upload sensors [first, first+n_run), run, read back.  Returns total vertices or -1.
+static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params, Mesh *out_mesh, const float bounds[6], int first, int n_run,
+	int filter_k, float filter_maxDist, int *per_map_counts)
+{
+	clear_error();
+	if (out_mesh) mesh_reset(out_mesh);
+	if (!out_mesh || !depth_maps || !depth_colors || !widths || !heights || !intr_params || !wtransform_params) { set_error("null argument"); return -1; }
+	if (n_maps <= 0 || first < 0 || n_run <= 0 || first + n_run > n_maps) { set_error("sensor range [%d,%d) outside 0..%d", first, first + n_run, n_maps); return -1; }
+	if (!ensure_device()) return -1;
+	std::lock_guard<std::mutex> lk(api_mutex());
+	cudaStream_t st = api_stream();
+	if (!st) return -1;
+	Ls3dFrame *f = cached_frame(n_maps, widths, heights);
+	if (!f) return -1;
+	const SensorDesc &a = f->h_sd[first], &z = f->h_sd[first + n_run];
+	if (!cuda_ok(cudaMemcpyAsync(f->in_depth.as<uint8_t>() + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off), cudaMemcpyHostToDevice, st), "upload depth")) return -1;
+	if (!cuda_ok(cudaMemcpyAsync(f->in_colors.as<uint8_t>() + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off), cudaMemcpyHostToDevice, st), "upload colours")) return -1;
+	if (frame_set_params(f, n_maps, intr_params, wtransform_params, bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5], filter_k, filter_maxDist, st) < 0) return -1;
+	if (ls3d_frame_run(f, f->in_depth.p, f->in_colors.p, first, n_run, st) < 0) return -1;
+	// read back the counts, then exactly the bytes that exist
+	int *po = f->pin_out;
+	const int *starts = ls3d_frame_sensor_starts(f);
+	if (!cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read counts")) return -1;
+	if (!cuda_ok(cudaMemcpyAsync(po + 16, starts, sizeof(int) * (n_maps + 1), cudaMemcpyDeviceToHost, st), "read sensor starts")) return -1;
+	if (!cuda_ok(cudaStreamSynchronize(st), "frame pipeline")) return -1;
+	const FrameCtl *hc = reinterpret_cast<const FrameCtl *>(po);
+	if (hc->err) { set_error("device reported error flags 0x%x in the frame pipeline", hc->err); return -1; }
+	const int n = hc->n_final;
+	if (per_map_counts) {
+		for (int i = 0; i < n_maps; i++) per_map_counts[i] = 0;
+		for (int i = first; i < first + n_run; i++) per_map_counts[i] = po[16 + i + 1] - po[16 + i];
+	}
+	if (n > 0) {
+		void *v = host_block_alloc((size_t)n * sizeof(VertexC4ubV3f));
+		if (!v) { set_error("out of host memory for %d vertices", n); return -1; }
+		if (!cuda_ok(cudaMemcpyAsync(v, f->final_.p, (size_t)n * sizeof(VertexC4ubV3f), cudaMemcpyDeviceToHost, st), "read vertices") ||
+			!cuda_ok(cudaStreamSynchronize(st), "read vertices")) { host_block_free(v); return -1; }
+		out_mesh->vertices = (VertexC4ubV3f *)v;
+	} else {
+		out_mesh->vertices = (VertexC4ubV3f *)host_block_alloc(sizeof(VertexC4ubV3f));   // valid empty allocation
+	}
+	out_mesh->nVertices = n;
+	return n;
+}
+
+extern "C" void generateVerticesFromDepthMap(unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params, Mesh *out_mesh,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int depth_map_index)
+{
+	const float b[6] = {minX, minY, minZ, maxX, maxY, maxZ};
+	// the reference only ever reads entries 0..depth_map_index of widths/heights (depthprocessing.cpp:1646-1650)
+	host_frame(depth_map_index + 1, depth_maps, depth_colors, widths, heights, intr_params, wtransform_params, out_mesh, b, depth_map_index, 1, 0, 0.0f, nullptr);
+}
+
+extern "C" void generateMeshFromDepthMaps(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params, Mesh *out_mesh, int bcolor_transfer,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int bgenerate_triangles)
+{
+	const float b[6] = {minX, minY, minZ, maxX, maxY, maxZ};
+	(void)bcolor_transfer; (void)bgenerate_triangles;     // colour transfer and triangles are outside this path
+	host_frame(n_maps, depth_maps, depth_colors, widths, heights, intr_params, wtransform_params, out_mesh, b, 0, n_maps, 0, 0.0f, nullptr);
+}
+
+extern "C" int ls3d_frame_pipeline(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params, Mesh *out_mesh,
+	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int filter_k, float filter_maxDist, int *per_map_counts)
+{
+	const float b[6] = {minX, minY, minZ, maxX, maxY, maxZ};
+	return host_frame(n_maps, depth_maps, depth_colors, widths, heights, intr_params, wtransform_params, out_mesh, b, 0, n_maps, filter_k, filter_maxDist, per_map_counts);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// ls3d_filter: the reference's filter() on flat arrays
+// ------------------------------------------------------------------------------------------------------
+static Ls3dFrame *g_filter_frame = nullptr;
+static DevBuf g_fv, g_fc;
+
+extern "C" int ls3d_filter(Point3f *verts, RGB *colors, int n, int k, float maxDist, int *old_to_new) {
+	clear_error();
+	if (n < 0 || (n > 0 && (!verts || !colors))) { set_error("ls3d_filter: bad arguments"); return -1; }
+	if (k <= 0 || maxDist <= 0) {                      // filter.cpp:38-41: nothing happens
+		if (old_to_new) for (int i = 0; i < n; i++) old_to_new[i] = -2;
+		return n;
+	}
+	if (n == 0) return 0;
+	if (n >= (1 << 24)) { set_error("ls3d_filter: at most 2^24-1 points per call"); return -1; }
+	if (!ensure_device()) return -1;
+	std::lock_guard<std::mutex> lk(api_mutex());
+	cudaStream_t st = api_stream();
+	if (!st) return -1;
+	// a one-"sensor" context whose pixel budget covers n points
+	if (!g_filter_frame || g_filter_frame->total_px < n) {
+		if (g_filter_frame) frame_free(g_filter_frame);
+		int cap = 1 << 16;
+		while (cap < n) cap <<= 1;
+		if (cap >= (1 << 24)) cap = (1 << 24) - 1;
+		const int one = 1;
+		g_filter_frame = ls3d_frame_create(1, &cap, &one);
+		if (!g_filter_frame) return -1;
+	}
+	Ls3dFrame *f = g_filter_frame;
+	if (!g_fv.reserve(12 * (size_t)n, "alloc filter verts") || !g_fc.reserve(4 * (size_t)n, "alloc filter colours")) return -1;
+	f->filter_on = true;
+	f->filter_k = k;
+	f->filter_max_dist = maxDist;
+	f->filter_thr = (float)pow((double)maxDist, 2.0);
+	f->params_set = true;
+	FilterBox hb;
+	for (int a = 0; a < 3; a++) { hb.mn[a] = 0xffffffffu; hb.mx[a] = 0u; }
+	memcpy(f->pin_sd, f->h_sd.data(), sizeof(SensorDesc) * 2);
+	bool ok = cuda_ok(cudaMemcpyAsync(g_fv.p, verts, 12 * (size_t)n, cudaMemcpyHostToDevice, st), "upload verts") &&
+		cuda_ok(cudaMemcpyAsync(g_fc.p, colors, 4 * (size_t)n, cudaMemcpyHostToDevice, st), "upload colours") &&
+		cuda_ok(cudaMemcpyAsync(f->sd.p, f->pin_sd, sizeof(SensorDesc) * 2, cudaMemcpyHostToDevice, st), "upload descriptor") &&
+		cuda_ok(cudaMemcpyAsync(f->box.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, st), "init bbox") &&
+		cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block");
+	if (!ok) return -1;
+	const int blocks = std::min((n + 255) / 256, f->sm_count * 8);
+	k_filter_pack<<<blocks, 256, 0, st>>>(g_fv.as<float>(), g_fc.as<unsigned>(), n, f->cloud0.as<uint4>(), f->box.as<FilterBox>());
+	k_filter_grid_params<<<1, 1, 0, st>>>(f->box.as<FilterBox>(), f->sd.as<SensorDesc>(), f->ctl, f->culled_starts, n, maxDist);
+	count_launch(2);
+	PeerDst none; none.n = 0;
+	if (frame_filter_stages(f, 0, 1, n, f->final_.as<uint4>(), nullptr, none, st) < 0) return -1;
+	k_filter_unpack<<<blocks, 256, 0, st>>>(f->final_.as<uint4>(), f->ctl, g_fv.as<float>(), g_fc.as<unsigned>());
+	count_launch(1);
+	int *po = f->pin_out;
+	ok = cuda_ok(cudaGetLastError(), "filter kernels") && cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read counts") &&
+		cuda_ok(cudaStreamSynchronize(st), "filter");
+	if (!ok) return -1;
+	const FrameCtl *hc = reinterpret_cast<const FrameCtl *>(po);
+	if (hc->err) { set_error("device reported error flags 0x%x in the filter", hc->err); return -1; }
+	const int m = hc->n_final;
+	ok = true;
+	if (m > 0) {
+		ok = cuda_ok(cudaMemcpyAsync(verts, g_fv.p, 12 * (size_t)m, cudaMemcpyDeviceToHost, st), "read verts") &&
+			cuda_ok(cudaMemcpyAsync(colors, g_fc.p, 4 * (size_t)m, cudaMemcpyDeviceToHost, st), "read colours");
+	}
+	if (ok && old_to_new) ok = cuda_ok(cudaMemcpyAsync(old_to_new, f->map.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st), "read index map");
+	ok = ok && cuda_ok(cudaStreamSynchronize(st), "filter read-back");
+	return ok ? m : -1;
+}

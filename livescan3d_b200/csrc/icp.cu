@@ -1,0 +1,846 @@
+// icp.cu — the NativeUtils ICP refinement loop on the device, plus its host-buffer entry points.
+//
+// Reference behaviour reproduced (paths relative to the LiveScan3D tree):
+//   ICP                       src/NativeUtils/icp.cpp:75-177
+//   FindClosestPointForEach   src/NativeUtils/icp.cpp:18-32   (nanoflann kd-tree, exact 1-NN, include/nanoflann.h)
+//   one-to-one dedupe         src/NativeUtils/icp.cpp:95-126  (smaller d2 wins, later source index wins ties)
+//   GetStandardDeviation / RejectOutlierMatches   src/NativeUtils/icp.cpp:34-73  (sigma of SQUARED distances, keep d2 <= 2.5 sigma)
+//   Kabsch block              src/NativeUtils/icp.cpp:138-168 (T = mean(p-q); M = sum (q+T) p^T about the origin; Rk = U V^T)
+//
+// Device design:
+//   * the target grid is built ONCE per call (the reference rebuilds its kd-tree every iteration): a dense
+//     G^3 grid in Morton order.  Morton order makes every octree node a contiguous range of the cell-start
+//     array, so node occupancy is start[end]-start[begin] and no pyramid has to be stored.
+//   * k_icp_match: exact nearest neighbour = home cell, then the 26 neighbours whose box can still hold a closer
+//     point, then — only if the 3x3x3 block cannot prove the answer — a near-first depth-first walk of the
+//     implicit octree with the current best as the pruning bound (exact for arbitrarily distant points).
+//     One-to-one dedupe is a 64-bit atomicMin of (bits(d2) << 32 | ~i) per target point.
+//   * k_icp_stats / k_icp_sums: warp-shuffle + block reductions in fp64 with a fixed-order last-block final
+//     pass (deterministic); the 3x3 SVD (one-sided Jacobi) runs on the device in the next kernel's prologue.
+//   * iterations are stream-ordered launches (or one CUDA graph): no host round trip inside ICP.
+#include "ls3d_common.cuh"
+#include "ls3d_internal.h"
+#include "../../include/ls3d.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace ls3d {
+
+constexpr unsigned long long kSlotEmpty = 0x7FFFFFFFFFFFFFFFull;   // positive as int64: MIN-reducible by NCCL/torch as signed
+constexpr int kRedBlocks = 296;                                    // 2 per SM: blocks of the reduction kernels
+constexpr int kTraceCap = 64;
+
+struct IcpGrid {
+	float ox, oy, oz;     // origin (bbox min of the target)
+	float h, inv_h;       // cell edge and its reciprocal
+	int G, levels;        // cells per axis (power of two), log2(G)
+	int pad;
+};
+
+struct IcpState {
+	float R[9], t[3];       // accumulated pose (ls3d_icp_Rt points here)
+	int iters_applied, err, pad0, pad1;
+	unsigned ticket_stats, ticket_sums, scan_counter, pad2;
+};
+
+struct IcpBox { unsigned mn[3], mx[3]; };
+
+__device__ __forceinline__ unsigned spread3(unsigned v) {     // 10 bits -> every third bit
+	v &= 0x3ffu;
+	v = (v | (v << 16)) & 0x030000FFu;
+	v = (v | (v << 8)) & 0x0300F00Fu;
+	v = (v | (v << 4)) & 0x030C30C3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+__device__ __forceinline__ unsigned morton3(unsigned x, unsigned y, unsigned z) { return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2); }
+
+__device__ __forceinline__ int icp_cell(float rel, float inv_h, int G) {
+	float u = floorf(rel * inv_h);
+	u = fminf(fmaxf(u, 0.0f), (float)(G - 1));
+	return (int)u;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// target grid build
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_icp_bbox(const float *__restrict__ v, int n, IcpBox *box) {
+	float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+		for (int a = 0; a < 3; a++) {
+			const float x = v[3 * (size_t)i + a];
+			if (isfinite(x)) { mn[a] = fminf(mn[a], x); mx[a] = fmaxf(mx[a], x); }
+		}
+	}
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			mn[a] = fminf(mn[a], __shfl_xor_sync(kFull, mn[a], o));
+			mx[a] = fmaxf(mx[a], __shfl_xor_sync(kFull, mx[a], o));
+		}
+	}
+	if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+		for (int a = 0; a < 3; a++) { atomicMin(&box->mn[a], f2ord(mn[a])); atomicMax(&box->mx[a], f2ord(mx[a])); }
+	}
+}
+
+__global__ void k_icp_grid_params(const IcpBox *box, IcpGrid *grid, int G, int levels) {
+	double lo[3], ext = 0;
+	for (int a = 0; a < 3; a++) {
+		double l = (double)ord2f(box->mn[a]), h = (double)ord2f(box->mx[a]);
+		if (!(l <= h)) { l = 0; h = 0; }
+		lo[a] = l;
+		if (h - l > ext) ext = h - l;
+	}
+	double h = ext / (double)G * 1.0001;
+	if (!(h > 1e-30)) h = 1.0;
+	grid->ox = (float)lo[0]; grid->oy = (float)lo[1]; grid->oz = (float)lo[2];
+	grid->h = (float)h;
+	grid->inv_h = (float)(1.0 / h);
+	grid->G = G;
+	grid->levels = levels;
+}
+
+__global__ void __launch_bounds__(256) k_icp_count(const float *__restrict__ v, int n, const IcpGrid *__restrict__ grid,
+	unsigned *cell_count, unsigned *__restrict__ cell_of, unsigned *__restrict__ rank_of)
+{
+	const IcpGrid g = *grid;
+	const int lane = threadIdx.x & 31;
+	for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
+		const int i = i0 + lane;
+		const bool active = i < n;
+		unsigned m = 0xffffffffu - (unsigned)lane;      // unique tags for idle lanes
+		if (active) {
+			const float x = v[3 * (size_t)i], y = v[3 * (size_t)i + 1], z = v[3 * (size_t)i + 2];
+			m = morton3(icp_cell(x - g.ox, g.inv_h, g.G), icp_cell(y - g.oy, g.inv_h, g.G), icp_cell(z - g.oz, g.inv_h, g.G));
+		}
+		const unsigned grp = __match_any_sync(kFull, m);
+		const int leader = __ffs(grp) - 1;
+		unsigned base = 0;
+		if (active && lane == leader) base = atomicAdd(&cell_count[m], (unsigned)__popc(grp));
+		base = __shfl_sync(kFull, base, leader);
+		if (active) { cell_of[i] = m; rank_of[i] = base + __popc(grp & ((1u << lane) - 1u)); }
+	}
+}
+
+// in-place exclusive scan of n unsigned values (single pass, decoupled look-back)
+__global__ void __launch_bounds__(kScanThreads) k_exclusive_scan(unsigned *data, int n, unsigned *tile_counter, unsigned long long *status, int *err) {
+	__shared__ unsigned sm[16];
+	__shared__ int s_tile;
+	const int ntiles = (n + kTile - 1) / kTile;
+	const int tid = threadIdx.x;
+	for (;;) {
+		if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
+		__syncthreads();
+		const int tile = s_tile;
+		if (tile >= ntiles) break;
+		const int i0 = tile * kTile + tid * 8;
+		unsigned v[8];
+		if (i0 + 8 <= n) {
+			const uint4 a = *reinterpret_cast<const uint4 *>(data + i0), b = *reinterpret_cast<const uint4 *>(data + i0 + 4);
+			v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+		} else {
+#pragma unroll
+			for (int j = 0; j < 8; j++) v[j] = (i0 + j < n) ? data[i0 + j] : 0u;
+		}
+		unsigned cnt = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) cnt += v[j];
+		unsigned total, base;
+		const unsigned off = tile_scan(cnt, sm, status, tile, err, &total, &base);
+		unsigned run = base + off;
+#pragma unroll
+		for (int j = 0; j < 8; j++) { const unsigned x = v[j]; v[j] = run; run += x; }
+		if (i0 + 8 <= n) {
+			*reinterpret_cast<uint4 *>(data + i0) = make_uint4(v[0], v[1], v[2], v[3]);
+			*reinterpret_cast<uint4 *>(data + i0 + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+		} else {
+#pragma unroll
+			for (int j = 0; j < 8; j++) if (i0 + j < n) data[i0 + j] = v[j];
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(256) k_icp_scatter(const float *__restrict__ v, int n, const unsigned *__restrict__ cell_of,
+	const unsigned *__restrict__ rank_of, const unsigned *__restrict__ cell_start, float4 *__restrict__ sorted)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const unsigned pos = cell_start[cell_of[i]] + rank_of[i];
+		sorted[pos] = make_float4(v[3 * (size_t)i], v[3 * (size_t)i + 1], v[3 * (size_t)i + 2], __int_as_float(i));
+	}
+}
+
+__global__ void __launch_bounds__(256) k_fill_u64(unsigned long long *p, int n, unsigned long long v) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 3x3 helpers (OpenCV 3.2 CV_32F semantics as the oracle restates them, oracle/ls3d_oracle.cpp svd3/mul33)
+// ------------------------------------------------------------------------------------------------------
+__device__ void mul33(const float *A, const float *B, float *D) {      // fp32, left to right, no FMA
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++)
+			D[i * 3 + j] = __fadd_rn(__fadd_rn(__fmul_rn(A[i * 3 + 0], B[0 * 3 + j]), __fmul_rn(A[i * 3 + 1], B[1 * 3 + j])), __fmul_rn(A[i * 3 + 2], B[2 * 3 + j]));
+}
+
+__device__ float det33(const float *m) {
+	const float a = __fsub_rn(__fmul_rn(m[4], m[8]), __fmul_rn(m[5], m[7]));
+	const float b = __fsub_rn(__fmul_rn(m[3], m[8]), __fmul_rn(m[5], m[6]));
+	const float c = __fsub_rn(__fmul_rn(m[3], m[7]), __fmul_rn(m[4], m[6]));
+	return __fadd_rn(__fsub_rn(__fmul_rn(m[0], a), __fmul_rn(m[1], b)), __fmul_rn(m[2], c));
+}
+
+// One-sided (Hestenes) Jacobi SVD of a 3x3: fp32 storage, fp64 dot products, singular values descending.
+// M = U diag(w) Vt.
+__device__ void svd33(const float *M, float *U, float *Vt) {
+	float A[3][3], V[3][3];
+	double W[3];
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) { A[i][j] = M[j * 3 + i]; V[i][j] = (i == j) ? 1.0f : 0.0f; }     // rows of A = columns of M
+	for (int i = 0; i < 3; i++) { double s = 0; for (int k = 0; k < 3; k++) s += (double)A[i][k] * (double)A[i][k]; W[i] = s; }
+	const double eps = 2.0 * 1.1920929e-07;
+	for (int sweep = 0; sweep < 30; sweep++) {
+		bool changed = false;
+		for (int i = 0; i < 2; i++)
+			for (int j = i + 1; j < 3; j++) {
+				double a = W[i], b = W[j], p = 0;
+				for (int k = 0; k < 3; k++) p += (double)A[i][k] * (double)A[j][k];
+				if (fabs(p) <= eps * sqrt(a * b)) continue;
+				p *= 2;
+				const double beta = a - b, gamma = hypot(p, beta);
+				float c, s;
+				if (beta < 0) { const double delta = (gamma - beta) * 0.5; s = (float)sqrt(delta / gamma); c = (float)(p / (gamma * s * 2)); }
+				else { c = (float)sqrt((gamma + beta) / (gamma * 2)); s = (float)(p / (gamma * c * 2)); }
+				a = b = 0;
+				for (int k = 0; k < 3; k++) {
+					const float t0 = __fadd_rn(__fmul_rn(c, A[i][k]), __fmul_rn(s, A[j][k]));
+					const float t1 = __fadd_rn(__fmul_rn(-s, A[i][k]), __fmul_rn(c, A[j][k]));
+					A[i][k] = t0; A[j][k] = t1;
+					a += (double)t0 * (double)t0; b += (double)t1 * (double)t1;
+				}
+				W[i] = a; W[j] = b;
+				changed = true;
+				for (int k = 0; k < 3; k++) {
+					const float t0 = __fadd_rn(__fmul_rn(c, V[i][k]), __fmul_rn(s, V[j][k]));
+					const float t1 = __fadd_rn(__fmul_rn(-s, V[i][k]), __fmul_rn(c, V[j][k]));
+					V[i][k] = t0; V[j][k] = t1;
+				}
+			}
+		if (!changed) break;
+	}
+	for (int i = 0; i < 3; i++) { double s = 0; for (int k = 0; k < 3; k++) s += (double)A[i][k] * (double)A[i][k]; W[i] = sqrt(s); }
+	for (int i = 0; i < 2; i++) {
+		int j = i;
+		for (int k = i + 1; k < 3; k++) if (W[j] < W[k]) j = k;
+		if (i != j) {
+			const double tw = W[i]; W[i] = W[j]; W[j] = tw;
+			for (int k = 0; k < 3; k++) { float t = A[i][k]; A[i][k] = A[j][k]; A[j][k] = t; t = V[i][k]; V[i][k] = V[j][k]; V[j][k] = t; }
+		}
+	}
+	for (int i = 0; i < 3; i++) {
+		const float inv = W[i] > 0 ? (float)(1.0 / W[i]) : 0.0f;
+		for (int k = 0; k < 3; k++) { U[k * 3 + i] = __fmul_rn(A[i][k], inv); Vt[i * 3 + k] = V[i][k]; }
+	}
+}
+
+// (T, Rk) of the iteration whose 16 correspondence sums are in `sums`; executed by one thread per block
+// (every block derives the same values from the same inputs).  Returns false when there were no matches.
+__device__ bool icp_solve(const double *sums, float *T, float *Rk) {
+	const double m = sums[0];
+	if (!(m >= 0.5)) {
+		T[0] = T[1] = T[2] = 0.0f;
+		for (int i = 0; i < 9; i++) Rk[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+		return false;
+	}
+	const float scale = (float)(1.0 / m);                       // cv::reduce AVG: column sum * (1/rows)
+	for (int a = 0; a < 3; a++) T[a] = __fmul_rn((float)sums[1 + a], scale);
+	float M[9];
+	for (int a = 0; a < 3; a++)
+		for (int b = 0; b < 3; b++) M[a * 3 + b] = (float)(sums[7 + 3 * a + b] + (double)T[a] * sums[4 + b]);   // sum (q+T)_a p_b
+	float U[9], Vt[9];
+	svd33(M, U, Vt);
+	mul33(U, Vt, Rk);
+	if ((double)det33(Rk) < 0) {                                 // icp.cpp:156-163
+		const float D[9] = {1, 0, 0, 0, 1, 0, 0, 0, -1};
+		float UD[9];
+		mul33(U, D, UD);
+		mul33(UD, Vt, Rk);
+	}
+	return true;
+}
+
+// pose accumulation of icp.cpp:167-168, by exactly one thread per iteration
+__device__ void icp_accumulate(IcpState *st, const float *T, const float *Rk, bool solved, Ls3dIcpTrace *trace, int trace_idx, const double *sums) {
+	for (int j = 0; j < 3; j++) {
+		double s = 0;
+		for (int k = 0; k < 3; k++) s += (double)T[k] * (double)st->R[j * 3 + k];     // tempT * matR^T: general gemm path, fp64 accumulate
+		st->t[j] = __fadd_rn(st->t[j], (float)s);
+	}
+	float nr[9];
+	mul33(st->R, Rk, nr);
+	for (int i = 0; i < 9; i++) st->R[i] = nr[i];
+	st->iters_applied += 1;
+	if (!solved) st->err |= kErrNoMatches;
+	if (trace && trace_idx >= 0 && trace_idx < kTraceCap) {
+		trace[trace_idx].n_accepted = (int)(sums[0] + 0.5);
+		for (int a = 0; a < 3; a++) trace[trace_idx].T[a] = T[a];
+		for (int a = 0; a < 9; a++) trace[trace_idx].Rk[a] = Rk[a];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// nearest neighbour
+// ------------------------------------------------------------------------------------------------------
+struct Best { float d2; int idx; };
+
+__device__ __forceinline__ void scan_cell(const float4 *__restrict__ sorted, unsigned s, unsigned e, float qx, float qy, float qz, Best &b) {
+	for (unsigned p = s; p < e; p++) {
+		const float4 c = __ldg(sorted + p);
+		const float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
+		const int idx = __float_as_int(c.w);
+		if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; }
+	}
+}
+
+// conservative squared distance from the (origin-relative) query to the axis-aligned box [lo, lo+size]^3
+__device__ __forceinline__ float box_lb2(float rx, float ry, float rz, float lx, float ly, float lz, float size, float slack) {
+	const float dx = fmaxf(fmaxf(lx - rx, rx - (lx + size)) - slack, 0.0f);
+	const float dy = fmaxf(fmaxf(ly - ry, ry - (ly + size)) - slack, 0.0f);
+	const float dz = fmaxf(fmaxf(lz - rz, rz - (lz + size)) - slack, 0.0f);
+	return (dx * dx + dy * dy + dz * dz) * 0.99999f;
+}
+
+__device__ Best nearest_in_grid(const IcpGrid &g, const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted, float qx, float qy, float qz) {
+	Best best;
+	best.d2 = INFINITY;
+	best.idx = -1;
+	const float rx = qx - g.ox, ry = qy - g.oy, rz = qz - g.oz;
+	if (!(isfinite(rx) && isfinite(ry) && isfinite(rz))) return best;
+	const float h = g.h, slack = 1e-3f * g.h;
+	const int G = g.G;
+	const int cx = icp_cell(rx, g.inv_h, G), cy = icp_cell(ry, g.inv_h, G), cz = icp_cell(rz, g.inv_h, G);
+	{
+		const unsigned m = morton3(cx, cy, cz);
+		scan_cell(sorted, cell_start[m], cell_start[m + 1], qx, qy, qz, best);
+	}
+	for (int dz = -1; dz <= 1; dz++)
+		for (int dy = -1; dy <= 1; dy++)
+			for (int dx = -1; dx <= 1; dx++) {
+				if ((dx | dy | dz) == 0) continue;
+				const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+				if (nx < 0 || ny < 0 || nz < 0 || nx >= G || ny >= G || nz >= G) continue;
+				if (box_lb2(rx, ry, rz, nx * h, ny * h, nz * h, h, slack) > best.d2) continue;
+				const unsigned m = morton3(nx, ny, nz);
+				const unsigned s = cell_start[m], e = cell_start[m + 1];
+				if (s != e) scan_cell(sorted, s, e, qx, qy, qz, best);
+			}
+	// is everything outside the 3x3x3 block provably no closer?
+	float rho = INFINITY;
+	if (cx - 1 > 0) rho = fminf(rho, rx - (cx - 1) * h);
+	if (cx + 2 < G) rho = fminf(rho, (cx + 2) * h - rx);
+	if (cy - 1 > 0) rho = fminf(rho, ry - (cy - 1) * h);
+	if (cy + 2 < G) rho = fminf(rho, (cy + 2) * h - ry);
+	if (cz - 1 > 0) rho = fminf(rho, rz - (cz - 1) * h);
+	if (cz + 2 < G) rho = fminf(rho, (cz + 2) * h - rz);
+	rho = fmaxf(rho - slack, 0.0f);
+	if (best.d2 <= rho * rho * 0.99999f) return best;
+
+	// near-first depth-first walk of the implicit octree (Morton order => a node is a contiguous cell range)
+	const int L = g.levels;
+	int level = L;                       // current node is at `level` (cell edge h * 2^level), coordinates n*, Morton prefix mp
+	unsigned nx = 0, ny = 0, nz = 0, mp = 0, ranks = 0;
+	for (;;) {
+		const int sh = 4 * (level - 1);
+		const unsigned r = (ranks >> sh) & 15u;
+		if (r == 8) {
+			if (level == L) break;
+			ranks &= ~(15u << sh);
+			level++;
+			nx >>= 1; ny >>= 1; nz >>= 1; mp >>= 3;
+			continue;
+		}
+		ranks += 1u << sh;
+		const float half = h * (float)(1u << (level - 1));
+		const unsigned near = (rx >= (float)(2 * nx + 1) * half ? 1u : 0u) | (ry >= (float)(2 * ny + 1) * half ? 2u : 0u) | (rz >= (float)(2 * nz + 1) * half ? 4u : 0u);
+		const unsigned child = near ^ ((0x76534210u >> (4 * r)) & 7u);
+		const unsigned ccx = (nx << 1) | (child & 1u), ccy = (ny << 1) | ((child >> 1) & 1u), ccz = (nz << 1) | (child >> 2);
+		const unsigned cmp = (mp << 3) | child;
+		const int csh = 3 * (level - 1);
+		const unsigned s = cell_start[cmp << csh], e = cell_start[(cmp + 1u) << csh];
+		if (s == e) continue;
+		if (box_lb2(rx, ry, rz, ccx * half, ccy * half, ccz * half, half, slack) > best.d2) continue;
+		if (level == 1) scan_cell(sorted, s, e, qx, qy, qz, best);
+		else { level--; nx = ccx; ny = ccy; nz = ccz; mp = cmp; }
+	}
+	return best;
+}
+
+// apply (T, Rk) the way icp.cpp:143-165 does: fp32 add, then row-vector times matrix, left to right
+__device__ __forceinline__ void apply_xform(float &x, float &y, float &z, const float *T, const float *Rk) {
+	const float a0 = __fadd_rn(x, T[0]), a1 = __fadd_rn(y, T[1]), a2 = __fadd_rn(z, T[2]);
+	x = __fadd_rn(__fadd_rn(__fmul_rn(a0, Rk[0]), __fmul_rn(a1, Rk[3])), __fmul_rn(a2, Rk[6]));
+	y = __fadd_rn(__fadd_rn(__fmul_rn(a0, Rk[1]), __fmul_rn(a1, Rk[4])), __fmul_rn(a2, Rk[7]));
+	z = __fadd_rn(__fadd_rn(__fmul_rn(a0, Rk[2]), __fmul_rn(a1, Rk[5])), __fmul_rn(a2, Rk[8]));
+}
+
+// apply != 0: first apply the previous iteration's update (from sums_buf) to every source point.
+// search != 0: NN + dedupe for the slice [i_begin, i_end).
+__global__ void __launch_bounds__(256) k_icp_match(float *__restrict__ verts2, int n2, int i_begin, int i_end, int apply, int search,
+	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted,
+	unsigned long long *slots, IcpState *state, const double *__restrict__ sums_buf, Ls3dIcpTrace *trace, int trace_idx,
+	int *__restrict__ nn_idx, float *__restrict__ nn_d2)
+{
+	__shared__ float sT[3], sR[9];
+	if (apply) {
+		if (threadIdx.x == 0) {
+			float T[3], Rk[9];
+			const bool solved = icp_solve(sums_buf, T, Rk);
+			for (int a = 0; a < 3; a++) sT[a] = T[a];
+			for (int a = 0; a < 9; a++) sR[a] = Rk[a];
+			if (blockIdx.x == 0) icp_accumulate(state, T, Rk, solved, trace, trace_idx, sums_buf);
+		}
+		__syncthreads();
+	}
+	const IcpGrid g = *grid;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+		float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
+		if (apply) {
+			apply_xform(x, y, z, sT, sR);
+			verts2[3 * (size_t)i] = x; verts2[3 * (size_t)i + 1] = y; verts2[3 * (size_t)i + 2] = z;
+		}
+		if (search) {
+			int bi = -1;
+			float bd = 0.0f;
+			if (i >= i_begin && i < i_end) {
+				const Best b = nearest_in_grid(g, cell_start, sorted, x, y, z);
+				bi = b.idx; bd = b.d2;
+				if (bi >= 0) {
+					const unsigned long long key = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+					atomicMin(&slots[bi], key);
+				}
+			}
+			nn_idx[i] = bi;
+			nn_d2[i] = bd;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double *v, double *smem /* [8][NV] */, double *partials) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int a = 0; a < NV; a++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v[a] += __shfl_xor_sync(kFull, v[a], o);
+	}
+	if (lane == 0) {
+#pragma unroll
+		for (int a = 0; a < NV; a++) smem[warp * NV + a] = v[a];
+	}
+	__syncthreads();
+	if (threadIdx.x < NV) {
+		double s = 0;
+		for (int w = 0; w < 8; w++) s += smem[w * NV + threadIdx.x];
+		partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+	}
+}
+
+// last block to arrive sums the per-block partials in a fixed order -> out[0..NV)
+template <int NV>
+__device__ __forceinline__ void last_block_finish(const double *partials, double *out, unsigned *ticket) {
+	__shared__ bool s_last;
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	if (threadIdx.x < NV) {
+		double s = 0;
+		for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(partials + (size_t)b * NV + threadIdx.x);
+		out[threadIdx.x] = s;
+	}
+	if (threadIdx.x == 0) *ticket = 0;
+}
+
+// count, sum d2, sum d2^2 over the matched slots of [j_begin, j_end)
+__global__ void __launch_bounds__(256) k_icp_stats(const unsigned long long *__restrict__ slots, int j_begin, int j_end,
+	double *partials, double *stats_buf, IcpState *state)
+{
+	__shared__ double smem[8 * 3];
+	double v[3] = {0, 0, 0};
+	for (int j = j_begin + blockIdx.x * blockDim.x + threadIdx.x; j < j_end; j += gridDim.x * blockDim.x) {
+		const unsigned long long key = slots[j];
+		if (key != kSlotEmpty) {
+			const double d = (double)__uint_as_float((unsigned)(key >> 32));
+			v[0] += 1.0; v[1] += d; v[2] += d * d;
+		}
+	}
+	block_reduce_store<3>(v, smem, partials);
+	last_block_finish<3>(partials, stats_buf, &state->ticket_stats);
+}
+
+// 2.5 sigma gate (icp.cpp:34-73) + the 16 correspondence sums over [j_begin, j_end); every slot is reset.
+//   sums: [0] accepted count, [1..3] sum (p - q) (fp32 differences), [4..6] sum p, [7..15] sum q_a p_b
+__global__ void __launch_bounds__(256) k_icp_sums(unsigned long long *__restrict__ slots, int n1, int j_begin, int j_end,
+	const float *__restrict__ verts1, const float *__restrict__ verts2, const double *__restrict__ stats_buf,
+	double *partials, double *sums_buf, IcpState *state, Ls3dIcpTrace *trace, int trace_idx)
+{
+	__shared__ double smem[8 * 16];
+	__shared__ float s_thr;
+	if (threadIdx.x == 0) {
+		const double cnt = stats_buf[0];
+		float sigma = 0.0f;
+		if (cnt >= 0.5) {
+			const double mean = stats_buf[1] / cnt;
+			double var = stats_buf[2] / cnt - mean * mean;
+			if (!(var > 0)) var = 0;
+			sigma = (float)sqrt(var);
+		}
+		s_thr = __fmul_rn(2.5f, sigma);
+		if (blockIdx.x == 0 && trace && trace_idx >= 0 && trace_idx < kTraceCap) {
+			trace[trace_idx].n_matched = (int)(cnt + 0.5);
+			trace[trace_idx].sigma = sigma;
+		}
+	}
+	__syncthreads();
+	const float thr = s_thr;
+	double v[16];
+#pragma unroll
+	for (int a = 0; a < 16; a++) v[a] = 0;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
+		const unsigned long long key = slots[j];
+		if (key == kSlotEmpty) continue;
+		slots[j] = kSlotEmpty;
+		if (j < j_begin || j >= j_end) continue;
+		const float d2 = __uint_as_float((unsigned)(key >> 32));
+		if (d2 > thr) continue;
+		const unsigned i = 0xFFFFFFFFu - (unsigned)key;
+		const float px = verts1[3 * (size_t)j], py = verts1[3 * (size_t)j + 1], pz = verts1[3 * (size_t)j + 2];
+		const float qx = verts2[3 * (size_t)i], qy = verts2[3 * (size_t)i + 1], qz = verts2[3 * (size_t)i + 2];
+		v[0] += 1.0;
+		v[1] += (double)__fsub_rn(px, qx); v[2] += (double)__fsub_rn(py, qy); v[3] += (double)__fsub_rn(pz, qz);
+		v[4] += (double)px; v[5] += (double)py; v[6] += (double)pz;
+		v[7] += (double)qx * (double)px; v[8] += (double)qx * (double)py; v[9] += (double)qx * (double)pz;
+		v[10] += (double)qy * (double)px; v[11] += (double)qy * (double)py; v[12] += (double)qy * (double)pz;
+		v[13] += (double)qz * (double)px; v[14] += (double)qz * (double)py; v[15] += (double)qz * (double)pz;
+	}
+	block_reduce_store<16>(v, smem, partials);
+	last_block_finish<16>(partials, sums_buf, &state->ticket_sums);
+}
+
+struct Pose12 { float v[12]; };     // R[9] then t[3], passed by value (no staging buffer to race on)
+
+__global__ void k_icp_init_state(IcpState *st, Pose12 p) {
+	for (int i = 0; i < 9; i++) st->R[i] = p.v[i];
+	for (int i = 0; i < 3; i++) st->t[i] = p.v[9 + i];
+	st->iters_applied = 0;
+	st->err = 0;
+	st->ticket_stats = 0;
+	st->ticket_sums = 0;
+}
+
+}  // namespace ls3d
+
+using namespace ls3d;
+
+// ======================================================================================================
+// ICP context
+// ======================================================================================================
+struct Ls3dIcp {
+	int n1_max = 0, n2_max = 0;
+	int n1 = 0, n2 = 0, i_begin = 0, i_end = 0;
+	int G = 0, levels = 0;
+	int iter = 0;                 // iterations whose match stage has been enqueued
+	bool pending = false;         // sums of the last iteration not yet applied
+	int sm_count = 148;
+	const float *d_verts1 = nullptr;
+	float *d_verts2 = nullptr;
+	DevBuf grid, box, state, cell_start, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, trace, small;
+	DevBuf own_v1, own_v2;        // device copies for the host-buffer API
+	float *pin = nullptr;         // pinned read-back: Rt[12] + status[4]
+	cudaGraphExec_t graph = nullptr;
+	int graph_iters = 0, graph_n1 = 0, graph_n2 = 0, graph_ib = 0, graph_ie = 0;
+	const void *graph_v1 = nullptr, *graph_v2 = nullptr;
+};
+
+static void icp_free(Ls3dIcp *c) {
+	if (!c) return;
+	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
+		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->trace, &c->small, &c->own_v1, &c->own_v2};
+	for (DevBuf *b : bufs) b->release();
+	if (c->pin) cudaFreeHost(c->pin);
+	if (c->graph) cudaGraphExecDestroy(c->graph);
+	delete c;
+}
+
+extern "C" Ls3dIcp *ls3d_icp_create(int n1_max, int n2_max) {
+	clear_error();
+	if (!ensure_device()) return nullptr;
+	if (n1_max <= 0 || n2_max < 0) { set_error("ls3d_icp_create: sizes must be positive"); return nullptr; }
+	Ls3dIcp *c = new Ls3dIcp();
+	int dev = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
+	c->n1_max = n1_max;
+	c->n2_max = n2_max;
+	const size_t n1 = (size_t)n1_max, n2 = (size_t)std::max(n2_max, 1);
+	bool ok = c->grid.reserve(sizeof(IcpGrid), "alloc grid") && c->box.reserve(sizeof(IcpBox), "alloc bbox") && c->state.reserve(sizeof(IcpState), "alloc state") &&
+		c->cell_of.reserve(4 * n1, "alloc cells") && c->rank_of.reserve(4 * n1, "alloc ranks") && c->sorted.reserve(16 * n1, "alloc sorted target") &&
+		c->slots.reserve(8 * n1, "alloc slots") && c->partials.reserve(sizeof(double) * 16 * kRedBlocks, "alloc partials") &&
+		c->stats_buf.reserve(sizeof(double) * 4, "alloc stats") && c->sums_buf.reserve(sizeof(double) * 16, "alloc sums") &&
+		c->nn_idx.reserve(4 * n2, "alloc nn index") && c->nn_d2.reserve(4 * n2, "alloc nn dist") &&
+		c->trace.reserve(sizeof(Ls3dIcpTrace) * kTraceCap, "alloc trace") && c->small.reserve(256, "alloc small");
+	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin, 256, cudaHostAllocDefault), "alloc pinned read-back");
+	if (!ok) { icp_free(c); return nullptr; }
+	cudaMemset(c->stats_buf.p, 0, sizeof(double) * 4);
+	cudaMemset(c->sums_buf.p, 0, sizeof(double) * 16);
+	cudaMemset(c->trace.p, 0, sizeof(Ls3dIcpTrace) * kTraceCap);
+	cudaMemset(c->state.p, 0, sizeof(IcpState));
+	return c;
+}
+
+extern "C" void ls3d_icp_destroy(Ls3dIcp *c) { icp_free(c); }
+
+static int pt_blocks(const Ls3dIcp *c, int n) { return std::max(1, std::min((n + 255) / 256, c->sm_count * 8)); }
+
+extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, void *stream) {
+	if (!c || !d_verts1) { set_error("ls3d_icp_set_target: null argument"); return -1; }
+	if (n1 <= 0 || n1 > c->n1_max) { set_error("ls3d_icp_set_target: n1=%d outside 1..%d (the reference throws on an empty target, nanoflann.h:904)", n1, c->n1_max); return -1; }
+	cudaStream_t st = (cudaStream_t)stream;
+	c->d_verts1 = (const float *)d_verts1;
+	c->n1 = n1;
+	c->levels = n1 <= 32768 ? 6 : (n1 <= 1000000 ? 7 : 8);
+	c->G = 1 << c->levels;
+	const size_t cells = (size_t)c->G * c->G * c->G;
+	const int scan_n = (int)cells + 1;
+	const int scan_tiles = (scan_n + kTile - 1) / kTile;
+	if (!c->cell_start.reserve(4 * (cells + 8), "alloc cell starts") || !c->scan_status.reserve(8 * (size_t)(scan_tiles + 1), "alloc scan status")) return -1;
+	IcpBox hb;
+	for (int a = 0; a < 3; a++) { hb.mn[a] = 0xffffffffu; hb.mx[a] = 0u; }
+	bool ok = cuda_ok(cudaMemcpyAsync(c->box.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, st), "init bbox") &&
+		cuda_ok(cudaMemsetAsync(c->cell_start.p, 0, 4 * (cells + 8), st), "clear cells") &&
+		cuda_ok(cudaMemsetAsync(c->scan_status.p, 0, 8 * (size_t)(scan_tiles + 1), st), "clear scan status") &&
+		cuda_ok(cudaMemsetAsync(c->small.p, 0, 256, st), "clear counters");
+	if (!ok) return -1;
+	unsigned *scan_counter = c->small.as<unsigned>();
+	int *scan_err = c->small.as<int>() + 1;
+	const int nb = pt_blocks(c, n1);
+	k_icp_bbox<<<nb, 256, 0, st>>>(c->d_verts1, n1, c->box.as<IcpBox>());
+	k_icp_grid_params<<<1, 1, 0, st>>>(c->box.as<IcpBox>(), c->grid.as<IcpGrid>(), c->G, c->levels);
+	k_icp_count<<<nb, 256, 0, st>>>(c->d_verts1, n1, c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->cell_of.as<unsigned>(), c->rank_of.as<unsigned>());
+	k_exclusive_scan<<<std::min(scan_tiles, c->sm_count * 8), kScanThreads, 0, st>>>(c->cell_start.as<unsigned>(), scan_n, scan_counter, c->scan_status.as<unsigned long long>(), scan_err);
+	k_icp_scatter<<<nb, 256, 0, st>>>(c->d_verts1, n1, c->cell_of.as<unsigned>(), c->rank_of.as<unsigned>(), c->cell_start.as<unsigned>(), c->sorted.as<float4>());
+	k_fill_u64<<<nb, 256, 0, st>>>(c->slots.as<unsigned long long>(), n1, kSlotEmpty);
+	count_launch(6);
+	return cuda_ok(cudaGetLastError(), "target grid kernels") ? 0 : -1;
+}
+
+extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_begin, int i_end, const float *R0, const float *t0, void *stream) {
+	if (!c || (!d_verts2 && n2 > 0) || !R0 || !t0) { set_error("ls3d_icp_set_source: null argument"); return -1; }
+	if (n2 < 0 || n2 > c->n2_max || i_begin < 0 || i_end > n2 || i_begin > i_end) { set_error("ls3d_icp_set_source: bad sizes n2=%d slice [%d,%d) capacity %d", n2, i_begin, i_end, c->n2_max); return -1; }
+	cudaStream_t st = (cudaStream_t)stream;
+	c->d_verts2 = (float *)d_verts2;
+	c->n2 = n2;
+	c->i_begin = i_begin;
+	c->i_end = i_end;
+	c->iter = 0;
+	c->pending = false;
+	Pose12 pose;
+	memcpy(pose.v, R0, 9 * sizeof(float));
+	memcpy(pose.v + 9, t0, 3 * sizeof(float));
+	k_icp_init_state<<<1, 1, 0, st>>>(c->state.as<IcpState>(), pose);
+	count_launch(1);
+	return cuda_ok(cudaGetLastError(), "k_icp_init_state") ? 0 : -1;
+}
+
+static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) {
+	const int trace_idx = c->iter - 1;     // the update being applied belongs to the previous iteration
+	k_icp_match<<<pt_blocks(c, std::max(c->n2, 1)), 256, 0, st>>>(c->d_verts2, c->n2, c->i_begin, c->i_end, apply, search,
+		c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->sorted.as<float4>(), c->slots.as<unsigned long long>(), c->state.as<IcpState>(),
+		c->sums_buf.as<double>(), c->trace.as<Ls3dIcpTrace>(), trace_idx, c->nn_idx.as<int>(), c->nn_d2.as<float>());
+	count_launch(1);
+	return cuda_ok(cudaGetLastError(), "k_icp_match") ? 0 : -1;
+}
+
+extern "C" int ls3d_icp_match(Ls3dIcp *c, void *stream) {
+	if (!c || !c->d_verts1 || !c->d_verts2) { set_error("ls3d_icp_match: target/source not set"); return -1; }
+	const int r = icp_launch_match(c, c->pending ? 1 : 0, 1, (cudaStream_t)stream);
+	c->pending = false;
+	c->iter++;
+	return r;
+}
+
+extern "C" int ls3d_icp_stats(Ls3dIcp *c, int j_begin, int j_end, void *stream) {
+	if (!c || !c->d_verts1) { set_error("ls3d_icp_stats: target not set"); return -1; }
+	if (j_begin < 0) j_begin = 0;
+	if (j_end > c->n1 || j_end < 0) j_end = c->n1;
+	k_icp_stats<<<std::min(kRedBlocks, std::max(1, (c->n1 + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(c->slots.as<unsigned long long>(), j_begin, j_end,
+		c->partials.as<double>(), c->stats_buf.as<double>(), c->state.as<IcpState>());
+	count_launch(1);
+	return cuda_ok(cudaGetLastError(), "k_icp_stats") ? 0 : -1;
+}
+
+extern "C" int ls3d_icp_sums(Ls3dIcp *c, int j_begin, int j_end, void *stream) {
+	if (!c || !c->d_verts1 || !c->d_verts2) { set_error("ls3d_icp_sums: target/source not set"); return -1; }
+	if (j_begin < 0) j_begin = 0;
+	if (j_end > c->n1 || j_end < 0) j_end = c->n1;
+	k_icp_sums<<<std::min(kRedBlocks, std::max(1, (c->n1 + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(c->slots.as<unsigned long long>(), c->n1, j_begin, j_end,
+		c->d_verts1, c->d_verts2, c->stats_buf.as<double>(), c->partials.as<double>(), c->sums_buf.as<double>(), c->state.as<IcpState>(),
+		c->trace.as<Ls3dIcpTrace>(), c->iter - 1);
+	count_launch(1);
+	c->pending = true;
+	return cuda_ok(cudaGetLastError(), "k_icp_sums") ? 0 : -1;
+}
+
+extern "C" int ls3d_icp_finish(Ls3dIcp *c, void *stream) {
+	if (!c) { set_error("ls3d_icp_finish: null context"); return -1; }
+	if (!c->pending) return 0;
+	const int r = icp_launch_match(c, 1, 0, (cudaStream_t)stream);
+	c->pending = false;
+	return r;
+}
+
+static int icp_enqueue_all(Ls3dIcp *c, int maxIter, cudaStream_t st) {
+	for (int it = 0; it < maxIter; it++) {
+		if (ls3d_icp_match(c, st) < 0 || ls3d_icp_stats(c, 0, c->n1, st) < 0 || ls3d_icp_sums(c, 0, c->n1, st) < 0) return -1;
+	}
+	return ls3d_icp_finish(c, st);
+}
+
+extern "C" int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream) {
+	if (!c || !c->d_verts1 || !c->d_verts2) { set_error("ls3d_icp_run: target/source not set"); return -1; }
+	if (maxIter <= 0) return 0;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (c->iter != 0 || c->pending) { set_error("ls3d_icp_run: call ls3d_icp_set_source first"); return -1; }
+	// One CUDA graph per (shape, buffers, iteration count): 3*maxIter+1 kernel nodes replayed with one launch.
+	const bool reuse = c->graph && c->graph_iters == maxIter && c->graph_n1 == c->n1 && c->graph_n2 == c->n2 && c->graph_v1 == c->d_verts1 && c->graph_v2 == c->d_verts2 &&
+		c->graph_ib == c->i_begin && c->graph_ie == c->i_end;
+	if (!reuse) {
+		if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+		cudaGraph_t graph = nullptr;
+		if (cuda_ok(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "begin graph capture")) {
+			const long long before = g_launches.load();
+			const int r = icp_enqueue_all(c, maxIter, st);
+			const cudaError_t e = cudaStreamEndCapture(st, &graph);
+			g_launches.store(before);
+			if (r == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&c->graph, graph, 0) == cudaSuccess) {
+				c->graph_iters = maxIter; c->graph_n1 = c->n1; c->graph_n2 = c->n2; c->graph_v1 = c->d_verts1; c->graph_v2 = c->d_verts2;
+				c->graph_ib = c->i_begin; c->graph_ie = c->i_end;
+			} else {
+				c->graph = nullptr;
+				cudaGetLastError();
+			}
+			if (graph) cudaGraphDestroy(graph);
+		} else {
+			cudaGetLastError();
+		}
+		c->iter = 0;
+		c->pending = false;
+	}
+	if (c->graph) {
+		if (!cuda_ok(cudaGraphLaunch(c->graph, st), "launch ICP graph")) return -1;
+		count_launch(3 * maxIter + 1);
+		c->iter = maxIter;
+		c->pending = false;
+		return 0;
+	}
+	return icp_enqueue_all(c, maxIter, st);     // capture unavailable: plain stream-ordered launches
+}
+
+extern "C" long long *ls3d_icp_slots(Ls3dIcp *c) { return c ? c->slots.as<long long>() : nullptr; }
+extern "C" double *ls3d_icp_stats_buf(Ls3dIcp *c) { return c ? c->stats_buf.as<double>() : nullptr; }
+extern "C" double *ls3d_icp_sums_buf(Ls3dIcp *c) { return c ? c->sums_buf.as<double>() : nullptr; }
+extern "C" float *ls3d_icp_Rt(Ls3dIcp *c) { return c ? c->state.as<float>() : nullptr; }
+extern "C" const int *ls3d_icp_nn_index(Ls3dIcp *c) { return c ? c->nn_idx.as<int>() : nullptr; }
+extern "C" const float *ls3d_icp_nn_dist(Ls3dIcp *c) { return c ? c->nn_d2.as<float>() : nullptr; }
+extern "C" Ls3dIcpTrace *ls3d_icp_trace_buf(Ls3dIcp *c) { return c ? c->trace.as<Ls3dIcpTrace>() : nullptr; }
+extern "C" const int *ls3d_icp_status(Ls3dIcp *c) { return c ? reinterpret_cast<const int *>(c->state.as<float>() + 12) : nullptr; }
+
+// ======================================================================================================
+// Host-buffer (drop-in) entry points
+// ======================================================================================================
+static Ls3dIcp *g_icp = nullptr;
+
+static Ls3dIcp *cached_icp(int n1, int n2) {
+	if (g_icp && g_icp->n1_max >= n1 && g_icp->n2_max >= n2) return g_icp;
+	int c1 = g_icp ? g_icp->n1_max : 0, c2 = g_icp ? g_icp->n2_max : 0;
+	if (g_icp) { icp_free(g_icp); g_icp = nullptr; }
+	c1 = std::max(c1, n1 + n1 / 8);
+	c2 = std::max(c2, n2 + n2 / 8);
+	g_icp = ls3d_icp_create(std::max(c1, 1), std::max(c2, 1));
+	return g_icp;
+}
+
+extern "C" float ls3d_icp_trace(Point3f *verts1, Point3f *verts2, int nVerts1, int nVerts2, float *R, float *t, int maxIter, Ls3dIcpTrace *trace) {
+	clear_error();
+	const float ret = 1.0f;                                      // icp.cpp:85,176: `error` is never updated
+	if (!verts1 || !verts2 || !R || !t) { set_error("ICP: null argument"); return ret; }
+	if (maxIter <= 0) return ret;                                // the loop body never runs; nothing changes
+	if (nVerts1 <= 0) { set_error("ICP: empty target cloud (the reference throws here, nanoflann.h:904)"); return ret; }
+	if (nVerts2 <= 0) { set_error("ICP: empty source cloud"); return ret; }
+	if (!ensure_device()) return ret;
+	std::lock_guard<std::mutex> lk(api_mutex());
+	cudaStream_t st = api_stream();
+	if (!st) return ret;
+	Ls3dIcp *c = cached_icp(nVerts1, nVerts2);
+	if (!c) return ret;
+	if (!c->own_v1.reserve(12 * (size_t)c->n1_max, "alloc target copy") || !c->own_v2.reserve(12 * (size_t)c->n2_max, "alloc source copy")) return ret;
+	bool ok = cuda_ok(cudaMemcpyAsync(c->own_v1.p, verts1, 12 * (size_t)nVerts1, cudaMemcpyHostToDevice, st), "upload target") &&
+		cuda_ok(cudaMemcpyAsync(c->own_v2.p, verts2, 12 * (size_t)nVerts2, cudaMemcpyHostToDevice, st), "upload source");
+	if (!ok) return ret;
+	if (ls3d_icp_set_target(c, c->own_v1.p, nVerts1, st) < 0) return ret;
+	if (ls3d_icp_set_source(c, c->own_v2.p, nVerts2, 0, nVerts2, R, t, st) < 0) return ret;
+	if (ls3d_icp_run(c, maxIter, st) < 0) return ret;
+	ok = cuda_ok(cudaMemcpyAsync(c->pin, c->state.p, sizeof(float) * 12 + sizeof(int) * 4, cudaMemcpyDeviceToHost, st), "read pose") &&
+		cuda_ok(cudaMemcpyAsync(verts2, c->own_v2.p, 12 * (size_t)nVerts2, cudaMemcpyDeviceToHost, st), "read source");
+	if (ok && trace) ok = cuda_ok(cudaMemcpyAsync(trace, c->trace.p, sizeof(Ls3dIcpTrace) * (size_t)std::min(maxIter, kTraceCap), cudaMemcpyDeviceToHost, st), "read trace");
+	ok = ok && cuda_ok(cudaStreamSynchronize(st), "ICP");
+	if (!ok) return ret;
+	memcpy(R, c->pin, 9 * sizeof(float));
+	memcpy(t, c->pin + 9, 3 * sizeof(float));
+	const int *status = reinterpret_cast<const int *>(c->pin + 12);
+	if (status[1]) set_error("ICP: device status flags 0x%x (%s)", status[1], (status[1] & kErrNoMatches) ? "an iteration had no accepted correspondences" : "internal");
+	return ret;
+}
+
+extern "C" float ICP(Point3f *verts1, Point3f *verts2, int nVerts1, int nVerts2, float *R, float *t, int maxIter) {
+	return ls3d_icp_trace(verts1, verts2, nVerts1, nVerts2, R, t, maxIter, nullptr);
+}
+
+extern "C" int ls3d_find_closest(const Point3f *verts1, int nVerts1, const Point3f *verts2, int nVerts2, unsigned long long *indices, float *distances) {
+	clear_error();
+	if (!verts1 || !verts2 || !indices || !distances || nVerts1 <= 0 || nVerts2 < 0) { set_error("ls3d_find_closest: bad arguments"); return -1; }
+	if (nVerts2 == 0) return 0;
+	if (!ensure_device()) return -1;
+	std::lock_guard<std::mutex> lk(api_mutex());
+	cudaStream_t st = api_stream();
+	if (!st) return -1;
+	Ls3dIcp *c = cached_icp(nVerts1, nVerts2);
+	if (!c) return -1;
+	if (!c->own_v1.reserve(12 * (size_t)c->n1_max, "alloc target copy") || !c->own_v2.reserve(12 * (size_t)c->n2_max, "alloc source copy")) return -1;
+	const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, z[3] = {0, 0, 0};
+	bool ok = cuda_ok(cudaMemcpyAsync(c->own_v1.p, verts1, 12 * (size_t)nVerts1, cudaMemcpyHostToDevice, st), "upload target") &&
+		cuda_ok(cudaMemcpyAsync(c->own_v2.p, verts2, 12 * (size_t)nVerts2, cudaMemcpyHostToDevice, st), "upload source");
+	if (!ok) return -1;
+	if (ls3d_icp_set_target(c, c->own_v1.p, nVerts1, st) < 0 || ls3d_icp_set_source(c, c->own_v2.p, nVerts2, 0, nVerts2, I, z, st) < 0) return -1;
+	if (ls3d_icp_match(c, st) < 0) return -1;
+	std::vector<int> idx(nVerts2);
+	ok = cuda_ok(cudaMemcpyAsync(idx.data(), c->nn_idx.p, 4 * (size_t)nVerts2, cudaMemcpyDeviceToHost, st), "read nn index") &&
+		cuda_ok(cudaMemcpyAsync(distances, c->nn_d2.p, 4 * (size_t)nVerts2, cudaMemcpyDeviceToHost, st), "read nn dist") &&
+		cuda_ok(cudaStreamSynchronize(st), "find closest");
+	if (!ok) return -1;
+	for (int i = 0; i < nVerts2; i++) indices[i] = (unsigned long long)(long long)idx[i];
+	return 0;
+}

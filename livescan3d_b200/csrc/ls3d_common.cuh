@@ -1,0 +1,150 @@
+// ls3d_common.cuh — shared device/host helpers for libls3d_b200.so (sm_100a only).
+//
+// Conventions used by every kernel in this library:
+//   * parity-critical fp32 arithmetic is written with __fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn so nvcc can never
+//     contract it into FMAs: the reference (g++ -O2 -ffp-contract=off) evaluates a*b + c*d with separate
+//     roundings, and cull / filter masks must be bit-exact (BASELINE.json north_star).
+//   * 16-byte VertexC4ubV3f records move as uint4 (one LDG.128 / STG.128 per record).
+//   * order-preserving compaction uses a single-pass decoupled look-back scan over 2048-element tiles
+//     (tile ids handed out by an atomic counter, so a tile's predecessors are always running or done).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace ls3d {
+
+constexpr int kTile = 2048;          // elements per compaction tile
+constexpr int kScanThreads = 256;    // threads per compaction block (8 elements per thread)
+constexpr unsigned kFull = 0xffffffffu;
+
+// error bits accumulated in device status words
+enum : int {
+	kErrScanSpin = 1,        // look-back spin limit hit (should never happen)
+	kErrCellOverflow = 2,    // more than 2^24-1 points in one voxel
+	kErrNoMatches = 4,       // an ICP iteration had zero accepted correspondences
+	kErrProbeLimit = 8,      // hash probe sequence exceeded the table (should never happen)
+};
+
+struct alignas(16) SensorDesc {
+	int w, h, px, tile_begin;           // tile_begin: first compaction tile of this sensor (entry n_maps is the sentinel)
+	long long depth_off, color_off;     // byte offsets into the packed depth / colour buffers
+	long long pix_begin;                // first global pixel index of this sensor
+	float cx, cy, fx, fy;               // IntrinsicCameraParameters (depthprocessing.h:90-98)
+	float t[3];                         // WorldTranformation.t (depthprocessing.h:50-63)
+	float R[9];                         // WorldTranformation.R, row-major
+	float gox, goy, goz, ginv_h;        // voxel-hash origin and 1/cell edge for the neighbour-count filter
+	unsigned tbl_off, tbl_mask;         // this sensor's region of the voxel hash table (power-of-two capacity)
+	int pad0, pad1;
+};
+
+// small device-resident control block, zeroed at the start of every run
+struct FrameCtl {
+	unsigned tile_counter_a;   // map/cull compaction
+	unsigned tile_counter_b;   // filter compaction
+	unsigned cursor;           // sorted-array range allocator
+	unsigned work_counter;     // neighbour-count work stealing
+	int n_final, n_culled, err, n_kept;   // n_kept: survivors counted by the neighbour-count kernel (known before compaction)
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned warp_sum(unsigned v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+	return v;
+}
+__device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		unsigned n = __shfl_up_sync(kFull, v, o);
+		if (lane >= o) v += n;
+	}
+	return v;
+}
+
+// Decoupled look-back (Merrill & Garland): called by ALL 32 lanes of warp 0 of the block that owns `tile`.
+// status[tile] = (flag << 32) | value with flag 0 = nothing yet, 1 = tile aggregate, 2 = inclusive prefix.
+// Returns the exclusive prefix of `tile`.  A bounded spin protects the GPU box from a hang if the protocol
+// were ever broken; it raises kErrScanSpin instead.
+__device__ __forceinline__ unsigned lookback_exclusive(unsigned long long *status, int tile, unsigned aggregate, int *err) {
+	const int lane = threadIdx.x & 31;
+	if (tile == 0) {
+		if (lane == 0) st_volatile_u64(status, (2ull << 32) | aggregate);
+		return 0u;
+	}
+	if (lane == 0) st_volatile_u64(status + tile, (1ull << 32) | aggregate);
+	unsigned excl = 0;
+	int idx = tile - 1;
+	for (;;) {
+		const int my = idx - lane;
+		unsigned long long w = 2ull << 32;       // lanes before tile 0 contribute a zero prefix
+		int spins = 0;
+		for (;;) {
+			if (my >= 0) w = ld_volatile_u64(status + my);
+			if (!__any_sync(kFull, (w >> 32) == 0)) break;
+			if (++spins > (1 << 22)) { if (lane == 0) atomicOr(err, kErrScanSpin); break; }
+		}
+		const unsigned flag = (unsigned)(w >> 32), val = (unsigned)w;
+		const unsigned pmask = __ballot_sync(kFull, flag == 2);
+		if (pmask) {
+			const int first = __ffs(pmask) - 1;
+			excl += warp_sum(lane <= first ? val : 0u);
+			break;
+		}
+		excl += warp_sum(val);
+		idx -= 32;
+	}
+	if (lane == 0) st_volatile_u64(status + tile, (2ull << 32) | (unsigned long long)(excl + aggregate));
+	return excl;
+}
+
+// Block-wide exclusive scan of one count per thread (kScanThreads threads) + look-back for the tile base.
+// Returns this thread's exclusive offset inside the tile; *tile_total and *tile_base are block-uniform.
+// smem: at least 16 unsigned.
+__device__ __forceinline__ unsigned tile_scan(unsigned cnt, unsigned *smem, unsigned long long *status, int tile, int *err,
+	unsigned *tile_total, unsigned *tile_base) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned incl = warp_incl_scan(cnt, lane);
+	if (lane == 31) smem[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		unsigned v = lane < (kScanThreads / 32) ? smem[lane] : 0u;
+		const unsigned s = warp_incl_scan(v, lane);
+		const unsigned total = __shfl_sync(kFull, s, kScanThreads / 32 - 1);
+		const unsigned base = lookback_exclusive(status, tile, total, err);
+		if (lane < (kScanThreads / 32)) smem[lane] = s - v;      // exclusive warp offsets
+		if (lane == 0) { smem[8] = total; smem[9] = base; }
+	}
+	__syncthreads();
+	*tile_total = smem[8];
+	*tile_base = smem[9];
+	return smem[warp] + incl - cnt;
+}
+
+// fp32 squared distance exactly as PointCloud::kdtree_distance evaluates it (icp.h:40-47, filter.h:38-45):
+// d0*d0 + d1*d1 + d2*d2, every product and sum rounded separately.
+__device__ __forceinline__ float dist2_ref(float qx, float qy, float qz, float px, float py, float pz) {
+	const float d0 = __fsub_rn(qx, px), d1 = __fsub_rn(qy, py), d2 = __fsub_rn(qz, pz);
+	return __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+}
+
+// order-preserving float <-> unsigned map for atomicMin/atomicMax on floats
+__device__ __forceinline__ unsigned f2ord(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __host__ __forceinline__ float ord2f(unsigned u) {
+	u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+	return __uint_as_float(u);
+#else
+	float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+}  // namespace ls3d

@@ -1,0 +1,42 @@
+// ls3d_internal.h — host-side internals shared by the translation units of libls3d_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstddef>
+#include <mutex>
+
+namespace ls3d {
+
+// thread-local error text behind ls3d_last_error()
+void set_error(const char *fmt, ...);
+void clear_error();
+// returns true when e == cudaSuccess, otherwise records "<what>: <cuda error string>"
+bool cuda_ok(cudaError_t e, const char *what);
+
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// One lock for the host-buffer (drop-in) entry points: LiveScanServer calls them from two worker threads
+// (MainWindowForm.cs:238,304) and they share cached device contexts.
+std::mutex &api_mutex();
+
+// Lazily created library stream (non-blocking) for the host-buffer entry points; nullptr on failure.
+cudaStream_t api_stream();
+// Makes sure a CUDA device is usable; false (with the error recorded) otherwise.  No CPU fallback exists.
+bool ensure_device();
+
+// Pinned host blocks handed out as Mesh::vertices so the device->host copy lands directly in the memory the
+// caller reads (no staging copy); recycled by deleteMesh.
+void *host_block_alloc(size_t bytes);
+void host_block_free(void *p);
+
+// device scratch with grow-only semantics
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	bool reserve(size_t bytes, const char *what);
+	void release();
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+}  // namespace ls3d

@@ -1,0 +1,319 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI of libls3d_b200.so, against the CPU oracle
+on the same seeded inputs and against the committed golden vectors.
+
+Bars (BASELINE.json north_star): vertex bytes, cull/filter masks, index maps and all counts BIT-EXACT; nearest
+neighbour indices identical except equidistant ties; final ICP R within 1e-5 per entry, t within 1e-4 m.
+Nothing here reads /root/reference (it does not exist on the GPU box)."""
+import os
+
+import numpy as np
+import pytest
+
+from common import GOLDEN, cloud_of, icp_pair, nn_parity, rot_err, small_frame, synth, orc, xyz_of
+
+pytestmark = pytest.mark.gpu
+
+R_TOL = 1e-5      # rotation entries (north star)
+T_TOL = 1e-4      # translation, metres (0.1 mm)
+
+BOUNDS = {"default": synth.DEFAULT_BOUNDS, "server": synth.SERVER_BOUNDS, "client": synth.CLIENT_BOUNDS}
+
+
+@pytest.fixture(scope="module")
+def api():
+    from livescan3d_b200 import api as a
+    v = a.version()
+    assert "sm_100a" in v and "device:" in v, v
+    return a
+
+
+# ---------------------------------------------------------------------------------------------------------
+# map + world transform + cull + merge
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bname", ["default", "server", "client"])
+@pytest.mark.parametrize("seed", [1000, 2000, 3000])
+def test_vertices_bit_exact_small(api, bname, seed):
+    fr = small_frame(S=3, seed_base=seed)
+    b = BOUNDS[bname]
+    want, counts = orc.orc_generate_mesh(fr, b)
+    got = api.generate_mesh_from_depth_maps(fr, b)
+    assert len(got) == len(want)
+    assert got.tobytes() == want.tobytes()
+    for i in range(3):                                         # the single-sensor export, every index
+        one = api.generate_vertices_from_depth_map(fr, b, i)
+        w1, _ = orc.orc_generate_mesh(fr, b, i)
+        assert one.tobytes() == w1.tobytes()
+
+
+def test_vertices_fixture_poses_and_odd_sizes(api):
+    # the two calibration.txt poses the reference ships, and sizes that defeat every vector-load alignment
+    fr = synth.make_frame(2, 160, 120, poses=synth.FIXTURE_POSES)
+    for b in BOUNDS.values():
+        assert api.generate_mesh_from_depth_maps(fr, b).tobytes() == orc.orc_generate_mesh(fr, b)[0].tobytes()
+    for (w, h) in [(127, 95), (33, 7), (1, 1), (2049, 3)]:
+        fr = synth.make_frame(3, w, h, ring=8)
+        got = api.generate_mesh_from_depth_maps(fr, synth.SERVER_BOUNDS)
+        want, _ = orc.orc_generate_mesh(fr, synth.SERVER_BOUNDS)
+        assert got.tobytes() == want.tobytes(), (w, h)
+
+
+def test_vertices_mixed_resolutions_and_empty(api):
+    a = synth.make_frame(1, 128, 96)
+    b = synth.make_frame(1, 64, 48, seed_base=5)
+    fr = {"n_maps": 2, "depth_maps": np.concatenate([a["depth_maps"], b["depth_maps"]]), "depth_colors": np.concatenate([a["depth_colors"], b["depth_colors"]]),
+          "widths": np.array([128, 64], np.int32), "heights": np.array([96, 48], np.int32),
+          "intr": np.concatenate([a["intr"], b["intr"]]), "wt": np.concatenate([a["wt"], b["wt"]])}
+    assert api.generate_mesh_from_depth_maps(fr, synth.SERVER_BOUNDS).tobytes() == orc.orc_generate_mesh(fr, synth.SERVER_BOUNDS)[0].tobytes()
+    # all-zero depth: no vertices at all; bounds that cull everything: the same
+    z = dict(fr)
+    z["depth_maps"] = np.zeros_like(fr["depth_maps"])
+    assert len(api.generate_mesh_from_depth_maps(z, synth.SERVER_BOUNDS)) == 0
+    assert len(api.generate_mesh_from_depth_maps(fr, [10, 10, 10, 11, 11, 11])) == 0
+    # boundary semantics: the cull is strict (< min or > max), points ON the box stay
+    v = orc.orc_generate_mesh(fr, synth.SERVER_BOUNDS)[0]
+    p = v[len(v) // 2]
+    tight = [float(p["X"]), float(p["Y"]), float(p["Z"]), float(p["X"]), float(p["Y"]), float(p["Z"])]
+    got = api.generate_mesh_from_depth_maps(fr, tight)
+    want = orc.orc_generate_mesh(fr, tight)[0]
+    assert len(want) >= 1 and got.tobytes() == want.tobytes()
+
+
+def test_vertices_full_size_8_sensors(api):
+    fr = synth.make_frame(8)                                   # 8 x 512x424, BASELINE.json configs[3] shape
+    want, counts = orc.orc_generate_mesh(fr, synth.DEFAULT_BOUNDS)
+    got = api.generate_mesh_from_depth_maps(fr, synth.DEFAULT_BOUNDS)
+    assert len(got) == len(want) and got.tobytes() == want.tobytes()
+    got5 = api.generate_vertices_from_depth_map(fr, synth.DEFAULT_BOUNDS, 5)
+    s = int(counts[:5].sum())
+    assert got5.tobytes() == want[s:s + int(counts[5])].tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# neighbour-count filter
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,md", [(10, 0.01), (10, 0.1), (1, 0.01), (50, 0.05), (3, 0.02), (200, 0.1), (2, 1e-4)])
+def test_filter_bit_exact(api, k, md):
+    fr = small_frame(S=1, w=160, h=120)
+    xyz, rgba = cloud_of(fr, synth.DEFAULT_BOUNDS, 0)
+    wv, wc, wm = orc.orc_filter(xyz, rgba, k, md)
+    gv, gc, gm = api.filter(xyz, rgba, k, md)
+    assert np.array_equal(gm, wm), f"mask mismatches: {(gm != wm).sum()} of {len(wm)}"
+    assert gv.tobytes() == wv.tobytes() and gc.tobytes() == wc.tobytes()
+
+
+def test_filter_edge_cases(api):
+    fr = small_frame(S=1, w=64, h=48)
+    xyz, rgba = cloud_of(fr, synth.SERVER_BOUNDS, 0)
+    for k, md in [(0, 0.01), (10, 0.0), (-1, -1.0)]:            # filter.cpp:38-41 early return
+        gv, gc, gm = api.filter(xyz, rgba, k, md)
+        assert len(gv) == len(xyz) and np.all(gm == -2) and gv.tobytes() == xyz.tobytes()
+    gv, gc, gm = api.filter(xyz[:5], rgba[:5], 10, 10.0)        # fewer points than k: all removed
+    assert len(gv) == 0 and np.all(gm == -1)
+    gv, gc, gm = api.filter(xyz[:0], rgba[:0], 10, 0.01)        # empty
+    assert len(gv) == 0 and len(gm) == 0
+    one = np.array([[0.1, 0.2, 0.3]], np.float32)
+    assert len(api.filter(one, rgba[:1], 1, 0.01)[0]) == 1      # k=1 counts the point itself
+    dup = np.repeat(one, 40, axis=0)                            # 40 coincident points, k=40: all kept, d2 = 0
+    wv, wc, wm = orc.orc_filter(dup, np.repeat(rgba[:1], 40, axis=0), 40, 0.01)
+    gv, gc, gm = api.filter(dup, np.repeat(rgba[:1], 40, axis=0), 40, 0.01)
+    assert np.array_equal(gm, wm) and len(gv) == 40
+    # huge radius: every point sees every other (one voxel of candidates, multi-chunk staging)
+    sub = xyz[:1500]
+    wv, wc, wm = orc.orc_filter(sub, rgba[:1500], 700, 50.0)
+    gv, gc, gm = api.filter(sub, rgba[:1500], 700, 50.0)
+    assert np.array_equal(gm, wm)
+    # far-apart clusters (large bounding box relative to the radius: the voxel grid has to coarsen)
+    far = np.concatenate([xyz[:800], xyz[:800] + np.float32(900.0)])
+    col = np.concatenate([rgba[:800], rgba[:800]])
+    wv, wc, wm = orc.orc_filter(far, col, 5, 0.02)
+    gv, gc, gm = api.filter(far, col, 5, 0.02)
+    assert np.array_equal(gm, wm)
+
+
+def test_filter_full_size_sensor(api):
+    fr = synth.make_frame(1, ring=8)
+    xyz, rgba = cloud_of(fr, synth.DEFAULT_BOUNDS, 0)
+    for k, md in [(10, 0.01), (10, 0.1)]:
+        wv, wc, wm = orc.orc_filter(xyz, rgba, k, md)
+        gv, gc, gm = api.filter(xyz, rgba, k, md)
+        assert np.array_equal(gm, wm), f"(k={k}, maxDist={md}): {(gm != wm).sum()} mask mismatches of {len(wm)}"
+        assert gv.tobytes() == wv.tobytes() and gc.tobytes() == wc.tobytes()
+
+
+def _pipeline_oracle(fr, bounds, k, md):
+    """createVertices -> filter per sensor -> formMesh, composed from the oracle's stages."""
+    parts, counts = [], []
+    for i in range(int(fr["n_maps"])):
+        v, _ = orc.orc_generate_mesh(fr, bounds, i)
+        xyz = xyz_of(v)
+        col = np.stack([v["R"], v["G"], v["B"], v["A"]], axis=1)
+        _, _, m = orc.orc_filter(xyz, col, k, md)
+        keep = m >= 0 if (k > 0 and md > 0) else np.ones(len(v), bool)
+        parts.append(v[keep])
+        counts.append(int(keep.sum()))
+    return np.concatenate(parts), np.array(counts)
+
+
+@pytest.mark.parametrize("k,md", [(10, 0.01), (10, 0.1), (4, 0.03), (0, 0.0)])
+def test_frame_pipeline_small(api, k, md):
+    fr = small_frame(S=4, w=160, h=120)
+    want, wcounts = _pipeline_oracle(fr, synth.DEFAULT_BOUNDS, k, md)
+    got, gcounts = api.frame_pipeline(fr, synth.DEFAULT_BOUNDS, k, md)
+    assert np.array_equal(gcounts, wcounts)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_frame_pipeline_full_size_8_sensors(api):
+    fr = synth.make_frame(8)
+    want, wcounts = _pipeline_oracle(fr, synth.DEFAULT_BOUNDS, 10, 0.01)
+    got, gcounts = api.frame_pipeline(fr, synth.DEFAULT_BOUNDS, 10, 0.01)
+    assert np.array_equal(gcounts, wcounts), (gcounts, wcounts)
+    assert got.tobytes() == want.tobytes()
+    # size-independent property: the survivors are an in-order subsequence of the culled cloud
+    culled = api.generate_mesh_from_depth_maps(fr, synth.DEFAULT_BOUNDS)
+    cv = culled.view(np.dtype((np.void, 16)))
+    gv = got.view(np.dtype((np.void, 16)))
+    order = np.argsort(cv, kind="stable")
+    where = order[np.searchsorted(cv[order], gv)]
+    assert np.array_equal(cv[where], gv) and np.all(np.diff(where) > 0)
+
+
+def test_golden_vectors(api):
+    g = np.load(os.path.join(GOLDEN, "hotpath_small.npz"))
+    fr = synth.make_frame(int(g["S"]), int(g["w"]), int(g["h"]), seed_base=int(g["seed_base"]), ring=int(g["ring"]))
+    assert api.generate_mesh_from_depth_maps(fr, g["bounds"]).tobytes() == g["vertices"].tobytes()
+    xyz, rgba = cloud_of(fr, g["bounds"], 0)
+    for i, (k, md) in enumerate(zip(g["filter_k"], g["filter_maxdist"])):
+        assert np.array_equal(api.filter(xyz, rgba, int(k), float(md))[2], g[f"filter_map_{i}"])
+    A, B = icp_pair(fr, g["bounds"])
+    gi, gd = api.find_closest(A, B)
+    mism, bad = nn_parity(gi, gd, g["nn_index"], g["nn_d2"])
+    assert bad == 0 and np.array_equal(gd.view(np.uint32), g["nn_d2"].view(np.uint32))
+    _, R, t = api.icp(A, B, max_iter=int(g["icp_iters"]))
+    assert rot_err(R, g["icp_R"]) <= R_TOL and np.max(np.abs(t - g["icp_t"])) <= T_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# nearest neighbour + ICP
+# ---------------------------------------------------------------------------------------------------------
+def test_find_closest_parity(api):
+    fr = small_frame(S=2, w=160, h=120)
+    A, B = icp_pair(fr, synth.DEFAULT_BOUNDS)
+    wi, wd = orc.orc_find_closest(A, B)
+    gi, gd = api.find_closest(A, B)
+    mism, bad = nn_parity(gi, gd, wi, wd)
+    assert bad == 0, f"{bad} wrong neighbours ({mism} index mismatches)"
+    assert np.array_equal(gd.view(np.uint32), wd.view(np.uint32))
+    assert mism <= len(B) // 1000, f"{mism} tie mismatches is implausibly many"
+
+
+def test_find_closest_far_and_outside_queries(api):
+    """nanoflann always returns the true nearest neighbour, however far: queries metres away from the target,
+    outside its bounding box, and in its empty regions must stay exact (octree fallback of the grid search)."""
+    fr = small_frame(S=2, w=160, h=120)
+    A, _ = cloud_of(fr, synth.DEFAULT_BOUNDS, 0)
+    rng = np.random.RandomState(7)
+    lo, hi = A.min(0), A.max(0)
+    q_in = rng.uniform(lo, hi, size=(4000, 3)).astype(np.float32)                 # mostly empty space inside the box
+    q_out = (rng.uniform(-1, 1, size=(2000, 3)) * 25.0).astype(np.float32)        # far outside
+    q_edge = (A[rng.randint(0, len(A), 1000)] + rng.normal(0, 0.2, size=(1000, 3))).astype(np.float32)
+    Q = np.concatenate([q_in, q_out, q_edge, A[:500]])                            # and exact hits (d2 == 0)
+    wi, wd = orc.orc_find_closest(A, Q, brute=True)
+    gi, gd = api.find_closest(A, Q)
+    mism, bad = nn_parity(gi, gd, wi, wd)
+    assert bad == 0, f"{bad} wrong neighbours ({mism} index mismatches)"
+    assert np.array_equal(gd.view(np.uint32), wd.view(np.uint32))
+    # degenerate targets: a single point, coincident points, a line
+    for T in [A[:1], np.repeat(A[:1], 50, axis=0), np.stack([np.linspace(0, 1, 300)] * 3, axis=1).astype(np.float32)]:
+        wi, wd = orc.orc_find_closest(T, Q[:800], brute=True)
+        gi, gd = api.find_closest(T, Q[:800])
+        assert nn_parity(gi, gd, wi, wd)[1] == 0 and np.array_equal(gd.view(np.uint32), wd.view(np.uint32))
+
+
+def _check_icp(api, A, B, iters, R0=None, t0=None):
+    wv, wR, wt, wtr = orc.orc_icp(A, B, R0, t0, max_iter=iters)
+    gv, gR, gt, gtr = api.icp_trace(A, B, R0, t0, max_iter=iters)
+    dR, dt = rot_err(gR, wR), float(np.max(np.abs(gt.astype(np.float64) - wt)))
+    assert dR <= R_TOL, f"max |dR| = {dR:.3e}"
+    assert dt <= T_TOL, f"max |dt| = {dt:.3e} m"
+    assert float(np.max(np.abs(gv.astype(np.float64) - wv))) <= 2 * T_TOL
+    # stage level: match / accept counts per iteration (a handful of borderline pairs may flip at the 2.5 sigma gate,
+    # because sigma is an fp64 parallel reduction here and a sequential fp32 sum in the reference)
+    assert gtr[0]["n_matched"] == wtr[0]["n_matched"]
+    for g, w in zip(gtr, wtr):
+        assert abs(g["n_matched"] - w["n_matched"]) <= max(3, w["n_matched"] // 2000)
+        assert abs(g["n_accepted"] - w["n_accepted"]) <= max(3, w["n_matched"] // 500)
+        assert abs(g["sigma"] - w["sigma"]) <= 1e-3 * w["sigma"]
+    return dR, dt
+
+
+def test_icp_parity_small(api):
+    fr = small_frame(S=2, w=160, h=120)
+    A, B = icp_pair(fr, synth.DEFAULT_BOUNDS)
+    _check_icp(api, A, B, 10)
+    _check_icp(api, A, B, 1)
+    R0 = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], dtype=np.float32)
+    _check_icp(api, A, B, 3, R0, np.array([0.1, -0.2, 0.3], np.float32))
+    # maxIter = 0: nothing changes
+    v, R, t = api.icp(A, B, max_iter=0)
+    assert v.tobytes() == B.tobytes() and np.array_equal(R, np.eye(3, dtype=np.float32)) and not t.any()
+
+
+def test_icp_parity_full_size_pair(api):
+    """BASELINE.json configs[0]: two overlapping 512x424 clouds with the known rigid offset, maxIter 10."""
+    fr = synth.make_frame(2, ring=8)
+    A, B = icp_pair(fr, synth.DEFAULT_BOUNDS)
+    assert len(A) > 150_000 and len(B) > 150_000
+    dR, dt = _check_icp(api, A, B, 10)
+    print(f"full-size ICP parity: max|dR|={dR:.2e} max|dt|={dt:.2e} m")
+
+
+def test_icp_error_reporting(api):
+    from livescan3d_b200.native import Ls3dError
+    A = np.zeros((0, 3), np.float32)
+    B = np.ones((10, 3), np.float32)
+    with pytest.raises(Ls3dError):
+        api.icp(A, B, max_iter=1)                              # empty target: the reference throws (nanoflann.h:904)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device-resident API (what bench.py times)
+# ---------------------------------------------------------------------------------------------------------
+def test_device_api_matches_host_api(api):
+    import torch
+    from livescan3d_b200.device import FramePipeline, IcpSolver
+    fr = small_frame(S=4, w=160, h=120)
+    fp = FramePipeline(fr["widths"], fr["heights"])
+    dd = torch.from_numpy(fr["depth_maps"]).cuda()
+    dc = torch.from_numpy(fr["depth_colors"]).cuda()
+    fp.set_params(fr["intr"], fr["wt"], synth.DEFAULT_BOUNDS, 10, 0.01)
+    for _ in range(3):                                         # re-runnable without re-creating anything
+        fp.run(dd, dc)
+    v, counts = fp.result()
+    want, wcounts = api.frame_pipeline(fr, synth.DEFAULT_BOUNDS, 10, 0.01)
+    assert v.tobytes() == want.tobytes() and np.array_equal(counts, wcounts)
+    fp.run(dd, dc, first_map=2, n_run=1)                       # a sensor sub-range
+    v1, c1 = fp.result()
+    assert len(v1) == wcounts[2] and v1.tobytes() == want[wcounts[:2].sum():wcounts[:3].sum()].tobytes()
+    fp.close()
+
+    A, B = icp_pair(fr, synth.DEFAULT_BOUNDS)
+    s = IcpSolver(len(A), len(B))
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B.copy()).cuda()
+    s.set_target(dA)
+    s.set_source(dB)
+    s.run(6)
+    R, t, st = s.pose()
+    hv, hR, ht = api.icp(A, B, max_iter=6)
+    assert st[0] == 6 and st[1] == 0
+    assert np.array_equal(R, hR) and np.array_equal(t, ht) and dB.cpu().numpy().tobytes() == hv.tobytes()
+    # staged driving (what the multi-GPU host does) == the captured graph
+    dB2 = torch.from_numpy(B.copy()).cuda()
+    s.set_target(dA)
+    s.set_source(dB2)
+    for _ in range(6):
+        s.match(); s.stats(); s.sums()
+    s.finish()
+    R2, t2, _ = s.pose()
+    assert np.array_equal(R2, hR) and np.array_equal(t2, ht)
+    s.close()

@@ -1,0 +1,130 @@
+"""Pins the CPU oracle (oracle/ls3d_oracle.cpp, a restatement) against the reference's OWN sources compiled in
+place (oracle/_ref/, built by oracle/Makefile from /root/reference) on seeded inputs, and against the golden
+vectors under tests/golden/ that were generated from that build (tests/golden/make_golden.py).
+
+The reference ships no golden vectors for this path, so these two are what "pinned" means here.
+CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from common import GOLDEN, cloud_of, icp_pair, nn_parity, rot_err, small_frame, synth, orc
+
+needs_ref = pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+BOUNDS = [synth.DEFAULT_BOUNDS, synth.SERVER_BOUNDS, synth.CLIENT_BOUNDS]
+
+
+@needs_ref
+@pytest.mark.parametrize("bi", [0, 1, 2])
+@pytest.mark.parametrize("seed", [1000, 2000])
+def test_vertices_bit_exact_vs_reference(bi, seed):
+    fr = small_frame(S=3, seed_base=seed)
+    ref_v, ref_counts = orc.ref_generate_mesh(fr, BOUNDS[bi])
+    orc_v, orc_counts = orc.orc_generate_mesh(fr, BOUNDS[bi])
+    assert np.array_equal(ref_counts, orc_counts)
+    assert ref_v.tobytes() == orc_v.tobytes()
+    # the reference's single-sensor export agrees with the corresponding slice
+    one = orc.ref_generate_vertices_from_depth_map(fr, BOUNDS[bi], 1)
+    s = int(ref_counts[0])
+    assert one.tobytes() == ref_v[s:s + int(ref_counts[1])].tobytes()
+
+
+@needs_ref
+def test_fixture_poses_and_pixel_maps_vs_reference():
+    fr = synth.make_frame(2, 160, 120, poses=synth.FIXTURE_POSES)
+    for b in BOUNDS:
+        assert orc.ref_generate_mesh(fr, b)[0].tobytes() == orc.orc_generate_mesh(fr, b)[0].tobytes()
+    w, h = 160, 120
+    d = fr["depth_maps"].view(np.uint16)[: w * h]
+    c = fr["depth_colors"][: 3 * w * h]
+    n1, a1, b1 = orc.ref_vertex_maps(d, c, w, h, fr["intr"][:7], fr["wt"][:12], synth.SERVER_BOUNDS)
+    n2, a2, b2 = orc.orc_vertex_maps(d, c, w, h, fr["intr"][:7], fr["wt"][:12], synth.SERVER_BOUNDS)
+    assert n1 == n2 and np.array_equal(a1, a2) and np.array_equal(b1, b2)
+
+
+@needs_ref
+@pytest.mark.parametrize("k,md", [(10, 0.01), (10, 0.1), (1, 0.01), (50, 0.05), (3, 0.02)])
+def test_filter_bit_exact_vs_reference(k, md):
+    fr = small_frame(S=1, w=160, h=120)
+    xyz, rgba = cloud_of(fr, synth.DEFAULT_BOUNDS, 0)
+    rv, rc, rm = orc.ref_filter(xyz, rgba, k, md)
+    ov, oc, om = orc.orc_filter(xyz, rgba, k, md)
+    assert np.array_equal(rm, om)
+    assert rv.tobytes() == ov.tobytes() and rc.tobytes() == oc.tobytes()
+    assert np.array_equal(orc.ref_knn_kdist(xyz, k).view(np.uint32), orc.orc_knn_kdist(xyz, k).view(np.uint32))
+
+
+@needs_ref
+def test_filter_edge_cases_vs_reference():
+    fr = small_frame(S=1, w=64, h=48)
+    xyz, rgba = cloud_of(fr, synth.SERVER_BOUNDS, 0)
+    for k, md in [(0, 0.01), (10, 0.0), (-1, -1.0)]:            # early return: untouched, map holds only the sentinel
+        rv, rc, rm = orc.ref_filter(xyz, rgba, k, md)
+        ov, oc, om = orc.orc_filter(xyz, rgba, k, md)
+        assert len(rv) == len(xyz) and np.array_equal(rm, om) and np.all(rm == -2)
+    few = xyz[:5]                                                # k > n: every point is removed (nanoflann.h:93)
+    rv, rc, rm = orc.ref_filter(few, rgba[:5], 10, 10.0)
+    ov, oc, om = orc.orc_filter(few, rgba[:5], 10, 10.0)
+    assert len(rv) == 0 and len(ov) == 0 and np.array_equal(rm, om)
+
+
+@needs_ref
+def test_find_closest_vs_reference_and_brute_force():
+    fr = small_frame(S=2, w=160, h=120)
+    A, B = icp_pair(fr, synth.DEFAULT_BOUNDS)
+    ri, rd = orc.ref_find_closest(A, B)
+    oi, od = orc.orc_find_closest(A, B)
+    assert np.array_equal(ri, oi) and np.array_equal(rd.view(np.uint32), od.view(np.uint32))
+    bi, bd = orc.orc_find_closest(A, B, brute=True)
+    mism, bad = nn_parity(oi, od, bi, bd)
+    assert bad == 0
+
+
+@needs_ref
+def test_icp_vs_reference():
+    fr = small_frame(S=2, w=160, h=120)
+    A, B = icp_pair(fr, synth.DEFAULT_BOUNDS)
+    rv, rR, rt = orc.ref_icp(A, B, max_iter=5)
+    ov, oR, ot, _ = orc.orc_icp(A, B, max_iter=5)
+    # same source compiled around the same mini-cv arithmetic: identical results
+    assert np.array_equal(rR.view(np.uint32), oR.view(np.uint32))
+    assert np.array_equal(rt.view(np.uint32), ot.view(np.uint32))
+    assert rv.tobytes() == ov.tobytes()
+    # accumulate-into semantics: non-identity R, non-zero t on entry (MainWindowForm.cs:330-344 passes I, 0)
+    R0 = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], dtype=np.float32)
+    t0 = np.array([0.1, -0.2, 0.3], dtype=np.float32)
+    rv, rR, rt = orc.ref_icp(A, B, R0, t0, max_iter=2)
+    ov, oR, ot, _ = orc.orc_icp(A, B, R0, t0, max_iter=2)
+    assert np.array_equal(rR.view(np.uint32), oR.view(np.uint32)) and np.array_equal(rt.view(np.uint32), ot.view(np.uint32))
+
+
+def test_icp_recovers_known_offset():
+    """Sanity of the oracle itself: ICP reduces the known 1.5 deg / (8,-5,6) mm perturbation (point-to-point ICP
+    slides along the scene's planes, so 10 iterations only take part of it back)."""
+    fr = small_frame(S=2, w=160, h=120)
+    A, _ = cloud_of(fr, synth.DEFAULT_BOUNDS, 0)
+    B = synth.perturb(A)
+    ov, oR, ot, tr = orc.orc_icp(A, B, max_iter=10)
+    assert np.sqrt(((ov - A) ** 2).sum(1)).mean() < 0.8 * np.sqrt(((B - A) ** 2).sum(1)).mean()
+    assert tr[0]["n_matched"] > 0 and tr[0]["n_accepted"] <= tr[0]["n_matched"]
+
+
+def test_oracle_vs_golden_vectors():
+    """tests/golden/*.npz were written by tests/golden/make_golden.py from the compiled reference (oracle/_ref)."""
+    path = os.path.join(GOLDEN, "hotpath_small.npz")
+    assert os.path.exists(path), "golden fixture missing: run python tests/golden/make_golden.py in the build container"
+    g = np.load(path)
+    fr = synth.make_frame(int(g["S"]), int(g["w"]), int(g["h"]), seed_base=int(g["seed_base"]), ring=int(g["ring"]))
+    assert fr["depth_maps"].tobytes() == g["depth_maps"].tobytes(), "synthetic generator drifted from the fixture"
+    v, counts = orc.orc_generate_mesh(fr, g["bounds"])
+    assert np.array_equal(counts, g["vertex_counts"]) and v.tobytes() == g["vertices"].tobytes()
+    xyz, rgba = cloud_of(fr, g["bounds"], 0)
+    for i, (k, md) in enumerate(zip(g["filter_k"], g["filter_maxdist"])):
+        _, _, m = orc.orc_filter(xyz, rgba, int(k), float(md))
+        assert np.array_equal(m, g[f"filter_map_{i}"])
+    A, B = icp_pair(fr, g["bounds"])
+    oi, od = orc.orc_find_closest(A, B)
+    assert np.array_equal(oi, g["nn_index"]) and np.array_equal(od.view(np.uint32), g["nn_d2"].view(np.uint32))
+    ov, oR, ot, _ = orc.orc_icp(A, B, max_iter=int(g["icp_iters"]))
+    assert rot_err(oR, g["icp_R"]) == 0.0 and np.array_equal(ot, g["icp_t"])
