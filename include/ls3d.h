@@ -146,6 +146,13 @@ const int *ls3d_frame_culled_starts(Ls3dFrame *f);    /* device int[n_maps+1]: s
 const int *ls3d_frame_old_to_new(Ls3dFrame *f);       /* device int[n_culled]: culled index -> merged index or -1 */
 const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f);  /* device int[sum w*h]: pixel -> culled vertex index within its sensor, or -1 */
 
+/* Optional per-stage timing for the roofline report: with timing on, ls3d_frame_run records CUDA events between
+ * its kernels on the run's stream; ls3d_frame_stage_ms waits for the last run and returns, in milliseconds,
+ * [0] clear+map/cull/compact [1] hash clear [2] voxel insert [3] cell ranges+scatter [4] neighbour count
+ * [5] survivor compaction (the merge) [6] whole run.  Returns 0/-1. */
+void ls3d_frame_enable_timing(Ls3dFrame *f, int on);
+int ls3d_frame_stage_ms(Ls3dFrame *f, float out[8]);
+
 /* Same path, writing the merged cloud to a caller-provided device buffer at record offset read from
  * d_dst_offset (device int, may be NULL = 0): the multi-GPU merge writes peer-mapped memory through this. */
 int ls3d_frame_run_to(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run,

@@ -606,7 +606,17 @@ struct Ls3dFrame {
 	// pinned read-back block: FrameCtl + starts
 	int *pin_out = nullptr;
 	bool want_d2v = false;
+	// optional per-stage timing (bench.py's roofline pass): events recorded on the run's stream between kernels
+	bool timing = false;
+	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	int ev_recorded = 0;     // bit mask
 };
+
+static void stage_mark(Ls3dFrame *f, int i, cudaStream_t st) {
+	if (!f->timing) return;
+	if (!f->ev[i] && cudaEventCreate(&f->ev[i]) != cudaSuccess) { f->ev[i] = nullptr; return; }
+	if (cudaEventRecord(f->ev[i], st) == cudaSuccess) f->ev_recorded |= 1 << i;
+}
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -617,6 +627,7 @@ static void frame_free(Ls3dFrame *f) {
 	for (DevBuf *b : bufs) b->release();
 	if (f->pin_sd) cudaFreeHost(f->pin_sd);
 	if (f->pin_out) cudaFreeHost(f->pin_out);
+	for (cudaEvent_t e : f->ev) if (e) cudaEventDestroy(e);
 	delete f;
 }
 
@@ -769,6 +780,7 @@ static int frame_merge_stage(Ls3dFrame *f, int s_first, int s_end, long long n_m
 	k_filter_compact<<<std::max(1, std::min(tiles, f->sm_count * 6)), kScanThreads, 0, st>>>(f->cloud0.as<uint4>(), f->keep.as<uint8_t>(),
 		f->culled_starts, s_first, s_end, f->ctl, f->status_b, f->final_starts, dst, d_dst_offset, f->map.as<int>(), peers);
 	count_launch(1);
+	stage_mark(f, 6, st);
 	return cuda_ok(cudaGetLastError(), "k_filter_compact") ? 1 : -1;
 }
 
@@ -777,13 +789,17 @@ static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n
 	const unsigned slot_lo = f->h_sd[s_first].tbl_off, slot_hi = f->h_sd[s_end].tbl_off;
 	if (!cuda_ok(cudaMemsetAsync(f->table.as<unsigned long long>() + slot_lo, 0, 8 * (size_t)(slot_hi - slot_lo), st), "clear voxel hash")) return -1;
 	const int pt_blocks = (int)std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8);
+	stage_mark(f, 2, st);
 	k_voxel_insert<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
 		f->table.as<unsigned long long>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>());
+	stage_mark(f, 3, st);
 	k_cell_ranges<<<(slot_hi - slot_lo + 255) / 256, 256, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(), slot_lo, slot_hi, f->ctl);
 	k_cell_scatter<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(),
 		f->cell_start.as<unsigned>(), f->ctl, f->sorted.as<float4>());
+	stage_mark(f, 4, st);
 	k_neighbour_count<<<f->sm_count * 6, kCountWarps * 32, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(),
 		f->sorted.as<float4>(), sd, s_first, s_end, f->ctl, f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
+	stage_mark(f, 5, st);
 	count_launch(4);
 	if (!cuda_ok(cudaGetLastError(), "filter kernels")) return -1;
 	if (!(stages & kStageMerge)) return 4;
@@ -808,6 +824,8 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 	if (n_run <= 0) { first_map = 0; n_run = f->S; }
 	if (first_map < 0 || first_map + n_run > f->S) { set_error("ls3d_frame_run: sensor range [%d,%d) outside 0..%d", first_map, first_map + n_run, f->S); return -1; }
 	const int s_first = first_map, s_end = first_map + n_run;
+	f->ev_recorded = 0;
+	stage_mark(f, 0, st);
 	if (!cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block")) return -1;
 	const int ntiles = f->h_sd[s_end].tile_begin - f->h_sd[s_first].tile_begin;
 	const long long n_max = f->h_sd[s_end].pix_begin - f->h_sd[s_first].pix_begin;
@@ -822,6 +840,7 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 		k_map_cull_compact<false><<<blocks, kScanThreads, 0, st>>>((const uint8_t *)d_depth, (const uint8_t *)d_colors, f->sd.as<SensorDesc>(), s_first, s_end,
 			b[0], b[1], b[2], b[3], b[4], b[5], f->ctl, f->status_a, f->culled_starts, k1_out, k1_off, nullptr);
 	count_launch(1);
+	stage_mark(f, 1, st);
 	if (!cuda_ok(cudaGetLastError(), "k_map_cull_compact")) return -1;
 	int launched = 1;
 	if (f->filter_on) {
@@ -871,6 +890,24 @@ extern "C" int ls3d_frame_run_peers(Ls3dFrame *f, const void *d_depth_maps, cons
 	peers.n = n_peers;
 	for (int i = 0; i < kMaxPeers; i++) peers.ptr[i] = i < n_peers ? (uint4 *)peer_dst_vertices[i] : nullptr;
 	return frame_run_impl(f, d_depth_maps, d_depth_colors, first_map, n_run, (uint4 *)peer_dst_vertices[0], d_dst_offset, peers, (cudaStream_t)stream);
+}
+
+extern "C" void ls3d_frame_enable_timing(Ls3dFrame *f, int on) { if (f) f->timing = on != 0; }
+
+// Stage durations of the last ls3d_frame_run (milliseconds; waits for it to finish):
+//   [0] control-block clear + map/cull/compact   [1] hash clear   [2] voxel insert   [3] cell ranges + scatter
+//   [4] neighbour count   [5] survivor compaction / merge   [6] whole run   [7] unused
+extern "C" int ls3d_frame_stage_ms(Ls3dFrame *f, float *out) {
+	if (!f || !out) { set_error("ls3d_frame_stage_ms: null argument"); return -1; }
+	for (int i = 0; i < 8; i++) out[i] = 0.0f;
+	int last = -1;
+	for (int i = 0; i < 7; i++) if (f->ev_recorded & (1 << i)) last = i;
+	if (last < 1 || !(f->ev_recorded & 1)) { set_error("ls3d_frame_stage_ms: no timed run (call ls3d_frame_enable_timing first)"); return -1; }
+	if (!cuda_ok(cudaEventSynchronize(f->ev[last]), "stage timing")) return -1;
+	for (int i = 1; i <= last; i++)
+		if ((f->ev_recorded & (1 << i)) && (f->ev_recorded & (1 << (i - 1)))) cudaEventElapsedTime(&out[i - 1], f->ev[i - 1], f->ev[i]);
+	cudaEventElapsedTime(&out[6], f->ev[0], f->ev[last]);
+	return 0;
 }
 
 extern "C" const void *ls3d_frame_vertices(Ls3dFrame *f) { return f ? f->final_.p : nullptr; }

@@ -85,6 +85,15 @@ class FramePipeline:
         native.check(r >= 0, "ls3d_frame_merge_peers")
         return r
 
+    def enable_timing(self, on=True):
+        self.lib.ls3d_frame_enable_timing(self.h, 1 if on else 0)
+
+    def stage_ms(self) -> np.ndarray:
+        """[map_cull, hash_clear, insert, ranges+scatter, neighbour_count, compact_merge, whole] of the last timed run."""
+        out = np.zeros(8, dtype=np.float32)
+        native.check(self.lib.ls3d_frame_stage_ms(self.h, out.ctypes.data_as(C.c_void_p)) == 0, "ls3d_frame_stage_ms")
+        return out[:7]
+
     # ---- results (views of library memory; valid until the next run) ----
     def vertices(self) -> torch.Tensor:
         """uint8 [total_px, 16] view of the merged cloud buffer; rows [0, n_final) are valid."""
