@@ -36,8 +36,7 @@ namespace ls3d {
 constexpr int kCellBits = 13;                 // voxel coordinate bits per axis
 constexpr int kCellMax = (1 << kCellBits) - 1;
 constexpr unsigned long long kCountMask = 0xFFFFFFull;
-constexpr int kCountWarps = 8;                // warps per block in K5
-constexpr int kChunk = 256;                   // candidates staged per warp in K5
+constexpr int kCountWarps = 4;                // warps per block in K5
 constexpr int kMaxPeers = 8;
 
 struct PeerDst { int n; uint4 *ptr[kMaxPeers]; };
@@ -251,23 +250,31 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 // ------------------------------------------------------------------------------------------------------
 // K3: contiguous range of the sorted array for every occupied voxel
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cell_ranges(const unsigned long long *__restrict__ table, unsigned *__restrict__ cell_start,
+constexpr int kRangeThreads = 1024;
+__global__ void __launch_bounds__(kRangeThreads) k_cell_ranges(const unsigned long long *__restrict__ table, unsigned *__restrict__ cell_start,
 	unsigned slot_lo, unsigned slot_hi, FrameCtl *ctl)
 {
-	const unsigned i = slot_lo + blockIdx.x * blockDim.x + threadIdx.x;    // ranges are multiples of 32
-	const int lane = threadIdx.x & 31;
+	// one atomicAdd on the shared cursor per 1024 slots (ncu: one per warp serialised ~1e5 same-address atomics)
+	__shared__ unsigned s_w[32];
+	__shared__ unsigned s_base;
+	const unsigned i = slot_lo + blockIdx.x * kRangeThreads + threadIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned cnt = 0;
 	if (i < slot_hi) {
 		const unsigned long long w = table[i];
 		if (w >> 24) cnt = (unsigned)(w & kCountMask);
 	}
 	const unsigned incl = warp_incl_scan(cnt, lane);
-	const unsigned total = __shfl_sync(kFull, incl, 31);
-	if (total == 0) return;
-	unsigned base = 0;
-	if (lane == 0) base = atomicAdd(&ctl->cursor, total);
-	base = __shfl_sync(kFull, base, 0);
-	if (cnt) cell_start[i] = base + incl - cnt;
+	if (lane == 31) s_w[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		const unsigned v = s_w[lane];
+		const unsigned sc = warp_incl_scan(v, lane);
+		s_w[lane] = sc - v;
+		if (lane == 31) s_base = sc ? atomicAdd(&ctl->cursor, sc) : 0u;
+	}
+	__syncthreads();
+	if (cnt) cell_start[i] = s_base + s_w[warp] + incl - cnt;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -295,65 +302,64 @@ __constant__ signed char c_nb[27][3] = {
 	{-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1}, {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
 	{-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
 
-// Count staged candidates against the (up to 32) queries of this group.  Candidates sit in lanes, queries are
-// broadcast by shuffle, so the running count of a query is warp-uniform and the exit at k costs no divergence.
-__device__ __forceinline__ bool count_chunk(const float4 *buf, int fill, int nq, const float4 &myq, int &mycount, int k, float thr, int lane) {
-	for (int q = 0; q < nq; q++) {
-		int c = __shfl_sync(kFull, mycount, q);
-		if (c >= k) continue;
-		const float qx = __shfl_sync(kFull, myq.x, q), qy = __shfl_sync(kFull, myq.y, q), qz = __shfl_sync(kFull, myq.z, q);
-		for (int s = 0; s < fill; s += 32) {
-			const int idx = s + lane;
-			const float4 cd = buf[idx];                // idx < kChunk always; entries past `fill` are masked below
-			const float d2 = dist2_ref(qx, qy, qz, cd.x, cd.y, cd.z);
-			c += __popc(__ballot_sync(kFull, idx < fill && d2 <= thr));
-			if (c >= k) break;
-		}
-		if (lane == q) mycount = c;
-	}
-	return __all_sync(kFull, mycount >= k);
-}
+// One lane per query point, 32 consecutive points of the voxel-sorted array per warp.
+//  1. the distinct voxels among the warp's 32 points (a voxel's points are contiguous) are looked up once each:
+//     27 lanes probe the 27 neighbour voxels in parallel and the non-empty (start, count) ranges are compacted
+//     into shared memory in visiting order (home voxel first);
+//  2. every lane then walks its own voxel's candidate ranges with a private cursor — a flattened loop, so lanes
+//     with different range layouts stay busy — counting d2 <= thr and leaving as soon as it reaches k;
+//  3. lanes that are still undecided after kLaneIters candidates (isolated points in dense surroundings, large
+//     radii) are finished one at a time by the whole warp: candidates in lanes, ballot/popc, warp-uniform exit.
+// (Round-1 profile of the previous one-warp-per-voxel version: 350 M warp instructions for 739 k queries, 75 %
+// issue-bound on per-voxel staging overhead; see profiles/.)
+constexpr int kLaneIters = 96;
 
 __global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const unsigned long long *__restrict__ table,
 	const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted, const SensorDesc *__restrict__ sd,
-	int s_first, int s_end, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep)
+	const int *__restrict__ culled_starts, int s_first, int s_end, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep)
 {
-	__shared__ float4 sbuf[kCountWarps][kChunk];
+	__shared__ uint2 s_rng[kCountWarps][32][27];      // [warp][voxel slot][range] = (start, count)
+	__shared__ unsigned char s_nr[kCountWarps][32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	float4 *buf = sbuf[warp];
-	const unsigned slot_lo = sd[s_first].tbl_off, slot_hi = sd[s_end].tbl_off;
-	const unsigned nbatches = (slot_hi - slot_lo) >> 5;
+	const int N = ctl->n_culled;
+	const int nbatches = (N + 31) >> 5;
 
 	for (;;) {
-		unsigned b = 0;
-		if (lane == 0) b = atomicAdd(&ctl->work_counter, 1u);
+		int b = 0;
+		if (lane == 0) b = (int)atomicAdd(&ctl->work_counter, 1u);
 		b = __shfl_sync(kFull, b, 0);
 		if (b >= nbatches) break;
-		const unsigned i = slot_lo + (b << 5) + lane;
-		const unsigned long long w = table[i];
-		const bool occ = (w >> 24) != 0;
-		const unsigned mystart = occ ? cell_start[i] : 0u;
-		unsigned mask = __ballot_sync(kFull, occ);
-		if (!mask) continue;
-		int s = s_first;
-		while (sd[s + 1].tbl_off <= slot_lo + (b << 5)) s++;
-		const unsigned toff = sd[s].tbl_off, tmask = sd[s].tbl_mask;
+		const int pos = (b << 5) + lane;
+		const bool valid = pos < N;
+		float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+		int s = s_first, cx = 0, cy = 0, cz = 0;
+		unsigned long long tag = ~0ull - (unsigned long long)lane;
+		if (valid) {
+			q = sorted[pos];
+			const int g = __float_as_int(q.w);
+			while (s + 1 < s_end && culled_starts[s + 1] <= g) s++;
+			cx = cell_coord(q.x, sd[s].gox, sd[s].ginv_h);
+			cy = cell_coord(q.y, sd[s].goy, sd[s].ginv_h);
+			cz = cell_coord(q.z, sd[s].goz, sd[s].ginv_h);
+			tag = ((unsigned long long)s << 40) | ((unsigned long long)cz << (2 * kCellBits)) | ((unsigned long long)cy << kCellBits) | (unsigned long long)cx;
+		}
+		const unsigned long long prev = __shfl_up_sync(kFull, tag, 1);
+		const bool leader = valid && (lane == 0 || prev != tag);
+		const unsigned lead_mask = __ballot_sync(kFull, leader);
+		const int slot = __popc(lead_mask & (0xffffffffu >> (31 - lane))) - 1;      // this lane's voxel slot (valid lanes only)
 
-		while (mask) {
-			const int j = __ffs(mask) - 1;
-			mask &= mask - 1;
-			const unsigned long long wj = __shfl_sync(kFull, w, j);
-			const unsigned sj = __shfl_sync(kFull, mystart, j);
-			const unsigned long long key = (wj >> 24) - 1;
-			const int Q = (int)(wj & kCountMask);
-			const int cx = (int)(key & kCellMax), cy = (int)((key >> kCellBits) & kCellMax), cz = (int)(key >> (2 * kCellBits));
-
-			// 27 voxel look-ups by 27 lanes
+		// ---- 1. one cooperative look-up per distinct voxel ----
+		unsigned m = lead_mask;
+		int vs = 0;
+		while (m) {
+			const int l = __ffs(m) - 1;
+			m &= m - 1;
+			const int ls = __shfl_sync(kFull, s, l), lx = __shfl_sync(kFull, cx, l), ly = __shfl_sync(kFull, cy, l), lz = __shfl_sync(kFull, cz, l);
 			unsigned ncnt = 0, nstart = 0;
-			if (lane == 0) { ncnt = (unsigned)Q; nstart = sj; }
-			else if (lane < 27) {
-				const int nx = cx + c_nb[lane][0], ny = cy + c_nb[lane][1], nz = cz + c_nb[lane][2];
+			if (lane < 27) {
+				const int nx = lx + c_nb[lane][0], ny = ly + c_nb[lane][1], nz = lz + c_nb[lane][2];
 				if (nx >= 0 && nx <= kCellMax && ny >= 0 && ny <= kCellMax && nz >= 0 && nz <= kCellMax) {
+					const unsigned toff = sd[ls].tbl_off, tmask = sd[ls].tbl_mask;
 					const unsigned long long nkey = ((unsigned long long)nz << (2 * kCellBits)) | ((unsigned long long)ny << kCellBits) | (unsigned long long)nx;
 					unsigned h = voxel_hash(nkey) & tmask;
 					for (unsigned probe = 0; probe <= tmask; probe++) {
@@ -365,49 +371,62 @@ __global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const unsi
 					}
 				}
 			}
-			__syncwarp();
+			const unsigned nz_mask = __ballot_sync(kFull, ncnt != 0);
+			if (ncnt) s_rng[warp][vs][__popc(nz_mask & ((1u << lane) - 1u))] = make_uint2(nstart, ncnt);
+			if (lane == 0) s_nr[warp][vs] = (unsigned char)__popc(nz_mask);
+			vs++;
+		}
+		__syncwarp();
 
-			for (int qg = 0; qg < Q; qg += 32) {
-				const int nq = min(32, Q - qg);
-				float4 myq = make_float4(0.f, 0.f, 0.f, 0.f);
-				int mycount = k;                                   // lanes without a query count as done
-				if (lane < nq) { myq = sorted[sj + qg + lane]; mycount = 0; }
-				int fill = 0;
-				bool done = false;
-				for (int c = 0; c < 27 && !done; c++) {
-					const unsigned cc = __shfl_sync(kFull, ncnt, c), cs = __shfl_sync(kFull, nstart, c);
-					unsigned off = 0;
-					while (off < cc) {
-						const int take = min((int)(cc - off), kChunk - fill);
-						for (int t = lane; t < take; t += 32) buf[fill + t] = sorted[cs + off + t];
-						fill += take;
-						off += take;
-						if (fill == kChunk) {
-							__syncwarp();
-							done = count_chunk(buf, fill, nq, myq, mycount, k, thr, lane);
-							fill = 0;
-							__syncwarp();
-							if (done) break;
-						}
-					}
-					if (c == 0 && fill > 0 && !done) {       // the home voxel alone often settles every query
-						__syncwarp();
-						done = count_chunk(buf, fill, nq, myq, mycount, k, thr, lane);
-						fill = 0;
-						__syncwarp();
-					}
+		// ---- 2. private cursors ----
+		int cnt = 0, c = 0, nr = 0;
+		unsigned p = 0, e = 0;
+		if (valid) {
+			nr = s_nr[warp][slot];
+			const uint2 r = s_rng[warp][slot][0];        // the home voxel: never empty, it holds the query itself
+			p = r.x; e = r.x + r.y;
+		}
+		for (int it = 0; it < kLaneIters; it++) {
+			const bool act = valid && cnt < k && c < nr;
+			if (!__any_sync(kFull, act)) break;
+			if (act) {
+				const float4 cd = __ldg(sorted + p);
+				cnt += dist2_ref(q.x, q.y, q.z, cd.x, cd.y, cd.z) <= thr ? 1 : 0;
+				if (++p == e) {
+					if (++c < nr) { const uint2 r = s_rng[warp][slot][c]; p = r.x; e = r.x + r.y; }
 				}
-				if (!done && fill > 0) {
-					__syncwarp();
-					count_chunk(buf, fill, nq, myq, mycount, k, thr, lane);
-					__syncwarp();
-				}
-				const bool kept = lane < nq && mycount >= k;
-				if (lane < nq) keep[__float_as_int(myq.w)] = (uint8_t)(kept ? 1 : 0);
-				const unsigned km = __ballot_sync(kFull, kept);
-				if (lane == 0 && km) atomicAdd(&ctl->n_kept, __popc(km));
 			}
 		}
+
+		// ---- 3. cooperative tail for the undecided lanes ----
+		unsigned rem = __ballot_sync(kFull, valid && cnt < k && c < nr);
+		while (rem) {
+			const int l = __ffs(rem) - 1;
+			rem &= rem - 1;
+			const float qx = __shfl_sync(kFull, q.x, l), qy = __shfl_sync(kFull, q.y, l), qz = __shfl_sync(kFull, q.z, l);
+			const int lslot = __shfl_sync(kFull, slot, l), lnr = __shfl_sync(kFull, nr, l);
+			int lc = __shfl_sync(kFull, c, l), lcnt = __shfl_sync(kFull, cnt, l);
+			unsigned lp = __shfl_sync(kFull, p, l), le = __shfl_sync(kFull, e, l);
+			while (lcnt < k && lc < lnr) {
+				for (unsigned base = lp; base < le && lcnt < k; base += 32) {
+					const unsigned pp = base + lane;
+					bool ok = false;
+					if (pp < le) {
+						const float4 cd = __ldg(sorted + pp);
+						ok = dist2_ref(qx, qy, qz, cd.x, cd.y, cd.z) <= thr;
+					}
+					lcnt += __popc(__ballot_sync(kFull, ok));
+				}
+				if (++lc < lnr) { const uint2 r = s_rng[warp][lslot][lc]; lp = r.x; le = r.x + r.y; }
+			}
+			if (lane == l) cnt = lcnt;
+		}
+
+		const bool kept = valid && cnt >= k;
+		if (valid) keep[__float_as_int(q.w)] = (uint8_t)(kept ? 1 : 0);
+		const unsigned km = __ballot_sync(kFull, kept);
+		if (lane == 0 && km) atomicAdd(&ctl->n_kept, __popc(km));
+		__syncwarp();
 	}
 }
 
@@ -793,12 +812,12 @@ static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n
 	k_voxel_insert<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
 		f->table.as<unsigned long long>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>());
 	stage_mark(f, 3, st);
-	k_cell_ranges<<<(slot_hi - slot_lo + 255) / 256, 256, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(), slot_lo, slot_hi, f->ctl);
+	k_cell_ranges<<<(slot_hi - slot_lo + kRangeThreads - 1) / kRangeThreads, kRangeThreads, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(), slot_lo, slot_hi, f->ctl);
 	k_cell_scatter<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(),
 		f->cell_start.as<unsigned>(), f->ctl, f->sorted.as<float4>());
 	stage_mark(f, 4, st);
-	k_neighbour_count<<<f->sm_count * 6, kCountWarps * 32, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(),
-		f->sorted.as<float4>(), sd, s_first, s_end, f->ctl, f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
+	k_neighbour_count<<<f->sm_count * 8, kCountWarps * 32, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(),
+		f->sorted.as<float4>(), sd, f->culled_starts, s_first, s_end, f->ctl, f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
 	stage_mark(f, 5, st);
 	count_launch(4);
 	if (!cuda_ok(cudaGetLastError(), "filter kernels")) return -1;

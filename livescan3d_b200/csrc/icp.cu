@@ -59,6 +59,9 @@ __device__ __forceinline__ unsigned spread3(unsigned v) {     // 10 bits -> ever
 }
 __device__ __forceinline__ unsigned morton3(unsigned x, unsigned y, unsigned z) { return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2); }
 
+// first entry of level l (1..L) in the child-mask array: sum_{j<l} (G >> j)^3 with G = 2^L
+__device__ __host__ __forceinline__ unsigned icp_mask_off(int L, int l) { return ((1u << (3 * L)) - (1u << (3 * (L - l + 1)))) / 7u; }
+
 __device__ __forceinline__ int icp_cell(float rel, float inv_h, int G) {
 	float u = floorf(rel * inv_h);
 	u = fminf(fmaxf(u, 0.0f), (float)(G - 1));
@@ -106,6 +109,28 @@ __global__ void k_icp_grid_params(const IcpBox *box, IcpGrid *grid, int G, int l
 	grid->inv_h = (float)(1.0 / h);
 	grid->G = G;
 	grid->levels = levels;
+}
+
+// Octree child masks for every level: bit c of masks[mask_off[l] + mp] says whether child c (Morton order) of the
+// level-l node with Morton prefix mp holds any target point.  Morton cell order makes every node a contiguous
+// range of cell_start, so each bit is one subtraction.
+__global__ void __launch_bounds__(256) k_icp_masks(const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, unsigned char *__restrict__ masks, unsigned total) {
+	const IcpGrid g = *grid;
+	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		int l = 1;
+		while (l < g.levels && t >= icp_mask_off(g.levels, l + 1)) l++;
+		const unsigned mp = t - icp_mask_off(g.levels, l);
+		const int sh = 3 * (l - 1);
+		unsigned m = 0;
+		unsigned prev = cell_start[(mp << 3) << sh];
+#pragma unroll
+		for (unsigned c = 0; c < 8; c++) {
+			const unsigned nxt = cell_start[((mp << 3) + c + 1) << sh];
+			if (nxt != prev) m |= 1u << c;
+			prev = nxt;
+		}
+		masks[t] = (unsigned char)m;
+	}
 }
 
 __global__ void __launch_bounds__(256) k_icp_count(const float *__restrict__ v, int n, const IcpGrid *__restrict__ grid,
@@ -318,67 +343,76 @@ __device__ __forceinline__ float box_lb2(float rx, float ry, float rz, float lx,
 	return (dx * dx + dy * dy + dz * dz) * 0.99999f;
 }
 
-__device__ Best nearest_in_grid(const IcpGrid &g, const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted, float qx, float qy, float qz) {
-	Best best;
-	best.d2 = INFINITY;
-	best.idx = -1;
+// Exact nearest neighbour, bottom-up over the implicit octree:
+//   scan the query's home cell, then climb: at every level first ask whether everything outside the subtree
+//   already searched is provably farther than the best so far (distance to the subtree's faces; faces on the
+//   grid boundary have nothing behind them) and stop if so; otherwise search the siblings — a near-first
+//   depth-first walk driven by the 8-bit child masks (empty children cost nothing, non-empty ones one box test)
+//   — and climb one level.  Near queries stop after a level or two, distant ones (points of the source that the
+//   target never saw) climb until their ball fits, so the result is exact at any distance like nanoflann's.
+//   `best` may arrive seeded with a real candidate (the previous iteration's neighbour).
+__device__ __forceinline__ Best nearest_in_grid(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned char *__restrict__ masks,
+	const float4 *__restrict__ sorted, float qx, float qy, float qz, Best best)
+{
 	const float rx = qx - g.ox, ry = qy - g.oy, rz = qz - g.oz;
 	if (!(isfinite(rx) && isfinite(ry) && isfinite(rz))) return best;
 	const float h = g.h, slack = 1e-3f * g.h;
-	const int G = g.G;
-	const int cx = icp_cell(rx, g.inv_h, G), cy = icp_cell(ry, g.inv_h, G), cz = icp_cell(rz, g.inv_h, G);
+	const int G = g.G, L = g.levels;
+	unsigned nx = (unsigned)icp_cell(rx, g.inv_h, G), ny = (unsigned)icp_cell(ry, g.inv_h, G), nz = (unsigned)icp_cell(rz, g.inv_h, G);
+	unsigned mp = morton3(nx, ny, nz);
 	{
-		const unsigned m = morton3(cx, cy, cz);
-		scan_cell(sorted, cell_start[m], cell_start[m + 1], qx, qy, qz, best);
+		const unsigned s = cell_start[mp], e = cell_start[mp + 1];
+		if (s != e) scan_cell(sorted, s, e, qx, qy, qz, best);
 	}
-	for (int dz = -1; dz <= 1; dz++)
-		for (int dy = -1; dy <= 1; dy++)
-			for (int dx = -1; dx <= 1; dx++) {
-				if ((dx | dy | dz) == 0) continue;
-				const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-				if (nx < 0 || ny < 0 || nz < 0 || nx >= G || ny >= G || nz >= G) continue;
-				if (box_lb2(rx, ry, rz, nx * h, ny * h, nz * h, h, slack) > best.d2) continue;
-				const unsigned m = morton3(nx, ny, nz);
-				const unsigned s = cell_start[m], e = cell_start[m + 1];
-				if (s != e) scan_cell(sorted, s, e, qx, qy, qz, best);
-			}
-	// is everything outside the 3x3x3 block provably no closer?
-	float rho = INFINITY;
-	if (cx - 1 > 0) rho = fminf(rho, rx - (cx - 1) * h);
-	if (cx + 2 < G) rho = fminf(rho, (cx + 2) * h - rx);
-	if (cy - 1 > 0) rho = fminf(rho, ry - (cy - 1) * h);
-	if (cy + 2 < G) rho = fminf(rho, (cy + 2) * h - ry);
-	if (cz - 1 > 0) rho = fminf(rho, rz - (cz - 1) * h);
-	if (cz + 2 < G) rho = fminf(rho, (cz + 2) * h - rz);
-	rho = fmaxf(rho - slack, 0.0f);
-	if (best.d2 <= rho * rho * 0.99999f) return best;
+	for (int lvl = 0; lvl < L; lvl++) {
+		// the subtree rooted at (nx,ny,nz)@lvl is done: can anything outside it still be closer?
+		const float size = h * (float)(1u << lvl);
+		const unsigned dim = (unsigned)G >> lvl;
+		float rho = INFINITY;
+		if (nx > 0) rho = fminf(rho, rx - (float)nx * size);
+		if (nx + 1 < dim) rho = fminf(rho, (float)(nx + 1) * size - rx);
+		if (ny > 0) rho = fminf(rho, ry - (float)ny * size);
+		if (ny + 1 < dim) rho = fminf(rho, (float)(ny + 1) * size - ry);
+		if (nz > 0) rho = fminf(rho, rz - (float)nz * size);
+		if (nz + 1 < dim) rho = fminf(rho, (float)(nz + 1) * size - rz);
+		rho = fmaxf(rho - slack, 0.0f);
+		if (best.d2 <= rho * rho * 0.99999f) break;
 
-	// near-first depth-first walk of the implicit octree (Morton order => a node is a contiguous cell range)
-	const int L = g.levels;
-	int level = L;                       // current node is at `level` (cell edge h * 2^level), coordinates n*, Morton prefix mp
-	unsigned nx = 0, ny = 0, nz = 0, mp = 0, ranks = 0;
-	for (;;) {
-		const int sh = 4 * (level - 1);
-		const unsigned r = (ranks >> sh) & 15u;
-		if (r == 8) {
-			if (level == L) break;
-			ranks &= ~(15u << sh);
-			level++;
-			nx >>= 1; ny >>= 1; nz >>= 1; mp >>= 3;
-			continue;
+		// siblings: depth-first from the parent (level lvl+1) with the finished child masked out
+		const int top = lvl + 1;
+		int t = top;
+		unsigned ux = nx >> 1, uy = ny >> 1, uz = nz >> 1, ump = mp >> 3;
+		unsigned long long rem = (unsigned long long)(masks[icp_mask_off(L, t) + ump] & ~(1u << (mp & 7u))) << (8 * (t - 1));
+		for (;;) {
+			const int sh8 = 8 * (t - 1);
+			const unsigned rm = (unsigned)(rem >> sh8) & 0xffu;
+			if (rm == 0) {
+				if (t == top) break;
+				t++;
+				ux >>= 1; uy >>= 1; uz >>= 1; ump >>= 3;
+				continue;
+			}
+			const float half = h * (float)(1u << (t - 1));            // child edge
+			const unsigned near = (rx >= (float)(2 * ux + 1) * half ? 1u : 0u) | (ry >= (float)(2 * uy + 1) * half ? 2u : 0u) | (rz >= (float)(2 * uz + 1) * half ? 4u : 0u);
+			unsigned child = 0;
+#pragma unroll
+			for (int r = 0; r < 8; r++) {
+				child = near ^ ((0x76534210u >> (4 * r)) & 7u);
+				if ((rm >> child) & 1u) break;
+			}
+			rem &= ~(1ull << (sh8 + child));
+			const unsigned ccx = (ux << 1) | (child & 1u), ccy = (uy << 1) | ((child >> 1) & 1u), ccz = (uz << 1) | (child >> 2);
+			if (box_lb2(rx, ry, rz, (float)ccx * half, (float)ccy * half, (float)ccz * half, half, slack) > best.d2) continue;
+			const unsigned cmp = (ump << 3) | child;
+			if (t == 1) {
+				scan_cell(sorted, cell_start[cmp], cell_start[cmp + 1], qx, qy, qz, best);
+			} else {
+				t--;
+				ux = ccx; uy = ccy; uz = ccz; ump = cmp;
+				rem |= (unsigned long long)masks[icp_mask_off(L, t) + ump] << (8 * (t - 1));
+			}
 		}
-		ranks += 1u << sh;
-		const float half = h * (float)(1u << (level - 1));
-		const unsigned near = (rx >= (float)(2 * nx + 1) * half ? 1u : 0u) | (ry >= (float)(2 * ny + 1) * half ? 2u : 0u) | (rz >= (float)(2 * nz + 1) * half ? 4u : 0u);
-		const unsigned child = near ^ ((0x76534210u >> (4 * r)) & 7u);
-		const unsigned ccx = (nx << 1) | (child & 1u), ccy = (ny << 1) | ((child >> 1) & 1u), ccz = (nz << 1) | (child >> 2);
-		const unsigned cmp = (mp << 3) | child;
-		const int csh = 3 * (level - 1);
-		const unsigned s = cell_start[cmp << csh], e = cell_start[(cmp + 1u) << csh];
-		if (s == e) continue;
-		if (box_lb2(rx, ry, rz, ccx * half, ccy * half, ccz * half, half, slack) > best.d2) continue;
-		if (level == 1) scan_cell(sorted, s, e, qx, qy, qz, best);
-		else { level--; nx = ccx; ny = ccy; nz = ccz; mp = cmp; }
+		nx >>= 1; ny >>= 1; nz >>= 1; mp >>= 3;
 	}
 	return best;
 }
@@ -394,8 +428,8 @@ __device__ __forceinline__ void apply_xform(float &x, float &y, float &z, const 
 // apply != 0: first apply the previous iteration's update (from sums_buf) to every source point.
 // search != 0: NN + dedupe for the slice [i_begin, i_end).
 __global__ void __launch_bounds__(256) k_icp_match(float *__restrict__ verts2, int n2, int i_begin, int i_end, int apply, int search,
-	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted,
-	unsigned long long *slots, IcpState *state, const double *__restrict__ sums_buf, Ls3dIcpTrace *trace, int trace_idx,
+	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned char *__restrict__ masks, const float4 *__restrict__ sorted,
+	const float *__restrict__ verts1, unsigned long long *slots, IcpState *state, const double *__restrict__ sums_buf, Ls3dIcpTrace *trace, int trace_idx,
 	int *__restrict__ nn_idx, float *__restrict__ nn_d2)
 {
 	__shared__ float sT[3], sR[9];
@@ -420,7 +454,18 @@ __global__ void __launch_bounds__(256) k_icp_match(float *__restrict__ verts2, i
 			int bi = -1;
 			float bd = 0.0f;
 			if (i >= i_begin && i < i_end) {
-				const Best b = nearest_in_grid(g, cell_start, sorted, x, y, z);
+				// seed with last iteration's neighbour: a real candidate, so exactness is untouched, and the source
+				// barely moves between iterations, so the bound is already nearly tight
+				Best b;
+				b.d2 = INFINITY;
+				b.idx = -1;
+				const int prev = nn_idx[i];
+				if (prev >= 0) {
+					b.idx = prev;
+					b.d2 = dist2_ref(x, y, z, verts1[3 * (size_t)prev], verts1[3 * (size_t)prev + 1], verts1[3 * (size_t)prev + 2]);
+					if (!(b.d2 == b.d2)) { b.d2 = INFINITY; b.idx = -1; }
+				}
+				b = nearest_in_grid(g, cell_start, masks, sorted, x, y, z, b);
 				bi = b.idx; bd = b.d2;
 				if (bi >= 0) {
 					const unsigned long long key = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
@@ -567,7 +612,7 @@ struct Ls3dIcp {
 	int sm_count = 148;
 	const float *d_verts1 = nullptr;
 	float *d_verts2 = nullptr;
-	DevBuf grid, box, state, cell_start, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, trace, small;
+	DevBuf grid, box, state, cell_start, masks, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, trace, small;
 	DevBuf own_v1, own_v2;        // device copies for the host-buffer API
 	float *pin = nullptr;         // pinned read-back: Rt[12] + status[4]
 	cudaGraphExec_t graph = nullptr;
@@ -577,7 +622,7 @@ struct Ls3dIcp {
 
 static void icp_free(Ls3dIcp *c) {
 	if (!c) return;
-	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
+	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->masks, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
 		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->trace, &c->small, &c->own_v1, &c->own_v2};
 	for (DevBuf *b : bufs) b->release();
 	if (c->pin) cudaFreeHost(c->pin);
@@ -626,7 +671,10 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 	const size_t cells = (size_t)c->G * c->G * c->G;
 	const int scan_n = (int)cells + 1;
 	const int scan_tiles = (scan_n + kTile - 1) / kTile;
-	if (!c->cell_start.reserve(4 * (cells + 8), "alloc cell starts") || !c->scan_status.reserve(8 * (size_t)(scan_tiles + 1), "alloc scan status")) return -1;
+	unsigned mask_total = 0;
+	for (int l = 1; l <= c->levels; l++) { const unsigned n = (unsigned)(c->G >> l); mask_total += n * n * n; }
+	if (!c->cell_start.reserve(4 * (cells + 8), "alloc cell starts") || !c->scan_status.reserve(8 * (size_t)(scan_tiles + 1), "alloc scan status") ||
+		!c->masks.reserve(mask_total + 16, "alloc octree masks")) return -1;
 	IcpBox hb;
 	for (int a = 0; a < 3; a++) { hb.mn[a] = 0xffffffffu; hb.mx[a] = 0u; }
 	bool ok = cuda_ok(cudaMemcpyAsync(c->box.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, st), "init bbox") &&
@@ -642,8 +690,9 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 	k_icp_count<<<nb, 256, 0, st>>>(c->d_verts1, n1, c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->cell_of.as<unsigned>(), c->rank_of.as<unsigned>());
 	k_exclusive_scan<<<std::min(scan_tiles, c->sm_count * 8), kScanThreads, 0, st>>>(c->cell_start.as<unsigned>(), scan_n, scan_counter, c->scan_status.as<unsigned long long>(), scan_err);
 	k_icp_scatter<<<nb, 256, 0, st>>>(c->d_verts1, n1, c->cell_of.as<unsigned>(), c->rank_of.as<unsigned>(), c->cell_start.as<unsigned>(), c->sorted.as<float4>());
+	k_icp_masks<<<std::min((mask_total + 255) / 256, (unsigned)c->sm_count * 8), 256, 0, st>>>(c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->masks.as<unsigned char>(), mask_total);
 	k_fill_u64<<<nb, 256, 0, st>>>(c->slots.as<unsigned long long>(), n1, kSlotEmpty);
-	count_launch(6);
+	count_launch(7);
 	return cuda_ok(cudaGetLastError(), "target grid kernels") ? 0 : -1;
 }
 
@@ -657,6 +706,7 @@ extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_beg
 	c->i_end = i_end;
 	c->iter = 0;
 	c->pending = false;
+	if (n2 > 0 && !cuda_ok(cudaMemsetAsync(c->nn_idx.p, 0xff, 4 * (size_t)n2, st), "reset nn index")) return -1;     // no previous neighbour yet
 	Pose12 pose;
 	memcpy(pose.v, R0, 9 * sizeof(float));
 	memcpy(pose.v + 9, t0, 3 * sizeof(float));
@@ -668,7 +718,7 @@ extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_beg
 static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) {
 	const int trace_idx = c->iter - 1;     // the update being applied belongs to the previous iteration
 	k_icp_match<<<pt_blocks(c, std::max(c->n2, 1)), 256, 0, st>>>(c->d_verts2, c->n2, c->i_begin, c->i_end, apply, search,
-		c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->sorted.as<float4>(), c->slots.as<unsigned long long>(), c->state.as<IcpState>(),
+		c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->masks.as<unsigned char>(), c->sorted.as<float4>(), c->d_verts1, c->slots.as<unsigned long long>(), c->state.as<IcpState>(),
 		c->sums_buf.as<double>(), c->trace.as<Ls3dIcpTrace>(), trace_idx, c->nn_idx.as<int>(), c->nn_d2.as<float>());
 	count_launch(1);
 	return cuda_ok(cudaGetLastError(), "k_icp_match") ? 0 : -1;

@@ -72,8 +72,12 @@ __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
 
 // Decoupled look-back (Merrill & Garland): called by ALL 32 lanes of warp 0 of the block that owns `tile`.
 // status[tile] = (flag << 32) | value with flag 0 = nothing yet, 1 = tile aggregate, 2 = inclusive prefix.
-// Returns the exclusive prefix of `tile`.  A bounded spin protects the GPU box from a hang if the protocol
-// were ever broken; it raises kErrScanSpin instead.
+// Returns the exclusive prefix of `tile`.
+// All tiles of these small grids are co-resident and publish their aggregates at about the same time, so a tile
+// usually has to walk all the way back; the walk is therefore 256 predecessors wide per round trip (8 independent
+// loads per lane in flight) instead of the textbook 32, which cuts the dependent L2 round trips 8-fold (ncu:
+// 54 % of the map kernel's stall samples were the block barrier behind this walk).
+// A bounded spin protects the GPU box from a hang if the protocol were ever broken; it raises kErrScanSpin.
 __device__ __forceinline__ unsigned lookback_exclusive(unsigned long long *status, int tile, unsigned aggregate, int *err) {
 	const int lane = threadIdx.x & 31;
 	if (tile == 0) {
@@ -81,26 +85,38 @@ __device__ __forceinline__ unsigned lookback_exclusive(unsigned long long *statu
 		return 0u;
 	}
 	if (lane == 0) st_volatile_u64(status + tile, (1ull << 32) | aggregate);
+	constexpr int kWide = 8;
 	unsigned excl = 0;
 	int idx = tile - 1;
-	for (;;) {
-		const int my = idx - lane;
-		unsigned long long w = 2ull << 32;       // lanes before tile 0 contribute a zero prefix
+	bool done = false;
+	while (!done) {
+		unsigned long long w[kWide];
 		int spins = 0;
 		for (;;) {
-			if (my >= 0) w = ld_volatile_u64(status + my);
-			if (!__any_sync(kFull, (w >> 32) == 0)) break;
+			bool missing = false;
+#pragma unroll
+			for (int u = 0; u < kWide; u++) {
+				const int my = idx - lane - 32 * u;
+				w[u] = my >= 0 ? ld_volatile_u64(status + my) : (2ull << 32);     // before tile 0: a zero prefix
+				missing |= (w[u] >> 32) == 0;
+			}
+			if (!__any_sync(kFull, missing)) break;
 			if (++spins > (1 << 22)) { if (lane == 0) atomicOr(err, kErrScanSpin); break; }
 		}
-		const unsigned flag = (unsigned)(w >> 32), val = (unsigned)w;
-		const unsigned pmask = __ballot_sync(kFull, flag == 2);
-		if (pmask) {
-			const int first = __ffs(pmask) - 1;
-			excl += warp_sum(lane <= first ? val : 0u);
-			break;
+#pragma unroll
+		for (int u = 0; u < kWide; u++) {
+			if (done) break;
+			const unsigned flag = (unsigned)(w[u] >> 32), val = (unsigned)w[u];
+			const unsigned pmask = __ballot_sync(kFull, flag == 2);
+			if (pmask) {
+				const int first = __ffs(pmask) - 1;
+				excl += warp_sum(lane <= first ? val : 0u);
+				done = true;
+			} else {
+				excl += warp_sum(val);
+			}
 		}
-		excl += warp_sum(val);
-		idx -= 32;
+		idx -= 32 * kWide;
 	}
 	if (lane == 0) st_volatile_u64(status + tile, (2ull << 32) | (unsigned long long)(excl + aggregate));
 	return excl;
