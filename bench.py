@@ -271,6 +271,10 @@ def run_ours(args, rank, local_rank, world):
     h_colors = torch.from_numpy(frame["depth_colors"]).pin_memory()
     d_depth, d_colors = h_depth.to(dev), h_colors.to(dev)
     fp = FramePipeline(frame["widths"], frame["heights"])
+    fp.set_params(frame["intr"], frame["wt"], FRAME_BOUNDS, 0, 0.0)                 # one unfiltered run: how many points survive the cull
+    fp.run(d_depth, d_colors)
+    torch.cuda.synchronize()
+    n_culled = int(fp.counts.cpu()[0])
     fp.set_params(frame["intr"], frame["wt"], FRAME_BOUNDS, FILTER_K, FILTER_MAXDIST)
 
     def frame_step():
@@ -301,14 +305,30 @@ def run_ours(args, rank, local_rank, world):
     frame_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e)))
     counts = fp.counts.cpu().numpy()
     assert counts[2] == 0, f"device error flags {counts[2]}"
-    n_final, n_culled = int(counts[0]), int(counts[1])
+    n_final = int(counts[0])
     ms_per_step = frame_ms / args.steps
     value = world * 1000.0 / ms_per_step
     total_launches = int(sum_over_ranks(float(launches)))
 
-    # per-stage pass (events recorded inside the library on the same stream), same K steps, for the roofline
+    # the same frame with the voxel-hash candidate enumeration forced (what ls3d_filter and non-image inputs use)
+    fp.set_filter_mode(1)
+    for _ in range(3):
+        frame_step()
+    torch.cuda.synchronize()
+    hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hash_ms = 0.0
+    for i in range(args.steps):
+        flush.zero_()
+        hs.record(); frame_step(); he.record()
+        torch.cuda.synchronize()
+        hash_ms += hs.elapsed_time(he)
+    hash_ms /= args.steps
+    assert int(fp.counts.cpu()[0]) == n_final
+    fp.set_filter_mode(0)
+
+    # per-stage pass (event pairs recorded inside the library on the same stream), same K steps, for the roofline
     fp.enable_timing(True)
-    stage = np.zeros(7)
+    stage = np.zeros(8)
     for i in range(args.steps):
         flush.zero_()
         frame_step()
@@ -316,18 +336,22 @@ def run_ours(args, rank, local_rank, world):
     fp.enable_timing(False)
     stage /= args.steps
     px = S * W_PX * H_PX
-    names = ["map_cull_compact", "hash_clear", "voxel_insert", "cell_ranges_scatter", "neighbour_count", "filter_compact_merge"]
-    alg_bytes = [5 * px + 16 * n_culled, 0, 16 * n_culled + 8 * n_culled, 16 * n_culled + 16 * n_culled, 16 * n_culled + n_culled, n_culled + 16 * n_final + 4 * n_culled + 16 * n_final]
+    # algorithmic bytes per launch: organized count reads every depth pixel once and writes one flag per pixel;
+    # map/cull/compact reads depth + colour + flag per pixel and writes one 16-byte record per survivor
+    alg = {"organized_neighbour_count": 2 * px + px, "map_cull_compact": 2 * px + px + 3 * n_final + 16 * n_final,
+           "hash_clear": 0, "voxel_insert": 24 * n_culled, "cell_ranges_scatter": 32 * n_culled, "voxel_neighbour_count": 17 * n_culled,
+           "survivor_compact": n_culled + 32 * n_final + 4 * n_culled}
     stages = []
-    for nm, ms, ab in zip(names, stage[:6], alg_bytes):
-        stages.append({"kernel": nm, "ms": float(ms), "share": float(ms / max(stage[6], 1e-9)), "alg_bytes": int(ab),
-                       "gbs": float(ab / max(ms, 1e-9) / 1e6)})
-    dom = int(np.argmax(stage[:6]))
-    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": stages[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": stages[dom]["gbs"] / hbm_peak,
+    for nm, ms in zip(FramePipeline.STAGES[:7], stage[:7]):
+        if ms <= 0:
+            continue
+        stages.append({"kernel": nm, "ms": float(ms), "share": float(ms / max(stage[7], 1e-9)), "alg_bytes": int(alg[nm]), "gbs": float(alg[nm] / ms / 1e6)})
+    dom = max(stages, key=lambda x: x["ms"])
+    whole_alg = 5 * px + 16 * n_final
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak,
                 "traffic": None, "peak_source": peak_src,
-                "note": "dominant kernel is the neighbour count: L2-resident candidates, FP32/LSU-issue bound (see profiles/); the HBM-bound kernel is map_cull_compact",
-                "map_cull_compact": {"achieved": stages[0]["gbs"], "frac": stages[0]["gbs"] / hbm_peak, "alg_bytes": stages[0]["alg_bytes"]},
-                "whole_pipeline": {"alg_bytes": 5 * px + 16 * n_final, "achieved": (5 * px + 16 * n_final) / ms_per_step / 1e6, "frac": (5 * px + 16 * n_final) / ms_per_step / 1e6 / hbm_peak},
+                "note": "neighbour counts work on L2/shared-memory resident candidates (FP32/LSU-issue bound, see profiles/); map_cull_compact is the streaming kernel",
+                "whole_pipeline": {"alg_bytes": whole_alg, "achieved": whole_alg / ms_per_step / 1e6, "frac": whole_alg / ms_per_step / 1e6 / hbm_peak},
                 "stages": stages}
 
     # ------------------------------------------------------------------ frame pipeline, end to end through the C ABI (host buffers)
@@ -474,6 +498,7 @@ def run_ours(args, rank, local_rank, world):
         out = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                "points": {"pixels_per_frame": px, "culled": n_culled, "merged": n_final},
+               "voxel_hash_mode_ms_per_step": hash_ms,
                "e2e": e2e, "gpu_launches": total_launches + icp_launches, "gpu_launches_frame": total_launches, "clocks": clocks,
                "roofline": roofline, "cpu_baseline": cpu_f,
                "icp": {"metric": ICP_METRIC, "value": icp_value, "unit": "Mpts*iter/s", "ms_per_step": icp_ms, "ms_per_iter": icp_ms / ICP_ITERS,

@@ -146,10 +146,21 @@ const int *ls3d_frame_culled_starts(Ls3dFrame *f);    /* device int[n_maps+1]: s
 const int *ls3d_frame_old_to_new(Ls3dFrame *f);       /* device int[n_culled]: culled index -> merged index or -1 */
 const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f);  /* device int[sum w*h]: pixel -> culled vertex index within its sensor, or -1 */
 
-/* Optional per-stage timing for the roofline report: with timing on, ls3d_frame_run records CUDA events between
- * its kernels on the run's stream; ls3d_frame_stage_ms waits for the last run and returns, in milliseconds,
- * [0] clear+map/cull/compact [1] hash clear [2] voxel insert [3] cell ranges+scatter [4] neighbour count
- * [5] survivor compaction (the merge) [6] whole run.  Returns 0/-1. */
+/* How the neighbour count enumerates candidates (results are identical; only speed differs):
+ *   0 auto      : organized (pixel-window) count when every sensor's pose and intrinsics admit its bound, else voxel hash
+ *   1 voxel hash: always the voxel-hash path (also what ls3d_filter uses: it has no image to exploit)
+ *   2 organized : insist on the pixel-window path; ls3d_frame_run fails if it is not applicable.
+ * On the organized path the unfiltered culled cloud is never materialised: ls3d_frame_culled_vertices and
+ * ls3d_frame_old_to_new return NULL after such a run. */
+int ls3d_frame_set_filter_mode(Ls3dFrame *f, int mode);
+
+/* The same switch for the host-buffer entry points (ls3d_frame_pipeline); process-wide, default 0. */
+int ls3d_set_default_filter_mode(int mode);
+
+/* Optional per-stage timing for the roofline report: with timing on, ls3d_frame_run brackets its kernels with CUDA
+ * events on the run's stream; ls3d_frame_stage_ms waits for the last run and returns, in milliseconds (0 = stage
+ * did not run): [0] map/cull/compact [1] hash clear [2] voxel insert [3] cell ranges+scatter [4] voxel-hash neighbour
+ * count [5] survivor compaction [6] organized neighbour count [7] whole run.  Returns 0/-1. */
 void ls3d_frame_enable_timing(Ls3dFrame *f, int on);
 int ls3d_frame_stage_ms(Ls3dFrame *f, float out[8]);
 

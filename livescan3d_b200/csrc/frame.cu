@@ -52,18 +52,59 @@ __device__ __forceinline__ int cell_coord(float x, float o, float inv_h) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1: map + world transform + cull + stable compaction
+// the per-pixel arithmetic, in the reference's evaluation order (createVertices, depthprocessing.cpp:148-162,
+// RotatePoint :109-120).  One definition shared by every kernel that needs a pixel's world position, so the
+// organized neighbour count sees bit-identical coordinates to the ones the cloud carries.
 // ------------------------------------------------------------------------------------------------------
-template <bool kWriteD2V>
-__global__ void __launch_bounds__(kScanThreads) k_map_cull_compact(
-	const uint8_t *__restrict__ depth, const uint8_t *__restrict__ colors, const SensorDesc *__restrict__ sd,
-	int s_first, int s_end, float minX, float minY, float minZ, float maxX, float maxY, float maxZ,
-	FrameCtl *ctl, unsigned long long *status, int *culled_starts,
-	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ d2v)
+struct PixelXform {
+	float cx, cy, fx, fy, t0, t1, t2, r0, r1, r2, r3, r4, r5, r6, r7, r8;
+	float minX, minY, minZ, maxX, maxY, maxZ;
+};
+
+__device__ __forceinline__ PixelXform load_xform(const SensorDesc *__restrict__ sd, int s, const float *b) {
+	PixelXform m;
+	m.cx = sd[s].cx; m.cy = sd[s].cy; m.fx = sd[s].fx; m.fy = sd[s].fy;
+	m.t0 = sd[s].t[0]; m.t1 = sd[s].t[1]; m.t2 = sd[s].t[2];
+	m.r0 = sd[s].R[0]; m.r1 = sd[s].R[1]; m.r2 = sd[s].R[2]; m.r3 = sd[s].R[3]; m.r4 = sd[s].R[4];
+	m.r5 = sd[s].R[5]; m.r6 = sd[s].R[6]; m.r7 = sd[s].R[7]; m.r8 = sd[s].R[8];
+	m.minX = b[0]; m.minY = b[1]; m.minZ = b[2]; m.maxX = b[3]; m.maxY = b[4]; m.maxZ = b[5];
+	return m;
+}
+
+// returns true when the pixel yields a vertex (non-zero depth and inside the strict cull box)
+__device__ __forceinline__ bool map_pixel(const PixelXform &m, int x, int y, unsigned d, float &wx, float &wy, float &wz) {
+	if (d == 0) return false;
+	const float val = (float)d;
+	float Z = __fdiv_rn(val, 1000.0f);
+	float X = __fdiv_rn(__fsub_rn((float)x, m.cx), m.fx);
+	float Y = __fdiv_rn(__fsub_rn(m.cy, (float)y), m.fy);
+	X = __fmul_rn(X, Z);
+	Y = __fmul_rn(Y, Z);
+	X = __fadd_rn(X, m.t0); Y = __fadd_rn(Y, m.t1); Z = __fadd_rn(Z, m.t2);
+	wx = __fadd_rn(__fadd_rn(__fmul_rn(X, m.r0), __fmul_rn(Y, m.r1)), __fmul_rn(Z, m.r2));
+	wy = __fadd_rn(__fadd_rn(__fmul_rn(X, m.r3), __fmul_rn(Y, m.r4)), __fmul_rn(Z, m.r5));
+	wz = __fadd_rn(__fadd_rn(__fmul_rn(X, m.r6), __fmul_rn(Y, m.r7)), __fmul_rn(Z, m.r8));
+	return !(wx < m.minX || wx > m.maxX || wy < m.minY || wy > m.maxY || wz < m.minZ || wz > m.maxZ);
+}
+
+struct Bounds6 { float v[6]; };
+
+// ------------------------------------------------------------------------------------------------------
+// K1: map + world transform + cull (+ optional per-pixel keep mask) + stable compaction
+// ------------------------------------------------------------------------------------------------------
+// Two passes over the thread's 8 pixels: validity first (one bit each), then — once the tile's base is known
+// from the look-back scan — the coordinates are recomputed and the 16-byte records stored straight to their
+// final place.  Recomputing (~40 instructions per pixel) is cheaper than holding 24 coordinates across the scan:
+// the round-1 profile showed 74-80 registers, 3 blocks/SM, two waves and 57 % barrier stalls for the staged
+// version; this one keeps every tile of an 8-sensor frame resident in one wave.
+template <bool kWriteD2V, bool kKeepMask>
+__global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
+	const uint8_t *__restrict__ depth, const uint8_t *__restrict__ colors, const SensorDesc *__restrict__ sd, const unsigned short *__restrict__ tile_sensor,
+	int s_first, int s_end, Bounds6 bnd, FrameCtl *ctl, unsigned long long *status, int *culled_starts,
+	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ d2v, const uint8_t *__restrict__ keep_px, PeerDst peers)
 {
-	__shared__ uint4 stage[kTile];
 	__shared__ unsigned sm[16];
-	__shared__ int s_tile, s_sensor;
+	__shared__ int s_tile;
 
 	const int tile0 = sd[s_first].tile_begin;
 	const int ntiles = sd[s_end].tile_begin - tile0;
@@ -71,103 +112,108 @@ __global__ void __launch_bounds__(kScanThreads) k_map_cull_compact(
 	const int tid = threadIdx.x;
 
 	for (;;) {
-		if (tid == 0) {
-			const int t = (int)atomicAdd(&ctl->tile_counter_a, 1u);
-			s_tile = t;
-			if (t < ntiles) {
-				int s = s_first;
-				while (sd[s + 1].tile_begin <= t + tile0) s++;
-				s_sensor = s;
-			}
-		}
+		if (tid == 0) s_tile = (int)atomicAdd(&ctl->tile_counter_a, 1u);
 		__syncthreads();
 		const int tile = s_tile;
 		if (tile >= ntiles) break;
-		const int s = s_sensor;
+		const int s = tile_sensor[tile + tile0];
 		const int w = sd[s].w, px = sd[s].px;
 		const int p0 = (tile + tile0 - sd[s].tile_begin) * kTile + tid * 8;
 		const int rem = px - p0;
+		const PixelXform m = load_xform(sd, s, bnd.v);
 
-		// ---- loads: 8 u16 depths (one LDG.128), 8 RGB triples (three LDG.64) ----
-		unsigned short dv[8];
+		// ---- 8 u16 depths: one LDG.128 (kept packed in 4 registers) ----
+		uint4 dq = make_uint4(0u, 0u, 0u, 0u);
 		const uint8_t *dp = depth + sd[s].depth_off + 2ll * p0;
 		if (rem >= 8 && (((uintptr_t)dp) & 15) == 0) {
-			const uint4 v = __ldg(reinterpret_cast<const uint4 *>(dp));
-			dv[0] = v.x & 0xffff; dv[1] = v.x >> 16; dv[2] = v.y & 0xffff; dv[3] = v.y >> 16;
-			dv[4] = v.z & 0xffff; dv[5] = v.z >> 16; dv[6] = v.w & 0xffff; dv[7] = v.w >> 16;
+			dq = __ldg(reinterpret_cast<const uint4 *>(dp));
 		} else {
+			unsigned t[8];
 #pragma unroll
-			for (int j = 0; j < 8; j++) dv[j] = (j < rem) ? __ldg(reinterpret_cast<const unsigned short *>(dp) + j) : (unsigned short)0;
+			for (int j = 0; j < 8; j++) t[j] = (j < rem) ? (unsigned)__ldg(reinterpret_cast<const unsigned short *>(dp) + j) : 0u;
+			dq = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
 		}
-		unsigned nz = 0;
+		unsigned keepm = 0xffu;
+		if (kKeepMask) {
+			const uint8_t *kp = keep_px + sd[s].pix_begin + p0;
+			keepm = 0;
+			if (rem >= 8 && (((uintptr_t)kp) & 7) == 0) {
+				const uint2 f = __ldg(reinterpret_cast<const uint2 *>(kp));
 #pragma unroll
-		for (int j = 0; j < 8; j++) nz |= (dv[j] != 0 ? 1u : 0u) << j;
-
-		unsigned cw[6] = {0, 0, 0, 0, 0, 0};     // 24 colour bytes
-		const uint8_t *cp = colors + sd[s].color_off + 3ll * p0;
-		if (nz) {
-			if (rem >= 8 && (((uintptr_t)cp) & 7) == 0) {
-				const uint2 a = __ldg(reinterpret_cast<const uint2 *>(cp));
-				const uint2 b = __ldg(reinterpret_cast<const uint2 *>(cp) + 1);
-				const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cp) + 2);
-				cw[0] = a.x; cw[1] = a.y; cw[2] = b.x; cw[3] = b.y; cw[4] = c.x; cw[5] = c.y;
+				for (int j = 0; j < 4; j++) {
+					if ((f.x >> (8 * j)) & 0xff) keepm |= 1u << j;
+					if ((f.y >> (8 * j)) & 0xff) keepm |= 1u << (4 + j);
+				}
 			} else {
 #pragma unroll
-				for (int j = 0; j < 8; j++)
-					if ((nz >> j) & 1) {
-#pragma unroll
-						for (int c = 0; c < 3; c++) {
-							const int bi = 3 * j + c;
-							cw[bi >> 2] |= (unsigned)__ldg(cp + bi) << (8 * (bi & 3));
-						}
-					}
+				for (int j = 0; j < 8; j++) if (j < rem && __ldg(kp + j)) keepm |= 1u << j;
 			}
 		}
+		auto depth_of = [&](int j) -> unsigned {
+			const unsigned wsel = (j < 4) ? ((j < 2) ? dq.x : dq.y) : ((j < 6) ? dq.z : dq.w);
+			return (j & 1) ? (wsel >> 16) : (wsel & 0xffffu);
+		};
 
-		// ---- per-pixel arithmetic, in the reference's evaluation order (depthprocessing.cpp:148-162) ----
-		const float cx = sd[s].cx, cy = sd[s].cy, fx = sd[s].fx, fy = sd[s].fy;
-		const float t0 = sd[s].t[0], t1 = sd[s].t[1], t2 = sd[s].t[2];
-		const float r0 = sd[s].R[0], r1 = sd[s].R[1], r2 = sd[s].R[2];
-		const float r3 = sd[s].R[3], r4 = sd[s].R[4], r5 = sd[s].R[5];
-		const float r6 = sd[s].R[6], r7 = sd[s].R[7], r8 = sd[s].R[8];
-		int y = p0 / w, x = p0 - y * w;
-		float vx[8], vy[8], vz[8];
+		// ---- pass 1 (rolled: registers, not instructions, are what this kernel is short of): which pixels yield a vertex ----
+		const int y0 = p0 / w, x0 = p0 - y0 * w;
 		unsigned valid = 0;
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			if ((nz >> j) & 1) {
-				const float val = (float)dv[j];
-				float Z = __fdiv_rn(val, 1000.0f);
-				float X = __fdiv_rn(__fsub_rn((float)x, cx), fx);
-				float Y = __fdiv_rn(__fsub_rn(cy, (float)y), fy);
-				X = __fmul_rn(X, Z);
-				Y = __fmul_rn(Y, Z);
-				X = __fadd_rn(X, t0); Y = __fadd_rn(Y, t1); Z = __fadd_rn(Z, t2);
-				const float wx = __fadd_rn(__fadd_rn(__fmul_rn(X, r0), __fmul_rn(Y, r1)), __fmul_rn(Z, r2));
-				const float wy = __fadd_rn(__fadd_rn(__fmul_rn(X, r3), __fmul_rn(Y, r4)), __fmul_rn(Z, r5));
-				const float wz = __fadd_rn(__fadd_rn(__fmul_rn(X, r6), __fmul_rn(Y, r7)), __fmul_rn(Z, r8));
-				const bool outside = wx < minX || wx > maxX || wy < minY || wy > maxY || wz < minZ || wz > maxZ;
-				vx[j] = wx; vy[j] = wy; vz[j] = wz;
-				if (!outside) valid |= 1u << j;
+		{
+			int x = x0, y = y0;
+#pragma unroll 1
+			for (int j = 0; j < 8; j++) {
+				float wx, wy, wz;
+				if (((keepm >> j) & 1) && map_pixel(m, x, y, depth_of(j), wx, wy, wz)) valid |= 1u << j;
+				if (++x == w) { x = 0; y++; }
 			}
-			if (++x == w) { x = 0; y++; }
 		}
 
 		// ---- stable compaction ----
 		const unsigned cnt = __popc(valid);
 		unsigned total, base;
 		const unsigned off = tile_scan(cnt, sm, status, tile, &ctl->err, &total, &base);
-		{
-			unsigned o = off;
+
+		// ---- pass 2: recompute and store the records (24 colour bytes: three LDG.64) ----
+		if (valid) {
+			unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+			const uint8_t *cp = colors + sd[s].color_off + 3ll * p0;
+			if (rem >= 8 && (((uintptr_t)cp) & 7) == 0) {
+				const uint2 a = __ldg(reinterpret_cast<const uint2 *>(cp));
+				const uint2 b = __ldg(reinterpret_cast<const uint2 *>(cp) + 1);
+				const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cp) + 2);
+				c0 = a.x; c1 = a.y; c2 = b.x; c3 = b.y; c4 = c.x; c5 = c.y;
+			} else {
+				unsigned cw[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-			for (int j = 0; j < 8; j++)
-				if ((valid >> j) & 1) {
-					const int bi = 3 * j;
-					// bytes bi, bi+1, bi+2 of the 24-byte colour block -> R,G,B,255
-					const unsigned long long lo = ((unsigned long long)cw[(bi >> 2) + ((bi >> 2) < 5 ? 1 : 0)] << 32) | cw[bi >> 2];
-					const unsigned rgb = (unsigned)(lo >> (8 * (bi & 3))) & 0xffffffu;
-					stage[o++] = make_uint4(rgb | 0xff000000u, __float_as_uint(vx[j]), __float_as_uint(vy[j]), __float_as_uint(vz[j]));
-				}
+				for (int j = 0; j < 8; j++)
+					if ((valid >> j) & 1) {
+#pragma unroll
+						for (int c = 0; c < 3; c++) {
+							const int bi = 3 * j + c;
+							cw[bi >> 2] |= (unsigned)__ldg(cp + bi) << (8 * (bi & 3));
+						}
+					}
+				c0 = cw[0]; c1 = cw[1]; c2 = cw[2]; c3 = cw[3]; c4 = cw[4]; c5 = cw[5];
+			}
+			size_t o = (size_t)out_off + base + off;
+			unsigned rest = valid;
+#pragma unroll 1
+			while (rest) {
+				const int j = __ffs(rest) - 1;
+				rest &= rest - 1;
+				int x = x0 + j, y = y0;
+				while (x >= w) { x -= w; y++; }
+				float wx, wy, wz;
+				map_pixel(m, x, y, depth_of(j), wx, wy, wz);
+				// bytes 3j, 3j+1, 3j+2 of the 24-byte colour block -> R,G,B,255
+				const int bi = 3 * j, wi = bi >> 2;
+				const unsigned lo = wi == 0 ? c0 : wi == 1 ? c1 : wi == 2 ? c2 : wi == 3 ? c3 : wi == 4 ? c4 : c5;
+				const unsigned hi = wi == 0 ? c1 : wi == 1 ? c2 : wi == 2 ? c3 : wi == 3 ? c4 : c5;
+				const unsigned rgb = __funnelshift_r(lo, hi, 8 * (bi & 3)) & 0xffffffu;
+				const uint4 rec = make_uint4(rgb | 0xff000000u, __float_as_uint(wx), __float_as_uint(wy), __float_as_uint(wz));
+				if (peers.n == 0) out[o] = rec;
+				else for (int p = 0; p < peers.n; p++) peers.ptr[p][o] = rec;
+				o++;
+			}
 		}
 		if (kWriteD2V) {
 			int *dst = d2v + sd[s].pix_begin + p0;
@@ -181,10 +227,93 @@ __global__ void __launch_bounds__(kScanThreads) k_map_cull_compact(
 			if (tile == ntiles - 1) { culled_starts[s_end] = (int)(base + total); ctl->n_culled = (int)(base + total); ctl->n_final = (int)(base + total); }
 		}
 		__syncthreads();
-		uint4 *o4 = out + out_off + base;
-		for (unsigned i = tid; i < total; i += kScanThreads) o4[i] = stage[i];
-		__syncthreads();
 	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1o: neighbour count on the ORGANIZED cloud (the depth image is a uniform grid in pixel space)
+// ------------------------------------------------------------------------------------------------------
+// Every point of a sensor's cloud comes from one pixel, so the points that can lie within maxDist of a pixel's
+// point are confined to a window around that pixel: two camera-space points closer than r' project at most
+//     |du| <= fx r' sqrt(1 + xn^2) / (Z - r'),   |dv| <= fy r' sqrt(1 + yn^2) / (Z - r')
+// apart (xn, yn = the pixel's normalised ray, Z its camera depth; r' = (maxDist + fp32 slop) / sigma_min(R) is set
+// on the host so that "world fp32 d2 <= thr" implies "camera distance <= r'").  A block stages the world positions
+// of a 32x8 pixel tile plus an 8-pixel halo in shared memory (NaN where there is no vertex) and every thread counts
+// d2 <= thr over its window, leaving at k; pixels whose window exceeds the halo (very near depth, large radii)
+// walk the window in global memory instead, recomputing candidates from the depth image.  Same fp32 expressions,
+// same count >= k decision as the voxel-hash path and the reference — only the candidate enumeration differs.
+constexpr int kOrgTW = 32, kOrgTH = 8, kOrgHalo = 8;
+constexpr int kOrgSW = kOrgTW + 2 * kOrgHalo, kOrgSH = kOrgTH + 2 * kOrgHalo;
+
+__global__ void __launch_bounds__(kOrgTW * kOrgTH) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
+	int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px)
+{
+	__shared__ float xs[kOrgSH * kOrgSW], ys[kOrgSH * kOrgSW], zs[kOrgSH * kOrgSW];
+	__shared__ unsigned s_kept;
+	const int s = s_first + blockIdx.z;
+	const int w = sd[s].w, h = sd[s].h;
+	const int tx0 = blockIdx.x * kOrgTW, ty0 = blockIdx.y * kOrgTH;
+	if (tx0 >= w || ty0 >= h) return;
+	const PixelXform m = load_xform(sd, s, bnd.v);
+	const unsigned short *dimg = reinterpret_cast<const unsigned short *>(depth + sd[s].depth_off);
+	const int tid = threadIdx.x;
+	if (tid == 0) s_kept = 0;
+
+	for (int i = tid; i < kOrgSH * kOrgSW; i += kOrgTW * kOrgTH) {
+		const int r = i / kOrgSW, c = i - r * kOrgSW;
+		const int gx = tx0 - kOrgHalo + c, gy = ty0 - kOrgHalo + r;
+		float wx = __int_as_float(0x7fc00000), wy = wx, wz = wx;
+		if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+			float ax, ay, az;
+			if (map_pixel(m, gx, gy, (unsigned)__ldg(dimg + (size_t)gy * w + gx), ax, ay, az)) { wx = ax; wy = ay; wz = az; }
+		}
+		xs[i] = wx; ys[i] = wy; zs[i] = wz;
+	}
+	__syncthreads();
+
+	const int lx = tid & (kOrgTW - 1), ly = tid / kOrgTW;
+	const int x = tx0 + lx, y = ty0 + ly;
+	bool kept = false;
+	if (x < w && y < h) {
+		const int ci = (ly + kOrgHalo) * kOrgSW + lx + kOrgHalo;
+		const float qx = xs[ci], qy = ys[ci], qz = zs[ci];
+		if (qx == qx) {                                   // this pixel has a vertex
+			const float rp = sd[s].org_rp;
+			const float zc = (float)__ldg(dimg + (size_t)y * w + x) / 1000.0f;
+			const float xn = ((float)x - m.cx) / m.fx, yn = (m.cy - (float)y) / m.fy;
+			const float den = zc - rp;
+			int ru = 1 << 28, rv = 1 << 28;
+			if (den > 0.0f) {
+				const float fu = fabsf(m.fx) * rp * sqrtf(1.0f + xn * xn) / den * 1.001f + 1e-3f;
+				const float fv = fabsf(m.fy) * rp * sqrtf(1.0f + yn * yn) / den * 1.001f + 1e-3f;
+				if (fu < 1e8f) ru = (int)ceilf(fu);
+				if (fv < 1e8f) rv = (int)ceilf(fv);
+			}
+			int cnt = 0;
+			if (ru <= kOrgHalo && rv <= kOrgHalo) {
+				for (int dy = -rv; dy <= rv && cnt < k; dy++) {
+					const int row = ci + dy * kOrgSW;
+					for (int dx = -ru; dx <= ru; dx++)
+						cnt += dist2_ref(qx, qy, qz, xs[row + dx], ys[row + dx], zs[row + dx]) <= thr ? 1 : 0;
+				}
+			} else {
+				const int xa = max(0, x - min(ru, w)), xb = min(w - 1, x + min(ru, w));
+				const int ya = max(0, y - min(rv, h)), yb = min(h - 1, y + min(rv, h));
+				for (int yy = ya; yy <= yb && cnt < k; yy++)
+					for (int xx = xa; xx <= xb; xx++) {
+						float ax, ay, az;
+						if (map_pixel(m, xx, yy, (unsigned)__ldg(dimg + (size_t)yy * w + xx), ax, ay, az))
+							cnt += dist2_ref(qx, qy, qz, ax, ay, az) <= thr ? 1 : 0;
+					}
+			}
+			kept = cnt >= k;
+		}
+		keep_px[sd[s].pix_begin + (size_t)y * w + x] = (uint8_t)(kept ? 1 : 0);
+	}
+	const unsigned km = __ballot_sync(kFull, kept);
+	if ((tid & 31) == 0 && km) atomicAdd(&s_kept, (unsigned)__popc(km));
+	__syncthreads();
+	if (tid == 0 && s_kept) atomicAdd(&ctl->n_kept, (int)s_kept);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -598,12 +727,17 @@ using namespace ls3d;
 // ======================================================================================================
 // Frame context
 // ======================================================================================================
+// stage slots of the optional timing pass (ls3d_frame_stage_ms)
+enum { kTsMap = 0, kTsHashClear, kTsInsert, kTsRanges, kTsCount, kTsCompact, kTsOrganized, kTsWhole, kTsN };
+enum { kModeAuto = 0, kModeVoxelHash = 1, kModeOrganized = 2 };
+
 struct Ls3dFrame {
 	int device = 0;
 	int S = 0;
 	std::vector<int> w, h;
 	long long total_px = 0;
 	int total_tiles = 0;
+	int max_w = 0, max_h = 0;
 	size_t depth_bytes = 0, color_bytes = 0;
 	unsigned total_slots = 0;
 	std::vector<SensorDesc> h_sd;       // S+1 entries (sentinel last)
@@ -613,10 +747,14 @@ struct Ls3dFrame {
 	float filter_max_dist = 0, filter_thr = 0;
 	bool filter_on = false;
 	bool params_set = false;
+	int filter_mode = kModeAuto;
+	bool organized_ok = false;          // every sensor's pose/intrinsics admit the pixel-window bound
+	bool last_organized = false;        // what the last count stage ran (the merge stage has to match)
+	const void *last_depth = nullptr, *last_colors = nullptr;
 	int sm_count = 148;
 
 	// device memory
-	DevBuf sd, zero, cloud0, sorted, final_, slot_of, rank_of, keep, map, d2v, table, cell_start, in_depth, in_colors, box;
+	DevBuf sd, tile_sensor, zero, cloud0, sorted, final_, slot_of, rank_of, keep, keep_px, map, d2v, table, cell_start, in_depth, in_colors, box;
 	// carve-outs of `zero` (re-zeroed by one memset per run)
 	FrameCtl *ctl = nullptr;
 	unsigned long long *status_a = nullptr, *status_b = nullptr;
@@ -625,35 +763,40 @@ struct Ls3dFrame {
 	// pinned read-back block: FrameCtl + starts
 	int *pin_out = nullptr;
 	bool want_d2v = false;
-	// optional per-stage timing (bench.py's roofline pass): events recorded on the run's stream between kernels
+	// optional per-stage timing (bench.py's roofline pass): a (begin, end) event pair per stage on the run's stream
 	bool timing = false;
-	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-	int ev_recorded = 0;     // bit mask
+	cudaEvent_t ev[kTsN][2] = {};
+	int ev_recorded = 0;     // bit mask of stages with both events recorded
 };
 
-static void stage_mark(Ls3dFrame *f, int i, cudaStream_t st) {
+static void stage_begin(Ls3dFrame *f, int i, cudaStream_t st) {
 	if (!f->timing) return;
-	if (!f->ev[i] && cudaEventCreate(&f->ev[i]) != cudaSuccess) { f->ev[i] = nullptr; return; }
-	if (cudaEventRecord(f->ev[i], st) == cudaSuccess) f->ev_recorded |= 1 << i;
+	for (int j = 0; j < 2; j++)
+		if (!f->ev[i][j] && cudaEventCreate(&f->ev[i][j]) != cudaSuccess) { f->ev[i][j] = nullptr; return; }
+	cudaEventRecord(f->ev[i][0], st);
+}
+static void stage_end(Ls3dFrame *f, int i, cudaStream_t st) {
+	if (!f->timing || !f->ev[i][1]) return;
+	if (cudaEventRecord(f->ev[i][1], st) == cudaSuccess) f->ev_recorded |= 1 << i;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static void frame_free(Ls3dFrame *f) {
 	if (!f) return;
-	DevBuf *bufs[] = {&f->sd, &f->zero, &f->cloud0, &f->sorted, &f->final_, &f->slot_of, &f->rank_of, &f->keep, &f->map, &f->d2v,
+	DevBuf *bufs[] = {&f->sd, &f->tile_sensor, &f->zero, &f->cloud0, &f->sorted, &f->final_, &f->slot_of, &f->rank_of, &f->keep, &f->keep_px, &f->map, &f->d2v,
 		&f->table, &f->cell_start, &f->in_depth, &f->in_colors, &f->box};
 	for (DevBuf *b : bufs) b->release();
 	if (f->pin_sd) cudaFreeHost(f->pin_sd);
 	if (f->pin_out) cudaFreeHost(f->pin_out);
-	for (cudaEvent_t e : f->ev) if (e) cudaEventDestroy(e);
+	for (auto &e : f->ev) for (cudaEvent_t x : e) if (x) cudaEventDestroy(x);
 	delete f;
 }
 
 extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int *heights) {
 	clear_error();
 	if (!ensure_device()) return nullptr;
-	if (n_maps <= 0 || !widths || !heights) { set_error("ls3d_frame_create: n_maps must be positive"); return nullptr; }
+	if (n_maps <= 0 || n_maps > 65535 || !widths || !heights) { set_error("ls3d_frame_create: n_maps must be in 1..65535"); return nullptr; }
 	Ls3dFrame *f = new Ls3dFrame();
 	cudaGetDevice(&f->device);
 	cudaDeviceGetAttribute(&f->sm_count, cudaDevAttrMultiProcessorCount, f->device);
@@ -664,6 +807,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 	long long px_acc = 0, depth_off = 0, color_off = 0;
 	int tile_acc = 0;
 	unsigned long long slot_acc = 0;
+	std::vector<unsigned short> tile_sensor;
 	for (int i = 0; i <= n_maps; i++) {
 		SensorDesc &d = f->h_sd[i];
 		memset(&d, 0, sizeof(d));
@@ -680,6 +824,8 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		}
 		const long long px = (long long)widths[i] * heights[i];
 		d.w = widths[i]; d.h = heights[i]; d.px = (int)px;
+		f->max_w = std::max(f->max_w, d.w);
+		f->max_h = std::max(f->max_h, d.h);
 		unsigned long long cap = 64;
 		while (cap < (unsigned long long)px * 3 / 2) cap <<= 1;
 		d.tbl_mask = (unsigned)(cap - 1);
@@ -687,7 +833,9 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		px_acc += px;
 		depth_off += px * 2;
 		color_off += px * 3;
-		tile_acc += (int)((px + kTile - 1) / kTile);
+		const int nt = (int)((px + kTile - 1) / kTile);
+		tile_sensor.insert(tile_sensor.end(), nt, (unsigned short)i);
+		tile_acc += nt;
 	}
 	if (px_acc >= (1ll << 31) - kTile || slot_acc >= (1ull << 32)) { set_error("ls3d_frame_create: frame too large"); delete f; return nullptr; }
 	f->total_px = px_acc;
@@ -702,13 +850,16 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 	const size_t starts_b = align_up(sizeof(int) * (size_t)(n_maps + 1), 256);
 	f->zero_bytes = ctl_b + 2 * st_b + 2 * starts_b;
 	bool ok = f->sd.reserve(sizeof(SensorDesc) * (n_maps + 1), "alloc descriptors") && f->zero.reserve(f->zero_bytes, "alloc control block") &&
+		f->tile_sensor.reserve(sizeof(unsigned short) * (tile_sensor.size() + 1), "alloc tile table") &&
 		f->cloud0.reserve(16 * n, "alloc culled cloud") && f->sorted.reserve(16 * n, "alloc sorted cloud") && f->final_.reserve(16 * n, "alloc merged cloud") &&
 		f->slot_of.reserve(4 * n, "alloc slots") && f->rank_of.reserve(4 * n, "alloc ranks") && f->keep.reserve(align_up(n, 16) + 16, "alloc keep flags") &&
+		f->keep_px.reserve(align_up(n, 16) + 16, "alloc pixel keep flags") &&
 		f->map.reserve(4 * n, "alloc index map") && f->d2v.reserve(4 * n, "alloc pixel map") &&
 		f->table.reserve(8 * (size_t)f->total_slots, "alloc voxel hash") && f->cell_start.reserve(4 * (size_t)f->total_slots, "alloc voxel ranges") &&
 		f->box.reserve(sizeof(FilterBox), "alloc bbox");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_sd, sizeof(SensorDesc) * (n_maps + 1), cudaHostAllocDefault), "alloc pinned descriptors");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_out, sizeof(int) * (size_t)(16 + 2 * (n_maps + 1)), cudaHostAllocDefault), "alloc pinned read-back");
+	ok = ok && cuda_ok(cudaMemcpy(f->tile_sensor.p, tile_sensor.data(), sizeof(unsigned short) * tile_sensor.size(), cudaMemcpyHostToDevice), "upload tile table");
 	if (!ok) { frame_free(f); return nullptr; }
 	uint8_t *z = f->zero.as<uint8_t>();
 	f->ctl = reinterpret_cast<FrameCtl *>(z);
@@ -749,6 +900,31 @@ static void sensor_world_bounds(const SensorDesc &d, const float *b, double lo[3
 	}
 }
 
+// smallest singular value of a row-major 3x3 (Jacobi on R^T R, fp64)
+static double sigma_min3(const float *R) {
+	double A[3][3];
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) {
+			double s = 0;
+			for (int k = 0; k < 3; k++) s += (double)R[3 * k + i] * (double)R[3 * k + j];
+			A[i][j] = s;
+		}
+	for (int sweep = 0; sweep < 40; sweep++) {
+		const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+		if (!(off > 1e-300)) break;
+		for (int p = 0; p < 2; p++)
+			for (int q = p + 1; q < 3; q++) {
+				if (fabs(A[p][q]) < 1e-300) continue;
+				const double th = 0.5 * atan2(2 * A[p][q], A[q][q] - A[p][p]);
+				const double c = cos(th), sn = sin(th);
+				for (int k = 0; k < 3; k++) { const double a = A[k][p], b2 = A[k][q]; A[k][p] = c * a - sn * b2; A[k][q] = sn * a + c * b2; }
+				for (int k = 0; k < 3; k++) { const double a = A[p][k], b2 = A[q][k]; A[p][k] = c * a - sn * b2; A[q][k] = sn * a + c * b2; }
+			}
+	}
+	const double e = fmin(A[0][0], fmin(A[1][1], A[2][2]));
+	return (e > 0 && e == e) ? sqrt(e) : 0.0;
+}
+
 // n_set: how many leading sensors intr_params / wtransform_params describe (<= f->S)
 static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, const float *wtransform_params,
 	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int filter_k, float filter_maxDist, void *stream)
@@ -759,6 +935,7 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 	f->filter_k = filter_k;
 	f->filter_max_dist = filter_maxDist;
 	f->filter_thr = (float)pow((double)filter_maxDist, 2.0);  // filter.cpp:52: float = pow(float, int)
+	f->organized_ok = f->filter_on;
 	for (int i = 0; i < n_set && i < f->S; i++) {
 		SensorDesc &d = f->h_sd[i];
 		const float *ip = intr_params + 7 * i;                 // IntrinsicCameraParameters(float*), depthprocessing.h:96-97
@@ -766,12 +943,23 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 		const float *tp = wtransform_params + 12 * i;          // WorldTranformation(float*), depthprocessing.h:56-63
 		memcpy(d.t, tp, 3 * sizeof(float));
 		memcpy(d.R, tp + 3, 9 * sizeof(float));
+		d.org_rp = 0.0f;
 		if (f->filter_on) {
 			double lo[3], hi[3];
 			sensor_world_bounds(d, f->bounds, lo, hi);
 			float o[3];
 			voxel_grid_params(lo, hi, (double)filter_maxDist, o, &d.ginv_h);
 			d.gox = o[0]; d.goy = o[1]; d.goz = o[2];
+			// organized path: world fp32 d2 <= thr  ==>  camera-space distance <= r'
+			//   true world distance <= sqrt(thr)(1+1e-6); fp32 world coordinates carry <= ~4e-6 * |coordinate| of rounding;
+			//   |R(a-b)| >= sigma_min |a-b|
+			double mag = 0;
+			for (int a = 0; a < 3; a++) mag = fmax(mag, fmax(fabs(lo[a]), fabs(hi[a])));
+			const double smin = sigma_min3(d.R);
+			const double rp = (sqrt((double)f->filter_thr) * (1.0 + 1e-5) + 4e-6 * mag) / smin * (1.0 + 1e-4);
+			const bool fin = std::isfinite(d.fx) && std::isfinite(d.fy) && std::isfinite(d.cx) && std::isfinite(d.cy) && d.fx != 0.0f && d.fy != 0.0f;
+			if (smin > 1e-3 && mag < 1e6 && fin && std::isfinite(rp) && rp > 0) d.org_rp = (float)rp;
+			else f->organized_ok = false;
 		}
 	}
 	memcpy(f->pin_sd, f->h_sd.data(), sizeof(SensorDesc) * (f->S + 1));
@@ -786,6 +974,12 @@ extern "C" int ls3d_frame_set_params(Ls3dFrame *f, const float *intr_params, con
 	return frame_set_params(f, f ? f->S : 0, intr_params, wtransform_params, minX, minY, minZ, maxX, maxY, maxZ, filter_k, filter_maxDist, stream);
 }
 
+extern "C" int ls3d_frame_set_filter_mode(Ls3dFrame *f, int mode) {
+	if (!f || mode < kModeAuto || mode > kModeOrganized) { set_error("ls3d_frame_set_filter_mode: mode must be 0 (auto), 1 (voxel hash) or 2 (organized)"); return -1; }
+	f->filter_mode = mode;
+	return 0;
+}
+
 enum { kStageCount = 1, kStageMerge = 2 };
 
 __global__ void __launch_bounds__(256) k_keep_all(uint8_t *keep, FrameCtl *ctl) {
@@ -794,83 +988,136 @@ __global__ void __launch_bounds__(256) k_keep_all(uint8_t *keep, FrameCtl *ctl) 
 	if (blockIdx.x == 0 && threadIdx.x == 0) ctl->n_kept = N;
 }
 
+// K1 launcher.  keep_px != nullptr: AND the organized neighbour-count mask into the validity test.
+static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, int s_first, int s_end, uint4 *out, const int *d_off,
+	const uint8_t *keep_px, const PeerDst &peers, cudaStream_t st)
+{
+	const int ntiles = f->h_sd[s_end].tile_begin - f->h_sd[s_first].tile_begin;
+	const int blocks = std::max(1, std::min(ntiles, f->sm_count * 8));
+	Bounds6 b;
+	memcpy(b.v, f->bounds, sizeof(b.v));
+	const uint8_t *dd = (const uint8_t *)d_depth, *dc = (const uint8_t *)d_colors;
+	const SensorDesc *sd = f->sd.as<SensorDesc>();
+	const unsigned short *ts = f->tile_sensor.as<unsigned short>();
+	stage_begin(f, kTsMap, st);
+	if (f->want_d2v) {
+		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, peers);
+		else k_map_cull_compact<true, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, peers);
+	} else {
+		if (keep_px) k_map_cull_compact<false, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, peers);
+		else k_map_cull_compact<false, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, peers);
+	}
+	stage_end(f, kTsMap, st);
+	count_launch(1);
+	return cuda_ok(cudaGetLastError(), "k_map_cull_compact") ? 1 : -1;
+}
+
 static int frame_merge_stage(Ls3dFrame *f, int s_first, int s_end, long long n_max, uint4 *dst, const int *d_dst_offset, const PeerDst &peers, cudaStream_t st) {
 	const int tiles = (int)((n_max + kTile - 1) / kTile);
+	stage_begin(f, kTsCompact, st);
 	k_filter_compact<<<std::max(1, std::min(tiles, f->sm_count * 6)), kScanThreads, 0, st>>>(f->cloud0.as<uint4>(), f->keep.as<uint8_t>(),
 		f->culled_starts, s_first, s_end, f->ctl, f->status_b, f->final_starts, dst, d_dst_offset, f->map.as<int>(), peers);
+	stage_end(f, kTsCompact, st);
 	count_launch(1);
-	stage_mark(f, 6, st);
 	return cuda_ok(cudaGetLastError(), "k_filter_compact") ? 1 : -1;
 }
 
+// voxel-hash neighbour count on the culled cloud in cloud0 (4 kernels), optionally followed by the compaction
 static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n_max, uint4 *dst, const int *d_dst_offset, const PeerDst &peers, cudaStream_t st, int stages = kStageCount | kStageMerge) {
 	const SensorDesc *sd = f->sd.as<SensorDesc>();
 	const unsigned slot_lo = f->h_sd[s_first].tbl_off, slot_hi = f->h_sd[s_end].tbl_off;
+	stage_begin(f, kTsHashClear, st);
 	if (!cuda_ok(cudaMemsetAsync(f->table.as<unsigned long long>() + slot_lo, 0, 8 * (size_t)(slot_hi - slot_lo), st), "clear voxel hash")) return -1;
+	stage_end(f, kTsHashClear, st);
 	const int pt_blocks = (int)std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8);
-	stage_mark(f, 2, st);
+	stage_begin(f, kTsInsert, st);
 	k_voxel_insert<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
 		f->table.as<unsigned long long>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>());
-	stage_mark(f, 3, st);
+	stage_end(f, kTsInsert, st);
+	stage_begin(f, kTsRanges, st);
 	k_cell_ranges<<<(slot_hi - slot_lo + kRangeThreads - 1) / kRangeThreads, kRangeThreads, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(), slot_lo, slot_hi, f->ctl);
 	k_cell_scatter<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(),
 		f->cell_start.as<unsigned>(), f->ctl, f->sorted.as<float4>());
-	stage_mark(f, 4, st);
+	stage_end(f, kTsRanges, st);
+	stage_begin(f, kTsCount, st);
 	k_neighbour_count<<<f->sm_count * 8, kCountWarps * 32, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(),
 		f->sorted.as<float4>(), sd, f->culled_starts, s_first, s_end, f->ctl, f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
-	stage_mark(f, 5, st);
+	stage_end(f, kTsCount, st);
 	count_launch(4);
 	if (!cuda_ok(cudaGetLastError(), "filter kernels")) return -1;
 	if (!(stages & kStageMerge)) return 4;
 	return frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st) < 0 ? -1 : 5;
 }
 
-// stages: kStageCount runs map/cull (+ the filter through the neighbour count); kStageMerge runs the final
-// compaction.  `split` forces the culled cloud to stay local so a later kStageMerge call can place it.
+// stages: kStageCount = everything up to the survivor decision (n_kept known on the device); kStageMerge = the
+// final compaction that places the survivors.  Both together is the normal single-GPU run; the multi-GPU merge
+// runs them separately with the count exchange in between.
 static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_colors, int first_map, int n_run,
 	uint4 *dst, const int *d_dst_offset, const PeerDst &peers, cudaStream_t st, int stages = kStageCount | kStageMerge)
 {
 	if (!f) { set_error("ls3d_frame_run: null frame"); return -1; }
-	if (stages == kStageMerge) {
-		if (n_run <= 0) { first_map = 0; n_run = f->S; }
-		if (first_map < 0 || first_map + n_run > f->S) { set_error("ls3d_frame_merge: sensor range outside 0..%d", f->S); return -1; }
-		const long long n_max = f->h_sd[first_map + n_run].pix_begin - f->h_sd[first_map].pix_begin;
-		return frame_merge_stage(f, first_map, first_map + n_run, n_max, dst, d_dst_offset, peers, st);
-	}
-	const bool split = !(stages & kStageMerge);
-	if (!d_depth || !d_colors) { set_error("ls3d_frame_run: null argument"); return -1; }
 	if (!f->params_set) { set_error("ls3d_frame_run: ls3d_frame_set_params has not been called"); return -1; }
 	if (n_run <= 0) { first_map = 0; n_run = f->S; }
 	if (first_map < 0 || first_map + n_run > f->S) { set_error("ls3d_frame_run: sensor range [%d,%d) outside 0..%d", first_map, first_map + n_run, f->S); return -1; }
 	const int s_first = first_map, s_end = first_map + n_run;
-	f->ev_recorded = 0;
-	stage_mark(f, 0, st);
-	if (!cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block")) return -1;
-	const int ntiles = f->h_sd[s_end].tile_begin - f->h_sd[s_first].tile_begin;
 	const long long n_max = f->h_sd[s_end].pix_begin - f->h_sd[s_first].pix_begin;
-	const int blocks = std::max(1, std::min(ntiles, f->sm_count * 6));
-	const float *b = f->bounds;
-	uint4 *k1_out = (f->filter_on || split) ? f->cloud0.as<uint4>() : dst;
-	const int *k1_off = (f->filter_on || split) ? nullptr : d_dst_offset;
-	if (f->want_d2v)
-		k_map_cull_compact<true><<<blocks, kScanThreads, 0, st>>>((const uint8_t *)d_depth, (const uint8_t *)d_colors, f->sd.as<SensorDesc>(), s_first, s_end,
-			b[0], b[1], b[2], b[3], b[4], b[5], f->ctl, f->status_a, f->culled_starts, k1_out, k1_off, f->d2v.as<int>());
-	else
-		k_map_cull_compact<false><<<blocks, kScanThreads, 0, st>>>((const uint8_t *)d_depth, (const uint8_t *)d_colors, f->sd.as<SensorDesc>(), s_first, s_end,
-			b[0], b[1], b[2], b[3], b[4], b[5], f->ctl, f->status_a, f->culled_starts, k1_out, k1_off, nullptr);
-	count_launch(1);
-	stage_mark(f, 1, st);
-	if (!cuda_ok(cudaGetLastError(), "k_map_cull_compact")) return -1;
-	int launched = 1;
-	if (f->filter_on) {
-		const int r = frame_filter_stages(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st, stages);
+	const PeerDst none = PeerDst{0, {}};
+	int launched = 0;
+
+	if (stages & kStageCount) {
+		if (!d_depth || !d_colors) { set_error("ls3d_frame_run: null argument"); return -1; }
+		if (f->filter_mode == kModeOrganized && f->filter_on && !f->organized_ok) {
+			set_error("ls3d_frame_run: organized filter mode requested but a sensor's pose/intrinsics do not admit the pixel-window bound");
+			return -1;
+		}
+		const bool organized = f->filter_on && f->organized_ok && f->filter_mode != kModeVoxelHash;
+		f->last_organized = organized;
+		f->last_depth = d_depth;
+		f->last_colors = d_colors;
+		f->ev_recorded = 0;
+		stage_begin(f, kTsWhole, st);
+		if (!cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block")) return -1;
+		if (organized) {
+			// K1o: per-pixel survivor mask straight from the depth images; the cloud is only materialised by the merge stage
+			Bounds6 b;
+			memcpy(b.v, f->bounds, sizeof(b.v));
+			int mw = 0, mh = 0;
+			for (int i = s_first; i < s_end; i++) { mw = std::max(mw, f->w[i]); mh = std::max(mh, f->h[i]); }
+			const dim3 grid((mw + kOrgTW - 1) / kOrgTW, (mh + kOrgTH - 1) / kOrgTH, n_run);
+			stage_begin(f, kTsOrganized, st);
+			k_organized_count<<<grid, kOrgTW * kOrgTH, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), s_first, b, f->ctl, f->filter_k, f->filter_thr, f->keep_px.as<uint8_t>());
+			stage_end(f, kTsOrganized, st);
+			count_launch(1);
+			if (!cuda_ok(cudaGetLastError(), "k_organized_count")) return -1;
+			launched += 1;
+		} else if (f->filter_on) {
+			if (launch_map(f, d_depth, d_colors, s_first, s_end, f->cloud0.as<uint4>(), nullptr, nullptr, none, st) < 0) return -1;
+			const int r = frame_filter_stages(f, s_first, s_end, n_max, nullptr, nullptr, none, st, kStageCount);
+			if (r < 0) return -1;
+			launched += 1 + r;
+		} else if (!(stages & kStageMerge)) {
+			// no filter, split run: keep the culled cloud local and mark everything as kept
+			if (launch_map(f, d_depth, d_colors, s_first, s_end, f->cloud0.as<uint4>(), nullptr, nullptr, none, st) < 0) return -1;
+			k_keep_all<<<(int)std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8), 256, 0, st>>>(f->keep.as<uint8_t>(), f->ctl);
+			count_launch(1);
+			if (!cuda_ok(cudaGetLastError(), "k_keep_all")) return -1;
+			launched += 2;
+		}
+	}
+	if (stages & kStageMerge) {
+		if (!dst && peers.n == 0) { set_error("ls3d_frame_run: no destination buffer"); return -1; }
+		int r;
+		if (f->filter_on && f->last_organized) {
+			if (!f->last_depth) { set_error("ls3d_frame_merge: no count stage has run"); return -1; }
+			r = launch_map(f, f->last_depth, f->last_colors, s_first, s_end, dst, d_dst_offset, f->keep_px.as<uint8_t>(), peers, st);
+		} else if (f->filter_on || !(stages & kStageCount)) {
+			r = frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st);
+		} else {
+			r = launch_map(f, d_depth, d_colors, s_first, s_end, dst, d_dst_offset, nullptr, peers, st);     // no filter: K1 writes the result directly
+		}
 		if (r < 0) return -1;
 		launched += r;
-	} else if (split) {
-		k_keep_all<<<(int)std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8), 256, 0, st>>>(f->keep.as<uint8_t>(), f->ctl);
-		count_launch(1);
-		if (!cuda_ok(cudaGetLastError(), "k_keep_all")) return -1;
-		launched += 1;
+		stage_end(f, kTsWhole, st);
 	}
 	return launched;
 }
@@ -904,7 +1151,6 @@ extern "C" int ls3d_frame_merge_peers(Ls3dFrame *f, int first_map, int n_run, in
 extern "C" int ls3d_frame_run_peers(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run,
 	int n_peers, void *const *peer_dst_vertices, const int *d_dst_offset, void *stream) {
 	if (!f || !peer_dst_vertices || n_peers <= 0 || n_peers > kMaxPeers) { set_error("ls3d_frame_run_peers: need 1..%d destination buffers", kMaxPeers); return -1; }
-	if (!f->filter_on) { set_error("ls3d_frame_run_peers: the peer-store merge is fused into the filter compaction; enable the filter"); return -1; }
 	PeerDst peers;
 	peers.n = n_peers;
 	for (int i = 0; i < kMaxPeers; i++) peers.ptr[i] = i < n_peers ? (uint4 *)peer_dst_vertices[i] : nullptr;
@@ -913,28 +1159,29 @@ extern "C" int ls3d_frame_run_peers(Ls3dFrame *f, const void *d_depth_maps, cons
 
 extern "C" void ls3d_frame_enable_timing(Ls3dFrame *f, int on) { if (f) f->timing = on != 0; }
 
-// Stage durations of the last ls3d_frame_run (milliseconds; waits for it to finish):
-//   [0] control-block clear + map/cull/compact   [1] hash clear   [2] voxel insert   [3] cell ranges + scatter
-//   [4] neighbour count   [5] survivor compaction / merge   [6] whole run   [7] unused
+// Stage durations of the last ls3d_frame_run (milliseconds; waits for it to finish); stages that did not run are 0:
+//   [0] map/cull/compact (K1)  [1] hash clear  [2] voxel insert  [3] cell ranges + scatter  [4] voxel-hash neighbour count
+//   [5] survivor compaction    [6] organized neighbour count (K1o)   [7] whole run incl. the control-block clear
 extern "C" int ls3d_frame_stage_ms(Ls3dFrame *f, float *out) {
 	if (!f || !out) { set_error("ls3d_frame_stage_ms: null argument"); return -1; }
-	for (int i = 0; i < 8; i++) out[i] = 0.0f;
-	int last = -1;
-	for (int i = 0; i < 7; i++) if (f->ev_recorded & (1 << i)) last = i;
-	if (last < 1 || !(f->ev_recorded & 1)) { set_error("ls3d_frame_stage_ms: no timed run (call ls3d_frame_enable_timing first)"); return -1; }
-	if (!cuda_ok(cudaEventSynchronize(f->ev[last]), "stage timing")) return -1;
-	for (int i = 1; i <= last; i++)
-		if ((f->ev_recorded & (1 << i)) && (f->ev_recorded & (1 << (i - 1)))) cudaEventElapsedTime(&out[i - 1], f->ev[i - 1], f->ev[i]);
-	cudaEventElapsedTime(&out[6], f->ev[0], f->ev[last]);
+	for (int i = 0; i < kTsN; i++) out[i] = 0.0f;
+	if (!(f->ev_recorded & (1 << kTsWhole))) { set_error("ls3d_frame_stage_ms: no timed run (call ls3d_frame_enable_timing first)"); return -1; }
+	if (!cuda_ok(cudaEventSynchronize(f->ev[kTsWhole][1]), "stage timing")) return -1;
+	for (int i = 0; i < kTsN; i++)
+		if (f->ev_recorded & (1 << i)) cudaEventElapsedTime(&out[i], f->ev[i][0], f->ev[i][1]);
 	return 0;
 }
 
 extern "C" const void *ls3d_frame_vertices(Ls3dFrame *f) { return f ? f->final_.p : nullptr; }
-extern "C" const void *ls3d_frame_culled_vertices(Ls3dFrame *f) { return f ? (f->filter_on ? f->cloud0.p : f->final_.p) : nullptr; }
+extern "C" const void *ls3d_frame_culled_vertices(Ls3dFrame *f) {
+	if (!f) return nullptr;
+	if (!f->filter_on) return f->final_.p;
+	return f->last_organized ? nullptr : f->cloud0.p;      // the organized path never materialises the unfiltered cloud
+}
 extern "C" const int *ls3d_frame_count_ptr(Ls3dFrame *f) { return f ? &f->ctl->n_final : nullptr; }
-extern "C" const int *ls3d_frame_sensor_starts(Ls3dFrame *f) { return f ? (f->filter_on ? f->final_starts : f->culled_starts) : nullptr; }
+extern "C" const int *ls3d_frame_sensor_starts(Ls3dFrame *f) { return f ? ((f->filter_on && !f->last_organized) ? f->final_starts : f->culled_starts) : nullptr; }
 extern "C" const int *ls3d_frame_culled_starts(Ls3dFrame *f) { return f ? f->culled_starts : nullptr; }
-extern "C" const int *ls3d_frame_old_to_new(Ls3dFrame *f) { return f ? f->map.as<int>() : nullptr; }
+extern "C" const int *ls3d_frame_old_to_new(Ls3dFrame *f) { return (f && !(f->filter_on && f->last_organized)) ? f->map.as<int>() : nullptr; }
 extern "C" const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f) {
 	if (!f) return nullptr;
 	f->want_d2v = true;      // produced from the next run on
@@ -945,6 +1192,13 @@ extern "C" const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f) {
 // Host-buffer (drop-in) entry points
 // ======================================================================================================
 static Ls3dFrame *g_frame = nullptr;     // cached context for the host-buffer API, keyed by the size list
+static int g_default_filter_mode = kModeAuto;
+
+extern "C" int ls3d_set_default_filter_mode(int mode) {
+	if (mode < kModeAuto || mode > kModeOrganized) { set_error("ls3d_set_default_filter_mode: mode must be 0, 1 or 2"); return -1; }
+	g_default_filter_mode = mode;
+	return 0;
+}
 
 static Ls3dFrame *cached_frame(int n_maps, const int *widths, const int *heights) {
 	// a context built for a longer size list serves any prefix of it (generateVerticesFromDepthMap is called once
@@ -987,6 +1241,7 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 	const SensorDesc &a = f->h_sd[first], &z = f->h_sd[first + n_run];
 	if (!cuda_ok(cudaMemcpyAsync(f->in_depth.as<uint8_t>() + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off), cudaMemcpyHostToDevice, st), "upload depth")) return -1;
 	if (!cuda_ok(cudaMemcpyAsync(f->in_colors.as<uint8_t>() + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off), cudaMemcpyHostToDevice, st), "upload colours")) return -1;
+	f->filter_mode = g_default_filter_mode;
 	if (frame_set_params(f, n_maps, intr_params, wtransform_params, bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5], filter_k, filter_maxDist, st) < 0) return -1;
 	if (ls3d_frame_run(f, f->in_depth.p, f->in_colors.p, first, n_run, st) < 0) return -1;
 	// read back the counts, then exactly the bytes that exist

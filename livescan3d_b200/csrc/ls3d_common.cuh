@@ -35,7 +35,8 @@ struct alignas(16) SensorDesc {
 	float R[9];                         // WorldTranformation.R, row-major
 	float gox, goy, goz, ginv_h;        // voxel-hash origin and 1/cell edge for the neighbour-count filter
 	unsigned tbl_off, tbl_mask;         // this sensor's region of the voxel hash table (power-of-two capacity)
-	int pad0, pad1;
+	float org_rp;                       // organized neighbour count: camera-space radius r' (0 = path not applicable)
+	int pad1;
 };
 
 // small device-resident control block, zeroed at the start of every run

@@ -88,11 +88,18 @@ class FramePipeline:
     def enable_timing(self, on=True):
         self.lib.ls3d_frame_enable_timing(self.h, 1 if on else 0)
 
+    STAGES = ["map_cull_compact", "hash_clear", "voxel_insert", "cell_ranges_scatter", "voxel_neighbour_count", "survivor_compact",
+              "organized_neighbour_count", "whole"]
+
     def stage_ms(self) -> np.ndarray:
-        """[map_cull, hash_clear, insert, ranges+scatter, neighbour_count, compact_merge, whole] of the last timed run."""
+        """Milliseconds per stage (order: FramePipeline.STAGES) of the last timed run; 0 where a stage did not run."""
         out = np.zeros(8, dtype=np.float32)
         native.check(self.lib.ls3d_frame_stage_ms(self.h, out.ctypes.data_as(C.c_void_p)) == 0, "ls3d_frame_stage_ms")
-        return out[:7]
+        return out
+
+    def set_filter_mode(self, mode: int):
+        """0 auto, 1 voxel hash, 2 organized (pixel window)."""
+        native.check(self.lib.ls3d_frame_set_filter_mode(self.h, int(mode)) == 0, "ls3d_frame_set_filter_mode")
 
     # ---- results (views of library memory; valid until the next run) ----
     def vertices(self) -> torch.Tensor:

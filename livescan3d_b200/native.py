@@ -56,6 +56,8 @@ _SIG = {
     "ls3d_ipc_export": (_i, [_vp, _vp]),
     "ls3d_ipc_open": (_vp, [_vp]),
     "ls3d_ipc_close": (None, [_vp]),
+    "ls3d_frame_set_filter_mode": (_i, [_vp, _i]),
+    "ls3d_set_default_filter_mode": (_i, [_i]),
     "ls3d_frame_enable_timing": (None, [_vp, _i]),
     "ls3d_frame_stage_ms": (_i, [_vp, _vp]),
     "ls3d_frame_vertices": (_vp, [_vp]),

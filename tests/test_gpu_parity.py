@@ -154,8 +154,19 @@ def _pipeline_oracle(fr, bounds, k, md):
     return np.concatenate(parts), np.array(counts)
 
 
-@pytest.mark.parametrize("k,md", [(10, 0.01), (10, 0.1), (4, 0.03), (0, 0.0)])
-def test_frame_pipeline_small(api, k, md):
+@pytest.fixture(params=[2, 1], ids=["organized", "voxelhash"])
+def filter_mode(request):
+    """Both candidate enumerations of the neighbour count (pixel window on the organized cloud / voxel hash) must give
+    the reference's result; the host-buffer entry points pick by this process-wide switch."""
+    from livescan3d_b200 import native
+    lib = native.load()
+    assert lib.ls3d_set_default_filter_mode(request.param) == 0
+    yield request.param
+    lib.ls3d_set_default_filter_mode(0)
+
+
+@pytest.mark.parametrize("k,md", [(10, 0.01), (10, 0.1), (4, 0.03), (0, 0.0), (30, 0.3)])
+def test_frame_pipeline_small(api, filter_mode, k, md):
     fr = small_frame(S=4, w=160, h=120)
     want, wcounts = _pipeline_oracle(fr, synth.DEFAULT_BOUNDS, k, md)
     got, gcounts = api.frame_pipeline(fr, synth.DEFAULT_BOUNDS, k, md)
@@ -163,7 +174,33 @@ def test_frame_pipeline_small(api, k, md):
     assert got.tobytes() == want.tobytes()
 
 
-def test_frame_pipeline_full_size_8_sensors(api):
+def test_frame_pipeline_poses_bounds_and_odd_sizes(api, filter_mode):
+    # the shipped calibration poses (not exactly orthonormal), every bounds preset, sizes that are not tile multiples
+    fr = synth.make_frame(2, 160, 120, poses=synth.FIXTURE_POSES)
+    for b in BOUNDS.values():
+        want, wcounts = _pipeline_oracle(fr, b, 6, 0.02)
+        got, gcounts = api.frame_pipeline(fr, b, 6, 0.02)
+        assert np.array_equal(gcounts, wcounts) and got.tobytes() == want.tobytes()
+    for (w, h) in [(127, 95), (33, 7), (70, 50)]:
+        fr = synth.make_frame(3, w, h, ring=8)
+        want, wcounts = _pipeline_oracle(fr, synth.SERVER_BOUNDS, 5, 0.05)
+        got, gcounts = api.frame_pipeline(fr, synth.SERVER_BOUNDS, 5, 0.05)
+        assert np.array_equal(gcounts, wcounts) and got.tobytes() == want.tobytes(), (w, h)
+
+
+def test_frame_pipeline_near_depth_large_windows(api, filter_mode):
+    """Very near depth makes the organized path's pixel window exceed its shared-memory halo (global-window branch)."""
+    fr = small_frame(S=2, w=96, h=72)
+    d = fr["depth_maps"].view(np.uint16).copy()
+    d[d > 0] = (d[d > 0] // 40 + 3).astype(np.uint16)           # 3..200 mm: a dense blob right in front of the sensor
+    fr["depth_maps"] = d.view(np.uint8)
+    for k, md in [(10, 0.01), (25, 0.004)]:
+        want, wcounts = _pipeline_oracle(fr, synth.SERVER_BOUNDS, k, md)
+        got, gcounts = api.frame_pipeline(fr, synth.SERVER_BOUNDS, k, md)
+        assert np.array_equal(gcounts, wcounts) and got.tobytes() == want.tobytes()
+
+
+def test_frame_pipeline_full_size_8_sensors(api, filter_mode):
     fr = synth.make_frame(8)
     want, wcounts = _pipeline_oracle(fr, synth.DEFAULT_BOUNDS, 10, 0.01)
     got, gcounts = api.frame_pipeline(fr, synth.DEFAULT_BOUNDS, 10, 0.01)
@@ -287,14 +324,24 @@ def test_device_api_matches_host_api(api):
     dd = torch.from_numpy(fr["depth_maps"]).cuda()
     dc = torch.from_numpy(fr["depth_colors"]).cuda()
     fp.set_params(fr["intr"], fr["wt"], synth.DEFAULT_BOUNDS, 10, 0.01)
-    for _ in range(3):                                         # re-runnable without re-creating anything
-        fp.run(dd, dc)
-    v, counts = fp.result()
     want, wcounts = api.frame_pipeline(fr, synth.DEFAULT_BOUNDS, 10, 0.01)
-    assert v.tobytes() == want.tobytes() and np.array_equal(counts, wcounts)
-    fp.run(dd, dc, first_map=2, n_run=1)                       # a sensor sub-range
-    v1, c1 = fp.result()
-    assert len(v1) == wcounts[2] and v1.tobytes() == want[wcounts[:2].sum():wcounts[:3].sum()].tobytes()
+    for mode in (2, 1, 0):
+        fp.set_filter_mode(mode)
+        for _ in range(3):                                     # re-runnable without re-creating anything
+            fp.run(dd, dc)
+        v, counts = fp.result()
+        assert v.tobytes() == want.tobytes() and np.array_equal(counts, wcounts), mode
+        assert int(fp.counts.cpu()[3]) == len(want)            # n_kept (known before compaction) == final count
+        fp.run(dd, dc, first_map=2, n_run=1)                   # a sensor sub-range
+        v1, c1 = fp.result()
+        assert len(v1) == wcounts[2] and v1.tobytes() == want[wcounts[:2].sum():wcounts[:3].sum()].tobytes()
+        # split run (what the multi-GPU merge does): count stage, then placement at a device-side offset into a caller buffer
+        fp.run_count(dd, dc)
+        dst = torch.zeros((fp.total_px + 7, 16), dtype=torch.uint8, device="cuda")
+        off = torch.tensor([7], dtype=torch.int32, device="cuda")
+        fp.merge_peers([dst.data_ptr()], off)
+        torch.cuda.synchronize()
+        assert dst[7:7 + len(want)].cpu().numpy().tobytes() == want.tobytes() and not dst[:7].any()
     fp.close()
 
     A, B = icp_pair(fr, synth.DEFAULT_BOUNDS)
