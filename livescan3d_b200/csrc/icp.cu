@@ -58,6 +58,47 @@ __device__ __forceinline__ unsigned spread3(unsigned v) {     // 10 bits -> ever
 	return v;
 }
 __device__ __forceinline__ unsigned morton3(unsigned x, unsigned y, unsigned z) { return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2); }
+__device__ __forceinline__ unsigned compact3(unsigned v) {   // inverse of spread3
+	v &= 0x09249249u;
+	v = (v ^ (v >> 2)) & 0x030C30C3u;
+	v = (v ^ (v >> 4)) & 0x0300F00Fu;
+	v = (v ^ (v >> 8)) & 0x030000FFu;
+	v = (v ^ (v >> 16)) & 0x000003FFu;
+	return v;
+}
+
+// Octree node record (one u64 per node of every level, and per occupied cell): the bounding box of the node's POINTS,
+// quantised to 8 bits per bound inside the node's cube (rounded outward, so the decoded box always contains the
+// points), plus the 8-bit child-occupancy mask.  bytes: 0..2 min xyz, 3..5 max xyz, 6 child mask.
+// Tight boxes are what keeps far queries cheap: a wall tangent to the search ball passes the cube test in ~2d/h cells
+// but the box test in a handful.
+__device__ __forceinline__ unsigned long long box_encode(const float mn[3], const float mx[3], float ox, float oy, float oz, float size, unsigned mask) {
+	const float sc = 255.0f / size;
+	const float o[3] = {ox, oy, oz};
+	unsigned long long r = (unsigned long long)mask << 48;
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const float lo = fminf(fmaxf(floorf((mn[a] - o[a]) * sc - 0.02f), 0.0f), 255.0f);
+		const float hi = fminf(fmaxf(ceilf((mx[a] - o[a]) * sc + 0.02f), 0.0f), 255.0f);
+		r |= (unsigned long long)(unsigned)lo << (8 * a);
+		r |= (unsigned long long)(unsigned)hi << (8 * (3 + a));
+	}
+	return r;
+}
+__device__ __forceinline__ void box_decode(unsigned long long r, float ox, float oy, float oz, float size, float mn[3], float mx[3]) {
+	const float q = size * (1.0f / 255.0f);
+	mn[0] = ox + (float)(unsigned)(r & 0xff) * q;         mn[1] = oy + (float)(unsigned)((r >> 8) & 0xff) * q;  mn[2] = oz + (float)(unsigned)((r >> 16) & 0xff) * q;
+	mx[0] = ox + (float)(unsigned)((r >> 24) & 0xff) * q; mx[1] = oy + (float)(unsigned)((r >> 32) & 0xff) * q; mx[2] = oz + (float)(unsigned)((r >> 40) & 0xff) * q;
+}
+// conservative squared distance from the origin-relative query to a decoded record box
+__device__ __forceinline__ float rec_lb2(unsigned long long r, float rx, float ry, float rz, float ox, float oy, float oz, float size, float slack) {
+	float mn[3], mx[3];
+	box_decode(r, ox, oy, oz, size, mn, mx);
+	const float dx = fmaxf(fmaxf(mn[0] - rx, rx - mx[0]) - slack, 0.0f);
+	const float dy = fmaxf(fmaxf(mn[1] - ry, ry - mx[1]) - slack, 0.0f);
+	const float dz = fmaxf(fmaxf(mn[2] - rz, rz - mx[2]) - slack, 0.0f);
+	return (dx * dx + dy * dy + dz * dz) * 0.99999f;
+}
 
 // first entry of level l (1..L) in the child-mask array: sum_{j<l} (G >> j)^3 with G = 2^L
 __device__ __host__ __forceinline__ unsigned icp_mask_off(int L, int l) { return ((1u << (3 * L)) - (1u << (3 * (L - l + 1)))) / 7u; }
@@ -111,25 +152,75 @@ __global__ void k_icp_grid_params(const IcpBox *box, IcpGrid *grid, int G, int l
 	grid->levels = levels;
 }
 
-// Octree child masks for every level: bit c of masks[mask_off[l] + mp] says whether child c (Morton order) of the
-// level-l node with Morton prefix mp holds any target point.  Morton cell order makes every node a contiguous
-// range of cell_start, so each bit is one subtraction.
-__global__ void __launch_bounds__(256) k_icp_masks(const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, unsigned char *__restrict__ masks, unsigned total) {
+// level 0: one record per occupied cell, stored at the index of the cell's first point in the sorted array
+__global__ void __launch_bounds__(256) k_icp_cellbox(const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted,
+	unsigned long long *__restrict__ cellbox, unsigned ncells)
+{
 	const IcpGrid g = *grid;
-	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-		int l = 1;
-		while (l < g.levels && t >= icp_mask_off(g.levels, l + 1)) l++;
-		const unsigned mp = t - icp_mask_off(g.levels, l);
-		const int sh = 3 * (l - 1);
-		unsigned m = 0;
-		unsigned prev = cell_start[(mp << 3) << sh];
+	for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < ncells; m += gridDim.x * blockDim.x) {
+		const unsigned s = cell_start[m], e = cell_start[m + 1];
+		if (s == e) continue;
+		float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+		for (unsigned p = s; p < e; p++) {
+			const float4 c = sorted[p];
+			const float r[3] = {c.x - g.ox, c.y - g.oy, c.z - g.oz};
 #pragma unroll
-		for (unsigned c = 0; c < 8; c++) {
-			const unsigned nxt = cell_start[((mp << 3) + c + 1) << sh];
-			if (nxt != prev) m |= 1u << c;
-			prev = nxt;
+			for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], r[a]); mx[a] = fmaxf(mx[a], r[a]); }
 		}
-		masks[t] = (unsigned char)m;
+		const float nx = (float)compact3(m), ny = (float)compact3(m >> 1), nz = (float)compact3(m >> 2);
+		cellbox[s] = box_encode(mn, mx, nx * g.h, ny * g.h, nz * g.h, g.h, 0u);
+	}
+}
+
+// one octree node of level l from its 8 children (cells for l == 1)
+__device__ __forceinline__ void icp_make_node(const IcpGrid &g, int l, unsigned mp, const unsigned *__restrict__ cell_start,
+	const unsigned long long *__restrict__ cellbox, unsigned long long *nodes)
+{
+	const int L = g.levels;
+	const float csize = g.h * (float)(1u << (l - 1));
+	float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+	unsigned mask = 0;
+	for (unsigned c = 0; c < 8; c++) {
+		const unsigned cmp = (mp << 3) | c;
+		unsigned long long r;
+		if (l == 1) {
+			const unsigned s = cell_start[cmp], e = cell_start[cmp + 1];
+			if (s == e) continue;
+			r = cellbox[s];
+		} else {
+			r = nodes[icp_mask_off(L, l - 1) + cmp];
+			if (((r >> 48) & 0xff) == 0) continue;
+		}
+		mask |= 1u << c;
+		float cmn[3], cmx[3];
+		box_decode(r, (float)compact3(cmp) * csize, (float)compact3(cmp >> 1) * csize, (float)compact3(cmp >> 2) * csize, csize, cmn, cmx);
+#pragma unroll
+		for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], cmn[a]); mx[a] = fmaxf(mx[a], cmx[a]); }
+	}
+	const float size = csize * 2.0f;
+	unsigned long long rec = 0;
+	if (mask) rec = box_encode(mn, mx, (float)compact3(mp) * size, (float)compact3(mp >> 1) * size, (float)compact3(mp >> 2) * size, size, mask);
+	nodes[icp_mask_off(L, l) + mp] = rec;
+}
+
+__global__ void __launch_bounds__(256) k_icp_nodebox(const IcpGrid *__restrict__ grid, int l, const unsigned *__restrict__ cell_start,
+	const unsigned long long *__restrict__ cellbox, unsigned long long *nodes)
+{
+	const IcpGrid g = *grid;
+	const unsigned dim = (unsigned)g.G >> l, n = dim * dim * dim;
+	for (unsigned mp = blockIdx.x * blockDim.x + threadIdx.x; mp < n; mp += gridDim.x * blockDim.x) icp_make_node(g, l, mp, cell_start, cellbox, nodes);
+}
+
+// levels l_first..L in one block (at most 512 nodes per level), level by level
+__global__ void __launch_bounds__(512) k_icp_nodebox_top(const IcpGrid *__restrict__ grid, int l_first, const unsigned *__restrict__ cell_start,
+	const unsigned long long *__restrict__ cellbox, unsigned long long *nodes)
+{
+	const IcpGrid g = *grid;
+	for (int l = l_first; l <= g.levels; l++) {
+		const unsigned dim = (unsigned)g.G >> l, n = dim * dim * dim;
+		for (unsigned mp = threadIdx.x; mp < n; mp += blockDim.x) icp_make_node(g, l, mp, cell_start, cellbox, nodes);
+		__threadfence_block();
+		__syncthreads();
 	}
 }
 
@@ -345,14 +436,15 @@ __device__ __forceinline__ float box_lb2(float rx, float ry, float rz, float lx,
 
 // Exact nearest neighbour, bottom-up over the implicit octree:
 //   scan the query's home cell, then climb: at every level first ask whether everything outside the subtree
-//   already searched is provably farther than the best so far (distance to the subtree's faces; faces on the
+//   already searched is provably farther than the best so far (distance to the subtree's cube faces; faces on the
 //   grid boundary have nothing behind them) and stop if so; otherwise search the siblings — a near-first
-//   depth-first walk driven by the 8-bit child masks (empty children cost nothing, non-empty ones one box test)
-//   — and climb one level.  Near queries stop after a level or two, distant ones (points of the source that the
-//   target never saw) climb until their ball fits, so the result is exact at any distance like nanoflann's.
+//   depth-first walk over the node records: empty children cost nothing (mask), a child is entered only if first its
+//   cube and then the tight box of its points can still hold something closer — and climb one level.
+//   Near queries stop after a level or two, distant ones (points of the source that the target never saw) climb
+//   until their ball fits, so the result is exact at any distance like nanoflann's.
 //   `best` may arrive seeded with a real candidate (the previous iteration's neighbour).
-__device__ __forceinline__ Best nearest_in_grid(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned char *__restrict__ masks,
-	const float4 *__restrict__ sorted, float qx, float qy, float qz, Best best)
+__device__ __forceinline__ Best nearest_in_grid(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellbox, const float4 *__restrict__ sorted, float qx, float qy, float qz, Best best)
 {
 	const float rx = qx - g.ox, ry = qy - g.oy, rz = qz - g.oz;
 	if (!(isfinite(rx) && isfinite(ry) && isfinite(rz))) return best;
@@ -382,7 +474,8 @@ __device__ __forceinline__ Best nearest_in_grid(const IcpGrid &g, const unsigned
 		const int top = lvl + 1;
 		int t = top;
 		unsigned ux = nx >> 1, uy = ny >> 1, uz = nz >> 1, ump = mp >> 3;
-		unsigned long long rem = (unsigned long long)(masks[icp_mask_off(L, t) + ump] & ~(1u << (mp & 7u))) << (8 * (t - 1));
+		const unsigned pmask = (unsigned)(nodes[icp_mask_off(L, t) + ump] >> 48) & 0xffu;
+		unsigned long long rem = (unsigned long long)(pmask & ~(1u << (mp & 7u))) << (8 * (t - 1));
 		for (;;) {
 			const int sh8 = 8 * (t - 1);
 			const unsigned rm = (unsigned)(rem >> sh8) & 0xffu;
@@ -402,14 +495,19 @@ __device__ __forceinline__ Best nearest_in_grid(const IcpGrid &g, const unsigned
 			}
 			rem &= ~(1ull << (sh8 + child));
 			const unsigned ccx = (ux << 1) | (child & 1u), ccy = (uy << 1) | ((child >> 1) & 1u), ccz = (uz << 1) | (child >> 2);
-			if (box_lb2(rx, ry, rz, (float)ccx * half, (float)ccy * half, (float)ccz * half, half, slack) > best.d2) continue;
+			const float bx = (float)ccx * half, by = (float)ccy * half, bz = (float)ccz * half;
+			if (box_lb2(rx, ry, rz, bx, by, bz, half, slack) > best.d2) continue;           // cube test: no memory traffic
 			const unsigned cmp = (ump << 3) | child;
 			if (t == 1) {
-				scan_cell(sorted, cell_start[cmp], cell_start[cmp + 1], qx, qy, qz, best);
+				const unsigned s = cell_start[cmp], e = cell_start[cmp + 1];
+				if (rec_lb2(cellbox[s], rx, ry, rz, bx, by, bz, half, slack) > best.d2) continue;
+				scan_cell(sorted, s, e, qx, qy, qz, best);
 			} else {
+				const unsigned long long crec = nodes[icp_mask_off(L, t - 1) + cmp];
+				if (rec_lb2(crec, rx, ry, rz, bx, by, bz, half, slack) > best.d2) continue;
 				t--;
 				ux = ccx; uy = ccy; uz = ccz; ump = cmp;
-				rem |= (unsigned long long)masks[icp_mask_off(L, t) + ump] << (8 * (t - 1));
+				rem |= ((crec >> 48) & 0xffull) << (8 * (t - 1));
 			}
 		}
 		nx >>= 1; ny >>= 1; nz >>= 1; mp >>= 3;
@@ -428,8 +526,8 @@ __device__ __forceinline__ void apply_xform(float &x, float &y, float &z, const 
 // apply != 0: first apply the previous iteration's update (from sums_buf) to every source point.
 // search != 0: NN + dedupe for the slice [i_begin, i_end).
 __global__ void __launch_bounds__(256) k_icp_match(float *__restrict__ verts2, int n2, int i_begin, int i_end, int apply, int search,
-	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned char *__restrict__ masks, const float4 *__restrict__ sorted,
-	const float *__restrict__ verts1, unsigned long long *slots, IcpState *state, const double *__restrict__ sums_buf, Ls3dIcpTrace *trace, int trace_idx,
+	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellbox, const float4 *__restrict__ sorted, const float *__restrict__ verts1, unsigned long long *slots, IcpState *state, const double *__restrict__ sums_buf, Ls3dIcpTrace *trace, int trace_idx,
 	int *__restrict__ nn_idx, float *__restrict__ nn_d2)
 {
 	__shared__ float sT[3], sR[9];
@@ -465,7 +563,7 @@ __global__ void __launch_bounds__(256) k_icp_match(float *__restrict__ verts2, i
 					b.d2 = dist2_ref(x, y, z, verts1[3 * (size_t)prev], verts1[3 * (size_t)prev + 1], verts1[3 * (size_t)prev + 2]);
 					if (!(b.d2 == b.d2)) { b.d2 = INFINITY; b.idx = -1; }
 				}
-				b = nearest_in_grid(g, cell_start, masks, sorted, x, y, z, b);
+				b = nearest_in_grid(g, cell_start, nodes, cellbox, sorted, x, y, z, b);
 				bi = b.idx; bd = b.d2;
 				if (bi >= 0) {
 					const unsigned long long key = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
@@ -612,7 +710,7 @@ struct Ls3dIcp {
 	int sm_count = 148;
 	const float *d_verts1 = nullptr;
 	float *d_verts2 = nullptr;
-	DevBuf grid, box, state, cell_start, masks, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, trace, small;
+	DevBuf grid, box, state, cell_start, nodes, cellbox, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, trace, small;
 	DevBuf own_v1, own_v2;        // device copies for the host-buffer API
 	float *pin = nullptr;         // pinned read-back: Rt[12] + status[4]
 	cudaGraphExec_t graph = nullptr;
@@ -622,7 +720,7 @@ struct Ls3dIcp {
 
 static void icp_free(Ls3dIcp *c) {
 	if (!c) return;
-	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->masks, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
+	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->nodes, &c->cellbox, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
 		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->trace, &c->small, &c->own_v1, &c->own_v2};
 	for (DevBuf *b : bufs) b->release();
 	if (c->pin) cudaFreeHost(c->pin);
@@ -674,7 +772,7 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 	unsigned mask_total = 0;
 	for (int l = 1; l <= c->levels; l++) { const unsigned n = (unsigned)(c->G >> l); mask_total += n * n * n; }
 	if (!c->cell_start.reserve(4 * (cells + 8), "alloc cell starts") || !c->scan_status.reserve(8 * (size_t)(scan_tiles + 1), "alloc scan status") ||
-		!c->masks.reserve(mask_total + 16, "alloc octree masks")) return -1;
+		!c->nodes.reserve(8 * (size_t)(mask_total + 16), "alloc octree nodes") || !c->cellbox.reserve(8 * (size_t)c->n1_max, "alloc cell boxes")) return -1;
 	IcpBox hb;
 	for (int a = 0; a < 3; a++) { hb.mn[a] = 0xffffffffu; hb.mx[a] = 0u; }
 	bool ok = cuda_ok(cudaMemcpyAsync(c->box.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, st), "init bbox") &&
@@ -690,9 +788,22 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 	k_icp_count<<<nb, 256, 0, st>>>(c->d_verts1, n1, c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->cell_of.as<unsigned>(), c->rank_of.as<unsigned>());
 	k_exclusive_scan<<<std::min(scan_tiles, c->sm_count * 8), kScanThreads, 0, st>>>(c->cell_start.as<unsigned>(), scan_n, scan_counter, c->scan_status.as<unsigned long long>(), scan_err);
 	k_icp_scatter<<<nb, 256, 0, st>>>(c->d_verts1, n1, c->cell_of.as<unsigned>(), c->rank_of.as<unsigned>(), c->cell_start.as<unsigned>(), c->sorted.as<float4>());
-	k_icp_masks<<<std::min((mask_total + 255) / 256, (unsigned)c->sm_count * 8), 256, 0, st>>>(c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->masks.as<unsigned char>(), mask_total);
+	k_icp_cellbox<<<std::min((unsigned)((cells + 255) / 256), (unsigned)c->sm_count * 16), 256, 0, st>>>(c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->sorted.as<float4>(),
+		c->cellbox.as<unsigned long long>(), (unsigned)cells);
+	int launches = 7;
+	int l = 1;
+	for (; l <= c->levels; l++) {
+		const unsigned dim = (unsigned)c->G >> l, nn = dim * dim * dim;
+		if (nn <= 512) break;
+		k_icp_nodebox<<<std::min((nn + 255) / 256, (unsigned)c->sm_count * 8), 256, 0, st>>>(c->grid.as<IcpGrid>(), l, c->cell_start.as<unsigned>(), c->cellbox.as<unsigned long long>(), c->nodes.as<unsigned long long>());
+		launches++;
+	}
+	if (l <= c->levels) {
+		k_icp_nodebox_top<<<1, 512, 0, st>>>(c->grid.as<IcpGrid>(), l, c->cell_start.as<unsigned>(), c->cellbox.as<unsigned long long>(), c->nodes.as<unsigned long long>());
+		launches++;
+	}
 	k_fill_u64<<<nb, 256, 0, st>>>(c->slots.as<unsigned long long>(), n1, kSlotEmpty);
-	count_launch(7);
+	count_launch(launches);
 	return cuda_ok(cudaGetLastError(), "target grid kernels") ? 0 : -1;
 }
 
@@ -718,7 +829,7 @@ extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_beg
 static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) {
 	const int trace_idx = c->iter - 1;     // the update being applied belongs to the previous iteration
 	k_icp_match<<<pt_blocks(c, std::max(c->n2, 1)), 256, 0, st>>>(c->d_verts2, c->n2, c->i_begin, c->i_end, apply, search,
-		c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->masks.as<unsigned char>(), c->sorted.as<float4>(), c->d_verts1, c->slots.as<unsigned long long>(), c->state.as<IcpState>(),
+		c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(), c->d_verts1, c->slots.as<unsigned long long>(), c->state.as<IcpState>(),
 		c->sums_buf.as<double>(), c->trace.as<Ls3dIcpTrace>(), trace_idx, c->nn_idx.as<int>(), c->nn_d2.as<float>());
 	count_launch(1);
 	return cuda_ok(cudaGetLastError(), "k_icp_match") ? 0 : -1;
