@@ -71,15 +71,16 @@ __device__ __forceinline__ PixelXform load_xform(const SensorDesc *__restrict__ 
 	return m;
 }
 
-// returns true when the pixel yields a vertex (non-zero depth and inside the strict cull box)
-__device__ __forceinline__ bool map_pixel(const PixelXform &m, int x, int y, unsigned d, float &wx, float &wy, float &wz) {
+// returns true when the pixel yields a vertex (non-zero depth and inside the strict cull box).
+// xn = (x - cx) / fx and yn = (cy - y) / fy come from the per-sensor RAY TABLE (w + h floats, computed once per
+// parameter set on the host with the same two IEEE fp32 operations the reference performs per pixel,
+// depthprocessing.cpp:151-152), so only Z = d / 1000 is divided per pixel and the result is bit-identical.
+__device__ __forceinline__ bool map_pixel(const PixelXform &m, float xn, float yn, unsigned d, float &wx, float &wy, float &wz) {
 	if (d == 0) return false;
 	const float val = (float)d;
 	float Z = __fdiv_rn(val, 1000.0f);
-	float X = __fdiv_rn(__fsub_rn((float)x, m.cx), m.fx);
-	float Y = __fdiv_rn(__fsub_rn(m.cy, (float)y), m.fy);
-	X = __fmul_rn(X, Z);
-	Y = __fmul_rn(Y, Z);
+	float X = __fmul_rn(xn, Z);
+	float Y = __fmul_rn(yn, Z);
 	X = __fadd_rn(X, m.t0); Y = __fadd_rn(Y, m.t1); Z = __fadd_rn(Z, m.t2);
 	wx = __fadd_rn(__fadd_rn(__fmul_rn(X, m.r0), __fmul_rn(Y, m.r1)), __fmul_rn(Z, m.r2));
 	wy = __fadd_rn(__fadd_rn(__fmul_rn(X, m.r3), __fmul_rn(Y, m.r4)), __fmul_rn(Z, m.r5));
@@ -97,11 +98,15 @@ struct Bounds6 { float v[6]; };
 // final place.  Recomputing (~40 instructions per pixel) is cheaper than holding 24 coordinates across the scan:
 // the round-1 profile showed 74-80 registers, 3 blocks/SM, two waves and 57 % barrier stalls for the staged
 // version; this one keeps every tile of an 8-sensor frame resident in one wave.
+// kKeepMask: AND the organized neighbour count's per-pixel mask into the validity test.  In that mode the count kernel
+// has already left every tile's survivor count in tile_count[], so a tile's base is a plain sum over its predecessors
+// (no inter-block dependency at all) and tiles are assigned statically; otherwise the base comes from the look-back scan.
 template <bool kWriteD2V, bool kKeepMask>
 __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 	const uint8_t *__restrict__ depth, const uint8_t *__restrict__ colors, const SensorDesc *__restrict__ sd, const unsigned short *__restrict__ tile_sensor,
-	int s_first, int s_end, Bounds6 bnd, FrameCtl *ctl, unsigned long long *status, int *culled_starts,
-	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ d2v, const uint8_t *__restrict__ keep_px, PeerDst peers)
+	const float *__restrict__ rays, int s_first, int s_end, Bounds6 bnd, FrameCtl *ctl, unsigned long long *status, int *culled_starts,
+	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ d2v, const uint8_t *__restrict__ keep_px,
+	const unsigned *__restrict__ tile_count, PeerDst peers)
 {
 	__shared__ unsigned sm[16];
 	__shared__ int s_tile;
@@ -110,11 +115,18 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 	const int ntiles = sd[s_end].tile_begin - tile0;
 	const int out_off = d_out_offset ? *d_out_offset : 0;
 	const int tid = threadIdx.x;
+	int static_tile = blockIdx.x;
 
 	for (;;) {
-		if (tid == 0) s_tile = (int)atomicAdd(&ctl->tile_counter_a, 1u);
-		__syncthreads();
-		const int tile = s_tile;
+		int tile;
+		if (kKeepMask) {
+			tile = static_tile;
+			static_tile += gridDim.x;
+		} else {
+			if (tid == 0) s_tile = (int)atomicAdd(&ctl->tile_counter_a, 1u);
+			__syncthreads();
+			tile = s_tile;
+		}
 		if (tile >= ntiles) break;
 		const int s = tile_sensor[tile + tile0];
 		const int w = sd[s].w, px = sd[s].px;
@@ -156,21 +168,42 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 
 		// ---- pass 1 (rolled: registers, not instructions, are what this kernel is short of): which pixels yield a vertex ----
 		const int y0 = p0 / w, x0 = p0 - y0 * w;
+		const float *xray = rays + sd[s].ray_off, *yray = xray + w;
 		unsigned valid = 0;
-		{
+		if (kKeepMask) {
+			valid = keepm;            // the count kernel only keeps pixels that have a vertex
+		} else if (rem > 0) {
 			int x = x0, y = y0;
+			float yn = __ldg(yray + y);
 #pragma unroll 1
 			for (int j = 0; j < 8; j++) {
 				float wx, wy, wz;
-				if (((keepm >> j) & 1) && map_pixel(m, x, y, depth_of(j), wx, wy, wz)) valid |= 1u << j;
-				if (++x == w) { x = 0; y++; }
+				if (map_pixel(m, __ldg(xray + x), yn, depth_of(j), wx, wy, wz)) valid |= 1u << j;
+				if (++x == w) { x = 0; y++; yn = __ldg(yray + min(y, sd[s].h - 1)); }
 			}
 		}
 
 		// ---- stable compaction ----
 		const unsigned cnt = __popc(valid);
-		unsigned total, base;
-		const unsigned off = tile_scan(cnt, sm, status, tile, &ctl->err, &total, &base);
+		unsigned total, base, off;
+		if (kKeepMask) {
+			// base = survivors of all earlier tiles: 256 threads sum tile_count[tile0 .. tile0+tile) (no look-back, no waiting)
+			unsigned part = 0;
+			for (int t = tid; t < tile; t += kScanThreads) part += __ldg(tile_count + tile0 + t);
+			const int lane = tid & 31, warp = tid >> 5;
+			const unsigned incl = warp_incl_scan(cnt, lane);
+			part = warp_sum(part);
+			__syncthreads();                       // sm[] may still be read by the previous iteration
+			if (lane == 31) sm[warp] = incl;
+			if (lane == 0) sm[8 + warp] = part;
+			__syncthreads();
+			unsigned woff = 0, b = 0, tot = 0;
+#pragma unroll
+			for (int i = 0; i < kScanThreads / 32; i++) { b += sm[8 + i]; tot += sm[i]; if (i < warp) woff += sm[i]; }
+			base = b; total = tot; off = woff + incl - cnt;
+		} else {
+			off = tile_scan(cnt, sm, status, tile, &ctl->err, &total, &base);
+		}
 
 		// ---- pass 2: recompute and store the records (24 colour bytes: three LDG.64) ----
 		if (valid) {
@@ -203,7 +236,7 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 				int x = x0 + j, y = y0;
 				while (x >= w) { x -= w; y++; }
 				float wx, wy, wz;
-				map_pixel(m, x, y, depth_of(j), wx, wy, wz);
+				map_pixel(m, __ldg(xray + x), __ldg(yray + y), depth_of(j), wx, wy, wz);
 				// bytes 3j, 3j+1, 3j+2 of the 24-byte colour block -> R,G,B,255
 				const int bi = 3 * j, wi = bi >> 2;
 				const unsigned lo = wi == 0 ? c0 : wi == 1 ? c1 : wi == 2 ? c2 : wi == 3 ? c3 : wi == 4 ? c4 : c5;
@@ -226,7 +259,7 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 			if (tile + tile0 == sd[s].tile_begin) culled_starts[s] = (int)base;
 			if (tile == ntiles - 1) { culled_starts[s_end] = (int)(base + total); ctl->n_culled = (int)(base + total); ctl->n_final = (int)(base + total); }
 		}
-		__syncthreads();
+		if (!kKeepMask) __syncthreads();
 	}
 }
 
@@ -246,7 +279,7 @@ constexpr int kOrgTW = 32, kOrgTH = 8, kOrgHalo = 8;
 constexpr int kOrgSW = kOrgTW + 2 * kOrgHalo, kOrgSH = kOrgTH + 2 * kOrgHalo;
 
 __global__ void __launch_bounds__(kOrgTW * kOrgTH) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
-	int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px)
+	const float *__restrict__ rays, int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px, unsigned *tile_count)
 {
 	__shared__ float xs[kOrgSH * kOrgSW], ys[kOrgSH * kOrgSW], zs[kOrgSH * kOrgSW];
 	__shared__ unsigned s_kept;
@@ -256,6 +289,7 @@ __global__ void __launch_bounds__(kOrgTW * kOrgTH) k_organized_count(const uint8
 	if (tx0 >= w || ty0 >= h) return;
 	const PixelXform m = load_xform(sd, s, bnd.v);
 	const unsigned short *dimg = reinterpret_cast<const unsigned short *>(depth + sd[s].depth_off);
+	const float *xray = rays + sd[s].ray_off, *yray = xray + w;
 	const int tid = threadIdx.x;
 	if (tid == 0) s_kept = 0;
 
@@ -265,7 +299,7 @@ __global__ void __launch_bounds__(kOrgTW * kOrgTH) k_organized_count(const uint8
 		float wx = __int_as_float(0x7fc00000), wy = wx, wz = wx;
 		if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
 			float ax, ay, az;
-			if (map_pixel(m, gx, gy, (unsigned)__ldg(dimg + (size_t)gy * w + gx), ax, ay, az)) { wx = ax; wy = ay; wz = az; }
+			if (map_pixel(m, __ldg(xray + gx), __ldg(yray + gy), (unsigned)__ldg(dimg + (size_t)gy * w + gx), ax, ay, az)) { wx = ax; wy = ay; wz = az; }
 		}
 		xs[i] = wx; ys[i] = wy; zs[i] = wz;
 	}
@@ -280,7 +314,7 @@ __global__ void __launch_bounds__(kOrgTW * kOrgTH) k_organized_count(const uint8
 		if (qx == qx) {                                   // this pixel has a vertex
 			const float rp = sd[s].org_rp;
 			const float zc = (float)__ldg(dimg + (size_t)y * w + x) / 1000.0f;
-			const float xn = ((float)x - m.cx) / m.fx, yn = (m.cy - (float)y) / m.fy;
+			const float xn = __ldg(xray + x), yn = __ldg(yray + y);
 			const float den = zc - rp;
 			int ru = 1 << 28, rv = 1 << 28;
 			if (den > 0.0f) {
@@ -299,19 +333,32 @@ __global__ void __launch_bounds__(kOrgTW * kOrgTH) k_organized_count(const uint8
 			} else {
 				const int xa = max(0, x - min(ru, w)), xb = min(w - 1, x + min(ru, w));
 				const int ya = max(0, y - min(rv, h)), yb = min(h - 1, y + min(rv, h));
-				for (int yy = ya; yy <= yb && cnt < k; yy++)
+				for (int yy = ya; yy <= yb && cnt < k; yy++) {
+					const float yny = __ldg(yray + yy);
 					for (int xx = xa; xx <= xb; xx++) {
 						float ax, ay, az;
-						if (map_pixel(m, xx, yy, (unsigned)__ldg(dimg + (size_t)yy * w + xx), ax, ay, az))
+						if (map_pixel(m, __ldg(xray + xx), yny, (unsigned)__ldg(dimg + (size_t)yy * w + xx), ax, ay, az))
 							cnt += dist2_ref(qx, qy, qz, ax, ay, az) <= thr ? 1 : 0;
 					}
+				}
 			}
 			kept = cnt >= k;
 		}
 		keep_px[sd[s].pix_begin + (size_t)y * w + x] = (uint8_t)(kept ? 1 : 0);
 	}
+	// survivors per compaction tile of the map kernel (a warp is one 32-pixel row segment: it touches at most two tiles)
 	const unsigned km = __ballot_sync(kFull, kept);
-	if ((tid & 31) == 0 && km) atomicAdd(&s_kept, (unsigned)__popc(km));
+	if (km) {
+		const int pix = min(y, h - 1) * w + min(x, w - 1);
+		const int t = sd[s].tile_begin + pix / kTile;
+		const int tA = __shfl_sync(kFull, t, 0), tB = __shfl_sync(kFull, t, 31);
+		const unsigned inA = __ballot_sync(kFull, kept && t == tA), inB = km & ~inA;
+		if ((tid & 31) == 0) {
+			if (inA) atomicAdd(&tile_count[tA], (unsigned)__popc(inA));
+			if (inB) atomicAdd(&tile_count[tB], (unsigned)__popc(inB));
+			atomicAdd(&s_kept, (unsigned)__popc(km));
+		}
+	}
 	__syncthreads();
 	if (tid == 0 && s_kept) atomicAdd(&ctl->n_kept, (int)s_kept);
 }
@@ -742,6 +789,8 @@ struct Ls3dFrame {
 	unsigned total_slots = 0;
 	std::vector<SensorDesc> h_sd;       // S+1 entries (sentinel last)
 	SensorDesc *pin_sd = nullptr;       // pinned staging for the descriptor upload
+	float *pin_rays = nullptr;          // pinned staging for the ray tables
+	size_t n_rays = 0;
 	float bounds[6] = {0, 0, 0, 0, 0, 0};
 	int filter_k = 0;
 	float filter_max_dist = 0, filter_thr = 0;
@@ -754,7 +803,7 @@ struct Ls3dFrame {
 	int sm_count = 148;
 
 	// device memory
-	DevBuf sd, tile_sensor, zero, cloud0, sorted, final_, slot_of, rank_of, keep, keep_px, map, d2v, table, cell_start, in_depth, in_colors, box;
+	DevBuf sd, tile_sensor, rays, zero, cloud0, sorted, final_, slot_of, rank_of, keep, keep_px, map, d2v, table, cell_start, in_depth, in_colors, box;
 	// carve-outs of `zero` (re-zeroed by one memset per run)
 	FrameCtl *ctl = nullptr;
 	unsigned long long *status_a = nullptr, *status_b = nullptr;
@@ -784,10 +833,11 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static void frame_free(Ls3dFrame *f) {
 	if (!f) return;
-	DevBuf *bufs[] = {&f->sd, &f->tile_sensor, &f->zero, &f->cloud0, &f->sorted, &f->final_, &f->slot_of, &f->rank_of, &f->keep, &f->keep_px, &f->map, &f->d2v,
+	DevBuf *bufs[] = {&f->sd, &f->tile_sensor, &f->rays, &f->zero, &f->cloud0, &f->sorted, &f->final_, &f->slot_of, &f->rank_of, &f->keep, &f->keep_px, &f->map, &f->d2v,
 		&f->table, &f->cell_start, &f->in_depth, &f->in_colors, &f->box};
 	for (DevBuf *b : bufs) b->release();
 	if (f->pin_sd) cudaFreeHost(f->pin_sd);
+	if (f->pin_rays) cudaFreeHost(f->pin_rays);
 	if (f->pin_out) cudaFreeHost(f->pin_out);
 	for (auto &e : f->ev) for (cudaEvent_t x : e) if (x) cudaEventDestroy(x);
 	delete f;
@@ -833,6 +883,8 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		px_acc += px;
 		depth_off += px * 2;
 		color_off += px * 3;
+		d.ray_off = (int)f->n_rays;
+		f->n_rays += (size_t)widths[i] + (size_t)heights[i];
 		const int nt = (int)((px + kTile - 1) / kTile);
 		tile_sensor.insert(tile_sensor.end(), nt, (unsigned short)i);
 		tile_acc += nt;
@@ -850,7 +902,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 	const size_t starts_b = align_up(sizeof(int) * (size_t)(n_maps + 1), 256);
 	f->zero_bytes = ctl_b + 2 * st_b + 2 * starts_b;
 	bool ok = f->sd.reserve(sizeof(SensorDesc) * (n_maps + 1), "alloc descriptors") && f->zero.reserve(f->zero_bytes, "alloc control block") &&
-		f->tile_sensor.reserve(sizeof(unsigned short) * (tile_sensor.size() + 1), "alloc tile table") &&
+		f->tile_sensor.reserve(sizeof(unsigned short) * (tile_sensor.size() + 1), "alloc tile table") && f->rays.reserve(sizeof(float) * (f->n_rays + 4), "alloc ray tables") &&
 		f->cloud0.reserve(16 * n, "alloc culled cloud") && f->sorted.reserve(16 * n, "alloc sorted cloud") && f->final_.reserve(16 * n, "alloc merged cloud") &&
 		f->slot_of.reserve(4 * n, "alloc slots") && f->rank_of.reserve(4 * n, "alloc ranks") && f->keep.reserve(align_up(n, 16) + 16, "alloc keep flags") &&
 		f->keep_px.reserve(align_up(n, 16) + 16, "alloc pixel keep flags") &&
@@ -858,6 +910,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		f->table.reserve(8 * (size_t)f->total_slots, "alloc voxel hash") && f->cell_start.reserve(4 * (size_t)f->total_slots, "alloc voxel ranges") &&
 		f->box.reserve(sizeof(FilterBox), "alloc bbox");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_sd, sizeof(SensorDesc) * (n_maps + 1), cudaHostAllocDefault), "alloc pinned descriptors");
+	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_rays, sizeof(float) * (f->n_rays + 4), cudaHostAllocDefault), "alloc pinned ray tables");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_out, sizeof(int) * (size_t)(16 + 2 * (n_maps + 1)), cudaHostAllocDefault), "alloc pinned read-back");
 	ok = ok && cuda_ok(cudaMemcpy(f->tile_sensor.p, tile_sensor.data(), sizeof(unsigned short) * tile_sensor.size(), cudaMemcpyHostToDevice), "upload tile table");
 	if (!ok) { frame_free(f); return nullptr; }
@@ -943,6 +996,12 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 		const float *tp = wtransform_params + 12 * i;          // WorldTranformation(float*), depthprocessing.h:56-63
 		memcpy(d.t, tp, 3 * sizeof(float));
 		memcpy(d.R, tp + 3, 9 * sizeof(float));
+		// ray table: the reference's own two fp32 operations per coordinate (depthprocessing.cpp:151-152), once per column / row
+		{
+			float *xr = f->pin_rays + d.ray_off, *yr = xr + d.w;
+			for (int x = 0; x < d.w; x++) { volatile float a = (float)x - d.cx; xr[x] = a / d.fx; }
+			for (int y = 0; y < d.h; y++) { volatile float a = d.cy - (float)y; yr[y] = a / d.fy; }
+		}
 		d.org_rp = 0.0f;
 		if (f->filter_on) {
 			double lo[3], hi[3];
@@ -964,6 +1023,7 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 	}
 	memcpy(f->pin_sd, f->h_sd.data(), sizeof(SensorDesc) * (f->S + 1));
 	if (!cuda_ok(cudaMemcpyAsync(f->sd.p, f->pin_sd, sizeof(SensorDesc) * (f->S + 1), cudaMemcpyHostToDevice, (cudaStream_t)stream), "upload descriptors")) return -1;
+	if (!cuda_ok(cudaMemcpyAsync(f->rays.p, f->pin_rays, sizeof(float) * f->n_rays, cudaMemcpyHostToDevice, (cudaStream_t)stream), "upload ray tables")) return -1;
 	f->params_set = true;
 	return 0;
 }
@@ -999,13 +1059,15 @@ static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, i
 	const uint8_t *dd = (const uint8_t *)d_depth, *dc = (const uint8_t *)d_colors;
 	const SensorDesc *sd = f->sd.as<SensorDesc>();
 	const unsigned short *ts = f->tile_sensor.as<unsigned short>();
+	const float *rays = f->rays.as<float>();
+	const unsigned *tc = reinterpret_cast<const unsigned *>(f->status_b);      // per-tile survivor counts left by the organized count
 	stage_begin(f, kTsMap, st);
 	if (f->want_d2v) {
-		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, peers);
-		else k_map_cull_compact<true, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, peers);
+		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers);
+		else k_map_cull_compact<true, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers);
 	} else {
-		if (keep_px) k_map_cull_compact<false, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, peers);
-		else k_map_cull_compact<false, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, peers);
+		if (keep_px) k_map_cull_compact<false, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers);
+		else k_map_cull_compact<false, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers);
 	}
 	stage_end(f, kTsMap, st);
 	count_launch(1);
@@ -1085,7 +1147,8 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 			for (int i = s_first; i < s_end; i++) { mw = std::max(mw, f->w[i]); mh = std::max(mh, f->h[i]); }
 			const dim3 grid((mw + kOrgTW - 1) / kOrgTW, (mh + kOrgTH - 1) / kOrgTH, n_run);
 			stage_begin(f, kTsOrganized, st);
-			k_organized_count<<<grid, kOrgTW * kOrgTH, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), s_first, b, f->ctl, f->filter_k, f->filter_thr, f->keep_px.as<uint8_t>());
+			k_organized_count<<<grid, kOrgTW * kOrgTH, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->rays.as<float>(), s_first, b, f->ctl, f->filter_k, f->filter_thr,
+				f->keep_px.as<uint8_t>(), reinterpret_cast<unsigned *>(f->status_b));
 			stage_end(f, kTsOrganized, st);
 			count_launch(1);
 			if (!cuda_ok(cudaGetLastError(), "k_organized_count")) return -1;

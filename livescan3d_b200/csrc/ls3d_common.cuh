@@ -36,7 +36,7 @@ struct alignas(16) SensorDesc {
 	float gox, goy, goz, ginv_h;        // voxel-hash origin and 1/cell edge for the neighbour-count filter
 	unsigned tbl_off, tbl_mask;         // this sensor's region of the voxel hash table (power-of-two capacity)
 	float org_rp;                       // organized neighbour count: camera-space radius r' (0 = path not applicable)
-	int pad1;
+	int ray_off;                        // this sensor's ray table: xn[w] then yn[h] floats at rays + ray_off
 };
 
 // small device-resident control block, zeroed at the start of every run
