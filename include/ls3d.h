@@ -206,14 +206,22 @@ int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_begin, int i_e
  *                    dedupe by 64-bit atomicMin into the slot array (ls3d_icp_slots: int64[n1], MIN-reducible)
  *   ls3d_icp_stats : count / sum / sum of squares of matched d2 over slots [j_begin,j_end) -> ls3d_icp_stats_buf (f64[4])
  *   ls3d_icp_sums  : 2.5 sigma rejection + the 16 correspondence sums over slots [j_begin,j_end) -> ls3d_icp_sums_buf
- *                    (f64[16]); resets all slots for the next iteration.
+ *                    (f64[16]); resets all slots for the next iteration.  When the range covers every slot (one GPU) the
+ *                    same kernel also runs the solve step; otherwise all-reduce the sums and call
+ *   ls3d_icp_solve : 3x3 Kabsch/SVD on the device from ls3d_icp_sums_buf -> the (T, Rk) the next match applies, and the
+ *                    R,t accumulation of icp.cpp:167-168 (ls3d_icp_match / ls3d_icp_finish call it themselves if needed)
  * ls3d_icp_finish applies the last (T,Rk), leaving R,t in ls3d_icp_Rt (device f32[12]: R[9] then t[3]). */
 int ls3d_icp_match(Ls3dIcp *c, void *stream);
 int ls3d_icp_stats(Ls3dIcp *c, int j_begin, int j_end, void *stream);
 int ls3d_icp_sums(Ls3dIcp *c, int j_begin, int j_end, void *stream);
+int ls3d_icp_solve(Ls3dIcp *c, void *stream);
 int ls3d_icp_finish(Ls3dIcp *c, void *stream);
 /* All maxIter iterations on one GPU, no host round trips (captured once per shape as a CUDA graph). */
 int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream);
+
+/* Tuning aid: per-source-point work statistics of the last match stage (3 u32 each: octree child steps, candidate points
+ * scanned, resume level + 1 with 0 = finished in the first kernel); pass NULL to switch off. */
+void ls3d_icp_set_debug(Ls3dIcp *c, void *d_stats);
 
 long long *ls3d_icp_slots(Ls3dIcp *c);      /* device int64[n1] */
 double *ls3d_icp_stats_buf(Ls3dIcp *c);     /* device f64[4]  : count, sum d2, sum d2^2, 0 */

@@ -44,7 +44,8 @@ struct IcpGrid {
 struct IcpState {
 	float R[9], t[3];       // accumulated pose (ls3d_icp_Rt points here)
 	int iters_applied, err, pad0, pad1;
-	unsigned ticket_stats, ticket_sums, scan_counter, pad2;
+	unsigned ticket_stats, ticket_sums, n_work, pad2;
+	float xf[12];           // the update the next match kernel applies: T[3] then Rk[9] (written by the solve step)
 };
 
 struct IcpBox { unsigned mn[3], mx[3]; };
@@ -415,9 +416,10 @@ __device__ void icp_accumulate(IcpState *st, const float *T, const float *Rk, bo
 // ------------------------------------------------------------------------------------------------------
 // nearest neighbour
 // ------------------------------------------------------------------------------------------------------
-struct Best { float d2; int idx; };
+struct Best { float d2; int idx; unsigned steps, scanned; };     // steps/scanned: work counters (debug statistics)
 
 __device__ __forceinline__ void scan_cell(const float4 *__restrict__ sorted, unsigned s, unsigned e, float qx, float qy, float qz, Best &b) {
+	b.scanned += e - s;
 	for (unsigned p = s; p < e; p++) {
 		const float4 c = __ldg(sorted + p);
 		const float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
@@ -435,28 +437,40 @@ __device__ __forceinline__ float box_lb2(float rx, float ry, float rz, float lx,
 }
 
 // Exact nearest neighbour, bottom-up over the implicit octree:
-//   scan the query's home cell, then climb: at every level first ask whether everything outside the subtree
+//   (home cell scanned by the caller) climb: at every level first ask whether everything outside the subtree
 //   already searched is provably farther than the best so far (distance to the subtree's cube faces; faces on the
-//   grid boundary have nothing behind them) and stop if so; otherwise search the siblings — a near-first
-//   depth-first walk over the node records: empty children cost nothing (mask), a child is entered only if first its
+//   grid boundary have nothing behind them) and stop if so; otherwise search the siblings — a depth-first walk over
+//   the node records, nearest octant first: empty children cost nothing (mask), a child is entered only if first its
 //   cube and then the tight box of its points can still hold something closer — and climb one level.
 //   Near queries stop after a level or two, distant ones (points of the source that the target never saw) climb
 //   until their ball fits, so the result is exact at any distance like nanoflann's.
 //   `best` may arrive seeded with a real candidate (the previous iteration's neighbour).
-__device__ __forceinline__ Best nearest_in_grid(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellbox, const float4 *__restrict__ sorted, float qx, float qy, float qz, Best best)
+//
+// The walk is resumable at level boundaries: with step_budget > 0 it returns the level to resume at (>= 0) once it has
+// spent that many child steps, and -1 when the search is complete.  The match kernel runs every query with a small
+// budget and hands the expensive ones to a second kernel, so warps stay homogeneous (round-1 profile: 11 of 32 lanes
+// active when near and far queries shared warps).
+// s_stack: this thread's column of a [8][blockDim] byte array in shared memory (remaining-children masks per level).
+constexpr int kNnThreads = 256;
+
+__device__ __forceinline__ unsigned octant_permute(unsigned m, unsigned near) {      // bit c -> bit (c ^ near)
+	if (near & 1u) m = ((m & 0xAAu) >> 1) | ((m & 0x55u) << 1);
+	if (near & 2u) m = ((m & 0xCCu) >> 2) | ((m & 0x33u) << 2);
+	if (near & 4u) m = ((m & 0xF0u) >> 4) | ((m & 0x0Fu) << 4);
+	return m;
+}
+
+__device__ __forceinline__ int nn_climb(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellbox, const float4 *__restrict__ sorted, float qx, float qy, float qz, float rx, float ry, float rz,
+	unsigned hx, unsigned hy, unsigned hz, Best &best, int lvl_begin, int step_budget, unsigned char *s_stack)
 {
-	const float rx = qx - g.ox, ry = qy - g.oy, rz = qz - g.oz;
-	if (!(isfinite(rx) && isfinite(ry) && isfinite(rz))) return best;
 	const float h = g.h, slack = 1e-3f * g.h;
 	const int G = g.G, L = g.levels;
-	unsigned nx = (unsigned)icp_cell(rx, g.inv_h, G), ny = (unsigned)icp_cell(ry, g.inv_h, G), nz = (unsigned)icp_cell(rz, g.inv_h, G);
-	unsigned mp = morton3(nx, ny, nz);
-	{
-		const unsigned s = cell_start[mp], e = cell_start[mp + 1];
-		if (s != e) scan_cell(sorted, s, e, qx, qy, qz, best);
-	}
-	for (int lvl = 0; lvl < L; lvl++) {
+	unsigned nx = hx >> lvl_begin, ny = hy >> lvl_begin, nz = hz >> lvl_begin;
+	unsigned mp = morton3(hx, hy, hz) >> (3 * lvl_begin);
+	int steps = 0;
+	for (int lvl = lvl_begin; lvl < L; lvl++) {
+		if (step_budget > 0 && steps >= step_budget) return lvl;
 		// the subtree rooted at (nx,ny,nz)@lvl is done: can anything outside it still be closer?
 		const float size = h * (float)(1u << lvl);
 		const unsigned dim = (unsigned)G >> lvl;
@@ -468,32 +482,34 @@ __device__ __forceinline__ Best nearest_in_grid(const IcpGrid &g, const unsigned
 		if (nz > 0) rho = fminf(rho, rz - (float)nz * size);
 		if (nz + 1 < dim) rho = fminf(rho, (float)(nz + 1) * size - rz);
 		rho = fmaxf(rho - slack, 0.0f);
-		if (best.d2 <= rho * rho * 0.99999f) break;
+		if (best.d2 <= rho * rho * 0.99999f) return -1;
 
 		// siblings: depth-first from the parent (level lvl+1) with the finished child masked out
 		const int top = lvl + 1;
 		int t = top;
 		unsigned ux = nx >> 1, uy = ny >> 1, uz = nz >> 1, ump = mp >> 3;
-		const unsigned pmask = (unsigned)(nodes[icp_mask_off(L, t) + ump] >> 48) & 0xffu;
-		unsigned long long rem = (unsigned long long)(pmask & ~(1u << (mp & 7u))) << (8 * (t - 1));
+		unsigned nearpack = 0;
+		{
+			const unsigned pmask = ((unsigned)(nodes[icp_mask_off(L, t) + ump] >> 48) & 0xffu) & ~(1u << (mp & 7u));
+			const float half = h * (float)(1u << (t - 1));
+			const unsigned near = (rx >= (float)(2 * ux + 1) * half ? 1u : 0u) | (ry >= (float)(2 * uy + 1) * half ? 2u : 0u) | (rz >= (float)(2 * uz + 1) * half ? 4u : 0u);
+			nearpack = near << (3 * (t - 1));
+			s_stack[(t - 1) * kNnThreads] = (unsigned char)octant_permute(pmask, near);
+		}
 		for (;;) {
-			const int sh8 = 8 * (t - 1);
-			const unsigned rm = (unsigned)(rem >> sh8) & 0xffu;
+			const unsigned rm = s_stack[(t - 1) * kNnThreads];
 			if (rm == 0) {
 				if (t == top) break;
 				t++;
 				ux >>= 1; uy >>= 1; uz >>= 1; ump >>= 3;
 				continue;
 			}
+			steps++;
+			best.steps++;
+			const unsigned cp = (unsigned)__ffs(rm) - 1u;
+			s_stack[(t - 1) * kNnThreads] = (unsigned char)(rm & (rm - 1u));
+			const unsigned child = cp ^ ((nearpack >> (3 * (t - 1))) & 7u);
 			const float half = h * (float)(1u << (t - 1));            // child edge
-			const unsigned near = (rx >= (float)(2 * ux + 1) * half ? 1u : 0u) | (ry >= (float)(2 * uy + 1) * half ? 2u : 0u) | (rz >= (float)(2 * uz + 1) * half ? 4u : 0u);
-			unsigned child = 0;
-#pragma unroll
-			for (int r = 0; r < 8; r++) {
-				child = near ^ ((0x76534210u >> (4 * r)) & 7u);
-				if ((rm >> child) & 1u) break;
-			}
-			rem &= ~(1ull << (sh8 + child));
 			const unsigned ccx = (ux << 1) | (child & 1u), ccy = (uy << 1) | ((child >> 1) & 1u), ccz = (uz << 1) | (child >> 2);
 			const float bx = (float)ccx * half, by = (float)ccy * half, bz = (float)ccz * half;
 			if (box_lb2(rx, ry, rz, bx, by, bz, half, slack) > best.d2) continue;           // cube test: no memory traffic
@@ -507,12 +523,15 @@ __device__ __forceinline__ Best nearest_in_grid(const IcpGrid &g, const unsigned
 				if (rec_lb2(crec, rx, ry, rz, bx, by, bz, half, slack) > best.d2) continue;
 				t--;
 				ux = ccx; uy = ccy; uz = ccz; ump = cmp;
-				rem |= ((crec >> 48) & 0xffull) << (8 * (t - 1));
+				const float q4 = half * 0.5f;
+				const unsigned near = (rx >= (float)(2 * ux + 1) * q4 ? 1u : 0u) | (ry >= (float)(2 * uy + 1) * q4 ? 2u : 0u) | (rz >= (float)(2 * uz + 1) * q4 ? 4u : 0u);
+				nearpack = (nearpack & ~(7u << (3 * (t - 1)))) | (near << (3 * (t - 1)));
+				s_stack[(t - 1) * kNnThreads] = (unsigned char)octant_permute((unsigned)(crec >> 48) & 0xffu, near);
 			}
 		}
 		nx >>= 1; ny >>= 1; nz >>= 1; mp >>= 3;
 	}
-	return best;
+	return -1;
 }
 
 // apply (T, Rk) the way icp.cpp:143-165 does: fp32 add, then row-vector times matrix, left to right
@@ -523,56 +542,109 @@ __device__ __forceinline__ void apply_xform(float &x, float &y, float &z, const 
 	z = __fadd_rn(__fadd_rn(__fmul_rn(a0, Rk[2]), __fmul_rn(a1, Rk[5])), __fmul_rn(a2, Rk[8]));
 }
 
-// apply != 0: first apply the previous iteration's update (from sums_buf) to every source point.
-// search != 0: NN + dedupe for the slice [i_begin, i_end).
-__global__ void __launch_bounds__(256) k_icp_match(float *__restrict__ verts2, int n2, int i_begin, int i_end, int apply, int search,
+__device__ __forceinline__ void nn_commit(int i, const Best &b, unsigned long long *slots, int *__restrict__ nn_idx, float *__restrict__ nn_d2) {
+	nn_idx[i] = b.idx;
+	nn_d2[i] = b.idx >= 0 ? b.d2 : 0.0f;
+	if (b.idx >= 0) {
+		// one-to-one dedupe (icp.cpp:95-126): smallest d2 wins the target point, the LATER source index wins ties
+		const unsigned long long key = ((unsigned long long)__float_as_uint(b.d2) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+		atomicMin(&slots[b.idx], key);
+	}
+}
+
+constexpr int kNearBudget = 12;      // child steps a query may spend in the first kernel before it is deferred
+
+// apply != 0: first apply the update left in state->xf by the solve step to every source point.
+// search != 0: nearest neighbour + dedupe for the slice [i_begin, i_end); queries that exceed the step budget are
+// queued (index | resume level << 28) for k_icp_match_far with their best-so-far as the seed.
+__global__ void __launch_bounds__(kNnThreads) k_icp_match(float *__restrict__ verts2, int n2, int i_begin, int i_end, int apply, int search,
 	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellbox, const float4 *__restrict__ sorted, const float *__restrict__ verts1, unsigned long long *slots, IcpState *state, const double *__restrict__ sums_buf, Ls3dIcpTrace *trace, int trace_idx,
-	int *__restrict__ nn_idx, float *__restrict__ nn_d2)
+	const unsigned long long *__restrict__ cellbox, const float4 *__restrict__ sorted, const float *__restrict__ verts1, unsigned long long *slots,
+	IcpState *state, unsigned *__restrict__ work, int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg)
 {
-	__shared__ float sT[3], sR[9];
+	__shared__ unsigned char s_stack[8 * kNnThreads];
+	float T[3] = {0.f, 0.f, 0.f}, Rk[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
 	if (apply) {
-		if (threadIdx.x == 0) {
-			float T[3], Rk[9];
-			const bool solved = icp_solve(sums_buf, T, Rk);
-			for (int a = 0; a < 3; a++) sT[a] = T[a];
-			for (int a = 0; a < 9; a++) sR[a] = Rk[a];
-			if (blockIdx.x == 0) icp_accumulate(state, T, Rk, solved, trace, trace_idx, sums_buf);
-		}
-		__syncthreads();
+#pragma unroll
+		for (int a = 0; a < 3; a++) T[a] = state->xf[a];
+#pragma unroll
+		for (int a = 0; a < 9; a++) Rk[a] = state->xf[3 + a];
 	}
 	const IcpGrid g = *grid;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
-		float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
-		if (apply) {
-			apply_xform(x, y, z, sT, sR);
-			verts2[3 * (size_t)i] = x; verts2[3 * (size_t)i + 1] = y; verts2[3 * (size_t)i + 2] = z;
-		}
-		if (search) {
-			int bi = -1;
-			float bd = 0.0f;
-			if (i >= i_begin && i < i_end) {
-				// seed with last iteration's neighbour: a real candidate, so exactness is untouched, and the source
-				// barely moves between iterations, so the bound is already nearly tight
+	const int lane = threadIdx.x & 31;
+	const int n_pad = (n2 + 31) & ~31;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+		int resume = -1;
+		if (i < n2) {
+			float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
+			if (apply) {
+				apply_xform(x, y, z, T, Rk);
+				verts2[3 * (size_t)i] = x; verts2[3 * (size_t)i + 1] = y; verts2[3 * (size_t)i + 2] = z;
+			}
+			if (search) {
 				Best b;
 				b.d2 = INFINITY;
 				b.idx = -1;
-				const int prev = nn_idx[i];
-				if (prev >= 0) {
-					b.idx = prev;
-					b.d2 = dist2_ref(x, y, z, verts1[3 * (size_t)prev], verts1[3 * (size_t)prev + 1], verts1[3 * (size_t)prev + 2]);
-					if (!(b.d2 == b.d2)) { b.d2 = INFINITY; b.idx = -1; }
-				}
-				b = nearest_in_grid(g, cell_start, nodes, cellbox, sorted, x, y, z, b);
-				bi = b.idx; bd = b.d2;
-				if (bi >= 0) {
-					const unsigned long long key = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-					atomicMin(&slots[bi], key);
+				b.steps = 0; b.scanned = 0;
+				if (i >= i_begin && i < i_end) {
+					// seed with last iteration's neighbour: a real candidate, so exactness is untouched, and the source
+					// barely moves between iterations, so the bound is already nearly tight
+					const int prev = nn_idx[i];
+					if (prev >= 0) {
+						b.idx = prev;
+						b.d2 = dist2_ref(x, y, z, verts1[3 * (size_t)prev], verts1[3 * (size_t)prev + 1], verts1[3 * (size_t)prev + 2]);
+						if (!(b.d2 == b.d2)) { b.d2 = INFINITY; b.idx = -1; }
+					}
+					const float rx = x - g.ox, ry = y - g.oy, rz = z - g.oz;
+					if (isfinite(rx) && isfinite(ry) && isfinite(rz)) {
+						const unsigned hx = (unsigned)icp_cell(rx, g.inv_h, g.G), hy = (unsigned)icp_cell(ry, g.inv_h, g.G), hz = (unsigned)icp_cell(rz, g.inv_h, g.G);
+						const unsigned m = morton3(hx, hy, hz);
+						const unsigned s = cell_start[m], e = cell_start[m + 1];
+						if (s != e) scan_cell(sorted, s, e, x, y, z, b);
+						resume = nn_climb(g, cell_start, nodes, cellbox, sorted, x, y, z, rx, ry, rz, hx, hy, hz, b, 0, kNearBudget, s_stack + threadIdx.x);
+					}
+					if (resume < 0) nn_commit(i, b, slots, nn_idx, nn_d2);
+					else { nn_idx[i] = b.idx; nn_d2[i] = b.d2; }          // the seed for the far kernel
+					if (dbg) { dbg[3 * (size_t)i] = b.steps; dbg[3 * (size_t)i + 1] = b.scanned; dbg[3 * (size_t)i + 2] = (unsigned)(resume + 1); }
+				} else {
+					nn_idx[i] = -1;
+					nn_d2[i] = 0.0f;
 				}
 			}
-			nn_idx[i] = bi;
-			nn_d2[i] = bd;
 		}
+		// queue the deferred queries (warp-aggregated)
+		const unsigned dm = __ballot_sync(kFull, resume >= 0);
+		if (dm) {
+			unsigned base = 0;
+			if (lane == __ffs(dm) - 1) base = atomicAdd(&state->n_work, (unsigned)__popc(dm));
+			base = __shfl_sync(kFull, base, __ffs(dm) - 1);
+			if (resume >= 0) work[base + __popc(dm & ((1u << lane) - 1u))] = (unsigned)i | ((unsigned)resume << 28);
+		}
+	}
+}
+
+// the deferred (distant) queries: the same climb, resumed, with no budget
+__global__ void __launch_bounds__(kNnThreads) k_icp_match_far(const float *__restrict__ verts2, const IcpGrid *__restrict__ grid,
+	const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes, const unsigned long long *__restrict__ cellbox,
+	const float4 *__restrict__ sorted, unsigned long long *slots, const IcpState *state, const unsigned *__restrict__ work,
+	int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg)
+{
+	__shared__ unsigned char s_stack[8 * kNnThreads];
+	const IcpGrid g = *grid;
+	const unsigned n_work = state->n_work;
+	for (unsigned wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
+		const unsigned ent = work[wi];
+		const int i = (int)(ent & 0x0FFFFFFFu), lvl = (int)(ent >> 28);
+		const float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
+		Best b;
+		b.idx = nn_idx[i];
+		b.d2 = b.idx >= 0 ? nn_d2[i] : INFINITY;
+		b.steps = 0; b.scanned = 0;
+		const float rx = x - g.ox, ry = y - g.oy, rz = z - g.oz;
+		const unsigned hx = (unsigned)icp_cell(rx, g.inv_h, g.G), hy = (unsigned)icp_cell(ry, g.inv_h, g.G), hz = (unsigned)icp_cell(rz, g.inv_h, g.G);
+		nn_climb(g, cell_start, nodes, cellbox, sorted, x, y, z, rx, ry, rz, hx, hy, hz, b, lvl, 0, s_stack + threadIdx.x);
+		nn_commit(i, b, slots, nn_idx, nn_d2);
+		if (dbg) { dbg[3 * (size_t)i] += b.steps; dbg[3 * (size_t)i + 1] += b.scanned; }
 	}
 }
 
@@ -599,22 +671,34 @@ __device__ __forceinline__ void block_reduce_store(double *v, double *smem /* [8
 	}
 }
 
-// last block to arrive sums the per-block partials in a fixed order -> out[0..NV)
+// last block to arrive sums the per-block partials in a fixed order -> out[0..NV); returns true in that block
 template <int NV>
-__device__ __forceinline__ void last_block_finish(const double *partials, double *out, unsigned *ticket) {
+__device__ __forceinline__ bool last_block_finish(const double *partials, double *out, unsigned *ticket) {
 	__shared__ bool s_last;
 	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
 	__syncthreads();
-	if (!s_last) return;
+	if (!s_last) return false;
 	__threadfence();
+	// thread t = grp * NV + a sums value a of blocks grp, grp + kGroups, ...; then NV threads fold the groups in order:
+	// a fixed assignment, so the result does not depend on which block happened to arrive last
+	constexpr int kGroups = 256 / NV;          // 85 for NV = 3, 16 for NV = 16
+	const int a = threadIdx.x % NV, grp = threadIdx.x / NV;
+	double acc = 0;
+	if (grp < kGroups)
+		for (unsigned b = grp; b < gridDim.x; b += kGroups) acc += __ldcg(partials + (size_t)b * NV + a);
+	__shared__ double s_red[256];
+	s_red[threadIdx.x] = grp < kGroups ? acc : 0.0;
+	__syncthreads();
 	if (threadIdx.x < NV) {
-		double s = 0;
-		for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(partials + (size_t)b * NV + threadIdx.x);
-		out[threadIdx.x] = s;
+		double t = 0;
+		for (int gI = 0; gI < kGroups; gI++) t += s_red[gI * NV + threadIdx.x];
+		out[threadIdx.x] = t;
 	}
 	if (threadIdx.x == 0) *ticket = 0;
+	__syncthreads();
+	return true;
 }
 
 // count, sum d2, sum d2^2 over the matched slots of [j_begin, j_end)
@@ -622,6 +706,7 @@ __global__ void __launch_bounds__(256) k_icp_stats(const unsigned long long *__r
 	double *partials, double *stats_buf, IcpState *state)
 {
 	__shared__ double smem[8 * 3];
+	if (blockIdx.x == 0 && threadIdx.x == 0) state->n_work = 0;       // both match kernels of this iteration are done
 	double v[3] = {0, 0, 0};
 	for (int j = j_begin + blockIdx.x * blockDim.x + threadIdx.x; j < j_end; j += gridDim.x * blockDim.x) {
 		const unsigned long long key = slots[j];
@@ -634,11 +719,23 @@ __global__ void __launch_bounds__(256) k_icp_stats(const unsigned long long *__r
 	last_block_finish<3>(partials, stats_buf, &state->ticket_stats);
 }
 
+// the solve step: (T, Rk) from the 16 sums -> state->xf, pose accumulation (icp.cpp:167-168), trace.  One thread.
+__device__ void icp_solve_step(const double *sums, IcpState *state, Ls3dIcpTrace *trace, int trace_idx) {
+	float T[3], Rk[9];
+	const bool solved = icp_solve(sums, T, Rk);
+	for (int a = 0; a < 3; a++) state->xf[a] = T[a];
+	for (int a = 0; a < 9; a++) state->xf[3 + a] = Rk[a];
+	icp_accumulate(state, T, Rk, solved, trace, trace_idx, sums);
+}
+
+__global__ void k_icp_solve(const double *sums, IcpState *state, Ls3dIcpTrace *trace, int trace_idx) { icp_solve_step(sums, state, trace, trace_idx); }
+
 // 2.5 sigma gate (icp.cpp:34-73) + the 16 correspondence sums over [j_begin, j_end); every slot is reset.
 //   sums: [0] accepted count, [1..3] sum (p - q) (fp32 differences), [4..6] sum p, [7..15] sum q_a p_b
+// solve_here: the last block also runs the solve step (single GPU; with several ranks the sums are all-reduced first).
 __global__ void __launch_bounds__(256) k_icp_sums(unsigned long long *__restrict__ slots, int n1, int j_begin, int j_end,
 	const float *__restrict__ verts1, const float *__restrict__ verts2, const double *__restrict__ stats_buf,
-	double *partials, double *sums_buf, IcpState *state, Ls3dIcpTrace *trace, int trace_idx)
+	double *partials, double *sums_buf, IcpState *state, Ls3dIcpTrace *trace, int trace_idx, int solve_here)
 {
 	__shared__ double smem[8 * 16];
 	__shared__ float s_thr;
@@ -680,7 +777,8 @@ __global__ void __launch_bounds__(256) k_icp_sums(unsigned long long *__restrict
 		v[13] += (double)qz * (double)px; v[14] += (double)qz * (double)py; v[15] += (double)qz * (double)pz;
 	}
 	block_reduce_store<16>(v, smem, partials);
-	last_block_finish<16>(partials, sums_buf, &state->ticket_sums);
+	const bool last = last_block_finish<16>(partials, sums_buf, &state->ticket_sums);
+	if (last && solve_here && threadIdx.x == 0) icp_solve_step(sums_buf, state, trace, trace_idx);
 }
 
 struct Pose12 { float v[12]; };     // R[9] then t[3], passed by value (no staging buffer to race on)
@@ -692,6 +790,8 @@ __global__ void k_icp_init_state(IcpState *st, Pose12 p) {
 	st->err = 0;
 	st->ticket_stats = 0;
 	st->ticket_sums = 0;
+	st->n_work = 0;
+	for (int i = 0; i < 12; i++) st->xf[i] = (i == 3 || i == 7 || i == 11) ? 1.0f : 0.0f;
 }
 
 }  // namespace ls3d
@@ -707,10 +807,12 @@ struct Ls3dIcp {
 	int G = 0, levels = 0;
 	int iter = 0;                 // iterations whose match stage has been enqueued
 	bool pending = false;         // sums of the last iteration not yet applied
+	bool solved = false;          // ... and already turned into (T, Rk) by the solve step
+	unsigned *dbg = nullptr;      // optional per-query work statistics (3 u32 per source point), see ls3d_icp_set_debug
 	int sm_count = 148;
 	const float *d_verts1 = nullptr;
 	float *d_verts2 = nullptr;
-	DevBuf grid, box, state, cell_start, nodes, cellbox, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, trace, small;
+	DevBuf grid, box, state, cell_start, nodes, cellbox, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, work, trace, small;
 	DevBuf own_v1, own_v2;        // device copies for the host-buffer API
 	float *pin = nullptr;         // pinned read-back: Rt[12] + status[4]
 	cudaGraphExec_t graph = nullptr;
@@ -721,7 +823,7 @@ struct Ls3dIcp {
 static void icp_free(Ls3dIcp *c) {
 	if (!c) return;
 	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->nodes, &c->cellbox, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
-		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->trace, &c->small, &c->own_v1, &c->own_v2};
+		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->work, &c->trace, &c->small, &c->own_v1, &c->own_v2};
 	for (DevBuf *b : bufs) b->release();
 	if (c->pin) cudaFreeHost(c->pin);
 	if (c->graph) cudaGraphExecDestroy(c->graph);
@@ -743,7 +845,7 @@ extern "C" Ls3dIcp *ls3d_icp_create(int n1_max, int n2_max) {
 		c->cell_of.reserve(4 * n1, "alloc cells") && c->rank_of.reserve(4 * n1, "alloc ranks") && c->sorted.reserve(16 * n1, "alloc sorted target") &&
 		c->slots.reserve(8 * n1, "alloc slots") && c->partials.reserve(sizeof(double) * 16 * kRedBlocks, "alloc partials") &&
 		c->stats_buf.reserve(sizeof(double) * 4, "alloc stats") && c->sums_buf.reserve(sizeof(double) * 16, "alloc sums") &&
-		c->nn_idx.reserve(4 * n2, "alloc nn index") && c->nn_d2.reserve(4 * n2, "alloc nn dist") &&
+		c->nn_idx.reserve(4 * n2, "alloc nn index") && c->nn_d2.reserve(4 * n2, "alloc nn dist") && c->work.reserve(4 * n2 + 256, "alloc work list") &&
 		c->trace.reserve(sizeof(Ls3dIcpTrace) * kTraceCap, "alloc trace") && c->small.reserve(256, "alloc small");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin, 256, cudaHostAllocDefault), "alloc pinned read-back");
 	if (!ok) { icp_free(c); return nullptr; }
@@ -827,16 +929,25 @@ extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_beg
 }
 
 static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) {
-	const int trace_idx = c->iter - 1;     // the update being applied belongs to the previous iteration
-	k_icp_match<<<pt_blocks(c, std::max(c->n2, 1)), 256, 0, st>>>(c->d_verts2, c->n2, c->i_begin, c->i_end, apply, search,
-		c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(), c->d_verts1, c->slots.as<unsigned long long>(), c->state.as<IcpState>(),
-		c->sums_buf.as<double>(), c->trace.as<Ls3dIcpTrace>(), trace_idx, c->nn_idx.as<int>(), c->nn_d2.as<float>());
+	if (c->n2 >= (1 << 28)) { set_error("ICP: at most 2^28-1 source points"); return -1; }
+	const int nb = pt_blocks(c, std::max(c->n2, 1));
+	k_icp_match<<<nb, kNnThreads, 0, st>>>(c->d_verts2, c->n2, c->i_begin, c->i_end, apply, search,
+		c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(), c->d_verts1,
+		c->slots.as<unsigned long long>(), c->state.as<IcpState>(), c->work.as<unsigned>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg);
 	count_launch(1);
+	if (search) {
+		// the deferred queries; the count lives on the device, so the grid is sized for the worst case and idles otherwise
+		k_icp_match_far<<<std::max(1, std::min((c->i_end - c->i_begin + kNnThreads - 1) / kNnThreads, c->sm_count * 6)), kNnThreads, 0, st>>>(c->d_verts2, c->grid.as<IcpGrid>(),
+			c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(),
+			c->slots.as<unsigned long long>(), c->state.as<IcpState>(), c->work.as<unsigned>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg);
+		count_launch(1);
+	}
 	return cuda_ok(cudaGetLastError(), "k_icp_match") ? 0 : -1;
 }
 
 extern "C" int ls3d_icp_match(Ls3dIcp *c, void *stream) {
 	if (!c || !c->d_verts1 || !c->d_verts2) { set_error("ls3d_icp_match: target/source not set"); return -1; }
+	if (c->pending && !c->solved && ls3d_icp_solve(c, stream) < 0) return -1;
 	const int r = icp_launch_match(c, c->pending ? 1 : 0, 1, (cudaStream_t)stream);
 	c->pending = false;
 	c->iter++;
@@ -857,17 +968,29 @@ extern "C" int ls3d_icp_sums(Ls3dIcp *c, int j_begin, int j_end, void *stream) {
 	if (!c || !c->d_verts1 || !c->d_verts2) { set_error("ls3d_icp_sums: target/source not set"); return -1; }
 	if (j_begin < 0) j_begin = 0;
 	if (j_end > c->n1 || j_end < 0) j_end = c->n1;
+	const int solve_here = (j_begin == 0 && j_end == c->n1) ? 1 : 0;       // a partial range means the sums still have to be all-reduced
 	k_icp_sums<<<std::min(kRedBlocks, std::max(1, (c->n1 + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(c->slots.as<unsigned long long>(), c->n1, j_begin, j_end,
 		c->d_verts1, c->d_verts2, c->stats_buf.as<double>(), c->partials.as<double>(), c->sums_buf.as<double>(), c->state.as<IcpState>(),
-		c->trace.as<Ls3dIcpTrace>(), c->iter - 1);
+		c->trace.as<Ls3dIcpTrace>(), c->iter - 1, solve_here);
 	count_launch(1);
 	c->pending = true;
+	c->solved = solve_here != 0;
 	return cuda_ok(cudaGetLastError(), "k_icp_sums") ? 0 : -1;
+}
+
+extern "C" int ls3d_icp_solve(Ls3dIcp *c, void *stream) {
+	if (!c) { set_error("ls3d_icp_solve: null context"); return -1; }
+	if (!c->pending || c->solved) return 0;
+	k_icp_solve<<<1, 1, 0, (cudaStream_t)stream>>>(c->sums_buf.as<double>(), c->state.as<IcpState>(), c->trace.as<Ls3dIcpTrace>(), c->iter - 1);
+	count_launch(1);
+	c->solved = true;
+	return cuda_ok(cudaGetLastError(), "k_icp_solve") ? 0 : -1;
 }
 
 extern "C" int ls3d_icp_finish(Ls3dIcp *c, void *stream) {
 	if (!c) { set_error("ls3d_icp_finish: null context"); return -1; }
 	if (!c->pending) return 0;
+	if (!c->solved && ls3d_icp_solve(c, stream) < 0) return -1;
 	const int r = icp_launch_match(c, 1, 0, (cudaStream_t)stream);
 	c->pending = false;
 	return r;
@@ -885,7 +1008,7 @@ extern "C" int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream) {
 	if (maxIter <= 0) return 0;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (c->iter != 0 || c->pending) { set_error("ls3d_icp_run: call ls3d_icp_set_source first"); return -1; }
-	// One CUDA graph per (shape, buffers, iteration count): 3*maxIter+1 kernel nodes replayed with one launch.
+	// One CUDA graph per (shape, buffers, iteration count): 4*maxIter+1 kernel nodes replayed with one launch.
 	const bool reuse = c->graph && c->graph_iters == maxIter && c->graph_n1 == c->n1 && c->graph_n2 == c->n2 && c->graph_v1 == c->d_verts1 && c->graph_v2 == c->d_verts2 &&
 		c->graph_ib == c->i_begin && c->graph_ie == c->i_end;
 	if (!reuse) {
@@ -912,13 +1035,17 @@ extern "C" int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream) {
 	}
 	if (c->graph) {
 		if (!cuda_ok(cudaGraphLaunch(c->graph, st), "launch ICP graph")) return -1;
-		count_launch(3 * maxIter + 1);
+		count_launch(4 * maxIter + 1);
 		c->iter = maxIter;
 		c->pending = false;
 		return 0;
 	}
 	return icp_enqueue_all(c, maxIter, st);     // capture unavailable: plain stream-ordered launches
 }
+
+// Work statistics for tuning: d_stats (device, 3 u32 per source point, or NULL to switch off) receives, for the LAST match
+// stage, the octree child steps, the candidate points scanned and (resume level + 1, 0 = finished in the first kernel).
+extern "C" void ls3d_icp_set_debug(Ls3dIcp *c, void *d_stats) { if (c) c->dbg = (unsigned *)d_stats; }
 
 extern "C" long long *ls3d_icp_slots(Ls3dIcp *c) { return c ? c->slots.as<long long>() : nullptr; }
 extern "C" double *ls3d_icp_stats_buf(Ls3dIcp *c) { return c ? c->stats_buf.as<double>() : nullptr; }

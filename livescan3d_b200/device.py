@@ -179,6 +179,9 @@ class IcpSolver:
     def sums(self, j_begin=0, j_end=-1):
         native.check(self.lib.ls3d_icp_sums(self.h, int(j_begin), int(j_end), _stream()) == 0, "ls3d_icp_sums")
 
+    def solve(self):
+        native.check(self.lib.ls3d_icp_solve(self.h, _stream()) == 0, "ls3d_icp_solve")
+
     def finish(self):
         native.check(self.lib.ls3d_icp_finish(self.h, _stream()) == 0, "ls3d_icp_finish")
 
