@@ -1,0 +1,335 @@
+"""Multi-GPU host side of the hot path: one process per GPU, torch.distributed for the plumbing.
+
+Two sharded variants, both bit-identical to the single-GPU result:
+
+  ShardedFrame  one or more sensor streams per GPU.  Every rank maps, culls and neighbour-counts its own sensors
+                (no communication), the per-rank survivor counts are all-gathered (world ints), and the final
+                compaction kernel stores every surviving 16-byte record straight into EVERY rank's merged buffer at
+                its global offset over NVLink peer stores (CUDA IPC mapped memory): compaction + all-gather in one
+                kernel, no NCCL on the vertex data.  formMesh's order (sensor order, row-major inside a sensor,
+                depthprocessing.cpp:1594-1608) is kept because ranks own contiguous sensor ranges.
+
+  ShardedIcp    the target octree is replicated, the SOURCE points are partitioned.  Per iteration every rank
+                searches its slice and atomicMin's the one-to-one keys (bits(d2) << 32 | ~i, icp.cpp:95-126) into its
+                slot array; one NCCL all-reduce(MIN) over int64[n1] makes the dedupe globally exact.  Then either
+                  reduce="replicated"   every rank reduces all slots itself (same fixed-order fp64 reduction as one
+                                        GPU, so R,t are bit-identical to the single-GPU run; 1 collective / iteration)
+                  reduce="partitioned"  every rank reduces its share of the slots and the partial counts / centroid /
+                                        3x3 covariance sums are all-reduced by NCCL (f64[4] + f64[16]; 3 collectives /
+                                        iteration, the layout the north star describes).
+
+The pure planning helpers at the top (no CUDA, no library) are what the world_size-2 gloo tests in tests/ exercise.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SLOT_EMPTY = 0x7FFFFFFFFFFFFFFF
+
+
+# ---------------------------------------------------------------------------------------------------------
+# planning helpers (host logic; CPU-testable)
+# ---------------------------------------------------------------------------------------------------------
+def sensor_ranges(n_sensors: int, world: int):
+    """Contiguous, balanced sensor ranges per rank: [(first, count)] * world.  Contiguity is what keeps the merged cloud
+    in formMesh's sensor order when rank r writes at offset sum(counts of ranks < r)."""
+    if n_sensors < 0 or world <= 0:
+        raise ValueError("sensor_ranges: need n_sensors >= 0 and world > 0")
+    base, extra = divmod(n_sensors, world)
+    out, first = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((first, n))
+        first += n
+    return out
+
+
+def slice_ranges(n: int, world: int, align: int = 32):
+    """[begin, end) per rank over n items, boundaries rounded to `align` (a warp of queries never straddles two ranks)."""
+    if n < 0 or world <= 0 or align <= 0:
+        raise ValueError("slice_ranges: bad arguments")
+    per = -(-n // world)
+    per = -(-per // align) * align
+    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def exclusive_offsets(counts):
+    """Exclusive prefix sum of the per-rank survivor counts = where each rank's records start in the merged cloud."""
+    c = np.asarray(counts, dtype=np.int64).reshape(-1)
+    out = np.zeros_like(c)
+    if len(c) > 1:
+        out[1:] = np.cumsum(c[:-1])
+    return out
+
+
+def pack_slot_keys(n1: int, nn_index, nn_d2, i_offset: int = 0):
+    """The dedupe slot array a rank produces for its slice (numpy restatement of nn_commit in csrc/icp.cu, used by the CPU
+    tests): slot[j] = min over source points i with NN j of (bits(d2) << 32 | (0xFFFFFFFF - i)), else SLOT_EMPTY.
+    Smaller d2 wins; on equal d2 the LATER source index wins (icp.cpp:103).  All keys are positive as int64, so a signed
+    MIN all-reduce merges per-rank arrays exactly."""
+    idx = np.asarray(nn_index, dtype=np.int64).reshape(-1)
+    d2 = np.ascontiguousarray(nn_d2, dtype=np.float32).reshape(-1)
+    i = np.arange(len(idx), dtype=np.int64) + int(i_offset)
+    keys = (d2.view(np.uint32).astype(np.int64) << 32) | (0xFFFFFFFF - i)
+    slots = np.full(int(n1), SLOT_EMPTY, dtype=np.int64)
+    ok = idx >= 0
+    np.minimum.at(slots, idx[ok], keys[ok])
+    return slots
+
+
+def unpack_slot_keys(slots):
+    """-> (winner source index per target point or -1, d2 of the winning match)."""
+    s = np.asarray(slots, dtype=np.int64).reshape(-1)
+    has = s != SLOT_EMPTY
+    win = np.where(has, 0xFFFFFFFF - (s & 0xFFFFFFFF), -1).astype(np.int64)
+    d2 = ((s >> 32) & 0xFFFFFFFF).astype(np.uint32).view(np.float32).copy()
+    d2[~has] = 0
+    return win, d2
+
+
+def _world(group=None):
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# peer-mapped buffers (CUDA IPC between the ranks of one node)
+# ---------------------------------------------------------------------------------------------------------
+class PeerBuffer:
+    """The same-sized device allocation on every rank, each mapped into every other rank's address space: ptrs[r] is
+    rank r's buffer as seen from this process (NVLink loads/stores).  ptrs[rank] is the local allocation."""
+
+    def __init__(self, nbytes: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import native
+        self.lib = native.load()
+        self.rank, self.world = _world(group)
+        self.nbytes = int(nbytes)
+        self.local = self.lib.ls3d_dev_alloc(self.nbytes)
+        native.check(bool(self.local), "ls3d_dev_alloc")
+        self.ptrs = [None] * self.world
+        self.ptrs[self.rank] = int(self.local)
+        self._opened = []
+        if self.world > 1:
+            h = (C.c_ubyte * 64)()
+            native.check(self.lib.ls3d_ipc_export(C.c_void_p(self.local), h) == 0, "ls3d_ipc_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(h), group=group)
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    continue
+                buf = (C.c_ubyte * 64).from_buffer_copy(hb)
+                p = self.lib.ls3d_ipc_open(buf)
+                native.check(bool(p), f"ls3d_ipc_open (rank {r})")
+                self.ptrs[r] = int(p)
+                self._opened.append(p)
+
+    def tensor(self, shape, typestr):
+        from .device import view
+        return view(self.local, shape, typestr)
+
+    def close(self):
+        import ctypes as C
+        for p in self._opened:
+            self.lib.ls3d_ipc_close(C.c_void_p(p))
+        self._opened = []
+        if self.local:
+            self.lib.ls3d_dev_free(C.c_void_p(self.local))
+            self.local = None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sensor streams sharded over GPUs, merged by peer stores
+# ---------------------------------------------------------------------------------------------------------
+class ShardedFrame:
+    def __init__(self, widths, heights, group=None):
+        import torch
+        from .device import FramePipeline
+        self.group = group
+        self.rank, self.world = _world(group)
+        self.fp = FramePipeline(widths, heights)           # descriptors for the whole rig; only this rank's range is run
+        self.first, self.n_own = sensor_ranges(self.fp.n_maps, self.world)[self.rank]
+        self.merged = PeerBuffer(16 * self.fp.total_px, group)
+        dev = self.fp.device
+        self.kept_all = torch.zeros(self.world, dtype=torch.int32, device=dev)
+        self.kept_own = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.offset = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._fence = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def set_params(self, intr, wt, bounds, filter_k=10, filter_max_dist=0.01):
+        self.fp.set_params(intr, wt, bounds, filter_k, filter_max_dist)
+
+    def step(self, d_depth, d_colors):
+        """Enqueue one frame on the current stream.  d_depth / d_colors use the packed whole-rig layout; only this rank's
+        sensor range has to hold data.  Afterwards every rank's merged buffer holds the whole merged cloud (rows
+        [0, kept_all.sum()))."""
+        import torch.distributed as dist
+        if self.n_own > 0:
+            self.fp.run_count(d_depth, d_colors, self.first, self.n_own)
+            self.kept_own.copy_(self.fp.counts[3:4])
+        else:
+            self.kept_own.zero_()
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.kept_all, self.kept_own, group=self.group)
+        else:
+            self.kept_all.copy_(self.kept_own)
+        self.offset.copy_(self.kept_all[: self.rank].sum().to(self.offset.dtype).reshape(1))      # 8 ints: plumbing, not data path
+        if self.n_own > 0:
+            self.fp.merge_peers(self.merged.ptrs, self.offset, self.first, self.n_own)
+        if self.world > 1:
+            dist.all_reduce(self._fence, group=self.group)     # every rank's peer stores are complete once this returns on the stream
+
+    def result(self):
+        """Synchronise; -> (merged VertexC4ubV3f ndarray, per-rank counts)."""
+        import torch
+        from .api import VERTEX_DTYPE
+        torch.cuda.current_stream().synchronize()
+        counts = self.kept_all.cpu().numpy()
+        n = int(counts.sum())
+        v = self.merged.tensor((self.fp.total_px, 16), "|u1")[:n].cpu().numpy().reshape(-1).view(VERTEX_DTYPE)
+        return v, counts
+
+    def close(self):
+        self.merged.close()
+        self.fp.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ICP with partitioned source points
+# ---------------------------------------------------------------------------------------------------------
+class ShardedIcp:
+    def __init__(self, n1_max: int, n2_max: int, group=None, reduce: str = "replicated"):
+        from .device import IcpSolver
+        if reduce not in ("replicated", "partitioned"):
+            raise ValueError("reduce must be 'replicated' or 'partitioned'")
+        self.group = group
+        self.reduce = reduce
+        self.rank, self.world = _world(group)
+        self.solver = IcpSolver(n1_max, n2_max)
+
+    def run(self, d_verts1, d_verts2, max_iter: int, R0=None, t0=None):
+        """Enqueue a whole ICP call on the current stream.  Every rank passes the full clouds (replicated); verts2 is
+        transformed in place on every rank, so all ranks end with identical verts2, R, t."""
+        import torch.distributed as dist
+        s = self.solver
+        s.set_target(d_verts1)
+        n2 = d_verts2.numel() // 3
+        b, e = slice_ranges(n2, self.world)[self.rank]
+        s.set_source(d_verts2, b, e, R0, t0)
+        jb, je = slice_ranges(s.n1, self.world, align=1)[self.rank]
+        slots = s.slots()
+        for _ in range(int(max_iter)):
+            s.match()
+            if self.world > 1:
+                dist.all_reduce(slots, op=dist.ReduceOp.MIN, group=self.group)
+            if self.reduce == "replicated" or self.world == 1:
+                s.stats()
+                s.sums()
+            else:
+                s.stats(jb, je)
+                dist.all_reduce(s.stats_buf, group=self.group)
+                s.sums(jb, je)
+                dist.all_reduce(s.sums_buf, group=self.group)
+                s.solve()
+        s.finish()
+
+    def pose(self):
+        return self.solver.pose()
+
+    def close(self):
+        self.solver.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bench.py's "sharded" block (N > 1)
+# ---------------------------------------------------------------------------------------------------------
+def bench_sharded(args, rank, world, dev, flush):
+    """Strong-scaling variants: ONE 8-sensor rig split over the ranks (peer-store merge) and ONE ICP pair with the source
+    partitioned.  Checked against this rank's own single-GPU result before timing.  Times are CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import bench
+    from . import api
+    from .device import FramePipeline, IcpSolver
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sync():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {}
+    frame, pair = bench.make_inputs(0)                       # every rank: the SAME rig / pair (rank 0's)
+    d_depth = torch.from_numpy(frame["depth_maps"]).to(dev)
+    d_colors = torch.from_numpy(frame["depth_colors"]).to(dev)
+
+    # ---- frame: single-GPU truth on this rank, then the sharded run
+    fp = FramePipeline(frame["widths"], frame["heights"])
+    fp.set_params(frame["intr"], frame["wt"], bench.FRAME_BOUNDS, bench.FILTER_K, bench.FILTER_MAXDIST)
+    fp.run(d_depth, d_colors)
+    want, _ = fp.result()
+    want = want.copy()
+    fp.close()
+    sf = ShardedFrame(frame["widths"], frame["heights"])
+    sf.set_params(frame["intr"], frame["wt"], bench.FRAME_BOUNDS, bench.FILTER_K, bench.FILTER_MAXDIST)
+    for _ in range(max(args.warmup, 3)):
+        sf.step(d_depth, d_colors)
+    got, counts = sf.result()
+    same = got.tobytes() == want.tobytes()
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sync()
+    for i in range(args.steps):
+        flush.zero_()
+        ev_s[i].record()
+        sf.step(d_depth, d_colors)
+        ev_e[i].record()
+    sync()
+    ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / args.steps
+    ok_all = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+    out["frame_one_rig_over_ranks"] = {"ms_per_step": ms, "clouds_per_s": 1000.0 / ms, "scaling": "strong", "merged": int(counts.sum()),
+                                       "per_rank_counts": [int(c) for c in counts], "bit_identical_to_single_gpu_on_every_rank": bool(ok_all.item()),
+                                       "exchange": "all-gather of world ints (NCCL) + peer stores of 16*n_kept bytes to every rank (NVLink, CUDA IPC)"}
+    sf.close()
+
+    # ---- ICP: single-GPU truth, then partitioned source
+    A, B = bench.icp_clouds(pair, api.generate_vertices_from_depth_map)
+    dA = torch.from_numpy(A).to(dev)
+    dB0 = torch.from_numpy(B).to(dev)
+    dB = dB0.clone()
+    one = IcpSolver(len(A), len(B))
+    one.set_target(dA)
+    one.set_source(dB)
+    one.run(bench.ICP_ITERS)
+    R1, t1, _ = one.pose()
+    one.close()
+    for mode in ("replicated", "partitioned"):
+        si = ShardedIcp(len(A), len(B), reduce=mode)
+        for _ in range(max(args.warmup, 3)):
+            dB.copy_(dB0)
+            si.run(dA, dB, bench.ICP_ITERS)
+        R, t, st = si.pose()
+        sync()
+        for i in range(args.steps):
+            dB.copy_(dB0)
+            flush.zero_()
+            ev_s[i].record()
+            si.run(dA, dB, bench.ICP_ITERS)
+            ev_e[i].record()
+        sync()
+        ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / args.steps
+        out[f"icp_source_partitioned_{mode}"] = {
+            "ms_per_step": ms, "ms_per_iter": ms / bench.ICP_ITERS, "Mpts_iter_per_s": len(B) * bench.ICP_ITERS / (ms / 1000.0) / 1e6, "scaling": "strong",
+            "max_abs_dR_vs_single_gpu": float(np.max(np.abs(R.astype(np.float64) - R1))), "max_abs_dt_vs_single_gpu_m": float(np.max(np.abs(t.astype(np.float64) - t1))),
+            "status": [int(x) for x in st],
+            "collectives_per_iter": "all-reduce MIN int64[n1]" + ("" if mode == "replicated" else " + all-reduce SUM f64[4] + all-reduce SUM f64[16]")}
+        si.close()
+    return out

@@ -1,0 +1,139 @@
+"""Sharded (multi-GPU) variants on real devices: the world=1 degenerate case always, and a 2-rank NCCL run (peer-store
+merge over CUDA IPC, MIN all-reduce of the dedupe keys) whenever the box has >= 2 GPUs.  Truth = the CPU oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from common import ROOT, icp_pair, rot_err, small_frame, synth, orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pipeline_oracle(fr, bounds, k, md):
+    parts = []
+    for s in range(int(fr["n_maps"])):
+        v, _ = orc.orc_generate_mesh(fr, bounds, s)
+        xyz = np.stack([v["X"], v["Y"], v["Z"]], axis=1)
+        col = np.stack([v["R"], v["G"], v["B"], v["A"]], axis=1)
+        _, _, m = orc.orc_filter(xyz, col, k, md)
+        parts.append(v[m >= 0])
+    return np.concatenate(parts), [len(p) for p in parts]
+
+
+def _run_rank(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from livescan3d_b200 import dist as ldist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        res = {}
+        fr = small_frame(S=5, w=128, h=96)
+        d_depth = torch.from_numpy(fr["depth_maps"]).to(dev)
+        d_colors = torch.from_numpy(fr["depth_colors"]).to(dev)
+        if world > 1:
+            # only this rank's sensors hold data on this rank: poison the rest
+            first, n_own = ldist.sensor_ranges(5, world)[rank]
+            px = 128 * 96
+            mask = torch.ones(5, dtype=torch.bool)
+            mask[first:first + n_own] = False
+            for s in torch.nonzero(mask).flatten().tolist():
+                d_depth[2 * px * s:2 * px * (s + 1)] = 0x5a
+        for k, md in ((6, 0.03), (0, 0.0)):
+            sf = ldist.ShardedFrame(fr["widths"], fr["heights"])
+            sf.set_params(fr["intr"], fr["wt"], synth.DEFAULT_BOUNDS, k, md)
+            for _ in range(2):                                    # twice: buffers and control blocks are reused
+                sf.step(d_depth, d_colors)
+            v, counts = sf.result()
+            res[f"frame_{k}"] = (v.tobytes(), counts.tolist())
+            sf.close()
+
+        A, B = icp_pair(small_frame(S=2, w=128, h=96), synth.SERVER_BOUNDS)
+        dA = torch.from_numpy(A).to(dev)
+        for mode in ("replicated", "partitioned"):
+            dB = torch.from_numpy(B).to(dev)
+            si = ldist.ShardedIcp(len(A), len(B), reduce=mode)
+            si.run(dA, dB, 5)
+            R, t, st = si.pose()
+            res[f"icp_{mode}"] = (R, t, st.tolist(), dB.cpu().numpy())
+            si.close()
+        q.put((rank, res))
+        if world > 1:
+            dist.barrier()
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def _check(results, world):
+    fr = small_frame(S=5, w=128, h=96)
+    for k, md in ((6, 0.03), (0, 0.0)):
+        if k > 0:
+            want, per = _pipeline_oracle(fr, synth.DEFAULT_BOUNDS, k, md)
+        else:
+            want, per = orc.orc_generate_mesh(fr, synth.DEFAULT_BOUNDS)
+            per = [int(x) for x in per]
+        from livescan3d_b200 import dist as ldist
+        per_rank = [sum(per[f:f + n]) for f, n in ldist.sensor_ranges(5, world)]
+        for r in range(world):
+            got, counts = results[r][f"frame_{k}"]
+            assert counts == per_rank
+            assert got == want.tobytes(), f"rank {r}: merged cloud differs from the oracle (k={k})"
+    A, B = icp_pair(small_frame(S=2, w=128, h=96), synth.SERVER_BOUNDS)
+    wv, wR, wt, _ = orc.orc_icp(A, B, max_iter=5)
+    for r in range(world):
+        for mode in ("replicated", "partitioned"):
+            R, t, st, v2 = results[r][f"icp_{mode}"]
+            assert st[0] == 5 and st[1] == 0
+            assert rot_err(R, wR) <= 1e-5 and np.max(np.abs(t.astype(np.float64) - wt)) <= 1e-4      # north-star tolerances
+            assert np.max(np.abs(v2.astype(np.float64) - wv)) <= 2e-4
+        if r > 0:        # replicated reduction: every rank derives the identical pose
+            assert np.array_equal(results[r]["icp_replicated"][0], results[0]["icp_replicated"][0])
+            assert np.array_equal(results[r]["icp_replicated"][1], results[0]["icp_replicated"][1])
+
+
+def _spawn(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [ctx.Process(target=_run_rank, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=280) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return results
+
+
+@pytest.mark.timeout(300)
+def test_sharded_world1():
+    _check(_spawn(1), 1)
+
+
+@pytest.mark.timeout(300)
+def test_sharded_world2_nccl_peer_stores():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    _check(_spawn(2), 2)
+
+
+@pytest.mark.timeout(300)
+def test_sharded_world4_nccl_peer_stores():
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs >= 4 GPUs (run with gpurun --gpus 4)")
+    _check(_spawn(4), 4)
