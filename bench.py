@@ -328,7 +328,7 @@ def run_ours(args, rank, local_rank, world):
 
     # per-stage pass (event pairs recorded inside the library on the same stream), same K steps, for the roofline
     fp.enable_timing(True)
-    stage = np.zeros(8)
+    stage = np.zeros(9)
     for i in range(args.steps):
         flush.zero_()
         frame_step()

@@ -56,9 +56,11 @@ void generateVerticesFromDepthMap(unsigned char *depth_maps, unsigned char *dept
 
 /* Replaces include/NativeUtils/depthprocessing.h:108-110 (src/NativeUtils/depthprocessing.cpp:1715-1792);
  * C# binding LiveScanServer/KinectServer.cs:35-38.  All sensors -> one merged Mesh in sensor order.
- * Scope: the vertex path (bcolor_transfer=false); triangle generation is row N3 ("next"),
- * so nTriangles is 0 and `triangles` is a valid empty allocation.  Both flags are read as their low byte
- * (the C# side marshals 4-byte BOOLs, KinectServer.cs:36-38). */
+ * Result = the reference's (bcolor_transfer, bgenerate_triangles) = (false, false) branch: vertices plus the depth-grid
+ * triangles generateTriangles always produces (depthprocessing.cpp:1786, meshGenerator.cpp:76-181), indices rebased per
+ * sensor as formMesh does (:1611-1626).  The two flags only add colour correction and the multi-view vertex merge in
+ * the reference (:1757-1778); both are outside this path and the flags are ignored (read as their low byte: the C# side
+ * marshals 4-byte BOOLs, KinectServer.cs:36-38). */
 void generateMeshFromDepthMaps(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
 	float *intr_params, float *wtransform_params, Mesh *out_mesh, int bcolor_transfer,
 	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int bgenerate_triangles);
@@ -140,11 +142,19 @@ int ls3d_frame_run(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_c
 
 const void *ls3d_frame_vertices(Ls3dFrame *f);        /* device pointer: merged, filtered cloud */
 const void *ls3d_frame_culled_vertices(Ls3dFrame *f); /* device pointer: mapped+culled cloud before the filter */
-const int *ls3d_frame_count_ptr(Ls3dFrame *f);        /* device int[4]: {n_final, n_culled, error_flags, n_kept} */
+const int *ls3d_frame_count_ptr(Ls3dFrame *f);        /* device int[5]: {n_final, n_culled, error_flags, n_kept, n_triangles} */
 const int *ls3d_frame_sensor_starts(Ls3dFrame *f);    /* device int[n_maps+1]: start of each sensor in the merged cloud */
 const int *ls3d_frame_culled_starts(Ls3dFrame *f);    /* device int[n_maps+1]: same for the culled cloud */
 const int *ls3d_frame_old_to_new(Ls3dFrame *f);       /* device int[n_culled]: culled index -> merged index or -1 */
-const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f);  /* device int[sum w*h]: pixel -> culled vertex index within its sensor, or -1 */
+const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f);  /* device int[sum w*h]: pixel -> index of its vertex in the culled cloud of the run (all sensors), or -1;
+                                                         produced from the next run on (createVertices' depth_to_vertices_map + formMesh's rebasing) */
+
+/* Triangle stage (generateTrianglesGradients, meshGenerator.cpp:76-181): when enabled, every UNFILTERED run also leaves the
+ * triangles of all sensors (3 ints each: indices into the merged cloud, sensor order, raster order inside a sensor) in
+ * ls3d_frame_triangles(), their number in ls3d_frame_count_ptr()[4] and per-sensor starts in ls3d_frame_triangle_starts(). */
+void ls3d_frame_enable_triangles(Ls3dFrame *f, int on);
+const int *ls3d_frame_triangles(Ls3dFrame *f);        /* device int[3 * n_triangles] */
+const int *ls3d_frame_triangle_starts(Ls3dFrame *f);  /* device int[n_maps+1] */
 
 /* How the neighbour count enumerates candidates (results are identical; only speed differs):
  *   0 auto      : organized (pixel-window) count when every sensor's pose and intrinsics admit its bound, else voxel hash
@@ -160,9 +170,9 @@ int ls3d_set_default_filter_mode(int mode);
 /* Optional per-stage timing for the roofline report: with timing on, ls3d_frame_run brackets its kernels with CUDA
  * events on the run's stream; ls3d_frame_stage_ms waits for the last run and returns, in milliseconds (0 = stage
  * did not run): [0] map/cull/compact [1] hash clear [2] voxel insert [3] cell ranges+scatter [4] voxel-hash neighbour
- * count [5] survivor compaction [6] organized neighbour count [7] whole run.  Returns 0/-1. */
+ * count [5] survivor compaction [6] organized neighbour count [7] whole run [8] triangles.  Returns 0/-1. */
 void ls3d_frame_enable_timing(Ls3dFrame *f, int on);
-int ls3d_frame_stage_ms(Ls3dFrame *f, float out[8]);
+int ls3d_frame_stage_ms(Ls3dFrame *f, float out[9]);
 
 /* Same path, writing the merged cloud to a caller-provided device buffer at record offset read from
  * d_dst_offset (device int, may be NULL = 0): the multi-GPU merge writes peer-mapped memory through this. */

@@ -33,8 +33,9 @@ def _c(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
-def _take_mesh(lib, mesh: Mesh, what: str) -> np.ndarray:
-    """Copy Mesh.vertices out (what the C# side does with Marshal.Copy, KinectServer.cs:376-389), then deleteMesh."""
+def _take_mesh(lib, mesh: Mesh, what: str, triangles: bool = False):
+    """Copy Mesh.vertices (and Mesh.triangles) out — what the C# side does with Marshal.Copy, KinectServer.cs:342-352,
+    376-389 — then deleteMesh."""
     err = native.last_error()
     try:
         n = mesh.nVertices
@@ -43,11 +44,17 @@ def _take_mesh(lib, mesh: Mesh, what: str) -> np.ndarray:
         out = np.empty(n, dtype=VERTEX_DTYPE)
         if n > 0:
             C.memmove(out.ctypes.data, mesh.vertices, n * 16)
+        nt = mesh.nTriangles
+        if not mesh.triangles:
+            raise Ls3dError(f"{what}: Mesh.triangles must never be NULL after a call")
+        tri = np.empty((nt, 3), dtype=np.int32)
+        if nt > 0:
+            C.memmove(tri.ctypes.data, mesh.triangles, nt * 12)
     finally:
         lib.deleteMesh(C.byref(mesh))
     if err:
         raise Ls3dError(f"{what}: {err}")
-    return out
+    return (out, tri) if triangles else out
 
 
 def _frame_args(frame):
@@ -65,15 +72,16 @@ def generate_vertices_from_depth_map(frame: dict, bounds, depth_map_index: int) 
     return _take_mesh(lib, mesh, "generateVerticesFromDepthMap")
 
 
-def generate_mesh_from_depth_maps(frame: dict, bounds, color_transfer: bool = False, generate_triangles: bool = False) -> np.ndarray:
-    """All sensors -> one merged VertexC4ubV3f[n] in sensor order (vertex path of generateMeshFromDepthMaps)."""
+def generate_mesh_from_depth_maps(frame: dict, bounds, color_transfer: bool = False, generate_triangles: bool = False, triangles: bool = False):
+    """All sensors -> one merged VertexC4ubV3f[n] in sensor order; with triangles=True -> (vertices, int32[nt,3] triangles),
+    the whole Mesh generateMeshFromDepthMaps fills."""
     lib = native.load()
     d, c, w, h, ip, wt = _frame_args(frame)
     b = [float(x) for x in bounds]
     mesh = Mesh()
     lib.generateMeshFromDepthMaps(int(frame["n_maps"]), _ptr(d), _ptr(c), _ptr(w), _ptr(h), _ptr(ip), _ptr(wt), C.byref(mesh),
                                   int(bool(color_transfer)), *b, int(bool(generate_triangles)))
-    return _take_mesh(lib, mesh, "generateMeshFromDepthMaps")
+    return _take_mesh(lib, mesh, "generateMeshFromDepthMaps", triangles)
 
 
 def frame_pipeline(frame: dict, bounds, filter_k: int = 10, filter_max_dist: float = 0.01):

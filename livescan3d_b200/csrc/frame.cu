@@ -264,6 +264,101 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 }
 
 // ------------------------------------------------------------------------------------------------------
+// K1t: triangles over the depth grid
+// ------------------------------------------------------------------------------------------------------
+// MeshGenerator::checkTriangleConstraints (meshGenerator.cpp:14-62) on pixel indices a, b, c of one depth image: all three
+// depths non-zero, and every edge either flat (|dv| < thr) or continuing the gradient of the pixel one step beyond
+// either end.  thr is the reference's double-precision expression, truncated (:26) — true IEEE division by 3.0.
+__device__ __forceinline__ bool triangle_ok(const unsigned short *__restrict__ d, int a, int b, int c) {
+	const int at[3] = {a, b, c};
+	const int v[3] = {(int)__ldg(d + a), (int)__ldg(d + b), (int)__ldg(d + c)};
+	if (v[0] == 0 || v[1] == 0 || v[2] == 0) return false;
+	const int thr = (int)__dadd_rn(__dmul_rn(__ddiv_rn((double)(v[0] + v[1] + v[2]), 3.0), 0.00272), 7.273);
+#pragma unroll
+	for (int e = 0; e < 3; e++) {
+		const int i1 = e, i2 = (e + 1) % 3;
+		const int v1 = v[i1], v2 = v[i2];
+		if (abs(v1 - v2) < thr) continue;
+		const int step = at[i2] - at[i1];
+		const int fwd = (int)__ldg(d + at[i2] + step);
+		if (fwd != 0 && abs(v2 - v1 - (fwd - v2)) < thr) continue;
+		const int bwd = (int)__ldg(d + at[i1] - step);
+		if (bwd != 0 && abs(v2 - v1 - (v1 - bwd)) < thr) continue;
+		return false;
+	}
+	return true;
+}
+
+// generateTrianglesGradients (meshGenerator.cpp:76-181) for every sensor of the run + formMesh's index rebasing and
+// sensor-order concatenation (depthprocessing.cpp:1611-1626).  d2v holds GLOBAL vertex indices (K1 with kWriteD2V), so no
+// rebasing is left to do.  8 pixels per thread as in K1: a 4-bit emit mask per pixel first, then — with the tile's base from
+// the look-back scan — the index triples are stored in raster order (the reference's band threads concatenate to exactly that).
+__global__ void __launch_bounds__(kScanThreads) k_triangles(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
+	const unsigned short *__restrict__ tile_sensor, const int *__restrict__ d2v, int s_first, int s_end, FrameCtl *ctl,
+	unsigned long long *status, int *tri_starts, int *__restrict__ tri)
+{
+	__shared__ unsigned sm[16];
+	__shared__ int s_tile;
+	const int tile0 = sd[s_first].tile_begin;
+	const int ntiles = sd[s_end].tile_begin - tile0;
+	const int tid = threadIdx.x;
+	for (;;) {
+		if (tid == 0) s_tile = (int)atomicAdd(&ctl->tile_counter_b, 1u);
+		__syncthreads();
+		const int tile = s_tile;
+		if (tile >= ntiles) break;
+		const int s = tile_sensor[tile + tile0];
+		const int w = sd[s].w, h = sd[s].h, px = sd[s].px;
+		const int p0 = (tile + tile0 - sd[s].tile_begin) * kTile + tid * 8;
+		const unsigned short *dimg = reinterpret_cast<const unsigned short *>(depth + sd[s].depth_off);
+		const int *map = d2v + sd[s].pix_begin;
+		const int corner[4][3] = {{1, -w, 0}, {1, -w + 1, -w}, {0, -w + 1, -w}, {0, 1, -w + 1}};
+
+		unsigned emit = 0;          // 4 bits per pixel
+		int y = p0 / w, x = p0 - y * w;
+#pragma unroll 1
+		for (int j = 0; j < 8; j++) {
+			const int p = p0 + j;
+			if (p < px && y >= 2 && y < h - 2 && x >= 1 && x < w - 2 && __ldg(map + p) != -1) {
+				unsigned ok = 0;
+				if (triangle_ok(dimg, p, p - w, p + 1)) ok |= 1u;
+				if (triangle_ok(dimg, p + 1, p - w, p - w + 1)) ok |= 2u;
+				if (!ok) {
+					if (triangle_ok(dimg, p, p - w, p - w + 1)) ok |= 4u;
+					if (triangle_ok(dimg, p, p - w + 1, p + 1)) ok |= 8u;
+				}
+#pragma unroll
+				for (int t = 0; t < 4; t++)
+					if ((ok >> t) & 1u)
+						if (__ldg(map + p + corner[t][0]) == -1 || __ldg(map + p + corner[t][1]) == -1 || __ldg(map + p + corner[t][2]) == -1) ok &= ~(1u << t);
+				emit |= ok << (4 * j);
+			}
+			if (++x == w) { x = 0; y++; }
+		}
+		const unsigned cnt = __popc(emit);
+		unsigned total, base;
+		const unsigned off = tile_scan(cnt, sm, status, tile, &ctl->err, &total, &base);
+		int *o = tri + 3 * (size_t)(base + off);
+		unsigned rest = emit;
+#pragma unroll 1
+		while (rest) {
+			const int bit = __ffs(rest) - 1;
+			rest &= rest - 1;
+			const int p = p0 + (bit >> 2), t = bit & 3;
+			o[0] = __ldg(map + p + corner[t][0]);
+			o[1] = __ldg(map + p + corner[t][1]);
+			o[2] = __ldg(map + p + corner[t][2]);
+			o += 3;
+		}
+		if (tid == 0) {
+			if (tile + tile0 == sd[s].tile_begin) tri_starts[s] = (int)base;
+			if (tile == ntiles - 1) { tri_starts[s_end] = (int)(base + total); ctl->n_triangles = (int)(base + total); }
+		}
+		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
 // K1o: neighbour count on the ORGANIZED cloud (the depth image is a uniform grid in pixel space)
 // ------------------------------------------------------------------------------------------------------
 // Every point of a sensor's cloud comes from one pixel, so the points that can lie within maxDist of a pixel's
@@ -775,7 +870,7 @@ using namespace ls3d;
 // Frame context
 // ======================================================================================================
 // stage slots of the optional timing pass (ls3d_frame_stage_ms)
-enum { kTsMap = 0, kTsHashClear, kTsInsert, kTsRanges, kTsCount, kTsCompact, kTsOrganized, kTsWhole, kTsN };
+enum { kTsMap = 0, kTsHashClear, kTsInsert, kTsRanges, kTsCount, kTsCompact, kTsOrganized, kTsWhole, kTsTriangles, kTsN };
 enum { kModeAuto = 0, kModeVoxelHash = 1, kModeOrganized = 2 };
 
 struct Ls3dFrame {
@@ -803,15 +898,16 @@ struct Ls3dFrame {
 	int sm_count = 148;
 
 	// device memory
-	DevBuf sd, tile_sensor, rays, zero, cloud0, sorted, final_, slot_of, rank_of, keep, keep_px, map, d2v, table, cell_start, in_depth, in_colors, box;
+	DevBuf sd, tile_sensor, rays, zero, cloud0, sorted, final_, slot_of, rank_of, keep, keep_px, map, d2v, table, cell_start, in_depth, in_colors, box, tri;
 	// carve-outs of `zero` (re-zeroed by one memset per run)
 	FrameCtl *ctl = nullptr;
 	unsigned long long *status_a = nullptr, *status_b = nullptr;
-	int *culled_starts = nullptr, *final_starts = nullptr;
+	int *culled_starts = nullptr, *final_starts = nullptr, *tri_starts = nullptr;
 	size_t zero_bytes = 0;
 	// pinned read-back block: FrameCtl + starts
 	int *pin_out = nullptr;
 	bool want_d2v = false;
+	bool want_triangles = false;   // run the triangle stage after K1 (unfiltered runs only)
 	// optional per-stage timing (bench.py's roofline pass): a (begin, end) event pair per stage on the run's stream
 	bool timing = false;
 	cudaEvent_t ev[kTsN][2] = {};
@@ -834,7 +930,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static void frame_free(Ls3dFrame *f) {
 	if (!f) return;
 	DevBuf *bufs[] = {&f->sd, &f->tile_sensor, &f->rays, &f->zero, &f->cloud0, &f->sorted, &f->final_, &f->slot_of, &f->rank_of, &f->keep, &f->keep_px, &f->map, &f->d2v,
-		&f->table, &f->cell_start, &f->in_depth, &f->in_colors, &f->box};
+		&f->table, &f->cell_start, &f->in_depth, &f->in_colors, &f->box, &f->tri};
 	for (DevBuf *b : bufs) b->release();
 	if (f->pin_sd) cudaFreeHost(f->pin_sd);
 	if (f->pin_rays) cudaFreeHost(f->pin_rays);
@@ -900,7 +996,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 	const size_t ctl_b = align_up(sizeof(FrameCtl), 256);
 	const size_t st_b = align_up(sizeof(unsigned long long) * (size_t)(f->total_tiles + 1), 256);
 	const size_t starts_b = align_up(sizeof(int) * (size_t)(n_maps + 1), 256);
-	f->zero_bytes = ctl_b + 2 * st_b + 2 * starts_b;
+	f->zero_bytes = ctl_b + 2 * st_b + 3 * starts_b;
 	bool ok = f->sd.reserve(sizeof(SensorDesc) * (n_maps + 1), "alloc descriptors") && f->zero.reserve(f->zero_bytes, "alloc control block") &&
 		f->tile_sensor.reserve(sizeof(unsigned short) * (tile_sensor.size() + 1), "alloc tile table") && f->rays.reserve(sizeof(float) * (f->n_rays + 4), "alloc ray tables") &&
 		f->cloud0.reserve(16 * n, "alloc culled cloud") && f->sorted.reserve(16 * n, "alloc sorted cloud") && f->final_.reserve(16 * n, "alloc merged cloud") &&
@@ -911,7 +1007,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		f->box.reserve(sizeof(FilterBox), "alloc bbox");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_sd, sizeof(SensorDesc) * (n_maps + 1), cudaHostAllocDefault), "alloc pinned descriptors");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_rays, sizeof(float) * (f->n_rays + 4), cudaHostAllocDefault), "alloc pinned ray tables");
-	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_out, sizeof(int) * (size_t)(16 + 2 * (n_maps + 1)), cudaHostAllocDefault), "alloc pinned read-back");
+	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_out, sizeof(int) * (size_t)(16 + 3 * (n_maps + 1)), cudaHostAllocDefault), "alloc pinned read-back");
 	ok = ok && cuda_ok(cudaMemcpy(f->tile_sensor.p, tile_sensor.data(), sizeof(unsigned short) * tile_sensor.size(), cudaMemcpyHostToDevice), "upload tile table");
 	if (!ok) { frame_free(f); return nullptr; }
 	uint8_t *z = f->zero.as<uint8_t>();
@@ -920,6 +1016,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 	f->status_b = reinterpret_cast<unsigned long long *>(z + ctl_b + st_b);
 	f->culled_starts = reinterpret_cast<int *>(z + ctl_b + 2 * st_b);
 	f->final_starts = reinterpret_cast<int *>(z + ctl_b + 2 * st_b + starts_b);
+	f->tri_starts = reinterpret_cast<int *>(z + ctl_b + 2 * st_b + 2 * starts_b);
 	cudaMemset(f->zero.p, 0, f->zero_bytes);
 	return f;
 }
@@ -1062,7 +1159,7 @@ static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, i
 	const float *rays = f->rays.as<float>();
 	const unsigned *tc = reinterpret_cast<const unsigned *>(f->status_b);      // per-tile survivor counts left by the organized count
 	stage_begin(f, kTsMap, st);
-	if (f->want_d2v) {
+	if (f->want_d2v || f->want_triangles) {
 		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers);
 		else k_map_cull_compact<true, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers);
 	} else {
@@ -1177,6 +1274,18 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 			r = frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st);
 		} else {
 			r = launch_map(f, d_depth, d_colors, s_first, s_end, dst, d_dst_offset, nullptr, peers, st);     // no filter: K1 writes the result directly
+			if (r >= 0 && f->want_triangles) {
+				// K1t: the pixel->vertex map K1 just wrote + the raw depth -> index triples (status_b / tile_counter_b are free: no filter ran)
+				if (!f->tri.reserve(sizeof(int) * 6 * (size_t)f->total_px + 64, "alloc triangles")) return -1;
+				const int ntiles = f->h_sd[s_end].tile_begin - f->h_sd[s_first].tile_begin;
+				stage_begin(f, kTsTriangles, st);
+				k_triangles<<<std::max(1, std::min(ntiles, f->sm_count * 8)), kScanThreads, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->tile_sensor.as<unsigned short>(),
+					f->d2v.as<int>(), s_first, s_end, f->ctl, f->status_b, f->tri_starts, f->tri.as<int>());
+				stage_end(f, kTsTriangles, st);
+				count_launch(1);
+				if (!cuda_ok(cudaGetLastError(), "k_triangles")) return -1;
+				r += 1;
+			}
 		}
 		if (r < 0) return -1;
 		launched += r;
@@ -1245,6 +1354,13 @@ extern "C" const int *ls3d_frame_count_ptr(Ls3dFrame *f) { return f ? &f->ctl->n
 extern "C" const int *ls3d_frame_sensor_starts(Ls3dFrame *f) { return f ? ((f->filter_on && !f->last_organized) ? f->final_starts : f->culled_starts) : nullptr; }
 extern "C" const int *ls3d_frame_culled_starts(Ls3dFrame *f) { return f ? f->culled_starts : nullptr; }
 extern "C" const int *ls3d_frame_old_to_new(Ls3dFrame *f) { return (f && !(f->filter_on && f->last_organized)) ? f->map.as<int>() : nullptr; }
+extern "C" void ls3d_frame_enable_triangles(Ls3dFrame *f, int on) { if (f) f->want_triangles = on != 0; }
+extern "C" const int *ls3d_frame_triangles(Ls3dFrame *f) {
+	if (!f) return nullptr;
+	if (!f->tri.reserve(sizeof(int) * 6 * (size_t)f->total_px + 64, "alloc triangles")) return nullptr;
+	return f->tri.as<int>();
+}
+extern "C" const int *ls3d_frame_triangle_starts(Ls3dFrame *f) { return f ? f->tri_starts : nullptr; }
 extern "C" const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f) {
 	if (!f) return nullptr;
 	f->want_d2v = true;      // produced from the next run on
@@ -1289,7 +1405,7 @@ static void mesh_reset(Mesh *m) {
 // Shared body: upload sensors [first, first+n_run), run, read back.  Returns total vertices or -1.
 static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
 	float *intr_params, float *wtransform_params, Mesh *out_mesh, const float bounds[6], int first, int n_run,
-	int filter_k, float filter_maxDist, int *per_map_counts)
+	int filter_k, float filter_maxDist, int *per_map_counts, bool with_triangles = false)
 {
 	clear_error();
 	if (out_mesh) mesh_reset(out_mesh);
@@ -1305,6 +1421,7 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 	if (!cuda_ok(cudaMemcpyAsync(f->in_depth.as<uint8_t>() + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off), cudaMemcpyHostToDevice, st), "upload depth")) return -1;
 	if (!cuda_ok(cudaMemcpyAsync(f->in_colors.as<uint8_t>() + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off), cudaMemcpyHostToDevice, st), "upload colours")) return -1;
 	f->filter_mode = g_default_filter_mode;
+	f->want_triangles = with_triangles && !(filter_k > 0 && filter_maxDist > 0);
 	if (frame_set_params(f, n_maps, intr_params, wtransform_params, bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5], filter_k, filter_maxDist, st) < 0) return -1;
 	if (ls3d_frame_run(f, f->in_depth.p, f->in_colors.p, first, n_run, st) < 0) return -1;
 	// read back the counts, then exactly the bytes that exist
@@ -1330,6 +1447,16 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 		out_mesh->vertices = (VertexC4ubV3f *)host_block_alloc(sizeof(VertexC4ubV3f));   // valid empty allocation
 	}
 	out_mesh->nVertices = n;
+	const int nt = f->want_triangles ? hc->n_triangles : 0;
+	if (nt > 0) {
+		void *t = host_block_alloc((size_t)nt * 3 * sizeof(int));
+		if (!t) { set_error("out of host memory for %d triangles", nt); return -1; }
+		if (!cuda_ok(cudaMemcpyAsync(t, f->tri.p, (size_t)nt * 3 * sizeof(int), cudaMemcpyDeviceToHost, st), "read triangles") ||
+			!cuda_ok(cudaStreamSynchronize(st), "read triangles")) { host_block_free(t); return -1; }
+		free(out_mesh->triangles);
+		out_mesh->triangles = (int *)t;
+		out_mesh->nTriangles = nt;
+	}
 	return n;
 }
 
@@ -1347,8 +1474,11 @@ extern "C" void generateMeshFromDepthMaps(int n_maps, unsigned char *depth_maps,
 	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int bgenerate_triangles)
 {
 	const float b[6] = {minX, minY, minZ, maxX, maxY, maxZ};
-	(void)bcolor_transfer; (void)bgenerate_triangles;     // colour transfer and triangles are outside this path
-	host_frame(n_maps, depth_maps, depth_colors, widths, heights, intr_params, wtransform_params, out_mesh, b, 0, n_maps, 0, 0.0f, nullptr);
+	// The reference runs generateTriangles unconditionally (depthprocessing.cpp:1786); its two flags only add the colour
+	// correction and the multi-view vertex merge (:1757-1778), both outside this path, so they are read and ignored here:
+	// the result is the reference's (false, false) branch — vertices in sensor order plus their depth-grid triangles.
+	(void)bcolor_transfer; (void)bgenerate_triangles;
+	host_frame(n_maps, depth_maps, depth_colors, widths, heights, intr_params, wtransform_params, out_mesh, b, 0, n_maps, 0, 0.0f, nullptr, true);
 }
 
 extern "C" int ls3d_frame_pipeline(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,

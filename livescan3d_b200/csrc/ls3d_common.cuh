@@ -46,6 +46,8 @@ struct FrameCtl {
 	unsigned cursor;           // sorted-array range allocator
 	unsigned work_counter;     // neighbour-count work stealing
 	int n_final, n_culled, err, n_kept;   // n_kept: survivors counted by the neighbour-count kernel (known before compaction)
+	int n_triangles;           // triangles emitted by the triangle stage (0 when it did not run)
+	int pad[3];
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {

@@ -195,7 +195,7 @@ Mesh *createMesh(void) {
 
 void deleteMesh(Mesh *mesh) {
 	if (!mesh) return;
-	if (mesh->triangles) free(mesh->triangles);
+	if (mesh->triangles) host_block_free(mesh->triangles);     // a recycled pinned block, or plain malloc memory (freed as such)
 	if (mesh->vertices) host_block_free(mesh->vertices);
 	// like the reference, neither pointer is cleared and the struct itself is not freed
 }

@@ -44,7 +44,7 @@ class FramePipeline:
         self.h = self.lib.ls3d_frame_create(self.n_maps, self.widths.ctypes.data_as(C.c_void_p), self.heights.ctypes.data_as(C.c_void_p))
         native.check(bool(self.h), "ls3d_frame_create")
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.counts = view(self.lib.ls3d_frame_count_ptr(self.h), (4,), "<i4", self.device)     # n_final, n_culled, err, n_kept
+        self.counts = view(self.lib.ls3d_frame_count_ptr(self.h), (5,), "<i4", self.device)     # n_final, n_culled, err, n_kept, n_triangles
         self.filter_on = False
 
     def close(self):
@@ -89,13 +89,25 @@ class FramePipeline:
         self.lib.ls3d_frame_enable_timing(self.h, 1 if on else 0)
 
     STAGES = ["map_cull_compact", "hash_clear", "voxel_insert", "cell_ranges_scatter", "voxel_neighbour_count", "survivor_compact",
-              "organized_neighbour_count", "whole"]
+              "organized_neighbour_count", "whole", "triangles"]
 
     def stage_ms(self) -> np.ndarray:
         """Milliseconds per stage (order: FramePipeline.STAGES) of the last timed run; 0 where a stage did not run."""
-        out = np.zeros(8, dtype=np.float32)
+        out = np.zeros(9, dtype=np.float32)
         native.check(self.lib.ls3d_frame_stage_ms(self.h, out.ctypes.data_as(C.c_void_p)) == 0, "ls3d_frame_stage_ms")
         return out
+
+    def enable_triangles(self, on=True):
+        """Also produce the depth-grid triangles on unfiltered runs (generateTrianglesGradients)."""
+        self.lib.ls3d_frame_enable_triangles(self.h, 1 if on else 0)
+
+    def triangles(self) -> torch.Tensor:
+        """int32 [2 * total_px, 3] view of the triangle buffer; rows [0, counts[4]) are valid."""
+        return view(self.lib.ls3d_frame_triangles(self.h), (2 * self.total_px, 3), "<i4", self.device)
+
+    def depth_to_vertex(self) -> torch.Tensor:
+        """int32 [total_px]: pixel -> index of its vertex in the culled cloud of the run, -1 = none (from the next run on)."""
+        return view(self.lib.ls3d_frame_depth_to_vertex(self.h), (self.total_px,), "<i4", self.device)
 
     def set_filter_mode(self, mode: int):
         """0 auto, 1 voxel hash, 2 organized (pixel window)."""

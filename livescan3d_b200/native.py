@@ -67,6 +67,9 @@ _SIG = {
     "ls3d_frame_culled_starts": (_vp, [_vp]),
     "ls3d_frame_old_to_new": (_vp, [_vp]),
     "ls3d_frame_depth_to_vertex": (_vp, [_vp]),
+    "ls3d_frame_enable_triangles": (None, [_vp, _i]),
+    "ls3d_frame_triangles": (_vp, [_vp]),
+    "ls3d_frame_triangle_starts": (_vp, [_vp]),
     "ls3d_icp_create": (_vp, [_i, _i]),
     "ls3d_icp_destroy": (None, [_vp]),
     "ls3d_icp_set_target": (_i, [_vp, _vp, _i, _vp]),

@@ -366,6 +366,103 @@ int orc_generate_mesh(int n_maps, const unsigned char *depth_maps, const unsigne
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Triangle generation
+// ---------------------------------------------------------------------------------------------------
+
+// MeshGenerator::checkTriangleConstraints, src/NativeUtils/meshGenerator.cpp:14-62, on pixel indices a, b, c of one
+// depth image.  All three depths must be non-zero; every edge (a->b, b->c, c->a) must either be flat
+// (|dv| < thr) or continue the depth gradient of the pixel one step beyond either end of the edge.  The threshold
+// grows linearly with the mean depth and is evaluated in double precision, then truncated (:26).
+static bool orc_triangle_ok(const unsigned short *d, long a, long b, long c)
+{
+	const long at[3] = {a, b, c};
+	const int v[3] = {d[a], d[b], d[c]};
+	if (v[0] == 0 || v[1] == 0 || v[2] == 0) return false;
+	const int thr = (int)((v[0] + v[1] + v[2]) / 3.0 * 0.00272 + 7.273);
+	for (int e = 0; e < 3; e++) {
+		const int i1 = e, i2 = (e + 1) % 3;
+		const int v1 = v[i1], v2 = v[i2];
+		if (std::abs(v1 - v2) < thr) continue;
+		const long step = at[i2] - at[i1];
+		const int fwd = d[at[i2] + step];
+		if (fwd != 0 && std::abs(v2 - v1 - (fwd - v2)) < thr) continue;
+		const int bwd = d[at[i1] - step];
+		if (bwd != 0 && std::abs(v2 - v1 - (v1 - bwd)) < thr) continue;
+		return false;
+	}
+	return true;
+}
+
+// MeshGenerator::generateTrianglesGradients (+Region), meshGenerator.cpp:76-181: the four row bands the reference
+// hands to its threads tile [0,h) and are concatenated in order, so the result is one raster scan over
+// y in [2, h-2), x in [1, w-2) (:86-89).  For a pixel that owns a vertex, the quad {p, p-w, p-w+1, p+1} is split along
+// one diagonal (triangles 0,1) or — only when neither of those passes — the other (2,3) (:113-121); a triangle is
+// emitted when all three of its corners own vertices, with the corner order of triangles_shifts (:100-103).
+// tri receives 3 ints per triangle (per-sensor vertex indices + vertex_base); returns the triangle count.
+int orc_triangles_one(const unsigned short *depth, const int *depth_to_vertices, int w, int h, int vertex_base, int *tri)
+{
+	int n = 0;
+	const long W = w;
+	const long corner[4][3] = {{1, -W, 0}, {1, -W + 1, -W}, {0, -W + 1, -W}, {0, 1, -W + 1}};
+	for (int y = 2; y < h - 2; y++)
+		for (int x = 1; x < w - 2; x++) {
+			const long p = (long)y * w + x;
+			if (depth_to_vertices[p] == -1) continue;
+			bool ok[4] = {false, false, false, false};
+			ok[0] = orc_triangle_ok(depth, p, p - W, p + 1);
+			ok[1] = orc_triangle_ok(depth, p + 1, p - W, p - W + 1);
+			if (!ok[0] && !ok[1]) {
+				ok[2] = orc_triangle_ok(depth, p, p - W, p - W + 1);
+				ok[3] = orc_triangle_ok(depth, p, p - W + 1, p + 1);
+			}
+			for (int t = 0; t < 4; t++) {
+				if (!ok[t]) continue;
+				const int m0 = depth_to_vertices[p + corner[t][0]], m1 = depth_to_vertices[p + corner[t][1]], m2 = depth_to_vertices[p + corner[t][2]];
+				if (m0 == -1 || m1 == -1 || m2 == -1) continue;
+				tri[3 * n] = m0 + vertex_base; tri[3 * n + 1] = m1 + vertex_base; tri[3 * n + 2] = m2 + vertex_base;
+				n++;
+			}
+		}
+	return n;
+}
+
+// The bcolor_transfer = bgenerate_triangles = false branch of generateMeshFromDepthMaps (depthprocessing.cpp:1715-1792):
+// createVertices per sensor, generateTriangles (always executed, :1786) on the raw depth copy and the pixel->vertex map,
+// formMesh (:1578-1629) concatenating vertices and triangles in sensor order with the indices rebased.
+// out_triangles must hold 6*sum(w*h) ints.  Returns the vertex count; *n_triangles receives the triangle count.
+int orc_generate_mesh_triangles(int n_maps, const unsigned char *depth_maps, const unsigned char *depth_colors,
+	const int *widths, const int *heights, const float *intr_params, const float *wtransform_params,
+	const float *bounds6, void *out_vertices, int *out_triangles, int *n_triangles, int *per_map_counts, int *per_map_triangles)
+{
+	Vtx *out = (Vtx*)out_vertices;
+	size_t depth_pos = 0, colors_pos = 0;
+	int total = 0, ntri = 0;
+	for (int i = 0; i < n_maps; i++) {
+		const size_t npx = (size_t)widths[i] * heights[i];
+		std::vector<float> xyz(3 * npx);
+		std::vector<unsigned char> rgb(3 * npx);
+		std::vector<int> d2v(npx);
+		const unsigned short *dm = (const unsigned short*)(depth_maps + depth_pos);
+		int n = orc_create_vertices(dm, depth_colors + colors_pos, widths[i], heights[i], intr_params + 7 * i, wtransform_params + 12 * i, bounds6,
+			xyz.data(), rgb.data(), d2v.data(), nullptr);
+		for (int j = 0; j < n; j++) {
+			Vtx &v = out[total + j];
+			v.R = rgb[3 * j]; v.G = rgb[3 * j + 1]; v.B = rgb[3 * j + 2]; v.A = 255;
+			v.X = xyz[3 * j]; v.Y = xyz[3 * j + 1]; v.Z = xyz[3 * j + 2];
+		}
+		const int nt = orc_triangles_one(dm, d2v.data(), widths[i], heights[i], total, out_triangles + 3 * (size_t)ntri);
+		if (per_map_counts) per_map_counts[i] = n;
+		if (per_map_triangles) per_map_triangles[i] = nt;
+		total += n;
+		ntri += nt;
+		depth_pos += npx * 2;
+		colors_pos += npx * 3;
+	}
+	*n_triangles = ntri;
+	return total;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Nearest neighbours
 // ---------------------------------------------------------------------------------------------------
 

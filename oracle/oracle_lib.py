@@ -90,6 +90,26 @@ def orc_generate_mesh(frame: dict, bounds, map_index: int = -1):
     return out[:n].copy(), counts
 
 
+def orc_generate_mesh_triangles(frame: dict, bounds):
+    """The (bcolor_transfer, bgenerate_triangles) = (false, false) branch of generateMeshFromDepthMaps, triangles included
+    -> (VertexC4ubV3f[n], triangles int32[nt,3], per_map_vertex_counts, per_map_triangle_counts)"""
+    o = oracle()
+    S = int(frame["n_maps"])
+    w = np.ascontiguousarray(frame["widths"], dtype=np.int32)
+    h = np.ascontiguousarray(frame["heights"], dtype=np.int32)
+    total = int((w.astype(np.int64) * h).sum())
+    out = np.zeros(total, dtype=VERTEX_DTYPE)
+    tri = np.zeros(6 * total + 3, dtype=np.int32)
+    counts = np.zeros(S, dtype=np.int32)
+    tcounts = np.zeros(S, dtype=np.int32)
+    nt = C.c_int(0)
+    d = np.ascontiguousarray(frame["depth_maps"], dtype=np.uint8)
+    c = np.ascontiguousarray(frame["depth_colors"], dtype=np.uint8)
+    ip, wt, b = _f32(frame["intr"]), _f32(frame["wt"]), _f32(bounds)
+    n = o.orc_generate_mesh_triangles(S, _p(d), _p(c), _p(w), _p(h), _p(ip), _p(wt), _p(b), _p(out), _p(tri), C.byref(nt), _p(counts), _p(tcounts))
+    return out[:n].copy(), tri[:3 * nt.value].reshape(-1, 3).copy(), counts, tcounts
+
+
 def orc_vertex_maps(depth_u16, colors, w, h, intr7, wt12, bounds):
     """createVertices side outputs for one sensor -> (n, depth_to_vertices[w*h], vertices_to_depth[n])"""
     o = oracle()
@@ -158,7 +178,8 @@ def orc_dedupe(indices, dists, n1: int):
 # ---------------------------------------------------------------------------------------------------------
 # reference (its own sources, compiled in place)
 # ---------------------------------------------------------------------------------------------------------
-def ref_generate_mesh(frame: dict, bounds):
+def ref_generate_mesh(frame: dict, bounds, with_triangles: bool = False):
+    """-> (vertices, per_map_counts), plus triangles int32[nt,3] as a third value when with_triangles."""
     r = ref_native()
     S = int(frame["n_maps"])
     w = np.ascontiguousarray(frame["widths"], dtype=np.int32)
@@ -169,11 +190,16 @@ def ref_generate_mesh(frame: dict, bounds):
     b = [C.c_float(float(x)) for x in bounds]
     mesh = RefMesh()
     counts = np.zeros(S, dtype=np.int32)
-    r.ref_generate_mesh(S, _p(d), _p(c), _p(w), _p(h), _p(ip), _p(wt), C.byref(mesh), *b, 0, _p(counts))
+    r.ref_generate_mesh(S, _p(d), _p(c), _p(w), _p(h), _p(ip), _p(wt), C.byref(mesh), *b, 1 if with_triangles else 0, _p(counts))
     out = np.empty(mesh.nVertices, dtype=VERTEX_DTYPE)
     if mesh.nVertices:
         C.memmove(out.ctypes.data, mesh.vertices, mesh.nVertices * 16)
+    tri = np.empty(3 * mesh.nTriangles, dtype=np.int32)
+    if mesh.nTriangles:
+        C.memmove(tri.ctypes.data, mesh.triangles, mesh.nTriangles * 12)
     r.deleteMesh(C.byref(mesh))
+    if with_triangles:
+        return out, counts, tri.reshape(-1, 3)
     return out, counts
 
 

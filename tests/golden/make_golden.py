@@ -15,11 +15,11 @@ S, W, H, SEED, RING = 2, 128, 96, 1000, 8
 assert orc.have_ref(), "build oracle/_ref first (make -C oracle)"
 fr = synth.make_frame(S, W, H, seed_base=SEED, ring=RING)
 bounds = synth.DEFAULT_BOUNDS
-verts, counts = orc.ref_generate_mesh(fr, bounds)
+verts, counts, triangles = orc.ref_generate_mesh(fr, bounds, with_triangles=True)
 xyz, rgba = cloud_of(fr, bounds, 0)
 fk = np.array([10, 10, 1, 50], dtype=np.int32)
 fd = np.array([0.01, 0.1, 0.01, 0.05], dtype=np.float32)
-out = dict(S=S, w=W, h=H, seed_base=SEED, ring=RING, bounds=bounds, depth_maps=fr["depth_maps"], vertices=verts, vertex_counts=counts,
+out = dict(S=S, w=W, h=H, seed_base=SEED, ring=RING, bounds=bounds, depth_maps=fr["depth_maps"], vertices=verts, vertex_counts=counts, triangles=triangles,
            filter_k=fk, filter_maxdist=fd)
 for i, (k, md) in enumerate(zip(fk, fd)):
     out[f"filter_map_{i}"] = orc.ref_filter(xyz, rgba, int(k), float(md))[2]

@@ -89,6 +89,72 @@ def test_vertices_full_size_8_sensors(api):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# triangles (generateTrianglesGradients + formMesh's rebasing): the whole Mesh generateMeshFromDepthMaps fills
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,w,h", [(3, 128, 96), (2, 160, 120), (2, 37, 29), (1, 5, 5), (1, 4, 3), (3, 1, 7), (2, 301, 2)])
+@pytest.mark.parametrize("bname", ["default", "server"])
+def test_mesh_triangles_bit_exact(api, S, w, h, bname):
+    fr = synth.make_frame(S, w, h)
+    wv, wt, _, _ = orc.orc_generate_mesh_triangles(fr, BOUNDS[bname])
+    gv, gt = api.generate_mesh_from_depth_maps(fr, BOUNDS[bname], triangles=True)
+    assert gv.tobytes() == wv.tobytes()
+    assert gt.shape == wt.shape and np.array_equal(gt, wt)
+
+
+def test_mesh_triangles_mixed_sizes_and_full_size(api):
+    a = synth.make_frame(1, 96, 64, seed_base=11)
+    b = synth.make_frame(1, 200, 33, seed_base=12, ring=3)
+    c = synth.make_frame(1, 64, 64, seed_base=13)
+    c["depth_maps"][:] = 0                                       # a sensor that sees nothing
+    fr = {"n_maps": 3, "depth_maps": np.concatenate([a["depth_maps"], c["depth_maps"], b["depth_maps"]]),
+          "depth_colors": np.concatenate([a["depth_colors"], c["depth_colors"], b["depth_colors"]]),
+          "widths": np.array([96, 64, 200], np.int32), "heights": np.array([64, 64, 33], np.int32),
+          "intr": np.concatenate([a["intr"], c["intr"], b["intr"]]), "wt": np.concatenate([a["wt"], c["wt"], b["wt"]])}
+    wv, wt, _, wtc = orc.orc_generate_mesh_triangles(fr, synth.SERVER_BOUNDS)
+    gv, gt = api.generate_mesh_from_depth_maps(fr, synth.SERVER_BOUNDS, triangles=True)
+    assert wtc[1] == 0 and gv.tobytes() == wv.tobytes() and np.array_equal(gt, wt)
+    fr = synth.make_frame(8)                                     # 8 x 512x424
+    for bnd in (synth.DEFAULT_BOUNDS, synth.SERVER_BOUNDS):
+        wv, wt, _, _ = orc.orc_generate_mesh_triangles(fr, bnd)
+        gv, gt = api.generate_mesh_from_depth_maps(fr, bnd, triangles=True)
+        assert gv.tobytes() == wv.tobytes() and np.array_equal(gt, wt)
+        assert len(wt) > 100000
+
+
+def test_device_triangles_and_pixel_map(api):
+    import torch
+    from livescan3d_b200.device import FramePipeline
+    fr = small_frame(S=3, w=160, h=120)
+    fp = FramePipeline(fr["widths"], fr["heights"])
+    dd = torch.from_numpy(fr["depth_maps"]).cuda()
+    dc = torch.from_numpy(fr["depth_colors"]).cuda()
+    fp.set_params(fr["intr"], fr["wt"], synth.DEFAULT_BOUNDS, 0, 0.0)
+    fp.enable_triangles(True)
+    for _ in range(2):
+        fp.run(dd, dc)
+    v, counts = fp.result()
+    wv, wt, wc, wtc = orc.orc_generate_mesh_triangles(fr, synth.DEFAULT_BOUNDS)
+    nt = int(fp.counts.cpu()[4])
+    assert v.tobytes() == wv.tobytes() and nt == len(wt)
+    assert np.array_equal(fp.triangles()[:nt].cpu().numpy(), wt)
+    # pixel -> vertex map == createVertices' depth_to_vertices_map rebased by formMesh
+    d2v = fp.depth_to_vertex().cpu().numpy()
+    px, base = 160 * 120, 0
+    for s in range(3):
+        d = fr["depth_maps"].view(np.uint16)[s * px:(s + 1) * px]
+        c = fr["depth_colors"][3 * s * px:3 * (s + 1) * px]
+        n, want, _ = orc.orc_vertex_maps(d, c, 160, 120, fr["intr"][7 * s:7 * s + 7], fr["wt"][12 * s:12 * s + 12], synth.DEFAULT_BOUNDS)
+        assert np.array_equal(d2v[s * px:(s + 1) * px], np.where(want >= 0, want + base, -1))
+        base += n
+    # with the filter on, the triangle stage does not run
+    fp.set_params(fr["intr"], fr["wt"], synth.DEFAULT_BOUNDS, 10, 0.02)
+    fp.run(dd, dc)
+    fp.result()
+    assert int(fp.counts.cpu()[4]) == 0
+    fp.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
 # neighbour-count filter
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("k,md", [(10, 0.01), (10, 0.1), (1, 0.01), (50, 0.05), (3, 0.02), (200, 0.1), (2, 1e-4)])
@@ -218,7 +284,8 @@ def test_frame_pipeline_full_size_8_sensors(api, filter_mode):
 def test_golden_vectors(api):
     g = np.load(os.path.join(GOLDEN, "hotpath_small.npz"))
     fr = synth.make_frame(int(g["S"]), int(g["w"]), int(g["h"]), seed_base=int(g["seed_base"]), ring=int(g["ring"]))
-    assert api.generate_mesh_from_depth_maps(fr, g["bounds"]).tobytes() == g["vertices"].tobytes()
+    gv, gt = api.generate_mesh_from_depth_maps(fr, g["bounds"], triangles=True)
+    assert gv.tobytes() == g["vertices"].tobytes() and np.array_equal(gt, g["triangles"])
     xyz, rgba = cloud_of(fr, g["bounds"], 0)
     for i, (k, md) in enumerate(zip(g["filter_k"], g["filter_maxdist"])):
         assert np.array_equal(api.filter(xyz, rgba, int(k), float(md))[2], g[f"filter_map_{i}"])

@@ -31,6 +31,19 @@ def test_vertices_bit_exact_vs_reference(bi, seed):
 
 
 @needs_ref
+@pytest.mark.parametrize("S,w,h", [(3, 128, 96), (2, 37, 29), (1, 5, 5), (1, 4, 3), (2, 512, 424)])
+def test_triangles_bit_exact_vs_reference(S, w, h):
+    """generateTriangles + formMesh (depthprocessing.cpp:1659-1691,1611-1626; meshGenerator.cpp:14-181) through the reference's
+    own objects vs the restatement."""
+    fr = synth.make_frame(S, w, h)
+    for b in BOUNDS[:2]:
+        rv, rc, rt = orc.ref_generate_mesh(fr, b, with_triangles=True)
+        ov, ot, oc, otc = orc.orc_generate_mesh_triangles(fr, b)
+        assert rv.tobytes() == ov.tobytes() and np.array_equal(rc, oc)
+        assert rt.shape == ot.shape and np.array_equal(rt, ot) and int(otc.sum()) == len(ot)
+
+
+@needs_ref
 def test_fixture_poses_and_pixel_maps_vs_reference():
     fr = synth.make_frame(2, 160, 120, poses=synth.FIXTURE_POSES)
     for b in BOUNDS:
@@ -119,6 +132,8 @@ def test_oracle_vs_golden_vectors():
     assert fr["depth_maps"].tobytes() == g["depth_maps"].tobytes(), "synthetic generator drifted from the fixture"
     v, counts = orc.orc_generate_mesh(fr, g["bounds"])
     assert np.array_equal(counts, g["vertex_counts"]) and v.tobytes() == g["vertices"].tobytes()
+    tv, tri, _, _ = orc.orc_generate_mesh_triangles(fr, g["bounds"])
+    assert tv.tobytes() == g["vertices"].tobytes() and np.array_equal(tri, g["triangles"])
     xyz, rgba = cloud_of(fr, g["bounds"], 0)
     for i, (k, md) in enumerate(zip(g["filter_k"], g["filter_maxdist"])):
         _, _, m = orc.orc_filter(xyz, rgba, int(k), float(md))
