@@ -373,11 +373,35 @@ __global__ void __launch_bounds__(kScanThreads) k_triangles(const uint8_t *__res
 constexpr int kOrgTW = 32, kOrgTH = 8, kOrgHalo = 8;
 constexpr int kOrgSW = kOrgTW + 2 * kOrgHalo, kOrgSH = kOrgTH + 2 * kOrgHalo;
 
-__global__ void __launch_bounds__(kOrgTW * kOrgTH) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
+// count{d2 <= thr} over rows ci + dy*kOrgSW (dy = 0, -1, +1, -2, ... up to +-rv: centre rows first, so an inlier reaches k
+// after a few rows), columns -HX..+HX fully unrolled: one LDS.128 per candidate at an immediate offset, no loop bookkeeping.
+// HX is the block's column reach (>= every in-halo lane's own reach; extra candidates are real points, so counting them
+// is still exact).
+template <int HX>
+__device__ __forceinline__ int org_count_rows(const float4 *__restrict__ tile, int ci, int rv, float qx, float qy, float qz, int k, float thr) {
+	int cnt = 0;
+#pragma unroll 1
+	for (int j = 0; j <= 2 * rv && cnt < k; j++) {
+		const int dy = (j & 1) ? -((j + 1) >> 1) : (j >> 1);
+		const float4 *row = tile + ci + dy * kOrgSW - HX;
+#pragma unroll
+		for (int dx = 0; dx <= 2 * HX; dx++) {
+			const float4 c = row[dx];
+			cnt += dist2_ref(qx, qy, qz, c.x, c.y, c.z) <= thr ? 1 : 0;
+		}
+	}
+	return cnt;
+}
+
+#ifndef LS3D_ORG_MINBLOCKS
+#define LS3D_ORG_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(kOrgTW * kOrgTH, LS3D_ORG_MINBLOCKS) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
 	const float *__restrict__ rays, int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px, unsigned *tile_count)
 {
-	__shared__ float xs[kOrgSH * kOrgSW], ys[kOrgSH * kOrgSW], zs[kOrgSH * kOrgSW];
+	__shared__ float4 tile[kOrgSH * kOrgSW];
 	__shared__ unsigned s_kept;
+	__shared__ int s_hx, s_hy;
 	const int s = s_first + blockIdx.z;
 	const int w = sd[s].w, h = sd[s].h;
 	const int tx0 = blockIdx.x * kOrgTW, ty0 = blockIdx.y * kOrgTH;
@@ -386,61 +410,95 @@ __global__ void __launch_bounds__(kOrgTW * kOrgTH) k_organized_count(const uint8
 	const unsigned short *dimg = reinterpret_cast<const unsigned short *>(depth + sd[s].depth_off);
 	const float *xray = rays + sd[s].ray_off, *yray = xray + w;
 	const int tid = threadIdx.x;
-	if (tid == 0) s_kept = 0;
-
-	for (int i = tid; i < kOrgSH * kOrgSW; i += kOrgTW * kOrgTH) {
-		const int r = i / kOrgSW, c = i - r * kOrgSW;
-		const int gx = tx0 - kOrgHalo + c, gy = ty0 - kOrgHalo + r;
-		float wx = __int_as_float(0x7fc00000), wy = wx, wz = wx;
-		if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-			float ax, ay, az;
-			if (map_pixel(m, __ldg(xray + gx), __ldg(yray + gy), (unsigned)__ldg(dimg + (size_t)gy * w + gx), ax, ay, az)) { wx = ax; wy = ay; wz = az; }
-		}
-		xs[i] = wx; ys[i] = wy; zs[i] = wz;
-	}
+	if (tid == 0) { s_kept = 0; s_hx = 0; s_hy = 0; }
 	__syncthreads();
 
+	// ---- phase 0: this thread's own pixel -> world position into the tile centre, and how far its window reaches ----
 	const int lx = tid & (kOrgTW - 1), ly = tid / kOrgTW;
 	const int x = tx0 + lx, y = ty0 + ly;
-	bool kept = false;
+	const int ci = (ly + kOrgHalo) * kOrgSW + lx + kOrgHalo;
+	const float qnan = __int_as_float(0x7fc00000);
+	float qx = qnan, qy = qnan, qz = qnan;
+	int ru = 0, rv = 0;
+	bool has = false;
 	if (x < w && y < h) {
-		const int ci = (ly + kOrgHalo) * kOrgSW + lx + kOrgHalo;
-		const float qx = xs[ci], qy = ys[ci], qz = zs[ci];
-		if (qx == qx) {                                   // this pixel has a vertex
+		const unsigned d = (unsigned)__ldg(dimg + (size_t)y * w + x);
+		const float xn = __ldg(xray + x), yn = __ldg(yray + y);
+		float ax, ay, az;
+		if (map_pixel(m, xn, yn, d, ax, ay, az)) {
+			has = true;
+			qx = ax; qy = ay; qz = az;
 			const float rp = sd[s].org_rp;
-			const float zc = (float)__ldg(dimg + (size_t)y * w + x) / 1000.0f;
-			const float xn = __ldg(xray + x), yn = __ldg(yray + y);
-			const float den = zc - rp;
-			int ru = 1 << 28, rv = 1 << 28;
+			const float den = (float)d / 1000.0f - rp;
+			ru = 1 << 28; rv = 1 << 28;
 			if (den > 0.0f) {
 				const float fu = fabsf(m.fx) * rp * sqrtf(1.0f + xn * xn) / den * 1.001f + 1e-3f;
 				const float fv = fabsf(m.fy) * rp * sqrtf(1.0f + yn * yn) / den * 1.001f + 1e-3f;
 				if (fu < 1e8f) ru = (int)ceilf(fu);
 				if (fv < 1e8f) rv = (int)ceilf(fv);
 			}
-			int cnt = 0;
-			if (ru <= kOrgHalo && rv <= kOrgHalo) {
-				for (int dy = -rv; dy <= rv && cnt < k; dy++) {
-					const int row = ci + dy * kOrgSW;
-					for (int dx = -ru; dx <= ru; dx++)
-						cnt += dist2_ref(qx, qy, qz, xs[row + dx], ys[row + dx], zs[row + dx]) <= thr ? 1 : 0;
-				}
-			} else {
-				const int xa = max(0, x - min(ru, w)), xb = min(w - 1, x + min(ru, w));
-				const int ya = max(0, y - min(rv, h)), yb = min(h - 1, y + min(rv, h));
-				for (int yy = ya; yy <= yb && cnt < k; yy++) {
-					const float yny = __ldg(yray + yy);
-					for (int xx = xa; xx <= xb; xx++) {
-						float ax, ay, az;
-						if (map_pixel(m, __ldg(xray + xx), yny, (unsigned)__ldg(dimg + (size_t)yy * w + xx), ax, ay, az))
-							cnt += dist2_ref(qx, qy, qz, ax, ay, az) <= thr ? 1 : 0;
-					}
+		}
+	}
+	tile[ci] = make_float4(qx, qy, qz, 0.0f);
+	const bool in_halo = has && ru <= kOrgHalo && rv <= kOrgHalo;
+	{
+		const int mu = __reduce_max_sync(kFull, in_halo ? ru : 0), mv = __reduce_max_sync(kFull, in_halo ? rv : 0);
+		if ((tid & 31) == 0 && (mu | mv)) { atomicMax(&s_hx, mu); atomicMax(&s_hy, mv); }
+	}
+	__syncthreads();
+	const int hx = s_hx, hy = s_hy;          // block-uniform reach of the shared-memory windows (0,0: nobody needs the halo)
+
+	// ---- phase 1: stage only the halo ring that some window reaches: hy rows above/below, hx columns left/right ----
+	auto stage = [&](int r, int c) {          // tile coordinates
+		const int gx = tx0 - kOrgHalo + c, gy = ty0 - kOrgHalo + r;
+		float wx = qnan, wy = qnan, wz = qnan;
+		if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+			float ax, ay, az;
+			if (map_pixel(m, __ldg(xray + gx), __ldg(yray + gy), (unsigned)__ldg(dimg + (size_t)gy * w + gx), ax, ay, az)) { wx = ax; wy = ay; wz = az; }
+		}
+		tile[r * kOrgSW + c] = make_float4(wx, wy, wz, 0.0f);
+	};
+	if (hx | hy) {
+		for (int r = ly; r < 2 * hy; r += kOrgTH) {
+			const int row = r < hy ? kOrgHalo - hy + r : kOrgHalo + kOrgTH + (r - hy);
+			for (int c = lx; c < kOrgTW + 2 * hx; c += kOrgTW) stage(row, kOrgHalo - hx + c);
+		}
+		if (lx < 2 * hx) stage(kOrgHalo + ly, lx < hx ? kOrgHalo - hx + lx : kOrgHalo + kOrgTW + (lx - hx));
+	}
+	__syncthreads();
+
+	// ---- phase 2: count ----
+	bool kept = false;
+	if (has) {
+		int cnt = 0;
+		if (in_halo) {
+			switch (hx) {
+			case 0: cnt = org_count_rows<0>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			case 1: cnt = org_count_rows<1>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			case 2: cnt = org_count_rows<2>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			case 3: cnt = org_count_rows<3>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			case 4: cnt = org_count_rows<4>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			case 5: cnt = org_count_rows<5>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			case 6: cnt = org_count_rows<6>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			case 7: cnt = org_count_rows<7>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			default: cnt = org_count_rows<8>(tile, ci, rv, qx, qy, qz, k, thr); break;
+			}
+		} else {
+			// window larger than the halo (very near depth, large radii): walk it in global memory, recomputing candidates
+			const int xa = max(0, x - min(ru, w)), xb = min(w - 1, x + min(ru, w));
+			const int ya = max(0, y - min(rv, h)), yb = min(h - 1, y + min(rv, h));
+			for (int yy = ya; yy <= yb && cnt < k; yy++) {
+				const float yny = __ldg(yray + yy);
+				for (int xx = xa; xx <= xb; xx++) {
+					float ax, ay, az;
+					if (map_pixel(m, __ldg(xray + xx), yny, (unsigned)__ldg(dimg + (size_t)yy * w + xx), ax, ay, az))
+						cnt += dist2_ref(qx, qy, qz, ax, ay, az) <= thr ? 1 : 0;
 				}
 			}
-			kept = cnt >= k;
 		}
-		keep_px[sd[s].pix_begin + (size_t)y * w + x] = (uint8_t)(kept ? 1 : 0);
+		kept = cnt >= k;
 	}
+	if (x < w && y < h) keep_px[sd[s].pix_begin + (size_t)y * w + x] = (uint8_t)(kept ? 1 : 0);
 	// survivors per compaction tile of the map kernel (a warp is one 32-pixel row segment: it touches at most two tiles)
 	const unsigned km = __ballot_sync(kFull, kept);
 	if (km) {

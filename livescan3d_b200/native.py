@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libls3d_b200.so")
+LIB_PATH = os.environ.get("LS3D_B200_LIB") or os.path.join(_HERE, "libls3d_b200.so")     # the override is for A/B builds of the same library
 
 
 class Ls3dError(RuntimeError):
