@@ -44,7 +44,8 @@ struct IcpGrid {
 struct IcpState {
 	float R[9], t[3];       // accumulated pose (ls3d_icp_Rt points here)
 	int iters_applied, err, pad0, pad1;
-	unsigned ticket_stats, ticket_sums, n_work, pad2;
+	unsigned ticket_stats, ticket_sums, n_work, blocks_done;   // n_work: packet counter of the match stage
+	unsigned n_packets, pad3[3];                               // packets of the current source ordering
 	float xf[12];           // the update the next match kernel applies: T[3] then Rk[9] (written by the solve step)
 };
 
@@ -153,23 +154,27 @@ __global__ void k_icp_grid_params(const IcpBox *box, IcpGrid *grid, int G, int l
 	grid->levels = levels;
 }
 
-// level 0: one record per occupied cell, stored at the index of the cell's first point in the sorted array
+// level 0: one record per cell, indexed by the cell's Morton code: the tight box of its points with bit 48 set ("occupied"),
+// 0 for an empty cell
 __global__ void __launch_bounds__(256) k_icp_cellbox(const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted,
-	unsigned long long *__restrict__ cellbox, unsigned ncells)
+	unsigned long long *__restrict__ cellrec, unsigned ncells)
 {
 	const IcpGrid g = *grid;
 	for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < ncells; m += gridDim.x * blockDim.x) {
 		const unsigned s = cell_start[m], e = cell_start[m + 1];
-		if (s == e) continue;
-		float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-		for (unsigned p = s; p < e; p++) {
-			const float4 c = sorted[p];
-			const float r[3] = {c.x - g.ox, c.y - g.oy, c.z - g.oz};
+		unsigned long long rec = 0;
+		if (s != e) {
+			float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+			for (unsigned p = s; p < e; p++) {
+				const float4 c = sorted[p];
+				const float r[3] = {c.x - g.ox, c.y - g.oy, c.z - g.oz};
 #pragma unroll
-			for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], r[a]); mx[a] = fmaxf(mx[a], r[a]); }
+				for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], r[a]); mx[a] = fmaxf(mx[a], r[a]); }
+			}
+			const float nx = (float)compact3(m), ny = (float)compact3(m >> 1), nz = (float)compact3(m >> 2);
+			rec = box_encode(mn, mx, nx * g.h, ny * g.h, nz * g.h, g.h, 1u);
 		}
-		const float nx = (float)compact3(m), ny = (float)compact3(m >> 1), nz = (float)compact3(m >> 2);
-		cellbox[s] = box_encode(mn, mx, nx * g.h, ny * g.h, nz * g.h, g.h, 0u);
+		cellrec[m] = rec;
 	}
 }
 
@@ -184,14 +189,8 @@ __device__ __forceinline__ void icp_make_node(const IcpGrid &g, int l, unsigned 
 	for (unsigned c = 0; c < 8; c++) {
 		const unsigned cmp = (mp << 3) | c;
 		unsigned long long r;
-		if (l == 1) {
-			const unsigned s = cell_start[cmp], e = cell_start[cmp + 1];
-			if (s == e) continue;
-			r = cellbox[s];
-		} else {
-			r = nodes[icp_mask_off(L, l - 1) + cmp];
-			if (((r >> 48) & 0xff) == 0) continue;
-		}
+		r = l == 1 ? cellbox[cmp] : nodes[icp_mask_off(L, l - 1) + cmp];
+		if (((r >> 48) & 0xff) == 0) continue;        // empty cell / node
 		mask |= 1u << c;
 		float cmn[3], cmx[3];
 		box_decode(r, (float)compact3(cmp) * csize, (float)compact3(cmp >> 1) * csize, (float)compact3(cmp >> 2) * csize, csize, cmn, cmx);
@@ -416,122 +415,11 @@ __device__ void icp_accumulate(IcpState *st, const float *T, const float *Rk, bo
 // ------------------------------------------------------------------------------------------------------
 // nearest neighbour
 // ------------------------------------------------------------------------------------------------------
-struct Best { float d2; int idx; unsigned steps, scanned; };     // steps/scanned: work counters (debug statistics)
-
-__device__ __forceinline__ void scan_cell(const float4 *__restrict__ sorted, unsigned s, unsigned e, float qx, float qy, float qz, Best &b) {
-	b.scanned += e - s;
-	for (unsigned p = s; p < e; p++) {
-		const float4 c = __ldg(sorted + p);
-		const float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
-		const int idx = __float_as_int(c.w);
-		if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; }
-	}
-}
-
-// conservative squared distance from the (origin-relative) query to the axis-aligned box [lo, lo+size]^3
-__device__ __forceinline__ float box_lb2(float rx, float ry, float rz, float lx, float ly, float lz, float size, float slack) {
-	const float dx = fmaxf(fmaxf(lx - rx, rx - (lx + size)) - slack, 0.0f);
-	const float dy = fmaxf(fmaxf(ly - ry, ry - (ly + size)) - slack, 0.0f);
-	const float dz = fmaxf(fmaxf(lz - rz, rz - (lz + size)) - slack, 0.0f);
-	return (dx * dx + dy * dy + dz * dz) * 0.99999f;
-}
-
-// Exact nearest neighbour, bottom-up over the implicit octree:
-//   (home cell scanned by the caller) climb: at every level first ask whether everything outside the subtree
-//   already searched is provably farther than the best so far (distance to the subtree's cube faces; faces on the
-//   grid boundary have nothing behind them) and stop if so; otherwise search the siblings — a depth-first walk over
-//   the node records, nearest octant first: empty children cost nothing (mask), a child is entered only if first its
-//   cube and then the tight box of its points can still hold something closer — and climb one level.
-//   Near queries stop after a level or two, distant ones (points of the source that the target never saw) climb
-//   until their ball fits, so the result is exact at any distance like nanoflann's.
-//   `best` may arrive seeded with a real candidate (the previous iteration's neighbour).
-//
-// The walk is resumable at level boundaries: with step_budget > 0 it returns the level to resume at (>= 0) once it has
-// spent that many child steps, and -1 when the search is complete.  The match kernel runs every query with a small
-// budget and hands the expensive ones to a second kernel, so warps stay homogeneous (round-1 profile: 11 of 32 lanes
-// active when near and far queries shared warps).
-// s_stack: this thread's column of a [8][blockDim] byte array in shared memory (remaining-children masks per level).
-constexpr int kNnThreads = 256;
-
 __device__ __forceinline__ unsigned octant_permute(unsigned m, unsigned near) {      // bit c -> bit (c ^ near)
 	if (near & 1u) m = ((m & 0xAAu) >> 1) | ((m & 0x55u) << 1);
 	if (near & 2u) m = ((m & 0xCCu) >> 2) | ((m & 0x33u) << 2);
 	if (near & 4u) m = ((m & 0xF0u) >> 4) | ((m & 0x0Fu) << 4);
 	return m;
-}
-
-__device__ __forceinline__ int nn_climb(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellbox, const float4 *__restrict__ sorted, float qx, float qy, float qz, float rx, float ry, float rz,
-	unsigned hx, unsigned hy, unsigned hz, Best &best, int lvl_begin, int step_budget, unsigned char *s_stack)
-{
-	const float h = g.h, slack = 1e-3f * g.h;
-	const int G = g.G, L = g.levels;
-	unsigned nx = hx >> lvl_begin, ny = hy >> lvl_begin, nz = hz >> lvl_begin;
-	unsigned mp = morton3(hx, hy, hz) >> (3 * lvl_begin);
-	int steps = 0;
-	for (int lvl = lvl_begin; lvl < L; lvl++) {
-		if (step_budget > 0 && steps >= step_budget) return lvl;
-		// the subtree rooted at (nx,ny,nz)@lvl is done: can anything outside it still be closer?
-		const float size = h * (float)(1u << lvl);
-		const unsigned dim = (unsigned)G >> lvl;
-		float rho = INFINITY;
-		if (nx > 0) rho = fminf(rho, rx - (float)nx * size);
-		if (nx + 1 < dim) rho = fminf(rho, (float)(nx + 1) * size - rx);
-		if (ny > 0) rho = fminf(rho, ry - (float)ny * size);
-		if (ny + 1 < dim) rho = fminf(rho, (float)(ny + 1) * size - ry);
-		if (nz > 0) rho = fminf(rho, rz - (float)nz * size);
-		if (nz + 1 < dim) rho = fminf(rho, (float)(nz + 1) * size - rz);
-		rho = fmaxf(rho - slack, 0.0f);
-		if (best.d2 <= rho * rho * 0.99999f) return -1;
-
-		// siblings: depth-first from the parent (level lvl+1) with the finished child masked out
-		const int top = lvl + 1;
-		int t = top;
-		unsigned ux = nx >> 1, uy = ny >> 1, uz = nz >> 1, ump = mp >> 3;
-		unsigned nearpack = 0;
-		{
-			const unsigned pmask = ((unsigned)(nodes[icp_mask_off(L, t) + ump] >> 48) & 0xffu) & ~(1u << (mp & 7u));
-			const float half = h * (float)(1u << (t - 1));
-			const unsigned near = (rx >= (float)(2 * ux + 1) * half ? 1u : 0u) | (ry >= (float)(2 * uy + 1) * half ? 2u : 0u) | (rz >= (float)(2 * uz + 1) * half ? 4u : 0u);
-			nearpack = near << (3 * (t - 1));
-			s_stack[(t - 1) * kNnThreads] = (unsigned char)octant_permute(pmask, near);
-		}
-		for (;;) {
-			const unsigned rm = s_stack[(t - 1) * kNnThreads];
-			if (rm == 0) {
-				if (t == top) break;
-				t++;
-				ux >>= 1; uy >>= 1; uz >>= 1; ump >>= 3;
-				continue;
-			}
-			steps++;
-			best.steps++;
-			const unsigned cp = (unsigned)__ffs(rm) - 1u;
-			s_stack[(t - 1) * kNnThreads] = (unsigned char)(rm & (rm - 1u));
-			const unsigned child = cp ^ ((nearpack >> (3 * (t - 1))) & 7u);
-			const float half = h * (float)(1u << (t - 1));            // child edge
-			const unsigned ccx = (ux << 1) | (child & 1u), ccy = (uy << 1) | ((child >> 1) & 1u), ccz = (uz << 1) | (child >> 2);
-			const float bx = (float)ccx * half, by = (float)ccy * half, bz = (float)ccz * half;
-			if (box_lb2(rx, ry, rz, bx, by, bz, half, slack) > best.d2) continue;           // cube test: no memory traffic
-			const unsigned cmp = (ump << 3) | child;
-			if (t == 1) {
-				const unsigned s = cell_start[cmp], e = cell_start[cmp + 1];
-				if (rec_lb2(cellbox[s], rx, ry, rz, bx, by, bz, half, slack) > best.d2) continue;
-				scan_cell(sorted, s, e, qx, qy, qz, best);
-			} else {
-				const unsigned long long crec = nodes[icp_mask_off(L, t - 1) + cmp];
-				if (rec_lb2(crec, rx, ry, rz, bx, by, bz, half, slack) > best.d2) continue;
-				t--;
-				ux = ccx; uy = ccy; uz = ccz; ump = cmp;
-				const float q4 = half * 0.5f;
-				const unsigned near = (rx >= (float)(2 * ux + 1) * q4 ? 1u : 0u) | (ry >= (float)(2 * uy + 1) * q4 ? 2u : 0u) | (rz >= (float)(2 * uz + 1) * q4 ? 4u : 0u);
-				nearpack = (nearpack & ~(7u << (3 * (t - 1)))) | (near << (3 * (t - 1)));
-				s_stack[(t - 1) * kNnThreads] = (unsigned char)octant_permute((unsigned)(crec >> 48) & 0xffu, near);
-			}
-		}
-		nx >>= 1; ny >>= 1; nz >>= 1; mp >>= 3;
-	}
-	return -1;
 }
 
 // apply (T, Rk) the way icp.cpp:143-165 does: fp32 add, then row-vector times matrix, left to right
@@ -542,27 +430,224 @@ __device__ __forceinline__ void apply_xform(float &x, float &y, float &z, const 
 	z = __fadd_rn(__fadd_rn(__fmul_rn(a0, Rk[2]), __fmul_rn(a1, Rk[5])), __fmul_rn(a2, Rk[8]));
 }
 
-__device__ __forceinline__ void nn_commit(int i, const Best &b, unsigned long long *slots, int *__restrict__ nn_idx, float *__restrict__ nn_d2) {
-	nn_idx[i] = b.idx;
-	nn_d2[i] = b.idx >= 0 ? b.d2 : 0.0f;
-	if (b.idx >= 0) {
+__device__ __forceinline__ void nn_commit(int i, float d2, int idx, unsigned long long *slots, int *__restrict__ nn_idx, float *__restrict__ nn_d2) {
+	nn_idx[i] = idx;
+	nn_d2[i] = idx >= 0 ? d2 : 0.0f;
+	if (idx >= 0) {
 		// one-to-one dedupe (icp.cpp:95-126): smallest d2 wins the target point, the LATER source index wins ties
-		const unsigned long long key = ((unsigned long long)__float_as_uint(b.d2) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-		atomicMin(&slots[b.idx], key);
+		const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+		atomicMin(&slots[idx], key);
+	}
+}
+// ------------------------------------------------------------------------------------------------------
+// packet nearest neighbour: one warp = 32 spatially adjacent queries walking the octree together
+// ------------------------------------------------------------------------------------------------------
+// A thread-per-query walk spends most of its issue slots idle: neighbouring lanes take different paths of very
+// different length (ncu, round 1: 9-12 of 32 lanes active).  Here the source points are Morton-sorted once per call
+// (icp_build_order), so a warp's 32 queries sit within about one grid cell of each other and need nearly the same nodes.
+// The warp walks ONE path — the union of what its lanes need: every branch below is warp-uniform (ballots), the node
+// records are loaded once per warp (lanes 0-7 fetch the 8 children of a node in one request and park them in shared
+// memory, lanes 8-16 the cell ranges), candidate points are fetched 32 at a time by one coalesced request and broadcast
+// from shared memory, and only the lower-bound arithmetic and the distance tests are per lane.
+// Exactness: a node is skipped only when EVERY lane's conservative lower bound exceeds that lane's best; the climb stops only
+// when every lane's ball fits inside the subtree already searched (distance to the subtree's cube faces; faces on the grid
+// boundary have nothing behind them), so the result is exact at any distance like nanoflann's; ties resolve to the smallest
+// target index.  `best` starts from last iteration's neighbour (a real candidate, so exactness is untouched).
+constexpr int kPkWarps = 8;
+constexpr int kPkDone = 4;             // home cells scanned up front (and skipped by the walk)
+
+struct PkWarp {
+	unsigned long long rec[8][8];   // [level t-1][child]: records of the children of the node being iterated at level t
+	float4 pts[32];                 // staged candidate points
+	uint2 rng[8];                   // point ranges of the 8 cells under the current level-1 node
+	unsigned char rem[8];           // remaining (octant-permuted) child masks per level
+};
+
+// d2/idx: best real candidate so far.  bnd: pruning bound = min(d2, upper bounds proven from non-empty boxes): a non-empty box
+// holds a point no farther than its farthest corner, so the nearest neighbour is at most that far even before any point of
+// it has been seen — far queries start pruning at once instead of walking with an infinite bound (first iteration: no seed).
+struct PkLane { float qx, qy, qz, rx, ry, rz, d2, bnd; int idx; bool valid; };
+
+// conservative lower AND upper bound of the squared distance from the origin-relative query to the points summarised by a record
+__device__ __forceinline__ void rec_bounds(unsigned long long r, float rx, float ry, float rz, float ox, float oy, float oz, float size, float slack, float &lb, float &ub) {
+	float mn[3], mx[3];
+	box_decode(r, ox, oy, oz, size, mn, mx);
+	const float ax = mn[0] - rx, bx = rx - mx[0], ay = mn[1] - ry, by = ry - mx[1], az = mn[2] - rz, bz = rz - mx[2];
+	const float dx = fmaxf(fmaxf(ax, bx) - slack, 0.0f), dy = fmaxf(fmaxf(ay, by) - slack, 0.0f), dz = fmaxf(fmaxf(az, bz) - slack, 0.0f);
+	lb = (dx * dx + dy * dy + dz * dz) * 0.99999f;
+	const float fx = fmaxf(-ax, -bx) + slack, fy = fmaxf(-ay, -by) + slack, fz = fmaxf(-az, -bz) + slack;     // farthest face per axis
+	ub = (fx * fx + fy * fy + fz * fz) * 1.00001f;
+}
+
+__device__ __forceinline__ void pk_scan(const float4 *__restrict__ sorted, unsigned s, unsigned e, PkLane &q, PkWarp &sh) {
+	const int lane = threadIdx.x & 31;
+	for (unsigned base = s; base < e; base += 32) {
+		const unsigned n = min(32u, e - base);
+		__syncwarp();
+		if ((unsigned)lane < n) sh.pts[lane] = __ldg(sorted + base + lane);
+		__syncwarp();
+#pragma unroll 4
+		for (unsigned j = 0; j < n; j++) {
+			const float4 c = sh.pts[j];                           // broadcast
+			const float d2 = dist2_ref(q.qx, q.qy, q.qz, c.x, c.y, c.z);
+			const int idx = __float_as_int(c.w);
+			if (d2 < q.d2 || (d2 == q.d2 && idx < q.idx)) { q.d2 = d2; q.idx = idx; }
+		}
+	}
+	q.bnd = fminf(q.bnd, q.d2);
+}
+
+// The 8 child records of node (t; ump) -> sh.rec[t-1] (and their point ranges -> sh.rng when the children are cells).
+// Returns the mask of non-empty children.  One memory round trip: lanes 0-7 fetch the records, lanes 8-16 the ranges.
+__device__ __forceinline__ unsigned pk_load_children(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellrec, PkWarp &sh, int t, unsigned ump)
+{
+	const int lane = threadIdx.x & 31;
+	unsigned long long rec = 0;
+	__syncwarp();                                                        // earlier readers of sh.rec / sh.rng are done
+	if (lane < 8) {
+		const unsigned cmp = (ump << 3) | (unsigned)lane;
+		rec = t == 1 ? __ldg(cellrec + cmp) : __ldg(nodes + icp_mask_off(g.levels, t - 1) + cmp);      // 0 = empty
+		sh.rec[t - 1][lane] = rec;
+	} else if (t == 1 && lane < 17) {
+		// cell_start[(ump << 3) + 0 .. 8]: the 8 cells are consecutive in Morton order, so 9 values give the 8 ranges
+		const unsigned v = __ldg(cell_start + (ump << 3) + (unsigned)(lane - 8));
+		if (lane < 16) sh.rng[lane - 8].x = v;
+		if (lane > 8) sh.rng[lane - 9].y = v;
+	}
+	const unsigned exist = __ballot_sync(kFull, rec != 0ull) & 0xffu;
+	__syncwarp();
+	return exist;
+}
+
+// A first real candidate for packets in which some lane has none (first iteration, home cell empty): greedy descent from
+// the root, at every level into the non-empty child nearest to that lane, and a scan of the cell it ends in.  L node
+// visits buy every lane of the packet a bound close to its final one, so the exact walk that follows prunes like a seeded one.
+__device__ __forceinline__ void pk_greedy_seed(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, PkWarp &sh, PkLane &q, int who, float slack, unsigned &steps, unsigned &scanned)
+{
+	unsigned ux = 0, uy = 0, uz = 0, ump = 0;
+	for (int t = g.levels; t >= 1; t--) {
+		unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ump);
+		if (!exist) return;                                               // empty target: cannot happen after ls3d_icp_set_target
+		const float half = g.h * (float)(1u << (t - 1));
+		float best_lb = INFINITY;
+		unsigned best_c = (unsigned)__ffs(exist) - 1u;
+		while (exist) {
+			const unsigned c = (unsigned)__ffs(exist) - 1u;
+			exist &= exist - 1u;
+			const float bx = (float)((ux << 1) | (c & 1u)) * half, by = (float)((uy << 1) | ((c >> 1) & 1u)) * half, bz = (float)((uz << 1) | (c >> 2)) * half;
+			const float lb = rec_lb2(sh.rec[t - 1][c], q.rx, q.ry, q.rz, bx, by, bz, half, slack);
+			if (lb < best_lb) { best_lb = lb; best_c = c; }
+		}
+		const unsigned c = __shfl_sync(kFull, best_c, who);
+		steps++;
+		if (t == 1) {
+			const uint2 r = sh.rng[c];
+			scanned += r.y - r.x;
+			pk_scan(sorted, r.x, r.y, q, sh);
+			return;
+		}
+		ux = (ux << 1) | (c & 1u); uy = (uy << 1) | ((c >> 1) & 1u); uz = (uz << 1) | (c >> 2); ump = (ump << 3) | c;
 	}
 }
 
-constexpr int kNearBudget = 12;      // child steps a query may spend in the first kernel before it is deferred
-
-// apply != 0: first apply the update left in state->xf by the solve step to every source point.
-// search != 0: nearest neighbour + dedupe for the slice [i_begin, i_end); queries that exceed the step budget are
-// queued (index | resume level << 28) for k_icp_match_far with their best-so-far as the seed.
-__global__ void __launch_bounds__(kNnThreads) k_icp_match(float *__restrict__ verts2, int n2, int i_begin, int i_end, int apply, int search,
-	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellbox, const float4 *__restrict__ sorted, const float *__restrict__ verts1, unsigned long long *slots,
-	IcpState *state, unsigned *__restrict__ work, int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg)
+// Leave in sh.rem[t-1] the octant-permuted mask of the children in `allowed` that some lane still needs.
+__device__ __forceinline__ void pk_enter(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellrec, PkWarp &sh, int t, unsigned ux, unsigned uy, unsigned uz, unsigned ump, unsigned allowed,
+	PkLane &q, int ref, unsigned &nearpack, float slack)
 {
-	__shared__ unsigned char s_stack[8 * kNnThreads];
+	const int lane = threadIdx.x & 31;
+	unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ump) & allowed;
+	const float half = g.h * (float)(1u << (t - 1));                     // child edge
+	unsigned need = 0;
+	if (__any_sync(kFull, q.valid && q.bnd == INFINITY)) {
+		// some lane has no bound at all yet (first iteration, far from everything): every non-empty child proves one
+		unsigned ex = exist;
+		while (ex) {
+			const unsigned c = (unsigned)__ffs(ex) - 1u;
+			ex &= ex - 1u;
+			const float bx = (float)((ux << 1) | (c & 1u)) * half, by = (float)((uy << 1) | ((c >> 1) & 1u)) * half, bz = (float)((uz << 1) | (c >> 2)) * half;
+			float lb, ub;
+			rec_bounds(sh.rec[t - 1][c], q.rx, q.ry, q.rz, bx, by, bz, half, slack, lb, ub);
+			q.bnd = fminf(q.bnd, ub);
+		}
+	}
+	while (exist) {
+		const unsigned c = (unsigned)__ffs(exist) - 1u;
+		exist &= exist - 1u;
+		const float bx = (float)((ux << 1) | (c & 1u)) * half, by = (float)((uy << 1) | ((c >> 1) & 1u)) * half, bz = (float)((uz << 1) | (c >> 2)) * half;
+		const float lb = rec_lb2(sh.rec[t - 1][c], q.rx, q.ry, q.rz, bx, by, bz, half, slack);
+		if (__any_sync(kFull, q.valid && lb <= q.bnd)) need |= 1u << c;
+	}
+	// near-first visiting order: the octant of the reference lane's query inside this node
+	unsigned near = (q.rx >= (float)(2 * ux + 1) * half ? 1u : 0u) | (q.ry >= (float)(2 * uy + 1) * half ? 2u : 0u) | (q.rz >= (float)(2 * uz + 1) * half ? 4u : 0u);
+	near = __shfl_sync(kFull, near, ref);
+	nearpack = (nearpack & ~(7u << (3 * (t - 1)))) | (near << (3 * (t - 1)));
+	if (lane == 0) sh.rem[t - 1] = (unsigned char)octant_permute(need, near);
+	__syncwarp();
+}
+
+struct PkDone { unsigned m[kPkDone]; };
+
+// depth-first walk below node (top; ux,uy,uz,ump) whose needed-children mask pk_enter has just left in sh.rem[top-1]
+__device__ __forceinline__ void pk_walk(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, PkWarp &sh, int top, unsigned ux, unsigned uy, unsigned uz, unsigned ump,
+	PkLane &q, int ref, unsigned &nearpack, float slack, const PkDone &done, unsigned &steps, unsigned &scanned)
+{
+	const int lane = threadIdx.x & 31;
+	int t = top;
+	for (;;) {
+		const unsigned rm = sh.rem[t - 1];
+		if (rm == 0) {
+			if (t == top) break;
+			t++;
+			ux >>= 1; uy >>= 1; uz >>= 1; ump >>= 3;
+			continue;
+		}
+		const unsigned cp = (unsigned)__ffs(rm) - 1u;
+		__syncwarp();
+		if (lane == 0) sh.rem[t - 1] = (unsigned char)(rm & (rm - 1u));
+		__syncwarp();
+		const unsigned child = cp ^ ((nearpack >> (3 * (t - 1))) & 7u);
+		const unsigned cmp = (ump << 3) | child;
+		if (t == 1) {
+			bool skip = false;
+#pragma unroll
+			for (int d = 0; d < kPkDone; d++) skip |= done.m[d] == cmp;     // a home cell: already scanned
+			if (skip) continue;
+		}
+		const float half = g.h * (float)(1u << (t - 1));
+		const unsigned ccx = (ux << 1) | (child & 1u), ccy = (uy << 1) | ((child >> 1) & 1u), ccz = (uz << 1) | (child >> 2);
+		// the bounds have tightened since this child was queued: test again before paying for the visit
+		const float lb = rec_lb2(sh.rec[t - 1][child], q.rx, q.ry, q.rz, (float)ccx * half, (float)ccy * half, (float)ccz * half, half, slack);
+		if (!__any_sync(kFull, q.valid && lb <= q.bnd)) continue;
+		steps++;
+		if (t == 1) {
+			const uint2 r = sh.rng[child];
+			scanned += r.y - r.x;
+			pk_scan(sorted, r.x, r.y, q, sh);
+		} else {
+			t--;
+			ux = ccx; uy = ccy; uz = ccz; ump = cmp;
+			pk_enter(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, 0xffu, q, ref, nearpack, slack);
+		}
+	}
+}
+
+// order[k], k in [0, i_end - i_begin): the slice's source indices in Morton order of their (initial) home cells.
+// apply != 0: first apply the update left in state->xf by the solve step to the points of the slice (points outside the
+// slice are transformed by k_icp_apply).
+#ifndef LS3D_PK_MINBLOCKS
+#define LS3D_PK_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_packet(float *__restrict__ verts2, int i_begin, int i_end, int apply,
+	const unsigned *__restrict__ order, const uint2 *__restrict__ desc, const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, const float *__restrict__ verts1, unsigned long long *slots,
+	IcpState *state, int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg)
+{
+	__shared__ PkWarp s_pk[kPkWarps];
+	PkWarp &sh = s_pk[threadIdx.x >> 5];
 	float T[3] = {0.f, 0.f, 0.f}, Rk[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
 	if (apply) {
 #pragma unroll
@@ -572,80 +657,145 @@ __global__ void __launch_bounds__(kNnThreads) k_icp_match(float *__restrict__ ve
 	}
 	const IcpGrid g = *grid;
 	const int lane = threadIdx.x & 31;
-	const int n_pad = (n2 + 31) & ~31;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-		int resume = -1;
-		if (i < n2) {
+	const int L = g.levels;
+	const float slack = 1e-3f * g.h;
+	const int n_packets = (int)state->n_packets;
+	for (;;) {
+		int pk = 0;
+		if (lane == 0) pk = (int)atomicAdd(&state->n_work, 1u);
+		pk = __shfl_sync(kFull, pk, 0);
+		if (pk >= n_packets) break;
+		const uint2 pd = __ldg(desc + pk);
+		const int i = (unsigned)lane < pd.y ? (int)__ldg(order + pd.x + lane) : -1;
+		PkLane q;
+		q.valid = false; q.d2 = INFINITY; q.bnd = INFINITY; q.idx = -1;
+		q.qx = q.qy = q.qz = q.rx = q.ry = q.rz = 0.0f;
+		unsigned mp = 0, hx = 0, hy = 0, hz = 0;
+		if (i >= 0) {
 			float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
+			const int prev = nn_idx[i];
 			if (apply) {
 				apply_xform(x, y, z, T, Rk);
 				verts2[3 * (size_t)i] = x; verts2[3 * (size_t)i + 1] = y; verts2[3 * (size_t)i + 2] = z;
 			}
-			if (search) {
-				Best b;
-				b.d2 = INFINITY;
-				b.idx = -1;
-				b.steps = 0; b.scanned = 0;
-				if (i >= i_begin && i < i_end) {
-					// seed with last iteration's neighbour: a real candidate, so exactness is untouched, and the source
-					// barely moves between iterations, so the bound is already nearly tight
-					const int prev = nn_idx[i];
-					if (prev >= 0) {
-						b.idx = prev;
-						b.d2 = dist2_ref(x, y, z, verts1[3 * (size_t)prev], verts1[3 * (size_t)prev + 1], verts1[3 * (size_t)prev + 2]);
-						if (!(b.d2 == b.d2)) { b.d2 = INFINITY; b.idx = -1; }
-					}
-					const float rx = x - g.ox, ry = y - g.oy, rz = z - g.oz;
-					if (isfinite(rx) && isfinite(ry) && isfinite(rz)) {
-						const unsigned hx = (unsigned)icp_cell(rx, g.inv_h, g.G), hy = (unsigned)icp_cell(ry, g.inv_h, g.G), hz = (unsigned)icp_cell(rz, g.inv_h, g.G);
-						const unsigned m = morton3(hx, hy, hz);
-						const unsigned s = cell_start[m], e = cell_start[m + 1];
-						if (s != e) scan_cell(sorted, s, e, x, y, z, b);
-						resume = nn_climb(g, cell_start, nodes, cellbox, sorted, x, y, z, rx, ry, rz, hx, hy, hz, b, 0, kNearBudget, s_stack + threadIdx.x);
-					}
-					if (resume < 0) nn_commit(i, b, slots, nn_idx, nn_d2);
-					else { nn_idx[i] = b.idx; nn_d2[i] = b.d2; }          // the seed for the far kernel
-					if (dbg) { dbg[3 * (size_t)i] = b.steps; dbg[3 * (size_t)i + 1] = b.scanned; dbg[3 * (size_t)i + 2] = (unsigned)(resume + 1); }
-				} else {
-					nn_idx[i] = -1;
-					nn_d2[i] = 0.0f;
+			q.qx = x; q.qy = y; q.qz = z;
+			q.rx = x - g.ox; q.ry = y - g.oy; q.rz = z - g.oz;
+			q.valid = isfinite(q.rx) && isfinite(q.ry) && isfinite(q.rz);
+			if (q.valid) {
+				if (prev >= 0) {
+					const float d2 = dist2_ref(x, y, z, verts1[3 * (size_t)prev], verts1[3 * (size_t)prev + 1], verts1[3 * (size_t)prev + 2]);
+					if (d2 == d2) { q.d2 = d2; q.bnd = d2; q.idx = prev; }
 				}
+				hx = (unsigned)icp_cell(q.rx, g.inv_h, g.G); hy = (unsigned)icp_cell(q.ry, g.inv_h, g.G); hz = (unsigned)icp_cell(q.rz, g.inv_h, g.G);
+				mp = morton3(hx, hy, hz);
 			}
 		}
-		// queue the deferred queries (warp-aggregated)
-		const unsigned dm = __ballot_sync(kFull, resume >= 0);
-		if (dm) {
-			unsigned base = 0;
-			if (lane == __ffs(dm) - 1) base = atomicAdd(&state->n_work, (unsigned)__popc(dm));
-			base = __shfl_sync(kFull, base, __ffs(dm) - 1);
-			if (resume >= 0) work[base + __popc(dm & ((1u << lane) - 1u))] = (unsigned)i | ((unsigned)resume << 28);
+		const unsigned vmask = __ballot_sync(kFull, q.valid);
+		unsigned steps = 0, scanned = 0;
+		if (vmask) {
+			const int ref = __ffs(vmask) - 1;
+			const unsigned mp_ref = __shfl_sync(kFull, mp, ref);
+			const unsigned rhx = __shfl_sync(kFull, hx, ref), rhy = __shfl_sync(kFull, hy, ref), rhz = __shfl_sync(kFull, hz, ref);
+			// ---- the home cells first: every lane gets a finite bound before the walk starts ----
+			PkDone done;
+#pragma unroll
+			for (int d = 0; d < kPkDone; d++) done.m[d] = 0xffffffffu;
+			{
+				unsigned todo = vmask;
+#pragma unroll
+				for (int d = 0; d < kPkDone; d++) {
+					if (todo) {
+						const unsigned m = __shfl_sync(kFull, mp, __ffs(todo) - 1);
+						todo &= ~__ballot_sync(kFull, q.valid && mp == m);
+						done.m[d] = m;
+						const unsigned s = __ldg(cell_start + m), e = __ldg(cell_start + m + 1);
+						if (s != e) { steps++; scanned += e - s; pk_scan(sorted, s, e, q, sh); }
+					}
+				}
+			}
+			{
+				const unsigned unseeded = __ballot_sync(kFull, q.valid && q.idx < 0);
+				if (unseeded) pk_greedy_seed(g, cell_start, nodes, cellrec, sorted, sh, q, __ffs(unseeded) - 1, slack, steps, scanned);
+			}
+			const unsigned diff = __reduce_or_sync(kFull, q.valid ? (mp ^ mp_ref) : 0u);
+			int lvl = diff ? (31 - __clz((int)diff)) / 3 + 1 : 0;      // lowest level whose node holds every lane's home cell
+			unsigned nearpack = 0;
+			unsigned nx = rhx >> lvl, ny = rhy >> lvl, nz = rhz >> lvl, nmp = mp_ref >> (3 * lvl);
+			// ---- the subtree all home cells share (level 0: the one home cell, done above) ----
+			if (lvl > 0) {
+				pk_enter(g, cell_start, nodes, cellrec, sh, lvl, nx, ny, nz, nmp, 0xffu, q, ref, nearpack, slack);
+				pk_walk(g, cell_start, nodes, cellrec, sorted, sh, lvl, nx, ny, nz, nmp, q, ref, nearpack, slack, done, steps, scanned);
+			}
+			// ---- climb: siblings of the finished subtree, level by level, until every lane's ball fits inside it ----
+			for (; lvl < L; lvl++) {
+				const float size = g.h * (float)(1u << lvl);
+				const unsigned dim = (unsigned)g.G >> lvl;
+				float rho = INFINITY;
+				if (nx > 0) rho = fminf(rho, q.rx - (float)nx * size);
+				if (nx + 1 < dim) rho = fminf(rho, (float)(nx + 1) * size - q.rx);
+				if (ny > 0) rho = fminf(rho, q.ry - (float)ny * size);
+				if (ny + 1 < dim) rho = fminf(rho, (float)(ny + 1) * size - q.ry);
+				if (nz > 0) rho = fminf(rho, q.rz - (float)nz * size);
+				if (nz + 1 < dim) rho = fminf(rho, (float)(nz + 1) * size - q.rz);
+				rho = fmaxf(rho - slack, 0.0f);
+				if (!__any_sync(kFull, q.valid && !(q.d2 <= rho * rho * 0.99999f))) break;
+				const unsigned done_child = nmp & 7u;
+				nx >>= 1; ny >>= 1; nz >>= 1; nmp >>= 3;
+				pk_enter(g, cell_start, nodes, cellrec, sh, lvl + 1, nx, ny, nz, nmp, 0xffu & ~(1u << done_child), q, ref, nearpack, slack);
+				pk_walk(g, cell_start, nodes, cellrec, sorted, sh, lvl + 1, nx, ny, nz, nmp, q, ref, nearpack, slack, done, steps, scanned);
+			}
 		}
+		if (i >= 0) {
+			nn_commit(i, q.d2, q.valid ? q.idx : -1, slots, nn_idx, nn_d2);
+			if (dbg) { dbg[3 * (size_t)i] = steps; dbg[3 * (size_t)i + 1] = scanned; dbg[3 * (size_t)i + 2] = 0u; }
+		}
+		__syncwarp();
+	}
+	// the last block to run dry re-arms the packet counter for the next match stage
+	__syncthreads();
+	if (threadIdx.x == 0 && atomicAdd(&state->blocks_done, 1u) == gridDim.x - 1) {
+		state->blocks_done = 0;
+		state->n_work = 0;
 	}
 }
 
-// the deferred (distant) queries: the same climb, resumed, with no budget
-__global__ void __launch_bounds__(kNnThreads) k_icp_match_far(const float *__restrict__ verts2, const IcpGrid *__restrict__ grid,
-	const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes, const unsigned long long *__restrict__ cellbox,
-	const float4 *__restrict__ sorted, unsigned long long *slots, const IcpState *state, const unsigned *__restrict__ work,
-	int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg)
-{
-	__shared__ unsigned char s_stack[8 * kNnThreads];
-	const IcpGrid g = *grid;
-	const unsigned n_work = state->n_work;
-	for (unsigned wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
-		const unsigned ent = work[wi];
-		const int i = (int)(ent & 0x0FFFFFFFu), lvl = (int)(ent >> 28);
-		const float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
-		Best b;
-		b.idx = nn_idx[i];
-		b.d2 = b.idx >= 0 ? nn_d2[i] : INFINITY;
-		b.steps = 0; b.scanned = 0;
-		const float rx = x - g.ox, ry = y - g.oy, rz = z - g.oz;
-		const unsigned hx = (unsigned)icp_cell(rx, g.inv_h, g.G), hy = (unsigned)icp_cell(ry, g.inv_h, g.G), hz = (unsigned)icp_cell(rz, g.inv_h, g.G);
-		nn_climb(g, cell_start, nodes, cellbox, sorted, x, y, z, rx, ry, rz, hx, hy, hz, b, lvl, 0, s_stack + threadIdx.x);
-		nn_commit(i, b, slots, nn_idx, nn_d2);
-		if (dbg) { dbg[3 * (size_t)i] += b.steps; dbg[3 * (size_t)i + 1] += b.scanned; }
+// Packets = runs of at most 32 consecutive entries of the Morton order that never leave one level-kPkRunLevel node: a packet
+// that straddled distant nodes (isolated points — flying pixels — sort next to each other but lie far apart) would drag one
+// warp through 32 unrelated searches in series; cut at node boundaries, such points become many small packets that run in
+// parallel on warps that would otherwise idle.
+constexpr int kPkRunLevel = 2;
+__global__ void __launch_bounds__(256) k_icp_packets(const unsigned *__restrict__ src_start, unsigned n_runs, uint2 *__restrict__ desc, IcpState *state) {
+	for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += gridDim.x * blockDim.x) {
+		const unsigned s = src_start[r << (3 * kPkRunLevel)], e = src_start[(r + 1) << (3 * kPkRunLevel)];
+		if (s == e) continue;
+		const unsigned n = e - s, np = (n + 31) >> 5;
+		const unsigned base = atomicAdd(&state->n_packets, np);
+		for (unsigned j = 0; j < np; j++) desc[base + j] = make_uint2(s + 32 * j, min(32u, n - 32 * j));
 	}
+}
+
+// (T, Rk) applied to the source points in [a0, a1) and [b0, b1): the final update of a call, and the points outside a rank's slice
+__global__ void __launch_bounds__(256) k_icp_apply(float *__restrict__ verts2, int a0, int a1, int b0, int b1, const IcpState *state) {
+	float T[3], Rk[9];
+#pragma unroll
+	for (int a = 0; a < 3; a++) T[a] = state->xf[a];
+#pragma unroll
+	for (int a = 0; a < 9; a++) Rk[a] = state->xf[3 + a];
+	const int na = a1 - a0, nb = b1 - b0;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < na + nb; j += gridDim.x * blockDim.x) {
+		const int i = j < na ? a0 + j : b0 + (j - na);
+		float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
+		apply_xform(x, y, z, T, Rk);
+		verts2[3 * (size_t)i] = x; verts2[3 * (size_t)i + 1] = y; verts2[3 * (size_t)i + 2] = z;
+	}
+}
+
+// Morton order of the slice's source points on the TARGET grid (counting sort: count -> exclusive scan -> scatter)
+__global__ void __launch_bounds__(256) k_icp_order_scatter(int i_begin, int n_slice, const unsigned *__restrict__ cell_of, const unsigned *__restrict__ rank_of,
+	const unsigned *__restrict__ src_start, unsigned *__restrict__ order)
+{
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_slice; j += gridDim.x * blockDim.x)
+		order[src_start[cell_of[j]] + rank_of[j]] = (unsigned)(i_begin + j);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -706,7 +856,6 @@ __global__ void __launch_bounds__(256) k_icp_stats(const unsigned long long *__r
 	double *partials, double *stats_buf, IcpState *state)
 {
 	__shared__ double smem[8 * 3];
-	if (blockIdx.x == 0 && threadIdx.x == 0) state->n_work = 0;       // both match kernels of this iteration are done
 	double v[3] = {0, 0, 0};
 	for (int j = j_begin + blockIdx.x * blockDim.x + threadIdx.x; j < j_end; j += gridDim.x * blockDim.x) {
 		const unsigned long long key = slots[j];
@@ -791,6 +940,8 @@ __global__ void k_icp_init_state(IcpState *st, Pose12 p) {
 	st->ticket_stats = 0;
 	st->ticket_sums = 0;
 	st->n_work = 0;
+	st->blocks_done = 0;
+	st->n_packets = 0;
 	for (int i = 0; i < 12; i++) st->xf[i] = (i == 3 || i == 7 || i == 11) ? 1.0f : 0.0f;
 }
 
@@ -813,6 +964,8 @@ struct Ls3dIcp {
 	const float *d_verts1 = nullptr;
 	float *d_verts2 = nullptr;
 	DevBuf grid, box, state, cell_start, nodes, cellbox, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, work, trace, small;
+	DevBuf src_start, src_cell, src_rank, pk_desc;   // Morton ordering of the source slice (work = the order itself) and its packets
+	bool order_valid = false;
 	DevBuf own_v1, own_v2;        // device copies for the host-buffer API
 	float *pin = nullptr;         // pinned read-back: Rt[12] + status[4]
 	cudaGraphExec_t graph = nullptr;
@@ -823,7 +976,7 @@ struct Ls3dIcp {
 static void icp_free(Ls3dIcp *c) {
 	if (!c) return;
 	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->nodes, &c->cellbox, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
-		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->work, &c->trace, &c->small, &c->own_v1, &c->own_v2};
+		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->work, &c->trace, &c->small, &c->own_v1, &c->own_v2, &c->src_start, &c->src_cell, &c->src_rank, &c->pk_desc};
 	for (DevBuf *b : bufs) b->release();
 	if (c->pin) cudaFreeHost(c->pin);
 	if (c->graph) cudaGraphExecDestroy(c->graph);
@@ -846,7 +999,8 @@ extern "C" Ls3dIcp *ls3d_icp_create(int n1_max, int n2_max) {
 		c->slots.reserve(8 * n1, "alloc slots") && c->partials.reserve(sizeof(double) * 16 * kRedBlocks, "alloc partials") &&
 		c->stats_buf.reserve(sizeof(double) * 4, "alloc stats") && c->sums_buf.reserve(sizeof(double) * 16, "alloc sums") &&
 		c->nn_idx.reserve(4 * n2, "alloc nn index") && c->nn_d2.reserve(4 * n2, "alloc nn dist") && c->work.reserve(4 * n2 + 256, "alloc work list") &&
-		c->trace.reserve(sizeof(Ls3dIcpTrace) * kTraceCap, "alloc trace") && c->small.reserve(256, "alloc small");
+		c->trace.reserve(sizeof(Ls3dIcpTrace) * kTraceCap, "alloc trace") && c->small.reserve(256, "alloc small") &&
+		c->src_cell.reserve(4 * n2, "alloc source cells") && c->src_rank.reserve(4 * n2, "alloc source ranks");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin, 256, cudaHostAllocDefault), "alloc pinned read-back");
 	if (!ok) { icp_free(c); return nullptr; }
 	cudaMemset(c->stats_buf.p, 0, sizeof(double) * 4);
@@ -866,6 +1020,7 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 	cudaStream_t st = (cudaStream_t)stream;
 	c->d_verts1 = (const float *)d_verts1;
 	c->n1 = n1;
+	c->order_valid = false;
 	c->levels = n1 <= 32768 ? 6 : (n1 <= 1000000 ? 7 : 8);
 	c->G = 1 << c->levels;
 	const size_t cells = (size_t)c->G * c->G * c->G;
@@ -874,7 +1029,9 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 	unsigned mask_total = 0;
 	for (int l = 1; l <= c->levels; l++) { const unsigned n = (unsigned)(c->G >> l); mask_total += n * n * n; }
 	if (!c->cell_start.reserve(4 * (cells + 8), "alloc cell starts") || !c->scan_status.reserve(8 * (size_t)(scan_tiles + 1), "alloc scan status") ||
-		!c->nodes.reserve(8 * (size_t)(mask_total + 16), "alloc octree nodes") || !c->cellbox.reserve(8 * (size_t)c->n1_max, "alloc cell boxes")) return -1;
+		!c->nodes.reserve(8 * (size_t)(mask_total + 16), "alloc octree nodes") || !c->cellbox.reserve(8 * (cells + 8), "alloc cell records") ||
+		!c->src_start.reserve(4 * (cells + 8), "alloc source cell starts") ||
+		!c->pk_desc.reserve(8 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet table")) return -1;
 	IcpBox hb;
 	for (int a = 0; a < 3; a++) { hb.mn[a] = 0xffffffffu; hb.mx[a] = 0u; }
 	bool ok = cuda_ok(cudaMemcpyAsync(c->box.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, st), "init bbox") &&
@@ -919,6 +1076,7 @@ extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_beg
 	c->i_end = i_end;
 	c->iter = 0;
 	c->pending = false;
+	c->order_valid = false;
 	if (n2 > 0 && !cuda_ok(cudaMemsetAsync(c->nn_idx.p, 0xff, 4 * (size_t)n2, st), "reset nn index")) return -1;     // no previous neighbour yet
 	Pose12 pose;
 	memcpy(pose.v, R0, 9 * sizeof(float));
@@ -928,19 +1086,53 @@ extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_beg
 	return cuda_ok(cudaGetLastError(), "k_icp_init_state") ? 0 : -1;
 }
 
+// Morton order of the slice's source points on the target grid (once per ls3d_icp_set_source; the source only moves by a
+// small rigid transform afterwards, so the packets stay compact).  Returns kernels launched or -1.
+static int icp_build_order(Ls3dIcp *c, cudaStream_t st) {
+	const int n_slice = c->i_end - c->i_begin;
+	if (n_slice <= 0) { c->order_valid = true; return 0; }
+	const size_t cells = (size_t)c->G * c->G * c->G;
+	const int scan_n = (int)cells + 1;
+	const int scan_tiles = (scan_n + kTile - 1) / kTile;
+	if (c->src_start.cap < 4 * (cells + 8)) { set_error("ICP: source ordering scratch not allocated (ls3d_icp_set_target first)"); return -1; }   // never allocate here: this may run under stream capture
+	bool ok = cuda_ok(cudaMemsetAsync(c->src_start.p, 0, 4 * (cells + 8), st), "clear source cells") &&
+		cuda_ok(cudaMemsetAsync(c->scan_status.p, 0, 8 * (size_t)(scan_tiles + 1), st), "clear scan status") &&
+		cuda_ok(cudaMemsetAsync(c->small.p, 0, 256, st), "clear counters");
+	if (!ok) return -1;
+	const int nb = std::max(1, std::min((n_slice + 255) / 256, c->sm_count * 8));
+	k_icp_count<<<nb, 256, 0, st>>>(c->d_verts2 + 3 * (size_t)c->i_begin, n_slice, c->grid.as<IcpGrid>(), c->src_start.as<unsigned>(), c->src_cell.as<unsigned>(), c->src_rank.as<unsigned>());
+	k_exclusive_scan<<<std::min(scan_tiles, c->sm_count * 8), kScanThreads, 0, st>>>(c->src_start.as<unsigned>(), scan_n, c->small.as<unsigned>(), c->scan_status.as<unsigned long long>(), c->small.as<int>() + 1);
+	k_icp_order_scatter<<<nb, 256, 0, st>>>(c->i_begin, n_slice, c->src_cell.as<unsigned>(), c->src_rank.as<unsigned>(), c->src_start.as<unsigned>(), c->work.as<unsigned>());
+	const unsigned n_runs = (unsigned)(cells >> (3 * kPkRunLevel));
+	if (!cuda_ok(cudaMemsetAsync(&c->state.as<IcpState>()->n_packets, 0, sizeof(unsigned), st), "clear packet count")) return -1;
+	k_icp_packets<<<std::max(1u, std::min((n_runs + 255) / 256, (unsigned)c->sm_count * 8)), 256, 0, st>>>(c->src_start.as<unsigned>(), n_runs, c->pk_desc.as<uint2>(), c->state.as<IcpState>());
+	count_launch(4);
+	if (!cuda_ok(cudaGetLastError(), "source ordering kernels")) return -1;
+	c->order_valid = true;
+	return 4;
+}
+
 static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) {
-	if (c->n2 >= (1 << 28)) { set_error("ICP: at most 2^28-1 source points"); return -1; }
-	const int nb = pt_blocks(c, std::max(c->n2, 1));
-	k_icp_match<<<nb, kNnThreads, 0, st>>>(c->d_verts2, c->n2, c->i_begin, c->i_end, apply, search,
-		c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(), c->d_verts1,
-		c->slots.as<unsigned long long>(), c->state.as<IcpState>(), c->work.as<unsigned>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg);
-	count_launch(1);
-	if (search) {
-		// the deferred queries; the count lives on the device, so the grid is sized for the worst case and idles otherwise
-		k_icp_match_far<<<std::max(1, std::min((c->i_end - c->i_begin + kNnThreads - 1) / kNnThreads, c->sm_count * 6)), kNnThreads, 0, st>>>(c->d_verts2, c->grid.as<IcpGrid>(),
-			c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(),
-			c->slots.as<unsigned long long>(), c->state.as<IcpState>(), c->work.as<unsigned>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg);
+	const int n_slice = c->i_end - c->i_begin;
+	if (search && n_slice > 0) {
+		if (!c->order_valid && icp_build_order(c, st) < 0) return -1;
+		const int n_packets = (n_slice + 31) / 32;        // at least; the exact number (node-bounded runs) lives on the device
+		const int nb = std::max(1, std::min((n_packets + kPkWarps - 1) / kPkWarps + 8, c->sm_count * 6));
+		k_icp_match_packet<<<nb, kPkWarps * 32, 0, st>>>(c->d_verts2, c->i_begin, c->i_end, apply, c->work.as<unsigned>(), c->pk_desc.as<uint2>(),
+			c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(), c->d_verts1,
+			c->slots.as<unsigned long long>(), c->state.as<IcpState>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg);
 		count_launch(1);
+	}
+	// the points the packet kernel did not touch: everything when there is no search, otherwise what lies outside the slice
+	int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+	if (apply) {
+		if (search && n_slice > 0) { a0 = 0; a1 = c->i_begin; b0 = c->i_end; b1 = c->n2; }
+		else { a0 = 0; a1 = c->n2; }
+		const int n_rest = (a1 - a0) + (b1 - b0);
+		if (n_rest > 0) {
+			k_icp_apply<<<pt_blocks(c, n_rest), 256, 0, st>>>(c->d_verts2, a0, a1, b0, b1, c->state.as<IcpState>());
+			count_launch(1);
+		}
 	}
 	return cuda_ok(cudaGetLastError(), "k_icp_match") ? 0 : -1;
 }
@@ -1035,7 +1227,7 @@ extern "C" int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream) {
 	}
 	if (c->graph) {
 		if (!cuda_ok(cudaGraphLaunch(c->graph, st), "launch ICP graph")) return -1;
-		count_launch(4 * maxIter + 1);
+		count_launch(3 * maxIter + 1 + 4);      // per iteration: match, stats, sums; once: source ordering (4) + final apply
 		c->iter = maxIter;
 		c->pending = false;
 		return 0;

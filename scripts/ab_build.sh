@@ -9,4 +9,4 @@ for f in runtime frame icp; do
 done
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o $out/libls3d_$tag.so $out/obj_$tag/runtime.o $out/obj_$tag/frame.o $out/obj_$tag/icp.o
-grep -A2 "k_organized_count" $out/obj_$tag/frame.ptxas.log | grep -E "Used|spill" | head -3
+grep -A2 -E "k_organized_count|k_icp_match_packet" $out/obj_$tag/*.ptxas.log | grep -E "Used|spill" | head -6
