@@ -457,7 +457,8 @@ constexpr int kPkWarps = 8;
 constexpr int kPkDone = 4;             // home cells scanned up front (and skipped by the walk)
 
 struct PkWarp {
-	unsigned long long rec[8][8];   // [level t-1][child]: records of the children of the node being iterated at level t
+	float4 lo[8][8], hi[8][8];      // [level t-1][child]: point boxes of the children of the node being iterated at level t, decoded
+	                                // (origin-relative, already widened by the slack): one lane decodes one child, every lane reads all
 	float4 pts[32];                 // staged candidate points
 	uint2 rng[8];                   // point ranges of the 8 cells under the current level-1 node
 	unsigned char rem[8];           // remaining (octant-permuted) child masks per level
@@ -467,17 +468,6 @@ struct PkWarp {
 // holds a point no farther than its farthest corner, so the nearest neighbour is at most that far even before any point of
 // it has been seen — far queries start pruning at once instead of walking with an infinite bound (first iteration: no seed).
 struct PkLane { float qx, qy, qz, rx, ry, rz, d2, bnd; int idx; bool valid; };
-
-// conservative lower AND upper bound of the squared distance from the origin-relative query to the points summarised by a record
-__device__ __forceinline__ void rec_bounds(unsigned long long r, float rx, float ry, float rz, float ox, float oy, float oz, float size, float slack, float &lb, float &ub) {
-	float mn[3], mx[3];
-	box_decode(r, ox, oy, oz, size, mn, mx);
-	const float ax = mn[0] - rx, bx = rx - mx[0], ay = mn[1] - ry, by = ry - mx[1], az = mn[2] - rz, bz = rz - mx[2];
-	const float dx = fmaxf(fmaxf(ax, bx) - slack, 0.0f), dy = fmaxf(fmaxf(ay, by) - slack, 0.0f), dz = fmaxf(fmaxf(az, bz) - slack, 0.0f);
-	lb = (dx * dx + dy * dy + dz * dz) * 0.99999f;
-	const float fx = fmaxf(-ax, -bx) + slack, fy = fmaxf(-ay, -by) + slack, fz = fmaxf(-az, -bz) + slack;     // farthest face per axis
-	ub = (fx * fx + fy * fy + fz * fz) * 1.00001f;
-}
 
 __device__ __forceinline__ void pk_scan(const float4 *__restrict__ sorted, unsigned s, unsigned e, PkLane &q, PkWarp &sh) {
 	const int lane = threadIdx.x & 31;
@@ -497,18 +487,28 @@ __device__ __forceinline__ void pk_scan(const float4 *__restrict__ sorted, unsig
 	q.bnd = fminf(q.bnd, q.d2);
 }
 
-// The 8 child records of node (t; ump) -> sh.rec[t-1] (and their point ranges -> sh.rng when the children are cells).
+// conservative squared distance from the origin-relative query to a decoded (slack-widened) box
+__device__ __forceinline__ float pk_lb2(const float4 lo, const float4 hi, float rx, float ry, float rz) {
+	const float dx = fmaxf(fmaxf(lo.x - rx, rx - hi.x), 0.0f), dy = fmaxf(fmaxf(lo.y - ry, ry - hi.y), 0.0f), dz = fmaxf(fmaxf(lo.z - rz, rz - hi.z), 0.0f);
+	return (dx * dx + dy * dy + dz * dz) * 0.99999f;
+}
+
+// The 8 child records of node (t; ump) -> sh.lo/hi[t-1] (and their point ranges -> sh.rng when the children are cells).
 // Returns the mask of non-empty children.  One memory round trip: lanes 0-7 fetch the records, lanes 8-16 the ranges.
 __device__ __forceinline__ unsigned pk_load_children(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellrec, PkWarp &sh, int t, unsigned ump)
+	const unsigned long long *__restrict__ cellrec, PkWarp &sh, int t, unsigned ux, unsigned uy, unsigned uz, unsigned ump, float slack)
 {
 	const int lane = threadIdx.x & 31;
 	unsigned long long rec = 0;
-	__syncwarp();                                                        // earlier readers of sh.rec / sh.rng are done
+	__syncwarp();                                                        // earlier readers of sh.lo/hi / sh.rng are done
 	if (lane < 8) {
-		const unsigned cmp = (ump << 3) | (unsigned)lane;
+		const unsigned c = (unsigned)lane, cmp = (ump << 3) | c;
 		rec = t == 1 ? __ldg(cellrec + cmp) : __ldg(nodes + icp_mask_off(g.levels, t - 1) + cmp);      // 0 = empty
-		sh.rec[t - 1][lane] = rec;
+		const float half = g.h * (float)(1u << (t - 1));
+		float mn[3], mx[3];
+		box_decode(rec, (float)((ux << 1) | (c & 1u)) * half, (float)((uy << 1) | ((c >> 1) & 1u)) * half, (float)((uz << 1) | (c >> 2)) * half, half, mn, mx);
+		sh.lo[t - 1][lane] = make_float4(mn[0] - slack, mn[1] - slack, mn[2] - slack, 0.0f);
+		sh.hi[t - 1][lane] = make_float4(mx[0] + slack, mx[1] + slack, mx[2] + slack, 0.0f);
 	} else if (t == 1 && lane < 17) {
 		// cell_start[(ump << 3) + 0 .. 8]: the 8 cells are consecutive in Morton order, so 9 values give the 8 ranges
 		const unsigned v = __ldg(cell_start + (ump << 3) + (unsigned)(lane - 8));
@@ -528,16 +528,14 @@ __device__ __forceinline__ void pk_greedy_seed(const IcpGrid &g, const unsigned 
 {
 	unsigned ux = 0, uy = 0, uz = 0, ump = 0;
 	for (int t = g.levels; t >= 1; t--) {
-		unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ump);
+		unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, slack);
 		if (!exist) return;                                               // empty target: cannot happen after ls3d_icp_set_target
-		const float half = g.h * (float)(1u << (t - 1));
 		float best_lb = INFINITY;
 		unsigned best_c = (unsigned)__ffs(exist) - 1u;
 		while (exist) {
 			const unsigned c = (unsigned)__ffs(exist) - 1u;
 			exist &= exist - 1u;
-			const float bx = (float)((ux << 1) | (c & 1u)) * half, by = (float)((uy << 1) | ((c >> 1) & 1u)) * half, bz = (float)((uz << 1) | (c >> 2)) * half;
-			const float lb = rec_lb2(sh.rec[t - 1][c], q.rx, q.ry, q.rz, bx, by, bz, half, slack);
+			const float lb = pk_lb2(sh.lo[t - 1][c], sh.hi[t - 1][c], q.rx, q.ry, q.rz);
 			if (lb < best_lb) { best_lb = lb; best_c = c; }
 		}
 		const unsigned c = __shfl_sync(kFull, best_c, who);
@@ -558,7 +556,7 @@ __device__ __forceinline__ void pk_enter(const IcpGrid &g, const unsigned *__res
 	PkLane &q, int ref, unsigned &nearpack, float slack)
 {
 	const int lane = threadIdx.x & 31;
-	unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ump) & allowed;
+	unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, slack) & allowed;
 	const float half = g.h * (float)(1u << (t - 1));                     // child edge
 	unsigned need = 0;
 	if (__any_sync(kFull, q.valid && q.bnd == INFINITY)) {
@@ -567,17 +565,16 @@ __device__ __forceinline__ void pk_enter(const IcpGrid &g, const unsigned *__res
 		while (ex) {
 			const unsigned c = (unsigned)__ffs(ex) - 1u;
 			ex &= ex - 1u;
-			const float bx = (float)((ux << 1) | (c & 1u)) * half, by = (float)((uy << 1) | ((c >> 1) & 1u)) * half, bz = (float)((uz << 1) | (c >> 2)) * half;
-			float lb, ub;
-			rec_bounds(sh.rec[t - 1][c], q.rx, q.ry, q.rz, bx, by, bz, half, slack, lb, ub);
-			q.bnd = fminf(q.bnd, ub);
+			// farthest corner of the (widened) box: some point of this non-empty box is at most that far
+			const float4 lo = sh.lo[t - 1][c], hi = sh.hi[t - 1][c];
+			const float fx = fmaxf(q.rx - lo.x, hi.x - q.rx), fy = fmaxf(q.ry - lo.y, hi.y - q.ry), fz = fmaxf(q.rz - lo.z, hi.z - q.rz);
+			q.bnd = fminf(q.bnd, (fx * fx + fy * fy + fz * fz) * 1.00001f);
 		}
 	}
 	while (exist) {
 		const unsigned c = (unsigned)__ffs(exist) - 1u;
 		exist &= exist - 1u;
-		const float bx = (float)((ux << 1) | (c & 1u)) * half, by = (float)((uy << 1) | ((c >> 1) & 1u)) * half, bz = (float)((uz << 1) | (c >> 2)) * half;
-		const float lb = rec_lb2(sh.rec[t - 1][c], q.rx, q.ry, q.rz, bx, by, bz, half, slack);
+		const float lb = pk_lb2(sh.lo[t - 1][c], sh.hi[t - 1][c], q.rx, q.ry, q.rz);
 		if (__any_sync(kFull, q.valid && lb <= q.bnd)) need |= 1u << c;
 	}
 	// near-first visiting order: the octant of the reference lane's query inside this node
@@ -617,10 +614,8 @@ __device__ __forceinline__ void pk_walk(const IcpGrid &g, const unsigned *__rest
 			for (int d = 0; d < kPkDone; d++) skip |= done.m[d] == cmp;     // a home cell: already scanned
 			if (skip) continue;
 		}
-		const float half = g.h * (float)(1u << (t - 1));
-		const unsigned ccx = (ux << 1) | (child & 1u), ccy = (uy << 1) | ((child >> 1) & 1u), ccz = (uz << 1) | (child >> 2);
 		// the bounds have tightened since this child was queued: test again before paying for the visit
-		const float lb = rec_lb2(sh.rec[t - 1][child], q.rx, q.ry, q.rz, (float)ccx * half, (float)ccy * half, (float)ccz * half, half, slack);
+		const float lb = pk_lb2(sh.lo[t - 1][child], sh.hi[t - 1][child], q.rx, q.ry, q.rz);
 		if (!__any_sync(kFull, q.valid && lb <= q.bnd)) continue;
 		steps++;
 		if (t == 1) {
@@ -629,7 +624,7 @@ __device__ __forceinline__ void pk_walk(const IcpGrid &g, const unsigned *__rest
 			pk_scan(sorted, r.x, r.y, q, sh);
 		} else {
 			t--;
-			ux = ccx; uy = ccy; uz = ccz; ump = cmp;
+			ux = (ux << 1) | (child & 1u); uy = (uy << 1) | ((child >> 1) & 1u); uz = (uz << 1) | (child >> 2); ump = cmp;
 			pk_enter(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, 0xffu, q, ref, nearpack, slack);
 		}
 	}
