@@ -65,6 +65,14 @@ void generateMeshFromDepthMaps(int n_maps, unsigned char *depth_maps, unsigned c
 	float *intr_params, float *wtransform_params, Mesh *out_mesh, int bcolor_transfer,
 	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int bgenerate_triangles);
 
+/* Replaces include/NativeUtils/depthprocessing.h:111 (src/NativeUtils/depthprocessing.cpp:1794-1815, per sensor :191-261);
+ * C# binding LiveScanServer/KinectServer.cs:51-53.  Radial-distortion correction of every sensor's depth and colour map,
+ * IN PLACE in the caller's packed buffers: forward warp by 1 - r2*r - r4*r^2 - r6*r^3 (the last source pixel in raster order
+ * wins a destination), then the reference's in-place raster-order hole fill (a zero pixel with more than 4 mutually
+ * consistent non-zero neighbours becomes their integer mean).  Bit-identical to the reference; on failure the buffers are
+ * left untouched and ls3d_last_error() says why. */
+void depthMapAndColorSetRadialCorrection(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights, float *intr_params);
+
 /* Replace src/NativeUtils/depthprocessing.cpp:1818-1835 (C# KinectServer.cs:56-60).  deleteMesh releases the
  * two arrays and leaves the struct itself alone, as the reference does. */
 Mesh *createMesh(void);
@@ -88,6 +96,12 @@ int ls3d_frame_pipeline(int n_maps, unsigned char *depth_maps, unsigned char *de
 	float *intr_params, float *wtransform_params, Mesh *out_mesh,
 	float minX, float minY, float minZ, float maxX, float maxY, float maxZ,
 	int filter_k, float filter_maxDist, int *per_map_counts);
+
+/* Replaces `void KinectCapture::filterFlyingPixels(int neighbourhoodSize, float thr, int maxNonFittingNeighbours)`
+ * (include/LiveScanClient/kinectCapture.h:39, src/LiveScanClient/kinectCapture.cpp:132-174; called per acquired frame at :199) on one
+ * width x height u16 depth image, in place: a pixel is zeroed when more than half of the (2k+1)^2-1 pixels around it differ from
+ * it by more than thr.  maxNonFittingNeighbours is accepted and ignored, as in the reference (:150 overwrites it).  Returns 1 / -1. */
+int ls3d_filter_flying_pixels(unsigned short *depth, int width, int height, int neighbourhoodSize, float thr, int maxNonFittingNeighbours);
 
 /* FindClosestPointForEach (src/NativeUtils/icp.cpp:18-32) as a flat entry, for stage-level parity tests:
  * index (into verts1) and squared distance of the nearest verts1 point for every verts2 point.  Returns 0/-1. */
@@ -191,6 +205,12 @@ int ls3d_frame_run_peers(Ls3dFrame *f, const void *d_depth_maps, const void *d_d
  *   ls3d_frame_merge_peers : the final compaction, storing to every peer buffer at *d_dst_offset. */
 int ls3d_frame_run_count(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run, void *stream);
 int ls3d_frame_merge_peers(Ls3dFrame *f, int first_map, int n_run, int n_peers, void *const *peer_dst_vertices, const int *d_dst_offset, void *stream);
+
+/* The two pre-passes on device-resident buffers, enqueued on `stream` without synchronisation: radial correction of a packed
+ * frame in place (same layouts as ls3d_frame_run's inputs, so it chains straight into it), flying-pixel filter from d_in to a
+ * distinct d_out.  Return the number of kernels enqueued or -1. */
+int ls3d_radial_correction_device(int n_maps, void *d_depth_maps, void *d_depth_colors, const int *widths, const int *heights, const float *intr_params, void *stream);
+int ls3d_filter_flying_pixels_device(const void *d_in, void *d_out, int width, int height, int neighbourhoodSize, float thr, void *stream);
 
 /* Plain device allocations that can be shared between the ranks of one node (one process per GPU) through CUDA
  * IPC: export a 64-byte handle, open it in another process to get a peer-mapped pointer (NVLink loads/stores). */

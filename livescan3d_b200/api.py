@@ -84,6 +84,30 @@ def generate_mesh_from_depth_maps(frame: dict, bounds, color_transfer: bool = Fa
     return _take_mesh(lib, mesh, "generateMeshFromDepthMaps", triangles)
 
 
+def radial_correction(frame: dict):
+    """depthMapAndColorSetRadialCorrection on copies of the frame's packed buffers -> (depth_maps u8[], depth_colors u8[])."""
+    lib = native.load()
+    d = np.array(frame["depth_maps"], dtype=np.uint8, order="C")
+    c = np.array(frame["depth_colors"], dtype=np.uint8, order="C")
+    w, h, ip = _c(frame["widths"], np.int32), _c(frame["heights"], np.int32), _c(frame["intr"], np.float32)
+    lib.depthMapAndColorSetRadialCorrection(int(frame["n_maps"]), _ptr(d), _ptr(c), _ptr(w), _ptr(h), _ptr(ip))
+    err = native.last_error()
+    if err:
+        raise Ls3dError(f"depthMapAndColorSetRadialCorrection: {err}")
+    return d, c
+
+
+def filter_flying_pixels(depth_u16: np.ndarray, width: int, height: int, neighbourhood_size: int = 1, thr: float = 10.0, max_non_fitting: int = 0):
+    """KinectCapture::filterFlyingPixels (kinectCapture.cpp:132-174) on a copy of one depth image -> filtered uint16[h*w]."""
+    lib = native.load()
+    d = np.array(depth_u16, dtype=np.uint16, order="C").reshape(-1)
+    if d.size != width * height:
+        raise ValueError("depth size does not match width*height")
+    r = lib.ls3d_filter_flying_pixels(_ptr(d), int(width), int(height), int(neighbourhood_size), float(thr), int(max_non_fitting))
+    native.check(r >= 0, "ls3d_filter_flying_pixels")
+    return d
+
+
 def frame_pipeline(frame: dict, bounds, filter_k: int = 10, filter_max_dist: float = 0.01):
     """map -> world transform -> cull -> per-sensor neighbour-count filter -> merge.  Returns (vertices, per_map_counts)."""
     lib = native.load()

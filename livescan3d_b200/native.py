@@ -33,6 +33,10 @@ _SIG = {
     "ICP": (_f, [_vp, _vp, _i, _i, _vp, _vp, _i]),
     "generateVerticesFromDepthMap": (None, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Mesh), _f, _f, _f, _f, _f, _f, _i]),
     "generateMeshFromDepthMaps": (None, [_i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Mesh), _i, _f, _f, _f, _f, _f, _f, _i]),
+    "depthMapAndColorSetRadialCorrection": (None, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "ls3d_filter_flying_pixels": (_i, [_vp, _i, _i, _i, _f, _i]),
+    "ls3d_radial_correction_device": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ls3d_filter_flying_pixels_device": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
     "createMesh": (C.POINTER(Mesh), []),
     "deleteMesh": (None, [C.POINTER(Mesh)]),
     "ls3d_filter": (_i, [_vp, _vp, _i, _i, _f, _vp]),

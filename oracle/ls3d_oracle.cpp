@@ -463,6 +463,103 @@ int orc_generate_mesh_triangles(int n_maps, const unsigned char *depth_maps, con
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Radial-distortion correction of the depth/colour maps
+// ---------------------------------------------------------------------------------------------------
+
+// depthMapAndColorRadialCorrection, src/NativeUtils/depthprocessing.cpp:191-261, one sensor, in place.
+//  1. forward warp (:201-220): every non-zero pixel moves to (int)(u*d*fx + cx), (int)(v*d*fy + cy) with
+//     u = (x-cx)/fx, v = (y-cy)/fy (note: y-cy, not cy-y), r = u*u + v*v, d = 1 - r2*r - r4*r*r - r6*r*r*r, all fp32,
+//     C truncation; sources are visited in raster order and simply overwrite, so the LAST source in raster order wins.
+//  2. hole closing (:226-257), raster order over the interior, IN PLACE: a zero pixel whose 8 neighbours (order
+//     NW,N,NE,W,E,SW,S,SE) contain more than 4 "consistent" non-zero depths — each within 30 of the previously accepted
+//     one — becomes their integer mean (colours likewise).  Because it is in place, neighbours NW,N,NE,W may already
+//     hold values filled earlier in the same pass.
+void orc_radial_correction_one(unsigned short *depth, unsigned char *colors, int w, int h, const float *intr7)
+{
+	const float cx = intr7[0], cy = intr7[1], fx = intr7[2], fy = intr7[3], r2 = intr7[4], r4 = intr7[5], r6 = intr7[6];
+	std::vector<unsigned short> out((size_t)w * h, 0);
+	std::vector<unsigned char> outc((size_t)w * h * 3, 0);
+	for (int y = 0; y < h; y++)
+		for (int x = 0; x < w; x++) {
+			const size_t src = (size_t)x + (size_t)y * w;
+			if (depth[src] == 0) continue;
+			const float u = (x - cx) / fx;
+			const float v = (y - cy) / fy;
+			const float r = u * u + v * v;
+			const float d = 1 - r2 * r - r4 * r * r - r6 * r * r * r;
+			const float fxc = u * d * fx + cx, fyc = v * d * fy + cy;
+			// (int) of an out-of-range or NaN float is the x86 "integer indefinite" value INT_MIN, which fails the >= 0 test below
+			const int xc = (fxc > -2147483904.0f && fxc < 2147483648.0f) ? (int)fxc : INT32_MIN;
+			const int yc = (fyc > -2147483904.0f && fyc < 2147483648.0f) ? (int)fyc : INT32_MIN;
+			if (xc >= 0 && yc >= 0 && xc < w && yc < h) {
+				const size_t dst = (size_t)xc + (size_t)yc * w;
+				out[dst] = depth[src];
+				memcpy(&outc[dst * 3], colors + src * 3, 3);
+			}
+		}
+	const int nb[8] = {-w - 1, -w, -w + 1, -1, 1, w - 1, w, w + 1};
+	for (int y = 1; y < h - 1; y++)
+		for (int x = 1; x < w - 1; x++) {
+			const long pos = (long)x + (long)y * w;
+			if (out[pos] != 0) continue;
+			int n = 0, sum = 0, sr = 0, sg = 0, sb = 0, prev = -1;
+			for (int i = 0; i < 8; i++) {
+				const int val = out[pos + nb[i]];
+				if (val > 0 && (prev == -1 || std::abs(val - prev) < 30)) {
+					prev = val; n++; sum += val;
+					sr += outc[(pos + nb[i]) * 3]; sg += outc[(pos + nb[i]) * 3 + 1]; sb += outc[(pos + nb[i]) * 3 + 2];
+				}
+			}
+			if (n > 4) {
+				out[pos] = (unsigned short)(sum / n);
+				outc[pos * 3] = (unsigned char)(sr / n); outc[pos * 3 + 1] = (unsigned char)(sg / n); outc[pos * 3 + 2] = (unsigned char)(sb / n);
+			}
+		}
+	memcpy(depth, out.data(), (size_t)w * h * 2);
+	memcpy(colors, outc.data(), (size_t)w * h * 3);
+}
+
+// depthMapAndColorSetRadialCorrection, depthprocessing.cpp:1794-1815: every sensor of the packed frame, independently.
+void orc_radial_correction(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, const int *widths, const int *heights, const float *intr_params)
+{
+	size_t dpos = 0, cpos = 0;
+	for (int i = 0; i < n_maps; i++) {
+		const size_t npx = (size_t)widths[i] * heights[i];
+		orc_radial_correction_one((unsigned short*)(depth_maps + dpos), depth_colors + cpos, widths[i], heights[i], intr_params + 7 * i);
+		dpos += npx * 2;
+		cpos += npx * 3;
+	}
+}
+
+// KinectCapture::filterFlyingPixels(int neighbourhoodSize, float thr, int maxNonFittingNeighbours),
+// src/LiveScanClient/kinectCapture.cpp:132-174.  PARITY UNPINNED: kinectCapture.cpp needs the Kinect SDK
+// headers and cannot be compiled here, so this restatement is checked against the source text only.
+// A pixel of the interior [k, w-k) x [k, h-k) is zeroed when more than nNeighbours/2 of its (2k+1)^2-1 neighbours differ
+// from it by more than thr (int difference compared with the float threshold, :163); the caller's
+// maxNonFittingNeighbours is overwritten (:150); removals are collected first and applied afterwards (:169-172).
+void orc_filter_flying_pixels(unsigned short *depth, int w, int h, int k, float thr, int maxNonFittingNeighbours)
+{
+	const int n_nb = (2 * k + 1) * (2 * k + 1) - 1;
+	std::vector<int> shifts;
+	for (int a = -k; a <= k; a++)
+		for (int b = -k; b <= k; b++)
+			if (a != 0 || b != 0) shifts.push_back(a * w + b);                  // :141-147 (x * width + y)
+	maxNonFittingNeighbours = n_nb / 2;
+	std::vector<int> remove;
+	for (int y = k; y < h - k; y++)
+		for (int x = k; x < w - k; x++) {
+			const int pos = y * w + x, val = depth[pos];
+			int n_diff = 0;
+			for (int sft : shifts) {
+				const int diff = std::abs((int)depth[pos + sft] - val);
+				if (diff > thr) n_diff++;
+			}
+			if (n_diff > maxNonFittingNeighbours) remove.push_back(pos);
+		}
+	for (int pos : remove) depth[pos] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Nearest neighbours
 // ---------------------------------------------------------------------------------------------------
 

@@ -110,6 +110,36 @@ def orc_generate_mesh_triangles(frame: dict, bounds):
     return out[:n].copy(), tri[:3 * nt.value].reshape(-1, 3).copy(), counts, tcounts
 
 
+def orc_radial_correction(frame: dict):
+    """depthMapAndColorSetRadialCorrection on copies of the frame's buffers -> (depth_maps u8[], depth_colors u8[])"""
+    o = oracle()
+    d = np.array(frame["depth_maps"], dtype=np.uint8, order="C")
+    c = np.array(frame["depth_colors"], dtype=np.uint8, order="C")
+    w = np.ascontiguousarray(frame["widths"], dtype=np.int32)
+    h = np.ascontiguousarray(frame["heights"], dtype=np.int32)
+    o.orc_radial_correction(int(frame["n_maps"]), _p(d), _p(c), _p(w), _p(h), _p(_f32(frame["intr"])))
+    return d, c
+
+
+def orc_filter_flying_pixels(depth_u16, w: int, h: int, k: int = 1, thr: float = 10.0, max_non_fitting: int = 0):
+    o = oracle()
+    d = np.array(depth_u16, dtype=np.uint16, order="C").reshape(-1)
+    o.orc_filter_flying_pixels(_p(d), int(w), int(h), int(k), C.c_float(thr), int(max_non_fitting))
+    return d
+
+
+def ref_radial_correction(frame: dict):
+    """The reference's own export depthMapAndColorSetRadialCorrection (depthprocessing.cpp:1794-1815) on copies."""
+    r = ref_native()
+    d = np.array(frame["depth_maps"], dtype=np.uint8, order="C")
+    c = np.array(frame["depth_colors"], dtype=np.uint8, order="C")
+    w = np.ascontiguousarray(frame["widths"], dtype=np.int32)
+    h = np.ascontiguousarray(frame["heights"], dtype=np.int32)
+    ip = _f32(frame["intr"]).copy()
+    r.depthMapAndColorSetRadialCorrection(int(frame["n_maps"]), _p(d), _p(c), _p(w), _p(h), _p(ip))
+    return d, c
+
+
 def orc_vertex_maps(depth_u16, colors, w, h, intr7, wt12, bounds):
     """createVertices side outputs for one sensor -> (n, depth_to_vertices[w*h], vertices_to_depth[n])"""
     o = oracle()

@@ -155,6 +155,83 @@ def test_device_triangles_and_pixel_map(api):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# pre-passes on the raw maps: radial correction (N1, a reference export) and the flying-pixel filter (N2)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,w,h,seed", [(3, 128, 96, 1000), (2, 160, 120, 7), (2, 37, 29, 3), (1, 5, 5, 1), (1, 3, 3, 1), (1, 2, 7, 2), (1, 1, 1, 4), (2, 512, 424, 1000)])
+def test_radial_correction_bit_exact(api, S, w, h, seed):
+    fr = synth.make_frame(S, w, h, seed_base=seed)
+    wd, wc = orc.orc_radial_correction(fr)
+    gd, gc = api.radial_correction(fr)
+    assert np.array_equal(gd, wd) and np.array_equal(gc, wc)
+    assert not np.array_equal(gd, fr["depth_maps"]) or w * h < 16          # the correction does move pixels
+
+
+def test_radial_correction_cascades_and_strong_distortion(api):
+    """Inputs built to stress the in-place raster-order hole fill: large invalid regions with straight and diagonal borders
+    (fills that feed later fills), sparse maps, and distortion coefficients strong enough to fold the image onto itself."""
+    rng = np.random.default_rng(3)
+    w, h = 200, 150
+    base = synth.make_frame(1, w, h, seed_base=5)
+    yy, xx = np.mgrid[0:h, 0:w]
+    variants = []
+    d = np.full((h, w), 1500, np.uint16); d[(xx + yy) % 7 == 0] = 0; d[yy > xx] = 0
+    variants.append(d)                                                    # diagonal border + regular holes
+    d = (1000 + 3 * xx + 2 * yy).astype(np.uint16); d[rng.random((h, w)) < 0.35] = 0
+    variants.append(d)                                                    # 35 % random holes on a ramp: long dependency chains
+    d = np.full((h, w), 2000, np.uint16); d[::2, :] = 0
+    variants.append(d)                                                    # every other row missing
+    d = (800 + 40 * ((xx // 3 + yy // 3) % 2)).astype(np.uint16); d[rng.random((h, w)) < 0.2] = 0
+    variants.append(d)                                                    # depth steps of 40 > the 30 consistency gate
+    for vi, d in enumerate(variants):
+        for coeffs in ((0.0905474, -0.26819, 0.0950862), (0.8, 0.3, -0.2), (-0.5, 0.0, 0.0), (0.0, 0.0, 0.0)):
+            fr = dict(base)
+            fr["depth_maps"] = d.astype("<u2").tobytes()
+            fr["depth_maps"] = np.frombuffer(fr["depth_maps"], dtype=np.uint8).copy()
+            intr = base["intr"].copy(); intr[4:7] = coeffs
+            fr["intr"] = intr
+            wd, wc = orc.orc_radial_correction(fr)
+            gd, gc = api.radial_correction(fr)
+            assert np.array_equal(gd, wd) and np.array_equal(gc, wc), (vi, coeffs)
+
+
+def test_radial_correction_device_chains_into_the_frame_pipeline(api):
+    import ctypes as C
+    import torch
+    from livescan3d_b200 import native
+    from livescan3d_b200.device import FramePipeline
+    fr = small_frame(S=3, w=160, h=120)
+    wd, wc = orc.orc_radial_correction(fr)
+    fr2 = dict(fr); fr2["depth_maps"] = wd; fr2["depth_colors"] = wc
+    want, _ = orc.orc_generate_mesh(fr2, synth.DEFAULT_BOUNDS)
+    lib = native.load()
+    dd = torch.from_numpy(fr["depth_maps"]).cuda()
+    dc = torch.from_numpy(fr["depth_colors"]).cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    r = lib.ls3d_radial_correction_device(3, C.c_void_p(dd.data_ptr()), C.c_void_p(dc.data_ptr()), p(fr["widths"]), p(fr["heights"]), p(fr["intr"]), st)
+    assert r > 0, native.last_error()
+    fp = FramePipeline(fr["widths"], fr["heights"])
+    fp.set_params(fr["intr"], fr["wt"], synth.DEFAULT_BOUNDS, 0, 0.0)
+    fp.run(dd, dc)
+    v, _ = fp.result()
+    assert v.tobytes() == want.tobytes()
+    assert np.array_equal(dd.cpu().numpy(), wd) and np.array_equal(dc.cpu().numpy(), wc)
+    fp.close()
+
+
+@pytest.mark.parametrize("k,thr", [(1, 10.0), (2, 25.0), (3, 5.5), (0, 1.0), (1, 0.0)])
+def test_flying_pixel_filter_bit_exact(api, k, thr):
+    for (w, h, seed) in ((512, 424, 1000), (160, 120, 5), (7, 5, 1), (3, 3, 2), (2, 9, 3)):
+        fr = synth.make_frame(1, w, h, seed_base=seed)
+        d = fr["depth_maps"].view(np.uint16)
+        want = orc.orc_filter_flying_pixels(d, w, h, k, thr, 123)
+        got = api.filter_flying_pixels(d, w, h, k, thr, 7)
+        assert np.array_equal(got, want)
+        if w == 512 and k == 1 and thr == 10.0:
+            assert (want == 0).sum() > (d == 0).sum()                      # it does remove the synthetic flying pixels
+
+
+# ---------------------------------------------------------------------------------------------------------
 # neighbour-count filter
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("k,md", [(10, 0.01), (10, 0.1), (1, 0.01), (50, 0.05), (3, 0.02), (200, 0.1), (2, 1e-4)])

@@ -44,6 +44,27 @@ def test_triangles_bit_exact_vs_reference(S, w, h):
 
 
 @needs_ref
+@pytest.mark.parametrize("S,w,h,seed", [(3, 128, 96, 1000), (2, 37, 29, 3), (1, 5, 5, 1), (1, 3, 3, 1), (1, 2, 7, 2), (2, 512, 424, 1000)])
+def test_radial_correction_bit_exact_vs_reference(S, w, h, seed):
+    """depthMapAndColorSetRadialCorrection (depthprocessing.cpp:1794-1815, :191-261): the reference's own export vs the restatement."""
+    fr = synth.make_frame(S, w, h, seed_base=seed)
+    rd, rc = orc.ref_radial_correction(fr)
+    od, oc = orc.orc_radial_correction(fr)
+    assert np.array_equal(rd, od) and np.array_equal(rc, oc)
+    # strong coefficients and many holes: the in-place fill cascades
+    rng = np.random.default_rng(seed)
+    fr2 = dict(fr)
+    d = fr["depth_maps"].view(np.uint16).copy()
+    d[rng.random(d.shape) < 0.3] = 0
+    fr2["depth_maps"] = d.view(np.uint8)
+    intr = fr["intr"].copy(); intr[4::7] = 0.8; intr[5::7] = 0.3; intr[6::7] = -0.2
+    fr2["intr"] = intr
+    rd, rc = orc.ref_radial_correction(fr2)
+    od, oc = orc.orc_radial_correction(fr2)
+    assert np.array_equal(rd, od) and np.array_equal(rc, oc)
+
+
+@needs_ref
 def test_fixture_poses_and_pixel_maps_vs_reference():
     fr = synth.make_frame(2, 160, 120, poses=synth.FIXTURE_POSES)
     for b in BOUNDS:
