@@ -13,8 +13,9 @@
 //                   neighbours (NW, N, NE, W) are final — then the reference's own neighbour loop is evaluated on final
 //                   values — or even if every unresolved one of them were filled it could not collect more than 4
 //                   neighbours, so it stays 0.  Values are published with "write, fence, flag", so any interleaving of
-//                   threads gives the sequential result.  A few grid-wide rounds settle all but the genuine fill cascades;
-//   k_rad_chain     one block per sensor iterates the remaining (short) worklist to its fixed point;
+//                   threads gives the sequential result.  One grid-wide round settles the vast majority of holes;
+//   k_rad_wavefront one block per sensor finishes what hangs on other holes (fill cascades, region borders) as a skewed
+//                   raster wavefront: w + 2h lockstep steps whatever the dependency structure;
 //   k_rad_writeback results back into the caller's buffers (the reference works in place).
 #include "ls3d_common.cuh"
 #include "ls3d_internal.h"
@@ -35,19 +36,26 @@ struct PreSensor {
 };
 
 enum : unsigned char { kRadDone = 1, kRadHole = 2 };
-constexpr int kRadRounds = 3;            // grid-wide rounds before the per-sensor worklists
+constexpr int kRadRounds = 1;            // grid-wide rounds before the wavefront
 constexpr int kRadChainThreads = 1024;
 
-__device__ __forceinline__ unsigned ld_vol_u8(const unsigned char *p) {
+// loads that must observe other threads' stores: device scope for the grid-wide round (other SMs write), block scope for the
+// wavefront (one block per sensor: every writer is on this SM, so the loads may hit its L1 and the fences stay local)
+template <bool kCta> __device__ __forceinline__ unsigned ld_vol_u8(const unsigned char *p) {
 	unsigned v;
-	asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+	if (kCta) asm volatile("ld.relaxed.cta.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	else asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ unsigned ld_vol_u16(const unsigned short *p) {
+template <bool kCta> __device__ __forceinline__ unsigned ld_vol_u16(const unsigned short *p) {
 	unsigned short v;
-	asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
+	if (kCta) asm volatile("ld.relaxed.cta.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+	else asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
 	return v;
 }
+// In the wavefront the ordering comes from its own step structure (__syncwarp inside a warp, fence + progress counter between warps),
+// so the per-pixel fences are only needed in the grid-wide round.
+template <bool kCta> __device__ __forceinline__ void rad_fence() { if (!kCta) __threadfence(); }
 
 // C's (int) of a float the way x86 does it: out of range / NaN -> INT_MIN ("integer indefinite"), which then fails the >= 0 test
 __device__ __forceinline__ int c_float_to_int(float f) {
@@ -96,24 +104,51 @@ __global__ void __launch_bounds__(256) k_rad_gather(const uint8_t *__restrict__ 
 }
 
 // Try to finalise the pending hole at pixel p of sensor s.  Returns true when it is final now.
-__device__ bool rad_try_resolve(const PreSensor &s, int p, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state) {
+template <bool kCta>
+__device__ __forceinline__ bool rad_try_resolve(const PreSensor &s, int p, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state) {
 	const long long gp = s.pix_begin + p;
 	const int w = s.w;
 	const int nb[8] = {-w - 1, -w, -w + 1, -1, 1, w - 1, w, w + 1};      // depthprocessing.cpp:226
 	unsigned st[8];
+	int raw[8];
+	unsigned col[8][3];
 	bool all_done = true;
+	if (kCta) {
+		// wavefront: the raster-earlier neighbours are final by construction, and every address is known up front, so all 40 loads are
+		// issued together (one memory round trip instead of a dependent chain through the consistency loop below).  Earlier neighbours
+		// may have been written by other threads of this block since the gather: block-scope strong loads; the rest cannot have changed.
 #pragma unroll
-	for (int i = 0; i < 8; i++) st[i] = ld_vol_u8(state + gp + nb[i]);
+		for (int i = 0; i < 8; i++) {
+			st[i] = (unsigned)state[gp + nb[i]] | kRadDone;                // only the immutable hole bit matters here
+			const uint8_t *c = fcolors + 3 * (gp + nb[i]);
+			if (i < 4) {
+				raw[i] = (int)ld_vol_u16<true>(fdepth + gp + nb[i]);
+				col[i][0] = ld_vol_u8<true>(c); col[i][1] = ld_vol_u8<true>(c + 1); col[i][2] = ld_vol_u8<true>(c + 2);
+			} else {
+				raw[i] = (int)fdepth[gp + nb[i]];
+				col[i][0] = c[0]; col[i][1] = c[1]; col[i][2] = c[2];
+			}
+		}
+	} else {
 #pragma unroll
-	for (int i = 0; i < 4; i++) all_done = all_done && (st[i] & kRadDone);
-	__threadfence();                                                       // values of neighbours seen as final are read after their flags
+		for (int i = 0; i < 8; i++) st[i] = ld_vol_u8<false>(state + gp + nb[i]);
+#pragma unroll
+		for (int i = 0; i < 4; i++) all_done = all_done && (st[i] & kRadDone);
+		__threadfence();                                                   // values of neighbours seen as final are read after their flags
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			raw[i] = (int)ld_vol_u16<false>(fdepth + gp + nb[i]);
+			const uint8_t *c = fcolors + 3 * (gp + nb[i]);
+			col[i][0] = ld_vol_u8<false>(c); col[i][1] = ld_vol_u8<false>(c + 1); col[i][2] = ld_vol_u8<false>(c + 2);
+		}
+	}
 	int val[8];
 #pragma unroll
 	for (int i = 0; i < 8; i++) {
-		// raster-earlier neighbours: their current (final, if flagged) value; raster-later neighbours: the warped value, which for an
+		// raster-earlier neighbours: their final value (unknown while not flagged); raster-later neighbours: the warped value, which for an
 		// original hole is 0 whatever has been filled into it since (the reference has not reached it yet)
-		if (i < 4) val[i] = (st[i] & kRadDone) ? (int)ld_vol_u16(fdepth + gp + nb[i]) : -1;       // -1: not known yet
-		else val[i] = (st[i] & kRadHole) ? 0 : (int)ld_vol_u16(fdepth + gp + nb[i]);
+		if (i < 4) val[i] = (st[i] & kRadDone) ? raw[i] : -1;
+		else val[i] = (st[i] & kRadHole) ? 0 : raw[i];
 	}
 	if (!all_done) {
 		int possible = 0;
@@ -129,54 +164,80 @@ __device__ bool rad_try_resolve(const PreSensor &s, int p, unsigned short *fdept
 	for (int i = 0; i < 8; i++) {
 		if (val[i] > 0 && (prev == -1 || abs(val[i] - prev) < 30)) {           // :239
 			prev = val[i]; n++; sum += val[i];
-			const uint8_t *c = fcolors + 3 * (gp + nb[i]);
-			sr += (int)ld_vol_u8(c); sg += (int)ld_vol_u8(c + 1); sb += (int)ld_vol_u8(c + 2);
+			sr += (int)col[i][0]; sg += (int)col[i][1]; sb += (int)col[i][2];
 		}
 	}
 	if (n > 4) {
 		fcolors[3 * gp] = (uint8_t)(sr / n); fcolors[3 * gp + 1] = (uint8_t)(sg / n); fcolors[3 * gp + 2] = (uint8_t)(sb / n);
 		fdepth[gp] = (unsigned short)(sum / n);
 	}
-	__threadfence();
+	rad_fence<kCta>();
 	state[gp] = kRadHole | kRadDone;
 	return true;
 }
 
-// one grid-wide round; the last one queues what is still pending (worklist of sensor s: items + s.pix_begin, count[s])
-__global__ void __launch_bounds__(256) k_rad_round(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state,
-	int queue, int *items, int *count)
+// one grid-wide round: settles every hole whose outcome does not hang on another undecided hole (the vast majority)
+__global__ void __launch_bounds__(256) k_rad_round(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state)
 {
 	const PreSensor s = sd[blockIdx.y];
 	const int px = s.w * s.h;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < px; p += gridDim.x * blockDim.x) {
-		if (ld_vol_u8(state + s.pix_begin + p) & kRadDone) continue;
-		if (!rad_try_resolve(s, p, fdepth, fcolors, state) && queue) items[s.pix_begin + atomicAdd(&count[blockIdx.y], 1)] = p;
+		if (ld_vol_u8<false>(state + s.pix_begin + p) & kRadDone) continue;
+		rad_try_resolve<false>(s, p, fdepth, fcolors, state);
 	}
 }
 
-// the remaining fill cascades of one sensor, to their fixed point.  The raster-first pending item can always be resolved, so
-// every round makes progress; the round limit only guards against a broken invariant (flagged in err).
-__global__ void __launch_bounds__(kRadChainThreads) k_rad_chain(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state,
-	int *items, const int *__restrict__ count, int *err)
+// What the grid-wide round left pending — holes that wait on other holes: the genuine fill cascades, and borders of invalid
+// regions that could only be decided once their neighbours were — is finished by a skewed wavefront, one block per sensor:
+// thread r owns image row r and visits pixel x = t - 2r at step t, so the pixels a hole reads as "already processed"
+// (NW, N, NE, W) were finished at earlier steps by construction.  Inside a warp the skew is kept by lockstep
+// (__syncwarp per step); between warps lane 0 waits on the progress counter of the row above (the previous warp's last row).
+// w + 2h steps whatever the dependency structure, instead of one block-wide round per link of the longest chain; a per-row
+// bitmap of the pending pixels in shared memory lets a warp skip, without touching memory, every step at which none of its rows has work.
+__global__ void __launch_bounds__(kRadChainThreads) k_rad_wavefront(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state, int words_per_row, int *err)
 {
-	__shared__ int s_left, s_prev;
+	extern __shared__ unsigned pend[];                          // [row of the band][words_per_row]: bit x = pixel x of that row is still pending
+	__shared__ volatile int prog[kRadChainThreads / 32];       // pixels finished in the last row of each warp
 	const PreSensor s = sd[blockIdx.x];
-	int *mine = items + s.pix_begin;
-	const int n = count[blockIdx.x];
-	if (n == 0) return;
-	if (threadIdx.x == 0) { s_left = n; s_prev = n + 1; }
-	__syncthreads();
-	for (int round = 0; round <= n; round++) {
-		for (int j = threadIdx.x; j < n; j += blockDim.x) {
-			const int p = mine[j];
-			if (p >= 0 && rad_try_resolve(s, p, fdepth, fcolors, state)) { mine[j] = -1; atomicSub(&s_left, 1); }
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int rows_per_band = (int)blockDim.x;
+	const int wpr = (s.w + 31) >> 5;                            // <= words_per_row
+	for (int band = 0; band * rows_per_band < s.h; band++) {
+		if (threadIdx.x < kRadChainThreads / 32) prog[threadIdx.x] = 0;
+		// the pending map of this band's rows (static from here on: only this kernel resolves pixels now); a warp packs its own 32 rows
+		unsigned my_any = 0;
+		for (int j = 0; j < 32; j++) {
+			const int yy = band * rows_per_band + warp * 32 + j;
+			for (int x0 = 0; x0 < wpr * 32; x0 += 32) {
+				const int x = x0 + lane;
+				bool pnd = false;
+				if (yy >= 1 && yy < s.h - 1 && x >= 1 && x < s.w - 1) pnd = !(state[s.pix_begin + (long long)yy * s.w + x] & kRadDone);
+				const unsigned bits = __ballot_sync(kFull, pnd);
+				if (lane == 0) pend[(warp * 32 + j) * words_per_row + (x0 >> 5)] = bits;
+				if (j == lane) my_any |= bits;
+			}
 		}
-		__syncthreads();
-		const int left = s_left, prev = s_prev;
-		__syncthreads();
-		if (left == 0) return;
-		if (left == prev) { if (threadIdx.x == 0) atomicOr(err, 16); return; }
-		if (threadIdx.x == 0) s_prev = left;
+		__syncthreads();                                        // also: the previous band's rows are complete
+		const int y = band * rows_per_band + threadIdx.x;
+		if (band * rows_per_band + warp * 32 < s.h) {
+			const unsigned *mine = pend + threadIdx.x * words_per_row;
+			const int steps = s.w + 2 * 31;
+			for (int t = 0; t < steps; t++) {
+				const int x = t - 2 * lane;
+				const bool todo = my_any && x >= 0 && x < s.w && ((mine[x >> 5] >> (x & 31)) & 1u);
+				if (__any_sync(kFull, todo)) {
+					if (warp > 0 && lane == 0 && todo) {
+						const int need = min(t + 2, s.w);         // N and NE of my pixel t are pixels t, t+1 of the row above
+						while (prog[warp - 1] < need) __nanosleep(32);
+					}
+					__syncwarp();
+					if (todo && !rad_try_resolve<true>(s, y * s.w + x, fdepth, fcolors, state)) atomicOr(err, 16);
+					__syncwarp();
+				}
+				// publish the last row's progress every 8 pixels (and at the row's end): one fence per 8 steps instead of one per step
+				if (lane == 31 && x >= 0 && x < s.w && ((x & 7) == 7 || x == s.w - 1)) { __threadfence_block(); prog[warp] = x + 1; }
+			}
+		}
 		__syncthreads();
 	}
 }
@@ -266,7 +327,7 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 	c->total_px = acc;
 	const size_t n = (size_t)acc;
 	bool ok = c->sd.reserve(sizeof(PreSensor) * n_maps, "alloc descriptors") && c->winner.reserve(4 * n, "alloc warp winners") && c->fdepth.reserve(2 * n, "alloc warped depth") &&
-		c->fcolors.reserve(3 * n, "alloc warped colours") && c->state.reserve(n, "alloc hole states") && c->items.reserve(4 * n, "alloc worklists") &&
+		c->fcolors.reserve(3 * n, "alloc warped colours") && c->state.reserve(n, "alloc hole states") &&
 		c->count.reserve(4 * (size_t)n_maps + 4, "alloc worklist counts");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin_sd, sizeof(PreSensor) * n_maps, cudaHostAllocDefault), "alloc pinned descriptors");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin_err, 64, cudaHostAllocDefault), "alloc pinned status");
@@ -298,8 +359,17 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 	k_rad_scatter<<<grid, 256, 0, st>>>(d_depth, sd, c->winner.as<int>());
 	k_rad_gather<<<grid, 256, 0, st>>>(d_depth, d_colors, sd, c->winner.as<int>(), c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
 	for (int r = 0; r < kRadRounds; r++)
-		k_rad_round<<<grid, 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), r == kRadRounds - 1 ? 1 : 0, c->items.as<int>(), count);
-	k_rad_chain<<<n_maps, kRadChainThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), count, count + n_maps);
+		k_rad_round<<<grid, 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+	int max_h = 1, max_w = 1;
+	for (int i = 0; i < n_maps; i++) { max_h = std::max(max_h, c->h[i]); max_w = std::max(max_w, c->w[i]); }
+	const int words_per_row = (max_w + 31) / 32;
+	int rows = std::min(kRadChainThreads, (max_h + 31) / 32 * 32);
+	const int smem_budget = 200 * 1024;                           // of the 227 KB a block may use
+	while (rows > 32 && (size_t)rows * words_per_row * 4 > (size_t)smem_budget) rows -= 32;
+	const size_t wf_smem = (size_t)rows * words_per_row * 4;
+	if (wf_smem > (size_t)smem_budget) { set_error("radial correction: image width %d too large for the wavefront's pending map", max_w); return -1; }
+	if (!cuda_ok(cudaFuncSetAttribute(k_rad_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget), "wavefront shared memory")) return -1;
+	k_rad_wavefront<<<n_maps, rows, wf_smem, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), words_per_row, count + n_maps);
 	k_rad_writeback<<<(unsigned)std::max<long long>(1, std::min<long long>((c->total_px + 255) / 256, (long long)c->sm_count * 8)), 256, 0, st>>>(d_depth, d_colors, c->total_px,
 		c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>());
 	count_launch(4 + kRadRounds);
