@@ -43,6 +43,17 @@ ICP_METRIC = "ICP Mpts*iter/s (2x217k cloud)"
 L2_FLUSH_BYTES = 256 << 20
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full capture of the
+    same workload (profiles/r01_kernel_traffic.json, made from profiles/r01_ncu_raw_v9_all_kernels_summary.txt); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    try:
+        with open(p) as f:
+            return int(json.load(f)["kernels"][kernel]["dram_bytes_per_launch_last"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -348,9 +359,10 @@ def run_ours(args, rank, local_rank, world):
         stages.append({"kernel": nm, "ms": float(ms), "share": float(ms / max(stage[7], 1e-9)), "alg_bytes": int(alg[nm]), "gbs": float(alg[nm] / ms / 1e6)})
     dom = max(stages, key=lambda x: x["ms"])
     whole_alg = 5 * px + 16 * n_final
+    ncu_name = {"organized_neighbour_count": "k_organized_count", "map_cull_compact": "k_map_cull_compact<0, 1>", "voxel_neighbour_count": "k_neighbour_count"}
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
-                "note": "neighbour counts work on L2/shared-memory resident candidates (FP32/LSU-issue bound, see profiles/); map_cull_compact is the streaming kernel",
+                "traffic": ncu_traffic(ncu_name.get(dom["kernel"], dom["kernel"])), "peak_source": peak_src,
+                "note": "the neighbour count tests ~50-80 shared-memory candidates per pixel with exact fp32 d2: issue bound (ncu: 73 % issue slots, 0 % tensor pipe), HBM traffic ~= algorithmic bytes; map_cull_compact is the streaming kernel (see profiles/)",
                 "whole_pipeline": {"alg_bytes": whole_alg, "achieved": whole_alg / ms_per_step / 1e6, "frac": whole_alg / ms_per_step / 1e6 / hbm_peak},
                 "stages": stages}
 
@@ -441,8 +453,8 @@ def run_ours(args, rank, local_rank, world):
     acc /= reps
     icp_alg = 64 * n2                                                   # 64 B per source point per iteration
     match_gbs = icp_alg / max(acc[1], 1e-9) / 1e6
-    icp_roofline = {"bound": "hbm", "kernel": "k_icp_match", "achieved": match_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": match_gbs / hbm_peak, "traffic": None,
-                    "peak_source": peak_src, "note": "grid NN on L2-resident data: FP32/LSU-issue and L2-latency bound, not HBM (see profiles/)",
+    icp_roofline = {"bound": "hbm", "kernel": "k_icp_match_packet", "achieved": match_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": match_gbs / hbm_peak, "traffic": ncu_traffic("k_icp_match_packet"),
+                    "peak_source": peak_src, "note": "packet octree NN on L2-resident data: issue- and dependent-latency bound, not HBM (ncu: 57 % issue slots, 27 of 32 lanes, 0 % tensor pipe; see profiles/)",
                     "stages_ms": {"target_grid_build_per_call": float(acc[0]), "match_per_iter": float(acc[1]), "stats_per_iter": float(acc[2]), "sums_per_iter": float(acc[3])},
                     "whole_iteration": {"alg_bytes": icp_alg, "achieved": icp_alg / (icp_ms / ICP_ITERS) / 1e6, "frac": icp_alg / (icp_ms / ICP_ITERS) / 1e6 / hbm_peak}}
 

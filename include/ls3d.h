@@ -171,7 +171,8 @@ const int *ls3d_frame_triangles(Ls3dFrame *f);        /* device int[3 * n_triang
 const int *ls3d_frame_triangle_starts(Ls3dFrame *f);  /* device int[n_maps+1] */
 
 /* How the neighbour count enumerates candidates (results are identical; only speed differs):
- *   0 auto      : organized (pixel-window) count when every sensor's pose and intrinsics admit its bound, else voxel hash
+ *   0 auto      : organized (pixel-window) count when every sensor's pose and intrinsics admit its bound and the window of a point
+ *                 1 m away fits the kernel's shared-memory halo (8 px), else voxel hash
  *   1 voxel hash: always the voxel-hash path (also what ls3d_filter uses: it has no image to exploit)
  *   2 organized : insist on the pixel-window path; ls3d_frame_run fails if it is not applicable.
  * On the organized path the unfiltered culled cloud is never materialised: ls3d_frame_culled_vertices and

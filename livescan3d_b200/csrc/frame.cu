@@ -951,6 +951,7 @@ struct Ls3dFrame {
 	bool params_set = false;
 	int filter_mode = kModeAuto;
 	bool organized_ok = false;          // every sensor's pose/intrinsics admit the pixel-window bound
+	bool organized_wide = false;        // ... but typical windows exceed the halo: auto mode prefers the voxel hash
 	bool last_organized = false;        // what the last count stage ran (the merge stage has to match)
 	const void *last_depth = nullptr, *last_colors = nullptr;
 	int sm_count = 148;
@@ -1144,6 +1145,7 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 	f->filter_max_dist = filter_maxDist;
 	f->filter_thr = (float)pow((double)filter_maxDist, 2.0);  // filter.cpp:52: float = pow(float, int)
 	f->organized_ok = f->filter_on;
+	f->organized_wide = false;
 	for (int i = 0; i < n_set && i < f->S; i++) {
 		SensorDesc &d = f->h_sd[i];
 		const float *ip = intr_params + 7 * i;                 // IntrinsicCameraParameters(float*), depthprocessing.h:96-97
@@ -1174,6 +1176,9 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 			const bool fin = std::isfinite(d.fx) && std::isfinite(d.fy) && std::isfinite(d.cx) && std::isfinite(d.cy) && d.fx != 0.0f && d.fy != 0.0f;
 			if (smin > 1e-3 && mag < 1e6 && fin && std::isfinite(rp) && rp > 0) d.org_rp = (float)rp;
 			else f->organized_ok = false;
+			// the pixel window of a point 1 m away should still fit the shared-memory halo; beyond that most windows fall back to the
+			// global-memory walk and the voxel hash is the faster enumeration (measured at 1920x1080, r = 1 cm: 1.41 vs 0.77 ms)
+			if (f->organized_ok && fmax(fabs((double)d.fx), fabs((double)d.fy)) * rp / (1.0 - fmin(rp, 0.5)) > (double)kOrgHalo) f->organized_wide = true;
 		}
 	}
 	memcpy(f->pin_sd, f->h_sd.data(), sizeof(SensorDesc) * (f->S + 1));
@@ -1287,7 +1292,7 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 			set_error("ls3d_frame_run: organized filter mode requested but a sensor's pose/intrinsics do not admit the pixel-window bound");
 			return -1;
 		}
-		const bool organized = f->filter_on && f->organized_ok && f->filter_mode != kModeVoxelHash;
+		const bool organized = f->filter_on && f->organized_ok && f->filter_mode != kModeVoxelHash && !(f->filter_mode == kModeAuto && f->organized_wide);
 		f->last_organized = organized;
 		f->last_depth = d_depth;
 		f->last_colors = d_colors;

@@ -32,6 +32,25 @@ fp.run(d_depth, d_colors)
 torch.cuda.synchronize()
 print("voxel hash:", fp.counts.cpu().tolist())
 
+# widened rows: unfiltered mesh with triangles, radial correction (device, on a copy), flying-pixel filter
+import ctypes as C  # noqa: E402
+from livescan3d_b200 import native  # noqa: E402
+lib = native.load()
+fp.set_filter_mode(0)
+fp.set_params(frame["intr"], frame["wt"], bench.FRAME_BOUNDS, 0, 0.0)
+fp.enable_triangles(True)
+fp.run(d_depth, d_colors)
+torch.cuda.synchronize()
+print("mesh:", fp.counts.cpu().tolist())
+dd, dc = d_depth.clone(), d_colors.clone()
+pp = lambda a: a.ctypes.data_as(C.c_void_p)
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+assert lib.ls3d_radial_correction_device(bench.S, C.c_void_p(dd.data_ptr()), C.c_void_p(dc.data_ptr()), pp(frame["widths"]), pp(frame["heights"]), pp(frame["intr"]), st) > 0
+one = d_depth[: 2 * bench.W_PX * bench.H_PX]
+fo = torch.empty_like(one)
+assert lib.ls3d_filter_flying_pixels_device(C.c_void_p(one.data_ptr()), C.c_void_p(fo.data_ptr()), bench.W_PX, bench.H_PX, 1, 10.0, st) > 0
+torch.cuda.synchronize()
+
 A, B = bench.icp_clouds(pair, api.generate_vertices_from_depth_map)
 dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
 s = IcpSolver(len(A), len(B))

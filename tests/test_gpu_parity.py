@@ -375,6 +375,32 @@ def test_golden_vectors(api):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# stress resolution (BASELINE.json configs[4]): 1920x1080 registered depth
+# ---------------------------------------------------------------------------------------------------------
+def test_stress_resolution_1920x1080(api):
+    fr = synth.make_frame(2, 1920, 1080, ring=8)
+    # vertices + triangles, whole Mesh
+    wv, wt, _, _ = orc.orc_generate_mesh_triangles(fr, synth.SERVER_BOUNDS)
+    gv, gt = api.generate_mesh_from_depth_maps(fr, synth.SERVER_BOUNDS, triangles=True)
+    assert len(wv) > 3_900_000 and gv.tobytes() == wv.tobytes() and np.array_equal(gt, wt)
+    # filtered pipeline, both candidate enumerations (pixel windows here exceed the shared-memory halo for near points)
+    want, per = _pipeline_oracle(fr, synth.DEFAULT_BOUNDS, 10, 0.004)
+    from livescan3d_b200 import native
+    for mode in (2, 1):
+        native.load().ls3d_set_default_filter_mode(mode)
+        try:
+            got, counts = api.frame_pipeline(fr, synth.DEFAULT_BOUNDS, 10, 0.004)
+        finally:
+            native.load().ls3d_set_default_filter_mode(0)
+        assert np.array_equal(counts, per) and got.tobytes() == want.tobytes(), mode
+    assert 0 < len(want) < sum(len(orc.orc_generate_mesh(fr, synth.DEFAULT_BOUNDS, i)[0]) for i in range(2))   # the filter does remove points
+    # radial correction
+    wd, wc = orc.orc_radial_correction(fr)
+    gd, gc = api.radial_correction(fr)
+    assert np.array_equal(gd, wd) and np.array_equal(gc, wc)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # nearest neighbour + ICP
 # ---------------------------------------------------------------------------------------------------------
 def test_find_closest_parity(api):
