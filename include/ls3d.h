@@ -129,6 +129,10 @@ const char *ls3d_last_error(void);
 /* Library/device identification: "ls3d-b200 <version> sm_100a; device: <name> (cc X.Y)" or the failure text. */
 const char *ls3d_version(void);
 
+/* Device self-check of arithmetic shortcuts that are exhaustive facts rather than identities (d / 1000.0f for every u16 d in three
+ * instructions).  Returns the number of failures (0 = good) or -1 without a usable device. */
+int ls3d_selftest(void);
+
 /* Number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches). */
 long long ls3d_launch_count(void);
 void ls3d_reset_launch_count(void);

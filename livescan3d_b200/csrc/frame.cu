@@ -71,6 +71,22 @@ __device__ __forceinline__ PixelXform load_xform(const SensorDesc *__restrict__ 
 	return m;
 }
 
+// v / 1000.0f, correctly rounded, for every integer v in [0, 65535] — i.e. bit-identical to the reference's `val / 1000.0f` on a u16
+// depth (depthprocessing.cpp:149) — in three instructions instead of the ~10 of a general IEEE division: one Newton correction of
+// v * fl(1/1000) with the exact FMA remainder.  Not a general identity: it is checked exhaustively over all 65536 inputs, on the
+// CPU when this was written and on the device by ls3d_selftest() (tests/test_gpu_parity.py).
+__device__ __forceinline__ float div1000_u16(float v) {
+	const float r = 1.0f / 1000.0f;
+	const float q0 = __fmul_rn(v, r);
+	const float rem = __fmaf_rn(-q0, 1000.0f, v);
+	return __fmaf_rn(rem, r, q0);
+}
+
+__global__ void k_selftest_div1000(int *mismatches) {
+	const int d = blockIdx.x * blockDim.x + threadIdx.x;
+	if (d < 65536 && __float_as_uint(div1000_u16((float)d)) != __float_as_uint(__fdiv_rn((float)d, 1000.0f))) atomicAdd(mismatches, 1);
+}
+
 // returns true when the pixel yields a vertex (non-zero depth and inside the strict cull box).
 // xn = (x - cx) / fx and yn = (cy - y) / fy come from the per-sensor RAY TABLE (w + h floats, computed once per
 // parameter set on the host with the same two IEEE fp32 operations the reference performs per pixel,
@@ -78,7 +94,7 @@ __device__ __forceinline__ PixelXform load_xform(const SensorDesc *__restrict__ 
 __device__ __forceinline__ bool map_pixel(const PixelXform &m, float xn, float yn, unsigned d, float &wx, float &wy, float &wz) {
 	if (d == 0) return false;
 	const float val = (float)d;
-	float Z = __fdiv_rn(val, 1000.0f);
+	float Z = div1000_u16(val);
 	float X = __fmul_rn(xn, Z);
 	float Y = __fmul_rn(yn, Z);
 	X = __fadd_rn(X, m.t0); Y = __fadd_rn(Y, m.t1); Z = __fadd_rn(Z, m.t2);
@@ -370,12 +386,12 @@ __global__ void __launch_bounds__(kScanThreads) k_triangles(const uint8_t *__res
 // d2 <= thr over its window, leaving at k; pixels whose window exceeds the halo (very near depth, large radii)
 // walk the window in global memory instead, recomputing candidates from the depth image.  Same fp32 expressions,
 // same count >= k decision as the voxel-hash path and the reference — only the candidate enumeration differs.
-constexpr int kOrgTW = 32, kOrgTH = 8, kOrgHalo = 8;
+constexpr int kOrgTW = 32, kOrgRows = 8, kOrgPPT = 2, kOrgTH = kOrgRows * kOrgPPT, kOrgHalo = 8;   // 32x16 pixel tile, 256 threads, 2 pixels (rows ly, ly+8) per thread
 constexpr int kOrgSW = kOrgTW + 2 * kOrgHalo, kOrgSH = kOrgTH + 2 * kOrgHalo;
 
 // count{d2 <= thr} over rows ci + dy*kOrgSW (dy = 0, -1, +1, -2, ... up to +-rv: centre rows first, so an inlier reaches k
 // after a few rows), columns -HX..+HX fully unrolled: one LDS.128 per candidate at an immediate offset, no loop bookkeeping.
-// HX is the block's column reach (>= every in-halo lane's own reach; extra candidates are real points, so counting them
+// HX is the warp's column reach (>= every in-halo lane's own reach; extra candidates are real points, so counting them
 // is still exact).
 template <int HX>
 __device__ __forceinline__ int org_count_rows(const float4 *__restrict__ tile, int ci, int rv, float qx, float qy, float qz, int k, float thr) {
@@ -393,10 +409,24 @@ __device__ __forceinline__ int org_count_rows(const float4 *__restrict__ tile, i
 	return cnt;
 }
 
+__device__ __forceinline__ int org_count_dispatch(int hx, const float4 *__restrict__ tile, int ci, int rv, float qx, float qy, float qz, int k, float thr) {
+	switch (hx) {
+	case 0: return org_count_rows<0>(tile, ci, rv, qx, qy, qz, k, thr);
+	case 1: return org_count_rows<1>(tile, ci, rv, qx, qy, qz, k, thr);
+	case 2: return org_count_rows<2>(tile, ci, rv, qx, qy, qz, k, thr);
+	case 3: return org_count_rows<3>(tile, ci, rv, qx, qy, qz, k, thr);
+	case 4: return org_count_rows<4>(tile, ci, rv, qx, qy, qz, k, thr);
+	case 5: return org_count_rows<5>(tile, ci, rv, qx, qy, qz, k, thr);
+	case 6: return org_count_rows<6>(tile, ci, rv, qx, qy, qz, k, thr);
+	case 7: return org_count_rows<7>(tile, ci, rv, qx, qy, qz, k, thr);
+	default: return org_count_rows<8>(tile, ci, rv, qx, qy, qz, k, thr);
+	}
+}
+
 #ifndef LS3D_ORG_MINBLOCKS
 #define LS3D_ORG_MINBLOCKS 5
 #endif
-__global__ void __launch_bounds__(kOrgTW * kOrgTH, LS3D_ORG_MINBLOCKS) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
+__global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
 	const float *__restrict__ rays, int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px, unsigned *tile_count)
 {
 	__shared__ float4 tile[kOrgSH * kOrgSW];
@@ -409,42 +439,48 @@ __global__ void __launch_bounds__(kOrgTW * kOrgTH, LS3D_ORG_MINBLOCKS) k_organiz
 	const PixelXform m = load_xform(sd, s, bnd.v);
 	const unsigned short *dimg = reinterpret_cast<const unsigned short *>(depth + sd[s].depth_off);
 	const float *xray = rays + sd[s].ray_off, *yray = xray + w;
+	const float *xreach = yray + h, *yreach = xreach + w;     // fx*sqrt(1+xn^2), fy*sqrt(1+yn^2): the window reach per unit of r'/(Z-r')
 	const int tid = threadIdx.x;
 	if (tid == 0) { s_kept = 0; s_hx = 0; s_hy = 0; }
 	__syncthreads();
 
-	// ---- phase 0: this thread's own pixel -> world position into the tile centre, and how far its window reaches ----
+	// ---- phase 0: this thread's own pixels -> world positions into the tile centre, and how far their windows reach ----
 	const int lx = tid & (kOrgTW - 1), ly = tid / kOrgTW;
-	const int x = tx0 + lx, y = ty0 + ly;
-	const int ci = (ly + kOrgHalo) * kOrgSW + lx + kOrgHalo;
+	const int x = tx0 + lx;
 	const float qnan = __int_as_float(0x7fc00000);
-	float qx = qnan, qy = qnan, qz = qnan;
-	int ru = 0, rv = 0;
-	bool has = false;
-	if (x < w && y < h) {
-		const unsigned d = (unsigned)__ldg(dimg + (size_t)y * w + x);
-		const float xn = __ldg(xray + x), yn = __ldg(yray + y);
-		float ax, ay, az;
-		if (map_pixel(m, xn, yn, d, ax, ay, az)) {
-			has = true;
-			qx = ax; qy = ay; qz = az;
-			const float rp = sd[s].org_rp;
-			const float den = (float)d / 1000.0f - rp;
-			ru = 1 << 28; rv = 1 << 28;
-			if (den > 0.0f) {
-				const float fu = fabsf(m.fx) * rp * sqrtf(1.0f + xn * xn) / den * 1.001f + 1e-3f;
-				const float fv = fabsf(m.fy) * rp * sqrtf(1.0f + yn * yn) / den * 1.001f + 1e-3f;
-				if (fu < 1e8f) ru = (int)ceilf(fu);
-				if (fv < 1e8f) rv = (int)ceilf(fv);
+	const float rp = sd[s].org_rp;
+	float qx[kOrgPPT], qy[kOrgPPT], qz[kOrgPPT];
+	int ru[kOrgPPT], rv[kOrgPPT];
+	bool has[kOrgPPT], in_halo[kOrgPPT];
+	int mu = 0, mv = 0;
+#pragma unroll
+	for (int p = 0; p < kOrgPPT; p++) {
+		const int y = ty0 + ly + kOrgRows * p;
+		qx[p] = qnan; qy[p] = qnan; qz[p] = qnan;
+		ru[p] = 0; rv[p] = 0; has[p] = false;
+		if (x < w && y < h) {
+			const unsigned d = (unsigned)__ldg(dimg + (size_t)y * w + x);
+			float ax, ay, az;
+			if (map_pixel(m, __ldg(xray + x), __ldg(yray + y), d, ax, ay, az)) {
+				has[p] = true;
+				qx[p] = ax; qy[p] = ay; qz[p] = az;
+				const float den = (float)d * 0.001f - rp;
+				ru[p] = 1 << 28; rv[p] = 1 << 28;
+				if (den > 1e-6f) {
+					// window reach in pixels; the 0.2 % + 0.01 px margin covers the approximate reciprocal and the rounded tables
+					const float g = __fdividef(rp, den) * 1.002f;
+					const float fu = __ldg(xreach + x) * g + 1e-2f, fv = __ldg(yreach + y) * g + 1e-2f;
+					if (fu < 1e8f) ru[p] = (int)ceilf(fu);
+					if (fv < 1e8f) rv[p] = (int)ceilf(fv);
+				}
 			}
 		}
+		tile[(ly + kOrgRows * p + kOrgHalo) * kOrgSW + lx + kOrgHalo] = make_float4(qx[p], qy[p], qz[p], 0.0f);
+		in_halo[p] = has[p] && ru[p] <= kOrgHalo && rv[p] <= kOrgHalo;
+		if (in_halo[p]) { mu = max(mu, ru[p]); mv = max(mv, rv[p]); }
 	}
-	tile[ci] = make_float4(qx, qy, qz, 0.0f);
-	const bool in_halo = has && ru <= kOrgHalo && rv <= kOrgHalo;
-	{
-		const int mu = __reduce_max_sync(kFull, in_halo ? ru : 0), mv = __reduce_max_sync(kFull, in_halo ? rv : 0);
-		if ((tid & 31) == 0 && (mu | mv)) { atomicMax(&s_hx, mu); atomicMax(&s_hy, mv); }
-	}
+	const int hxw = __reduce_max_sync(kFull, mu), hyw = __reduce_max_sync(kFull, mv);      // this warp's reach
+	if ((tid & 31) == 0 && (hxw | hyw)) { atomicMax(&s_hx, hxw); atomicMax(&s_hy, hyw); }
 	__syncthreads();
 	const int hx = s_hx, hy = s_hy;          // block-uniform reach of the shared-memory windows (0,0: nobody needs the halo)
 
@@ -459,59 +495,59 @@ __global__ void __launch_bounds__(kOrgTW * kOrgTH, LS3D_ORG_MINBLOCKS) k_organiz
 		tile[r * kOrgSW + c] = make_float4(wx, wy, wz, 0.0f);
 	};
 	if (hx | hy) {
-		for (int r = ly; r < 2 * hy; r += kOrgTH) {
+		for (int r = ly; r < 2 * hy; r += kOrgRows) {
 			const int row = r < hy ? kOrgHalo - hy + r : kOrgHalo + kOrgTH + (r - hy);
 			for (int c = lx; c < kOrgTW + 2 * hx; c += kOrgTW) stage(row, kOrgHalo - hx + c);
 		}
-		if (lx < 2 * hx) stage(kOrgHalo + ly, lx < hx ? kOrgHalo - hx + lx : kOrgHalo + kOrgTW + (lx - hx));
+		if (lx < 2 * hx) {
+			const int c = lx < hx ? kOrgHalo - hx + lx : kOrgHalo + kOrgTW + (lx - hx);
+#pragma unroll
+			for (int p = 0; p < kOrgPPT; p++) stage(kOrgHalo + ly + kOrgRows * p, c);
+		}
 	}
 	__syncthreads();
 
 	// ---- phase 2: count ----
-	bool kept = false;
-	if (has) {
-		int cnt = 0;
-		if (in_halo) {
-			switch (hx) {
-			case 0: cnt = org_count_rows<0>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			case 1: cnt = org_count_rows<1>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			case 2: cnt = org_count_rows<2>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			case 3: cnt = org_count_rows<3>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			case 4: cnt = org_count_rows<4>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			case 5: cnt = org_count_rows<5>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			case 6: cnt = org_count_rows<6>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			case 7: cnt = org_count_rows<7>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			default: cnt = org_count_rows<8>(tile, ci, rv, qx, qy, qz, k, thr); break;
-			}
-		} else {
-			// window larger than the halo (very near depth, large radii): walk it in global memory, recomputing candidates
-			const int xa = max(0, x - min(ru, w)), xb = min(w - 1, x + min(ru, w));
-			const int ya = max(0, y - min(rv, h)), yb = min(h - 1, y + min(rv, h));
-			for (int yy = ya; yy <= yb && cnt < k; yy++) {
-				const float yny = __ldg(yray + yy);
-				for (int xx = xa; xx <= xb; xx++) {
-					float ax, ay, az;
-					if (map_pixel(m, __ldg(xray + xx), yny, (unsigned)__ldg(dimg + (size_t)yy * w + xx), ax, ay, az))
-						cnt += dist2_ref(qx, qy, qz, ax, ay, az) <= thr ? 1 : 0;
+	unsigned kept_total = 0;
+#pragma unroll
+	for (int p = 0; p < kOrgPPT; p++) {
+		const int y = ty0 + ly + kOrgRows * p;
+		bool kept = false;
+		if (has[p]) {
+			int cnt = 0;
+			if (in_halo[p]) {
+				cnt = org_count_dispatch(hxw, tile, (ly + kOrgRows * p + kOrgHalo) * kOrgSW + lx + kOrgHalo, rv[p], qx[p], qy[p], qz[p], k, thr);
+			} else {
+				// window larger than the halo (very near depth, large radii): walk it in global memory, recomputing candidates
+				const int xa = max(0, x - min(ru[p], w)), xb = min(w - 1, x + min(ru[p], w));
+				const int ya = max(0, y - min(rv[p], h)), yb = min(h - 1, y + min(rv[p], h));
+				for (int yy = ya; yy <= yb && cnt < k; yy++) {
+					const float yny = __ldg(yray + yy);
+					for (int xx = xa; xx <= xb; xx++) {
+						float ax, ay, az;
+						if (map_pixel(m, __ldg(xray + xx), yny, (unsigned)__ldg(dimg + (size_t)yy * w + xx), ax, ay, az))
+							cnt += dist2_ref(qx[p], qy[p], qz[p], ax, ay, az) <= thr ? 1 : 0;
+					}
 				}
 			}
+			kept = cnt >= k;
 		}
-		kept = cnt >= k;
-	}
-	if (x < w && y < h) keep_px[sd[s].pix_begin + (size_t)y * w + x] = (uint8_t)(kept ? 1 : 0);
-	// survivors per compaction tile of the map kernel (a warp is one 32-pixel row segment: it touches at most two tiles)
-	const unsigned km = __ballot_sync(kFull, kept);
-	if (km) {
-		const int pix = min(y, h - 1) * w + min(x, w - 1);
-		const int t = sd[s].tile_begin + pix / kTile;
-		const int tA = __shfl_sync(kFull, t, 0), tB = __shfl_sync(kFull, t, 31);
-		const unsigned inA = __ballot_sync(kFull, kept && t == tA), inB = km & ~inA;
-		if ((tid & 31) == 0) {
-			if (inA) atomicAdd(&tile_count[tA], (unsigned)__popc(inA));
-			if (inB) atomicAdd(&tile_count[tB], (unsigned)__popc(inB));
-			atomicAdd(&s_kept, (unsigned)__popc(km));
+		if (x < w && y < h) keep_px[sd[s].pix_begin + (size_t)y * w + x] = (uint8_t)(kept ? 1 : 0);
+		// survivors per compaction tile of the map kernel (a warp is one 32-pixel row segment: it touches at most two tiles)
+		const unsigned km = __ballot_sync(kFull, kept);
+		if (km) {
+			const int pix = min(y, h - 1) * w + min(x, w - 1);
+			const int t = sd[s].tile_begin + pix / kTile;
+			const int tA = __shfl_sync(kFull, t, 0), tB = __shfl_sync(kFull, t, 31);
+			const unsigned inA = __ballot_sync(kFull, kept && t == tA), inB = km & ~inA;
+			if ((tid & 31) == 0) {
+				if (inA) atomicAdd(&tile_count[tA], (unsigned)__popc(inA));
+				if (inB) atomicAdd(&tile_count[tB], (unsigned)__popc(inB));
+				kept_total += (unsigned)__popc(km);
+			}
 		}
 	}
+	if ((tid & 31) == 0 && kept_total) atomicAdd(&s_kept, kept_total);
 	__syncthreads();
 	if (tid == 0 && s_kept) atomicAdd(&ctl->n_kept, (int)s_kept);
 }
@@ -1039,7 +1075,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		depth_off += px * 2;
 		color_off += px * 3;
 		d.ray_off = (int)f->n_rays;
-		f->n_rays += (size_t)widths[i] + (size_t)heights[i];
+		f->n_rays += 2 * ((size_t)widths[i] + (size_t)heights[i]);      // xn[w], yn[h], then the window-reach tables xreach[w], yreach[h]
 		const int nt = (int)((px + kTile - 1) / kTile);
 		tile_sensor.insert(tile_sensor.end(), nt, (unsigned short)i);
 		tile_acc += nt;
@@ -1158,6 +1194,10 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 			float *xr = f->pin_rays + d.ray_off, *yr = xr + d.w;
 			for (int x = 0; x < d.w; x++) { volatile float a = (float)x - d.cx; xr[x] = a / d.fx; }
 			for (int y = 0; y < d.h; y++) { volatile float a = d.cy - (float)y; yr[y] = a / d.fy; }
+			// organized neighbour count: pixels a camera-space radius r' spans per unit of r'/(Z - r') (rounded up a little)
+			float *xw = yr + d.h, *yw = xw + d.w;
+			for (int x = 0; x < d.w; x++) xw[x] = (float)(fabs((double)d.fx) * sqrt(1.0 + (double)xr[x] * (double)xr[x]) * (1.0 + 1e-6));
+			for (int y = 0; y < d.h; y++) yw[y] = (float)(fabs((double)d.fy) * sqrt(1.0 + (double)yr[y] * (double)yr[y]) * (1.0 + 1e-6));
 		}
 		d.org_rp = 0.0f;
 		if (f->filter_on) {
@@ -1307,7 +1347,7 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 			for (int i = s_first; i < s_end; i++) { mw = std::max(mw, f->w[i]); mh = std::max(mh, f->h[i]); }
 			const dim3 grid((mw + kOrgTW - 1) / kOrgTW, (mh + kOrgTH - 1) / kOrgTH, n_run);
 			stage_begin(f, kTsOrganized, st);
-			k_organized_count<<<grid, kOrgTW * kOrgTH, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->rays.as<float>(), s_first, b, f->ctl, f->filter_k, f->filter_thr,
+			k_organized_count<<<grid, kOrgTW * kOrgRows, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->rays.as<float>(), s_first, b, f->ctl, f->filter_k, f->filter_thr,
 				f->keep_px.as<uint8_t>(), reinterpret_cast<unsigned *>(f->status_b));
 			stage_end(f, kTsOrganized, st);
 			count_launch(1);
@@ -1620,4 +1660,24 @@ extern "C" int ls3d_filter(Point3f *verts, RGB *colors, int n, int k, float maxD
 	if (ok && old_to_new) ok = cuda_ok(cudaMemcpyAsync(old_to_new, f->map.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st), "read index map");
 	ok = ok && cuda_ok(cudaStreamSynchronize(st), "filter read-back");
 	return ok ? m : -1;
+}
+
+// Device self-checks of the arithmetic shortcuts whose correctness is an exhaustive fact rather than an identity.
+// Returns the number of failures (0 = all good), or -1 when no device is usable.
+extern "C" int ls3d_selftest(void) {
+	clear_error();
+	if (!ensure_device()) return -1;
+	std::lock_guard<std::mutex> lk(api_mutex());
+	cudaStream_t st = api_stream();
+	if (!st) return -1;
+	static DevBuf buf;
+	if (!buf.reserve(256, "alloc selftest")) return -1;
+	int bad = -1;
+	bool ok = cuda_ok(cudaMemsetAsync(buf.p, 0, 4, st), "selftest");
+	if (ok) { k_selftest_div1000<<<256, 256, 0, st>>>(buf.as<int>()); count_launch(1); }
+	ok = ok && cuda_ok(cudaGetLastError(), "k_selftest_div1000") && cuda_ok(cudaMemcpyAsync(&bad, buf.p, 4, cudaMemcpyDeviceToHost, st), "selftest read") &&
+		cuda_ok(cudaStreamSynchronize(st), "selftest");
+	if (!ok) return -1;
+	if (bad) set_error("ls3d_selftest: %d of 65536 depth values divide by 1000 differently from IEEE division", bad);
+	return bad;
 }

@@ -45,6 +45,7 @@ _SIG = {
     "ls3d_icp_trace": (_f, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "ls3d_last_error": (C.c_char_p, []),
     "ls3d_version": (C.c_char_p, []),
+    "ls3d_selftest": (_i, []),
     "ls3d_launch_count": (C.c_longlong, []),
     "ls3d_reset_launch_count": (None, []),
     "ls3d_frame_create": (_vp, [_i, _vp, _vp]),

@@ -30,6 +30,12 @@ def api():
 # ---------------------------------------------------------------------------------------------------------
 # map + world transform + cull + merge
 # ---------------------------------------------------------------------------------------------------------
+def test_device_selftest(api):
+    """d / 1000.0f through the 3-instruction shortcut == IEEE division for all 65536 u16 depths, checked on this device."""
+    from livescan3d_b200 import native
+    assert native.load().ls3d_selftest() == 0, native.last_error()
+
+
 @pytest.mark.parametrize("bname", ["default", "server", "client"])
 @pytest.mark.parametrize("seed", [1000, 2000, 3000])
 def test_vertices_bit_exact_small(api, bname, seed):
