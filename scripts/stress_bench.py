@@ -93,4 +93,35 @@ for target in (217_000, 500_000, 1_000_000, 2_000_000):
     sweep.append({"n1": len(A), "n2": len(B), "ms_per_call": ms, "ms_per_iter": ms / bench.ICP_ITERS, "Mpts_iter_per_s": len(B) * bench.ICP_ITERS / ms / 1e3})
     s.close()
 out["icp_sweep"] = sweep
+
+# ---- global ICP (BASELINE.json configs[3]): the refine-calibration schedule, 2 refine iterations x 8 sensors, target = the other 7 clouds
+from livescan3d_b200 import refine  # noqa: E402
+ring = synth.make_frame(8, synth.KINECT_W, synth.KINECT_H)
+clouds = []
+for i in range(8):
+    c = xyz(api.generate_vertices_from_depth_map(ring, synth.SERVER_BOUNDS, i))
+    if i:
+        c = synth.perturb(c, deg=0.3 + 0.1 * i, trans_mm=(2.0 * i, -3.0, 1.0 * i))
+    clouds.append(np.ascontiguousarray(c))
+dev_clouds0 = [torch.from_numpy(c).to(dev) for c in clouds]
+tot = 0.0
+reps = max(2, steps // 3)
+for it in range(reps + 1):
+    dc = [c.clone() for c in dev_clouds0]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Rs, Ts = refine.refine_poses_device(dc, 2, bench.ICP_ITERS)
+    if it:
+        tot += time.perf_counter() - t0
+n2_total = 2 * sum(len(c) for c in clouds)
+out["global_icp_refine_8_sensors"] = {"ms_per_refine": 1000 * tot / reps, "icp_calls": 16, "iters_per_call": bench.ICP_ITERS, "n_target_per_call": int(sum(len(c) for c in clouds) - len(clouds[0])),
+                                      "Mpts_iter_per_s": n2_total * bench.ICP_ITERS / (tot / reps) / 1e6, "timing": "wall clock around refine_poses_device (device-resident clouds, one host wait per refine iteration)"}
+if "--cpu" in sys.argv:
+    from oracle import oracle_lib as orc  # noqa: E402
+    v1 = np.concatenate(clouds[1:])
+    t0 = time.perf_counter()
+    (orc.ref_icp if orc.have_ref() else orc.orc_icp)(v1, clouds[0], max_iter=2)
+    t_cpu = time.perf_counter() - t0
+    out["global_icp_refine_8_sensors"]["cpu_reference_estimate_ms"] = 1000 * t_cpu / 2 * bench.ICP_ITERS * 16
+    out["global_icp_refine_8_sensors"]["cpu_sample"] = f"one ICP() call of 2 iterations on sensor 0 vs the other 7 clouds ({t_cpu:.2f} s, {os.cpu_count()} cores), scaled to 16 calls x {bench.ICP_ITERS} iterations"
 print(json.dumps(out))

@@ -540,3 +540,44 @@ def test_device_api_matches_host_api(api):
     R2, t2, _ = s.pose()
     assert np.array_equal(R2, hR) and np.array_equal(t2, ht)
     s.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the refine-calibration driver around ICP (MainWindowForm.cs:349-405)
+# ---------------------------------------------------------------------------------------------------------
+def test_refine_poses_schedule(api):
+    import torch
+    from livescan3d_b200 import refine
+    fr = small_frame(S=4, w=128, h=96, ring=8)
+    rng = np.random.default_rng(9)
+    clouds = []
+    for i in range(4):
+        xyz, _ = cloud_of(fr, synth.DEFAULT_BOUNDS, i)
+        if i:                                                  # every sensor but the first starts slightly mis-calibrated
+            xyz = synth.perturb(xyz, deg=0.4 + 0.2 * i, trans_mm=(3.0 * i, -2.0, 1.5 * i))
+        clouds.append(np.ascontiguousarray(xyz))
+    # oracle: the same schedule composed from the CPU ICP
+    want = [c.copy() for c in clouds]
+    wR = [np.eye(3, dtype=np.float32) for _ in range(4)]
+    wT = [np.zeros(3, np.float32) for _ in range(4)]
+    for _ in range(2):
+        for i in range(4):
+            v1 = np.concatenate([want[j] for j in range(4) if j != i])
+            want[i], wR[i], wT[i], _ = orc.orc_icp(v1, want[i], wR[i], wT[i], max_iter=4)
+    got, gR, gT = refine.refine_poses(clouds, 2, 4)
+    for i in range(4):
+        assert rot_err(gR[i], wR[i]) <= 2 * R_TOL and np.max(np.abs(gT[i].astype(np.float64) - wT[i])) <= 2 * T_TOL     # 8 chained ICP calls
+        assert np.max(np.abs(got[i].astype(np.float64) - want[i])) <= 4e-4
+    # device-resident driver == host driver, bit for bit
+    dev = [torch.from_numpy(c.copy()).cuda() for c in clouds]
+    dR, dT = refine.refine_poses_device(dev, 2, 4)
+    assert np.array_equal(dR, gR) and np.array_equal(dT, gT)
+    for i in range(4):
+        assert dev[i].cpu().numpy().tobytes() == got[i].tobytes()
+    # what the server then does with the result (MainWindowForm.cs:377-405)
+    R0 = np.stack([fr["wt"][12 * i + 3:12 * i + 12].reshape(3, 3) for i in range(4)])
+    t0 = np.stack([fr["wt"][12 * i:12 * i + 3] for i in range(4)])
+    nR, nt, cR, ct = refine.update_calibration(R0, t0, R0, t0, gR, gT)
+    for i in range(4):
+        assert np.allclose(nR[i], gR[i].T.astype(np.float64) @ R0[i], atol=1e-6) and np.allclose(nt[i], t0[i] + gT[i] @ R0[i], atol=1e-6)
+        assert np.array_equal(cR[i], nR[i]) and np.allclose(ct[i], t0[i] + gT[i], atol=1e-7)
