@@ -1002,6 +1002,10 @@ struct Ls3dFrame {
 	// pinned read-back block: FrameCtl + starts
 	int *pin_out = nullptr;
 	bool want_d2v = false;
+	// host-buffer path only: the colour upload runs on a second stream; K1 (the only consumer of colours) waits for this event
+	cudaEvent_t colors_ready = nullptr;
+	cudaEvent_t ev_colors = nullptr, ev_count = nullptr;
+	cudaStream_t st_colors = nullptr;
 	bool want_triangles = false;   // run the triangle stage after K1 (unfiltered runs only)
 	// optional per-stage timing (bench.py's roofline pass): a (begin, end) event pair per stage on the run's stream
 	bool timing = false;
@@ -1031,6 +1035,9 @@ static void frame_free(Ls3dFrame *f) {
 	if (f->pin_rays) cudaFreeHost(f->pin_rays);
 	if (f->pin_out) cudaFreeHost(f->pin_out);
 	for (auto &e : f->ev) for (cudaEvent_t x : e) if (x) cudaEventDestroy(x);
+	if (f->ev_colors) cudaEventDestroy(f->ev_colors);
+	if (f->ev_count) cudaEventDestroy(f->ev_count);
+	if (f->st_colors) cudaStreamDestroy(f->st_colors);
 	delete f;
 }
 
@@ -1261,6 +1268,7 @@ static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, i
 	const unsigned short *ts = f->tile_sensor.as<unsigned short>();
 	const float *rays = f->rays.as<float>();
 	const unsigned *tc = reinterpret_cast<const unsigned *>(f->status_b);      // per-tile survivor counts left by the organized count
+	if (f->colors_ready && !cuda_ok(cudaStreamWaitEvent(st, f->colors_ready, 0), "wait for the colour upload")) return -1;
 	stage_begin(f, kTsMap, st);
 	if (f->want_d2v || f->want_triangles) {
 		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers);
@@ -1505,7 +1513,14 @@ static void mesh_reset(Mesh *m) {
 	m->triangles = (int *)malloc(sizeof(int));    // valid empty allocation, like the reference's new int[0]
 }
 
+static bool frame_will_use_organized(const Ls3dFrame *f) {
+	return f->filter_on && f->organized_ok && f->filter_mode != kModeVoxelHash && !(f->filter_mode == kModeAuto && f->organized_wide);
+}
+
 // Shared body: upload sensors [first, first+n_run), run, read back.  Returns total vertices or -1.
+// Overlap: depth goes up on the library stream and the neighbour count starts as soon as it has landed, while the colours (60 % of
+// the input bytes, needed only by the final map/merge kernel) go up on a second stream; on the organized path the survivor count
+// is known before that kernel runs, so the host sizes the read-back while it executes and the call ends with a single wait.
 static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
 	float *intr_params, float *wtransform_params, Mesh *out_mesh, const float bounds[6], int first, int n_run,
 	int filter_k, float filter_maxDist, int *per_map_counts, bool with_triangles = false)
@@ -1521,19 +1536,52 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 	Ls3dFrame *f = cached_frame(n_maps, widths, heights);
 	if (!f) return -1;
 	const SensorDesc &a = f->h_sd[first], &z = f->h_sd[first + n_run];
+	if (!f->st_colors) {
+		if (!cuda_ok(cudaStreamCreateWithFlags(&f->st_colors, cudaStreamNonBlocking), "create colour stream") ||
+			!cuda_ok(cudaEventCreateWithFlags(&f->ev_colors, cudaEventDisableTiming), "create event") ||
+			!cuda_ok(cudaEventCreateWithFlags(&f->ev_count, cudaEventDisableTiming), "create event")) return -1;
+	}
+	struct ColorsGuard { Ls3dFrame *f; ~ColorsGuard() { f->colors_ready = nullptr; if (f->st_colors) cudaStreamSynchronize(f->st_colors); } } guard{f};
 	if (!cuda_ok(cudaMemcpyAsync(f->in_depth.as<uint8_t>() + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off), cudaMemcpyHostToDevice, st), "upload depth")) return -1;
-	if (!cuda_ok(cudaMemcpyAsync(f->in_colors.as<uint8_t>() + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off), cudaMemcpyHostToDevice, st), "upload colours")) return -1;
+	if (!cuda_ok(cudaMemcpyAsync(f->in_colors.as<uint8_t>() + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off), cudaMemcpyHostToDevice, f->st_colors), "upload colours") ||
+		!cuda_ok(cudaEventRecord(f->ev_colors, f->st_colors), "record colour upload")) return -1;
+	f->colors_ready = f->ev_colors;
 	f->filter_mode = g_default_filter_mode;
 	f->want_triangles = with_triangles && !(filter_k > 0 && filter_maxDist > 0);
 	if (frame_set_params(f, n_maps, intr_params, wtransform_params, bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5], filter_k, filter_maxDist, st) < 0) return -1;
+	int *po = f->pin_out;
+	const FrameCtl *hc = reinterpret_cast<const FrameCtl *>(po);
+	if (frame_will_use_organized(f)) {
+		// count stage -> survivor total to the host -> merge stage; the read-back is sized and enqueued while the merge kernel runs
+		PeerDst none; none.n = 0;
+		if (frame_run_impl(f, f->in_depth.p, f->in_colors.p, first, n_run, nullptr, nullptr, none, st, kStageCount) < 0) return -1;
+		if (!cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read survivor count") || !cuda_ok(cudaEventRecord(f->ev_count, st), "record count")) return -1;
+		if (frame_run_impl(f, nullptr, nullptr, first, n_run, f->final_.as<uint4>(), nullptr, none, st, kStageMerge) < 0) return -1;
+		if (!cuda_ok(cudaEventSynchronize(f->ev_count), "neighbour count")) return -1;
+		const int n_early = hc->n_kept;
+		void *v = host_block_alloc((size_t)std::max(n_early, 1) * sizeof(VertexC4ubV3f));
+		if (!v) { set_error("out of host memory for %d vertices", n_early); return -1; }
+		bool ok = (n_early == 0 || cuda_ok(cudaMemcpyAsync(v, f->final_.p, (size_t)n_early * sizeof(VertexC4ubV3f), cudaMemcpyDeviceToHost, st), "read vertices")) &&
+			cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read counts") &&
+			cuda_ok(cudaMemcpyAsync(po + 16, ls3d_frame_sensor_starts(f), sizeof(int) * (n_maps + 1), cudaMemcpyDeviceToHost, st), "read sensor starts") &&
+			cuda_ok(cudaStreamSynchronize(st), "frame pipeline");
+		if (ok && hc->err) { set_error("device reported error flags 0x%x in the frame pipeline", hc->err); ok = false; }
+		if (ok && hc->n_final != n_early) { set_error("internal: merged %d vertices but the neighbour count announced %d", hc->n_final, n_early); ok = false; }
+		if (!ok) { host_block_free(v); return -1; }
+		if (per_map_counts) {
+			for (int i = 0; i < n_maps; i++) per_map_counts[i] = 0;
+			for (int i = first; i < first + n_run; i++) per_map_counts[i] = po[16 + i + 1] - po[16 + i];
+		}
+		out_mesh->vertices = (VertexC4ubV3f *)v;
+		out_mesh->nVertices = n_early;
+		return n_early;
+	}
 	if (ls3d_frame_run(f, f->in_depth.p, f->in_colors.p, first, n_run, st) < 0) return -1;
 	// read back the counts, then exactly the bytes that exist
-	int *po = f->pin_out;
 	const int *starts = ls3d_frame_sensor_starts(f);
 	if (!cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read counts")) return -1;
 	if (!cuda_ok(cudaMemcpyAsync(po + 16, starts, sizeof(int) * (n_maps + 1), cudaMemcpyDeviceToHost, st), "read sensor starts")) return -1;
 	if (!cuda_ok(cudaStreamSynchronize(st), "frame pipeline")) return -1;
-	const FrameCtl *hc = reinterpret_cast<const FrameCtl *>(po);
 	if (hc->err) { set_error("device reported error flags 0x%x in the frame pipeline", hc->err); return -1; }
 	const int n = hc->n_final;
 	if (per_map_counts) {
