@@ -45,7 +45,7 @@ struct IcpState {
 	float R[9], t[3];       // accumulated pose (ls3d_icp_Rt points here)
 	int iters_applied, err, pad0, pad1;
 	unsigned ticket_stats, ticket_sums, n_work, blocks_done;   // n_work: packet counter of the match stage
-	unsigned n_packets, pad3[3];                               // packets of the current source ordering
+	unsigned n_packets, n_heavy, n_light, sched_valid;         // packets of the current source ordering; longest-first schedule (k_icp_stats)
 	float xf[12];           // the update the next match kernel applies: T[3] then Rk[9] (written by the solve step)
 };
 
@@ -637,7 +637,8 @@ __device__ __forceinline__ void pk_walk(const IcpGrid &g, const unsigned *__rest
 #define LS3D_PK_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_packet(float *__restrict__ verts2, int i_begin, int i_end, int apply,
-	const unsigned *__restrict__ order, const uint2 *__restrict__ desc, const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned *__restrict__ order, const uint2 *__restrict__ desc, const unsigned *__restrict__ sched, unsigned *__restrict__ pk_cost,
+	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
 	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, const float *__restrict__ verts1, unsigned long long *slots,
 	IcpState *state, int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg)
 {
@@ -655,9 +656,15 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_
 	const int L = g.levels;
 	const float slack = 1e-3f * g.h;
 	const int n_packets = (int)state->n_packets;
+	const bool use_sched = state->sched_valid != 0;
 	for (;;) {
 		int pk = 0;
-		if (lane == 0) pk = (int)atomicAdd(&state->n_work, 1u);
+		if (lane == 0) {
+			pk = (int)atomicAdd(&state->n_work, 1u);
+			// longest first: the packets that walked furthest last iteration (k_icp_stats' schedule) start in the first wave, so the
+			// kernel's tail is the longest packet alone instead of the longest packet plus whatever ran before it
+			if (pk < n_packets && use_sched) pk = (int)sched[pk];
+		}
 		pk = __shfl_sync(kFull, pk, 0);
 		if (pk >= n_packets) break;
 		const uint2 pd = __ldg(desc + pk);
@@ -744,6 +751,7 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_
 			nn_commit(i, q.d2, q.valid ? q.idx : -1, slots, nn_idx, nn_d2);
 			if (dbg) { dbg[3 * (size_t)i] = steps; dbg[3 * (size_t)i + 1] = scanned; dbg[3 * (size_t)i + 2] = 0u; }
 		}
+		if (lane == 0) pk_cost[pk] = steps;
 		__syncwarp();
 	}
 	// the last block to run dry re-arms the packet counter for the next match stage
@@ -751,6 +759,8 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_
 	if (threadIdx.x == 0 && atomicAdd(&state->blocks_done, 1u) == gridDim.x - 1) {
 		state->blocks_done = 0;
 		state->n_work = 0;
+		state->n_heavy = 0;
+		state->n_light = 0;
 	}
 }
 
@@ -847,10 +857,21 @@ __device__ __forceinline__ bool last_block_finish(const double *partials, double
 }
 
 // count, sum d2, sum d2^2 over the matched slots of [j_begin, j_end)
+constexpr unsigned kPkHeavySteps = 32;      // packets that took more steps than this go first next iteration
+
 __global__ void __launch_bounds__(256) k_icp_stats(const unsigned long long *__restrict__ slots, int j_begin, int j_end,
-	double *partials, double *stats_buf, IcpState *state)
+	double *partials, double *stats_buf, IcpState *state, const unsigned *__restrict__ pk_cost, unsigned *__restrict__ sched)
 {
 	__shared__ double smem[8 * 3];
+	// next iteration's packet schedule (the match stage of this iteration is complete): heavy packets from the front, the rest from the back
+	{
+		const unsigned np = state->n_packets;
+		for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+			if (pk_cost[p] > kPkHeavySteps) sched[atomicAdd(&state->n_heavy, 1u)] = p;
+			else sched[np - 1u - atomicAdd(&state->n_light, 1u)] = p;
+		}
+		if (blockIdx.x == 0 && threadIdx.x == 0) state->sched_valid = 1;
+	}
 	double v[3] = {0, 0, 0};
 	for (int j = j_begin + blockIdx.x * blockDim.x + threadIdx.x; j < j_end; j += gridDim.x * blockDim.x) {
 		const unsigned long long key = slots[j];
@@ -937,6 +958,9 @@ __global__ void k_icp_init_state(IcpState *st, Pose12 p) {
 	st->n_work = 0;
 	st->blocks_done = 0;
 	st->n_packets = 0;
+	st->n_heavy = 0;
+	st->n_light = 0;
+	st->sched_valid = 0;
 	for (int i = 0; i < 12; i++) st->xf[i] = (i == 3 || i == 7 || i == 11) ? 1.0f : 0.0f;
 }
 
@@ -959,7 +983,7 @@ struct Ls3dIcp {
 	const float *d_verts1 = nullptr;
 	float *d_verts2 = nullptr;
 	DevBuf grid, box, state, cell_start, nodes, cellbox, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, work, trace, small;
-	DevBuf src_start, src_cell, src_rank, pk_desc;   // Morton ordering of the source slice (work = the order itself) and its packets
+	DevBuf src_start, src_cell, src_rank, pk_desc, pk_cost, pk_sched;   // Morton ordering of the source slice (work = the order itself), its packets, their cost and schedule
 	bool order_valid = false;
 	DevBuf own_v1, own_v2;        // device copies for the host-buffer API
 	float *pin = nullptr;         // pinned read-back: Rt[12] + status[4]
@@ -971,7 +995,7 @@ struct Ls3dIcp {
 static void icp_free(Ls3dIcp *c) {
 	if (!c) return;
 	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->nodes, &c->cellbox, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
-		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->work, &c->trace, &c->small, &c->own_v1, &c->own_v2, &c->src_start, &c->src_cell, &c->src_rank, &c->pk_desc};
+		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->work, &c->trace, &c->small, &c->own_v1, &c->own_v2, &c->src_start, &c->src_cell, &c->src_rank, &c->pk_desc, &c->pk_cost, &c->pk_sched};
 	for (DevBuf *b : bufs) b->release();
 	if (c->pin) cudaFreeHost(c->pin);
 	if (c->graph) cudaGraphExecDestroy(c->graph);
@@ -1026,7 +1050,9 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 	if (!c->cell_start.reserve(4 * (cells + 8), "alloc cell starts") || !c->scan_status.reserve(8 * (size_t)(scan_tiles + 1), "alloc scan status") ||
 		!c->nodes.reserve(8 * (size_t)(mask_total + 16), "alloc octree nodes") || !c->cellbox.reserve(8 * (cells + 8), "alloc cell records") ||
 		!c->src_start.reserve(4 * (cells + 8), "alloc source cell starts") ||
-		!c->pk_desc.reserve(8 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet table")) return -1;
+		!c->pk_desc.reserve(8 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet table") ||
+		!c->pk_cost.reserve(4 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet costs") ||
+		!c->pk_sched.reserve(4 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet schedule")) return -1;
 	IcpBox hb;
 	for (int a = 0; a < 3; a++) { hb.mn[a] = 0xffffffffu; hb.mx[a] = 0u; }
 	bool ok = cuda_ok(cudaMemcpyAsync(c->box.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, st), "init bbox") &&
@@ -1113,7 +1139,7 @@ static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) 
 		if (!c->order_valid && icp_build_order(c, st) < 0) return -1;
 		const int n_packets = (n_slice + 31) / 32;        // at least; the exact number (node-bounded runs) lives on the device
 		const int nb = std::max(1, std::min((n_packets + kPkWarps - 1) / kPkWarps + 8, c->sm_count * 6));
-		k_icp_match_packet<<<nb, kPkWarps * 32, 0, st>>>(c->d_verts2, c->i_begin, c->i_end, apply, c->work.as<unsigned>(), c->pk_desc.as<uint2>(),
+		k_icp_match_packet<<<nb, kPkWarps * 32, 0, st>>>(c->d_verts2, c->i_begin, c->i_end, apply, c->work.as<unsigned>(), c->pk_desc.as<uint2>(), c->pk_sched.as<unsigned>(), c->pk_cost.as<unsigned>(),
 			c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(), c->d_verts1,
 			c->slots.as<unsigned long long>(), c->state.as<IcpState>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg);
 		count_launch(1);
@@ -1146,7 +1172,7 @@ extern "C" int ls3d_icp_stats(Ls3dIcp *c, int j_begin, int j_end, void *stream) 
 	if (j_begin < 0) j_begin = 0;
 	if (j_end > c->n1 || j_end < 0) j_end = c->n1;
 	k_icp_stats<<<std::min(kRedBlocks, std::max(1, (c->n1 + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(c->slots.as<unsigned long long>(), j_begin, j_end,
-		c->partials.as<double>(), c->stats_buf.as<double>(), c->state.as<IcpState>());
+		c->partials.as<double>(), c->stats_buf.as<double>(), c->state.as<IcpState>(), c->pk_cost.as<unsigned>(), c->pk_sched.as<unsigned>());
 	count_launch(1);
 	return cuda_ok(cudaGetLastError(), "k_icp_stats") ? 0 : -1;
 }
