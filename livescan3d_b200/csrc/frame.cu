@@ -307,17 +307,41 @@ __device__ __forceinline__ bool triangle_ok(const unsigned short *__restrict__ d
 
 // generateTrianglesGradients (meshGenerator.cpp:76-181) for every sensor of the run + formMesh's index rebasing and
 // sensor-order concatenation (depthprocessing.cpp:1611-1626).  d2v holds GLOBAL vertex indices (K1 with kWriteD2V), so no
-// rebasing is left to do.  8 pixels per thread as in K1: a 4-bit emit mask per pixel first, then — with the tile's base from
-// the look-back scan — the index triples are stored in raster order (the reference's band threads concatenate to exactly that).
+// rebasing is left to do.  Per 2048-pixel tile: the depth rows the tests can touch (2 rows above to 1 row below the tile) are
+// staged in shared memory by coalesced loads, so the ~30 u16 reads per pixel never leave the SM; thread t handles pixels
+// t, t+256, ... of the tile (coalesced map reads and triangle stores); a 4-bit emit mask per pixel first, then — with the
+// tile's base from the look-back scan and the 64 (pass, warp) segment offsets — the index triples are stored in raster order
+// (the reference's band threads concatenate to exactly that).
+__device__ __forceinline__ bool triangle_ok_s(const unsigned short *d, int a, int b, int c) {      // triangle_ok on staged depths
+	const int at[3] = {a, b, c};
+	const int v[3] = {(int)d[a], (int)d[b], (int)d[c]};
+	if (v[0] == 0 || v[1] == 0 || v[2] == 0) return false;
+	const int thr = (int)__dadd_rn(__dmul_rn(__ddiv_rn((double)(v[0] + v[1] + v[2]), 3.0), 0.00272), 7.273);
+#pragma unroll
+	for (int e = 0; e < 3; e++) {
+		const int i1 = e, i2 = (e + 1) % 3;
+		const int v1 = v[i1], v2 = v[i2];
+		if (abs(v1 - v2) < thr) continue;
+		const int step = at[i2] - at[i1];
+		const int fwd = (int)d[at[i2] + step];
+		if (fwd != 0 && abs(v2 - v1 - (fwd - v2)) < thr) continue;
+		const int bwd = (int)d[at[i1] - step];
+		if (bwd != 0 && abs(v2 - v1 - (v1 - bwd)) < thr) continue;
+		return false;
+	}
+	return true;
+}
+
 __global__ void __launch_bounds__(kScanThreads) k_triangles(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
 	const unsigned short *__restrict__ tile_sensor, const int *__restrict__ d2v, int s_first, int s_end, FrameCtl *ctl,
 	unsigned long long *status, int *tri_starts, int *__restrict__ tri)
 {
-	__shared__ unsigned sm[16];
+	extern __shared__ unsigned short s_depth[];        // kTile + 3 * max_w + 4 values
+	__shared__ unsigned s_seg[64], s_base, s_total;
 	__shared__ int s_tile;
 	const int tile0 = sd[s_first].tile_begin;
 	const int ntiles = sd[s_end].tile_begin - tile0;
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	for (;;) {
 		if (tid == 0) s_tile = (int)atomicAdd(&ctl->tile_counter_b, 1u);
 		__syncthreads();
@@ -325,50 +349,72 @@ __global__ void __launch_bounds__(kScanThreads) k_triangles(const uint8_t *__res
 		if (tile >= ntiles) break;
 		const int s = tile_sensor[tile + tile0];
 		const int w = sd[s].w, h = sd[s].h, px = sd[s].px;
-		const int p0 = (tile + tile0 - sd[s].tile_begin) * kTile + tid * 8;
+		const int tstart = (tile + tile0 - sd[s].tile_begin) * kTile;
 		const unsigned short *dimg = reinterpret_cast<const unsigned short *>(depth + sd[s].depth_off);
 		const int *map = d2v + sd[s].pix_begin;
-		const int corner[4][3] = {{1, -w, 0}, {1, -w + 1, -w}, {0, -w + 1, -w}, {0, 1, -w + 1}};
+		const int lo = max(0, tstart - 2 * w - 1), hi = min(px, tstart + kTile + w + 3);
+		for (int i = lo + tid; i < hi; i += kScanThreads) s_depth[i - lo] = __ldg(dimg + i);
+		__syncthreads();
+		const unsigned short *D = s_depth - lo;            // D[p] = depth of pixel p for every p the tests below can touch
 
-		unsigned emit = 0;          // 4 bits per pixel
-		int y = p0 / w, x = p0 - y * w;
+		unsigned emit = 0;                                  // 4 bits per pass
+		unsigned long long lane_off = 0;                    // 8 bits per pass: this lane's offset inside its (pass, warp) segment
 #pragma unroll 1
 		for (int j = 0; j < 8; j++) {
-			const int p = p0 + j;
-			if (p < px && y >= 2 && y < h - 2 && x >= 1 && x < w - 2 && __ldg(map + p) != -1) {
-				unsigned ok = 0;
-				if (triangle_ok(dimg, p, p - w, p + 1)) ok |= 1u;
-				if (triangle_ok(dimg, p + 1, p - w, p - w + 1)) ok |= 2u;
-				if (!ok) {
-					if (triangle_ok(dimg, p, p - w, p - w + 1)) ok |= 4u;
-					if (triangle_ok(dimg, p, p - w + 1, p + 1)) ok |= 8u;
+			const int p = tstart + j * kScanThreads + tid;
+			unsigned ok = 0;
+			if (p < px) {
+				const int y = p / w, x = p - y * w;
+				if (y >= 2 && y < h - 2 && x >= 1 && x < w - 2 && __ldg(map + p) != -1) {
+					if (triangle_ok_s(D, p, p - w, p + 1)) ok |= 1u;
+					if (triangle_ok_s(D, p + 1, p - w, p - w + 1)) ok |= 2u;
+					if (!ok) {
+						if (triangle_ok_s(D, p, p - w, p - w + 1)) ok |= 4u;
+						if (triangle_ok_s(D, p, p - w + 1, p + 1)) ok |= 8u;
+					}
+					if (ok) {
+						// a triangle is emitted only when all three corners own vertices (meshGenerator.cpp:131-133); corners per triangle: triangles_shifts (:100-103)
+						const bool m_e = __ldg(map + p + 1) != -1, m_n = __ldg(map + p - w) != -1, m_ne = __ldg(map + p - w + 1) != -1;
+						if (!(m_e && m_n)) ok &= ~1u;
+						if (!(m_e && m_ne && m_n)) ok &= ~2u;
+						if (!(m_ne && m_n)) ok &= ~4u;
+						if (!(m_e && m_ne)) ok &= ~8u;
+					}
 				}
-#pragma unroll
-				for (int t = 0; t < 4; t++)
-					if ((ok >> t) & 1u)
-						if (__ldg(map + p + corner[t][0]) == -1 || __ldg(map + p + corner[t][1]) == -1 || __ldg(map + p + corner[t][2]) == -1) ok &= ~(1u << t);
-				emit |= ok << (4 * j);
 			}
-			if (++x == w) { x = 0; y++; }
+			const unsigned cnt = __popc(ok);
+			const unsigned incl = warp_incl_scan(cnt, lane);
+			if (lane == 31) s_seg[j * 8 + warp] = incl;
+			emit |= ok << (4 * j);
+			lane_off |= (unsigned long long)(incl - cnt) << (8 * j);
 		}
-		const unsigned cnt = __popc(emit);
-		unsigned total, base;
-		const unsigned off = tile_scan(cnt, sm, status, tile, &ctl->err, &total, &base);
-		int *o = tri + 3 * (size_t)(base + off);
-		unsigned rest = emit;
+		__syncthreads();
+		if (warp == 0) {
+			const unsigned a = s_seg[2 * lane], b = s_seg[2 * lane + 1];
+			const unsigned sc = warp_incl_scan(a + b, lane);
+			const unsigned total = __shfl_sync(kFull, sc, 31);
+			const unsigned base = lookback_exclusive(status, tile, total, &ctl->err);
+			s_seg[2 * lane] = sc - a - b;
+			s_seg[2 * lane + 1] = sc - b;
+			if (lane == 0) { s_base = base; s_total = total; }
+		}
+		__syncthreads();
+		const unsigned base = s_base;
 #pragma unroll 1
-		while (rest) {
-			const int bit = __ffs(rest) - 1;
-			rest &= rest - 1;
-			const int p = p0 + (bit >> 2), t = bit & 3;
-			o[0] = __ldg(map + p + corner[t][0]);
-			o[1] = __ldg(map + p + corner[t][1]);
-			o[2] = __ldg(map + p + corner[t][2]);
-			o += 3;
+		for (int j = 0; j < 8; j++) {
+			unsigned ok = (emit >> (4 * j)) & 0xfu;
+			if (!ok) continue;
+			const int p = tstart + j * kScanThreads + tid;
+			int *o = tri + 3 * (size_t)(base + s_seg[j * 8 + warp] + (unsigned)((lane_off >> (8 * j)) & 0xffu));
+			const int m_p = __ldg(map + p), m_e = __ldg(map + p + 1), m_n = __ldg(map + p - w), m_ne = __ldg(map + p - w + 1);
+			if (ok & 1u) { o[0] = m_e; o[1] = m_n; o[2] = m_p; o += 3; }
+			if (ok & 2u) { o[0] = m_e; o[1] = m_ne; o[2] = m_n; o += 3; }
+			if (ok & 4u) { o[0] = m_p; o[1] = m_ne; o[2] = m_n; o += 3; }
+			if (ok & 8u) { o[0] = m_p; o[1] = m_e; o[2] = m_ne; o += 3; }
 		}
 		if (tid == 0) {
 			if (tile + tile0 == sd[s].tile_begin) tri_starts[s] = (int)base;
-			if (tile == ntiles - 1) { tri_starts[s_end] = (int)(base + total); ctl->n_triangles = (int)(base + total); }
+			if (tile == ntiles - 1) { tri_starts[s_end] = (int)(base + s_total); ctl->n_triangles = (int)(base + s_total); }
 		}
 		__syncthreads();
 	}
@@ -1390,7 +1436,12 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 				if (!f->tri.reserve(sizeof(int) * 6 * (size_t)f->total_px + 64, "alloc triangles")) return -1;
 				const int ntiles = f->h_sd[s_end].tile_begin - f->h_sd[s_first].tile_begin;
 				stage_begin(f, kTsTriangles, st);
-				k_triangles<<<std::max(1, std::min(ntiles, f->sm_count * 8)), kScanThreads, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->tile_sensor.as<unsigned short>(),
+				int mw = 0;
+				for (int i = s_first; i < s_end; i++) mw = std::max(mw, f->w[i]);
+				const size_t tri_smem = sizeof(unsigned short) * ((size_t)kTile + 3 * (size_t)mw + 4);
+				if (tri_smem > 200 * 1024) { set_error("triangle stage: image width %d too large for the staged depth rows", mw); return -1; }
+				if (tri_smem > 48 * 1024 && !cuda_ok(cudaFuncSetAttribute(k_triangles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem), "triangle stage shared memory")) return -1;
+				k_triangles<<<std::max(1, std::min(ntiles, f->sm_count * 8)), kScanThreads, tri_smem, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->tile_sensor.as<unsigned short>(),
 					f->d2v.as<int>(), s_first, s_end, f->ctl, f->status_b, f->tri_starts, f->tri.as<int>());
 				stage_end(f, kTsTriangles, st);
 				count_launch(1);
