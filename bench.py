@@ -518,6 +518,29 @@ def run_ours(args, rank, local_rank, world):
                    "unfiltered_mesh_with_triangles_8_sensors_ms": mesh_ms, "triangle_stage_ms": tri_ms, "vertices": int(mc[0]), "triangles": int(mc[4]),
                    "flying_pixel_filter_1_sensor_ms": fly_ms, "flying_alg_bytes": 4 * W_PX * H_PX,
                    "note": "device-resident, CUDA events, L2 flushed; N1 = depthMapAndColorSetRadialCorrection, N3 = generateTriangles+formMesh, N2 = filterFlyingPixels(k=1, thr=10)"}
+        # the reference's own two exports end to end (host buffers in, host Mesh / corrected host buffers out, wall clock)
+        def wall(fn, reps=max(5, min(args.steps, 20))):
+            for _ in range(2):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return 1000.0 * (time.perf_counter() - t0) / reps
+
+        def e2e_mesh():
+            mesh = Mesh()
+            lib.generateMeshFromDepthMaps(S, C.c_void_p(h_depth.data_ptr()), C.c_void_p(h_colors.data_ptr()), p(w_arr), p(h_arr), p(ip), p(wt), C.byref(mesh), 0, *b, 0)
+            nv, nt = mesh.nVertices, mesh.nTriangles
+            lib.deleteMesh(C.byref(mesh))
+            return nv, nt
+        assert e2e_mesh() == (int(mc[0]), int(mc[4])), native.last_error()
+        h_depth_w, h_colors_w = h_depth.clone().pin_memory(), h_colors.clone().pin_memory()
+
+        def e2e_radial():
+            h_depth_w.copy_(h_depth); h_colors_w.copy_(h_colors)
+            lib.depthMapAndColorSetRadialCorrection(S, C.c_void_p(h_depth_w.data_ptr()), C.c_void_p(h_colors_w.data_ptr()), p(w_arr), p(h_arr), p(ip))
+        widened["e2e"] = {"generateMeshFromDepthMaps_8_sensors_ms": wall(e2e_mesh), "mesh_d2h_bytes": int(16 * mc[0] + 12 * mc[4]),
+                          "depthMapAndColorSetRadialCorrection_8_sensors_ms": wall(e2e_radial), "call": "the reference's exports through the C ABI, pinned host buffers, wall clock (radial: includes re-priming the 8.7 MB input)"}
         if world == 1 and not args.no_cpu_baseline:
             orc_w, kind_w = cpu_impl()
             t0 = time.perf_counter(); (orc_w.ref_radial_correction if kind_w == "reference" else orc_w.orc_radial_correction)(frame); t_rad = time.perf_counter() - t0
