@@ -91,7 +91,16 @@ int ls3d_filter(Point3f *verts, RGB *colors, int n, int k, float maxDist, int *o
 /* The whole per-frame path in one call: per sensor map -> world transform -> cull (createVertices,
  * depthprocessing.cpp:122-187) -> neighbour-count filter per sensor (filter.cpp:36-81; skipped when
  * filter_k<=0 or filter_maxDist<=0) -> merge in sensor order (formMesh, depthprocessing.cpp:1578-1629).
- * per_map_counts (may be NULL) receives each sensor's surviving vertex count.  Returns total vertices or -1. */
+ * per_map_counts (may be NULL) receives each sensor's surviving vertex count.  Returns total vertices or -1.
+ *
+ * Host schedule (organized filter path): the sensors are processed in chunks on four streams — upload, count, merge, read-back —
+ * so a chunk's records travel to the host while the next chunk's depth is still arriving; Mesh.vertices is a page-locked
+ * block the device stores into directly (freed by deleteMesh as usual).  If depth_maps / depth_colors are themselves
+ * page-locked (cudaHostAlloc / cudaHostRegister'ed by the caller) the colours are never uploaded — the merge kernel reads the
+ * surviving pixels' colour bytes out of the caller's buffer — and the whole schedule is replayed as one CUDA graph.
+ * Pageable inputs take the same schedule with plain stream launches.  Tuning / diagnosis (environment, read once):
+ * LS3D_E2E_MODE 2|1|0 (pull colours | upload colours | unpipelined), LS3D_E2E_CHUNKS (default 4), LS3D_E2E_GRAPH 1|0,
+ * LS3D_E2E_TRACE n (print the device timeline of call n+8 to stderr). */
 int ls3d_frame_pipeline(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
 	float *intr_params, float *wtransform_params, Mesh *out_mesh,
 	float minX, float minY, float minZ, float maxX, float maxY, float maxZ,
@@ -164,6 +173,8 @@ const int *ls3d_frame_count_ptr(Ls3dFrame *f);        /* device int[5]: {n_final
 const int *ls3d_frame_sensor_starts(Ls3dFrame *f);    /* device int[n_maps+1]: start of each sensor in the merged cloud */
 const int *ls3d_frame_culled_starts(Ls3dFrame *f);    /* device int[n_maps+1]: same for the culled cloud */
 const int *ls3d_frame_old_to_new(Ls3dFrame *f);       /* device int[n_culled]: culled index -> merged index or -1 */
+const unsigned char *ls3d_frame_keep_mask(Ls3dFrame *f); /* device u8[sum w*h]: 1 where the pixel's vertex survived cull + filter in the last ORGANIZED run
+                                                           (the reference's filter mask in pixel order); NULL after any other run */
 const int *ls3d_frame_depth_to_vertex(Ls3dFrame *f);  /* device int[sum w*h]: pixel -> index of its vertex in the culled cloud of the run (all sensors), or -1;
                                                          produced from the next run on (createVertices' depth_to_vertices_map + formMesh's rebasing) */
 

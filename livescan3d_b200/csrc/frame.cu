@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 	const uint8_t *__restrict__ depth, const uint8_t *__restrict__ colors, const SensorDesc *__restrict__ sd, const unsigned short *__restrict__ tile_sensor,
 	const float *__restrict__ rays, int s_first, int s_end, Bounds6 bnd, FrameCtl *ctl, unsigned long long *status, int *culled_starts,
 	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ d2v, const uint8_t *__restrict__ keep_px,
-	const unsigned *__restrict__ tile_count, PeerDst peers)
+	const unsigned *__restrict__ tile_count, PeerDst peers, int tile_lo, int tile_hi)
 {
 	__shared__ unsigned sm[16];
 	__shared__ int s_tile;
@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 	const int ntiles = sd[s_end].tile_begin - tile0;
 	const int out_off = d_out_offset ? *d_out_offset : 0;
 	const int tid = threadIdx.x;
-	int static_tile = blockIdx.x;
+	// kKeepMask only: this launch places tiles [tile_lo, tile_hi) of the run (bases still count from the run's first tile), so
+	// the host path can merge sensor by sensor as the colours arrive; the look-back variant always walks the whole run
+	int static_tile = tile_lo + blockIdx.x;
 
 	for (;;) {
 		int tile;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 			__syncthreads();
 			tile = s_tile;
 		}
-		if (tile >= ntiles) break;
+		if (tile >= (kKeepMask ? tile_hi : ntiles)) break;
 		const int s = tile_sensor[tile + tile0];
 		const int w = sd[s].w, px = sd[s].px;
 		const int p0 = (tile + tile0 - sd[s].tile_begin) * kTile + tid * 8;
@@ -1013,6 +1015,8 @@ using namespace ls3d;
 enum { kTsMap = 0, kTsHashClear, kTsInsert, kTsRanges, kTsCount, kTsCompact, kTsOrganized, kTsWhole, kTsTriangles, kTsN };
 enum { kModeAuto = 0, kModeVoxelHash = 1, kModeOrganized = 2 };
 
+constexpr int kMaxChunks = 16, kEvN = 5 * kMaxChunks + 4;
+struct HostGraphKey { const void *depth, *colors, *out; int first, n_run, chunks, pull; unsigned long long params_version; };
 struct Ls3dFrame {
 	int device = 0;
 	int S = 0;
@@ -1031,6 +1035,7 @@ struct Ls3dFrame {
 	float filter_max_dist = 0, filter_thr = 0;
 	bool filter_on = false;
 	bool params_set = false;
+	std::vector<float> params_key;      // bit pattern of the arguments of the last successful frame_set_params
 	int filter_mode = kModeAuto;
 	bool organized_ok = false;          // every sensor's pose/intrinsics admit the pixel-window bound
 	bool organized_wide = false;        // ... but typical windows exceed the halo: auto mode prefers the voxel hash
@@ -1051,7 +1056,14 @@ struct Ls3dFrame {
 	// host-buffer path only: the colour upload runs on a second stream; K1 (the only consumer of colours) waits for this event
 	cudaEvent_t colors_ready = nullptr;
 	cudaEvent_t ev_colors = nullptr, ev_count = nullptr;
-	cudaStream_t st_colors = nullptr;
+	cudaEvent_t ev_up[kEvN] = {};      // host path: per chunk depth-landed / colours-landed / counted / merged, then fork + 3 joins
+	cudaStream_t st_merge = nullptr;
+	cudaEvent_t ev_tr[4 * kMaxChunks + 1] = {};    // LS3D_E2E_TRACE only: timed events (external records, so they also work inside the graph)
+	cudaGraphExec_t hg_exec = nullptr;  // host path: the captured per-frame schedule, valid for hg_key
+	HostGraphKey hg_key = {};
+	int hg_launches = 0;
+	unsigned long long params_version = 0;   // bumped whenever frame_set_params changes anything on the device
+	cudaStream_t st_colors = nullptr, st_out = nullptr;     // host path: upload stream, read-back stream
 	bool want_triangles = false;   // run the triangle stage after K1 (unfiltered runs only)
 	// optional per-stage timing (bench.py's roofline pass): a (begin, end) event pair per stage on the run's stream
 	bool timing = false;
@@ -1083,7 +1095,12 @@ static void frame_free(Ls3dFrame *f) {
 	for (auto &e : f->ev) for (cudaEvent_t x : e) if (x) cudaEventDestroy(x);
 	if (f->ev_colors) cudaEventDestroy(f->ev_colors);
 	if (f->ev_count) cudaEventDestroy(f->ev_count);
+	for (cudaEvent_t x : f->ev_up) if (x) cudaEventDestroy(x);
 	if (f->st_colors) cudaStreamDestroy(f->st_colors);
+	if (f->st_out) cudaStreamDestroy(f->st_out);
+	if (f->st_merge) cudaStreamDestroy(f->st_merge);
+	for (cudaEvent_t x : f->ev_tr) if (x) cudaEventDestroy(x);
+	if (f->hg_exec) cudaGraphExecDestroy(f->hg_exec);
 	delete f;
 }
 
@@ -1228,6 +1245,20 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 	float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int filter_k, float filter_maxDist, void *stream)
 {
 	if (!f || !intr_params || !wtransform_params) { set_error("ls3d_frame_set_params: null argument"); return -1; }
+	{
+		// a live rig sends the same calibration frame after frame: skip the table rebuild and both uploads when nothing changed
+		// (the device copies are only ever written here, in stream order)
+		std::vector<float> key;
+		key.reserve(10 + 19 * (size_t)n_set);
+		const float head[9] = {minX, minY, minZ, maxX, maxY, maxZ, (float)filter_k, filter_maxDist, (float)n_set};
+		key.insert(key.end(), head, head + 9);
+		key.insert(key.end(), intr_params, intr_params + 7 * (size_t)n_set);
+		key.insert(key.end(), wtransform_params, wtransform_params + 12 * (size_t)n_set);
+		if (f->params_set && key.size() == f->params_key.size() && !memcmp(key.data(), f->params_key.data(), sizeof(float) * key.size())) return 0;
+		f->params_key.swap(key);
+		f->params_set = false;
+		f->params_version++;
+	}
 	f->bounds[0] = minX; f->bounds[1] = minY; f->bounds[2] = minZ; f->bounds[3] = maxX; f->bounds[4] = maxY; f->bounds[5] = maxZ;
 	f->filter_on = filter_k > 0 && filter_maxDist > 0;        // filter.cpp:38-41
 	f->filter_k = filter_k;
@@ -1301,12 +1332,35 @@ __global__ void __launch_bounds__(256) k_keep_all(uint8_t *keep, FrameCtl *ctl) 
 	if (blockIdx.x == 0 && threadIdx.x == 0) ctl->n_kept = N;
 }
 
+// Host path: copies the records that the tiles [tile_lo, tile_hi) of a run produced from the device buffer into the mapped
+// pinned output block.  Every warp store is 512 contiguous bytes, so the PCIe writes are full-size; the record range comes
+// from the per-tile survivor counts (no host round trip to size the read-back).
+__global__ void __launch_bounds__(256) k_copy_out(const uint4 *__restrict__ src, uint4 *__restrict__ dst, const unsigned *__restrict__ tile_count,
+	int tile0, int tile_lo, int tile_hi)
+{
+	__shared__ unsigned s_part[2][8];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned lo = 0, mid = 0;
+	for (int t = tid; t < tile_hi; t += 256) {
+		const unsigned c = __ldg(tile_count + tile0 + t);
+		if (t < tile_lo) lo += c; else mid += c;
+	}
+	lo = warp_sum(lo); mid = warp_sum(mid);
+	if (lane == 0) { s_part[0][warp] = lo; s_part[1][warp] = mid; }
+	__syncthreads();
+	unsigned begin = 0, n = 0;
+#pragma unroll
+	for (int i = 0; i < 8; i++) { begin += s_part[0][i]; n += s_part[1][i]; }
+	for (unsigned i = blockIdx.x * 256 + tid; i < n; i += gridDim.x * 256) dst[begin + i] = src[begin + i];
+}
+
 // K1 launcher.  keep_px != nullptr: AND the organized neighbour-count mask into the validity test.
 static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, int s_first, int s_end, uint4 *out, const int *d_off,
-	const uint8_t *keep_px, const PeerDst &peers, cudaStream_t st)
+	const uint8_t *keep_px, const PeerDst &peers, cudaStream_t st, int tile_lo = 0, int tile_hi = -1)
 {
 	const int ntiles = f->h_sd[s_end].tile_begin - f->h_sd[s_first].tile_begin;
-	const int blocks = std::max(1, std::min(ntiles, f->sm_count * 8));
+	if (tile_hi < 0) tile_hi = ntiles;
+	const int blocks = std::max(1, std::min(tile_hi - tile_lo, f->sm_count * 8));
 	Bounds6 b;
 	memcpy(b.v, f->bounds, sizeof(b.v));
 	const uint8_t *dd = (const uint8_t *)d_depth, *dc = (const uint8_t *)d_colors;
@@ -1317,11 +1371,11 @@ static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, i
 	if (f->colors_ready && !cuda_ok(cudaStreamWaitEvent(st, f->colors_ready, 0), "wait for the colour upload")) return -1;
 	stage_begin(f, kTsMap, st);
 	if (f->want_d2v || f->want_triangles) {
-		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers);
-		else k_map_cull_compact<true, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers);
+		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers, tile_lo, tile_hi);
+		else k_map_cull_compact<true, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers, tile_lo, tile_hi);
 	} else {
-		if (keep_px) k_map_cull_compact<false, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers);
-		else k_map_cull_compact<false, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers);
+		if (keep_px) k_map_cull_compact<false, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers, tile_lo, tile_hi);
+		else k_map_cull_compact<false, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers, tile_lo, tile_hi);
 	}
 	stage_end(f, kTsMap, st);
 	count_launch(1);
@@ -1365,6 +1419,20 @@ static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n
 	return frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st) < 0 ? -1 : 5;
 }
 
+// K1o: per-pixel survivor mask of sensors [s_first, s_end) straight from the depth images (the cloud is only materialised by the
+// merge stage); adds to ctl->n_kept and the per-tile survivor counts, which the caller has zeroed
+static int launch_organized_count(Ls3dFrame *f, const void *d_depth, int s_first, int s_end, cudaStream_t st) {
+	Bounds6 b;
+	memcpy(b.v, f->bounds, sizeof(b.v));
+	int mw = 0, mh = 0;
+	for (int i = s_first; i < s_end; i++) { mw = std::max(mw, f->w[i]); mh = std::max(mh, f->h[i]); }
+	const dim3 grid((mw + kOrgTW - 1) / kOrgTW, (mh + kOrgTH - 1) / kOrgTH, s_end - s_first);
+	k_organized_count<<<grid, kOrgTW * kOrgRows, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->rays.as<float>(), s_first, b, f->ctl, f->filter_k, f->filter_thr,
+		f->keep_px.as<uint8_t>(), reinterpret_cast<unsigned *>(f->status_b));
+	count_launch(1);
+	return cuda_ok(cudaGetLastError(), "k_organized_count") ? 0 : -1;
+}
+
 // stages: kStageCount = everything up to the survivor decision (n_kept known on the device); kStageMerge = the
 // final compaction that places the survivors.  Both together is the normal single-GPU run; the multi-GPU merge
 // runs them separately with the count exchange in between.
@@ -1394,18 +1462,9 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 		stage_begin(f, kTsWhole, st);
 		if (!cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block")) return -1;
 		if (organized) {
-			// K1o: per-pixel survivor mask straight from the depth images; the cloud is only materialised by the merge stage
-			Bounds6 b;
-			memcpy(b.v, f->bounds, sizeof(b.v));
-			int mw = 0, mh = 0;
-			for (int i = s_first; i < s_end; i++) { mw = std::max(mw, f->w[i]); mh = std::max(mh, f->h[i]); }
-			const dim3 grid((mw + kOrgTW - 1) / kOrgTW, (mh + kOrgTH - 1) / kOrgTH, n_run);
 			stage_begin(f, kTsOrganized, st);
-			k_organized_count<<<grid, kOrgTW * kOrgRows, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->rays.as<float>(), s_first, b, f->ctl, f->filter_k, f->filter_thr,
-				f->keep_px.as<uint8_t>(), reinterpret_cast<unsigned *>(f->status_b));
+			if (launch_organized_count(f, d_depth, s_first, s_end, st) < 0) return -1;
 			stage_end(f, kTsOrganized, st);
-			count_launch(1);
-			if (!cuda_ok(cudaGetLastError(), "k_organized_count")) return -1;
 			launched += 1;
 		} else if (f->filter_on) {
 			if (launch_map(f, d_depth, d_colors, s_first, s_end, f->cloud0.as<uint4>(), nullptr, nullptr, none, st) < 0) return -1;
@@ -1516,6 +1575,7 @@ extern "C" const int *ls3d_frame_count_ptr(Ls3dFrame *f) { return f ? &f->ctl->n
 extern "C" const int *ls3d_frame_sensor_starts(Ls3dFrame *f) { return f ? ((f->filter_on && !f->last_organized) ? f->final_starts : f->culled_starts) : nullptr; }
 extern "C" const int *ls3d_frame_culled_starts(Ls3dFrame *f) { return f ? f->culled_starts : nullptr; }
 extern "C" const int *ls3d_frame_old_to_new(Ls3dFrame *f) { return (f && !(f->filter_on && f->last_organized)) ? f->map.as<int>() : nullptr; }
+extern "C" const unsigned char *ls3d_frame_keep_mask(Ls3dFrame *f) { return (f && f->filter_on && f->last_organized) ? f->keep_px.as<unsigned char>() : nullptr; }
 extern "C" void ls3d_frame_enable_triangles(Ls3dFrame *f, int on) { if (f) f->want_triangles = on != 0; }
 extern "C" const int *ls3d_frame_triangles(Ls3dFrame *f) {
 	if (!f) return nullptr;
@@ -1589,21 +1649,150 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 	const SensorDesc &a = f->h_sd[first], &z = f->h_sd[first + n_run];
 	if (!f->st_colors) {
 		if (!cuda_ok(cudaStreamCreateWithFlags(&f->st_colors, cudaStreamNonBlocking), "create colour stream") ||
+			!cuda_ok(cudaStreamCreateWithFlags(&f->st_out, cudaStreamNonBlocking), "create read-back stream") ||
 			!cuda_ok(cudaEventCreateWithFlags(&f->ev_colors, cudaEventDisableTiming), "create event") ||
 			!cuda_ok(cudaEventCreateWithFlags(&f->ev_count, cudaEventDisableTiming), "create event")) return -1;
 	}
-	struct ColorsGuard { Ls3dFrame *f; ~ColorsGuard() { f->colors_ready = nullptr; if (f->st_colors) cudaStreamSynchronize(f->st_colors); } } guard{f};
-	if (!cuda_ok(cudaMemcpyAsync(f->in_depth.as<uint8_t>() + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off), cudaMemcpyHostToDevice, st), "upload depth")) return -1;
-	if (!cuda_ok(cudaMemcpyAsync(f->in_colors.as<uint8_t>() + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off), cudaMemcpyHostToDevice, f->st_colors), "upload colours") ||
-		!cuda_ok(cudaEventRecord(f->ev_colors, f->st_colors), "record colour upload")) return -1;
-	f->colors_ready = f->ev_colors;
+	struct ColorsGuard { Ls3dFrame *f; ~ColorsGuard() { f->colors_ready = nullptr; if (f->st_colors) cudaStreamSynchronize(f->st_colors); if (f->st_out) cudaStreamSynchronize(f->st_out); if (f->st_merge) cudaStreamSynchronize(f->st_merge); } } guard{f};
 	f->filter_mode = g_default_filter_mode;
 	f->want_triangles = with_triangles && !(filter_k > 0 && filter_maxDist > 0);
 	if (frame_set_params(f, n_maps, intr_params, wtransform_params, bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5], filter_k, filter_maxDist, st) < 0) return -1;
 	int *po = f->pin_out;
 	const FrameCtl *hc = reinterpret_cast<const FrameCtl *>(po);
+	uint8_t *const dd = f->in_depth.as<uint8_t>(), *const dc = f->in_colors.as<uint8_t>();
+	cudaStream_t up = f->st_colors;
+	// LS3D_E2E_MODE: 2 (default) pipelined, colours pulled by the merge kernel when the caller's buffer is page-locked; 1 pipelined,
+	// colours uploaded; 0 legacy (upload everything, count -> sized copy)
+	static const int env_mode = getenv("LS3D_E2E_MODE") ? atoi(getenv("LS3D_E2E_MODE")) : 2;
+	static const int env_graph = getenv("LS3D_E2E_GRAPH") ? atoi(getenv("LS3D_E2E_GRAPH")) : 1;
+	static const int env_chunks = getenv("LS3D_E2E_CHUNKS") ? atoi(getenv("LS3D_E2E_CHUNKS")) : 4;
+	static const int env_cblocks = getenv("LS3D_E2E_COPY_BLOCKS") ? atoi(getenv("LS3D_E2E_COPY_BLOCKS")) : 16;
+	static const int env_trace = getenv("LS3D_E2E_TRACE") ? atoi(getenv("LS3D_E2E_TRACE")) : 0;    // 1: direct launches with timed events, timeline printed to stderr
+	if (env_mode != 0 && frame_will_use_organized(f)) {
+		// Pipelined over chunks of sensors on four streams (upload, count, merge, read-back): a chunk's neighbour count starts when
+		// its depth has landed; its map/merge kernel places the survivors at the base the per-tile survivor counts give it; a copy
+		// kernel then stores that record range into the page-locked output block (mapped host memory, 512-byte warp stores).  The
+		// read-back of chunk c therefore overlaps the upload of chunk c+1 (PCIe is full duplex) and needs no survivor count on the
+		// host.  When the caller's colour buffer is page-locked too it is never uploaded: the merge kernel reads the 24-byte colour
+		// groups of surviving pixels straight out of it (a fraction of the image).  With page-locked inputs the whole schedule is one
+		// CUDA graph, re-captured only when a pointer or a parameter changes: one launch and one wait per frame.
+		const int Cn = std::max(1, std::min(std::min(env_chunks, n_run), kMaxChunks));
+		const long long px_run = z.pix_begin - a.pix_begin;
+		void *v = host_block_alloc((size_t)std::max<long long>(px_run, 1) * sizeof(VertexC4ubV3f));
+		void *v_dev = nullptr;
+		if (v && host_block_is_pinned(v) && cudaHostGetDevicePointer(&v_dev, v, 0) == cudaSuccess && v_dev) {
+			auto locked = [](const void *p, void **dev) {
+				cudaPointerAttributes pa;
+				if (cudaPointerGetAttributes(&pa, p) != cudaSuccess) { cudaGetLastError(); return false; }
+				if (pa.type != cudaMemoryTypeHost) return false;
+				if (dev && (cudaHostGetDevicePointer(dev, const_cast<void *>(p), 0) != cudaSuccess || !*dev)) { cudaGetLastError(); return false; }
+				return true;
+			};
+			void *col_dev = nullptr;
+			const bool pull = env_mode == 2 && locked(depth_colors, &col_dev);
+			const bool graph_ok = env_graph != 0 && locked(depth_maps, nullptr) && (pull || locked(depth_colors, nullptr));
+			const uint8_t *col_src = pull ? (const uint8_t *)col_dev : dc;
+			bool ok = true;
+			for (int i = 0; i < kEvN && ok; i++)
+				if (!f->ev_up[i]) ok = cuda_ok(cudaEventCreateWithFlags(&f->ev_up[i], cudaEventDisableTiming), "create event");
+			for (int i = 0; i < 4 * kMaxChunks + 1 && ok && env_trace; i++)
+				if (!f->ev_tr[i]) ok = cuda_ok(cudaEventCreate(&f->ev_tr[i]), "create trace event");
+			auto trace = [&](int kind, int c, cudaStream_t s_) { return !env_trace || cuda_ok(cudaEventRecordWithFlags(f->ev_tr[kind < 0 ? 4 * kMaxChunks : kind * kMaxChunks + c], s_, cudaEventRecordExternal), "trace"); };
+			if (!f->st_merge) ok = ok && cuda_ok(cudaStreamCreateWithFlags(&f->st_merge, cudaStreamNonBlocking), "create merge stream");
+			cudaEvent_t *ev_d = f->ev_up, *ev_c = ev_d + kMaxChunks, *ev_n = ev_c + kMaxChunks, *ev_m = ev_n + kMaxChunks, *ev_o = ev_m + kMaxChunks, *ev_x = ev_o + kMaxChunks;   // ev_x: fork + 3 joins
+			cudaStream_t sm = f->st_merge, so = f->st_out;
+			auto bound = [&](int c) { return first + (int)((long long)n_run * c / Cn); };      // chunk c = sensors [bound(c), bound(c+1))
+			PeerDst none; none.n = 0;
+			auto enqueue = [&]() -> bool {
+				bool k = trace(-1, 0, st) && cuda_ok(cudaEventRecord(ev_x[0], st), "fork") && cuda_ok(cudaStreamWaitEvent(up, ev_x[0], 0), "fork") &&
+					cuda_ok(cudaStreamWaitEvent(sm, ev_x[0], 0), "fork") && cuda_ok(cudaStreamWaitEvent(so, ev_x[0], 0), "fork") &&
+					cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block");
+				for (int c = 0; c < Cn && k; c++) {
+					const SensorDesc &ca = f->h_sd[bound(c)], &cz = f->h_sd[bound(c + 1)];
+					const int tlo = ca.tile_begin - a.tile_begin, thi = cz.tile_begin - a.tile_begin;
+					k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off, depth_maps + ca.depth_off, (size_t)(cz.depth_off - ca.depth_off), cudaMemcpyHostToDevice, up), "upload depth") &&
+						cuda_ok(cudaEventRecord(ev_d[c], up), "record depth upload") && trace(0, c, up);
+					if (k && !pull)
+						k = cuda_ok(cudaMemcpyAsync(dc + ca.color_off, depth_colors + ca.color_off, (size_t)(cz.color_off - ca.color_off), cudaMemcpyHostToDevice, up), "upload colours") &&
+							cuda_ok(cudaEventRecord(ev_c[c], up), "record colour upload");
+					k = k && cuda_ok(cudaStreamWaitEvent(st, ev_d[c], 0), "wait for the depth upload") && launch_organized_count(f, dd, bound(c), bound(c + 1), st) == 0 && trace(1, c, st) &&
+						cuda_ok(cudaEventRecord(ev_n[c], st), "record count") && cuda_ok(cudaStreamWaitEvent(sm, ev_n[c], 0), "wait for the count") &&
+						(pull || cuda_ok(cudaStreamWaitEvent(sm, ev_c[c], 0), "wait for the colour upload")) &&
+						launch_map(f, dd, col_src, first, first + n_run, f->final_.as<uint4>(), nullptr, f->keep_px.as<uint8_t>(), none, sm, tlo, thi) >= 0 &&
+						trace(2, c, sm) && cuda_ok(cudaEventRecord(ev_m[c], sm), "record merge") && cuda_ok(cudaStreamWaitEvent(so, ev_m[c], 0), "wait for the merge");
+					if (!k) break;
+					k_copy_out<<<std::max(1, env_cblocks), 256, 0, so>>>(f->final_.as<uint4>(), (uint4 *)v_dev, reinterpret_cast<const unsigned *>(f->status_b), a.tile_begin, tlo, thi);
+					count_launch(1);
+					k = cuda_ok(cudaGetLastError(), "k_copy_out") && trace(3, c, so);
+				}
+				k = k && cuda_ok(cudaEventRecord(ev_x[1], up), "join") && cuda_ok(cudaEventRecord(ev_x[2], sm), "join") && cuda_ok(cudaEventRecord(ev_x[3], so), "join") &&
+					cuda_ok(cudaStreamWaitEvent(st, ev_x[1], 0), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[2], 0), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[3], 0), "join") &&
+					cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read counts") &&
+					cuda_ok(cudaMemcpyAsync(po + 16, f->culled_starts, sizeof(int) * (n_maps + 1), cudaMemcpyDeviceToHost, st), "read sensor starts");
+				return k;
+			};
+			f->last_organized = true;
+			f->last_depth = dd;
+			f->last_colors = dc;
+			f->ev_recorded = 0;
+			if (ok && graph_ok && !f->timing) {
+				const HostGraphKey key{depth_maps, depth_colors, v, first, n_run, Cn, pull ? 1 : 0, f->params_version};
+				if (!f->hg_exec || memcmp(&key, &f->hg_key, sizeof(key))) {
+					cudaGraph_t g = nullptr;
+					const long long l0 = g_launches.load();
+					ok = cuda_ok(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed), "begin capture");
+					if (ok) {
+						const bool k = enqueue();
+						char keep_err[512];
+						snprintf(keep_err, sizeof(keep_err), "%s", ls3d_last_error());
+						const cudaError_t e = cudaStreamEndCapture(st, &g);
+						if (!k) { set_error("%s", keep_err); ok = false; }
+						else ok = cuda_ok(e, "end capture") && g;
+					}
+					f->hg_launches = (int)(g_launches.load() - l0);
+					g_launches.fetch_sub(f->hg_launches);        // nothing ran yet: launches are counted per graph launch below
+					if (ok && f->hg_exec) {
+						cudaGraphExecUpdateResultInfo info;
+						if (cudaGraphExecUpdate(f->hg_exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(f->hg_exec); f->hg_exec = nullptr; }
+					}
+					if (ok && !f->hg_exec) ok = cuda_ok(cudaGraphInstantiate(&f->hg_exec, g, 0), "instantiate the frame graph");
+					if (g) cudaGraphDestroy(g);
+					if (ok) f->hg_key = key; else if (f->hg_exec) { cudaGraphExecDestroy(f->hg_exec); f->hg_exec = nullptr; }
+				}
+				ok = ok && cuda_ok(cudaGraphLaunch(f->hg_exec, st), "launch the frame graph");
+				if (ok) count_launch(f->hg_launches);
+			} else if (ok) {
+				ok = enqueue();
+			}
+			ok = cuda_ok(cudaStreamSynchronize(st), "frame pipeline") && ok;
+			if (ok && env_trace) {
+				static int trace_calls = 0;
+				if (++trace_calls == env_trace + 8) {
+					auto t = [&](int kind, int c) { float ms = -1; cudaEventElapsedTime(&ms, f->ev_tr[4 * kMaxChunks], f->ev_tr[kind * kMaxChunks + c]); return ms * 1000.0f; };
+					fprintf(stderr, "[ls3d trace] chunk: depth landed / counted / merged / copied out (us after the fork)\n");
+					for (int c = 0; c < Cn; c++) fprintf(stderr, "[ls3d trace] %2d: %7.1f %7.1f %7.1f %7.1f\n", c, t(0, c), t(1, c), t(2, c), t(3, c));
+				}
+			}
+			if (ok && hc->err) { set_error("device reported error flags 0x%x in the frame pipeline", hc->err); ok = false; }
+			if (ok && hc->n_final != hc->n_kept) { set_error("internal: merged %d vertices but the neighbour count announced %d", hc->n_final, hc->n_kept); ok = false; }
+			if (!ok) { host_block_free(v); return -1; }
+			if (per_map_counts) {
+				for (int i = 0; i < n_maps; i++) per_map_counts[i] = 0;
+				for (int i = first; i < first + n_run; i++) per_map_counts[i] = po[16 + i + 1] - po[16 + i];
+			}
+			out_mesh->vertices = (VertexC4ubV3f *)v;
+			out_mesh->nVertices = hc->n_final;
+			return hc->n_final;
+		}
+		if (v) host_block_free(v);
+	}
+	if (!cuda_ok(cudaMemcpyAsync(dd + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off), cudaMemcpyHostToDevice, st), "upload depth")) return -1;
+	if (!cuda_ok(cudaMemcpyAsync(dc + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off), cudaMemcpyHostToDevice, up), "upload colours") ||
+		!cuda_ok(cudaEventRecord(f->ev_colors, up), "record colour upload")) return -1;
+	f->colors_ready = f->ev_colors;
 	if (frame_will_use_organized(f)) {
-		// count stage -> survivor total to the host -> merge stage; the read-back is sized and enqueued while the merge kernel runs
+		// no pinned output block to store into: count stage -> survivor total to the host -> merge stage; the read-back is sized and
+		// enqueued while the merge kernel runs
 		PeerDst none; none.n = 0;
 		if (frame_run_impl(f, f->in_depth.p, f->in_colors.p, first, n_run, nullptr, nullptr, none, st, kStageCount) < 0) return -1;
 		if (!cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read survivor count") || !cuda_ok(cudaEventRecord(f->ev_count, st), "record count")) return -1;

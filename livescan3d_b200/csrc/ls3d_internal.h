@@ -29,6 +29,7 @@ bool ensure_device();
 // caller reads (no staging copy); recycled by deleteMesh.
 void *host_block_alloc(size_t bytes);
 void host_block_free(void *p);
+bool host_block_is_pinned(void *p);     // true: page-locked and mapped, a kernel may store into it
 
 // device scratch with grow-only semantics
 struct DevBuf {

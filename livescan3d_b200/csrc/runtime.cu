@@ -99,7 +99,7 @@ void *host_block_alloc(size_t bytes) {
 	}
 	void *p = nullptr;
 	bool pinned = true;
-	if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+	if (cudaHostAlloc(&p, cap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
 		cudaGetLastError();
 		p = malloc(cap);     // plain host memory is still valid output memory; the copy is just slower
 		pinned = false;
@@ -108,6 +108,12 @@ void *host_block_alloc(size_t bytes) {
 	std::lock_guard<std::mutex> lk(g_hb_mutex);
 	g_hb_live[p] = HostBlock{cap, pinned};
 	return p;
+}
+
+bool host_block_is_pinned(void *p) {
+	std::lock_guard<std::mutex> lk(g_hb_mutex);
+	auto it = g_hb_live.find(p);
+	return it != g_hb_live.end() && it->second.pinned;
 }
 
 void host_block_free(void *p) {

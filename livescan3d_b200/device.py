@@ -127,6 +127,12 @@ class FramePipeline:
     def old_to_new(self) -> torch.Tensor:
         return view(self.lib.ls3d_frame_old_to_new(self.h), (self.total_px,), "<i4", self.device)
 
+    def keep_mask(self) -> torch.Tensor:
+        """uint8 [total_px] survivor mask in pixel order (organized runs only)."""
+        ptr = self.lib.ls3d_frame_keep_mask(self.h)
+        native.check(bool(ptr), "ls3d_frame_keep_mask (no organized run yet)")
+        return view(ptr, (self.total_px,), "|u1", self.device)
+
     def result(self):
         """Synchronise and fetch (vertices ndarray[VERTEX], per-sensor counts) — test/debug convenience."""
         from .api import VERTEX_DTYPE

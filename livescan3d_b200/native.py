@@ -71,6 +71,7 @@ _SIG = {
     "ls3d_frame_sensor_starts": (_vp, [_vp]),
     "ls3d_frame_culled_starts": (_vp, [_vp]),
     "ls3d_frame_old_to_new": (_vp, [_vp]),
+    "ls3d_frame_keep_mask": (_vp, [_vp]),
     "ls3d_frame_depth_to_vertex": (_vp, [_vp]),
     "ls3d_frame_enable_triangles": (None, [_vp, _i]),
     "ls3d_frame_triangles": (_vp, [_vp]),

@@ -364,6 +364,53 @@ def test_frame_pipeline_full_size_8_sensors(api, filter_mode):
     assert np.array_equal(cv[where], gv) and np.all(np.diff(where) > 0)
 
 
+def _page_locked(fr):
+    """The same frame with depth / colours in page-locked host memory (what a capture server would hand over): the host entry
+    point then runs its CUDA-graph schedule and the merge kernel pulls the colours out of the caller's buffer."""
+    import torch
+    keep = [torch.from_numpy(np.ascontiguousarray(fr[k])).pin_memory() for k in ("depth_maps", "depth_colors")]
+    out = dict(fr)
+    out["depth_maps"], out["depth_colors"] = keep[0].numpy(), keep[1].numpy()
+    out["_keep_alive"] = keep
+    return out
+
+
+def test_frame_pipeline_page_locked_inputs_graph_path(api, filter_mode):
+    """Pinned inputs take the captured-graph schedule; alternating buffers, a parameter change and a size change force the
+    re-capture / exec-update paths; every result must equal the oracle's (and therefore the pageable-input path's)."""
+    fr_a = small_frame(S=4, w=160, h=120)
+    fr_b = small_frame(S=4, w=160, h=120, seed_base=4242)
+    want_a = _pipeline_oracle(fr_a, synth.DEFAULT_BOUNDS, 10, 0.02)
+    want_b = _pipeline_oracle(fr_b, synth.DEFAULT_BOUNDS, 10, 0.02)
+    pa, pb = _page_locked(fr_a), _page_locked(fr_b)
+    for rep in range(3):
+        for fr, (want, wcounts) in ((pa, want_a), (pb, want_b), (pa, want_a)):
+            got, gcounts = api.frame_pipeline(fr, synth.DEFAULT_BOUNDS, 10, 0.02)
+            assert np.array_equal(gcounts, wcounts) and got.tobytes() == want.tobytes(), rep
+    # same buffers, other parameters (bounds, k, radius), then pageable inputs again
+    for b, k, md in [(synth.SERVER_BOUNDS, 6, 0.03), (synth.DEFAULT_BOUNDS, 4, 0.05), (synth.DEFAULT_BOUNDS, 10, 0.02)]:
+        want, wcounts = _pipeline_oracle(fr_a, b, k, md)
+        for fr in (pa, fr_a, pa):
+            got, gcounts = api.frame_pipeline(fr, b, k, md)
+            assert np.array_equal(gcounts, wcounts) and got.tobytes() == want.tobytes(), (k, md)
+    # another rig size in between (new context), odd chunking (3 sensors), then back
+    fr_c = synth.make_frame(3, 127, 95, ring=8)
+    want, wcounts = _pipeline_oracle(fr_c, synth.SERVER_BOUNDS, 5, 0.05)
+    got, gcounts = api.frame_pipeline(_page_locked(fr_c), synth.SERVER_BOUNDS, 5, 0.05)
+    assert np.array_equal(gcounts, wcounts) and got.tobytes() == want.tobytes()
+    got, gcounts = api.frame_pipeline(pa, synth.DEFAULT_BOUNDS, 10, 0.02)
+    assert np.array_equal(gcounts, want_a[1]) and got.tobytes() == want_a[0].tobytes()
+
+
+def test_frame_pipeline_page_locked_full_size(api):
+    fr = synth.make_frame(8)
+    want, wcounts = _pipeline_oracle(fr, synth.DEFAULT_BOUNDS, 10, 0.01)
+    pl = _page_locked(fr)
+    for _ in range(3):
+        got, gcounts = api.frame_pipeline(pl, synth.DEFAULT_BOUNDS, 10, 0.01)
+        assert np.array_equal(gcounts, wcounts) and got.tobytes() == want.tobytes()
+
+
 def test_golden_vectors(api):
     g = np.load(os.path.join(GOLDEN, "hotpath_small.npz"))
     fr = synth.make_frame(int(g["S"]), int(g["w"]), int(g["h"]), seed_base=int(g["seed_base"]), ring=int(g["ring"]))
