@@ -471,13 +471,81 @@ __device__ __forceinline__ int org_count_dispatch(int hx, const float4 *__restri
 	}
 }
 
+// ---- packed-fp32 variant (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issue slot) ----
+// The tile is kept as three float planes, so one LDS.64 yields the same coordinate of two horizontally adjacent candidates;
+// the query is broadcast into both halves and every step of d0*d0 + d1*d1 + d2*d2 runs on the pair: 3 FADD2 (differences),
+// 3 FMUL2 (squares), 2 adds.  Each half is rounded exactly like the scalar sequence, so the masks stay bit-exact.  The adds are
+// issued as fma(a, 1.0f, b) == fl(a + b) with the 1.0f taken from a kernel argument: ptxas contracts a packed mul.rn + add.rn
+// into FFMA2 even under --fmad=false (checked in SASS), which would skip the rounding of the product; it cannot do that to an
+// fma whose multiplier it does not know.  Pairs start at even columns, so a window of reach HX is covered by HX+1 pairs (one
+// extra real candidate on one side, which keeps the count exact); the halo is staged one column wider for it.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+template <int HX>
+__device__ __forceinline__ int org_count_rows2(const float *__restrict__ tx, const float *__restrict__ ty, const float *__restrict__ tz,
+	int ci, int rv, float qx, float qy, float qz, int k, float thr, f32x2 one2) {
+	const f32x2 q2x = pk(qx, qx), q2y = pk(qy, qy), q2z = pk(qz, qz);
+	const int c0 = (ci - HX) & ~1;
+	const float kf = (float)k;
+	f32x2 acc = pk(0.0f, 0.0f);
+	float cnt = 0.0f;
+#pragma unroll 1
+	for (int j = 0; j <= 2 * rv && cnt < kf; j++) {
+		const int dy = (j & 1) ? -((j + 1) >> 1) : (j >> 1);
+		const int b = c0 + dy * kOrgSW;
+#pragma unroll
+		for (int p = 0; p <= HX; p++) {
+			const f32x2 X = *reinterpret_cast<const f32x2 *>(tx + b + 2 * p), Y = *reinterpret_cast<const f32x2 *>(ty + b + 2 * p), Z = *reinterpret_cast<const f32x2 *>(tz + b + 2 * p);
+			const f32x2 d0 = sub2(q2x, X), d1 = sub2(q2y, Y), d2 = sub2(q2z, Z);
+			const f32x2 s = fma2(fma2(mul2(d0, d0), one2, mul2(d1, d1)), one2, mul2(d2, d2));
+			float lo, hi;
+			upk(s, lo, hi);
+			acc = add2(acc, pk(lo <= thr ? 1.0f : 0.0f, hi <= thr ? 1.0f : 0.0f));
+		}
+		float a0, a1;
+		upk(acc, a0, a1);
+		cnt = a0 + a1;
+	}
+	return (int)cnt;
+}
+
+__device__ __forceinline__ int org_count_dispatch2(int hx, const float *__restrict__ tx, const float *__restrict__ ty, const float *__restrict__ tz,
+	int ci, int rv, float qx, float qy, float qz, int k, float thr, f32x2 one2) {
+	switch (hx) {
+	case 0: case 1: return org_count_rows2<1>(tx, ty, tz, ci, rv, qx, qy, qz, k, thr, one2);
+	case 2: return org_count_rows2<2>(tx, ty, tz, ci, rv, qx, qy, qz, k, thr, one2);
+	case 3: return org_count_rows2<3>(tx, ty, tz, ci, rv, qx, qy, qz, k, thr, one2);
+	case 4: return org_count_rows2<4>(tx, ty, tz, ci, rv, qx, qy, qz, k, thr, one2);
+	case 5: return org_count_rows2<5>(tx, ty, tz, ci, rv, qx, qy, qz, k, thr, one2);
+	case 6: return org_count_rows2<6>(tx, ty, tz, ci, rv, qx, qy, qz, k, thr, one2);
+	default: return org_count_rows2<7>(tx, ty, tz, ci, rv, qx, qy, qz, k, thr, one2);
+	}
+}
+
+#ifndef LS3D_ORG_PACKED
+#define LS3D_ORG_PACKED 1
+#endif
 #ifndef LS3D_ORG_MINBLOCKS
 #define LS3D_ORG_MINBLOCKS 5
 #endif
 __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
-	const float *__restrict__ rays, int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px, unsigned *tile_count)
+	const float *__restrict__ rays, int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px, unsigned *tile_count, float one)
 {
+#if LS3D_ORG_PACKED
+	__shared__ __align__(16) float tile_x[kOrgSH * kOrgSW], tile_y[kOrgSH * kOrgSW], tile_z[kOrgSH * kOrgSW];
+	auto put = [&](int i, float a, float b, float c) { tile_x[i] = a; tile_y[i] = b; tile_z[i] = c; };
+	constexpr int kReachX = kOrgHalo - 1;       // pairs start at even columns: one halo column is spent on the alignment
+#else
 	__shared__ float4 tile[kOrgSH * kOrgSW];
+	auto put = [&](int i, float a, float b, float c) { tile[i] = make_float4(a, b, c, 0.0f); };
+	constexpr int kReachX = kOrgHalo;
+#endif
 	__shared__ unsigned s_kept;
 	__shared__ int s_hx, s_hy;
 	const int s = s_first + blockIdx.z;
@@ -523,14 +591,15 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 				}
 			}
 		}
-		tile[(ly + kOrgRows * p + kOrgHalo) * kOrgSW + lx + kOrgHalo] = make_float4(qx[p], qy[p], qz[p], 0.0f);
-		in_halo[p] = has[p] && ru[p] <= kOrgHalo && rv[p] <= kOrgHalo;
+		put((ly + kOrgRows * p + kOrgHalo) * kOrgSW + lx + kOrgHalo, qx[p], qy[p], qz[p]);
+		in_halo[p] = has[p] && ru[p] <= kReachX && rv[p] <= kOrgHalo;
 		if (in_halo[p]) { mu = max(mu, ru[p]); mv = max(mv, rv[p]); }
 	}
 	const int hxw = __reduce_max_sync(kFull, mu), hyw = __reduce_max_sync(kFull, mv);      // this warp's reach
 	if ((tid & 31) == 0 && (hxw | hyw)) { atomicMax(&s_hx, hxw); atomicMax(&s_hy, hyw); }
 	__syncthreads();
-	const int hx = s_hx, hy = s_hy;          // block-uniform reach of the shared-memory windows (0,0: nobody needs the halo)
+	const int hy = s_hy;                      // block-uniform reach of the shared-memory windows (0,0: nobody needs the halo)
+	const int hx = (LS3D_ORG_PACKED && (s_hx | s_hy)) ? max(s_hx, 1) + 1 : s_hx;      // packed: dispatch floor 1, one column more for the pair alignment
 
 	// ---- phase 1: stage only the halo ring that some window reaches: hy rows above/below, hx columns left/right ----
 	auto stage = [&](int r, int c) {          // tile coordinates
@@ -540,7 +609,7 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 			float ax, ay, az;
 			if (map_pixel(m, __ldg(xray + gx), __ldg(yray + gy), (unsigned)__ldg(dimg + (size_t)gy * w + gx), ax, ay, az)) { wx = ax; wy = ay; wz = az; }
 		}
-		tile[r * kOrgSW + c] = make_float4(wx, wy, wz, 0.0f);
+		put(r * kOrgSW + c, wx, wy, wz);
 	};
 	if (hx | hy) {
 		for (int r = ly; r < 2 * hy; r += kOrgRows) {
@@ -564,7 +633,11 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 		if (has[p]) {
 			int cnt = 0;
 			if (in_halo[p]) {
+#if LS3D_ORG_PACKED
+				cnt = org_count_dispatch2(hxw, tile_x, tile_y, tile_z, (ly + kOrgRows * p + kOrgHalo) * kOrgSW + lx + kOrgHalo, rv[p], qx[p], qy[p], qz[p], k, thr, pk(one, one));
+#else
 				cnt = org_count_dispatch(hxw, tile, (ly + kOrgRows * p + kOrgHalo) * kOrgSW + lx + kOrgHalo, rv[p], qx[p], qy[p], qz[p], k, thr);
+#endif
 			} else {
 				// window larger than the halo (very near depth, large radii): walk it in global memory, recomputing candidates
 				const int xa = max(0, x - min(ru[p], w)), xb = min(w - 1, x + min(ru[p], w));
@@ -1428,7 +1501,7 @@ static int launch_organized_count(Ls3dFrame *f, const void *d_depth, int s_first
 	for (int i = s_first; i < s_end; i++) { mw = std::max(mw, f->w[i]); mh = std::max(mh, f->h[i]); }
 	const dim3 grid((mw + kOrgTW - 1) / kOrgTW, (mh + kOrgTH - 1) / kOrgTH, s_end - s_first);
 	k_organized_count<<<grid, kOrgTW * kOrgRows, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->rays.as<float>(), s_first, b, f->ctl, f->filter_k, f->filter_thr,
-		f->keep_px.as<uint8_t>(), reinterpret_cast<unsigned *>(f->status_b));
+		f->keep_px.as<uint8_t>(), reinterpret_cast<unsigned *>(f->status_b), 1.0f);
 	count_launch(1);
 	return cuda_ok(cudaGetLastError(), "k_organized_count") ? 0 : -1;
 }
