@@ -521,13 +521,30 @@ def run_ours(args, rank, local_rank, world):
         mesh_ms = timed(lambda: fpm.run(d_depth, d_colors))
         mc = fpm.counts.cpu().numpy()
         fpm.enable_timing(True); fpm.run(d_depth, d_colors); tri_ms = float(fpm.stage_ms()[8]); fpm.enable_timing(False)
+        # N4: the unfiltered mesh, still on the device, re-packed into the binary PLY body and into the TransferServer frame body
+        nv_m, nt_m = int(mc[0]), int(mc[4])
+        ply_out = torch.empty(15 * nv_m + 13 * nt_m + 16, dtype=torch.uint8, device=dev)
+        pv, pt = C.c_void_p(fpm.vertices().data_ptr()), C.c_void_p(fpm.triangles().data_ptr())
+        ply_ms = timed(lambda: native.check(lib.ls3d_pack_ply_body_device(pv, nv_m, pt, nt_m, C.c_void_p(ply_out.data_ptr()), st()) > 0, "ply"))
+        cvs, cts = np.zeros(4096, np.int32), np.zeros(4096, np.int32)
+        nv_out, body = C.c_int(0), C.c_void_p(0)
+        chunk_info = {}
+
+        def chunk_call():
+            chunk_info["chunks"] = lib.ls3d_transfer_chunks_device(pv, nv_m, pt, nt_m, p(cvs), p(cts), 4096, C.byref(nv_out), C.byref(body), st())
+            native.check(chunk_info["chunks"] > 0, "transfer chunks")
+        xfer_ms = timed(chunk_call, reps=5)
+        formats_block = {"ply_body_pack_ms": ply_ms, "ply_alg_bytes": 31 * nv_m + 25 * nt_m, "ply_gbs": (31 * nv_m + 25 * nt_m) / ply_ms / 1e6,
+                         "transfer_frame_chunking_ms": xfer_ms, "transfer_chunks": int(chunk_info["chunks"]), "transfer_vertices_emitted": int(nv_out.value),
+                         "note": "N4, device-resident input (the mesh above): 16 B records + 12 B index triples -> 15 B PLY vertices + 13 B faces; "
+                                 "formMeshChunks + SendFrame body (the chunk loop has one host wait per chunk)"}
         fpm.close()
         one = d_depth[: 2 * W_PX * H_PX]
         fly_out = torch.empty_like(one)
         fly_ms = timed(lambda: native.check(lib.ls3d_filter_flying_pixels_device(C.c_void_p(one.data_ptr()), C.c_void_p(fly_out.data_ptr()), W_PX, H_PX, 1, 10.0, st()) > 0, "flying"))
         widened = {"radial_correction_8_sensors_ms": rad_ms, "radial_alg_bytes": 2 * 5 * px, "radial_gbs": 2 * 5 * px / rad_ms / 1e6,
                    "unfiltered_mesh_with_triangles_8_sensors_ms": mesh_ms, "triangle_stage_ms": tri_ms, "vertices": int(mc[0]), "triangles": int(mc[4]),
-                   "flying_pixel_filter_1_sensor_ms": fly_ms, "flying_alg_bytes": 4 * W_PX * H_PX,
+                   "flying_pixel_filter_1_sensor_ms": fly_ms, "flying_alg_bytes": 4 * W_PX * H_PX, "formats": formats_block,
                    "note": "device-resident, CUDA events, L2 flushed; N1 = depthMapAndColorSetRadialCorrection, N3 = generateTriangles+formMesh, N2 = filterFlyingPixels(k=1, thr=10)"}
         # the reference's own two exports end to end (host buffers in, host Mesh / corrected host buffers out, wall clock)
         def wall(fn, reps=max(5, min(args.steps, 20))):

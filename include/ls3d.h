@@ -8,7 +8,8 @@
  * (filter) or no single entry (the whole frame pipeline), plus the error side channel.
  * Part 3 is the device-resident API (device pointers + a cudaStream_t passed as void*): what bench.py's
  * HBM-resident timing and the multi-GPU host (one process per GPU, torch.distributed for collectives)
- * drive.  Nothing here ever falls back to a CPU implementation: without a CUDA device every compute
+ * drive.  Part 4 covers the data formats either side of the path (client frame blob, frames dump, PLY, transfer frame).
+ * Nothing here ever falls back to a CPU implementation: without a CUDA device every compute
  * entry fails and ls3d_last_error() says why.
  */
 #ifndef LS3D_H
@@ -277,6 +278,71 @@ const int *ls3d_icp_nn_index(Ls3dIcp *c);   /* device int[n2]: last NN index per
 const float *ls3d_icp_nn_dist(Ls3dIcp *c);  /* device f32[n2] */
 Ls3dIcpTrace *ls3d_icp_trace_buf(Ls3dIcp *c); /* device trace[64]: entry i filled by iteration i (i < 64) */
 const int *ls3d_icp_status(Ls3dIcp *c);     /* device int[4]: {iterations applied, error flags, 0, 0} */
+
+/* ---- Part 4: the data formats either side of the path ------------------------------ */
+
+/* The client's frame blob: SerializeFrame (src/LiveScanClient/liveScanClient.cpp:185-290) -> KinectSocket.ReceiveFrame
+ * (LiveScanServer/KinectSocket.cs:211-304).  16-byte header {int payload_bytes, int compressed, int width, int height}, then the
+ * payload — u16 depth[w*h], RGB u8[3*w*h], int n_bodies, per body {u8 tracked, int n_joints, n_joints x {int type, int state,
+ * float x, y, z, float cx, cy}} — as is or as one zstd frame (compressed == 1). */
+typedef struct Ls3dClientFrameInfo {
+	int payload_bytes, compressed, width, height;   /* the header fields */
+	int n_bodies;                                   /* filled by ls3d_client_frame_unpack (-1 after ls3d_client_frame_header) */
+	long long raw_bytes;                            /* payload size after decompression (ditto) */
+} Ls3dClientFrameInfo;
+/* Header only.  0 / -1 (payload_bytes <= 0 is the client's "no more stored frames" marker, KinectSocket.cs:231-235). */
+int ls3d_client_frame_header(const unsigned char *blob, long long blob_bytes, Ls3dClientFrameInfo *info);
+/* Decompresses if needed and copies depth (2*w*h bytes) and colours (3*w*h) to where the caller wants them — typically sensor
+ * i's slot of the packed arrays the path takes (KinectServer.CopyLatestFrames, KinectServer.cs:404-500) — and the body records
+ * (count included) to bodies_out.  Any output may be NULL.  Returns the byte length of the body records or -1. */
+int ls3d_client_frame_unpack(const unsigned char *blob, long long blob_bytes, unsigned char *depth_out, unsigned char *colors_out,
+	unsigned char *bodies_out, long long bodies_cap, Ls3dClientFrameInfo *info);
+/* The writer: depth + per-depth-pixel colours (+ body records, NULL = none) -> blob; compression_level > 0 compresses the payload
+ * with zstd at that level (the client's default is 2, liveScanClient.cpp:60-61).  out == NULL returns a sufficient capacity.
+ * Returns the blob length or -1. */
+long long ls3d_client_frame_pack(const unsigned char *depth, const unsigned char *colors, int width, int height,
+	const unsigned char *bodies, long long bodies_bytes, int compression_level, unsigned char *out, long long out_cap);
+
+/* NativeUtils' frames dump: storeAllFramesInformation / loadAllFramesInformation (src/NativeUtils/depthprocessing.cpp:1316-1385), the
+ * file generateMeshFromDepthMaps reads instead of its arguments when built with LOAD_FRAMES_INFORMATION (:16,:1726-1730): exactly the
+ * argument list of the path's entry points.  Loaded images sit in page-locked memory.  0 / -1. */
+typedef struct Ls3dFramesInfo {
+	int n_maps;
+	unsigned char *depth_maps, *depth_colors;
+	int *widths, *heights;
+	float *intr_params, *wtransform_params;
+} Ls3dFramesInfo;
+int ls3d_frames_info_store(const char *filename, int n_maps, const unsigned char *depth_maps, const unsigned char *depth_colors,
+	const int *widths, const int *heights, const float *intr_params, const float *wtransform_params);
+int ls3d_frames_info_load(const char *filename, Ls3dFramesInfo *out);
+void ls3d_frames_info_free(Ls3dFramesInfo *info);
+
+/* Binary PLY as Utils.saveToPly writes it (LiveScanServer/Utils.cs:222-293; n_triangles < 0: the vertex-only overload :173-220):
+ * text header, 15 bytes per vertex (float x, y, z, uchar r, g, b), 13 per face (uchar 3, int a, b, c).  The first header line ends
+ * in "\r\n" (StreamWriter.WriteLine on Windows), the others in "\n", as in the files the server writes.  The ASCII variant
+ * (off by default, KinectSettings.cs:48) is .NET number formatting and is not provided.
+ * ls3d_ply_binary_size: bytes of the whole file.  ls3d_write_ply_binary: host arrays -> file image in out (the body is packed on
+ * the device); returns its length or -1.  ls3d_pack_ply_body_device: the body only (15*n + 13*nt bytes), device to device
+ * (d_out 16-byte aligned), enqueued on `stream`. */
+long long ls3d_ply_binary_size(int n_vertices, int n_triangles);
+long long ls3d_write_ply_binary(const VertexC4ubV3f *vertices, int n_vertices, const int *triangles, int n_triangles, unsigned char *out, long long out_cap);
+int ls3d_pack_ply_body_device(const void *d_vertices, int n_vertices, const int *d_triangles, int n_triangles, void *d_out, void *stream);
+
+/* The mesh frame TransferServer streams to viewers (HoloLens / Unity): formVerticesChunks / formMeshChunks
+ * (LiveScanServer/TransferServer.cs:179-271) split the mesh into chunks of at most 64 997 vertices — with triangles, a vertex is
+ * re-emitted in every chunk that uses it and the index list becomes chunk-local — and TransferSocket.SendFrame
+ * (LiveScanServer/TransferSocket.cs:50-105) sends int n_vertices, int n_triangles, int n_chunks, int chunk_vertices[n_chunks],
+ * int chunk_triangles[n_chunks], float xyz[3*n_vertices], uchar rgb[3*n_vertices], int triangles[3*n_triangles].
+ * ls3d_write_transfer_frame: host mesh -> that byte stream (out == NULL: returns the exact length); chunking and re-packing run
+ * on the device.  ls3d_transfer_chunks_device: the same for a device-resident mesh (e.g. ls3d_frame_vertices / _triangles): chunk
+ * sizes to the host arrays, the body (xyz | rgb | triangles) stays on the device at *d_body (library memory, valid until the
+ * next call); returns the number of chunks.  ls3d_pack_transfer_body_device: only the re-packing. */
+long long ls3d_transfer_frame_size(int n_vertices, int n_triangles, int n_chunks);
+int ls3d_set_transfer_chunk_limit(int limit);   /* test hook: the chunk size limit (default 65000 - 3, TransferServer.cs:181,205) */
+long long ls3d_write_transfer_frame(const VertexC4ubV3f *vertices, int n_vertices, const int *triangles, int n_triangles, unsigned char *out, long long out_cap);
+int ls3d_transfer_chunks_device(const void *d_vertices, int n_vertices, const int *d_triangles, int n_triangles,
+	int *chunk_vertices, int *chunk_triangles, int chunk_cap, int *n_vertices_out, const void **d_body, void *stream);
+int ls3d_pack_transfer_body_device(const void *d_vertices, int n_vertices, const int *d_triangles, int n_triangles, void *d_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,17 @@ class IcpTrace(C.Structure):
     _fields_ = [("n_matched", C.c_int), ("n_accepted", C.c_int), ("sigma", C.c_float), ("T", C.c_float * 3), ("Rk", C.c_float * 9)]
 
 
+class ClientFrameInfo(C.Structure):
+    """Ls3dClientFrameInfo (include/ls3d.h)"""
+    _fields_ = [("payload_bytes", C.c_int), ("compressed", C.c_int), ("width", C.c_int), ("height", C.c_int), ("n_bodies", C.c_int), ("raw_bytes", C.c_longlong)]
+
+
+class FramesInfo(C.Structure):
+    """Ls3dFramesInfo (include/ls3d.h)"""
+    _fields_ = [("n_maps", C.c_int), ("depth_maps", C.c_void_p), ("depth_colors", C.c_void_p), ("widths", C.c_void_p), ("heights", C.c_void_p),
+                ("intr_params", C.c_void_p), ("wtransform_params", C.c_void_p)]
+
+
 # every symbol include/ls3d.h declares: (restype, argtypes)
 _vp, _i, _f, _ip, _fp = C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_float)
 _SIG = {
@@ -48,6 +59,20 @@ _SIG = {
     "ls3d_selftest": (_i, []),
     "ls3d_launch_count": (C.c_longlong, []),
     "ls3d_reset_launch_count": (None, []),
+    "ls3d_client_frame_header": (_i, [_vp, C.c_longlong, C.POINTER(ClientFrameInfo)]),
+    "ls3d_client_frame_unpack": (_i, [_vp, C.c_longlong, _vp, _vp, _vp, C.c_longlong, C.POINTER(ClientFrameInfo)]),
+    "ls3d_client_frame_pack": (C.c_longlong, [_vp, _vp, _i, _i, _vp, C.c_longlong, _i, _vp, C.c_longlong]),
+    "ls3d_frames_info_store": (_i, [C.c_char_p, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ls3d_frames_info_load": (_i, [C.c_char_p, C.POINTER(FramesInfo)]),
+    "ls3d_frames_info_free": (None, [C.POINTER(FramesInfo)]),
+    "ls3d_ply_binary_size": (C.c_longlong, [_i, _i]),
+    "ls3d_write_ply_binary": (C.c_longlong, [_vp, _i, _vp, _i, _vp, C.c_longlong]),
+    "ls3d_pack_ply_body_device": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "ls3d_transfer_frame_size": (C.c_longlong, [_i, _i, _i]),
+    "ls3d_set_transfer_chunk_limit": (_i, [_i]),
+    "ls3d_write_transfer_frame": (C.c_longlong, [_vp, _i, _vp, _i, _vp, C.c_longlong]),
+    "ls3d_transfer_chunks_device": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ls3d_pack_transfer_body_device": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "ls3d_frame_create": (_vp, [_i, _vp, _vp]),
     "ls3d_frame_destroy": (None, [_vp]),
     "ls3d_frame_set_params": (_i, [_vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),

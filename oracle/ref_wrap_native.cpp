@@ -14,6 +14,10 @@ void generateVerticesFromDepthMaps(unsigned char *depth_maps, unsigned char *dep
 void formMesh(Mesh *out_mesh, vector<VerticesWithDepthColorMaps> &vertices_with_maps, vector<vector<TriangleIndexes>> &triangle_indexes);
 int generateTriangles(vector<VerticesWithDepthColorMaps> &vertices_with_maps, int *heights, int *widths,
 	vector<vector<TriangleIndexes>> &triangle_indexes);
+void storeAllFramesInformation(string filename, int n_maps, unsigned char* depth_maps,
+	unsigned char *depth_colors, int *widths, int *heights, float *intr_params, float *wtransform_params);
+void loadAllFramesInformation(string filename, int &n_maps, unsigned char** depth_maps,
+	unsigned char **depth_colors, int **widths, int **heights, float **intr_params, float **wtransform_params);
 void FindClosestPointForEach(PointCloud &sourceCloud, cv::Mat &destPoints, vector<float> &distances, vector<size_t> &indices);
 
 extern "C" {
@@ -66,6 +70,32 @@ void ref_find_closest(float *verts1, int n1, float *verts2, int n2, unsigned lon
 	vector<size_t> idx(n2);
 	FindClosestPointForEach(cloud1, verts2Mat, d, idx);
 	for (int i = 0; i < n2; i++) { indices[i] = idx[i]; dists[i] = d[i]; }
+}
+
+// storeAllFramesInformation / loadAllFramesInformation (depthprocessing.cpp:1316-1385): the frames dump, written and read by
+// the reference's own code.  ref_load_frames copies what the reference allocated into the caller's arrays (sized by the caller
+// from the file it wrote itself) and returns n_maps.
+void ref_store_frames(const char *filename, int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params)
+{
+	storeAllFramesInformation(filename, n_maps, depth_maps, depth_colors, widths, heights, intr_params, wtransform_params);
+}
+
+int ref_load_frames(const char *filename, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
+	float *intr_params, float *wtransform_params)
+{
+	int n = 0;
+	unsigned char *d = nullptr, *c = nullptr;
+	int *w = nullptr, *h = nullptr;
+	float *ip = nullptr, *wt = nullptr;
+	loadAllFramesInformation(filename, n, &d, &c, &w, &h, &ip, &wt);
+	size_t pd = 0, pc = 0;
+	for (int i = 0; i < n; i++) { pd += (size_t)w[i] * h[i] * 2; pc += (size_t)w[i] * h[i] * 3; }
+	memcpy(depth_maps, d, pd); memcpy(depth_colors, c, pc);
+	memcpy(widths, w, sizeof(int) * n); memcpy(heights, h, sizeof(int) * n);
+	memcpy(intr_params, ip, sizeof(float) * 7 * n); memcpy(wtransform_params, wt, sizeof(float) * 12 * n);
+	delete[] d; delete[] c; delete[] w; delete[] h; delete[] ip; delete[] wt;
+	return n;
 }
 
 }  // extern "C"
