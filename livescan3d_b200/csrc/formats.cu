@@ -256,36 +256,88 @@ __device__ __forceinline__ unsigned ply_byte(const uint8_t *__restrict__ v, cons
 	return k == 0 ? 3u : (unsigned)__ldg(t + 12 * r + (k - 1));
 }
 
+// 16 consecutive bytes of a byte string held in 8 little-endian words P[0..7], starting at byte k (0 <= k <= 15)
+__device__ __forceinline__ uint4 bytes16_at(const unsigned (&P)[8], int k) {
+	const unsigned sh = 8u * (unsigned)(k & 3);
+	switch (k >> 2) {
+	case 0: return make_uint4(__funnelshift_r(P[0], P[1], sh), __funnelshift_r(P[1], P[2], sh), __funnelshift_r(P[2], P[3], sh), __funnelshift_r(P[3], P[4], sh));
+	case 1: return make_uint4(__funnelshift_r(P[1], P[2], sh), __funnelshift_r(P[2], P[3], sh), __funnelshift_r(P[3], P[4], sh), __funnelshift_r(P[4], P[5], sh));
+	case 2: return make_uint4(__funnelshift_r(P[2], P[3], sh), __funnelshift_r(P[3], P[4], sh), __funnelshift_r(P[4], P[5], sh), __funnelshift_r(P[5], P[6], sh));
+	default: return make_uint4(__funnelshift_r(P[3], P[4], sh), __funnelshift_r(P[4], P[5], sh), __funnelshift_r(P[5], P[6], sh), __funnelshift_r(P[6], P[7], sh));
+	}
+}
+
+// One thread = one aligned 16-byte piece of the body.  Pieces that lie inside one section are assembled in registers from whole
+// words: the two 16-byte records a vertex piece touches (2 x LDG.128) are laid out as their 30-byte PLY string by fixed funnel
+// shifts, a face piece does the same with the seven indices it can touch; the piece is then cut out at its phase (piece offset mod
+// record size).  Only the piece that straddles the vertex/face boundary and the tail go byte by byte.
 __global__ void __launch_bounds__(256) k_pack_ply_body(const uint8_t *__restrict__ verts, long long n, const uint8_t *__restrict__ tris, long long nt, uint8_t *__restrict__ out) {
 	const long long vbytes = 15 * n, total = vbytes + 13 * nt;
+	const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(verts);
+	const unsigned *__restrict__ t4 = reinterpret_cast<const unsigned *>(tris);
 	for (long long o = 16ll * (blockIdx.x * 256ll + threadIdx.x); o < total; o += 16ll * 256 * gridDim.x) {
-		unsigned w[4] = {0, 0, 0, 0};
+		if (o + 16 <= vbytes) {
+			const long long r = o / 15;
+			const int k = (int)(o - 15 * r);
+			const uint4 a = __ldg(v4 + r), b = __ldg(v4 + r + 1);          // (rgba, x, y, z); a 16-byte piece always reaches into record r+1
+			const unsigned P[8] = {a.y, a.z, a.w, (a.x & 0xffffffu) | (b.y << 24), __funnelshift_r(b.y, b.z, 8), __funnelshift_r(b.z, b.w, 8),
+				(b.w >> 8) | (b.x << 24), (b.x >> 8) & 0xffffu};
+			*reinterpret_cast<uint4 *>(out + o) = bytes16_at(P, k);
+		} else if (o >= vbytes && o + 16 <= total) {
+			const long long q = o - vbytes, r = q / 13;
+			const int k = (int)(q - 13 * r);
+			const unsigned *src = t4 + 3 * r;
+			const unsigned a0 = __ldg(src), b0 = __ldg(src + 1), c0 = __ldg(src + 2), a1 = __ldg(src + 3), b1 = __ldg(src + 4), c1 = __ldg(src + 5);
+			const unsigned a2 = r + 2 < nt ? __ldg(src + 6) : 0u;           // only its low bytes, and only when the piece starts at k >= 10
+			const unsigned b2 = r + 2 < nt ? __ldg(src + 7) : 0u;
+			const unsigned P[8] = {3u | (a0 << 8), __funnelshift_r(a0, b0, 24), __funnelshift_r(b0, c0, 24), (c0 >> 24) | (3u << 8) | (a1 << 16),
+				__funnelshift_r(a1, b1, 16), __funnelshift_r(b1, c1, 16), (c1 >> 16) | (3u << 16) | (a2 << 24), __funnelshift_r(a2, b2, 8)};
+			*reinterpret_cast<uint4 *>(out + o) = bytes16_at(P, k);
+		} else {
+			unsigned w[4] = {0, 0, 0, 0};
 #pragma unroll
-		for (int b = 0; b < 16; b++)
-			if (o + b < total) w[b >> 2] |= ply_byte(verts, tris, vbytes, o + b) << (8 * (b & 3));
-		if (o + 16 <= total) *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
-		else for (int b = 0; o + b < total; b++) out[o + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+			for (int b = 0; b < 16; b++)
+				if (o + b < total) w[b >> 2] |= ply_byte(verts, tris, vbytes, o + b) << (8 * (b & 3));
+			if (o + 16 <= total) *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+			else for (int b = 0; o + b < total; b++) out[o + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+		}
 	}
 }
 
 // Body of a TransferSocket frame after its header and chunk-size lists (TransferSocket.cs:66-100): float xyz[3n] | uchar rgb[3n] |
-// int triangles[3nt]
+// int triangles[3nt].  xyz pieces are four word loads, triangle pieces a shifted copy; the rgb section (a ninth of the vertex
+// bytes) and the pieces on section boundaries are gathered byte by byte.
 __global__ void __launch_bounds__(256) k_pack_transfer_body(const uint8_t *__restrict__ verts, long long n, const uint8_t *__restrict__ tris, long long nt, uint8_t *__restrict__ out) {
-	const long long xb = 12 * n, cb = 3 * n, total = xb + cb + 12 * nt;
+	const long long xb = 12 * n, cb = 3 * n, tb = xb + cb, total = tb + 12 * nt;
+	const unsigned *__restrict__ v1 = reinterpret_cast<const unsigned *>(verts);
+	const unsigned *__restrict__ t4 = reinterpret_cast<const unsigned *>(tris);
 	for (long long o = 16ll * (blockIdx.x * 256ll + threadIdx.x); o < total; o += 16ll * 256 * gridDim.x) {
-		unsigned w[4] = {0, 0, 0, 0};
+		if (o + 16 <= xb) {
+			unsigned w[4];
 #pragma unroll
-		for (int b = 0; b < 16; b++) {
-			const long long q = o + b;
-			if (q >= total) break;
-			unsigned v;
-			if (q < xb) { const long long r = q / 12; v = __ldg(verts + 16 * r + 4 + (q - 12 * r)); }
-			else if (q < xb + cb) { const long long c = q - xb, r = c / 3; v = __ldg(verts + 16 * r + (c - 3 * r)); }
-			else v = __ldg(tris + (q - xb - cb));
-			w[b >> 2] |= v << (8 * (b & 3));
+			for (int i = 0; i < 4; i++) { const long long j = o / 4 + i, r = j / 3; w[i] = __ldg(v1 + 4 * r + 1 + (j - 3 * r)); }
+			*reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+		} else if (o >= tb && o + 16 <= total) {
+			const long long q = o - tb;                                     // source byte offset in the index list
+			const unsigned *src = t4 + q / 4;
+			const unsigned sh = 8u * (unsigned)(q & 3);
+			const unsigned s0 = __ldg(src), s1 = __ldg(src + 1), s2 = __ldg(src + 2), s3 = __ldg(src + 3), s4 = (sh && q / 4 + 4 < 3 * nt) ? __ldg(src + 4) : 0u;
+			*reinterpret_cast<uint4 *>(out + o) = make_uint4(__funnelshift_r(s0, s1, sh), __funnelshift_r(s1, s2, sh), __funnelshift_r(s2, s3, sh), __funnelshift_r(s3, s4, sh));
+		} else {
+			unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+			for (int b = 0; b < 16; b++) {
+				const long long q = o + b;
+				if (q >= total) break;
+				unsigned v;
+				if (q < xb) { const long long r = q / 12; v = __ldg(verts + 16 * r + 4 + (q - 12 * r)); }
+				else if (q < tb) { const long long c = q - xb, r = c / 3; v = __ldg(verts + 16 * r + (c - 3 * r)); }
+				else v = __ldg(tris + (q - tb));
+				w[b >> 2] |= v << (8 * (b & 3));
+			}
+			if (o + 16 <= total) *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+			else for (int b = 0; o + b < total; b++) out[o + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
 		}
-		if (o + 16 <= total) *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
-		else for (int b = 0; o + b < total; b++) out[o + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
 	}
 }
 
