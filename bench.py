@@ -45,7 +45,7 @@ L2_FLUSH_BYTES = 256 << 20
 
 def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full capture of the
-    same workload (profiles/r01_kernel_traffic.json, made from profiles/r01_ncu_raw_v9_all_kernels_summary.txt); None if absent."""
+    same workload (profiles/r01_kernel_traffic.json, made by profiles/make_kernel_traffic.py from the raw ncu pages named in its "source"); None if absent."""
     p = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
     try:
         with open(p) as f:

@@ -152,31 +152,31 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 		const int rem = px - p0;
 		const PixelXform m = load_xform(sd, s, bnd.v);
 
-		// ---- 8 u16 depths: one LDG.128 (kept packed in 4 registers) ----
-		uint4 dq = make_uint4(0u, 0u, 0u, 0u);
-		const uint8_t *dp = depth + sd[s].depth_off + 2ll * p0;
-		if (rem >= 8 && (((uintptr_t)dp) & 15) == 0) {
-			dq = __ldg(reinterpret_cast<const uint4 *>(dp));
-		} else {
-			unsigned t[8];
-#pragma unroll
-			for (int j = 0; j < 8; j++) t[j] = (j < rem) ? (unsigned)__ldg(reinterpret_cast<const unsigned short *>(dp) + j) : 0u;
-			dq = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
-		}
+		// ---- the organized count's verdicts for the 8 pixels: one LDG.64, bytes (0/1) -> bits by a multiply ----
 		unsigned keepm = 0xffu;
 		if (kKeepMask) {
 			const uint8_t *kp = keep_px + sd[s].pix_begin + p0;
 			keepm = 0;
 			if (rem >= 8 && (((uintptr_t)kp) & 7) == 0) {
 				const uint2 f = __ldg(reinterpret_cast<const uint2 *>(kp));
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					if ((f.x >> (8 * j)) & 0xff) keepm |= 1u << j;
-					if ((f.y >> (8 * j)) & 0xff) keepm |= 1u << (4 + j);
-				}
+				constexpr unsigned kGather = (1u << 24) | (1u << 17) | (1u << 10) | (1u << 3);      // byte j (0 or 1) -> bit 24 + j of the product
+				keepm = ((f.x * kGather) >> 24 & 0xfu) | ((f.y * kGather) >> 20 & 0xf0u);
 			} else {
 #pragma unroll
 				for (int j = 0; j < 8; j++) if (j < rem && __ldg(kp + j)) keepm |= 1u << j;
+			}
+		}
+		// ---- 8 u16 depths: one LDG.128 (kept packed in 4 registers); with a keep mask only threads that emit something need them ----
+		uint4 dq = make_uint4(0u, 0u, 0u, 0u);
+		const uint8_t *dp = depth + sd[s].depth_off + 2ll * p0;
+		if (!kKeepMask || keepm) {
+			if (rem >= 8 && (((uintptr_t)dp) & 15) == 0) {
+				dq = __ldg(reinterpret_cast<const uint4 *>(dp));
+			} else {
+				unsigned t[8];
+#pragma unroll
+				for (int j = 0; j < 8; j++) t[j] = (j < rem) ? (unsigned)__ldg(reinterpret_cast<const unsigned short *>(dp) + j) : 0u;
+				dq = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
 			}
 		}
 		auto depth_of = [&](int j) -> unsigned {

@@ -51,6 +51,32 @@ fo = torch.empty_like(one)
 assert lib.ls3d_filter_flying_pixels_device(C.c_void_p(one.data_ptr()), C.c_void_p(fo.data_ptr()), bench.W_PX, bench.H_PX, 1, 10.0, st) > 0
 torch.cuda.synchronize()
 
+# N4: the mesh just produced, re-packed on the device (PLY body, transfer frame chunking)
+mc = fp.counts.cpu().numpy()
+nv_m, nt_m = int(mc[0]), int(mc[4])
+ply_out = torch.empty(15 * nv_m + 13 * nt_m + 16, dtype=torch.uint8, device=dev)
+pv, pt = C.c_void_p(fp.vertices().data_ptr()), C.c_void_p(fp.triangles().data_ptr())
+assert lib.ls3d_pack_ply_body_device(pv, nv_m, pt, nt_m, C.c_void_p(ply_out.data_ptr()), st) > 0
+import numpy as np  # noqa: E402
+cvs, cts = np.zeros(4096, np.int32), np.zeros(4096, np.int32)
+nv_out, body = C.c_int(0), C.c_void_p(0)
+print("transfer chunks:", lib.ls3d_transfer_chunks_device(pv, nv_m, pt, nt_m, pp(cvs), pp(cts), 4096, C.byref(nv_out), C.byref(body), st))
+torch.cuda.synchronize()
+
+# the host entry point with page-locked inputs (chunked schedule, colours pulled by the merge kernel, copy-out kernels);
+# LS3D_E2E_GRAPH=0 makes it plain stream launches
+from livescan3d_b200.native import Mesh  # noqa: E402
+h_depth = torch.from_numpy(frame["depth_maps"]).pin_memory()
+h_colors = torch.from_numpy(frame["depth_colors"]).pin_memory()
+w_arr, h_arr = np.ascontiguousarray(frame["widths"], np.int32), np.ascontiguousarray(frame["heights"], np.int32)
+ipar, wtr = np.ascontiguousarray(frame["intr"], np.float32), np.ascontiguousarray(frame["wt"], np.float32)
+for _ in range(2):
+    mesh = Mesh()
+    n = lib.ls3d_frame_pipeline(bench.S, C.c_void_p(h_depth.data_ptr()), C.c_void_p(h_colors.data_ptr()), pp(w_arr), pp(h_arr), pp(ipar), pp(wtr), C.byref(mesh),
+                                *[float(x) for x in bench.FRAME_BOUNDS], bench.FILTER_K, bench.FILTER_MAXDIST, None)
+    lib.deleteMesh(C.byref(mesh))
+print("host pipeline:", n)
+
 A, B = bench.icp_clouds(pair, api.generate_vertices_from_depth_map)
 dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
 s = IcpSolver(len(A), len(B))
