@@ -227,8 +227,21 @@ __global__ void __launch_bounds__(kRadChainThreads) k_rad_wavefront(const PreSen
 				const bool todo = my_any && x >= 0 && x < s.w && ((mine[x >> 5] >> (x & 31)) & 1u);
 				if (__any_sync(kFull, todo)) {
 					if (warp > 0 && lane == 0 && todo) {
-						const int need = min(t + 2, s.w);         // N and NE of my pixel t are pixels t, t+1 of the row above
-						while (prog[warp - 1] < need) __nanosleep(32);
+						// NW, N, NE of my pixel t are pixels t-1, t, t+1 of the row above (the previous warp's last row).  Only one that was
+						// still pending when the band started can change under me; everything else in that row was final before this kernel
+						// began, so there is nothing to wait for.  (No gain on the synthetic bench frame: what the round leaves pending there are
+						// the thin hole curves of the forward warp, which cross the rows — genuine chains of ~h links, ~1 us per link.)
+						const unsigned *above = mine - words_per_row;
+						bool dep = false;
+#pragma unroll
+						for (int dx = -1; dx <= 1; dx++) {
+							const int xx = t + dx;
+							if (xx >= 0 && xx < s.w) dep = dep || ((above[xx >> 5] >> (xx & 31)) & 1u);
+						}
+						if (dep) {
+							const int need = min(t + 2, s.w);
+							while (prog[warp - 1] < need) __nanosleep(32);
+						}
 					}
 					__syncwarp();
 					if (todo && !rad_try_resolve<true>(s, y * s.w + x, fdepth, fcolors, state)) atomicOr(err, 16);
