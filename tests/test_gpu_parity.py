@@ -411,6 +411,19 @@ def test_frame_pipeline_page_locked_full_size(api):
         assert np.array_equal(gcounts, wcounts) and got.tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("env", [{"LS3D_E2E_MODE": "1"}, {"LS3D_E2E_MODE": "0"}, {"LS3D_E2E_GRAPH": "0"}, {"LS3D_E2E_CHUNKS": "1"}, {"LS3D_E2E_CHUNKS": "16"}],
+                         ids=lambda e: "_".join(f"{k[9:]}{v}" for k, v in e.items()))
+def test_frame_pipeline_host_schedule_variants(api, env):
+    """The host schedule's switches (colours uploaded instead of pulled, unpipelined legacy path, plain stream launches instead of
+    the graph, 1 / 16 chunks) are read once per process: each variant runs the page-locked tests in a fresh interpreter."""
+    import subprocess
+    import sys
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", "page_locked_inputs_graph_path and organized or page_locked_full_size"],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_golden_vectors(api):
     g = np.load(os.path.join(GOLDEN, "hotpath_small.npz"))
     fr = synth.make_frame(int(g["S"]), int(g["w"]), int(g["h"]), seed_base=int(g["seed_base"]), ring=int(g["ring"]))
