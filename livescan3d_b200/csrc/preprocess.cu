@@ -14,8 +14,10 @@
 //                   values — or even if every unresolved one of them were filled it could not collect more than 4
 //                   neighbours, so it stays 0.  Values are published with "write, fence, flag", so any interleaving of
 //                   threads gives the sequential result.  One grid-wide round settles the vast majority of holes;
-//   k_rad_wavefront one block per sensor finishes what hangs on other holes (fill cascades, region borders) as a skewed
-//                   raster wavefront: w + 2h lockstep steps whatever the dependency structure;
+//   k_rad_chains    one block per sensor finishes what hangs on other holes (fill cascades, the thin hole curves of the warp): the
+//                   pending pixels are listed in raster order and resolved chunk by chunk, each entry waiting only for the earlier
+//                   entries it really reads, whose results travel through shared memory (k_rad_wavefront, the lockstep w + 2h step
+//                   version it replaced, is kept behind LS3D_RADIAL_WAVEFRONT=1 for comparison);
 //   k_rad_writeback results back into the caller's buffers (the reference works in place).
 #include "ls3d_common.cuh"
 #include "ls3d_internal.h"
@@ -23,6 +25,8 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -255,6 +259,143 @@ __global__ void __launch_bounds__(kRadChainThreads) k_rad_wavefront(const PreSen
 	}
 }
 
+// What the grid-wide round left pending, finished chain by chain instead of step by step.  On warped Kinect frames the pending pixels
+// are thin hole curves that cross the rows: genuine dependency chains of ~h links, so what matters is the latency of ONE link, and a
+// link through global memory and a lockstep step costs ~1 us (k_rad_wavefront above: w + 2h steps, 1.6 ms for 512x424).  Here one
+// block per sensor (a) lists its pending pixels in raster order (ordered compaction; pixel -> list index map on the side), (b) walks
+// the list in chunks of 1024 entries, one thread per entry: everything an entry needs that cannot change any more — its four
+// raster-later neighbours, and the raster-earlier ones that are not pending entries of the same chunk — is loaded up front; the
+// thread then only waits for the (at most four) earlier entries of its own chunk, whose results travel through shared memory as
+// single 64-bit words (value + final bit, so no fence): a link costs one spin iteration, ~0.2 us.  Entries of earlier chunks are
+// final in global memory before a chunk starts (block barrier), so chains may cross chunk boundaries anywhere.
+constexpr int kChainThreads = 1024, kChainAdmit = 4;
+__global__ void __launch_bounds__(kChainThreads) k_rad_chains(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state,
+	int *__restrict__ list, int *__restrict__ pidx, int *err)
+{
+	__shared__ unsigned long long s_val[kChainThreads];          // entry i of the chunk: depth | r << 16 | g << 24 | b << 32 | final << 63
+	__shared__ unsigned s_w[32];
+	__shared__ unsigned s_total;
+	__shared__ unsigned s_ndone;                                   // warps of the current chunk that have finished all their entries
+	const PreSensor s = sd[blockIdx.x];
+	const int px = s.w * s.h, w = s.w;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	int *lst = list + s.pix_begin, *pix = pidx + s.pix_begin;
+	// ---- (a) pending list, raster order: 16 consecutive pixels per thread and pass ----
+	unsigned n_pending = 0;
+	for (int base = 0; base < px; base += kChainThreads * 16) {
+		const int p0 = base + tid * 16;
+		unsigned m = 0;
+#pragma unroll
+		for (int j = 0; j < 16; j++)
+			if (p0 + j < px && !(state[s.pix_begin + p0 + j] & kRadDone)) m |= 1u << j;
+		const unsigned cnt = __popc(m), incl = warp_incl_scan(cnt, lane);
+		if (lane == 31) s_w[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			const unsigned v = s_w[lane], sc = warp_incl_scan(v, lane);
+			s_w[lane] = sc - v;
+			if (lane == 31) s_total = sc;
+		}
+		__syncthreads();
+		unsigned o = n_pending + s_w[warp] + incl - cnt;
+		while (m) {
+			const int j = __ffs(m) - 1;
+			m &= m - 1;
+			lst[o] = p0 + j;
+			pix[p0 + j] = (int)o;
+			o++;
+		}
+		n_pending += s_total;
+		__syncthreads();
+	}
+	// ---- (b) chunks of the list ----
+	const int nb[8] = {-w - 1, -w, -w + 1, -1, 1, w - 1, w, w + 1};      // depthprocessing.cpp:226
+	for (unsigned cb = 0; cb < n_pending; cb += kChainThreads) {
+		((volatile unsigned long long *)s_val)[tid] = 0ull;
+		if (tid == 0) s_ndone = 0;
+		__syncthreads();                         // the list, the index map and every earlier chunk's results are visible from here on
+		const bool has = cb + tid < n_pending;
+		long long gp = 0;
+		int val[8], lidx[4];
+		unsigned col[8][3];
+		bool in_chunk[4] = {false, false, false, false};
+		if (has) {
+			const int p = lst[cb + tid];
+			gp = s.pix_begin + p;
+#pragma unroll
+			for (int i = 0; i < 8; i++) {
+				const long long q = gp + nb[i];
+				const uint8_t *c = fcolors + 3 * q;
+				if (i < 4) {
+					const unsigned st = ld_vol_u8<true>(state + q);
+					in_chunk[i] = (st & kRadHole) && !(st & kRadDone);         // pending and raster-earlier: an entry of this chunk
+					lidx[i] = 0;
+					if (in_chunk[i]) {
+						lidx[i] = pix[p + nb[i]] - (int)cb;
+						if (lidx[i] < 0 || lidx[i] >= tid) { atomicOr(err, 32); in_chunk[i] = false; }
+						val[i] = 0;
+					} else {
+						val[i] = (int)ld_vol_u16<true>(fdepth + q);              // final: as warped, or as filled by the round / an earlier chunk
+					}
+					col[i][0] = ld_vol_u8<true>(c); col[i][1] = ld_vol_u8<true>(c + 1); col[i][2] = ld_vol_u8<true>(c + 2);
+				} else {
+					// raster-later: the warped value, which for an original hole is 0 whatever has been filled into it since
+					val[i] = (state[q] & kRadHole) ? 0 : (int)fdepth[q];
+					col[i][0] = c[0]; col[i][1] = c[1]; col[i][2] = c[2];
+				}
+			}
+		}
+		__syncthreads();                         // nobody publishes before everybody has taken its snapshot: no entry of this chunk is final in it
+		bool done = !has;
+		// Results sweep through the chunk as a front (an entry only depends on entries at most a row earlier): a warp far behind the
+		// front has nothing to poll for and would only take issue slots from the warps that resolve — it sleeps until all but
+		// kChainAdmit of the warps before it are done, and only then polls, tightly: a link should cost one loop iteration
+		// (measured: no admission 0.67 ms, window 1 / 4 / 8 warps 0.90 / 0.54 / 0.55 ms; any sleeping inside the poll loop costs more)
+		while ((int)*(volatile unsigned *)&s_ndone < warp - kChainAdmit) __nanosleep(400);
+		for (;;) {
+			if (!done) {
+				bool ready = true;
+				unsigned long long pv[4] = {0, 0, 0, 0};
+#pragma unroll
+				for (int i = 0; i < 4; i++)
+					if (in_chunk[i]) { pv[i] = ((volatile unsigned long long *)s_val)[lidx[i]]; ready = ready && (pv[i] >> 63); }
+				if (ready) {
+#pragma unroll
+					for (int i = 0; i < 4; i++)
+						if (in_chunk[i]) {
+							val[i] = (int)(pv[i] & 0xffffull);
+							col[i][0] = (unsigned)(pv[i] >> 16) & 0xffu; col[i][1] = (unsigned)(pv[i] >> 24) & 0xffu; col[i][2] = (unsigned)(pv[i] >> 32) & 0xffu;
+						}
+					int n = 0, sum = 0, sr = 0, sg = 0, sb = 0, prev = -1;
+#pragma unroll
+					for (int i = 0; i < 8; i++) {
+						if (val[i] > 0 && (prev == -1 || abs(val[i] - prev) < 30)) {       // depthprocessing.cpp:239
+							prev = val[i]; n++; sum += val[i];
+							sr += (int)col[i][0]; sg += (int)col[i][1]; sb += (int)col[i][2];
+						}
+					}
+					unsigned long long r = 1ull << 63;                                   // stays 0 (:249)
+					if (n > 4) {
+						// x / n for 5 <= n <= 8 and x < 2^20 (eight depths / colour bytes) as a multiply: floor(x * ceil(2^32 / n) / 2^32) is exact there
+						// (the error of the scaled reciprocal, < x / 2^32 < 2^-12, cannot carry a quotient with fractional part <= 7/8 over the next integer)
+						const unsigned rcp = n == 5 ? 858993460u : n == 6 ? 715827883u : n == 7 ? 613566757u : 536870912u;
+						const unsigned d = __umulhi((unsigned)sum, rcp), cr = __umulhi((unsigned)sr, rcp) & 0xffu, cg = __umulhi((unsigned)sg, rcp) & 0xffu, cbl = __umulhi((unsigned)sb, rcp) & 0xffu;
+						r |= (unsigned long long)(d & 0xffffu) | ((unsigned long long)cr << 16) | ((unsigned long long)cg << 24) | ((unsigned long long)cbl << 32);
+						fcolors[3 * gp] = (uint8_t)cr; fcolors[3 * gp + 1] = (uint8_t)cg; fcolors[3 * gp + 2] = (uint8_t)cbl;
+						fdepth[gp] = (unsigned short)d;
+					}
+					((volatile unsigned long long *)s_val)[tid] = r;
+					state[gp] = kRadHole | kRadDone;
+					done = true;
+				}
+			}
+			if (__all_sync(kFull, done)) break;
+		}
+		if (lane == 0) atomicAdd(&s_ndone, 1u);
+		__syncthreads();
+	}
+}
+
 __global__ void __launch_bounds__(256) k_rad_writeback(uint8_t *__restrict__ depth, uint8_t *__restrict__ colors, long long total_px,
 	const unsigned short *__restrict__ fdepth, const uint8_t *__restrict__ fcolors)
 {
@@ -340,7 +481,7 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 	c->total_px = acc;
 	const size_t n = (size_t)acc;
 	bool ok = c->sd.reserve(sizeof(PreSensor) * n_maps, "alloc descriptors") && c->winner.reserve(4 * n, "alloc warp winners") && c->fdepth.reserve(2 * n, "alloc warped depth") &&
-		c->fcolors.reserve(3 * n, "alloc warped colours") && c->state.reserve(n, "alloc hole states") &&
+		c->fcolors.reserve(3 * n, "alloc warped colours") && c->state.reserve(n, "alloc hole states") && c->items.reserve(4 * n, "alloc pending lists") &&
 		c->count.reserve(4 * (size_t)n_maps + 4, "alloc worklist counts");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin_sd, sizeof(PreSensor) * n_maps, cudaHostAllocDefault), "alloc pinned descriptors");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin_err, 64, cudaHostAllocDefault), "alloc pinned status");
@@ -373,16 +514,22 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 	k_rad_gather<<<grid, 256, 0, st>>>(d_depth, d_colors, sd, c->winner.as<int>(), c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
 	for (int r = 0; r < kRadRounds; r++)
 		k_rad_round<<<grid, 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
-	int max_h = 1, max_w = 1;
-	for (int i = 0; i < n_maps; i++) { max_h = std::max(max_h, c->h[i]); max_w = std::max(max_w, c->w[i]); }
-	const int words_per_row = (max_w + 31) / 32;
-	int rows = std::min(kRadChainThreads, (max_h + 31) / 32 * 32);
-	const int smem_budget = 200 * 1024;                           // of the 227 KB a block may use
-	while (rows > 32 && (size_t)rows * words_per_row * 4 > (size_t)smem_budget) rows -= 32;
-	const size_t wf_smem = (size_t)rows * words_per_row * 4;
-	if (wf_smem > (size_t)smem_budget) { set_error("radial correction: image width %d too large for the wavefront's pending map", max_w); return -1; }
-	if (!cuda_ok(cudaFuncSetAttribute(k_rad_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget), "wavefront shared memory")) return -1;
-	k_rad_wavefront<<<n_maps, rows, wf_smem, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), words_per_row, count + n_maps);
+	static const int env_wavefront = getenv("LS3D_RADIAL_WAVEFRONT") ? atoi(getenv("LS3D_RADIAL_WAVEFRONT")) : 0;      // 1: the previous lockstep wavefront (A/B)
+	if (env_wavefront) {
+		int max_h = 1, max_w = 1;
+		for (int i = 0; i < n_maps; i++) { max_h = std::max(max_h, c->h[i]); max_w = std::max(max_w, c->w[i]); }
+		const int words_per_row = (max_w + 31) / 32;
+		int rows = std::min(kRadChainThreads, (max_h + 31) / 32 * 32);
+		const int smem_budget = 200 * 1024;                           // of the 227 KB a block may use
+		while (rows > 32 && (size_t)rows * words_per_row * 4 > (size_t)smem_budget) rows -= 32;
+		const size_t wf_smem = (size_t)rows * words_per_row * 4;
+		if (wf_smem > (size_t)smem_budget) { set_error("radial correction: image width %d too large for the wavefront's pending map", max_w); return -1; }
+		if (!cuda_ok(cudaFuncSetAttribute(k_rad_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget), "wavefront shared memory")) return -1;
+		k_rad_wavefront<<<n_maps, rows, wf_smem, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), words_per_row, count + n_maps);
+	} else {
+		// the winner map is free after the gather: it becomes the pixel -> list index map
+		k_rad_chains<<<n_maps, kChainThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps);
+	}
 	k_rad_writeback<<<(unsigned)std::max<long long>(1, std::min<long long>((c->total_px + 255) / 256, (long long)c->sm_count * 8)), 256, 0, st>>>(d_depth, d_colors, c->total_px,
 		c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>());
 	count_launch(4 + kRadRounds);
