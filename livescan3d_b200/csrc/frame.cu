@@ -532,7 +532,7 @@ __device__ __forceinline__ int org_count_dispatch2(int hx, const float *__restri
 #define LS3D_ORG_PACKED 1
 #endif
 #ifndef LS3D_ORG_MINBLOCKS
-#define LS3D_ORG_MINBLOCKS 5
+#define LS3D_ORG_MINBLOCKS 6
 #endif
 __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
 	const float *__restrict__ rays, int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px, unsigned *tile_count, float one)
