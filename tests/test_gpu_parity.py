@@ -641,3 +641,13 @@ def test_refine_poses_schedule(api):
     for i in range(4):
         assert np.allclose(nR[i], gR[i].T.astype(np.float64) @ R0[i], atol=1e-6) and np.allclose(nt[i], t0[i] + gT[i] @ R0[i], atol=1e-6)
         assert np.array_equal(cR[i], nR[i]) and np.allclose(ct[i], t0[i] + gT[i], atol=1e-7)
+
+
+def test_graft_entry_smoke(api):
+    """The driver's smoke() itself (it once fed ICP an empty cloud because its filter settings removed every point at 160x120)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import __graft_entry__ as g
+    g.smoke()
