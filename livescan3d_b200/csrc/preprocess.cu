@@ -40,7 +40,10 @@ struct PreSensor {
 };
 
 enum : unsigned char { kRadDone = 1, kRadHole = 2 };
-constexpr int kRadRounds = 1;            // grid-wide rounds before the wavefront
+#ifndef LS3D_RAD_ROUNDS
+#define LS3D_RAD_ROUNDS 1
+#endif
+constexpr int kRadRounds = LS3D_RAD_ROUNDS;   // grid-wide rounds before the chain kernel
 constexpr int kRadChainThreads = 1024;
 
 // loads that must observe other threads' stores: device scope for the grid-wide round (other SMs write), block scope for the
