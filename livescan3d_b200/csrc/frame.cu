@@ -1138,6 +1138,13 @@ struct Ls3dFrame {
 	unsigned long long params_version = 0;   // bumped whenever frame_set_params changes anything on the device
 	cudaStream_t st_colors = nullptr, st_out = nullptr;     // host path: upload stream, read-back stream
 	bool want_triangles = false;   // run the triangle stage after K1 (unfiltered runs only)
+	int *tri_override = nullptr;   // host mesh path: where this run's triangles go (a per-chunk region of `tri`)
+	DevBuf acc;                    // host mesh path: running totals + per-chunk records (k_mesh_chunk_done)
+	int *pin_acc = nullptr;
+	cudaGraphExec_t hm_exec = nullptr;   // host mesh path: the captured schedule, valid for hm_key
+	HostGraphKey hm_key = {};
+	const void *hm_tri_out = nullptr;
+	int hm_launches = 0;
 	// optional per-stage timing (bench.py's roofline pass): a (begin, end) event pair per stage on the run's stream
 	bool timing = false;
 	cudaEvent_t ev[kTsN][2] = {};
@@ -1174,6 +1181,9 @@ static void frame_free(Ls3dFrame *f) {
 	if (f->st_merge) cudaStreamDestroy(f->st_merge);
 	for (cudaEvent_t x : f->ev_tr) if (x) cudaEventDestroy(x);
 	if (f->hg_exec) cudaGraphExecDestroy(f->hg_exec);
+	if (f->hm_exec) cudaGraphExecDestroy(f->hm_exec);
+	if (f->pin_acc) cudaFreeHost(f->pin_acc);
+	f->acc.release();
 	delete f;
 }
 
@@ -1427,6 +1437,44 @@ __global__ void __launch_bounds__(256) k_copy_out(const uint4 *__restrict__ src,
 	for (unsigned i = blockIdx.x * 256 + tid; i < n; i += gridDim.x * 256) dst[begin + i] = src[begin + i];
 }
 
+// Host mesh path (unfiltered frame + triangles, sensors processed in chunks): after a chunk's K1 + triangle kernels, record where its
+// vertices and triangles go in the concatenated result and advance the running totals the next chunk's K1 reads as its output offset.
+//   acc[0] vertices so far, acc[1] triangles so far, acc[2] error flags; acc[4 + 4c ..] = {first vertex, vertices, first triangle,
+//   triangles} of chunk c; acc[4 + 4 * kMaxMeshChunks + s] = vertices of sensor s
+constexpr int kMaxMeshChunks = 16;
+__global__ void k_mesh_chunk_done(const FrameCtl *ctl, const int *culled_starts, int s_first, int s_end, int chunk, int *acc) {
+	for (int s = s_first + (int)threadIdx.x; s < s_end; s += (int)blockDim.x) acc[4 + 4 * kMaxMeshChunks + s] = culled_starts[s + 1] - culled_starts[s];
+	if (threadIdx.x == 0) {
+		const int nv = ctl->n_final, nt = ctl->n_triangles;
+		int *rec = acc + 4 + 4 * chunk;
+		rec[0] = acc[0]; rec[1] = nv; rec[2] = acc[1]; rec[3] = nt;
+		acc[0] += nv; acc[1] += nt; acc[2] |= ctl->err;
+	}
+}
+// ... and store the chunk into the page-locked Mesh blocks: its records as they are, its (chunk-relative) triangle indices rebased
+// by the chunk's first vertex — formMesh's index offset (depthprocessing.cpp:1611-1626) applied on the way out.
+__global__ void __launch_bounds__(256) k_copy_mesh_out(const uint4 *__restrict__ verts, uint4 *__restrict__ v_host, const int *__restrict__ tris, int *__restrict__ t_host,
+	const int *__restrict__ rec)
+{
+	const int v0 = rec[0], nv = rec[1], t0 = rec[2], nt = rec[3];
+	for (int i = blockIdx.x * 256 + threadIdx.x; i < nv; i += gridDim.x * 256) v_host[v0 + i] = verts[v0 + i];
+	// indices: whole 16-byte pieces of the destination (the PCIe writes stay 512 bytes per warp), ragged ends one by one
+	const long long lo = 3ll * t0, hi = lo + 3ll * nt;                 // destination range, in ints
+	const long long a4 = (lo + 3) / 4, b4 = hi / 4;                    // aligned int4 pieces fully inside it
+	if (a4 < b4) {
+		for (long long j = a4 + blockIdx.x * 256 + threadIdx.x; j < b4; j += (long long)gridDim.x * 256) {
+			const int *src = tris + (4 * j - lo);
+			reinterpret_cast<int4 *>(t_host)[j] = make_int4(src[0] + v0, src[1] + v0, src[2] + v0, src[3] + v0);
+		}
+		if (blockIdx.x == 0) {
+			for (long long i = lo + threadIdx.x; i < 4 * a4; i += 256) t_host[i] = tris[i - lo] + v0;
+			for (long long i = 4 * b4 + threadIdx.x; i < hi; i += 256) t_host[i] = tris[i - lo] + v0;
+		}
+	} else if (blockIdx.x == 0) {
+		for (long long i = lo + threadIdx.x; i < hi; i += 256) t_host[i] = tris[i - lo] + v0;
+	}
+}
+
 // K1 launcher.  keep_px != nullptr: AND the organized neighbour-count mask into the validity test.
 static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, int s_first, int s_end, uint4 *out, const int *d_off,
 	const uint8_t *keep_px, const PeerDst &peers, cudaStream_t st, int tile_lo = 0, int tile_hi = -1)
@@ -1574,7 +1622,7 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 				if (tri_smem > 200 * 1024) { set_error("triangle stage: image width %d too large for the staged depth rows", mw); return -1; }
 				if (tri_smem > 48 * 1024 && !cuda_ok(cudaFuncSetAttribute(k_triangles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem), "triangle stage shared memory")) return -1;
 				k_triangles<<<std::max(1, std::min(ntiles, f->sm_count * 8)), kScanThreads, tri_smem, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->tile_sensor.as<unsigned short>(),
-					f->d2v.as<int>(), s_first, s_end, f->ctl, f->status_b, f->tri_starts, f->tri.as<int>());
+					f->d2v.as<int>(), s_first, s_end, f->ctl, f->status_b, f->tri_starts, f->tri_override ? f->tri_override : f->tri.as<int>());
 				stage_end(f, kTsTriangles, st);
 				count_launch(1);
 				if (!cuda_ok(cudaGetLastError(), "k_triangles")) return -1;
@@ -1858,6 +1906,106 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 			return hc->n_final;
 		}
 		if (v) host_block_free(v);
+	}
+	if (env_mode != 0 && f->want_triangles && !f->filter_on) {
+		// The unfiltered mesh (what the live view asks for every frame) through the same kind of schedule: sensors in chunks; a chunk is a
+		// complete run of K1 + the triangle kernel on its sensors (vertices placed behind the previous chunks' through the device-side
+		// running total, triangles chunk-relative in the chunk's own region of the scratch buffer); k_mesh_chunk_done records the chunk's
+		// ranges; k_copy_mesh_out stores them into the two page-locked Mesh blocks, rebasing the indices, while the next chunk uploads
+		// and runs.  The 28 MB read-back, which used to start after everything else, overlaps the upload.
+		const int Cn = std::max(1, std::min(std::min(env_chunks, n_run), kMaxMeshChunks));
+		const long long px_run = z.pix_begin - a.pix_begin;
+		const size_t acc_ints = 4 + 4 * (size_t)kMaxMeshChunks + (size_t)f->S + 4;
+		void *v = host_block_alloc((size_t)std::max<long long>(px_run, 1) * sizeof(VertexC4ubV3f));
+		void *t = host_block_alloc((size_t)std::max<long long>(px_run, 1) * 6 * sizeof(int));
+		void *v_dev = nullptr, *t_dev = nullptr;
+		bool ok = v && t && host_block_is_pinned(v) && host_block_is_pinned(t) && cudaHostGetDevicePointer(&v_dev, v, 0) == cudaSuccess && cudaHostGetDevicePointer(&t_dev, t, 0) == cudaSuccess &&
+			v_dev && t_dev && f->tri.reserve(sizeof(int) * 6 * (size_t)f->total_px + 64, "alloc triangles") && f->acc.reserve(sizeof(int) * acc_ints, "alloc mesh totals") &&
+			(f->pin_acc || cudaHostAlloc((void **)&f->pin_acc, sizeof(int) * acc_ints, cudaHostAllocDefault) == cudaSuccess);
+		if (ok) {
+			auto locked = [](const void *p) {
+				cudaPointerAttributes pa;
+				if (cudaPointerGetAttributes(&pa, p) != cudaSuccess) { cudaGetLastError(); return false; }
+				return pa.type == cudaMemoryTypeHost;
+			};
+			const bool graph_ok = env_graph != 0 && locked(depth_maps) && locked(depth_colors) && !f->timing;
+			for (int i = 0; i < kEvN && ok; i++)
+				if (!f->ev_up[i]) ok = cuda_ok(cudaEventCreateWithFlags(&f->ev_up[i], cudaEventDisableTiming), "create event");
+			cudaEvent_t *ev_d = f->ev_up, *ev_n = ev_d + 2 * kMaxChunks, *ev_x = ev_d + 5 * kMaxChunks;
+			cudaStream_t so = f->st_out;
+			int *acc = f->acc.as<int>();
+			auto bound = [&](int c) { return first + (int)((long long)n_run * c / Cn); };
+			PeerDst none; none.n = 0;
+			auto enqueue = [&]() -> bool {
+				bool k = cuda_ok(cudaEventRecord(ev_x[0], st), "fork") && cuda_ok(cudaStreamWaitEvent(up, ev_x[0], 0), "fork") && cuda_ok(cudaStreamWaitEvent(so, ev_x[0], 0), "fork") &&
+					cuda_ok(cudaMemsetAsync(acc, 0, sizeof(int) * acc_ints, st), "clear mesh totals");
+				for (int c = 0; c < Cn && k; c++) {
+					const int sa = bound(c), sb = bound(c + 1);
+					const SensorDesc &ca = f->h_sd[sa], &cz = f->h_sd[sb];
+					k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off, depth_maps + ca.depth_off, (size_t)(cz.depth_off - ca.depth_off), cudaMemcpyHostToDevice, up), "upload depth") &&
+						cuda_ok(cudaMemcpyAsync(dc + ca.color_off, depth_colors + ca.color_off, (size_t)(cz.color_off - ca.color_off), cudaMemcpyHostToDevice, up), "upload colours") &&
+						cuda_ok(cudaEventRecord(ev_d[c], up), "record upload") && cuda_ok(cudaStreamWaitEvent(st, ev_d[c], 0), "wait for the upload");
+					if (!k) break;
+					f->tri_override = f->tri.as<int>() + 6 * (ca.pix_begin - a.pix_begin);
+					const int r = frame_run_impl(f, dd, dc, sa, sb - sa, f->final_.as<uint4>(), acc, none, st);
+					f->tri_override = nullptr;
+					if (r < 0) return false;
+					k_mesh_chunk_done<<<1, 64, 0, st>>>(f->ctl, f->culled_starts, sa, sb, c, acc);
+					k = cuda_ok(cudaGetLastError(), "k_mesh_chunk_done") && cuda_ok(cudaEventRecord(ev_n[c], st), "record chunk") && cuda_ok(cudaStreamWaitEvent(so, ev_n[c], 0), "wait for the chunk");
+					if (!k) break;
+					k_copy_mesh_out<<<std::max(1, 2 * env_cblocks), 256, 0, so>>>(f->final_.as<uint4>(), (uint4 *)v_dev, f->tri.as<int>() + 6 * (ca.pix_begin - a.pix_begin), (int *)t_dev, acc + 4 + 4 * c);
+					count_launch(2);
+					k = cuda_ok(cudaGetLastError(), "k_copy_mesh_out");
+				}
+				return k && cuda_ok(cudaEventRecord(ev_x[1], up), "join") && cuda_ok(cudaEventRecord(ev_x[3], so), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[1], 0), "join") &&
+					cuda_ok(cudaStreamWaitEvent(st, ev_x[3], 0), "join") && cuda_ok(cudaMemcpyAsync(f->pin_acc, acc, sizeof(int) * acc_ints, cudaMemcpyDeviceToHost, st), "read mesh totals");
+			};
+			if (ok && graph_ok) {
+				const HostGraphKey key{depth_maps, depth_colors, v, first, n_run, Cn, 2, f->params_version};
+				if (!f->hm_exec || memcmp(&key, &f->hm_key, sizeof(key)) || f->hm_tri_out != t) {
+					cudaGraph_t g = nullptr;
+					const long long l0 = g_launches.load();
+					ok = cuda_ok(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed), "begin capture");
+					if (ok) {
+						const bool k = enqueue();
+						char keep_err[512];
+						snprintf(keep_err, sizeof(keep_err), "%s", ls3d_last_error());
+						const cudaError_t e = cudaStreamEndCapture(st, &g);
+						if (!k) { set_error("%s", keep_err); ok = false; }
+						else ok = cuda_ok(e, "end capture") && g;
+					}
+					f->hm_launches = (int)(g_launches.load() - l0);
+					g_launches.fetch_sub(f->hm_launches);
+					if (ok && f->hm_exec) {
+						cudaGraphExecUpdateResultInfo info;
+						if (cudaGraphExecUpdate(f->hm_exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(f->hm_exec); f->hm_exec = nullptr; }
+					}
+					if (ok && !f->hm_exec) ok = cuda_ok(cudaGraphInstantiate(&f->hm_exec, g, 0), "instantiate the mesh graph");
+					if (g) cudaGraphDestroy(g);
+					if (ok) { f->hm_key = key; f->hm_tri_out = t; } else if (f->hm_exec) { cudaGraphExecDestroy(f->hm_exec); f->hm_exec = nullptr; }
+				}
+				ok = ok && cuda_ok(cudaGraphLaunch(f->hm_exec, st), "launch the mesh graph");
+				if (ok) count_launch(f->hm_launches);
+			} else if (ok) {
+				ok = enqueue();
+			}
+			ok = cuda_ok(cudaStreamSynchronize(st), "mesh pipeline") && ok;
+			const int *ha = f->pin_acc;
+			if (ok && ha[2]) { set_error("device reported error flags 0x%x in the mesh pipeline", ha[2]); ok = false; }
+			if (!ok) { host_block_free(v); host_block_free(t); return -1; }
+			if (per_map_counts) {
+				for (int i = 0; i < n_maps; i++) per_map_counts[i] = 0;
+				for (int i = first; i < first + n_run; i++) per_map_counts[i] = ha[4 + 4 * kMaxMeshChunks + i];
+			}
+			out_mesh->vertices = (VertexC4ubV3f *)v;
+			out_mesh->nVertices = ha[0];
+			free(out_mesh->triangles);
+			out_mesh->triangles = (int *)t;
+			out_mesh->nTriangles = ha[1];
+			return ha[0];
+		}
+		if (v) host_block_free(v);
+		if (t) host_block_free(t);
 	}
 	if (!cuda_ok(cudaMemcpyAsync(dd + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off), cudaMemcpyHostToDevice, st), "upload depth")) return -1;
 	if (!cuda_ok(cudaMemcpyAsync(dc + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off), cudaMemcpyHostToDevice, up), "upload colours") ||

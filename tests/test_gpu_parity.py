@@ -424,6 +424,31 @@ def test_frame_pipeline_host_schedule_variants(api, env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_mesh_page_locked_inputs_graph_path(api):
+    """generateMeshFromDepthMaps with page-locked inputs (chunked schedule replayed as a graph): vertices, triangles and their rebased
+    indices equal the reference's for alternating buffers, other bounds and another rig size in between."""
+    fr_a = small_frame(S=5, w=160, h=120)
+    fr_b = small_frame(S=5, w=160, h=120, seed_base=999)
+    pa, pb = _page_locked(fr_a), _page_locked(fr_b)
+    mesh = lambda fr, bounds: orc.orc_generate_mesh_triangles(fr, bounds)[:2]
+    for bounds in (synth.DEFAULT_BOUNDS, synth.SERVER_BOUNDS):
+        wants = [mesh(fr, bounds) for fr in (fr_a, fr_b)]
+        for rep in range(2):
+            for fr, (wv, wt) in ((pa, wants[0]), (pb, wants[1]), (pa, wants[0]), (fr_a, wants[0])):
+                gv, gt = api.generate_mesh_from_depth_maps(fr, bounds, triangles=True)
+                assert gv.tobytes() == wv.tobytes() and np.array_equal(gt, wt), (rep, len(gv), len(wv))
+    fr_c = synth.make_frame(3, 127, 95, ring=8)
+    wv, wt = mesh(fr_c, synth.SERVER_BOUNDS)
+    gv, gt = api.generate_mesh_from_depth_maps(_page_locked(fr_c), synth.SERVER_BOUNDS, triangles=True)
+    assert gv.tobytes() == wv.tobytes() and np.array_equal(gt, wt)
+    full = synth.make_frame(8)
+    wv, wt = mesh(full, synth.DEFAULT_BOUNDS)
+    pl = _page_locked(full)
+    for _ in range(2):
+        gv, gt = api.generate_mesh_from_depth_maps(pl, synth.DEFAULT_BOUNDS, triangles=True)
+        assert gv.tobytes() == wv.tobytes() and np.array_equal(gt, wt)
+
+
 def test_golden_vectors(api):
     g = np.load(os.path.join(GOLDEN, "hotpath_small.npz"))
     fr = synth.make_frame(int(g["S"]), int(g["w"]), int(g["h"]), seed_base=int(g["seed_base"]), ring=int(g["ring"]))
