@@ -117,6 +117,12 @@ while time.time() < t_end:
 
     # transfer frame of the unfiltered mesh with a random chunk limit
     v, t = api.generate_mesh_from_depth_maps(fr, bounds, triangles=True)
+    wv, wt = orc.orc_generate_mesh_triangles(fr, bounds)[:2]
+    assert v.tobytes() == wv.tobytes() and np.array_equal(t, wt), ("mesh", S, w, h)
+    for _ in range(2):                                         # page-locked inputs: the chunked schedule, second call replays the graph
+        pv, pt = api.generate_mesh_from_depth_maps(frp, bounds, triangles=True)
+        assert pv.tobytes() == wv.tobytes() and np.array_equal(pt, wt), ("mesh page-locked", S, w, h)
+    n_cases["mesh"] = n_cases.get("mesh", 0) + 1
     if len(t):
         limit = int(rng.integers(3, 3000))
         assert lib.ls3d_set_transfer_chunk_limit(limit) == 0

@@ -419,7 +419,7 @@ def test_frame_pipeline_host_schedule_variants(api, env):
     import subprocess
     import sys
     e = dict(os.environ, **env)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", "page_locked_inputs_graph_path and organized or page_locked_full_size"],
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", "page_locked_inputs_graph_path and organized or page_locked_full_size or mesh_page_locked"],
                        env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
