@@ -568,7 +568,7 @@ def run_ours(args, rank, local_rank, world):
             h_depth_w.copy_(h_depth); h_colors_w.copy_(h_colors)
             lib.depthMapAndColorSetRadialCorrection(S, C.c_void_p(h_depth_w.data_ptr()), C.c_void_p(h_colors_w.data_ptr()), p(w_arr), p(h_arr), p(ip))
         widened["e2e"] = {"generateMeshFromDepthMaps_8_sensors_ms": wall(e2e_mesh), "mesh_d2h_bytes": int(16 * mc[0] + 12 * mc[4]),
-                          "depthMapAndColorSetRadialCorrection_8_sensors_ms": wall(e2e_radial), "call": "the reference's exports through the C ABI, pinned host buffers, wall clock (radial: includes re-priming the 8.7 MB input)"}
+                          "depthMapAndColorSetRadialCorrection_8_sensors_ms": wall(e2e_radial), "call": "the reference's exports through the C ABI, pinned host buffers, wall clock (mesh: chunked schedule, read-back overlapped with the upload; radial: includes re-priming the 8.7 MB input)"}
         if world == 1 and not args.no_cpu_baseline:
             orc_w, kind_w = cpu_impl()
             t0 = time.perf_counter(); (orc_w.ref_radial_correction if kind_w == "reference" else orc_w.orc_radial_correction)(frame); t_rad = time.perf_counter() - t0
