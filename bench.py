@@ -537,7 +537,7 @@ def run_ours(args, rank, local_rank, world):
         formats_block = {"ply_body_pack_ms": ply_ms, "ply_alg_bytes": 31 * nv_m + 25 * nt_m, "ply_gbs": (31 * nv_m + 25 * nt_m) / ply_ms / 1e6,
                          "transfer_frame_chunking_ms": xfer_ms, "transfer_chunks": int(chunk_info["chunks"]), "transfer_vertices_emitted": int(nv_out.value),
                          "note": "N4, device-resident input (the mesh above): 16 B records + 12 B index triples -> 15 B PLY vertices + 13 B faces; "
-                                 "formMeshChunks + SendFrame body (the chunk loop has one host wait per chunk)"}
+                                 "formMeshChunks + SendFrame body (device-driven chunk loop, one host wait per 16 chunks)"}
         fpm.close()
         one = d_depth[: 2 * W_PX * H_PX]
         fly_out = torch.empty_like(one)

@@ -459,6 +459,31 @@ __global__ void __launch_bounds__(1024) k_scan_single(const unsigned *__restrict
 	}
 	if (tid == 0) start[n] = s_carry;
 }
+// the same exclusive scan, grid-wide (decoupled look-back over 2048-element tiles, tiles handed out by ticket): the single-block
+// version above needs ~1 us per 1024 elements, i.e. 0.7 ms for the 739 k vertices of an 8-sensor mesh
+__global__ void __launch_bounds__(kScanThreads) k_scan_excl(const unsigned *__restrict__ cnt, unsigned *__restrict__ start, long long n, unsigned long long *status, unsigned *ticket, int *err) {
+	__shared__ unsigned sm[16];
+	__shared__ int s_tile;
+	const int tid = threadIdx.x;
+	const int ntiles = (int)((n + kTile - 1) / kTile);
+	for (;;) {
+		if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+		__syncthreads();
+		const int tile = s_tile;
+		if (tile >= ntiles) break;
+		const long long p0 = (long long)tile * kTile + tid * 8;
+		unsigned v[8], sum = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) { v[j] = p0 + j < n ? cnt[p0 + j] : 0u; sum += v[j]; }
+		unsigned total, base;
+		unsigned run = tile_scan(sum, sm, status, tile, err, &total, &base) + base;
+#pragma unroll
+		for (int j = 0; j < 8; j++)
+			if (p0 + j < n) { start[p0 + j] = run; run += v[j]; }
+		if (tile == ntiles - 1 && tid == 0) start[n] = base + total;
+		__syncthreads();
+	}
+}
 __global__ void __launch_bounds__(256) k_occ_fill(const int *__restrict__ tri, long long m, int n_vertices, const unsigned *__restrict__ start, unsigned *__restrict__ cursor, unsigned *__restrict__ pos) {
 	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < m; i += 256ll * gridDim.x) {
 		const int v = __ldg(tri + i);
@@ -486,6 +511,12 @@ struct ChunkCtl {
 	long long end;          // first triangle-end position (inclusive) at which the chunk holds >= limit vertices, or m-1
 	unsigned total_new;     // new vertices in [s, end]
 	unsigned pad;
+	// device-driven loop (k_chunk_begin / k_chunk_close): the host only looks at these once per batch of chunks
+	long long s;            // start of the chunk being resolved
+	long long emit_s, emit_e;       // the chunk just resolved, for k_chunk_emit
+	long long tri_chunk_start;      // TransferServer.cs:250
+	unsigned vbase, emit_vbase;     // new vertices emitted before this chunk
+	int n_chunks, done, overflow, cap;
 };
 
 // One chunk: positions [s, s + span) in tiles of 2048; flag = prev < s; device-wide inclusive scan (decoupled look-back); the chunk's
@@ -497,6 +528,11 @@ __global__ void __launch_bounds__(kScanThreads) k_chunk_scan(const int *__restri
 	__shared__ unsigned sm[16];
 	__shared__ int s_tile;
 	const int tid = threadIdx.x;
+	if (s < 0) {                       // device-driven loop: the chunk start lives in ctl, span is the window limit
+		if (ctl->done) return;
+		s = ctl->s;
+		span = min(span, m - s);
+	}
 	const int ntiles = (int)((span + kTile - 1) / kTile);
 	for (;;) {
 		if (tid == 0) s_tile = (int)atomicAdd(&ctl->tile_counter, 1u);
@@ -527,8 +563,12 @@ __global__ void __launch_bounds__(kScanThreads) k_chunk_scan(const int *__restri
 
 // Emit one resolved chunk [s, e]: new triangle indices (chunk-local) and the vertex copies in first-occurrence order.
 __global__ void __launch_bounds__(256) k_chunk_emit(const int *__restrict__ tri, const int *__restrict__ prev, long long s, long long e,
-	const unsigned *__restrict__ incl, const uint4 *__restrict__ verts, unsigned vbase, int *__restrict__ new_tri, uint4 *__restrict__ new_verts)
+	const unsigned *__restrict__ incl, const uint4 *__restrict__ verts, unsigned vbase, int *__restrict__ new_tri, uint4 *__restrict__ new_verts, const ChunkCtl *ctl)
 {
+	if (ctl) {                         // device-driven loop: the range k_chunk_close resolved
+		if (ctl->done) return;
+		s = ctl->emit_s; e = ctl->emit_e; vbase = ctl->emit_vbase;
+	}
 	for (long long p = s + blockIdx.x * 256ll + threadIdx.x; p <= e; p += 256ll * gridDim.x) {
 		long long q = p;
 		int pv = __ldg(prev + q);
@@ -538,6 +578,34 @@ __global__ void __launch_bounds__(256) k_chunk_emit(const int *__restrict__ tri,
 		new_tri[p] = (int)local;
 		if (first) new_verts[vbase + local] = verts[__ldg(tri + p)];
 	}
+}
+
+// The chunk loop without the host: k_chunk_begin arms the scan of the chunk that starts at ctl->s (or marks the loop done), k_chunk_close
+// turns the scan's result into the chunk's sizes, the range k_chunk_emit writes, and the next start.  A chunk longer than the scan
+// window raises `overflow` and the host loop below takes over (its window grows on demand).
+__global__ void __launch_bounds__(256) k_chunk_begin(ChunkCtl *ctl, unsigned long long *status, long long m, long long span_max) {
+	if (ctl->done) return;
+	const long long s = ctl->s;
+	if (s >= m) { if (blockIdx.x == 0 && threadIdx.x == 0) ctl->done = 1; return; }
+	const long long tiles = (min(span_max, m - s) + kTile - 1) / kTile;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < tiles; i += 256ll * gridDim.x) status[i] = 0ull;
+	if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->tile_counter = 0; ctl->end = 0x7fffffffffffffffll; }
+}
+__global__ void k_chunk_close(ChunkCtl *ctl, const unsigned *__restrict__ incl, long long m, long long span_max, int *chunk_v, int *chunk_t) {
+	if (ctl->done) return;
+	const long long s = ctl->s, span = min(span_max, m - s);
+	const bool closed = ctl->end != 0x7fffffffffffffffll;
+	if ((!closed && s + span < m) || ctl->n_chunks >= ctl->cap) { ctl->overflow = 1; ctl->done = 1; return; }
+	const long long e = closed ? ctl->end : m - 1;
+	const unsigned n_new = incl[e - s];
+	const int c = ctl->n_chunks;
+	chunk_v[c] = (int)n_new;
+	chunk_t[c] = (int)(((closed ? e : m) - ctl->tri_chunk_start) / 3);       // TransferServer.cs:246-251,256-260 (see the host loop)
+	if (closed) ctl->tri_chunk_start = e;
+	ctl->emit_s = s; ctl->emit_e = e; ctl->emit_vbase = ctl->vbase;
+	ctl->vbase += n_new;
+	ctl->s = e + 1;
+	ctl->n_chunks = c + 1;
 }
 
 extern "C" long long ls3d_transfer_frame_size(int n_vertices, int n_triangles, int n_chunks) {
@@ -561,7 +629,7 @@ static int transfer_chunk_device(const uint4 *d_verts, int n_vertices, const int
 	const long long m = 3ll * n_triangles;
 	// scratch: cnt/cursor[n+1] start[n+1] pos[m] prev[m] incl[m] new_tri[m] new_verts[m] status ctl
 	const size_t nv1 = (size_t)n_vertices + 1;
-	const int max_tiles = (int)((m + kTile - 1) / kTile) + 1;
+	const int max_tiles = (int)((std::max<long long>(m, (long long)nv1) + kTile - 1) / kTile) + 1;
 	size_t off = 0;
 	auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
 	const size_t o_cnt = carve(4 * nv1), o_cur = carve(4 * nv1), o_start = carve(4 * nv1), o_pos = carve(4 * (size_t)m), o_prev = carve(4 * (size_t)m), o_incl = carve(4 * (size_t)m),
@@ -576,7 +644,13 @@ static int transfer_chunk_device(const uint4 *d_verts, int n_vertices, const int
 	const int grid = pack_grid(4 * m);
 	if (!cuda_ok(cudaMemsetAsync(b + o_cnt, 0, o_start - o_cnt, st), "clear counters") || !cuda_ok(cudaMemsetAsync(ctl, 0, sizeof(ChunkCtl), st), "clear control")) return -1;
 	k_occ_count<<<grid, 256, 0, st>>>(d_tri, m, n_vertices, cnt, &ctl->err);
-	k_scan_single<<<1, 1024, 0, st>>>(cnt, start, n_vertices);
+	if (n_vertices <= 8192) {
+		k_scan_single<<<1, 1024, 0, st>>>(cnt, start, n_vertices);
+	} else {
+		const int tiles = (int)(((long long)n_vertices + kTile - 1) / kTile);
+		if (!cuda_ok(cudaMemsetAsync(status, 0, 8 * (size_t)tiles, st), "clear scan status")) return -1;
+		k_scan_excl<<<std::max(1, std::min(tiles, 148 * 8)), kScanThreads, 0, st>>>(cnt, start, n_vertices, status, &ctl->tile_counter, &ctl->err);
+	}
 	k_occ_fill<<<grid, 256, 0, st>>>(d_tri, m, n_vertices, start, cur, pos);
 	k_occ_link<<<pack_grid(16ll * n_vertices), 256, 0, st>>>(n_vertices, start, pos, prev);
 	count_launch(4);
@@ -586,6 +660,51 @@ static int transfer_chunk_device(const uint4 *d_verts, int n_vertices, const int
 	if (h.err) { set_error("triangle index outside 0..%d", n_vertices - 1); return -1; }
 	long long s = 0, tri_chunk_start = 0;
 	unsigned vbase = 0;
+	static const int env_host_loop = getenv("LS3D_CHUNK_HOST_LOOP") ? atoi(getenv("LS3D_CHUNK_HOST_LOOP")) : 0;
+	if (!env_host_loop) {
+		// device-driven: batches of 16 chunks (begin, scan, close, emit each) per host wait; kernels of chunks past the end return at once
+		const long long span_max = 6ll * kChunkLimit + 3;
+		const int cap = (int)std::min<long long>(m / std::max(kChunkLimit, 1) + 2, 1 << 24);
+		static DevBuf sizes;
+		static int *pin = nullptr;
+		static size_t pin_cap = 0;
+		const size_t need = sizeof(ChunkCtl) + 8 * (size_t)cap;
+		if (pin_cap < need) { if (pin) cudaFreeHost(pin); pin = nullptr; pin_cap = 0; if (cudaHostAlloc((void **)&pin, need, cudaHostAllocDefault) == cudaSuccess) pin_cap = need; else cudaGetLastError(); }
+		if (pin && sizes.reserve(8 * (size_t)cap, "alloc chunk sizes")) {
+			int *cv = sizes.as<int>(), *ct = cv + cap;
+			ChunkCtl init; memset(&init, 0, sizeof(init)); init.end = 0x7fffffffffffffffll; init.cap = cap;
+			memcpy(pin, &init, sizeof(init));
+			bool ok = cuda_ok(cudaMemcpyAsync(ctl, pin, sizeof(ChunkCtl), cudaMemcpyHostToDevice, st), "reset control");
+			const int scan_grid = std::max(1, std::min((int)((std::min(span_max, m) + kTile - 1) / kTile), 148 * 8));
+			const ChunkCtl *hc = reinterpret_cast<const ChunkCtl *>(pin);
+			for (int batch = 0; ok; batch++) {
+				for (int i = 0; i < 16; i++) {
+					k_chunk_begin<<<32, 256, 0, st>>>(ctl, status, m, span_max);
+					k_chunk_scan<<<scan_grid, kScanThreads, 0, st>>>(prev, m, -1, span_max, status, ctl, incl, kChunkLimit);
+					k_chunk_close<<<1, 1, 0, st>>>(ctl, incl, m, span_max, cv, ct);
+					k_chunk_emit<<<pack_grid(4 * std::min(span_max, m)), 256, 0, st>>>(d_tri, prev, 0, -1, incl, d_verts, 0u, new_tri, new_verts, ctl);
+				}
+				count_launch(64);
+				ok = cuda_ok(cudaGetLastError(), "chunk loop") && cuda_ok(cudaMemcpyAsync(pin, ctl, sizeof(ChunkCtl), cudaMemcpyDeviceToHost, st), "read control") &&
+					cuda_ok(cudaStreamSynchronize(st), "chunk loop");
+				if (!ok) return -1;
+				if (hc->err) { set_error("device reported error flags 0x%x while chunking", hc->err); return -1; }
+				if (hc->done || hc->s >= m) break;
+			}
+			if (!hc->overflow) {
+				const int nc = hc->n_chunks;
+				if (nc > 0 && (!cuda_ok(cudaMemcpyAsync(pin + sizeof(ChunkCtl) / 4, cv, 4 * (size_t)nc, cudaMemcpyDeviceToHost, st), "read chunk sizes") ||
+					!cuda_ok(cudaMemcpyAsync(pin + sizeof(ChunkCtl) / 4 + cap, ct, 4 * (size_t)nc, cudaMemcpyDeviceToHost, st), "read chunk sizes") ||
+					!cuda_ok(cudaStreamSynchronize(st), "chunk sizes"))) return -1;
+				const int *hv = pin + sizeof(ChunkCtl) / 4, *ht = hv + cap;
+				v_sizes.assign(hv, hv + nc);
+				t_sizes.assign(ht, ht + nc);
+				vbase = hc->vbase;
+				s = m;                       // the host loop below has nothing left to do
+			}
+			// overflow: a chunk did not fit the window — start over with the host loop, whose window grows
+		}
+	}
 	while (s < m) {
 		// a chunk of L vertices spans at least L positions; grow the window until the end is inside it
 		long long span = std::min<long long>(m - s, 6ll * kChunkLimit + 3);
@@ -606,7 +725,7 @@ static int transfer_chunk_device(const uint4 *d_verts, int n_vertices, const int
 		const long long e = closed ? h.end : m - 1;
 		unsigned n_new = 0;
 		if (!cuda_ok(cudaMemcpyAsync(&n_new, incl + (e - s), 4, cudaMemcpyDeviceToHost, st), "read chunk size")) return -1;
-		k_chunk_emit<<<pack_grid(4 * (e - s + 1)), 256, 0, st>>>(d_tri, prev, s, e, incl, d_verts, vbase, new_tri, new_verts);
+		k_chunk_emit<<<pack_grid(4 * (e - s + 1)), 256, 0, st>>>(d_tri, prev, s, e, incl, d_verts, vbase, new_tri, new_verts, nullptr);
 		count_launch(1);
 		if (!cuda_ok(cudaGetLastError(), "k_chunk_emit") || !cuda_ok(cudaStreamSynchronize(st), "chunk emit")) return -1;
 		v_sizes.push_back((int)n_new);
