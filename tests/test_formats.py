@@ -74,6 +74,30 @@ def test_client_frame_blob_without_bodies_and_bad_input():
         formats.client_frame_unpack(garbage)
 
 
+def test_client_frame_blob_random_round_trips():
+    """Property: for any image size, content, body list and compression level, pack -> unpack returns the inputs, both codecs agree on the
+    uncompressed bytes, and each reads the other's blob (40 random cases, no device needed)."""
+    rng = np.random.default_rng(7)
+    for case in range(40):
+        w, h = int(rng.integers(0, 70)), int(rng.integers(0, 50))
+        d = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+        c = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+        bodies = [(bool(rng.integers(0, 2)), [(int(rng.integers(0, 25)), int(rng.integers(0, 3)), *[float(np.float32(x)) for x in rng.normal(size=5)])
+                                              for _ in range(int(rng.integers(0, 26)))]) for _ in range(int(rng.integers(0, 7)))]
+        bb = fo.bodies_bytes(bodies)
+        level = int(rng.choice([0, 1, 2, 9]))
+        ours = formats.client_frame_pack(d, c, bb, level)
+        theirs = fo.orc_client_frame_pack(d, c, bodies, level)
+        if level == 0:
+            assert ours == theirs, case
+        for blob in (ours, theirs):
+            gd, gc, gb, info = formats.client_frame_unpack(blob)
+            od, oc, ob_list, ob = fo.orc_client_frame_unpack(blob)
+            assert np.array_equal(gd, d) and np.array_equal(gc, c) and gb == bb == ob, case
+            assert np.array_equal(od, d) and np.array_equal(oc, c) and len(ob_list) == len(bodies)
+            assert (info.width, info.height, info.n_bodies) == (w, h, len(bodies))
+
+
 def test_client_frames_fill_the_packed_arrays_the_path_takes():
     """KinectServer.CopyLatestFrames (KinectServer.cs:404-500): every sensor's depth / colours land back to back."""
     fr = synth.make_frame(3, 40, 30, ring=8)
