@@ -986,6 +986,8 @@ struct Ls3dIcp {
 	DevBuf src_start, src_cell, src_rank, pk_desc, pk_cost, pk_sched;   // Morton ordering of the source slice (work = the order itself), its packets, their cost and schedule
 	bool order_valid = false;
 	DevBuf own_v1, own_v2;        // device copies for the host-buffer API
+	cudaStream_t up = nullptr;    // host-buffer API: the source cloud uploads here while the target is built
+	cudaEvent_t ev_up = nullptr, ev_go = nullptr;
 	float *pin = nullptr;         // pinned read-back: Rt[12] + status[4]
 	cudaGraphExec_t graph = nullptr;
 	int graph_iters = 0, graph_n1 = 0, graph_n2 = 0, graph_ib = 0, graph_ie = 0;
@@ -1001,6 +1003,9 @@ static void icp_free(Ls3dIcp *c) {
 	for (DevBuf *b : bufs) b->release();
 	if (c->pin) cudaFreeHost(c->pin);
 	if (c->graph) cudaGraphExecDestroy(c->graph);
+	if (c->ev_up) cudaEventDestroy(c->ev_up);
+	if (c->ev_go) cudaEventDestroy(c->ev_go);
+	if (c->up) cudaStreamDestroy(c->up);
 	delete c;
 }
 
@@ -1309,10 +1314,17 @@ extern "C" float ls3d_icp_trace(Point3f *verts1, Point3f *verts2, int nVerts1, i
 	Ls3dIcp *c = cached_icp(nVerts1, nVerts2);
 	if (!c) return ret;
 	if (!c->own_v1.reserve(12 * (size_t)c->n1_max, "alloc target copy") || !c->own_v2.reserve(12 * (size_t)c->n2_max, "alloc source copy")) return ret;
+	// the source goes up on a second stream while the target octree is being built (the build only needs the target)
+	if (!c->up && (!cuda_ok(cudaStreamCreateWithFlags(&c->up, cudaStreamNonBlocking), "create upload stream") ||
+		!cuda_ok(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming), "create event") || !cuda_ok(cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming), "create event"))) return ret;
+	struct UpGuard { cudaStream_t s; ~UpGuard() { cudaStreamSynchronize(s); } } guard{c->up};       // the caller's buffer must not be read after we return
 	bool ok = cuda_ok(cudaMemcpyAsync(c->own_v1.p, verts1, 12 * (size_t)nVerts1, cudaMemcpyHostToDevice, st), "upload target") &&
-		cuda_ok(cudaMemcpyAsync(c->own_v2.p, verts2, 12 * (size_t)nVerts2, cudaMemcpyHostToDevice, st), "upload source");
+		cuda_ok(cudaEventRecord(c->ev_go, st), "order uploads") && cuda_ok(cudaStreamWaitEvent(c->up, c->ev_go, 0), "order uploads") &&      // target first on the wire
+		cuda_ok(cudaMemcpyAsync(c->own_v2.p, verts2, 12 * (size_t)nVerts2, cudaMemcpyHostToDevice, c->up), "upload source") &&
+		cuda_ok(cudaEventRecord(c->ev_up, c->up), "record source upload");
 	if (!ok) return ret;
 	if (ls3d_icp_set_target(c, c->own_v1.p, nVerts1, st) < 0) return ret;
+	if (!cuda_ok(cudaStreamWaitEvent(st, c->ev_up, 0), "wait for the source upload")) return ret;
 	if (ls3d_icp_set_source(c, c->own_v2.p, nVerts2, 0, nVerts2, R, t, st) < 0) return ret;
 	if (ls3d_icp_run(c, maxIter, st) < 0) return ret;
 	ok = cuda_ok(cudaMemcpyAsync(c->pin, c->state.p, sizeof(float) * 12 + sizeof(int) * 4, cudaMemcpyDeviceToHost, st), "read pose") &&
