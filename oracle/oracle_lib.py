@@ -293,6 +293,14 @@ def ref_filter(verts, colors, k: int, max_dist: float):
     return v[:n].copy(), c[:n].copy(), m
 
 
+def ref_filter_flying_pixels(depth_u16, w: int, h: int, k: int = 1, thr: float = 10.0, max_non_fitting: int = 0):
+    """The reference's own KinectCapture::filterFlyingPixels (kinectCapture.cpp:132-174, compiled in place into oracle/_ref)."""
+    r = ref_filter_lib()
+    d = np.array(depth_u16, dtype=np.uint16, order="C").reshape(-1)
+    r.ref_filter_flying_pixels(_p(d), int(w), int(h), int(k), C.c_float(thr), int(max_non_fitting))
+    return d
+
+
 def ref_knn_kdist(v, k: int):
     r = ref_filter_lib()
     v = np.array(v, dtype=np.float32, order="C").reshape(-1, 3)

@@ -463,6 +463,10 @@ def test_golden_vectors(api):
     assert bad == 0 and np.array_equal(gd.view(np.uint32), g["nn_d2"].view(np.uint32))
     _, R, t = api.icp(A, B, max_iter=int(g["icp_iters"]))
     assert rot_err(R, g["icp_R"]) <= R_TOL and np.max(np.abs(t - g["icp_t"])) <= T_TOL
+    # N2: outputs of the reference's own filterFlyingPixels (tests/golden/make_golden_flying.py)
+    f = np.load(os.path.join(GOLDEN, "flying_small.npz"))
+    for i, (k, thr) in enumerate(zip(f["k"], f["thr"])):
+        assert np.array_equal(api.filter_flying_pixels(f["depth"], int(f["w"]), int(f["h"]), int(k), float(thr), 9), f[f"out_{i}"])
 
 
 # ---------------------------------------------------------------------------------------------------------

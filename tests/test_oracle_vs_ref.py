@@ -78,6 +78,25 @@ def test_fixture_poses_and_pixel_maps_vs_reference():
 
 
 @needs_ref
+@pytest.mark.parametrize("k,thr", [(1, 10.0), (2, 25.0), (3, 5.5), (0, 1.0), (1, 0.0), (4, 300.0)])
+def test_flying_pixel_filter_bit_exact_vs_reference(k, thr):
+    """N2: orc_filter_flying_pixels against the reference's own filterFlyingPixels (kinectCapture.cpp:132-174 compiled in
+    place), incl. the transposed shifts (:146), the overwritten maxNonFittingNeighbours (:150), non-square and tiny images."""
+    rng = np.random.default_rng(7)
+    for (w, h, seed) in ((512, 424, 1000), (160, 120, 5), (37, 29, 4), (7, 5, 1), (3, 3, 2), (2, 9, 3), (9, 2, 3)):
+        fr = synth.make_frame(1, w, h, seed_base=seed)
+        cases = [fr["depth_maps"].view(np.uint16).copy(), rng.integers(0, 65536, w * h).astype(np.uint16),
+                 (rng.integers(0, 3, w * h) * 4000).astype(np.uint16)]
+        for d in cases:
+            for mnf in (0, 123):
+                want = orc.ref_filter_flying_pixels(d, w, h, k, thr, mnf)
+                got = orc.orc_filter_flying_pixels(d, w, h, k, thr, mnf)
+                assert np.array_equal(got, want), (w, h, k, thr, mnf)
+        if w == 512 and k == 1 and thr == 10.0:
+            assert (orc.ref_filter_flying_pixels(cases[0], w, h, k, thr) == 0).sum() > (cases[0] == 0).sum()
+
+
+@needs_ref
 @pytest.mark.parametrize("k,md", [(10, 0.01), (10, 0.1), (1, 0.01), (50, 0.05), (3, 0.02)])
 def test_filter_bit_exact_vs_reference(k, md):
     fr = small_frame(S=1, w=160, h=120)
@@ -164,3 +183,13 @@ def test_oracle_vs_golden_vectors():
     assert np.array_equal(oi, g["nn_index"]) and np.array_equal(od.view(np.uint32), g["nn_d2"].view(np.uint32))
     ov, oR, ot, _ = orc.orc_icp(A, B, max_iter=int(g["icp_iters"]))
     assert rot_err(oR, g["icp_R"]) == 0.0 and np.array_equal(ot, g["icp_t"])
+
+
+def test_oracle_vs_golden_flying_pixels():
+    """tests/golden/flying_small.npz: outputs of the reference's own filterFlyingPixels (tests/golden/make_golden_flying.py)."""
+    g = np.load(os.path.join(GOLDEN, "flying_small.npz"))
+    w, h = int(g["w"]), int(g["h"])
+    d = synth.make_frame(1, w, h, seed_base=int(g["seed_base"]))["depth_maps"].view(np.uint16)
+    assert np.array_equal(d, g["depth"]), "synthetic generator drifted from the fixture"
+    for i, (k, thr) in enumerate(zip(g["k"], g["thr"])):
+        assert np.array_equal(orc.orc_filter_flying_pixels(d, w, h, int(k), float(thr), 55), g[f"out_{i}"])
