@@ -60,8 +60,10 @@ void generateVerticesFromDepthMap(unsigned char *depth_maps, unsigned char *dept
  * Result = the reference's (bcolor_transfer, bgenerate_triangles) = (false, false) branch: vertices plus the depth-grid
  * triangles generateTriangles always produces (depthprocessing.cpp:1786, meshGenerator.cpp:76-181), indices rebased per
  * sensor as formMesh does (:1611-1626).  The two flags only add colour correction and the multi-view vertex merge in
- * the reference (:1757-1778); both are outside this path and the flags are ignored (read as their low byte: the C# side
- * marshals 4-byte BOOLs, KinectServer.cs:36-38).  Host schedule as for ls3d_frame_pipeline (chunks of sensors, read-back overlapped with
+ * the reference (:1757-1778); both are outside this path (read as their low byte: the C# side marshals 4-byte BOOLs,
+ * KinectServer.cs:36-38).  When either flag is set the call still succeeds and returns the (false, false) mesh, and
+ * ls3d_last_error() carries a NON-FATAL text starting with "note:" that says so (the server's default is
+ * bGenerateTriangles = true, KinectSettings.cs:50).  Host schedule as for ls3d_frame_pipeline (chunks of sensors, read-back overlapped with
  * the upload, one CUDA graph when the inputs are page-locked); Mesh.vertices / Mesh.triangles are page-locked blocks sized for the worst case. */
 void generateMeshFromDepthMaps(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
 	float *intr_params, float *wtransform_params, Mesh *out_mesh, int bcolor_transfer,

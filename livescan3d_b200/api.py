@@ -37,6 +37,10 @@ def _take_mesh(lib, mesh: Mesh, what: str, triangles: bool = False):
     """Copy Mesh.vertices (and Mesh.triangles) out — what the C# side does with Marshal.Copy, KinectServer.cs:342-352,
     376-389 — then deleteMesh."""
     err = native.last_error()
+    if err.startswith("note:"):                               # non-fatal: e.g. flags whose extras are outside this path
+        import warnings
+        warnings.warn(f"{what}: {err}")
+        err = ""
     try:
         n = mesh.nVertices
         if n > 0 and not mesh.vertices:

@@ -1102,6 +1102,7 @@ struct Ls3dFrame {
 	std::vector<SensorDesc> h_sd;       // S+1 entries (sentinel last)
 	SensorDesc *pin_sd = nullptr;       // pinned staging for the descriptor upload
 	float *pin_rays = nullptr;          // pinned staging for the ray tables
+	cudaEvent_t ev_staged = nullptr;    // recorded after every upload out of pin_sd / pin_rays: waited for before they are rewritten
 	size_t n_rays = 0;
 	float bounds[6] = {0, 0, 0, 0, 0, 0};
 	int filter_k = 0;
@@ -1171,6 +1172,7 @@ static void frame_free(Ls3dFrame *f) {
 	for (DevBuf *b : bufs) b->release();
 	if (f->pin_sd) cudaFreeHost(f->pin_sd);
 	if (f->pin_rays) cudaFreeHost(f->pin_rays);
+	if (f->ev_staged) cudaEventDestroy(f->ev_staged);
 	if (f->pin_out) cudaFreeHost(f->pin_out);
 	for (auto &e : f->ev) for (cudaEvent_t x : e) if (x) cudaEventDestroy(x);
 	if (f->ev_colors) cudaEventDestroy(f->ev_colors);
@@ -1255,6 +1257,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		f->box.reserve(sizeof(FilterBox), "alloc bbox");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_sd, sizeof(SensorDesc) * (n_maps + 1), cudaHostAllocDefault), "alloc pinned descriptors");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_rays, sizeof(float) * (f->n_rays + 4), cudaHostAllocDefault), "alloc pinned ray tables");
+	ok = ok && cuda_ok(cudaEventCreateWithFlags(&f->ev_staged, cudaEventDisableTiming), "create staging event");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_out, sizeof(int) * (size_t)(16 + 3 * (n_maps + 1)), cudaHostAllocDefault), "alloc pinned read-back");
 	ok = ok && cuda_ok(cudaMemcpy(f->tile_sensor.p, tile_sensor.data(), sizeof(unsigned short) * tile_sensor.size(), cudaMemcpyHostToDevice), "upload tile table");
 	if (!ok) { frame_free(f); return nullptr; }
@@ -1342,6 +1345,9 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 		f->params_set = false;
 		f->params_version++;
 	}
+	// the previous parameter set may still be on its way out of the pinned staging blocks (set_params(A); run; set_params(B) on
+	// a busy stream): wait for that copy before the host rewrites them
+	if (!cuda_ok(cudaEventSynchronize(f->ev_staged), "wait for the previous parameter upload")) return -1;
 	f->bounds[0] = minX; f->bounds[1] = minY; f->bounds[2] = minZ; f->bounds[3] = maxX; f->bounds[4] = maxY; f->bounds[5] = maxZ;
 	f->filter_on = filter_k > 0 && filter_maxDist > 0;        // filter.cpp:38-41
 	f->filter_k = filter_k;
@@ -1391,6 +1397,7 @@ static int frame_set_params(Ls3dFrame *f, int n_set, const float *intr_params, c
 	memcpy(f->pin_sd, f->h_sd.data(), sizeof(SensorDesc) * (f->S + 1));
 	if (!cuda_ok(cudaMemcpyAsync(f->sd.p, f->pin_sd, sizeof(SensorDesc) * (f->S + 1), cudaMemcpyHostToDevice, (cudaStream_t)stream), "upload descriptors")) return -1;
 	if (!cuda_ok(cudaMemcpyAsync(f->rays.p, f->pin_rays, sizeof(float) * f->n_rays, cudaMemcpyHostToDevice, (cudaStream_t)stream), "upload ray tables")) return -1;
+	if (!cuda_ok(cudaEventRecord(f->ev_staged, (cudaStream_t)stream), "record parameter upload")) return -1;
 	f->params_set = true;
 	return 0;
 }
@@ -2089,8 +2096,14 @@ extern "C" void generateMeshFromDepthMaps(int n_maps, unsigned char *depth_maps,
 	// The reference runs generateTriangles unconditionally (depthprocessing.cpp:1786); its two flags only add the colour
 	// correction and the multi-view vertex merge (:1757-1778), both outside this path, so they are read and ignored here:
 	// the result is the reference's (false, false) branch — vertices in sensor order plus their depth-grid triangles.
-	(void)bcolor_transfer; (void)bgenerate_triangles;
-	host_frame(n_maps, depth_maps, depth_colors, widths, heights, intr_params, wtransform_params, out_mesh, b, 0, n_maps, 0, 0.0f, nullptr, true);
+	const int r = host_frame(n_maps, depth_maps, depth_colors, widths, heights, intr_params, wtransform_params, out_mesh, b, 0, n_maps, 0, 0.0f, nullptr, true);
+	// Only the low byte of each flag is meaningful: C# marshals a 4-byte BOOL into a C++ bool parameter (KinectServer.cs:36-38
+	// vs depthprocessing.h:108-110).  The call itself succeeded; say which branch the caller got (non-fatal, prefix "note:").
+	const bool ct = (bcolor_transfer & 0xff) != 0, gt = (bgenerate_triangles & 0xff) != 0;
+	if (r >= 0 && (ct || gt) && !ls3d_last_error()[0])
+		set_error("note: generateMeshFromDepthMaps returned the reference's (bcolor_transfer=false, bgenerate_triangles=false) branch; %s%s%s "
+			"(depthprocessing.cpp:1757-1778) %s outside this library's path and %s not applied", ct ? "colour transfer" : "",
+			ct && gt ? " and " : "", gt ? "the multi-view vertex merge (generateVerticesConfidence + mergeVerticesForViews)" : "", ct && gt ? "are" : "is", ct && gt ? "were" : "was");
 }
 
 extern "C" int ls3d_frame_pipeline(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights,
@@ -2139,6 +2152,7 @@ extern "C" int ls3d_filter(Point3f *verts, RGB *colors, int n, int k, float maxD
 	f->params_set = true;
 	FilterBox hb;
 	for (int a = 0; a < 3; a++) { hb.mn[a] = 0xffffffffu; hb.mx[a] = 0u; }
+	if (!cuda_ok(cudaEventSynchronize(f->ev_staged), "wait for the previous descriptor upload")) return -1;
 	memcpy(f->pin_sd, f->h_sd.data(), sizeof(SensorDesc) * 2);
 	bool ok = cuda_ok(cudaMemcpyAsync(g_fv.p, verts, 12 * (size_t)n, cudaMemcpyHostToDevice, st), "upload verts") &&
 		cuda_ok(cudaMemcpyAsync(g_fc.p, colors, 4 * (size_t)n, cudaMemcpyHostToDevice, st), "upload colours") &&

@@ -453,6 +453,10 @@ struct PreCtx {
 	long long total_px = 0;
 	DevBuf sd, winner, fdepth, fcolors, state, items, count, in_depth, in_colors, tmp;
 	PreSensor *pin_sd = nullptr;
+	cudaEvent_t ev_staged = nullptr;     // recorded after the descriptor upload out of pin_sd; waited for before pin_sd is rewritten
+	cudaEvent_t ev_done = nullptr;       // end of the previous correction: the scratch below is shared by every caller / stream
+	unsigned char *pin_out = nullptr;    // host export: results land here first, the caller's arrays are written after the final sync
+	size_t pin_out_cap = 0;
 	int *pin_err = nullptr;
 	int sm_count = 148;
 };
@@ -465,6 +469,9 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 		DevBuf *bufs[] = {&g_pre->sd, &g_pre->winner, &g_pre->fdepth, &g_pre->fcolors, &g_pre->state, &g_pre->items, &g_pre->count, &g_pre->in_depth, &g_pre->in_colors, &g_pre->tmp};
 		for (DevBuf *b : bufs) b->release();
 		if (g_pre->pin_sd) cudaFreeHost(g_pre->pin_sd);
+		if (g_pre->pin_out) cudaFreeHost(g_pre->pin_out);
+		if (g_pre->ev_staged) cudaEventDestroy(g_pre->ev_staged);
+		if (g_pre->ev_done) cudaEventDestroy(g_pre->ev_done);
 		if (g_pre->pin_err) cudaFreeHost(g_pre->pin_err);
 		delete g_pre;
 		g_pre = nullptr;
@@ -488,6 +495,8 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 		c->count.reserve(4 * (size_t)n_maps + 4, "alloc worklist counts");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin_sd, sizeof(PreSensor) * n_maps, cudaHostAllocDefault), "alloc pinned descriptors");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin_err, 64, cudaHostAllocDefault), "alloc pinned status");
+	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming), "create staging event") &&
+		cuda_ok(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming), "create completion event");
 	if (!ok) { delete c; return nullptr; }
 	g_pre = c;
 	return c;
@@ -497,6 +506,10 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, const float *intr_params, cudaStream_t st) {
 	long long acc = 0;
 	int max_px = 1;
+	// the previous call's descriptor upload must have left the pinned block before it is rewritten, and — the scratch buffers are
+	// one set per process — a correction enqueued on ANOTHER stream must not start before the previous one has finished
+	if (!cuda_ok(cudaEventSynchronize(c->ev_staged), "wait for the previous descriptor upload") ||
+		!cuda_ok(cudaStreamWaitEvent(st, c->ev_done, 0), "order after the previous correction")) return -1;
 	for (int i = 0; i < n_maps; i++) {
 		PreSensor &s = c->pin_sd[i];
 		memset(&s, 0, sizeof(s));
@@ -507,6 +520,7 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 		max_px = std::max(max_px, s.w * s.h);
 	}
 	bool ok = cuda_ok(cudaMemcpyAsync(c->sd.p, c->pin_sd, sizeof(PreSensor) * n_maps, cudaMemcpyHostToDevice, st), "upload descriptors") &&
+		cuda_ok(cudaEventRecord(c->ev_staged, st), "record descriptor upload") &&
 		cuda_ok(cudaMemsetAsync(c->winner.p, 0, 4 * (size_t)c->total_px, st), "clear winners") &&
 		cuda_ok(cudaMemsetAsync(c->count.p, 0, 4 * (size_t)n_maps + 4, st), "clear worklist counts");
 	if (!ok) return -1;
@@ -536,6 +550,7 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 	k_rad_writeback<<<(unsigned)std::max<long long>(1, std::min<long long>((c->total_px + 255) / 256, (long long)c->sm_count * 8)), 256, 0, st>>>(d_depth, d_colors, c->total_px,
 		c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>());
 	count_launch(4 + kRadRounds);
+	if (!cuda_ok(cudaEventRecord(c->ev_done, st), "record end of correction")) return -1;
 	return cuda_ok(cudaGetLastError(), "radial correction kernels") ? 4 + kRadRounds : -1;
 }
 
@@ -570,14 +585,20 @@ extern "C" void depthMapAndColorSetRadialCorrection(int n_maps, unsigned char *d
 		cuda_ok(cudaMemcpyAsync(c->in_colors.p, depth_colors, 3 * n, cudaMemcpyHostToDevice, st), "upload colours");
 	if (!ok || radial_enqueue(c, n_maps, c->in_depth.as<uint8_t>(), c->in_colors.as<uint8_t>(), intr_params, st) < 0) return;
 	// results go to pinned staging first: the caller's arrays are only overwritten once the whole call has succeeded
+	// (ls3d.h: "on failure the buffers are left untouched")
+	if (c->pin_out_cap < 5 * n) {
+		if (c->pin_out) { cudaFreeHost(c->pin_out); c->pin_out = nullptr; c->pin_out_cap = 0; }
+		if (!cuda_ok(cudaHostAlloc((void **)&c->pin_out, 5 * n, cudaHostAllocDefault), "alloc pinned result staging")) return;
+		c->pin_out_cap = 5 * n;
+	}
 	ok = cuda_ok(cudaMemcpyAsync(c->pin_err, c->count.as<int>() + n_maps, sizeof(int), cudaMemcpyDeviceToHost, st), "read status") &&
+		cuda_ok(cudaMemcpyAsync(c->pin_out, c->in_depth.p, 2 * n, cudaMemcpyDeviceToHost, st), "read depth") &&
+		cuda_ok(cudaMemcpyAsync(c->pin_out + 2 * n, c->in_colors.p, 3 * n, cudaMemcpyDeviceToHost, st), "read colours") &&
 		cuda_ok(cudaStreamSynchronize(st), "radial correction");
 	if (!ok) return;
 	if (*c->pin_err) { set_error("radial correction: device status flags 0x%x", *c->pin_err); return; }
-	ok = cuda_ok(cudaMemcpyAsync(depth_maps, c->in_depth.p, 2 * n, cudaMemcpyDeviceToHost, st), "read depth") &&
-		cuda_ok(cudaMemcpyAsync(depth_colors, c->in_colors.p, 3 * n, cudaMemcpyDeviceToHost, st), "read colours") &&
-		cuda_ok(cudaStreamSynchronize(st), "radial correction read-back");
-	(void)ok;
+	memcpy(depth_maps, c->pin_out, 2 * n);
+	memcpy(depth_colors, c->pin_out + 2 * n, 3 * n);
 }
 
 // KinectCapture::filterFlyingPixels (kinectCapture.cpp:132-174) on one host depth image, in place.  maxNonFittingNeighbours is accepted and

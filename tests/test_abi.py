@@ -89,3 +89,15 @@ def test_no_cpu_fallback_without_a_device():
     from livescan3d_b200 import api
     with pytest.raises(native.Ls3dError):
         api.filter(v, c, 2, 0.5)
+
+
+def test_header_compiles_and_links_as_c(tmp_path):
+    """include/ls3d.h is plain C: tests/c/abi_smoke.c is built as C99 with -pedantic -Werror, linked against the in-tree
+    library like any C caller would, and run (Mesh lifetime calls + ls3d_last_error need no device)."""
+    _ensure_built()
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(native.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lls3d_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=120).stdout
+    assert out.startswith("ok")

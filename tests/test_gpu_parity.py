@@ -127,6 +127,35 @@ def test_mesh_triangles_mixed_sizes_and_full_size(api):
         assert len(wt) > 100000
 
 
+def test_mesh_flags_return_the_plain_branch_with_a_note(api):
+    """bcolor_transfer / bgenerate_triangles (server default: bGenerateTriangles = true, KinectSettings.cs:50) add the colour
+    correction and multi-view merge in the reference (depthprocessing.cpp:1757-1778) — outside this path.  The call must still
+    succeed, return exactly the (false, false) mesh, and say so through a non-fatal "note:" in ls3d_last_error()."""
+    from livescan3d_b200 import native
+    fr = small_frame(S=3, w=128, h=96)
+    wv, wt, _, _ = orc.orc_generate_mesh_triangles(fr, synth.DEFAULT_BOUNDS)
+    v0, t0 = api.generate_mesh_from_depth_maps(fr, synth.DEFAULT_BOUNDS, triangles=True)
+    assert native.last_error() == ""
+    assert v0.tobytes() == wv.tobytes() and np.array_equal(t0, wt)
+    for ct, gt, words in ((False, True, ["mergeVerticesForViews"]), (True, False, ["colour transfer"]), (True, True, ["colour transfer", "mergeVerticesForViews"])):
+        with pytest.warns(UserWarning, match="note: generateMeshFromDepthMaps returned"):
+            v, t = api.generate_mesh_from_depth_maps(fr, synth.DEFAULT_BOUNDS, color_transfer=ct, generate_triangles=gt, triangles=True)
+        assert v.tobytes() == wv.tobytes() and np.array_equal(t, wt)
+        note = native.last_error()
+        assert note.startswith("note:") and all(w in note for w in words)
+    # a C# BOOL whose low byte is zero reads as false (only the low byte of the 4-byte argument is the C++ bool)
+    lib = native.load()
+    import ctypes as C
+    from livescan3d_b200.api import _frame_args, _ptr, _take_mesh
+    from livescan3d_b200.native import Mesh
+    d, c, w, h, ip, wtp = _frame_args(fr)
+    mesh = Mesh()
+    lib.generateMeshFromDepthMaps(int(fr["n_maps"]), _ptr(d), _ptr(c), _ptr(w), _ptr(h), _ptr(ip), _ptr(wtp), C.byref(mesh), 0x100,
+                                  *[float(x) for x in synth.DEFAULT_BOUNDS], 0x7f00)
+    assert native.last_error() == ""
+    assert _take_mesh(lib, mesh, "generateMeshFromDepthMaps").tobytes() == wv.tobytes()
+
+
 def test_device_triangles_and_pixel_map(api):
     import torch
     from livescan3d_b200.device import FramePipeline
