@@ -41,17 +41,23 @@ ICP_ITERS = 10                                 # KinectSettings.cs:45
 METRIC = "merged 8-sensor filtered clouds/s"
 ICP_METRIC = "ICP Mpts*iter/s (2x217k cloud)"
 L2_FLUSH_BYTES = 256 << 20
+MIN_REGION_MS = 50.0                           # every timed region: rounds of exactly K steps until it is at least this long
+
+
+TRAFFIC_FILES = ["r02_kernel_traffic.json", "r01_kernel_traffic.json"]
 
 
 def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full capture of the
-    same workload (profiles/r01_kernel_traffic.json, made by profiles/make_kernel_traffic.py from the raw ncu pages named in its "source"); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
-    try:
-        with open(p) as f:
-            return int(json.load(f)["kernels"][kernel]["dram_bytes_per_launch_last"])
-    except Exception:
-        return None
+    """(bytes, source): dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`.  DRAM counters cannot be read inside
+    a timed run, so this is a STORED number: the committed `ncu --set full` capture of the same workload (profiles/*_kernel_traffic.json,
+    made by profiles/make_kernel_traffic.py from the raw ncu pages named in its "source").  (None, reason) if the kernel is not in any."""
+    for name in TRAFFIC_FILES:
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return int(json.load(f)["kernels"][kernel]["dram_bytes_per_launch_last"]), f"stored ncu capture profiles/{name} (same workload, not measured in this run)"
+        except Exception:
+            continue
+    return None, "no stored ncu capture names this kernel"
 
 
 def peaks():
@@ -142,6 +148,28 @@ def icp_clouds(pair, gen):
 # ---------------------------------------------------------------------------------------------------------
 # the reference's CPU path (also the cpu_baseline leg)
 # ---------------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """The host cores this process may use (affinity-aware)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_omp_threads(n: int) -> int:
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, which would leave the reference's OpenMP loops
+    (icp.cpp:25, filter.cpp:24) on ONE thread.  Set the team size explicitly on the libgomp instance the reference / oracle
+    libraries link (OMP_NUM_THREADS = nproc) and return what OpenMP will really use."""
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        g = C.CDLL("libgomp.so.1")
+        g.omp_set_dynamic(0)
+        g.omp_set_num_threads(int(n))
+        return int(g.omp_get_max_threads())
+    except OSError:
+        return 1
+
+
 def cpu_impl():
     from oracle import oracle_lib as orc
     orc.oracle()
@@ -183,7 +211,7 @@ def cpu_icp_once(orc, kind, A, B):
 
 def cpu_baseline(frame, A, B, budget_s=12.0):
     orc, kind = cpu_impl()
-    cores = os.cpu_count() or 1
+    cores = set_omp_threads(host_threads())
     t1, _ = cpu_frame_once(orc, kind, frame, 1)                       # also the warm-up
     n_s = int(max(1, min(S, budget_s / max(t1, 1e-3))))
     t, _ = cpu_frame_once(orc, kind, frame, n_s)
@@ -191,7 +219,7 @@ def cpu_baseline(frame, A, B, budget_s=12.0):
     ti = cpu_icp_once(orc, kind, A, B)
     icp_v = len(B) * ICP_ITERS / ti / 1e6
     return ({"value": frame_fps, "unit": "clouds/s", "cores": cores, "kind": kind,
-             "sample": f"{n_s} of {S} sensors of one frame ({t:.2f} s), scaled by {S}/{n_s}; createVertices thread-per-sensor + OpenMP filter"},
+             "sample": f"{n_s} of {S} sensors of one frame ({t:.2f} s), scaled by {S}/{n_s}; createVertices thread-per-sensor + OpenMP filter on {cores} OpenMP threads"},
             {"value": icp_v, "unit": "Mpts*iter/s", "cores": cores, "kind": kind,
              "sample": f"one full ICP() call, {ICP_ITERS} iterations, n1={len(A)} n2={len(B)} ({ti:.2f} s)"})
 
@@ -201,7 +229,7 @@ def run_reference(args, rank, world):
         return
     orc, kind = cpu_impl()
     frame, pair = make_inputs(0)
-    cores = os.cpu_count() or 1
+    cores = set_omp_threads(host_threads())            # not os.cpu_count(): what OpenMP really uses (torchrun exports OMP_NUM_THREADS=1)
     t1, _ = cpu_frame_once(orc, kind, frame, 1)
     total = args.steps + args.warmup
     n_s = int(max(1, min(S, 150.0 / max(total * t1, 1e-3))))          # bounded sample: the whole run ends within minutes
@@ -215,7 +243,8 @@ def run_reference(args, rank, world):
     A, B = icp_clouds(pair, gen)
     ti = min(cpu_icp_once(orc, kind, A, B) for _ in range(2))
     icp_v = len(B) * ICP_ITERS / ti / 1e6
-    sample = f"{n_s} of {S} sensors per step, scaled by {S}/{n_s}; {cores} host threads (std::thread per sensor + OpenMP filter)"
+    sample = (f"{n_s} of {S} sensors per step, scaled by {S}/{n_s}; {cores} OpenMP threads (omp_get_max_threads) + one std::thread per sensor; "
+              f"one host runs one rig at a time, so the value does not grow with --gpus")
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": frame_config(),
@@ -303,21 +332,62 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    lib.ls3d_reset_launch_count()
-    w0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()
-        ev_s[i].record()
-        frame_step()
-        ev_e[i].record()
-    barrier()
-    windows.append((w0, time.perf_counter()))
-    launches = int(lib.ls3d_launch_count())
-    frame_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e)))
+
+    def agree_rounds(est_ms_per_step: float) -> int:
+        """How many rounds of exactly K steps make the timed region at least MIN_REGION_MS long (same number on every rank)."""
+        r = int(np.ceil(MIN_REGION_MS / max(args.steps * est_ms_per_step, 1e-3)))
+        return int(max_over_ranks(float(min(max(r, 1), 500))))
+
+    def device_rounds(step, prep=None, est_ms_per_step=0.1):
+        """Rounds of EXACTLY K steps, each step bracketed by CUDA events on the launching stream (L2 flush and `prep` between
+        steps are outside the event pairs).  -> (ms per step = median over rounds of the K-step sum / K, max over ranks;
+        launches of OUR kernels in one round; number of rounds; wall window)."""
+        R = agree_rounds(est_ms_per_step)
+        sums, launches_round = [], 0
+        barrier()
+        w0 = time.perf_counter()
+        for r in range(R):
+            if r == 0:
+                lib.ls3d_reset_launch_count()
+            for i in range(args.steps):
+                if prep:
+                    prep()
+                flush.zero_()
+                ev_s[i].record()
+                step()
+                ev_e[i].record()
+            torch.cuda.synchronize()
+            if r == 0:
+                launches_round = int(lib.ls3d_launch_count())
+            sums.append(sum(a.elapsed_time(b) for a, b in zip(ev_s, ev_e)))
+        barrier()
+        w1 = time.perf_counter()
+        return max_over_ranks(float(np.median(sums))) / args.steps, launches_round, R, (w0, w1), float(np.sum(sums))
+
+    def wall_rounds(call, prep=None, est_ms_per_step=0.3):
+        """The same for a host-side call (wall clock around K calls per round; `prep` outside the clock)."""
+        R = agree_rounds(est_ms_per_step)
+        sums = []
+        barrier()
+        for r in range(R):
+            tt = 0.0
+            for i in range(args.steps):
+                if prep:
+                    prep()
+                t0 = time.perf_counter()
+                call()
+                tt += time.perf_counter() - t0
+            sums.append(tt)
+        barrier()
+        return max_over_ranks(float(np.median(sums))) / args.steps, R
+
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(); frame_step(); a1.record(); torch.cuda.synchronize()
+    ms_per_step, launches, frame_rounds, win, frame_region_ms = device_rounds(frame_step, est_ms_per_step=a0.elapsed_time(a1))
+    windows.append(win)
     counts = fp.counts.cpu().numpy()
     assert counts[2] == 0, f"device error flags {counts[2]}"
     n_final = int(counts[0])
-    ms_per_step = frame_ms / args.steps
     value = world * 1000.0 / ms_per_step
     total_launches = int(sum_over_ranks(float(launches)))
 
@@ -361,7 +431,7 @@ def run_ours(args, rank, local_rank, world):
     whole_alg = 5 * px + 16 * n_final
     ncu_name = {"organized_neighbour_count": "k_organized_count", "map_cull_compact": "k_map_cull_compact<0, 1>", "voxel_neighbour_count": "k_neighbour_count"}
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak,
-                "traffic": ncu_traffic(ncu_name.get(dom["kernel"], dom["kernel"])), "peak_source": peak_src,
+                "traffic": ncu_traffic(ncu_name.get(dom["kernel"], dom["kernel"]))[0], "traffic_source": ncu_traffic(ncu_name.get(dom["kernel"], dom["kernel"]))[1], "peak_source": peak_src,
                 "note": "the neighbour count tests ~40 shared-memory candidates per surviving pixel with exact fp32 d2 (two per instruction, FADD2/FMUL2/FFMA2) after staging tile + halo: issue- and staging-latency-bound (ncu v12: 71 % issue slots, 28.1 M warp instructions, 0 % tensor pipe); its HBM traffic is below the algorithmic bytes because it never touches the colours; map_cull_compact is the streaming kernel (see profiles/)",
                 "whole_pipeline": {"alg_bytes": whole_alg, "achieved": whole_alg / ms_per_step / 1e6, "frac": whole_alg / ms_per_step / 1e6 / hbm_peak},
                 "stages": stages}
@@ -386,12 +456,22 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(args.warmup, 3)):
         n_e2e = e2e_frame()
     assert n_e2e == n_final, (n_e2e, n_final, native.last_error())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_frame()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    t0 = time.perf_counter(); e2e_frame(); est = 1000.0 * (time.perf_counter() - t0)
+    e2e_ms, e2e_rounds = wall_rounds(e2e_frame, est_ms_per_step=est)
+    # the real caller's buffers are GC-pinned byte[] (KinectServer.cs:354-374): pageable as far as CUDA is concerned
+    g_depth, g_colors = np.array(frame["depth_maps"], copy=True), np.array(frame["depth_colors"], copy=True)
+
+    def e2e_frame_pageable():
+        mesh = Mesh()
+        n = lib.ls3d_frame_pipeline(S, p(g_depth), p(g_colors), p(w_arr), p(h_arr), p(ip), p(wt), C.byref(mesh), *b, FILTER_K, FILTER_MAXDIST, p(pm))
+        lib.deleteMesh(C.byref(mesh))
+        return n
+
+    for _ in range(max(args.warmup, 3)):
+        n_pg = e2e_frame_pageable()
+    assert n_pg == n_final, (n_pg, n_final, native.last_error())
+    t0 = time.perf_counter(); e2e_frame_pageable(); est = 1000.0 * (time.perf_counter() - t0)
+    e2e_pg_ms, _ = wall_rounds(e2e_frame_pageable, est_ms_per_step=est)
     # bytes that actually cross PCIe per call: the depth images go up by copy engine; with page-locked inputs the colours are not
     # uploaded — the merge kernel reads the 24-byte colour group of every 8-pixel run holding a survivor out of the caller's
     # buffer (32-byte sectors) — and the records are stored into the page-locked Mesh block by a copy kernel
@@ -399,8 +479,11 @@ def run_ours(args, rank, local_rank, world):
     grp = np.flatnonzero(keep.reshape(-1, 8).any(axis=1)).astype(np.int64)
     sectors = np.unique(np.concatenate([(24 * grp) // 32, (24 * grp + 23) // 32]))
     pulled = int(32 * len(sectors))
-    e2e = {"value": world * args.steps / t_e2e, "unit": "clouds/s", "h2d_bytes_per_step": int(frame["depth_maps"].nbytes + pulled),
-           "d2h_bytes_per_step": int(16 * n_final + 32 + 4 * (S + 1)), "ms_per_step": 1000.0 * t_e2e / args.steps,
+    e2e = {"value": world * 1000.0 / e2e_ms, "unit": "clouds/s", "h2d_bytes_per_step": int(frame["depth_maps"].nbytes + pulled),
+           "d2h_bytes_per_step": int(16 * n_final + 32 + 4 * (S + 1)), "ms_per_step": e2e_ms, "rounds": e2e_rounds,
+           "pageable": {"value": world * 1000.0 / e2e_pg_ms, "unit": "clouds/s", "ms_per_step": e2e_pg_ms,
+                        "h2d_bytes_per_step": int(frame["depth_maps"].nbytes + frame["depth_colors"].nbytes), "d2h_bytes_per_step": int(16 * n_final + 32 + 4 * (S + 1)),
+                        "call": "the same ls3d_frame_pipeline call with plain (pageable) numpy buffers, as a P/Invoke caller's GC-pinned byte[] would be"},
            "h2d_detail": {"depth_copied": int(frame["depth_maps"].nbytes), "colour_sectors_read_by_the_merge_kernel": pulled,
                           "colour_bytes_in_the_caller_buffer": int(frame["depth_colors"].nbytes),
                           "parameters": "19 floats per sensor, uploaded only when they change (cached across calls)"},
@@ -427,18 +510,10 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     R_dev, t_dev, st = solver.pose()
     assert st[0] == ICP_ITERS and st[1] == 0, st
-    lib.ls3d_reset_launch_count()
-    w0 = time.perf_counter()
-    for i in range(args.steps):
-        dB.copy_(dB0)
-        flush.zero_()
-        ev_s[i].record()
-        icp_step()
-        ev_e[i].record()
-    barrier()
-    windows.append((w0, time.perf_counter()))
-    icp_launches = int(sum_over_ranks(float(lib.ls3d_launch_count())))
-    icp_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / args.steps
+    a0.record(); icp_step(); a1.record(); torch.cuda.synchronize()
+    icp_ms, icp_launches, icp_rounds, win, icp_region_ms = device_rounds(icp_step, prep=lambda: dB.copy_(dB0), est_ms_per_step=a0.elapsed_time(a1))
+    windows.append(win)
+    icp_launches = int(sum_over_ranks(float(icp_launches)))
     icp_value = world * n2 * ICP_ITERS / (icp_ms / 1000.0) / 1e6
 
     # staged pass with events between the three kernels of an iteration (what the captured graph replays)
@@ -464,7 +539,7 @@ def run_ours(args, rank, local_rank, world):
     acc /= reps
     icp_alg = 64 * n2                                                   # 64 B per source point per iteration
     match_gbs = icp_alg / max(acc[1], 1e-9) / 1e6
-    icp_roofline = {"bound": "hbm", "kernel": "k_icp_match_packet", "achieved": match_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": match_gbs / hbm_peak, "traffic": ncu_traffic("k_icp_match_packet"),
+    icp_roofline = {"bound": "hbm", "kernel": "k_icp_match_packet", "achieved": match_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": match_gbs / hbm_peak, "traffic": ncu_traffic("k_icp_match_packet")[0], "traffic_source": ncu_traffic("k_icp_match_packet")[1],
                     "peak_source": peak_src, "note": "packet octree NN on L2-resident data: issue- and dependent-latency bound, not HBM (ncu: 57 % issue slots, 27 of 32 lanes, 0 % tensor pipe; see profiles/)",
                     "stages_ms": {"target_grid_build_per_call": float(acc[0]), "match_per_iter": float(acc[1]), "stats_per_iter": float(acc[2]), "sums_per_iter": float(acc[3])},
                     "whole_iteration": {"alg_bytes": icp_alg, "achieved": icp_alg / (icp_ms / ICP_ITERS) / 1e6, "frac": icp_alg / (icp_ms / ICP_ITERS) / 1e6 / hbm_peak}}
@@ -481,20 +556,105 @@ def run_ours(args, rank, local_rank, world):
         t[:] = 0
         return lib.ICP(C.c_void_p(hA.data_ptr()), C.c_void_p(hB.data_ptr()), n1, n2, p(R), p(t), ICP_ITERS)
 
-    tt = 0.0
-    for i in range(max(args.warmup, 3) + args.steps):
+    for _ in range(max(args.warmup, 3)):
         hB.copy_(hB0)
-        if i == max(args.warmup, 3):
-            barrier()
-            tt = 0.0
-        t0 = time.perf_counter()
         e2e_icp()
-        tt += time.perf_counter() - t0
     assert not native.last_error(), native.last_error()
     assert np.array_equal(R.reshape(3, 3), R_dev) and np.array_equal(t, t_dev), "host and device ICP paths disagree"
-    t_icp_e2e = max_over_ranks(tt)
-    icp_e2e = {"value": world * n2 * ICP_ITERS * args.steps / t_icp_e2e / 1e6, "unit": "Mpts*iter/s", "h2d_bytes_per_step": int(12 * (n1 + n2) + 48), "d2h_bytes_per_step": int(12 * n2 + 64),
-               "ms_per_step": 1000.0 * t_icp_e2e / args.steps, "call": "ICP (C ABI, the reference's own export; pinned host clouds, wall clock)"}
+    hB.copy_(hB0); t0 = time.perf_counter(); e2e_icp(); est = 1000.0 * (time.perf_counter() - t0)
+    icp_e2e_ms, icp_e2e_rounds = wall_rounds(e2e_icp, prep=lambda: hB.copy_(hB0), est_ms_per_step=est)
+    gA, gB = np.array(A, copy=True), np.array(B, copy=True)             # pageable caller buffers (AllocHGlobal blocks, MainWindowForm.cs:364-368)
+
+    def e2e_icp_pageable():
+        R[:] = np.eye(3, dtype=np.float32).reshape(9)
+        t[:] = 0
+        return lib.ICP(p(gA), p(gB), n1, n2, p(R), p(t), ICP_ITERS)
+
+    def reset_gB():
+        gB[:] = B
+    for _ in range(3):
+        reset_gB(); e2e_icp_pageable()
+    assert np.array_equal(R.reshape(3, 3), R_dev) and np.array_equal(t, t_dev), "pageable and device ICP paths disagree"
+    icp_e2e_pg_ms, _ = wall_rounds(e2e_icp_pageable, prep=reset_gB, est_ms_per_step=est)
+    icp_e2e = {"value": world * n2 * ICP_ITERS / (icp_e2e_ms / 1000.0) / 1e6, "unit": "Mpts*iter/s", "h2d_bytes_per_step": int(12 * (n1 + n2) + 48), "d2h_bytes_per_step": int(12 * n2 + 64),
+               "ms_per_step": icp_e2e_ms, "rounds": icp_e2e_rounds, "call": "ICP (C ABI, the reference's own export; pinned host clouds, wall clock)",
+               "pageable": {"value": world * n2 * ICP_ITERS / (icp_e2e_pg_ms / 1000.0) / 1e6, "unit": "Mpts*iter/s", "ms_per_step": icp_e2e_pg_ms,
+                            "call": "the same ICP call with plain (pageable) numpy clouds"}}
+
+    # ------------------------------------------------------------------ BASELINE.json configs[1] and configs[2] (rank 0; device-timed + C ABI)
+    other_configs = None
+    if rank == 0:
+        def ev_timed(fn, prep=None, reps=max(5, min(args.steps, 20))):
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ts = []
+            for it in range(reps + 2):
+                if prep:
+                    prep()
+                flush.zero_()
+                a.record(); fn(); bb.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(a.elapsed_time(bb))
+            return float(np.median(ts))
+
+        def wall_timed(fn, prep=None, reps=30):
+            ts = []
+            for it in range(reps + 3):
+                if prep:
+                    prep()
+                t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
+                if it >= 3:
+                    ts.append(dt)
+            return 1000.0 * float(np.median(ts))
+
+        def rig_block(n_s):
+            fr = synth.make_frame(n_s, W_PX, H_PX, seed_base=1000)
+            hd, hc = torch.from_numpy(fr["depth_maps"]).pin_memory(), torch.from_numpy(fr["depth_colors"]).pin_memory()
+            dd, dc = hd.to(dev), hc.to(dev)
+            f1 = FramePipeline(fr["widths"], fr["heights"])
+            f1.set_params(fr["intr"], fr["wt"], FRAME_BOUNDS, FILTER_K, FILTER_MAXDIST)
+            dev_ms = ev_timed(lambda: f1.run(dd, dc))
+            kept = int(f1.counts.cpu()[0])
+            f1.close()
+            wa, ha = np.ascontiguousarray(fr["widths"], np.int32), np.ascontiguousarray(fr["heights"], np.int32)
+            ipa, wta, pma = np.ascontiguousarray(fr["intr"], np.float32), np.ascontiguousarray(fr["wt"], np.float32), np.zeros(n_s, np.int32)
+
+            def call():
+                mesh = Mesh()
+                n = lib.ls3d_frame_pipeline(n_s, C.c_void_p(hd.data_ptr()), C.c_void_p(hc.data_ptr()), p(wa), p(ha), p(ipa), p(wta), C.byref(mesh), *b, FILTER_K, FILTER_MAXDIST, p(pma))
+                lib.deleteMesh(C.byref(mesh))
+                return n
+            assert call() == kept, native.last_error()
+            return fr, {"sensors": n_s, "merged_points": kept, "device_ms_per_frame": dev_ms, "e2e_ms_per_frame": wall_timed(call),
+                        "frames_per_s_device": 1000.0 / dev_ms}
+        _, c1 = rig_block(1)
+        c1["workload"] = "BASELINE.json configs[1]: one 512x424 sensor -> map, world transform, cull (+-1.5 m), neighbour-count filter (k=10, 0.01)"
+        c1["budget_at_30_fps_ms"] = 1000.0 / 30.0
+        c1["e2e_share_of_the_30_fps_budget"] = c1["e2e_ms_per_frame"] / (1000.0 / 30.0)
+        fr4, c2 = rig_block(4)
+        c2["workload"] = ("BASELINE.json configs[2]: 4-sensor frame (map, filter, merge) + pairwise ICP refinement of neighbouring sensors "
+                          f"(i -> i+1 mod 4, cull +-5 m, known 1.5 deg / (8,-5,6) mm offset, maxIter={ICP_ITERS}) through the reference's ICP export")
+        clouds4 = [np.ascontiguousarray(np.stack([v["X"], v["Y"], v["Z"]], axis=1), dtype=np.float32)
+                   for v in (api.generate_vertices_from_depth_map(fr4, ICP_BOUNDS, i) for i in range(4))]
+        pair_ms, pair_pts = [], 0
+        for i in range(4):
+            tA, sB0 = clouds4[i], synth.perturb(clouds4[(i + 1) % 4])
+            sB = sB0.copy()
+            Rp, tp = np.zeros(9, np.float32), np.zeros(3, np.float32)
+
+            def call_icp():
+                Rp[:] = np.eye(3, dtype=np.float32).reshape(9); tp[:] = 0
+                lib.ICP(p(tA), p(sB), len(tA), len(sB), p(Rp), p(tp), ICP_ITERS)
+
+            def reset_sB():
+                sB[:] = sB0
+            pair_ms.append(wall_timed(call_icp, prep=reset_sB, reps=8))
+            pair_pts += len(sB)
+            assert not native.last_error(), native.last_error()
+        c2["pairwise_icp_e2e_ms"] = [float(x) for x in pair_ms]
+        c2["pairwise_icp_Mpts_iter_per_s_e2e"] = pair_pts * ICP_ITERS / (sum(pair_ms) / 1000.0) / 1e6
+        c2["frame_plus_4_pairwise_icp_e2e_ms"] = c2["e2e_ms_per_frame"] + float(sum(pair_ms))
+        other_configs = {"single_sensor_30fps": c1, "four_sensors_plus_pairwise_icp": c2}
 
     # ------------------------------------------------------------------ widened rows: pre-passes and triangles, HBM-resident
     widened = None
@@ -580,9 +740,10 @@ def run_ours(args, rank, local_rank, world):
             else:
                 orc_w.orc_generate_mesh_triangles(frame, FRAME_BOUNDS)
             t_mesh = time.perf_counter() - t0
-            t0 = time.perf_counter(); orc_w.orc_filter_flying_pixels(frame["depth_maps"].view(np.uint16)[: W_PX * H_PX], W_PX, H_PX, 1, 10.0); t_fly = time.perf_counter() - t0
+            fly_fn = orc_w.ref_filter_flying_pixels if kind_w == "reference" else orc_w.orc_filter_flying_pixels
+            t0 = time.perf_counter(); fly_fn(frame["depth_maps"].view(np.uint16)[: W_PX * H_PX], W_PX, H_PX, 1, 10.0); t_fly = time.perf_counter() - t0
             widened["cpu"] = {"kind": kind_w, "cores": os.cpu_count() or 1, "radial_correction_8_sensors_ms": 1000 * t_rad, "unfiltered_mesh_with_triangles_8_sensors_ms": 1000 * t_mesh,
-                              "flying_pixel_filter_1_sensor_ms": 1000 * t_fly, "flying_kind": "port (kinectCapture.cpp needs the Kinect SDK and cannot be compiled)"}
+                              "flying_pixel_filter_1_sensor_ms": 1000 * t_fly, "flying_kind": kind_w + " (kinectCapture.cpp:132-174 compiled in place behind a 3-member stub)" if kind_w == "reference" else "port"}
 
     # ------------------------------------------------------------------ sharded variants (N > 1): data crosses NVLink
     sharded = None
@@ -590,7 +751,7 @@ def run_ours(args, rank, local_rank, world):
         try:
             from livescan3d_b200 import dist as ldist
             sharded = ldist.bench_sharded(args, rank, world, dev, flush)
-        except Exception as e:                                        # reported, never silently dropped
+        except Exception as e:                                        # reported in the line AND the run exits non-zero (below)
             sharded = {"error": f"{type(e).__name__}: {e}"}
 
     clocks = None
@@ -604,22 +765,37 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_f, cpu_i = cpu_baseline(frame, A, B)
 
+    def ratios(ours_dev, ours_e2e, cpu):
+        """Speed-up against the CPU reference timed in THIS run (N = 1 only; at N > 1 the driver divides by the reference arm's line)."""
+        if not cpu:
+            return None
+        return {"reference_value": cpu["value"], "unit": cpu["unit"], "kind": cpu["kind"], "cores": cpu["cores"],
+                "device_ratio": ours_dev / cpu["value"], "e2e_ratio": ours_e2e / cpu["value"]}
+
     if rank == 0:
         cfg = frame_config()
+        cfg["timing"] = (f"every timed region = rounds of exactly K={args.steps} steps repeated until >= {MIN_REGION_MS:.0f} ms "
+                         f"(frame: {frame_rounds} rounds, {frame_region_ms:.1f} ms of kernel time; ICP: {icp_rounds} rounds, {icp_region_ms:.1f} ms); ms_per_step = median over rounds of the K-step sum / K, max over ranks")
         out = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                "points": {"pixels_per_frame": px, "culled": n_culled, "merged": n_final},
                "voxel_hash_mode_ms_per_step": hash_ms,
                "e2e": e2e, "gpu_launches": total_launches + icp_launches, "gpu_launches_frame": total_launches, "clocks": clocks,
-               "roofline": roofline, "cpu_baseline": cpu_f,
+               "roofline": roofline, "cpu_baseline": cpu_f, "vs_cpu_baseline": ratios(value, e2e["value"], cpu_f),
                "icp": {"metric": ICP_METRIC, "value": icp_value, "unit": "Mpts*iter/s", "ms_per_step": icp_ms, "ms_per_iter": icp_ms / ICP_ITERS,
                        "config": {"workload": f"ICP() of two overlapping {W_PX}x{H_PX} clouds (sensors 0,1 of an 8-ring, cull +-5 m), known 1.5 deg/(8,-5,6) mm offset, maxIter={ICP_ITERS}; "
                                               "target grid build inside the timed call", "n1": n1, "n2": n2, "iters": ICP_ITERS},
-                       "e2e": icp_e2e, "gpu_launches": icp_launches, "roofline": icp_roofline, "cpu_baseline": cpu_i},
-               "widened": widened, "sharded": sharded, "library": api.version()}
-        print(json.dumps(out))
+                       "e2e": icp_e2e, "gpu_launches": icp_launches, "roofline": icp_roofline, "cpu_baseline": cpu_i,
+                       "vs_cpu_baseline": ratios(icp_value, icp_e2e["value"], cpu_i)},
+               "other_configs": other_configs, "widened": widened, "sharded": sharded, "library": api.version()}
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if sharded and "error" in sharded:
+        # multi-GPU parity is part of the run's verdict: a sharded result that differs from the single-GPU one (or a sharded
+        # path that failed) makes the whole bench fail, on every rank
+        print(f"bench.py: sharded block failed on rank {rank}: {sharded['error']}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -633,6 +809,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # The CPU arms must see all host cores.  libgomp reads OMP_NUM_THREADS once, when it is loaded, and torch.distributed.run exports
+    # OMP_NUM_THREADS=1 to its ranks: restart this process image with the variable corrected before anything has loaded OpenMP
+    # (omp_set_num_threads alone was measured not to restore the filter's team size).
+    uses_cpu_arm = (args.impl == "reference" and rank == 0) or (args.impl == "ours" and world == 1 and args.gpus == 1 and not args.no_cpu_baseline)
+    if uses_cpu_arm and os.environ.get("OMP_NUM_THREADS") != str(host_threads()):
+        os.environ["OMP_NUM_THREADS"] = str(host_threads())
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -299,6 +299,8 @@ def bench_sharded(args, rank, world, dev, flush):
                                        "per_rank_counts": [int(c) for c in counts], "bit_identical_to_single_gpu_on_every_rank": bool(ok_all.item()),
                                        "exchange": "all-gather of world ints (NCCL) + peer stores of 16*n_kept bytes to every rank (NVLink, CUDA IPC)"}
     sf.close()
+    if not bool(ok_all.item()):
+        raise RuntimeError("sharded frame: the merged cloud differs from the single-GPU result on at least one rank")
 
     # ---- ICP: single-GPU truth, then partitioned source
     A, B = bench.icp_clouds(pair, api.generate_vertices_from_depth_map)
@@ -332,4 +334,9 @@ def bench_sharded(args, rank, world, dev, flush):
             "status": [int(x) for x in st],
             "collectives_per_iter": "all-reduce MIN int64[n1]" + ("" if mode == "replicated" else " + all-reduce SUM f64[4] + all-reduce SUM f64[16]")}
         si.close()
+        dR_s, dt_s = out[f"icp_source_partitioned_{mode}"]["max_abs_dR_vs_single_gpu"], out[f"icp_source_partitioned_{mode}"]["max_abs_dt_vs_single_gpu_m"]
+        bad = torch.tensor([0 if (mode != "replicated" or (dR_s == 0.0 and dt_s == 0.0)) and dR_s <= 1e-5 and dt_s <= 1e-4 else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            raise RuntimeError(f"sharded ICP ({mode}): pose differs from the single-GPU result (dR={dR_s:.3e}, dt={dt_s:.3e} m; replicated mode must be bit-identical)")
     return out
