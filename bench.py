@@ -379,7 +379,7 @@ def run_ours(args, rank, local_rank, world):
                 tt += time.perf_counter() - t0
             sums.append(tt)
         barrier()
-        return max_over_ranks(float(np.median(sums))) / args.steps, R
+        return 1000.0 * max_over_ranks(float(np.median(sums))) / args.steps, R      # ms per call
 
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record(); frame_step(); a1.record(); torch.cuda.synchronize()
@@ -529,7 +529,7 @@ def run_ours(args, rank, local_rank, world):
         eg1.record()
         solver.set_source(dB)
         for it in range(ICP_ITERS):
-            evs[it][0].record(); solver.match(); evs[it][1].record(); solver.stats(); evs[it][2].record(); solver.sums(); evs[it][3].record()
+            evs[it][0].record(); solver.match(); evs[it][1].record(); solver.reduce(); evs[it][2].record(); evs[it][3].record()
         solver.finish()
         torch.cuda.synchronize()
         acc[0] += eg0.elapsed_time(eg1)
@@ -541,7 +541,7 @@ def run_ours(args, rank, local_rank, world):
     match_gbs = icp_alg / max(acc[1], 1e-9) / 1e6
     icp_roofline = {"bound": "hbm", "kernel": "k_icp_match_packet", "achieved": match_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": match_gbs / hbm_peak, "traffic": ncu_traffic("k_icp_match_packet")[0], "traffic_source": ncu_traffic("k_icp_match_packet")[1],
                     "peak_source": peak_src, "note": "packet octree NN on L2-resident data: issue- and dependent-latency bound, not HBM (ncu: 57 % issue slots, 27 of 32 lanes, 0 % tensor pipe; see profiles/)",
-                    "stages_ms": {"target_grid_build_per_call": float(acc[0]), "match_per_iter": float(acc[1]), "stats_per_iter": float(acc[2]), "sums_per_iter": float(acc[3])},
+                    "stages_ms": {"target_grid_build_per_call": float(acc[0]), "match_per_iter": float(acc[1]), "reduce_per_iter": float(acc[2])},
                     "whole_iteration": {"alg_bytes": icp_alg, "achieved": icp_alg / (icp_ms / ICP_ITERS) / 1e6, "frac": icp_alg / (icp_ms / ICP_ITERS) / 1e6 / hbm_peak}}
 
     # ICP end to end through the reference's own export (host buffers)

@@ -251,20 +251,25 @@ int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, void *stream);
  * neighbours THIS rank searches (0,n2 on one GPU); R/t accumulators start from R0 (9 floats), t0 (3). */
 int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_begin, int i_end, const float *R0, const float *t0, void *stream);
 
-/* One iteration, in the three stream-ordered stages a multi-GPU host interleaves collectives with:
- *   ls3d_icp_match : apply the previous iteration's (T,Rk) to verts2, NN search of the local slice, one-to-one
- *                    dedupe by 64-bit atomicMin into the slot array (ls3d_icp_slots: int64[n1], MIN-reducible)
- *   ls3d_icp_stats : count / sum / sum of squares of matched d2 over slots [j_begin,j_end) -> ls3d_icp_stats_buf (f64[4])
- *   ls3d_icp_sums  : 2.5 sigma rejection + the 16 correspondence sums over slots [j_begin,j_end) -> ls3d_icp_sums_buf
- *                    (f64[16]); resets all slots for the next iteration.  When the range covers every slot (one GPU) the
- *                    same kernel also runs the solve step; otherwise all-reduce the sums and call
- *   ls3d_icp_solve : 3x3 Kabsch/SVD on the device from ls3d_icp_sums_buf -> the (T, Rk) the next match applies, and the
- *                    R,t accumulation of icp.cpp:167-168 (ls3d_icp_match / ls3d_icp_finish call it themselves if needed)
+/* One iteration = two stream-ordered stages:
+ *   ls3d_icp_match  : apply the previous iteration's (T,Rk) to verts2, exact NN search of the local source slice (warp packets,
+ *                     then a block-wide stage for the few packets that need 60+ node visits), one-to-one dedupe by 64-bit
+ *                     atomicMin into the dedupe slots (ls3d_icp_slots: int64[n1]; with peers set, into the OWNER rank's slots
+ *                     over NVLink)
+ *   ls3d_icp_reduce : mean / sigma of the matched squared distances in the reference's two-pass form (icp.cpp:34-54), the
+ *                     2.5 sigma gate, the 16 correspondence sums, the 3x3 Kabsch/SVD -> the (T, Rk) the next match applies, and
+ *                     the R,t accumulation of icp.cpp:167-168 — ONE launch with in-kernel grid barriers; every slot is reset.
+ *                     With peers set the ranks exchange their partial sums inside the kernel (peer stores + flags): no
+ *                     collective library call anywhere in the loop.  This pair is what ls3d_icp_run and ICP() enqueue.
  * ls3d_icp_finish applies the last (T,Rk), leaving R,t in ls3d_icp_Rt (device f32[12]: R[9] then t[3]). */
 int ls3d_icp_match(Ls3dIcp *c, void *stream);
-int ls3d_icp_stats(Ls3dIcp *c, int j_begin, int j_end, void *stream);
-int ls3d_icp_sums(Ls3dIcp *c, int j_begin, int j_end, void *stream);
-int ls3d_icp_solve(Ls3dIcp *c, void *stream);
+int ls3d_icp_reduce(Ls3dIcp *c, void *stream);
+/* Sharded ICP over `world` <= 8 GPUs of one node, one process each: replicated clouds, source slices searched per rank, dedupe
+ * slots and reduction chunks owned per target range.  slots/part/flag[r] = rank r's ls3d_icp_slots / ls3d_icp_red_part /
+ * ls3d_icp_red_flag as mapped into this process (CUDA IPC); entry `rank` must be the context's own.  world <= 1 switches it off. */
+int ls3d_icp_set_peers(Ls3dIcp *c, int world, int rank, void *const *slots, void *const *part, void *const *flag);
+double *ls3d_icp_red_part(Ls3dIcp *c);      /* device f64[3][296][16] */
+unsigned *ls3d_icp_red_flag(Ls3dIcp *c);    /* device u32[64] */
 int ls3d_icp_finish(Ls3dIcp *c, void *stream);
 /* All maxIter iterations on one GPU, no host round trips (captured once per shape as a CUDA graph). */
 int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream);
@@ -274,8 +279,6 @@ int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream);
 void ls3d_icp_set_debug(Ls3dIcp *c, void *d_stats);
 
 long long *ls3d_icp_slots(Ls3dIcp *c);      /* device int64[n1] */
-double *ls3d_icp_stats_buf(Ls3dIcp *c);     /* device f64[4]  : count, sum d2, sum d2^2, 0 */
-double *ls3d_icp_sums_buf(Ls3dIcp *c);      /* device f64[16] : count, sum(p-q)[3], sum p[3], sum q (x) p [9] */
 float *ls3d_icp_Rt(Ls3dIcp *c);             /* device f32[12] */
 const int *ls3d_icp_nn_index(Ls3dIcp *c);   /* device int[n2]: last NN index per source point (-1 outside the slice) */
 const float *ls3d_icp_nn_dist(Ls3dIcp *c);  /* device f32[n2] */

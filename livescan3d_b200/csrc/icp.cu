@@ -31,7 +31,6 @@
 namespace ls3d {
 
 constexpr unsigned long long kSlotEmpty = 0x7FFFFFFFFFFFFFFFull;   // positive as int64: MIN-reducible by NCCL/torch as signed
-constexpr int kRedBlocks = 296;                                    // 2 per SM: blocks of the reduction kernels
 constexpr int kTraceCap = 64;
 
 struct IcpGrid {
@@ -47,7 +46,13 @@ struct IcpState {
 	unsigned ticket_stats, ticket_sums, n_work, blocks_done;   // n_work: packet counter of the match stage
 	unsigned n_packets, n_heavy, n_light, sched_valid;         // packets of the current source ordering; longest-first schedule (k_icp_stats)
 	float xf[12];           // the update the next match kernel applies: T[3] then Rk[9] (written by the solve step)
+	unsigned hq_n, hq_head, hq_done, light_done;   // heavy packets of the current match stage: queued / handed out / blocks finished; the packet kernel has run dry
+	unsigned cls_n[8], cls_fill[8];            // packets per cost class of the match stage just run / placed so far by the scheduler (k_icp_stats)
+	unsigned red_bar, red_epoch, red_pad0, red_pad1;   // k_icp_reduce: arrivals at its grid barriers; launches so far (never reset: the cross-rank flags count on)
 };
+
+// cost class of a packet for the longest-first schedule: 0 = over budget (block-wide stage), then 7 classes of 8 visits, most expensive first
+__device__ __forceinline__ unsigned pk_cost_class(unsigned cost, unsigned budget) { return cost > budget ? 0u : 7u - min(6u, cost >> 3); }
 
 struct IcpBox { unsigned mn[3], mx[3]; };
 
@@ -430,12 +435,18 @@ __device__ __forceinline__ void apply_xform(float &x, float &y, float &z, const 
 	z = __fadd_rn(__fadd_rn(__fmul_rn(a0, Rk[2]), __fmul_rn(a1, Rk[5])), __fmul_rn(a2, Rk[8]));
 }
 
-__device__ __forceinline__ void nn_commit(int i, float d2, int idx, unsigned long long *slots, int *__restrict__ nn_idx, float *__restrict__ nn_d2) {
+// Where the dedupe slot of a target point lives: with several ranks the slot array is sharded by target chunk (k_icp_reduce's
+// chunks: `chunk` points each, `per` chunks per rank) and ptr[r] is rank r's array, mapped into this process (NVLink).
+struct SlotMap { int world, chunk, per, pad; unsigned long long *ptr[8]; };
+
+__device__ __forceinline__ void nn_commit(int i, float d2, int idx, const SlotMap &sm, int *__restrict__ nn_idx, float *__restrict__ nn_d2) {
 	nn_idx[i] = idx;
 	nn_d2[i] = idx >= 0 ? d2 : 0.0f;
 	if (idx >= 0) {
 		// one-to-one dedupe (icp.cpp:95-126): smallest d2 wins the target point, the LATER source index wins ties
 		const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+		unsigned long long *slots = sm.ptr[0];
+		if (sm.world > 1) slots = sm.ptr[min(sm.world - 1, (idx / sm.chunk) / sm.per)];      // the owner's array: a 64-bit atomic over NVLink
 		atomicMin(&slots[idx], key);
 	}
 }
@@ -458,8 +469,9 @@ constexpr int kPkDone = 4;             // home cells scanned up front (and skipp
 
 struct PkWarp {
 	float4 lo[8][8], hi[8][8];      // [level t-1][child]: point boxes of the children of the node being iterated at level t, decoded
-	                                // (origin-relative, already widened by the slack): one lane decodes one child, every lane reads all
-	float4 pts[32];                 // staged candidate points
+	                                // (origin-relative, already widened by the slack): lane 8a+c decodes axis a of child c, every lane reads all
+	float px[32], py[32], pz[32];   // staged candidate points, one plane per coordinate: an LDS.64 yields the same coordinate of two candidates
+	int pi[32];                     // ... and their original indices
 	uint2 rng[8];                   // point ranges of the 8 cells under the current level-1 node
 	unsigned char rem[8];           // remaining (octant-permuted) child masks per level
 };
@@ -469,21 +481,70 @@ struct PkWarp {
 // it has been seen — far queries start pruning at once instead of walking with an infinite bound (first iteration: no seed).
 struct PkLane { float qx, qy, qz, rx, ry, rz, d2, bnd; int idx; bool valid; };
 
-__device__ __forceinline__ void pk_scan(const float4 *__restrict__ sorted, unsigned s, unsigned e, PkLane &q, PkWarp &sh) {
+// What is the same for the whole packet: the bounding box of its queries (origin-relative) for the one-test-per-child coarse cull,
+// and the reference lane's query, which fixes the near-first visiting order (warp-uniform values).
+struct PkPacket { float qlo[3], qhi[3], refx, refy, refz; };
+
+// packed fp32 (sm_100 FADD2 / FMUL2 / FFMA2): both halves rounded exactly like the scalar _rn sequence.  The adds are issued as
+// fma(a, 1.0f, b) with the 1.0f from a kernel argument, so ptxas cannot contract mul + add into one FFMA2 (which would drop the
+// product's rounding; it does that even under --fmad=false — seen in SASS of the organized neighbour count, frame.cu).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// all lanes test the points sorted[s, e) against their own query; ties resolve to the smallest target index.
+// Optionally a real function call (arguments and result in registers; -DLS3D_PK_SCAN_CALL=1): the packet kernels scan from
+// several places and the loop, unrolled, is a third of their code.
+#ifndef LS3D_PK_SCAN_CALL
+#define LS3D_PK_SCAN_CALL 0            // measured: the call (185 us / iteration) loses to the inlined copies (170 us) although the latter is 42 KB of code
+#endif
+#if LS3D_PK_SCAN_CALL
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+unsigned long long pk_scan_fn(const float4 *__restrict__ sorted, unsigned s, unsigned e, float qx, float qy, float qz,
+	float best_d2, int best_idx, PkWarp *shp, f32x2 one2)
+{
+	PkWarp &sh = *shp;
 	const int lane = threadIdx.x & 31;
+	const f32x2 q2x = pk2(qx, qx), q2y = pk2(qy, qy), q2z = pk2(qz, qz);
+	// the next batch of 32 points is requested before the current one is tested, so its L2 round trip overlaps the arithmetic
+	float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (s + (unsigned)lane < e) c = __ldg(sorted + s + lane);
 	for (unsigned base = s; base < e; base += 32) {
 		const unsigned n = min(32u, e - base);
 		__syncwarp();
-		if ((unsigned)lane < n) sh.pts[lane] = __ldg(sorted + base + lane);
+		if ((unsigned)lane < n) {
+			sh.px[lane] = c.x; sh.py[lane] = c.y; sh.pz[lane] = c.z; sh.pi[lane] = __float_as_int(c.w);
+		} else if ((unsigned)lane == n) {
+			// pad an odd count: a candidate infinitely far away (d2 = inf never wins)
+			sh.px[lane] = INFINITY; sh.py[lane] = INFINITY; sh.pz[lane] = INFINITY; sh.pi[lane] = 0x7fffffff;
+		}
+		if (base + 32u + (unsigned)lane < e) c = __ldg(sorted + base + 32u + lane);
 		__syncwarp();
-#pragma unroll 4
-		for (unsigned j = 0; j < n; j++) {
-			const float4 c = sh.pts[j];                           // broadcast
-			const float d2 = dist2_ref(q.qx, q.qy, q.qz, c.x, c.y, c.z);
-			const int idx = __float_as_int(c.w);
-			if (d2 < q.d2 || (d2 == q.d2 && idx < q.idx)) { q.d2 = d2; q.idx = idx; }
+		const unsigned np = (n + 1) >> 1;
+#pragma unroll 2
+		for (unsigned j = 0; j < np; j++) {
+			const f32x2 X = *reinterpret_cast<const f32x2 *>(sh.px + 2 * j), Y = *reinterpret_cast<const f32x2 *>(sh.py + 2 * j), Z = *reinterpret_cast<const f32x2 *>(sh.pz + 2 * j);
+			const int2 I = *reinterpret_cast<const int2 *>(sh.pi + 2 * j);
+			const f32x2 d0 = sub2(q2x, X), d1 = sub2(q2y, Y), d2 = sub2(q2z, Z);
+			const f32x2 sq = fma2(fma2(mul2(d0, d0), one2, mul2(d1, d1)), one2, mul2(d2, d2));      // == dist2_ref on both halves
+			float da, db;
+			upk2(sq, da, db);
+			if (da < best_d2 || (da == best_d2 && I.x < best_idx)) { best_d2 = da; best_idx = I.x; }
+			if (db < best_d2 || (db == best_d2 && I.y < best_idx)) { best_d2 = db; best_idx = I.y; }
 		}
 	}
+	return ((unsigned long long)__float_as_uint(best_d2) << 32) | (unsigned)best_idx;
+}
+__device__ __forceinline__ void pk_scan(const float4 *__restrict__ sorted, unsigned s, unsigned e, PkLane &q, PkWarp &sh, f32x2 one2) {
+	const unsigned long long r = pk_scan_fn(sorted, s, e, q.qx, q.qy, q.qz, q.d2, q.idx, &sh, one2);
+	q.d2 = __uint_as_float((unsigned)(r >> 32));
+	q.idx = (int)(unsigned)r;
 	q.bnd = fminf(q.bnd, q.d2);
 }
 
@@ -494,28 +555,43 @@ __device__ __forceinline__ float pk_lb2(const float4 lo, const float4 hi, float 
 }
 
 // The 8 child records of node (t; ump) -> sh.lo/hi[t-1] (and their point ranges -> sh.rng when the children are cells).
-// Returns the mask of non-empty children.  One memory round trip: lanes 0-7 fetch the records, lanes 8-16 the ranges.
+// One memory round trip; lane 8a + c (a < 3) fetches child c's record and decodes its axis a, lanes 24-31 fetch the cell ranges.
+// Returns the mask of non-empty children; `coarse` = those of them whose box is within sqrt(maxbnd) of the PACKET's query box
+// (a superset of what any lane needs: one box-box test per child, in parallel over the children, instead of 8 per lane).
 __device__ __forceinline__ unsigned pk_load_children(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellrec, PkWarp &sh, int t, unsigned ux, unsigned uy, unsigned uz, unsigned ump, float slack)
+	const unsigned long long *__restrict__ cellrec, PkWarp &sh, int t, unsigned ux, unsigned uy, unsigned uz, unsigned ump, float slack,
+	const PkPacket &pkt, float maxbnd, unsigned &coarse)
 {
 	const int lane = threadIdx.x & 31;
+	const unsigned c = (unsigned)lane & 7u;
+	const int a = lane >> 3;
 	unsigned long long rec = 0;
+	float gap2 = 0.0f;
 	__syncwarp();                                                        // earlier readers of sh.lo/hi / sh.rng are done
-	if (lane < 8) {
-		const unsigned c = (unsigned)lane, cmp = (ump << 3) | c;
+	if (a < 3) {
+		const unsigned cmp = (ump << 3) | c;
 		rec = t == 1 ? __ldg(cellrec + cmp) : __ldg(nodes + icp_mask_off(g.levels, t - 1) + cmp);      // 0 = empty
-		const float half = g.h * (float)(1u << (t - 1));
-		float mn[3], mx[3];
-		box_decode(rec, (float)((ux << 1) | (c & 1u)) * half, (float)((uy << 1) | ((c >> 1) & 1u)) * half, (float)((uz << 1) | (c >> 2)) * half, half, mn, mx);
-		sh.lo[t - 1][lane] = make_float4(mn[0] - slack, mn[1] - slack, mn[2] - slack, 0.0f);
-		sh.hi[t - 1][lane] = make_float4(mx[0] + slack, mx[1] + slack, mx[2] + slack, 0.0f);
-	} else if (t == 1 && lane < 17) {
-		// cell_start[(ump << 3) + 0 .. 8]: the 8 cells are consecutive in Morton order, so 9 values give the 8 ranges
-		const unsigned v = __ldg(cell_start + (ump << 3) + (unsigned)(lane - 8));
-		if (lane < 16) sh.rng[lane - 8].x = v;
-		if (lane > 8) sh.rng[lane - 9].y = v;
+		const float half = g.h * (float)(1u << (t - 1));                 // child edge
+		const float qs = half * (1.0f / 255.0f);
+		const unsigned ua = a == 0 ? ux : (a == 1 ? uy : uz);
+		const float o = (float)((ua << 1) | ((c >> a) & 1u)) * half;     // child origin along this axis
+		const float mn = o + (float)(unsigned)((rec >> (8 * a)) & 0xff) * qs - slack;
+		const float mx = o + (float)(unsigned)((rec >> (24 + 8 * a)) & 0xff) * qs + slack;
+		reinterpret_cast<float *>(&sh.lo[t - 1][c])[a] = mn;
+		reinterpret_cast<float *>(&sh.hi[t - 1][c])[a] = mx;
+		const float ql = a == 0 ? pkt.qlo[0] : (a == 1 ? pkt.qlo[1] : pkt.qlo[2]);
+		const float qh = a == 0 ? pkt.qhi[0] : (a == 1 ? pkt.qhi[1] : pkt.qhi[2]);
+		const float gap = fmaxf(fmaxf(mn - qh, ql - mx), 0.0f);
+		gap2 = gap * gap;
+	} else if (t == 1) {
+		// the 8 cells are consecutive in Morton order: cell_start[(ump << 3) + c .. + 1] is cell c's range
+		const unsigned v0 = __ldg(cell_start + (ump << 3) + c), v1 = __ldg(cell_start + (ump << 3) + c + 1u);
+		sh.rng[c] = make_uint2(v0, v1);
 	}
-	const unsigned exist = __ballot_sync(kFull, rec != 0ull) & 0xffu;
+	const float g2 = (gap2 + __shfl_down_sync(kFull, gap2, 8)) + __shfl_down_sync(kFull, gap2, 16);
+	const bool ex = lane < 8 && rec != 0ull;
+	const unsigned exist = __ballot_sync(kFull, ex);
+	coarse = __ballot_sync(kFull, ex && g2 * 0.99999f <= maxbnd);
 	__syncwarp();
 	return exist;
 }
@@ -524,11 +600,13 @@ __device__ __forceinline__ unsigned pk_load_children(const IcpGrid &g, const uns
 // the root, at every level into the non-empty child nearest to that lane, and a scan of the cell it ends in.  L node
 // visits buy every lane of the packet a bound close to its final one, so the exact walk that follows prunes like a seeded one.
 __device__ __forceinline__ void pk_greedy_seed(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, PkWarp &sh, PkLane &q, int who, float slack, unsigned &steps, unsigned &scanned)
+	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, PkWarp &sh, PkLane &q, const PkPacket &pkt, int who, float slack,
+	f32x2 one2, unsigned &steps, unsigned &scanned)
 {
 	unsigned ux = 0, uy = 0, uz = 0, ump = 0;
 	for (int t = g.levels; t >= 1; t--) {
-		unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, slack);
+		unsigned coarse;
+		unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, slack, pkt, INFINITY, coarse);
 		if (!exist) return;                                               // empty target: cannot happen after ls3d_icp_set_target
 		float best_lb = INFINITY;
 		unsigned best_c = (unsigned)__ffs(exist) - 1u;
@@ -543,24 +621,29 @@ __device__ __forceinline__ void pk_greedy_seed(const IcpGrid &g, const unsigned 
 		if (t == 1) {
 			const uint2 r = sh.rng[c];
 			scanned += r.y - r.x;
-			pk_scan(sorted, r.x, r.y, q, sh);
+			pk_scan(sorted, r.x, r.y, q, sh, one2);
 			return;
 		}
 		ux = (ux << 1) | (c & 1u); uy = (uy << 1) | ((c >> 1) & 1u); uz = (uz << 1) | (c >> 2); ump = (ump << 3) | c;
 	}
 }
 
-// Leave in sh.rem[t-1] the octant-permuted mask of the children in `allowed` that some lane still needs.
+// Leave in sh.rem[t-1] the octant-permuted mask of the children in `allowed` that may hold something a lane still needs: the
+// coarse packet-level cull only — every child is tested again, per lane and against the bounds of that moment, when the walk
+// pops it (pk_walk), so nothing is lost by not doing the 8 per-lane tests here as well.
 __device__ __forceinline__ void pk_enter(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
 	const unsigned long long *__restrict__ cellrec, PkWarp &sh, int t, unsigned ux, unsigned uy, unsigned uz, unsigned ump, unsigned allowed,
-	PkLane &q, int ref, unsigned &nearpack, float slack)
+	PkLane &q, const PkPacket &pkt, unsigned &nearpack, float slack)
 {
 	const int lane = threadIdx.x & 31;
-	unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, slack) & allowed;
+	// the largest bound of any lane (bounds are non-negative, +inf included: their bit patterns order like unsigned integers)
+	const float maxbnd = __uint_as_float(__reduce_max_sync(kFull, q.valid ? __float_as_uint(q.bnd) : 0u));
+	unsigned coarse;
+	unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, slack, pkt, maxbnd, coarse) & allowed;
 	const float half = g.h * (float)(1u << (t - 1));                     // child edge
-	unsigned need = 0;
-	if (__any_sync(kFull, q.valid && q.bnd == INFINITY)) {
-		// some lane has no bound at all yet (first iteration, far from everything): every non-empty child proves one
+	if (maxbnd == INFINITY) {
+		// some lane has no bound at all yet (degenerate inputs only: the greedy seed gives every lane a candidate): every
+		// non-empty child proves one
 		unsigned ex = exist;
 		while (ex) {
 			const unsigned c = (unsigned)__ffs(ex) - 1u;
@@ -571,15 +654,9 @@ __device__ __forceinline__ void pk_enter(const IcpGrid &g, const unsigned *__res
 			q.bnd = fminf(q.bnd, (fx * fx + fy * fy + fz * fz) * 1.00001f);
 		}
 	}
-	while (exist) {
-		const unsigned c = (unsigned)__ffs(exist) - 1u;
-		exist &= exist - 1u;
-		const float lb = pk_lb2(sh.lo[t - 1][c], sh.hi[t - 1][c], q.rx, q.ry, q.rz);
-		if (__any_sync(kFull, q.valid && lb <= q.bnd)) need |= 1u << c;
-	}
-	// near-first visiting order: the octant of the reference lane's query inside this node
-	unsigned near = (q.rx >= (float)(2 * ux + 1) * half ? 1u : 0u) | (q.ry >= (float)(2 * uy + 1) * half ? 2u : 0u) | (q.rz >= (float)(2 * uz + 1) * half ? 4u : 0u);
-	near = __shfl_sync(kFull, near, ref);
+	const unsigned need = coarse & allowed;
+	// near-first visiting order: the octant of the reference lane's query inside this node (warp-uniform arithmetic)
+	const unsigned near = (pkt.refx >= (float)(2 * ux + 1) * half ? 1u : 0u) | (pkt.refy >= (float)(2 * uy + 1) * half ? 2u : 0u) | (pkt.refz >= (float)(2 * uz + 1) * half ? 4u : 0u);
 	nearpack = (nearpack & ~(7u << (3 * (t - 1)))) | (near << (3 * (t - 1)));
 	if (lane == 0) sh.rem[t - 1] = (unsigned char)octant_permute(need, near);
 	__syncwarp();
@@ -587,19 +664,51 @@ __device__ __forceinline__ void pk_enter(const IcpGrid &g, const unsigned *__res
 
 struct PkDone { unsigned m[kPkDone]; };
 
-// depth-first walk below node (top; ux,uy,uz,ump) whose needed-children mask pk_enter has just left in sh.rem[top-1]
-__device__ __forceinline__ void pk_walk(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, PkWarp &sh, int top, unsigned ux, unsigned uy, unsigned uz, unsigned ump,
-	PkLane &q, int ref, unsigned &nearpack, float slack, const PkDone &done, unsigned &steps, unsigned &scanned)
+// The exact search below / around one node, as ONE loop (one copy of pk_enter and one of pk_scan in the instruction stream: the
+// first version inlined walk and climb separately and the kernel outgrew the instruction cache — ncu: 19 % of the stall samples
+// were instruction fetch).
+//   * depth-first, near-first walk of the subtree under (lvl; nx,ny,nz,nmp): every child popped is tested per lane against the
+//     bounds of that moment; cells are scanned, inner nodes entered;
+//   * climb (when `climb`): once the subtree is finished and some lane's ball still reaches outside its cube, the parent is
+//     entered with the finished child masked out, and so on, level by level, until every ball fits (faces on the grid boundary
+//     have nothing behind them) or the root is done.
+// Returns early when `steps` exceeds `budget` (the caller queues the packet for the block-wide stage).
+__device__ __forceinline__ void pk_search(const IcpGrid &g, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, PkWarp &sh, int lvl, unsigned nx, unsigned ny, unsigned nz, unsigned nmp,
+	PkLane &q, const PkPacket &pkt, float slack, const PkDone &done, f32x2 one2, unsigned &steps, unsigned &scanned, unsigned budget, bool climb)
 {
 	const int lane = threadIdx.x & 31;
-	int t = top;
+	const int L = g.levels;
+	int top = lvl, t = lvl;
+	unsigned ux = nx, uy = ny, uz = nz, ump = nmp;          // the node whose children are being iterated (level t)
+	unsigned allowed = 0xffu, nearpack = 0;
+	bool enter = lvl > 0;
 	for (;;) {
-		const unsigned rm = sh.rem[t - 1];
+		if (steps > budget) return;
+		if (enter) {
+			pk_enter(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, allowed, q, pkt, nearpack, slack);
+			enter = false;
+		}
+		const unsigned rm = t > 0 ? sh.rem[t - 1] : 0u;
 		if (rm == 0) {
-			if (t == top) break;
-			t++;
+			if (t < top) { t++; ux >>= 1; uy >>= 1; uz >>= 1; ump >>= 3; continue; }
+			// the subtree under (top; ux,uy,uz) is finished
+			if (!climb || top >= L) return;
+			const float size = g.h * (float)(1u << top);
+			const unsigned dim = (unsigned)g.G >> top;
+			float rho = INFINITY;
+			if (ux > 0) rho = fminf(rho, q.rx - (float)ux * size);
+			if (ux + 1 < dim) rho = fminf(rho, (float)(ux + 1) * size - q.rx);
+			if (uy > 0) rho = fminf(rho, q.ry - (float)uy * size);
+			if (uy + 1 < dim) rho = fminf(rho, (float)(uy + 1) * size - q.ry);
+			if (uz > 0) rho = fminf(rho, q.rz - (float)uz * size);
+			if (uz + 1 < dim) rho = fminf(rho, (float)(uz + 1) * size - q.rz);
+			rho = fmaxf(rho - slack, 0.0f);
+			if (!__any_sync(kFull, q.valid && !(q.d2 <= rho * rho * 0.99999f))) return;
+			allowed = 0xffu & ~(1u << (ump & 7u));              // the child just finished
 			ux >>= 1; uy >>= 1; uz >>= 1; ump >>= 3;
+			top++; t = top;
+			enter = true;
 			continue;
 		}
 		const unsigned cp = (unsigned)__ffs(rm) - 1u;
@@ -614,18 +723,19 @@ __device__ __forceinline__ void pk_walk(const IcpGrid &g, const unsigned *__rest
 			for (int d = 0; d < kPkDone; d++) skip |= done.m[d] == cmp;     // a home cell: already scanned
 			if (skip) continue;
 		}
-		// the bounds have tightened since this child was queued: test again before paying for the visit
+		// the per-lane test, against the bounds as they are now
 		const float lb = pk_lb2(sh.lo[t - 1][child], sh.hi[t - 1][child], q.rx, q.ry, q.rz);
 		if (!__any_sync(kFull, q.valid && lb <= q.bnd)) continue;
 		steps++;
 		if (t == 1) {
 			const uint2 r = sh.rng[child];
 			scanned += r.y - r.x;
-			pk_scan(sorted, r.x, r.y, q, sh);
+			pk_scan(sorted, r.x, r.y, q, sh, one2);
 		} else {
 			t--;
 			ux = (ux << 1) | (child & 1u); uy = (uy << 1) | ((child >> 1) & 1u); uz = (uz << 1) | (child >> 2); ump = cmp;
-			pk_enter(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, 0xffu, q, ref, nearpack, slack);
+			allowed = 0xffu;
+			enter = true;
 		}
 	}
 }
@@ -636,68 +746,105 @@ __device__ __forceinline__ void pk_walk(const IcpGrid &g, const unsigned *__rest
 #ifndef LS3D_PK_MINBLOCKS
 #define LS3D_PK_MINBLOCKS 3
 #endif
+// A warp gives up on a packet after this many node / cell visits and queues it for k_icp_match_heavy, where a whole block
+// searches it.  A warp's instruction stream is serial: the few packets that need 100+ visits (queries far from the target whose
+// search balls graze a lot of surface) used to run for the whole length of the kernel while every other warp had long finished
+// (ncu, round 2: SMSPs active 56 % of the kernel's duration).  Packets that were over budget last iteration go straight there.
+#ifndef LS3D_PK_BUDGET
+#define LS3D_PK_BUDGET 64
+#endif
+constexpr unsigned kPkBudget = LS3D_PK_BUDGET;
+
+// this lane's query of packet `pd`: position (after the pending update when apply != 0, which is also written back), home cell,
+// and the previous nearest neighbour as the first candidate
+__device__ __forceinline__ int pk_load_lane(const uint2 pd, const unsigned *__restrict__ order, float *__restrict__ verts2, const float *__restrict__ verts1,
+	const int *__restrict__ nn_idx, const IcpGrid &g, const float *__restrict__ xf /* T[3] Rk[9], or NULL */, PkLane &q, unsigned &mp, unsigned &hx, unsigned &hy, unsigned &hz)
+{
+	const int lane = threadIdx.x & 31;
+	const int i = (unsigned)lane < pd.y ? (int)__ldg(order + pd.x + lane) : -1;
+	q.valid = false; q.d2 = INFINITY; q.bnd = INFINITY; q.idx = -1;
+	q.qx = q.qy = q.qz = q.rx = q.ry = q.rz = 0.0f;
+	mp = 0; hx = 0; hy = 0; hz = 0;
+	if (i >= 0) {
+		float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
+		const int prev = nn_idx[i];
+		if (xf) {
+			// the update is re-read per packet (12 cached, warp-uniform loads) instead of living in 12 registers for the whole kernel
+			float T[3], Rk[9];
+#pragma unroll
+			for (int a = 0; a < 3; a++) T[a] = xf[a];
+#pragma unroll
+			for (int a = 0; a < 9; a++) Rk[a] = xf[3 + a];
+			apply_xform(x, y, z, T, Rk);
+			verts2[3 * (size_t)i] = x; verts2[3 * (size_t)i + 1] = y; verts2[3 * (size_t)i + 2] = z;
+		}
+		q.qx = x; q.qy = y; q.qz = z;
+		q.rx = x - g.ox; q.ry = y - g.oy; q.rz = z - g.oz;
+		q.valid = isfinite(q.rx) && isfinite(q.ry) && isfinite(q.rz);
+		if (q.valid) {
+			if (prev >= 0) {
+				const float d2 = dist2_ref(x, y, z, verts1[3 * (size_t)prev], verts1[3 * (size_t)prev + 1], verts1[3 * (size_t)prev + 2]);
+				if (d2 == d2) { q.d2 = d2; q.bnd = d2; q.idx = prev; }
+			}
+			hx = (unsigned)icp_cell(q.rx, g.inv_h, g.G); hy = (unsigned)icp_cell(q.ry, g.inv_h, g.G); hz = (unsigned)icp_cell(q.rz, g.inv_h, g.G);
+			mp = morton3(hx, hy, hz);
+		}
+	}
+	return i;
+}
+
+__device__ __forceinline__ void pk_packet_box(const PkLane &q, int ref, PkPacket &pkt) {
+	pkt.refx = __shfl_sync(kFull, q.rx, ref); pkt.refy = __shfl_sync(kFull, q.ry, ref); pkt.refz = __shfl_sync(kFull, q.rz, ref);
+	pkt.qlo[0] = ord2f(__reduce_min_sync(kFull, q.valid ? f2ord(q.rx) : 0xffffffffu)); pkt.qhi[0] = ord2f(__reduce_max_sync(kFull, q.valid ? f2ord(q.rx) : 0u));
+	pkt.qlo[1] = ord2f(__reduce_min_sync(kFull, q.valid ? f2ord(q.ry) : 0xffffffffu)); pkt.qhi[1] = ord2f(__reduce_max_sync(kFull, q.valid ? f2ord(q.ry) : 0u));
+	pkt.qlo[2] = ord2f(__reduce_min_sync(kFull, q.valid ? f2ord(q.rz) : 0xffffffffu)); pkt.qhi[2] = ord2f(__reduce_max_sync(kFull, q.valid ? f2ord(q.rz) : 0u));
+}
+
 __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_packet(float *__restrict__ verts2, int i_begin, int i_end, int apply,
 	const unsigned *__restrict__ order, const uint2 *__restrict__ desc, const unsigned *__restrict__ sched, unsigned *__restrict__ pk_cost,
 	const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
-	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, const float *__restrict__ verts1, unsigned long long *slots,
-	IcpState *state, int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg)
+	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, const float *__restrict__ verts1, SlotMap slotmap,
+	IcpState *state, int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg, float one, unsigned *__restrict__ heavy_list, unsigned budget)
 {
-	__shared__ PkWarp s_pk[kPkWarps];
+	__shared__ __align__(16) PkWarp s_pk[kPkWarps];
+	// the block-wide stage (k_icp_match_heavy, a programmatic dependent launch) may start as soon as SM resources free up: it
+	// consumes the queue while this kernel's last packets are still running
+	asm volatile("griddepcontrol.launch_dependents;");
+	// this kernel itself may have been launched early (programmatic dependent launch behind the previous iteration's reduction):
+	// nothing that kernel wrote is read before it has completed
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	PkWarp &sh = s_pk[threadIdx.x >> 5];
-	float T[3] = {0.f, 0.f, 0.f}, Rk[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-	if (apply) {
-#pragma unroll
-		for (int a = 0; a < 3; a++) T[a] = state->xf[a];
-#pragma unroll
-		for (int a = 0; a < 9; a++) Rk[a] = state->xf[3 + a];
-	}
+	const float *xf = apply ? state->xf : nullptr;
 	const IcpGrid g = *grid;
 	const int lane = threadIdx.x & 31;
 	const int L = g.levels;
 	const float slack = 1e-3f * g.h;
+	const f32x2 one2 = pk2(one, one);
 	const int n_packets = (int)state->n_packets;
 	const bool use_sched = state->sched_valid != 0;
 	for (;;) {
 		int pk = 0;
 		if (lane == 0) {
 			pk = (int)atomicAdd(&state->n_work, 1u);
-			// longest first: the packets that walked furthest last iteration (k_icp_stats' schedule) start in the first wave, so the
-			// kernel's tail is the longest packet alone instead of the longest packet plus whatever ran before it
+			// longest first: the packets that walked furthest last iteration (k_icp_stats' schedule) start in the first wave
 			if (pk < n_packets && use_sched) pk = (int)sched[pk];
 		}
 		pk = __shfl_sync(kFull, pk, 0);
 		if (pk >= n_packets) break;
 		const uint2 pd = __ldg(desc + pk);
-		const int i = (unsigned)lane < pd.y ? (int)__ldg(order + pd.x + lane) : -1;
 		PkLane q;
-		q.valid = false; q.d2 = INFINITY; q.bnd = INFINITY; q.idx = -1;
-		q.qx = q.qy = q.qz = q.rx = q.ry = q.rz = 0.0f;
-		unsigned mp = 0, hx = 0, hy = 0, hz = 0;
-		if (i >= 0) {
-			float x = verts2[3 * (size_t)i], y = verts2[3 * (size_t)i + 1], z = verts2[3 * (size_t)i + 2];
-			const int prev = nn_idx[i];
-			if (apply) {
-				apply_xform(x, y, z, T, Rk);
-				verts2[3 * (size_t)i] = x; verts2[3 * (size_t)i + 1] = y; verts2[3 * (size_t)i + 2] = z;
-			}
-			q.qx = x; q.qy = y; q.qz = z;
-			q.rx = x - g.ox; q.ry = y - g.oy; q.rz = z - g.oz;
-			q.valid = isfinite(q.rx) && isfinite(q.ry) && isfinite(q.rz);
-			if (q.valid) {
-				if (prev >= 0) {
-					const float d2 = dist2_ref(x, y, z, verts1[3 * (size_t)prev], verts1[3 * (size_t)prev + 1], verts1[3 * (size_t)prev + 2]);
-					if (d2 == d2) { q.d2 = d2; q.bnd = d2; q.idx = prev; }
-				}
-				hx = (unsigned)icp_cell(q.rx, g.inv_h, g.G); hy = (unsigned)icp_cell(q.ry, g.inv_h, g.G); hz = (unsigned)icp_cell(q.rz, g.inv_h, g.G);
-				mp = morton3(hx, hy, hz);
-			}
-		}
+		unsigned mp, hx, hy, hz;
+		const int i = pk_load_lane(pd, order, verts2, verts1, nn_idx, g, xf, q, mp, hx, hy, hz);
 		const unsigned vmask = __ballot_sync(kFull, q.valid);
 		unsigned steps = 0, scanned = 0;
-		if (vmask) {
+		// over budget last iteration: straight to the block-wide stage (the points are transformed, the old neighbour stays the seed)
+		bool heavy = use_sched && vmask && __ldg(pk_cost + pk) > budget;
+		if (vmask && !heavy) {
 			const int ref = __ffs(vmask) - 1;
 			const unsigned mp_ref = __shfl_sync(kFull, mp, ref);
 			const unsigned rhx = __shfl_sync(kFull, hx, ref), rhy = __shfl_sync(kFull, hy, ref), rhz = __shfl_sync(kFull, hz, ref);
+			PkPacket pkt;
+			pk_packet_box(q, ref, pkt);
 			// ---- the home cells first: every lane gets a finite bound before the walk starts ----
 			PkDone done;
 #pragma unroll
@@ -711,56 +858,233 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_
 						todo &= ~__ballot_sync(kFull, q.valid && mp == m);
 						done.m[d] = m;
 						const unsigned s = __ldg(cell_start + m), e = __ldg(cell_start + m + 1);
-						if (s != e) { steps++; scanned += e - s; pk_scan(sorted, s, e, q, sh); }
+						if (s != e) { steps++; scanned += e - s; pk_scan(sorted, s, e, q, sh, one2); }
 					}
 				}
 			}
 			{
 				const unsigned unseeded = __ballot_sync(kFull, q.valid && q.idx < 0);
-				if (unseeded) pk_greedy_seed(g, cell_start, nodes, cellrec, sorted, sh, q, __ffs(unseeded) - 1, slack, steps, scanned);
+				if (unseeded) pk_greedy_seed(g, cell_start, nodes, cellrec, sorted, sh, q, pkt, __ffs(unseeded) - 1, slack, one2, steps, scanned);
 			}
 			const unsigned diff = __reduce_or_sync(kFull, q.valid ? (mp ^ mp_ref) : 0u);
 			int lvl = diff ? (31 - __clz((int)diff)) / 3 + 1 : 0;      // lowest level whose node holds every lane's home cell
-			unsigned nearpack = 0;
-			unsigned nx = rhx >> lvl, ny = rhy >> lvl, nz = rhz >> lvl, nmp = mp_ref >> (3 * lvl);
-			// ---- the subtree all home cells share (level 0: the one home cell, done above) ----
-			if (lvl > 0) {
-				pk_enter(g, cell_start, nodes, cellrec, sh, lvl, nx, ny, nz, nmp, 0xffu, q, ref, nearpack, slack);
-				pk_walk(g, cell_start, nodes, cellrec, sorted, sh, lvl, nx, ny, nz, nmp, q, ref, nearpack, slack, done, steps, scanned);
-			}
-			// ---- climb: siblings of the finished subtree, level by level, until every lane's ball fits inside it ----
-			for (; lvl < L; lvl++) {
-				const float size = g.h * (float)(1u << lvl);
-				const unsigned dim = (unsigned)g.G >> lvl;
-				float rho = INFINITY;
-				if (nx > 0) rho = fminf(rho, q.rx - (float)nx * size);
-				if (nx + 1 < dim) rho = fminf(rho, (float)(nx + 1) * size - q.rx);
-				if (ny > 0) rho = fminf(rho, q.ry - (float)ny * size);
-				if (ny + 1 < dim) rho = fminf(rho, (float)(ny + 1) * size - q.ry);
-				if (nz > 0) rho = fminf(rho, q.rz - (float)nz * size);
-				if (nz + 1 < dim) rho = fminf(rho, (float)(nz + 1) * size - q.rz);
-				rho = fmaxf(rho - slack, 0.0f);
-				if (!__any_sync(kFull, q.valid && !(q.d2 <= rho * rho * 0.99999f))) break;
-				const unsigned done_child = nmp & 7u;
-				nx >>= 1; ny >>= 1; nz >>= 1; nmp >>= 3;
-				pk_enter(g, cell_start, nodes, cellrec, sh, lvl + 1, nx, ny, nz, nmp, 0xffu & ~(1u << done_child), q, ref, nearpack, slack);
-				pk_walk(g, cell_start, nodes, cellrec, sorted, sh, lvl + 1, nx, ny, nz, nmp, q, ref, nearpack, slack, done, steps, scanned);
-			}
+			// ---- the subtree all home cells share (level 0: the one home cell, done above), then its siblings level by level ----
+			pk_search(g, cell_start, nodes, cellrec, sorted, sh, lvl, rhx >> lvl, rhy >> lvl, rhz >> lvl, mp_ref >> (3 * lvl), q, pkt, slack, done, one2, steps, scanned, budget, true);
+			heavy = steps > budget;
 		}
-		if (i >= 0) {
-			nn_commit(i, q.d2, q.valid ? q.idx : -1, slots, nn_idx, nn_d2);
-			if (dbg) { dbg[3 * (size_t)i] = steps; dbg[3 * (size_t)i + 1] = scanned; dbg[3 * (size_t)i + 2] = 0u; }
+		if (heavy) {
+			// the best candidate so far is a real point: it seeds the block-wide search (nothing is committed to the dedupe slots yet)
+			if (i >= 0 && q.valid && q.idx >= 0) nn_idx[i] = q.idx;
+			__threadfence();                                              // seeds and transformed points before the queue entry
+			__syncwarp();
+			if (lane == 0) st_volatile_u32(heavy_list + atomicAdd(&state->hq_n, 1u), (unsigned)pk);
+		} else {
+			if (i >= 0) {
+				nn_commit(i, q.d2, q.valid ? q.idx : -1, slotmap, nn_idx, nn_d2);
+				if (dbg) { dbg[3 * (size_t)i] = steps; dbg[3 * (size_t)i + 1] = scanned; dbg[3 * (size_t)i + 2] = 0u; }
+			}
+			if (lane == 0) { pk_cost[pk] = steps; atomicAdd(&state->cls_n[pk_cost_class(steps, budget)], 1u); }
 		}
-		if (lane == 0) pk_cost[pk] = steps;
 		__syncwarp();
 	}
 	// the last block to run dry re-arms the packet counter for the next match stage
+	__threadfence();                                                  // this block's results before its arrival
 	__syncthreads();
 	if (threadIdx.x == 0 && atomicAdd(&state->blocks_done, 1u) == gridDim.x - 1) {
 		state->blocks_done = 0;
 		state->n_work = 0;
 		state->n_heavy = 0;
 		state->n_light = 0;
+		__threadfence();
+		st_volatile_u32(&state->light_done, 1u);                      // the queue is final
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// block-wide search of the packets the warps gave up on
+// ------------------------------------------------------------------------------------------------------
+// One block = one heavy packet at a time; every warp holds the packet's 32 queries (lane i = query i) and the warps share the
+// tree: a level-synchronous top-down sweep from the root — the frontier of nodes that some lane still needs is split over the
+// warps, each tests the children of its nodes per lane against the bounds and appends the survivors to the next level's
+// frontier — then the surviving cells are scanned, again split over the warps, nearest first within what a warp draws.  The
+// lanes' best candidates are merged through 64-bit shared-memory atomicMin keys (bits(d2) << 32 | index: smaller distance, then
+// smaller target index, exactly the packet kernel's tie rule), which every warp re-reads before each test, so a neighbour
+// found by one warp prunes the others at once.  The seed is the best candidate the packet kernel left in nn_idx (a real point),
+// hence the bounds are near-final from the start and the sweep touches little more than the depth-first walk would have.
+// Exactness is the packet kernel's: a node is dropped only when every lane's conservative lower bound exceeds that lane's bound.
+constexpr unsigned kHvEmpty = 0xffffffffu;  // queue entry not (yet) written
+constexpr int kHvFrontCap = 1024;      // nodes per level; beyond that a warp walks the child depth-first on the spot
+constexpr int kHvCellCap = 1024;
+
+struct HvBlock {
+	PkWarp pkw[kPkWarps];
+	unsigned long long key[32];               // per query: bits(d2) << 32 | target index
+	unsigned front[2][kHvFrontCap];           // Morton codes of the frontier nodes of the current / next level
+	unsigned cells[kHvCellCap];               // Morton codes of the cells to scan
+	uint2 cell_rng[kHvCellCap];
+	float4 cell_lo[kHvCellCap], cell_hi[kHvCellCap];
+	unsigned n_front[2], n_cells, next_cell, steps, scanned;
+	int pk_id;
+};
+
+__device__ __forceinline__ void hv_refresh(const HvBlock &hb, PkLane &q) {
+	const unsigned long long k = hb.key[threadIdx.x & 31];
+	const float d = __uint_as_float((unsigned)(k >> 32));
+	if (d < q.d2 || (d == q.d2 && (int)(unsigned)k < q.idx)) { q.d2 = d; q.idx = (int)(unsigned)k; }
+	q.bnd = fminf(q.bnd, q.d2);
+}
+__device__ __forceinline__ void hv_publish(HvBlock &hb, const PkLane &q) {
+	if (q.valid && q.idx >= 0) {
+		const unsigned long long k = ((unsigned long long)__float_as_uint(q.d2) << 32) | (unsigned)q.idx;
+		if (k < hb.key[threadIdx.x & 31]) atomicMin(&hb.key[threadIdx.x & 31], k);
+	}
+}
+
+#ifndef LS3D_HV_MINBLOCKS
+#define LS3D_HV_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kPkWarps * 32, LS3D_HV_MINBLOCKS) k_icp_match_heavy(const float *__restrict__ verts2, const unsigned *__restrict__ order, const uint2 *__restrict__ desc,
+	unsigned *__restrict__ pk_cost, const IcpGrid *__restrict__ grid, const unsigned *__restrict__ cell_start, const unsigned long long *__restrict__ nodes,
+	const unsigned long long *__restrict__ cellrec, const float4 *__restrict__ sorted, const float *__restrict__ verts1, SlotMap slotmap,
+	IcpState *state, int *__restrict__ nn_idx, float *__restrict__ nn_d2, unsigned *__restrict__ dbg, float one, unsigned *heavy_list, unsigned budget)
+{
+	extern __shared__ __align__(16) unsigned char hv_smem[];
+	HvBlock &hb = *reinterpret_cast<HvBlock *>(hv_smem);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	PkWarp &sh = hb.pkw[warp];
+	const IcpGrid g = *grid;
+	const int L = g.levels;
+	const float slack = 1e-3f * g.h;
+	const f32x2 one2 = pk2(one, one);
+	for (;;) {
+		__syncthreads();                                                 // the previous packet's shared state is no longer read
+		if (threadIdx.x == 0) {
+			// entry h of the queue: wait until the packet kernel has published it, or has run dry without doing so
+			const unsigned h = atomicAdd(&state->hq_head, 1u);
+			unsigned e = ld_volatile_u32(heavy_list + h);
+			for (unsigned spins = 0; e == kHvEmpty; spins++) {
+				if (ld_volatile_u32(&state->light_done)) { __threadfence(); e = ld_volatile_u32(heavy_list + h); break; }
+				if (spins > (1u << 21)) { atomicOr(&state->err, kErrScanSpin); break; }      // ~0.5 s: the protocol is broken; never hang the GPU
+				__nanosleep(200);
+				e = ld_volatile_u32(heavy_list + h);
+			}
+			if (e != kHvEmpty) st_volatile_u32(heavy_list + h, kHvEmpty);      // the queue is all-empty again for the next match stage
+			hb.pk_id = e != kHvEmpty ? (int)e : -1;
+			hb.n_front[0] = 1; hb.n_front[1] = 0; hb.front[0][0] = 0u;     // the root
+			hb.n_cells = 0; hb.next_cell = 0; hb.steps = 0; hb.scanned = 0;
+		}
+		if (threadIdx.x < 32) hb.key[threadIdx.x] = ~0ull;
+		__syncthreads();
+		const int pk = hb.pk_id;
+		if (pk < 0) break;
+		const uint2 pd = __ldg(desc + pk);
+		PkLane q;
+		unsigned mp, hx, hy, hz;
+		const int i = pk_load_lane(pd, order, const_cast<float *>(verts2), verts1, nn_idx, g, nullptr, q, mp, hx, hy, hz);
+		const unsigned vmask = __ballot_sync(kFull, q.valid);
+		PkPacket pkt;
+		pk_packet_box(q, vmask ? __ffs(vmask) - 1 : 0, pkt);
+		if (warp == 0) hv_publish(hb, q);
+		unsigned steps = 0, scanned = 0;
+		PkDone done;
+#pragma unroll
+		for (int d = 0; d < kPkDone; d++) done.m[d] = 0xffffffffu;
+		// ---- level-synchronous sweep: nodes of level t in front[cur], their surviving children into front[cur ^ 1] (cells: the cell list) ----
+		int cur = 0;
+		for (int t = L; t >= 1; t--) {
+			const unsigned nf = hb.n_front[cur];
+			for (unsigned f = (unsigned)warp; f < nf; f += kPkWarps) {
+				const unsigned ump = hb.front[cur][f];
+				const unsigned ux = compact3(ump), uy = compact3(ump >> 1), uz = compact3(ump >> 2);
+				hv_refresh(hb, q);
+				unsigned coarse;
+				unsigned exist = pk_load_children(g, cell_start, nodes, cellrec, sh, t, ux, uy, uz, ump, slack, pkt, INFINITY, coarse);
+				steps++;
+				if (__any_sync(kFull, q.valid && q.bnd == INFINITY)) {
+					// degenerate seeds only: a non-empty child box proves a bound (its farthest corner)
+					unsigned ex = exist;
+					while (ex) {
+						const unsigned c = (unsigned)__ffs(ex) - 1u;
+						ex &= ex - 1u;
+						const float4 lo = sh.lo[t - 1][c], hi = sh.hi[t - 1][c];
+						const float fx = fmaxf(q.rx - lo.x, hi.x - q.rx), fy = fmaxf(q.ry - lo.y, hi.y - q.ry), fz = fmaxf(q.rz - lo.z, hi.z - q.rz);
+						q.bnd = fminf(q.bnd, (fx * fx + fy * fy + fz * fz) * 1.00001f);
+					}
+				}
+				unsigned need = 0;
+				while (exist) {
+					const unsigned c = (unsigned)__ffs(exist) - 1u;
+					exist &= exist - 1u;
+					const float lb = pk_lb2(sh.lo[t - 1][c], sh.hi[t - 1][c], q.rx, q.ry, q.rz);
+					if (__any_sync(kFull, q.valid && lb <= q.bnd)) need |= 1u << c;
+				}
+				const unsigned nn = (unsigned)__popc(need);
+				if (!nn) continue;
+				unsigned base = 0;
+				if (lane == 0) base = t > 1 ? atomicAdd(&hb.n_front[cur ^ 1], nn) : atomicAdd(&hb.n_cells, nn);
+				base = __shfl_sync(kFull, base, 0);
+				const unsigned cap = t > 1 ? (unsigned)kHvFrontCap : (unsigned)kHvCellCap;
+				unsigned k = 0;
+				while (need) {
+					const unsigned c = (unsigned)__ffs(need) - 1u;
+					need &= need - 1u;
+					const unsigned cmp = (ump << 3) | c;
+					if (base + k < cap) {
+						if (t > 1) { if (lane == 0) hb.front[cur ^ 1][base + k] = cmp; }
+						else if (lane == 0) { hb.cells[base + k] = cmp; hb.cell_rng[base + k] = sh.rng[c]; hb.cell_lo[base + k] = sh.lo[0][c]; hb.cell_hi[base + k] = sh.hi[0][c]; }
+					} else if (t > 1) {
+						// no room in the frontier: this warp walks the child depth-first right here
+						const unsigned cx = (ux << 1) | (c & 1u), cy = (uy << 1) | ((c >> 1) & 1u), cz = (uz << 1) | (c >> 2);
+						pk_search(g, cell_start, nodes, cellrec, sorted, sh, t - 1, cx, cy, cz, cmp, q, pkt, slack, done, one2, steps, scanned, 0xffffffffu, false);
+						hv_publish(hb, q);
+						// the walk reuses sh.lo/hi of the levels below t only: this node's remaining children are not disturbed
+					} else {
+						const uint2 r = sh.rng[c];
+						scanned += r.y - r.x;
+						pk_scan(sorted, r.x, r.y, q, sh, one2);
+						hv_publish(hb, q);
+					}
+					k++;
+				}
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) { hb.n_front[cur] = 0; if (hb.n_front[cur ^ 1] > (unsigned)kHvFrontCap) hb.n_front[cur ^ 1] = kHvFrontCap; }
+			cur ^= 1;
+			__syncthreads();
+		}
+		// ---- the surviving cells, handed out one at a time ----
+		const unsigned nc = min(hb.n_cells, (unsigned)kHvCellCap);
+		for (;;) {
+			unsigned k = 0;
+			if (lane == 0) k = atomicAdd(&hb.next_cell, 1u);
+			k = __shfl_sync(kFull, k, 0);
+			if (k >= nc) break;
+			hv_refresh(hb, q);
+			const float lb = pk_lb2(hb.cell_lo[k], hb.cell_hi[k], q.rx, q.ry, q.rz);
+			if (!__any_sync(kFull, q.valid && lb <= q.bnd)) continue;
+			const uint2 r = hb.cell_rng[k];
+			steps++;
+			scanned += r.y - r.x;
+			pk_scan(sorted, r.x, r.y, q, sh, one2);
+			hv_publish(hb, q);
+		}
+		if (lane == 0) { atomicAdd(&hb.steps, steps); atomicAdd(&hb.scanned, scanned); }
+		__syncthreads();
+		if (warp == 0) {
+			hv_refresh(hb, q);
+			if (i >= 0) {
+				nn_commit(i, q.d2, q.valid ? q.idx : -1, slotmap, nn_idx, nn_d2);
+				if (dbg) { dbg[3 * (size_t)i] = hb.steps; dbg[3 * (size_t)i + 1] = hb.scanned; dbg[3 * (size_t)i + 2] = 1u; }
+			}
+			if (lane == 0) { pk_cost[pk] = max(hb.steps, budget + 1u); atomicAdd(&state->cls_n[0], 1u); }      // stays with the block-wide stage for the rest of the call
+		}
+	}
+	// the last block re-arms the queue for the next match stage
+	if (threadIdx.x == 0 && atomicAdd(&state->hq_done, 1u) == gridDim.x - 1) {
+		state->hq_done = 0;
+		state->hq_head = 0;
+		state->hq_n = 0;
+		state->light_done = 0;
 	}
 }
 
@@ -806,131 +1130,209 @@ __global__ void __launch_bounds__(256) k_icp_order_scatter(int i_begin, int n_sl
 // ------------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------------
+// the whole reduction of an iteration in one launch
+// ------------------------------------------------------------------------------------------------------
+// GetStandardDeviation + RejectOutlierMatches + the Kabsch sums + the solve step (icp.cpp:34-73, 138-168) over the dedupe slots,
+// written as the reference writes it: the MEAN of the matched squared distances first (rounded to fp32, divided in fp32 like
+// `mean /= data.size()`), then the sum of (double)(fp32(d - mean))^2, an fp32 division and square root — the two-pass form, not
+// E[x^2] - mean^2 — then the 2.5 sigma gate and the 16 correspondence sums.  The three sums are fp64 and order-fixed where the
+// reference runs fp32 accumulators down the match list in first-occurrence order; that order is a property of the reference's
+// serial loop and is not reproduced (tests/test_gpu_icp_fuzz.py bounds what it costs: nothing, in accepted counts).
+//
+// Canonical chunked reduction.  The target range is cut into C = red_chunks(n1) equal chunks; one block reduces one chunk in a
+// fixed thread order and every total is the chunk partials folded in chunk order.  Nothing in that depends on how many GPUs
+// share the work: with `world` ranks each owns a contiguous run of chunks (and of dedupe slots: the match kernels atomicMin
+// straight into the owner's slots over NVLink), stores its chunk partials into every rank's partial table with peer stores and
+// raises a flag there; every rank then folds the same C numbers in the same order, so poses are bit-identical on 1, 2, 4 or 8
+// GPUs and no collective library call sits between the three passes.  Grid barriers are arrival counters (all blocks are
+// resident: at most 2 per SM); spins are bounded and raise kErrScanSpin rather than hang.
+constexpr int kRedChunksMax = 296;
+__host__ __device__ __forceinline__ int red_chunks(int n1) { const int c = (n1 + 255) / 256; return c < 1 ? 1 : (c > kRedChunksMax ? kRedChunksMax : c); }
+__host__ __device__ __forceinline__ int red_chunk_size(int n1) { const int C = red_chunks(n1); return (n1 + C - 1) / C; }
+constexpr int kRedPhaseStride = kRedChunksMax * 16;     // doubles per pass in a partial table
+
+struct IcpPeers {
+	int world, rank;
+	double *part[8];           // every rank's partial table [3][kRedChunksMax][16] (part[rank] is the local one)
+	unsigned *flag[8];         // every rank's flag words [8]: flag[r][src] is raised on rank r by rank src
+	unsigned long long *slots[8];   // every rank's dedupe slots (only the owner's range of each is ever used)
+};
+
+__device__ __forceinline__ unsigned ld_volatile_sys_u32(const unsigned *p) { unsigned v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
+// all local blocks have stored (and fenced) their pass-`phase` partials; the last one to arrive raises this rank's flag on every peer
+__device__ __forceinline__ void red_arrive_wait(IcpState *st, unsigned nblocks, unsigned phase, unsigned epoch, const IcpPeers &pe, bool wait) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned arrived = atomicAdd(&st->red_bar, 1u) + 1u;
+		if (pe.world > 1 && arrived == phase * nblocks) {
+			__threadfence_system();
+			for (int r = 0; r < pe.world; r++) if (r != pe.rank) st_volatile_u32(pe.flag[r] + pe.rank, epoch * 4u + phase);
+		}
+		if (wait) {
+			unsigned spins = 0;
+			while (ld_volatile_u32(&st->red_bar) < phase * nblocks) if (++spins > (1u << 24)) { atomicOr(&st->err, kErrScanSpin); break; }
+			for (int r = 0; r < pe.world; r++) {
+				if (r == pe.rank) continue;
+				spins = 0;
+				while (ld_volatile_sys_u32(pe.flag[pe.rank] + r) < epoch * 4u + phase) if (++spins > (1u << 24)) { atomicOr(&st->err, kErrScanSpin); break; }
+			}
+			__threadfence();
+		}
+	}
+	__syncthreads();
+}
+
+// the block's NV values (already reduced over the block into smem[0..NV)) -> chunk c of pass `phase` in every rank's table
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(double *v, double *smem /* [8][NV] */, double *partials) {
+__device__ __forceinline__ void red_store(const double *smem, int c, int phase, const IcpPeers &pe) {
+	if (threadIdx.x < NV && c >= 0) {
+		const double v = smem[threadIdx.x];
+		for (int r = 0; r < pe.world; r++) pe.part[r][(size_t)(phase - 1) * kRedPhaseStride + (size_t)c * 16 + threadIdx.x] = v;
+		if (pe.world > 1) __threadfence_system(); else __threadfence();
+	}
+}
+
+// fixed-order block reduction of NV doubles per thread -> smem[0..NV) (256 threads)
+template <int NV>
+__device__ __forceinline__ void red_block(double *v, double *smem /* [8][NV] + [NV] */) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
 	for (int a = 0; a < NV; a++) {
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) v[a] += __shfl_xor_sync(kFull, v[a], o);
 	}
+	__syncthreads();                                  // smem may still be read from the previous pass
 	if (lane == 0) {
 #pragma unroll
-		for (int a = 0; a < NV; a++) smem[warp * NV + a] = v[a];
+		for (int a = 0; a < NV; a++) smem[NV + warp * NV + a] = v[a];
 	}
 	__syncthreads();
 	if (threadIdx.x < NV) {
 		double s = 0;
-		for (int w = 0; w < 8; w++) s += smem[w * NV + threadIdx.x];
-		partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+		for (int w = 0; w < 8; w++) s += smem[NV + w * NV + threadIdx.x];
+		smem[threadIdx.x] = s;
 	}
+	__syncthreads();
 }
 
-// last block to arrive sums the per-block partials in a fixed order -> out[0..NV); returns true in that block
+// the C chunk partials of pass `phase` folded in chunk order (every block, every rank: the same numbers in the same order);
+// executed by warp 0, result broadcast through smem[0..NV)
 template <int NV>
-__device__ __forceinline__ bool last_block_finish(const double *partials, double *out, unsigned *ticket) {
-	__shared__ bool s_last;
-	__threadfence();
-	__syncthreads();
-	if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-	__syncthreads();
-	if (!s_last) return false;
-	__threadfence();
-	// thread t = grp * NV + a sums value a of blocks grp, grp + kGroups, ...; then NV threads fold the groups in order:
-	// a fixed assignment, so the result does not depend on which block happened to arrive last
-	constexpr int kGroups = 256 / NV;          // 85 for NV = 3, 16 for NV = 16
-	const int a = threadIdx.x % NV, grp = threadIdx.x / NV;
-	double acc = 0;
-	if (grp < kGroups)
-		for (unsigned b = grp; b < gridDim.x; b += kGroups) acc += __ldcg(partials + (size_t)b * NV + a);
-	__shared__ double s_red[256];
-	s_red[threadIdx.x] = grp < kGroups ? acc : 0.0;
-	__syncthreads();
-	if (threadIdx.x < NV) {
-		double t = 0;
-		for (int gI = 0; gI < kGroups; gI++) t += s_red[gI * NV + threadIdx.x];
-		out[threadIdx.x] = t;
+__device__ __forceinline__ void red_total(const double *part_local, int C, int phase, double *smem) {
+	if (threadIdx.x < 32) {
+		const int lane = threadIdx.x;
+		double acc[NV];
+#pragma unroll
+		for (int a = 0; a < NV; a++) acc[a] = 0;
+		for (int c = lane; c < C; c += 32) {
+#pragma unroll
+			for (int a = 0; a < NV; a++) acc[a] += __ldcg(part_local + (size_t)(phase - 1) * kRedPhaseStride + (size_t)c * 16 + a);
+		}
+#pragma unroll
+		for (int a = 0; a < NV; a++) {
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(kFull, acc[a], o);
+			if (lane == 0) smem[a] = acc[a];
+		}
 	}
-	if (threadIdx.x == 0) *ticket = 0;
 	__syncthreads();
-	return true;
 }
 
-// count, sum d2, sum d2^2 over the matched slots of [j_begin, j_end)
-constexpr unsigned kPkHeavySteps = 32;      // packets that took more steps than this go first next iteration
-
-__global__ void __launch_bounds__(256) k_icp_stats(const unsigned long long *__restrict__ slots, int j_begin, int j_end,
-	double *partials, double *stats_buf, IcpState *state, const unsigned *__restrict__ pk_cost, unsigned *__restrict__ sched)
+__global__ void __launch_bounds__(256, 2) k_icp_reduce(unsigned long long *__restrict__ slots, int n1, int c_begin, const float *__restrict__ verts1, const float *__restrict__ verts2,
+	IcpState *state, Ls3dIcpTrace *trace, int trace_idx, const unsigned *__restrict__ pk_cost, unsigned *__restrict__ sched, unsigned budget, IcpPeers pe)
 {
-	__shared__ double smem[8 * 3];
-	// next iteration's packet schedule (the match stage of this iteration is complete): heavy packets from the front, the rest from the back
+	__shared__ double smem[16 + 8 * 16];
+	asm volatile("griddepcontrol.launch_dependents;");                // the next match kernel may become resident (it waits for us to complete)
+	asm volatile("griddepcontrol.wait;" ::: "memory");                // the match stage (packet + block-wide kernels) is complete
+	const int C = red_chunks(n1), S = red_chunk_size(n1);
+	const int c = c_begin < 0 ? -1 : c_begin + (int)blockIdx.x;      // -1: this rank owns no chunk (fewer chunks than ranks); it still takes part in the exchanges
+	const unsigned nblocks = gridDim.x;
+	const unsigned epoch = ld_volatile_u32(&state->red_epoch);
+	double *part_local = pe.part[pe.rank];
+	// next iteration's packet schedule (the match stage of this iteration is complete): most expensive class first, so the kernel's
+	// tail is one cheap packet per warp instead of whatever happened to be drawn last
 	{
 		const unsigned np = state->n_packets;
+		unsigned off[8];
+		unsigned run = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) { off[k] = run; run += state->cls_n[k]; }
 		for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
-			if (pk_cost[p] > kPkHeavySteps) sched[atomicAdd(&state->n_heavy, 1u)] = p;
-			else sched[np - 1u - atomicAdd(&state->n_light, 1u)] = p;
+			const unsigned k = pk_cost_class(pk_cost[p], budget);
+			unsigned o = 0;
+#pragma unroll
+			for (int kk = 0; kk < 8; kk++) if (k == (unsigned)kk) o = off[kk];
+			const unsigned pos = o + atomicAdd(&state->cls_fill[k], 1u);
+			if (pos < np) sched[pos] = p;
 		}
-		if (blockIdx.x == 0 && threadIdx.x == 0) state->sched_valid = 1;
+		if (blockIdx.x == 0 && threadIdx.x == 0) state->sched_valid = run == np ? 1u : 0u;     // every packet was classed exactly once
 	}
-	double v[3] = {0, 0, 0};
-	for (int j = j_begin + blockIdx.x * blockDim.x + threadIdx.x; j < j_end; j += gridDim.x * blockDim.x) {
-		const unsigned long long key = slots[j];
-		if (key != kSlotEmpty) {
-			const double d = (double)__uint_as_float((unsigned)(key >> 32));
-			v[0] += 1.0; v[1] += d; v[2] += d * d;
+	// every rank's match kernels have finished (their atomicMin's into our slots are performed) before the slots are read
+	if (pe.world > 1) {
+		if (threadIdx.x == 0) {
+			if (blockIdx.x == 0) { __threadfence_system(); for (int r = 0; r < pe.world; r++) if (r != pe.rank) st_volatile_u32(pe.flag[r] + pe.rank, epoch * 4u); }
+			for (int r = 0; r < pe.world; r++) {
+				if (r == pe.rank) continue;
+				unsigned spins = 0;
+				while (ld_volatile_sys_u32(pe.flag[pe.rank] + r) < epoch * 4u) if (++spins > (1u << 24)) { atomicOr(&state->err, kErrScanSpin); break; }
+			}
+			__threadfence();
 		}
+		__syncthreads();
 	}
-	block_reduce_store<3>(v, smem, partials);
-	last_block_finish<3>(partials, stats_buf, &state->ticket_stats);
-}
+	const int j0 = c < 0 ? 0 : min(n1, c * S), j1 = c < 0 ? 0 : min(n1, j0 + S);
 
-// the solve step: (T, Rk) from the 16 sums -> state->xf, pose accumulation (icp.cpp:167-168), trace.  One thread.
-__device__ void icp_solve_step(const double *sums, IcpState *state, Ls3dIcpTrace *trace, int trace_idx) {
-	float T[3], Rk[9];
-	const bool solved = icp_solve(sums, T, Rk);
-	for (int a = 0; a < 3; a++) state->xf[a] = T[a];
-	for (int a = 0; a < 9; a++) state->xf[3 + a] = Rk[a];
-	icp_accumulate(state, T, Rk, solved, trace, trace_idx, sums);
-}
+	// the chunk's slots are read once: a thread's first kRedCache keys stay in registers for all three passes (a 2 x 213 k pair has
+	// 3 per thread), what lies beyond is re-read from L2
+	constexpr int kRedCache = 4;
+	unsigned long long kc[kRedCache];
+#pragma unroll
+	for (int u = 0; u < kRedCache; u++) { const int j = j0 + (int)threadIdx.x + 256 * u; kc[u] = j < j1 ? __ldcg(slots + j) : kSlotEmpty; }
 
-__global__ void k_icp_solve(const double *sums, IcpState *state, Ls3dIcpTrace *trace, int trace_idx) { icp_solve_step(sums, state, trace, trace_idx); }
-
-// 2.5 sigma gate (icp.cpp:34-73) + the 16 correspondence sums over [j_begin, j_end); every slot is reset.
-//   sums: [0] accepted count, [1..3] sum (p - q) (fp32 differences), [4..6] sum p, [7..15] sum q_a p_b
-// solve_here: the last block also runs the solve step (single GPU; with several ranks the sums are all-reduced first).
-__global__ void __launch_bounds__(256) k_icp_sums(unsigned long long *__restrict__ slots, int n1, int j_begin, int j_end,
-	const float *__restrict__ verts1, const float *__restrict__ verts2, const double *__restrict__ stats_buf,
-	double *partials, double *sums_buf, IcpState *state, Ls3dIcpTrace *trace, int trace_idx, int solve_here)
-{
-	__shared__ double smem[8 * 16];
-	__shared__ float s_thr;
-	if (threadIdx.x == 0) {
-		const double cnt = stats_buf[0];
-		float sigma = 0.0f;
-		if (cnt >= 0.5) {
-			const double mean = stats_buf[1] / cnt;
-			double var = stats_buf[2] / cnt - mean * mean;
-			if (!(var > 0)) var = 0;
-			sigma = (float)sqrt(var);
-		}
-		s_thr = __fmul_rn(2.5f, sigma);
-		if (blockIdx.x == 0 && trace && trace_idx >= 0 && trace_idx < kTraceCap) {
-			trace[trace_idx].n_matched = (int)(cnt + 0.5);
-			trace[trace_idx].sigma = sigma;
-		}
-	}
-	__syncthreads();
-	const float thr = s_thr;
+	// ---- pass 1: matched count and sum of d2 -> mean ----
 	double v[16];
 #pragma unroll
 	for (int a = 0; a < 16; a++) v[a] = 0;
-	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
-		const unsigned long long key = slots[j];
-		if (key == kSlotEmpty) continue;
+#pragma unroll
+	for (int u = 0; u < kRedCache; u++) if (kc[u] != kSlotEmpty) { v[0] += 1.0; v[1] += (double)__uint_as_float((unsigned)(kc[u] >> 32)); }
+	for (int j = j0 + (int)threadIdx.x + 256 * kRedCache; j < j1; j += 256) {
+		const unsigned long long key = __ldcg(slots + j);
+		if (key != kSlotEmpty) { v[0] += 1.0; v[1] += (double)__uint_as_float((unsigned)(key >> 32)); }
+	}
+	red_block<2>(v, smem);
+	red_store<2>(smem, c, 1, pe);
+	red_arrive_wait(state, nblocks, 1, epoch, pe, true);
+	red_total<2>(part_local, C, 1, smem);
+	const double cnt = smem[0];
+	const float nf = (float)cnt;                                     // (float)data.size()
+	const float meanf = cnt >= 0.5 ? __fdiv_rn((float)smem[1], nf) : 0.0f;
+
+	// ---- pass 2: sum of squared deviations -> sigma (icp.cpp:43-51) ----
+	v[0] = 0;
+#pragma unroll
+	for (int u = 0; u < kRedCache; u++) if (kc[u] != kSlotEmpty) { const double dv = (double)__fsub_rn(__uint_as_float((unsigned)(kc[u] >> 32)), meanf); v[0] += dv * dv; }
+	for (int j = j0 + (int)threadIdx.x + 256 * kRedCache; j < j1; j += 256) {
+		const unsigned long long key = __ldcg(slots + j);
+		if (key != kSlotEmpty) { const double dv = (double)__fsub_rn(__uint_as_float((unsigned)(key >> 32)), meanf); v[0] += dv * dv; }
+	}
+	red_block<1>(v, smem);
+	red_store<1>(smem, c, 2, pe);
+	red_arrive_wait(state, nblocks, 2, epoch, pe, true);
+	red_total<1>(part_local, C, 2, smem);
+	const float sigma = cnt >= 0.5 ? sqrtf(__fdiv_rn((float)smem[0], nf)) : 0.0f;
+	const float thr = __fmul_rn(2.5f, sigma);
+
+	// ---- pass 3: 2.5 sigma gate + the 16 correspondence sums; every slot of the chunk is reset ----
+	//   sums: [0] accepted count, [1..3] sum (p - q) (fp32 differences), [4..6] sum p, [7..15] sum q_a p_b
+#pragma unroll
+	for (int a = 0; a < 16; a++) v[a] = 0;
+	auto take = [&](int j, unsigned long long key) {
+		if (key == kSlotEmpty) return;
 		slots[j] = kSlotEmpty;
-		if (j < j_begin || j >= j_end) continue;
 		const float d2 = __uint_as_float((unsigned)(key >> 32));
-		if (d2 > thr) continue;
+		if (d2 > thr) return;
 		const unsigned i = 0xFFFFFFFFu - (unsigned)key;
 		const float px = verts1[3 * (size_t)j], py = verts1[3 * (size_t)j + 1], pz = verts1[3 * (size_t)j + 2];
 		const float qx = verts2[3 * (size_t)i], qy = verts2[3 * (size_t)i + 1], qz = verts2[3 * (size_t)i + 2];
@@ -940,10 +1342,45 @@ __global__ void __launch_bounds__(256) k_icp_sums(unsigned long long *__restrict
 		v[7] += (double)qx * (double)px; v[8] += (double)qx * (double)py; v[9] += (double)qx * (double)pz;
 		v[10] += (double)qy * (double)px; v[11] += (double)qy * (double)py; v[12] += (double)qy * (double)pz;
 		v[13] += (double)qz * (double)px; v[14] += (double)qz * (double)py; v[15] += (double)qz * (double)pz;
+	};
+#pragma unroll
+	for (int u = 0; u < kRedCache; u++) take(j0 + (int)threadIdx.x + 256 * u, kc[u]);
+	for (int j = j0 + (int)threadIdx.x + 256 * kRedCache; j < j1; j += 256) take(j, __ldcg(slots + j));
+	red_block<16>(v, smem);
+	red_store<16>(smem, c, 3, pe);
+	red_arrive_wait(state, nblocks, 3, epoch, pe, blockIdx.x == 0);
+	if (blockIdx.x != 0) return;
+	// ---- block 0 of every rank: fold, solve, accumulate (identical arithmetic on identical numbers everywhere) ----
+	red_total<16>(part_local, C, 3, smem);
+	if (threadIdx.x == 0) {
+		if (trace && trace_idx >= 0 && trace_idx < kTraceCap) { trace[trace_idx].n_matched = (int)(cnt + 0.5); trace[trace_idx].sigma = sigma; }
+		double sums[16];
+		for (int a = 0; a < 16; a++) sums[a] = smem[a];
+		float T[3], Rk[9];
+		const bool solved = icp_solve(sums, T, Rk);
+		for (int a = 0; a < 3; a++) state->xf[a] = T[a];
+		for (int a = 0; a < 9; a++) state->xf[3 + a] = Rk[a];
+		icp_accumulate(state, T, Rk, solved, trace, trace_idx, sums);
+		for (int k = 0; k < 8; k++) { state->cls_n[k] = 0; state->cls_fill[k] = 0; }
+		state->red_bar = 0;
+		state->red_epoch = epoch + 1u;
 	}
-	block_reduce_store<16>(v, smem, partials);
-	const bool last = last_block_finish<16>(partials, sums_buf, &state->ticket_sums);
-	if (last && solve_here && threadIdx.x == 0) icp_solve_step(sums_buf, state, trace, trace_idx);
+}
+
+// cross-rank rendezvous (sharded ICP, one block): every rank has reached this point of its stream.  ls3d_icp_set_source ends with
+// it, so no rank's first match kernel can put keys into a peer's dedupe slots before that peer has re-initialised them.
+__global__ void k_icp_peer_sync(IcpState *state, IcpPeers pe) {
+	if (threadIdx.x != 0 || pe.world <= 1) return;
+	const unsigned epoch = ld_volatile_u32(&state->red_epoch);
+	__threadfence_system();
+	for (int r = 0; r < pe.world; r++) if (r != pe.rank) st_volatile_u32(pe.flag[r] + pe.rank, epoch * 4u);
+	for (int r = 0; r < pe.world; r++) {
+		if (r == pe.rank) continue;
+		unsigned spins = 0;
+		while (ld_volatile_sys_u32(pe.flag[pe.rank] + r) < epoch * 4u) if (++spins > (1u << 26)) { atomicOr(&state->err, kErrScanSpin); break; }
+	}
+	__threadfence();
+	state->red_epoch = epoch + 1u;
 }
 
 struct Pose12 { float v[12]; };     // R[9] then t[3], passed by value (no staging buffer to race on)
@@ -961,6 +1398,9 @@ __global__ void k_icp_init_state(IcpState *st, Pose12 p) {
 	st->n_heavy = 0;
 	st->n_light = 0;
 	st->sched_valid = 0;
+	st->hq_n = 0; st->hq_head = 0; st->hq_done = 0; st->light_done = 0;
+	for (int i = 0; i < 8; i++) { st->cls_n[i] = 0; st->cls_fill[i] = 0; }
+	st->red_bar = 0;                                            // red_epoch is deliberately left alone
 	for (int i = 0; i < 12; i++) st->xf[i] = (i == 3 || i == 7 || i == 11) ? 1.0f : 0.0f;
 }
 
@@ -977,14 +1417,18 @@ struct Ls3dIcp {
 	int G = 0, levels = 0;
 	int iter = 0;                 // iterations whose match stage has been enqueued
 	bool pending = false;         // sums of the last iteration not yet applied
-	bool solved = false;          // ... and already turned into (T, Rk) by the solve step
 	unsigned *dbg = nullptr;      // optional per-query work statistics (3 u32 per source point), see ls3d_icp_set_debug
 	int sm_count = 148;
 	const float *d_verts1 = nullptr;
 	float *d_verts2 = nullptr;
-	DevBuf grid, box, state, cell_start, nodes, cellbox, cell_of, rank_of, sorted, slots, partials, stats_buf, sums_buf, scan_status, nn_idx, nn_d2, work, trace, small;
-	DevBuf src_start, src_cell, src_rank, pk_desc, pk_cost, pk_sched;   // Morton ordering of the source slice (work = the order itself), its packets, their cost and schedule
+	DevBuf grid, box, state, cell_start, nodes, cellbox, cell_of, rank_of, sorted, slots, scan_status, nn_idx, nn_d2, work, trace, small;
+	DevBuf src_start, src_cell, src_rank, pk_desc, pk_cost, pk_sched, pk_heavy;   // Morton ordering of the source slice (work = the order itself), its packets, their cost and schedule
 	bool order_valid = false;
+	DevBuf red_part, red_flag;    // k_icp_reduce: partial table [3][kRedChunksMax][16] f64 and cross-rank flag words (both mapped by the peers when sharded)
+	int world = 1, rank = 0;      // sharded ICP (ls3d_icp_set_peers): ranks sharing this call, and which one this is
+	double *peer_part[8] = {};
+	unsigned *peer_flag[8] = {};
+	unsigned long long *peer_slots[8] = {};
 	DevBuf own_v1, own_v2;        // device copies for the host-buffer API
 	cudaStream_t up = nullptr;    // host-buffer API: the source cloud uploads here while the target is built
 	cudaEvent_t ev_up = nullptr, ev_go = nullptr;
@@ -998,8 +1442,8 @@ struct Ls3dIcp {
 
 static void icp_free(Ls3dIcp *c) {
 	if (!c) return;
-	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->nodes, &c->cellbox, &c->cell_of, &c->rank_of, &c->sorted, &c->slots, &c->partials, &c->stats_buf,
-		&c->sums_buf, &c->scan_status, &c->nn_idx, &c->nn_d2, &c->work, &c->trace, &c->small, &c->own_v1, &c->own_v2, &c->src_start, &c->src_cell, &c->src_rank, &c->pk_desc, &c->pk_cost, &c->pk_sched};
+	DevBuf *bufs[] = {&c->grid, &c->box, &c->state, &c->cell_start, &c->nodes, &c->cellbox, &c->cell_of, &c->rank_of, &c->sorted, &c->slots,
+		&c->scan_status, &c->nn_idx, &c->nn_d2, &c->work, &c->trace, &c->small, &c->own_v1, &c->own_v2, &c->src_start, &c->src_cell, &c->src_rank, &c->pk_desc, &c->pk_cost, &c->pk_sched, &c->pk_heavy, &c->red_part, &c->red_flag};
 	for (DevBuf *b : bufs) b->release();
 	if (c->pin) cudaFreeHost(c->pin);
 	if (c->graph) cudaGraphExecDestroy(c->graph);
@@ -1022,17 +1466,17 @@ extern "C" Ls3dIcp *ls3d_icp_create(int n1_max, int n2_max) {
 	const size_t n1 = (size_t)n1_max, n2 = (size_t)std::max(n2_max, 1);
 	bool ok = c->grid.reserve(sizeof(IcpGrid), "alloc grid") && c->box.reserve(sizeof(IcpBox), "alloc bbox") && c->state.reserve(sizeof(IcpState), "alloc state") &&
 		c->cell_of.reserve(4 * n1, "alloc cells") && c->rank_of.reserve(4 * n1, "alloc ranks") && c->sorted.reserve(16 * n1, "alloc sorted target") &&
-		c->slots.reserve(8 * n1, "alloc slots") && c->partials.reserve(sizeof(double) * 16 * kRedBlocks, "alloc partials") &&
-		c->stats_buf.reserve(sizeof(double) * 4, "alloc stats") && c->sums_buf.reserve(sizeof(double) * 16, "alloc sums") &&
+		c->slots.reserve(8 * n1, "alloc slots") &&
 		c->nn_idx.reserve(4 * n2, "alloc nn index") && c->nn_d2.reserve(4 * n2, "alloc nn dist") && c->work.reserve(4 * n2 + 256, "alloc work list") &&
 		c->trace.reserve(sizeof(Ls3dIcpTrace) * kTraceCap, "alloc trace") && c->small.reserve(256, "alloc small") &&
-		c->src_cell.reserve(4 * n2, "alloc source cells") && c->src_rank.reserve(4 * n2, "alloc source ranks");
+		c->src_cell.reserve(4 * n2, "alloc source cells") && c->src_rank.reserve(4 * n2, "alloc source ranks") &&
+		c->red_part.reserve(sizeof(double) * 3 * kRedPhaseStride, "alloc reduction partials") && c->red_flag.reserve(256, "alloc reduction flags");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin, 256, cudaHostAllocDefault), "alloc pinned read-back");
 	if (!ok) { icp_free(c); return nullptr; }
-	cudaMemset(c->stats_buf.p, 0, sizeof(double) * 4);
-	cudaMemset(c->sums_buf.p, 0, sizeof(double) * 16);
 	cudaMemset(c->trace.p, 0, sizeof(Ls3dIcpTrace) * kTraceCap);
 	cudaMemset(c->state.p, 0, sizeof(IcpState));
+	cudaMemset(c->red_flag.p, 0, 256);
+	cudaMemset(c->red_part.p, 0, sizeof(double) * 3 * kRedPhaseStride);
 	return c;
 }
 
@@ -1059,7 +1503,8 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 		!c->src_start.reserve(4 * (cells + 8), "alloc source cell starts") ||
 		!c->pk_desc.reserve(8 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet table") ||
 		!c->pk_cost.reserve(4 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet costs") ||
-		!c->pk_sched.reserve(4 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet schedule")) return -1;
+		!c->pk_sched.reserve(4 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc packet schedule") ||
+		!c->pk_heavy.reserve(4 * ((size_t)c->n2_max / 32 + (cells >> (3 * kPkRunLevel)) + 8), "alloc heavy packet queue")) return -1;
 	IcpBox hb;
 	for (int a = 0; a < 3; a++) { hb.mn[a] = 0xffffffffu; hb.mx[a] = 0u; }
 	bool ok = cuda_ok(cudaMemcpyAsync(c->box.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, st), "init bbox") &&
@@ -1090,9 +1535,12 @@ extern "C" int ls3d_icp_set_target(Ls3dIcp *c, const void *d_verts1, int n1, voi
 		launches++;
 	}
 	k_fill_u64<<<nb, 256, 0, st>>>(c->slots.as<unsigned long long>(), n1, kSlotEmpty);
+	if (!cuda_ok(cudaMemsetAsync(c->pk_heavy.p, 0xff, c->pk_heavy.cap, st), "clear heavy packet queue")) return -1;      // all entries kHvEmpty
 	count_launch(launches);
 	return cuda_ok(cudaGetLastError(), "target grid kernels") ? 0 : -1;
 }
+
+static IcpPeers icp_peers(Ls3dIcp *c);
 
 extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_begin, int i_end, const float *R0, const float *t0, void *stream) {
 	if (!c || (!d_verts2 && n2 > 0) || !R0 || !t0) { set_error("ls3d_icp_set_source: null argument"); return -1; }
@@ -1111,6 +1559,7 @@ extern "C" int ls3d_icp_set_source(Ls3dIcp *c, void *d_verts2, int n2, int i_beg
 	memcpy(pose.v + 9, t0, 3 * sizeof(float));
 	k_icp_init_state<<<1, 1, 0, st>>>(c->state.as<IcpState>(), pose);
 	count_launch(1);
+	if (c->world > 1) { k_icp_peer_sync<<<1, 32, 0, st>>>(c->state.as<IcpState>(), icp_peers(c)); count_launch(1); }
 	return cuda_ok(cudaGetLastError(), "k_icp_init_state") ? 0 : -1;
 }
 
@@ -1140,16 +1589,104 @@ static int icp_build_order(Ls3dIcp *c, cudaStream_t st) {
 	return 4;
 }
 
+static SlotMap icp_slot_map(const Ls3dIcp *c) {
+	SlotMap m = {};
+	m.world = c->world;
+	m.chunk = std::max(1, red_chunk_size(c->n1));
+	m.per = std::max(1, (red_chunks(c->n1) + c->world - 1) / c->world);
+	if (c->world > 1) for (int r = 0; r < c->world; r++) m.ptr[r] = c->peer_slots[r];
+	else m.ptr[0] = const_cast<Ls3dIcp *>(c)->slots.as<unsigned long long>();
+	return m;
+}
+
+static IcpPeers icp_peers(Ls3dIcp *c) {
+	IcpPeers pe = {};
+	pe.world = c->world;
+	pe.rank = c->rank;
+	if (c->world > 1) {
+		for (int r = 0; r < c->world; r++) { pe.part[r] = c->peer_part[r]; pe.flag[r] = c->peer_flag[r]; pe.slots[r] = c->peer_slots[r]; }
+	} else {
+		pe.part[0] = c->red_part.as<double>(); pe.flag[0] = c->red_flag.as<unsigned>(); pe.slots[0] = c->slots.as<unsigned long long>();
+	}
+	return pe;
+}
+
+// Sharded ICP: `world` ranks (one process per GPU) run the same call on replicated clouds, each searching its slice of the source
+// (ls3d_icp_set_source's [i_begin, i_end)) and owning a contiguous run of the target's reduction chunks and dedupe slots.
+// slots / part / flag: for every rank r the device pointer, valid in THIS process, of rank r's ls3d_icp_slots / ls3d_icp_red_part /
+// ls3d_icp_red_flag (CUDA-IPC mappings of the peers' allocations; entry `rank` is the local one).  world = 1 switches sharding off.
+extern "C" int ls3d_icp_set_peers(Ls3dIcp *c, int world, int rank, void *const *slots, void *const *part, void *const *flag) {
+	if (!c) { set_error("ls3d_icp_set_peers: null context"); return -1; }
+	if (world <= 1) { c->world = 1; c->rank = 0; return 0; }
+	if (world > 8 || rank < 0 || rank >= world || !slots || !part || !flag) { set_error("ls3d_icp_set_peers: world must be 1..8, rank inside it, pointer tables non-null"); return -1; }
+	for (int r = 0; r < world; r++) {
+		if (!slots[r] || !part[r] || !flag[r]) { set_error("ls3d_icp_set_peers: missing mapping for rank %d", r); return -1; }
+		c->peer_slots[r] = (unsigned long long *)slots[r]; c->peer_part[r] = (double *)part[r]; c->peer_flag[r] = (unsigned *)flag[r];
+	}
+	if (c->peer_slots[rank] != c->slots.as<unsigned long long>() || c->peer_part[rank] != c->red_part.as<double>() || c->peer_flag[rank] != c->red_flag.as<unsigned>()) {
+		set_error("ls3d_icp_set_peers: entry %d must be this context's own buffers", rank); return -1;
+	}
+	c->world = world;
+	c->rank = rank;
+	if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+	return 0;
+}
+extern "C" double *ls3d_icp_red_part(Ls3dIcp *c) { return c ? c->red_part.as<double>() : nullptr; }
+extern "C" unsigned *ls3d_icp_red_flag(Ls3dIcp *c) { return c ? c->red_flag.as<unsigned>() : nullptr; }
+
+static bool icp_use_pdl() {
+	static const int v = getenv("LS3D_ICP_PDL") ? atoi(getenv("LS3D_ICP_PDL")) : 1;
+	return v != 0;
+}
+
+// kernel launch with the programmatic-stream-serialization attribute: the kernel may become resident while its predecessor in the
+// stream is still running; it orders itself with griddepcontrol.wait (or, for the block-wide match stage, with its queue protocol)
+template <typename... KArgs, typename... Args>
+static bool launch_dep(const char *what, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(block);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = icp_use_pdl() ? 1 : 0;
+	return cuda_ok(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...), what);
+}
+
+static unsigned icp_budget() {
+	static const unsigned budget = getenv("LS3D_PK_BUDGET") ? (unsigned)atoi(getenv("LS3D_PK_BUDGET")) : kPkBudget;      // tuning aid
+	return budget;
+}
+
 static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) {
 	const int n_slice = c->i_end - c->i_begin;
 	if (search && n_slice > 0) {
 		if (!c->order_valid && icp_build_order(c, st) < 0) return -1;
 		const int n_packets = (n_slice + 31) / 32;        // at least; the exact number (node-bounded runs) lives on the device
-		const int nb = std::max(1, std::min((n_packets + kPkWarps - 1) / kPkWarps + 8, c->sm_count * 6));
-		k_icp_match_packet<<<nb, kPkWarps * 32, 0, st>>>(c->d_verts2, c->i_begin, c->i_end, apply, c->work.as<unsigned>(), c->pk_desc.as<uint2>(), c->pk_sched.as<unsigned>(), c->pk_cost.as<unsigned>(),
-			c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(), c->d_verts1,
-			c->slots.as<unsigned long long>(), c->state.as<IcpState>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg);
-		count_launch(1);
+		// persistent grids: every block is resident from the start (the block-wide stage is a programmatic dependent launch that may
+		// only begin once every block of the packet kernel has started)
+		static int occ_light = 0, occ_heavy = 0;
+		if (!occ_light) {
+			if (!cuda_ok(cudaFuncSetAttribute(k_icp_match_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HvBlock)), "heavy stage shared memory") ||
+				!cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_light, k_icp_match_packet, kPkWarps * 32, 0), "occupancy query") ||
+				!cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_heavy, k_icp_match_heavy, kPkWarps * 32, sizeof(HvBlock)), "occupancy query")) return -1;
+			occ_light = std::max(occ_light, 1);
+			occ_heavy = std::max(occ_heavy, 1);
+		}
+		const int nb = std::max(1, std::min((n_packets + kPkWarps - 1) / kPkWarps + 8, c->sm_count * occ_light));
+		const unsigned budget = icp_budget();
+		if (!launch_dep("launch packet match", k_icp_match_packet, (unsigned)nb, kPkWarps * 32, 0, st, c->d_verts2, c->i_begin, c->i_end, apply, c->work.as<unsigned>(), c->pk_desc.as<uint2>(),
+			c->pk_sched.as<unsigned>(), c->pk_cost.as<unsigned>(), c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(), c->cellbox.as<unsigned long long>(),
+			c->sorted.as<float4>(), c->d_verts1, icp_slot_map(c), c->state.as<IcpState>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg, 1.0f, c->pk_heavy.as<unsigned>(), budget)) return -1;
+		// the packets the warps give up on: one block each, consumed while the packet kernel's tail is still running
+		if (!launch_dep("launch heavy stage", k_icp_match_heavy, (unsigned)std::max(1, std::min(n_packets, c->sm_count * occ_heavy)), kPkWarps * 32, sizeof(HvBlock), st,
+			c->d_verts2, c->work.as<unsigned>(), c->pk_desc.as<uint2>(), c->pk_cost.as<unsigned>(), c->grid.as<IcpGrid>(), c->cell_start.as<unsigned>(), c->nodes.as<unsigned long long>(),
+			c->cellbox.as<unsigned long long>(), c->sorted.as<float4>(), c->d_verts1, icp_slot_map(c), c->state.as<IcpState>(), c->nn_idx.as<int>(), c->nn_d2.as<float>(), c->dbg, 1.0f,
+			c->pk_heavy.as<unsigned>(), budget)) return -1;
+		count_launch(2);
 	}
 	// the points the packet kernel did not touch: everything when there is no search, otherwise what lies outside the slice
 	int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
@@ -1167,50 +1704,29 @@ static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) 
 
 extern "C" int ls3d_icp_match(Ls3dIcp *c, void *stream) {
 	if (!c || !c->d_verts1 || !c->d_verts2) { set_error("ls3d_icp_match: target/source not set"); return -1; }
-	if (c->pending && !c->solved && ls3d_icp_solve(c, stream) < 0) return -1;
 	const int r = icp_launch_match(c, c->pending ? 1 : 0, 1, (cudaStream_t)stream);
 	c->pending = false;
 	c->iter++;
 	return r;
 }
 
-extern "C" int ls3d_icp_stats(Ls3dIcp *c, int j_begin, int j_end, void *stream) {
-	if (!c || !c->d_verts1) { set_error("ls3d_icp_stats: target not set"); return -1; }
-	if (j_begin < 0) j_begin = 0;
-	if (j_end > c->n1 || j_end < 0) j_end = c->n1;
-	k_icp_stats<<<std::min(kRedBlocks, std::max(1, (c->n1 + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(c->slots.as<unsigned long long>(), j_begin, j_end,
-		c->partials.as<double>(), c->stats_buf.as<double>(), c->state.as<IcpState>(), c->pk_cost.as<unsigned>(), c->pk_sched.as<unsigned>());
-	count_launch(1);
-	return cuda_ok(cudaGetLastError(), "k_icp_stats") ? 0 : -1;
-}
-
-extern "C" int ls3d_icp_sums(Ls3dIcp *c, int j_begin, int j_end, void *stream) {
-	if (!c || !c->d_verts1 || !c->d_verts2) { set_error("ls3d_icp_sums: target/source not set"); return -1; }
-	if (j_begin < 0) j_begin = 0;
-	if (j_end > c->n1 || j_end < 0) j_end = c->n1;
-	const int solve_here = (j_begin == 0 && j_end == c->n1) ? 1 : 0;       // a partial range means the sums still have to be all-reduced
-	k_icp_sums<<<std::min(kRedBlocks, std::max(1, (c->n1 + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(c->slots.as<unsigned long long>(), c->n1, j_begin, j_end,
-		c->d_verts1, c->d_verts2, c->stats_buf.as<double>(), c->partials.as<double>(), c->sums_buf.as<double>(), c->state.as<IcpState>(),
-		c->trace.as<Ls3dIcpTrace>(), c->iter - 1, solve_here);
+// mean / sigma / gate / correspondence sums / solve of the iteration just matched, in one launch (k_icp_reduce); with peers set, the
+// ranks exchange their chunk partials inside the kernel
+extern "C" int ls3d_icp_reduce(Ls3dIcp *c, void *stream) {
+	if (!c || !c->d_verts1 || !c->d_verts2) { set_error("ls3d_icp_reduce: target/source not set"); return -1; }
+	const int C = red_chunks(c->n1);
+	const int per = (C + c->world - 1) / c->world;
+	const int c0 = std::min(C, c->rank * per), c1 = std::min(C, (c->rank + 1) * per);
+	if (!launch_dep("launch reduction", k_icp_reduce, (unsigned)std::max(1, c1 - c0), 256u, 0, (cudaStream_t)stream, c->slots.as<unsigned long long>(), c->n1, c1 > c0 ? c0 : -1, c->d_verts1,
+		(const float *)c->d_verts2, c->state.as<IcpState>(), c->trace.as<Ls3dIcpTrace>(), c->iter - 1, c->pk_cost.as<unsigned>(), c->pk_sched.as<unsigned>(), icp_budget(), icp_peers(c))) return -1;
 	count_launch(1);
 	c->pending = true;
-	c->solved = solve_here != 0;
-	return cuda_ok(cudaGetLastError(), "k_icp_sums") ? 0 : -1;
-}
-
-extern "C" int ls3d_icp_solve(Ls3dIcp *c, void *stream) {
-	if (!c) { set_error("ls3d_icp_solve: null context"); return -1; }
-	if (!c->pending || c->solved) return 0;
-	k_icp_solve<<<1, 1, 0, (cudaStream_t)stream>>>(c->sums_buf.as<double>(), c->state.as<IcpState>(), c->trace.as<Ls3dIcpTrace>(), c->iter - 1);
-	count_launch(1);
-	c->solved = true;
-	return cuda_ok(cudaGetLastError(), "k_icp_solve") ? 0 : -1;
+	return cuda_ok(cudaGetLastError(), "k_icp_reduce") ? 0 : -1;
 }
 
 extern "C" int ls3d_icp_finish(Ls3dIcp *c, void *stream) {
 	if (!c) { set_error("ls3d_icp_finish: null context"); return -1; }
 	if (!c->pending) return 0;
-	if (!c->solved && ls3d_icp_solve(c, stream) < 0) return -1;
 	const int r = icp_launch_match(c, 1, 0, (cudaStream_t)stream);
 	c->pending = false;
 	return r;
@@ -1218,7 +1734,7 @@ extern "C" int ls3d_icp_finish(Ls3dIcp *c, void *stream) {
 
 static int icp_enqueue_all(Ls3dIcp *c, int maxIter, cudaStream_t st) {
 	for (int it = 0; it < maxIter; it++) {
-		if (ls3d_icp_match(c, st) < 0 || ls3d_icp_stats(c, 0, c->n1, st) < 0 || ls3d_icp_sums(c, 0, c->n1, st) < 0) return -1;
+		if (ls3d_icp_match(c, st) < 0 || ls3d_icp_reduce(c, st) < 0) return -1;
 	}
 	return ls3d_icp_finish(c, st);
 }
@@ -1277,8 +1793,6 @@ extern "C" int ls3d_icp_run(Ls3dIcp *c, int maxIter, void *stream) {
 extern "C" void ls3d_icp_set_debug(Ls3dIcp *c, void *d_stats) { if (c) c->dbg = (unsigned *)d_stats; }
 
 extern "C" long long *ls3d_icp_slots(Ls3dIcp *c) { return c ? c->slots.as<long long>() : nullptr; }
-extern "C" double *ls3d_icp_stats_buf(Ls3dIcp *c) { return c ? c->stats_buf.as<double>() : nullptr; }
-extern "C" double *ls3d_icp_sums_buf(Ls3dIcp *c) { return c ? c->sums_buf.as<double>() : nullptr; }
 extern "C" float *ls3d_icp_Rt(Ls3dIcp *c) { return c ? c->state.as<float>() : nullptr; }
 extern "C" const int *ls3d_icp_nn_index(Ls3dIcp *c) { return c ? c->nn_idx.as<int>() : nullptr; }
 extern "C" const float *ls3d_icp_nn_dist(Ls3dIcp *c) { return c ? c->nn_d2.as<float>() : nullptr; }

@@ -59,6 +59,15 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 	asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
+	unsigned v;
+	asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st_volatile_u32(unsigned *p, unsigned v) {
+	asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned warp_sum(unsigned v) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

@@ -157,8 +157,6 @@ class IcpSolver:
         self.n1 = self.n2 = 0
         self.Rt = view(self.lib.ls3d_icp_Rt(self.h), (12,), "<f4", self.device)
         self.status = view(self.lib.ls3d_icp_status(self.h), (4,), "<i4", self.device)
-        self.stats_buf = view(self.lib.ls3d_icp_stats_buf(self.h), (4,), "<f8", self.device)
-        self.sums_buf = view(self.lib.ls3d_icp_sums_buf(self.h), (16,), "<f8", self.device)
 
     def close(self):
         if self.h:
@@ -191,14 +189,8 @@ class IcpSolver:
     def match(self):
         native.check(self.lib.ls3d_icp_match(self.h, _stream()) == 0, "ls3d_icp_match")
 
-    def stats(self, j_begin=0, j_end=-1):
-        native.check(self.lib.ls3d_icp_stats(self.h, int(j_begin), int(j_end), _stream()) == 0, "ls3d_icp_stats")
-
-    def sums(self, j_begin=0, j_end=-1):
-        native.check(self.lib.ls3d_icp_sums(self.h, int(j_begin), int(j_end), _stream()) == 0, "ls3d_icp_sums")
-
-    def solve(self):
-        native.check(self.lib.ls3d_icp_solve(self.h, _stream()) == 0, "ls3d_icp_solve")
+    def reduce(self):
+        native.check(self.lib.ls3d_icp_reduce(self.h, _stream()) == 0, "ls3d_icp_reduce")
 
     def finish(self):
         native.check(self.lib.ls3d_icp_finish(self.h, _stream()) == 0, "ls3d_icp_finish")

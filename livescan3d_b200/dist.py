@@ -9,14 +9,11 @@ Two sharded variants, both bit-identical to the single-GPU result:
                 kernel, no NCCL on the vertex data.  formMesh's order (sensor order, row-major inside a sensor,
                 depthprocessing.cpp:1594-1608) is kept because ranks own contiguous sensor ranges.
 
-  ShardedIcp    the target octree is replicated, the SOURCE points are partitioned.  Per iteration every rank
-                searches its slice and atomicMin's the one-to-one keys (bits(d2) << 32 | ~i, icp.cpp:95-126) into its
-                slot array; one NCCL all-reduce(MIN) over int64[n1] makes the dedupe globally exact.  Then either
-                  reduce="replicated"   every rank reduces all slots itself (same fixed-order fp64 reduction as one
-                                        GPU, so R,t are bit-identical to the single-GPU run; 1 collective / iteration)
-                  reduce="partitioned"  every rank reduces its share of the slots and the partial counts / centroid /
-                                        3x3 covariance sums are all-reduced by NCCL (f64[4] + f64[16]; 3 collectives /
-                                        iteration, the layout the north star describes).
+  ShardedIcp    the target octree is replicated, the SOURCE points are partitioned, the dedupe slots and the reduction are
+                sharded by target range.  Per iteration every rank searches its slice and atomicMin's the one-to-one keys
+                (bits(d2) << 32 | ~i, icp.cpp:95-126) into the OWNER rank's slot array over NVLink; the fused reduction kernel
+                then exchanges chunk partials by peer stores + flags inside the launch.  No NCCL call in the loop; the poses
+                are bit-identical to the single-GPU run (canonical chunked reduction, csrc/icp.cu).
 
 The pure planning helpers at the top (no CUDA, no library) are what the world_size-2 gloo tests in tests/ exercise.
 """
@@ -85,6 +82,50 @@ def unpack_slot_keys(slots):
     d2 = ((s >> 32) & 0xFFFFFFFF).astype(np.uint32).view(np.float32).copy()
     d2[~has] = 0
     return win, d2
+
+
+RED_CHUNKS_MAX = 296
+
+
+def reduction_chunks(n1: int) -> int:
+    """How many chunks the target range is cut into for the canonical reduction (red_chunks in csrc/icp.cu): a function of n1
+    alone, so the chunk partials — and every total folded from them — do not depend on how many ranks share the work."""
+    return max(1, min(RED_CHUNKS_MAX, (int(n1) + 255) // 256))
+
+
+def reduction_chunk_size(n1: int) -> int:
+    c = reduction_chunks(n1)
+    return (int(n1) + c - 1) // c
+
+
+def chunk_owner_ranges(n1: int, world: int):
+    """[(first chunk, end chunk)] per rank: contiguous runs of ceil(C / world) chunks (ls3d_icp_reduce)."""
+    if world <= 0:
+        raise ValueError("chunk_owner_ranges: world must be positive")
+    c = reduction_chunks(n1)
+    per = -(-c // world)
+    return [(min(c, r * per), min(c, (r + 1) * per)) for r in range(world)]
+
+
+def slot_owner(idx, n1: int, world: int):
+    """Rank that owns the dedupe slot of target point idx (SlotMap / nn_commit in csrc/icp.cu): the owner of its chunk."""
+    per = max(1, -(-reduction_chunks(n1) // world))
+    return np.minimum(world - 1, (np.asarray(idx, dtype=np.int64) // max(1, reduction_chunk_size(n1))) // per)
+
+
+def fold_chunk_partials(partials):
+    """The fixed-order fold every rank applies to the C chunk partials (red_total in csrc/icp.cu): lane l adds chunks l, l+32, ...
+    in increasing order, then a 5-step xor butterfly.  partials: [C] or [C, k] float64 -> scalar or [k]."""
+    p = np.asarray(partials, dtype=np.float64)
+    p2 = p.reshape(len(p), -1)
+    acc = np.zeros((32, p2.shape[1]), dtype=np.float64)
+    for c in range(len(p2)):
+        acc[c % 32] = acc[c % 32] + p2[c]
+    o = 16
+    while o > 0:
+        acc = acc + acc[np.arange(32) ^ o]
+        o >>= 1
+    return acc[0] if p.ndim > 1 else float(acc[0, 0])
 
 
 def _world(group=None):
@@ -200,46 +241,77 @@ class ShardedFrame:
 # ---------------------------------------------------------------------------------------------------------
 # ICP with partitioned source points
 # ---------------------------------------------------------------------------------------------------------
+def map_peers(local_ptr: int, group=None):
+    """CUDA-IPC mapping of the same allocation on every rank: -> ([pointer of rank r's buffer valid in this process], [opened handles])."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import native
+    lib = native.load()
+    rank, world = _world(group)
+    ptrs = [None] * world
+    ptrs[rank] = int(local_ptr)
+    opened = []
+    if world > 1:
+        h = (C.c_ubyte * 64)()
+        native.check(lib.ls3d_ipc_export(C.c_void_p(local_ptr), h) == 0, "ls3d_ipc_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h), group=group)
+        for r, hb in enumerate(handles):
+            if r == rank:
+                continue
+            p = lib.ls3d_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb))
+            native.check(bool(p), f"ls3d_ipc_open (rank {r})")
+            ptrs[r] = int(p)
+            opened.append(p)
+    return ptrs, opened
+
+
 class ShardedIcp:
-    def __init__(self, n1_max: int, n2_max: int, group=None, reduce: str = "replicated"):
+    """One ICP call over the ranks of a node.  The clouds are replicated; every rank searches its slice of the source and owns a
+    contiguous range of the target's dedupe slots and reduction chunks.  Per iteration there is NO collective call: the match
+    kernels atomicMin their one-to-one keys straight into the owner rank's slots over NVLink, and the reduction kernel exchanges
+    its chunk partials with peer stores + flags inside the launch (csrc/icp.cu, k_icp_reduce).  Every rank folds the same numbers
+    in the same order, so R, t and verts2 are bit-identical to the single-GPU run on every rank.  The whole call is one CUDA
+    graph per rank when it repeats."""
+
+    def __init__(self, n1_max: int, n2_max: int, group=None):
+        import ctypes as C
+        from . import native
         from .device import IcpSolver
-        if reduce not in ("replicated", "partitioned"):
-            raise ValueError("reduce must be 'replicated' or 'partitioned'")
         self.group = group
-        self.reduce = reduce
         self.rank, self.world = _world(group)
         self.solver = IcpSolver(n1_max, n2_max)
+        self._opened = []
+        if self.world > 1:
+            lib = self.solver.lib
+            h = self.solver.h
+            tables = []
+            for getter in (lib.ls3d_icp_slots, lib.ls3d_icp_red_part, lib.ls3d_icp_red_flag):
+                ptrs, opened = map_peers(int(getter(h)), group)
+                self._opened += opened
+                tables.append((C.c_void_p * self.world)(*[C.c_void_p(p) for p in ptrs]))
+            native.check(lib.ls3d_icp_set_peers(h, self.world, self.rank, tables[0], tables[1], tables[2]) == 0, "ls3d_icp_set_peers")
 
     def run(self, d_verts1, d_verts2, max_iter: int, R0=None, t0=None):
         """Enqueue a whole ICP call on the current stream.  Every rank passes the full clouds (replicated); verts2 is
         transformed in place on every rank, so all ranks end with identical verts2, R, t."""
-        import torch.distributed as dist
         s = self.solver
         s.set_target(d_verts1)
         n2 = d_verts2.numel() // 3
         b, e = slice_ranges(n2, self.world)[self.rank]
         s.set_source(d_verts2, b, e, R0, t0)
-        jb, je = slice_ranges(s.n1, self.world, align=1)[self.rank]
-        slots = s.slots()
-        for _ in range(int(max_iter)):
-            s.match()
-            if self.world > 1:
-                dist.all_reduce(slots, op=dist.ReduceOp.MIN, group=self.group)
-            if self.reduce == "replicated" or self.world == 1:
-                s.stats()
-                s.sums()
-            else:
-                s.stats(jb, je)
-                dist.all_reduce(s.stats_buf, group=self.group)
-                s.sums(jb, je)
-                dist.all_reduce(s.sums_buf, group=self.group)
-                s.solve()
-        s.finish()
+        s.run(int(max_iter))
 
     def pose(self):
         return self.solver.pose()
 
     def close(self):
+        import ctypes as C
+        if self.world > 1 and self.solver.h:
+            self.solver.lib.ls3d_icp_set_peers(self.solver.h, 1, 0, None, None, None)
+        for p in self._opened:
+            self.solver.lib.ls3d_ipc_close(C.c_void_p(p))
+        self._opened = []
         self.solver.close()
 
 
@@ -313,30 +385,28 @@ def bench_sharded(args, rank, world, dev, flush):
     one.run(bench.ICP_ITERS)
     R1, t1, _ = one.pose()
     one.close()
-    for mode in ("replicated", "partitioned"):
-        si = ShardedIcp(len(A), len(B), reduce=mode)
-        for _ in range(max(args.warmup, 3)):
-            dB.copy_(dB0)
-            si.run(dA, dB, bench.ICP_ITERS)
-        R, t, st = si.pose()
-        sync()
-        for i in range(args.steps):
-            dB.copy_(dB0)
-            flush.zero_()
-            ev_s[i].record()
-            si.run(dA, dB, bench.ICP_ITERS)
-            ev_e[i].record()
-        sync()
-        ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / args.steps
-        out[f"icp_source_partitioned_{mode}"] = {
-            "ms_per_step": ms, "ms_per_iter": ms / bench.ICP_ITERS, "Mpts_iter_per_s": len(B) * bench.ICP_ITERS / (ms / 1000.0) / 1e6, "scaling": "strong",
-            "max_abs_dR_vs_single_gpu": float(np.max(np.abs(R.astype(np.float64) - R1))), "max_abs_dt_vs_single_gpu_m": float(np.max(np.abs(t.astype(np.float64) - t1))),
-            "status": [int(x) for x in st],
-            "collectives_per_iter": "all-reduce MIN int64[n1]" + ("" if mode == "replicated" else " + all-reduce SUM f64[4] + all-reduce SUM f64[16]")}
-        si.close()
-        dR_s, dt_s = out[f"icp_source_partitioned_{mode}"]["max_abs_dR_vs_single_gpu"], out[f"icp_source_partitioned_{mode}"]["max_abs_dt_vs_single_gpu_m"]
-        bad = torch.tensor([0 if (mode != "replicated" or (dR_s == 0.0 and dt_s == 0.0)) and dR_s <= 1e-5 and dt_s <= 1e-4 else 1], dtype=torch.int32, device=dev)
-        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if int(bad.item()):
-            raise RuntimeError(f"sharded ICP ({mode}): pose differs from the single-GPU result (dR={dR_s:.3e}, dt={dt_s:.3e} m; replicated mode must be bit-identical)")
+    si = ShardedIcp(len(A), len(B))
+    for _ in range(max(args.warmup, 3)):
+        dB.copy_(dB0)
+        si.run(dA, dB, bench.ICP_ITERS)
+    R, t, st = si.pose()
+    sync()
+    for i in range(args.steps):
+        dB.copy_(dB0)
+        flush.zero_()
+        ev_s[i].record()
+        si.run(dA, dB, bench.ICP_ITERS)
+        ev_e[i].record()
+    sync()
+    ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / args.steps
+    dR_s, dt_s = float(np.max(np.abs(R.astype(np.float64) - R1))), float(np.max(np.abs(t.astype(np.float64) - t1)))
+    out["icp_source_partitioned"] = {
+        "ms_per_step": ms, "ms_per_iter": ms / bench.ICP_ITERS, "Mpts_iter_per_s": len(B) * bench.ICP_ITERS / (ms / 1000.0) / 1e6, "scaling": "strong",
+        "max_abs_dR_vs_single_gpu": dR_s, "max_abs_dt_vs_single_gpu_m": dt_s, "status": [int(x) for x in st],
+        "exchange": "dedupe keys: 64-bit atomicMin into the owner rank's slots over NVLink; partial sums: peer stores + flags inside k_icp_reduce; no collective call in the loop"}
+    si.close()
+    bad = torch.tensor([0 if (dR_s == 0.0 and dt_s == 0.0 and int(st[1]) == 0) else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    if int(bad.item()):
+        raise RuntimeError(f"sharded ICP: pose differs from the single-GPU result (dR={dR_s:.3e}, dt={dt_s:.3e} m, status {st}); it must be bit-identical")
     return out

@@ -106,15 +106,14 @@ _SIG = {
     "ls3d_icp_set_target": (_i, [_vp, _vp, _i, _vp]),
     "ls3d_icp_set_source": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ls3d_icp_match": (_i, [_vp, _vp]),
-    "ls3d_icp_stats": (_i, [_vp, _i, _i, _vp]),
-    "ls3d_icp_sums": (_i, [_vp, _i, _i, _vp]),
-    "ls3d_icp_solve": (_i, [_vp, _vp]),
+    "ls3d_icp_reduce": (_i, [_vp, _vp]),
+    "ls3d_icp_set_peers": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "ls3d_icp_red_part": (_vp, [_vp]),
+    "ls3d_icp_red_flag": (_vp, [_vp]),
     "ls3d_icp_finish": (_i, [_vp, _vp]),
     "ls3d_icp_run": (_i, [_vp, _i, _vp]),
     "ls3d_icp_set_debug": (None, [_vp, _vp]),
     "ls3d_icp_slots": (_vp, [_vp]),
-    "ls3d_icp_stats_buf": (_vp, [_vp]),
-    "ls3d_icp_sums_buf": (_vp, [_vp]),
     "ls3d_icp_Rt": (_vp, [_vp]),
     "ls3d_icp_nn_index": (_vp, [_vp]),
     "ls3d_icp_nn_dist": (_vp, [_vp]),

@@ -33,7 +33,7 @@ for rep in range(reps + 1):
     marks = []
     for it in range(its):
         m = [ev() for _ in range(4)]
-        m[0].record(); s.match(); m[1].record(); s.stats(); m[2].record(); s.sums(); m[3].record()
+        m[0].record(); s.match(); m[1].record(); s.reduce(); m[2].record(); m[3].record()
         marks.append(m)
     s.finish()
     torch.cuda.synchronize()

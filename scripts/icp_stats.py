@@ -27,7 +27,7 @@ for it in range(3):
     d = dbg.cpu().numpy().reshape(-1, 3).astype(np.int64)
     idx, d2 = s.nn()
     dist = np.sqrt(d2.cpu().numpy())
-    print(f"iter {it}: match {ev0.elapsed_time(ev1) * 1000:.0f} us  deferred {np.mean(d[:, 2] > 0):.3f}")
+    print(f"iter {it}: match {ev0.elapsed_time(ev1) * 1000:.0f} us  block-wide (heavy) share of the queries {np.mean(d[:, 2] > 0):.3f}")
     for name, col in (("steps", 0), ("scanned", 1)):
         v = d[:, col]
         print(f"   {name}: mean {v.mean():.1f} p50 {np.percentile(v, 50):.0f} p90 {np.percentile(v, 90):.0f} p99 {np.percentile(v, 99):.0f} max {v.max()}  sum {v.sum() / 1e6:.1f}M")
@@ -36,4 +36,4 @@ for it in range(3):
     print(f"   far (>5cm) fraction {far.mean():.3f}: steps mean {d[far, 0].mean():.1f} scanned mean {d[far, 1].mean():.1f} | near: steps {d[~far, 0].mean():.1f} scanned {d[~far, 1].mean():.1f}")
     w = d[: len(d) // 32 * 32].reshape(-1, 32, 3)
     print(f"   per-warp max: steps mean {w[:, :, 0].max(1).mean():.1f}, scanned mean {w[:, :, 1].max(1).mean():.1f}; lane-sum/warp-max utilisation steps {w[:, :, 0].sum() / (32 * w[:, :, 0].max(1).sum() + 1):.2f} scanned {w[:, :, 1].sum() / (32 * w[:, :, 1].max(1).sum() + 1):.2f}")
-    s.stats(); s.sums()
+    s.reduce()

@@ -26,7 +26,7 @@ for rep in range(6):
     s.set_source(dB)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(its + 1)]
     for it in range(its):
-        ev[it].record(); s.match(); s.stats(); s.sums()
+        ev[it].record(); s.match(); s.reduce()
     ev[its].record(); s.finish()
     torch.cuda.synchronize()
     if rep:

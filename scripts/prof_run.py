@@ -83,7 +83,7 @@ s = IcpSolver(len(A), len(B))
 s.set_target(dA)
 s.set_source(dB)
 for _ in range(iters):
-    s.match(); s.stats(); s.sums()
+    s.match(); s.reduce()
 s.finish()
 R, t, st = s.pose()
 print("icp:", st.tolist(), t.tolist())

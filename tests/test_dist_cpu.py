@@ -89,19 +89,30 @@ def _worker(rank, world, port, q):
         res["merged"] = merged.numpy().tobytes()
         res["counts"] = kept_all.numpy().tolist()
 
-        # ---- ICP dedupe: source slices, MIN all-reduce of the slot keys
+        # ---- ICP dedupe: source slices; every key goes to the OWNER rank's slots (on the GPUs: 64-bit atomicMin over NVLink peer
+        # mappings; here: a MIN all-reduce after which each rank keeps only the range it owns)
         A, B = icp_pair(small_frame(S=2, w=96, h=72), synth.SERVER_BOUNDS)
+        n1 = len(A)
         b, e = ldist.slice_ranges(len(B), world)[rank]
         idx, d2 = orc.orc_find_closest(A, B[b:e]) if e > b else (np.zeros(0, np.uint64), np.zeros(0, np.float32))
-        slots = torch.from_numpy(ldist.pack_slot_keys(len(A), idx.astype(np.int64), d2, b))
+        slots = torch.from_numpy(ldist.pack_slot_keys(n1, idx.astype(np.int64), d2, b))
         dist.all_reduce(slots, op=dist.ReduceOp.MIN)
-        res["slots"] = slots.numpy().copy()
-        # partitioned reduction of the matched d2 statistics: partial sums over this rank's share of the slots, then SUM
-        jb, je = ldist.slice_ranges(len(A), world, align=1)[rank]
-        win, wd2 = ldist.unpack_slot_keys(res["slots"][jb:je])
-        part = torch.tensor([float((win >= 0).sum()), float(wd2[win >= 0].astype(np.float64).sum())], dtype=torch.float64)
-        dist.all_reduce(part)
-        res["stats"] = part.numpy().copy()
+        S_ = ldist.reduction_chunk_size(n1)
+        c0, c1 = ldist.chunk_owner_ranges(n1, world)[rank]
+        own = slots.numpy()[min(n1, c0 * S_):min(n1, c1 * S_)].copy()            # the slots this rank owns
+        assert np.all(ldist.slot_owner(np.arange(min(n1, c0 * S_), min(n1, c1 * S_)), n1, world) == rank)
+        res["own_slots"] = (min(n1, c0 * S_), own)
+        # canonical chunked reduction of the matched d2 (pass 1 of k_icp_reduce): the owner computes its chunks' partials, every rank
+        # receives all C of them (peer stores on the GPUs, a SUM all-reduce of disjoint rows here) and folds them in the same order
+        C_ = ldist.reduction_chunks(n1)
+        table = torch.zeros(C_, 2, dtype=torch.float64)
+        for c in range(c0, c1):
+            win, wd2 = ldist.unpack_slot_keys(slots.numpy()[min(n1, c * S_):min(n1, (c + 1) * S_)])
+            table[c, 0] = float((win >= 0).sum())
+            table[c, 1] = float(wd2[win >= 0].astype(np.float64).sum())
+        dist.all_reduce(table)
+        res["stats"] = ldist.fold_chunk_partials(table.numpy())
+        res["table"] = table.numpy().copy()
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -138,12 +149,39 @@ def test_sharded_protocols_world2_gloo():
         assert sum(got[r]["counts"]) == len(want)
 
     A, B = icp_pair(small_frame(S=2, w=96, h=72), synth.SERVER_BOUNDS)
+    n1 = len(A)
     idx, d2 = orc.orc_find_closest(A, B)
-    winner = orc.orc_dedupe(idx, d2, len(A))
+    winner = orc.orc_dedupe(idx, d2, n1)
+    has = winner >= 0
+    # the owned ranges tile the target exactly, and together they hold the reference's one-to-one matches
+    whole = np.full(n1, ldist.SLOT_EMPTY, dtype=np.int64)
+    covered = 0
     for r in range(world):
-        win, wd2 = ldist.unpack_slot_keys(got[r]["slots"])
-        # identical except where nanoflann's per-slice query could tie differently: none here because queries are identical
-        assert np.array_equal(win, winner)
-        has = winner >= 0
-        assert got[r]["stats"][0] == has.sum()
-        assert abs(got[r]["stats"][1] - d2[winner[has]].astype(np.float64).sum()) <= 1e-9 * max(1.0, got[r]["stats"][1])
+        first, own = got[r]["own_slots"]
+        whole[first:first + len(own)] = own
+        covered += len(own)
+    assert covered == n1
+    win, wd2 = ldist.unpack_slot_keys(whole)
+    assert np.array_equal(win, winner)                                               # queries are identical, so no tie can differ
+    assert np.array_equal(wd2[has].view(np.uint32), d2[winner[has]].view(np.uint32))
+    # the single-rank table, computed the same way, folds to the same bits on every rank (world-independence of the reduction)
+    S_, C_ = ldist.reduction_chunk_size(n1), ldist.reduction_chunks(n1)
+    one = np.zeros((C_, 2))
+    for c in range(C_):
+        w1, wd1 = ldist.unpack_slot_keys(whole[min(n1, c * S_):min(n1, (c + 1) * S_)])
+        one[c] = [float((w1 >= 0).sum()), float(wd1[w1 >= 0].astype(np.float64).sum())]
+    want_stats = ldist.fold_chunk_partials(one)
+    for r in range(world):
+        assert np.array_equal(got[r]["table"], one)
+        assert np.array_equal(got[r]["stats"], want_stats) and got[r]["stats"][0] == has.sum()
+    # planning helpers: owners are monotone, contiguous and cover every rank count
+    for n in (1, 255, 256, 257, 5000, 212654, 2_000_000):
+        for w in (1, 2, 3, 4, 8):
+            rr = ldist.chunk_owner_ranges(n, w)
+            assert rr[0][0] == 0 and rr[-1][1] == ldist.reduction_chunks(n) and all(rr[i][1] == rr[i + 1][0] for i in range(w - 1))
+            o = ldist.slot_owner(np.arange(0, n, max(1, n // 997)), n, w)
+            assert np.all(np.diff(o) >= 0) and o.min() >= 0 and o.max() < w
+            S2 = ldist.reduction_chunk_size(n)
+            for r, (a0, a1) in enumerate(rr):
+                if a1 > a0 and a0 * S2 < n:
+                    assert ldist.slot_owner([a0 * S2, min(n, a1 * S2) - 1], n, w).tolist() == [r, r]

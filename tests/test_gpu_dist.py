@@ -1,5 +1,6 @@
-"""Sharded (multi-GPU) variants on real devices: the world=1 degenerate case always, and a 2-rank NCCL run (peer-store
-merge over CUDA IPC, MIN all-reduce of the dedupe keys) whenever the box has >= 2 GPUs.  Truth = the CPU oracle."""
+"""Sharded (multi-GPU) variants on real devices: the world=1 degenerate case always, and 2- / 4-rank runs (peer-store
+merge over CUDA IPC; dedupe keys by NVLink atomicMin into the owner's slots, partial sums exchanged inside the reduction kernel)
+whenever the box has that many GPUs.  Truth = the CPU oracle."""
 import os
 import socket
 import sys
@@ -58,13 +59,21 @@ def _run_rank(rank, world, port, q):
 
         A, B = icp_pair(small_frame(S=2, w=128, h=96), synth.SERVER_BOUNDS)
         dA = torch.from_numpy(A).to(dev)
-        for mode in ("replicated", "partitioned"):
+        # the single-GPU result on this rank, then the sharded call three times (the third replays the captured graph)
+        from livescan3d_b200.device import IcpSolver
+        dB = torch.from_numpy(B).to(dev)
+        one = IcpSolver(len(A), len(B))
+        one.set_target(dA); one.set_source(dB); one.run(5)
+        R1, t1, st1 = one.pose()
+        res["icp_single"] = (R1, t1, st1.tolist(), dB.cpu().numpy())
+        one.close()
+        si = ldist.ShardedIcp(len(A), len(B))
+        for rep in range(3):
             dB = torch.from_numpy(B).to(dev)
-            si = ldist.ShardedIcp(len(A), len(B), reduce=mode)
             si.run(dA, dB, 5)
             R, t, st = si.pose()
-            res[f"icp_{mode}"] = (R, t, st.tolist(), dB.cpu().numpy())
-            si.close()
+            res[f"icp_sharded_{rep}"] = (R, t, st.tolist(), dB.cpu().numpy())
+        si.close()
         q.put((rank, res))
         if world > 1:
             dist.barrier()
@@ -89,15 +98,15 @@ def _check(results, world):
             assert got == want.tobytes(), f"rank {r}: merged cloud differs from the oracle (k={k})"
     A, B = icp_pair(small_frame(S=2, w=128, h=96), synth.SERVER_BOUNDS)
     wv, wR, wt, _ = orc.orc_icp(A, B, max_iter=5)
+    R1, t1, st1, v1 = results[0]["icp_single"]
     for r in range(world):
-        for mode in ("replicated", "partitioned"):
-            R, t, st, v2 = results[r][f"icp_{mode}"]
+        for key in ("icp_single", "icp_sharded_0", "icp_sharded_1", "icp_sharded_2"):
+            R, t, st, v2 = results[r][key]
             assert st[0] == 5 and st[1] == 0
             assert rot_err(R, wR) <= 1e-5 and np.max(np.abs(t.astype(np.float64) - wt)) <= 1e-4      # north-star tolerances
             assert np.max(np.abs(v2.astype(np.float64) - wv)) <= 2e-4
-        if r > 0:        # replicated reduction: every rank derives the identical pose
-            assert np.array_equal(results[r]["icp_replicated"][0], results[0]["icp_replicated"][0])
-            assert np.array_equal(results[r]["icp_replicated"][1], results[0]["icp_replicated"][1])
+            # canonical chunked reduction + exact dedupe: the same bits on every rank, sharded or not
+            assert np.array_equal(R, R1) and np.array_equal(t, t1) and np.array_equal(v2, v1), (r, key)
 
 
 def _spawn(world):

@@ -653,7 +653,7 @@ def test_device_api_matches_host_api(api):
     s.set_target(dA)
     s.set_source(dB2)
     for _ in range(6):
-        s.match(); s.stats(); s.sums()
+        s.match(); s.reduce()
     s.finish()
     R2, t2, _ = s.pose()
     assert np.array_equal(R2, hR) and np.array_equal(t2, ht)
