@@ -109,6 +109,10 @@ __device__ __forceinline__ float rec_lb2(unsigned long long r, float rx, float r
 
 // first entry of level l (1..L) in the child-mask array: sum_{j<l} (G >> j)^3 with G = 2^L
 __device__ __host__ __forceinline__ unsigned icp_mask_off(int L, int l) { return ((1u << (3 * L)) - (1u << (3 * (L - l + 1)))) / 7u; }
+// the same as a table for the search kernels (the level is warp-uniform: one constant-bank load instead of shifts and a division by 7)
+constexpr unsigned icp_off_c(int L, int l) { return (l >= 1 && l <= L + 1) ? (unsigned)(((1ull << (3 * L)) - (1ull << (3 * (L - l + 1)))) / 7ull) : 0u; }
+#define LS3D_OFF_ROW(L) {0u, icp_off_c(L, 1), icp_off_c(L, 2), icp_off_c(L, 3), icp_off_c(L, 4), icp_off_c(L, 5), icp_off_c(L, 6), icp_off_c(L, 7), icp_off_c(L, 8), icp_off_c(L, 9)}
+__constant__ unsigned c_icp_off[10][10] = {LS3D_OFF_ROW(0), LS3D_OFF_ROW(1), LS3D_OFF_ROW(2), LS3D_OFF_ROW(3), LS3D_OFF_ROW(4), LS3D_OFF_ROW(5), LS3D_OFF_ROW(6), LS3D_OFF_ROW(7), LS3D_OFF_ROW(8), LS3D_OFF_ROW(9)};
 
 __device__ __forceinline__ int icp_cell(float rel, float inv_h, int G) {
 	float u = floorf(rel * inv_h);
@@ -136,11 +140,18 @@ __global__ void __launch_bounds__(256) k_icp_bbox(const float *__restrict__ v, i
 			mx[a] = fmaxf(mx[a], __shfl_xor_sync(kFull, mx[a], o));
 		}
 	}
+	// one set of atomics per block (one per warp was 40 k same-address atomics for a 213 k-point target)
+	__shared__ unsigned s_mn[3], s_mx[3];
+	if (threadIdx.x < 3) { s_mn[threadIdx.x] = 0xffffffffu; s_mx[threadIdx.x] = 0u; }
+	__syncthreads();
 	if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-		for (int a = 0; a < 3; a++) { atomicMin(&box->mn[a], f2ord(mn[a])); atomicMax(&box->mx[a], f2ord(mx[a])); }
+		for (int a = 0; a < 3; a++) { atomicMin(&s_mn[a], f2ord(mn[a])); atomicMax(&s_mx[a], f2ord(mx[a])); }
 	}
+	__syncthreads();
+	if (threadIdx.x < 3) { atomicMin(&box->mn[threadIdx.x], s_mn[threadIdx.x]); atomicMax(&box->mx[threadIdx.x], s_mx[threadIdx.x]); }
 }
+
 
 __global__ void k_icp_grid_params(const IcpBox *box, IcpGrid *grid, int G, int levels) {
 	double lo[3], ext = 0;
@@ -535,8 +546,11 @@ unsigned long long pk_scan_fn(const float4 *__restrict__ sorted, unsigned s, uns
 			const f32x2 sq = fma2(fma2(mul2(d0, d0), one2, mul2(d1, d1)), one2, mul2(d2, d2));      // == dist2_ref on both halves
 			float da, db;
 			upk2(sq, da, db);
-			if (da < best_d2 || (da == best_d2 && I.x < best_idx)) { best_d2 = da; best_idx = I.x; }
-			if (db < best_d2 || (db == best_d2 && I.y < best_idx)) { best_d2 = db; best_idx = I.y; }
+			// after the first few candidates almost nothing improves on the best: one warp-uniform branch skips the tie logic
+			if (__any_sync(kFull, fminf(da, db) <= best_d2)) {
+				if (da < best_d2 || (da == best_d2 && I.x < best_idx)) { best_d2 = da; best_idx = I.x; }
+				if (db < best_d2 || (db == best_d2 && I.y < best_idx)) { best_d2 = db; best_idx = I.y; }
+			}
 		}
 	}
 	return ((unsigned long long)__float_as_uint(best_d2) << 32) | (unsigned)best_idx;
@@ -570,7 +584,7 @@ __device__ __forceinline__ unsigned pk_load_children(const IcpGrid &g, const uns
 	__syncwarp();                                                        // earlier readers of sh.lo/hi / sh.rng are done
 	if (a < 3) {
 		const unsigned cmp = (ump << 3) | c;
-		rec = t == 1 ? __ldg(cellrec + cmp) : __ldg(nodes + icp_mask_off(g.levels, t - 1) + cmp);      // 0 = empty
+		rec = t == 1 ? __ldg(cellrec + cmp) : __ldg(nodes + c_icp_off[g.levels][t - 1] + cmp);      // 0 = empty
 		const float half = g.h * (float)(1u << (t - 1));                 // child edge
 		const float qs = half * (1.0f / 255.0f);
 		const unsigned ua = a == 0 ? ux : (a == 1 ? uy : uz);
@@ -754,6 +768,9 @@ __device__ __forceinline__ void pk_search(const IcpGrid &g, const unsigned *__re
 #define LS3D_PK_BUDGET 64
 #endif
 constexpr unsigned kPkBudget = LS3D_PK_BUDGET;
+#ifndef LS3D_PK_BUDGET0_FACTOR
+#define LS3D_PK_BUDGET0_FACTOR 1u       // measured on the bench pair: 1 -> 1.54 ms per call, 2 -> 1.79, 4 -> 1.59
+#endif
 
 // this lane's query of packet `pd`: position (after the pending update when apply != 0, which is also written back), home cell,
 // and the previous nearest neighbour as the first candidate
@@ -817,11 +834,12 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_
 	const float *xf = apply ? state->xf : nullptr;
 	const IcpGrid g = *grid;
 	const int lane = threadIdx.x & 31;
-	const int L = g.levels;
 	const float slack = 1e-3f * g.h;
 	const f32x2 one2 = pk2(one, one);
 	const int n_packets = (int)state->n_packets;
 	const bool use_sched = state->sched_valid != 0;
+	// first match stage of a call: no seeds and no cost history yet, walks are ~40 % longer (a larger budget there did not pay)
+	const unsigned walk_budget = use_sched ? budget : budget * LS3D_PK_BUDGET0_FACTOR;
 	for (;;) {
 		int pk = 0;
 		if (lane == 0) {
@@ -869,8 +887,8 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_
 			const unsigned diff = __reduce_or_sync(kFull, q.valid ? (mp ^ mp_ref) : 0u);
 			int lvl = diff ? (31 - __clz((int)diff)) / 3 + 1 : 0;      // lowest level whose node holds every lane's home cell
 			// ---- the subtree all home cells share (level 0: the one home cell, done above), then its siblings level by level ----
-			pk_search(g, cell_start, nodes, cellrec, sorted, sh, lvl, rhx >> lvl, rhy >> lvl, rhz >> lvl, mp_ref >> (3 * lvl), q, pkt, slack, done, one2, steps, scanned, budget, true);
-			heavy = steps > budget;
+			pk_search(g, cell_start, nodes, cellrec, sorted, sh, lvl, rhx >> lvl, rhy >> lvl, rhz >> lvl, mp_ref >> (3 * lvl), q, pkt, slack, done, one2, steps, scanned, walk_budget, true);
+			heavy = steps > walk_budget;
 		}
 		if (heavy) {
 			// the best candidate so far is a real point: it seeds the block-wide search (nothing is committed to the dedupe slots yet)
@@ -1162,7 +1180,7 @@ struct IcpPeers {
 __device__ __forceinline__ unsigned ld_volatile_sys_u32(const unsigned *p) { unsigned v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 
 // all local blocks have stored (and fenced) their pass-`phase` partials; the last one to arrive raises this rank's flag on every peer
-__device__ __forceinline__ void red_arrive_wait(IcpState *st, unsigned nblocks, unsigned phase, unsigned epoch, const IcpPeers &pe, bool wait) {
+__device__ __forceinline__ void red_arrive(IcpState *st, unsigned nblocks, unsigned phase, unsigned epoch, const IcpPeers &pe) {
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		const unsigned arrived = atomicAdd(&st->red_bar, 1u) + 1u;
@@ -1170,16 +1188,19 @@ __device__ __forceinline__ void red_arrive_wait(IcpState *st, unsigned nblocks, 
 			__threadfence_system();
 			for (int r = 0; r < pe.world; r++) if (r != pe.rank) st_volatile_u32(pe.flag[r] + pe.rank, epoch * 4u + phase);
 		}
-		if (wait) {
-			unsigned spins = 0;
-			while (ld_volatile_u32(&st->red_bar) < phase * nblocks) if (++spins > (1u << 24)) { atomicOr(&st->err, kErrScanSpin); break; }
-			for (int r = 0; r < pe.world; r++) {
-				if (r == pe.rank) continue;
-				spins = 0;
-				while (ld_volatile_sys_u32(pe.flag[pe.rank] + r) < epoch * 4u + phase) if (++spins > (1u << 24)) { atomicOr(&st->err, kErrScanSpin); break; }
-			}
-			__threadfence();
+	}
+}
+// ... and every block of every rank has arrived
+__device__ __forceinline__ void red_wait(IcpState *st, unsigned nblocks, unsigned phase, unsigned epoch, const IcpPeers &pe) {
+	if (threadIdx.x == 0) {
+		unsigned spins = 0;
+		while (ld_volatile_u32(&st->red_bar) < phase * nblocks) if (++spins > (1u << 24)) { atomicOr(&st->err, kErrScanSpin); break; }
+		for (int r = 0; r < pe.world; r++) {
+			if (r == pe.rank) continue;
+			spins = 0;
+			while (ld_volatile_sys_u32(pe.flag[pe.rank] + r) < epoch * 4u + phase) if (++spins > (1u << 24)) { atomicOr(&st->err, kErrScanSpin); break; }
 		}
+		__threadfence();
 	}
 	__syncthreads();
 }
@@ -1217,58 +1238,57 @@ __device__ __forceinline__ void red_block(double *v, double *smem /* [8][NV] + [
 	__syncthreads();
 }
 
-// the C chunk partials of pass `phase` folded in chunk order (every block, every rank: the same numbers in the same order);
-// executed by warp 0, result broadcast through smem[0..NV)
+// The C chunk partials of pass `phase` folded in a fixed order (every block, every rank: the same numbers in the same order, hence
+// the same bits).  The order: chunk c belongs to column l = c % 32 and row w = (c / 32) % 8; a (row, column) cell adds its chunks
+// in increasing c, a column adds its 8 cells in row order, the 32 columns are combined by a 5-step xor butterfly.  All 256
+// threads load in parallel (one cell each, at most two chunks for C <= 296); the result lands in out[0..NV).
 template <int NV>
-__device__ __forceinline__ void red_total(const double *part_local, int C, int phase, double *smem) {
-	if (threadIdx.x < 32) {
-		const int lane = threadIdx.x;
+__device__ __forceinline__ void red_total(const double *part_local, int C, int phase, double *cells /* [NV][256] */, double *out) {
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	{
 		double acc[NV];
 #pragma unroll
 		for (int a = 0; a < NV; a++) acc[a] = 0;
-		for (int c = lane; c < C; c += 32) {
+		for (int c = t; c < C; c += 256) {
 #pragma unroll
 			for (int a = 0; a < NV; a++) acc[a] += __ldcg(part_local + (size_t)(phase - 1) * kRedPhaseStride + (size_t)c * 16 + a);
 		}
 #pragma unroll
-		for (int a = 0; a < NV; a++) {
+		for (int a = 0; a < NV; a++) cells[a * 256 + t] = acc[a];          // component-major: conflict-free both ways
+	}
+	__syncthreads();
+	for (int a = warp; a < NV; a += 8) {          // warp `a` (and a + 8) folds component a: lane = column
+		double col = 0;
 #pragma unroll
-			for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(kFull, acc[a], o);
-			if (lane == 0) smem[a] = acc[a];
-		}
+		for (int w = 0; w < 8; w++) col += cells[a * 256 + w * 32 + lane];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) col += __shfl_xor_sync(kFull, col, o);
+		if (lane == 0) out[a] = col;
 	}
 	__syncthreads();
 }
 
+#ifdef LS3D_RED_TIMING
+__device__ unsigned long long g_red_t[16];
+__device__ __forceinline__ void red_mark(int k) { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_red_t[k] = t; } }
+extern "C" __global__ void k_red_timing_dump(unsigned long long *out) { if (threadIdx.x < 16) out[threadIdx.x] = g_red_t[threadIdx.x]; }
+#else
+__device__ __forceinline__ void red_mark(int) {}
+#endif
 __global__ void __launch_bounds__(256, 2) k_icp_reduce(unsigned long long *__restrict__ slots, int n1, int c_begin, const float *__restrict__ verts1, const float *__restrict__ verts2,
 	IcpState *state, Ls3dIcpTrace *trace, int trace_idx, const unsigned *__restrict__ pk_cost, unsigned *__restrict__ sched, unsigned budget, IcpPeers pe)
 {
 	__shared__ double smem[16 + 8 * 16];
+	__shared__ double s_cells[256 * 16];
 	asm volatile("griddepcontrol.launch_dependents;");                // the next match kernel may become resident (it waits for us to complete)
+	red_mark(0);
 	asm volatile("griddepcontrol.wait;" ::: "memory");                // the match stage (packet + block-wide kernels) is complete
+	red_mark(1);
 	const int C = red_chunks(n1), S = red_chunk_size(n1);
 	const int c = c_begin < 0 ? -1 : c_begin + (int)blockIdx.x;      // -1: this rank owns no chunk (fewer chunks than ranks); it still takes part in the exchanges
 	const unsigned nblocks = gridDim.x;
 	const unsigned epoch = ld_volatile_u32(&state->red_epoch);
 	double *part_local = pe.part[pe.rank];
-	// next iteration's packet schedule (the match stage of this iteration is complete): most expensive class first, so the kernel's
-	// tail is one cheap packet per warp instead of whatever happened to be drawn last
-	{
-		const unsigned np = state->n_packets;
-		unsigned off[8];
-		unsigned run = 0;
-#pragma unroll
-		for (int k = 0; k < 8; k++) { off[k] = run; run += state->cls_n[k]; }
-		for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
-			const unsigned k = pk_cost_class(pk_cost[p], budget);
-			unsigned o = 0;
-#pragma unroll
-			for (int kk = 0; kk < 8; kk++) if (k == (unsigned)kk) o = off[kk];
-			const unsigned pos = o + atomicAdd(&state->cls_fill[k], 1u);
-			if (pos < np) sched[pos] = p;
-		}
-		if (blockIdx.x == 0 && threadIdx.x == 0) state->sched_valid = run == np ? 1u : 0u;     // every packet was classed exactly once
-	}
 	// every rank's match kernels have finished (their atomicMin's into our slots are performed) before the slots are read
 	if (pe.world > 1) {
 		if (threadIdx.x == 0) {
@@ -1282,6 +1302,7 @@ __global__ void __launch_bounds__(256, 2) k_icp_reduce(unsigned long long *__res
 		}
 		__syncthreads();
 	}
+	red_mark(2);
 	const int j0 = c < 0 ? 0 : min(n1, c * S), j1 = c < 0 ? 0 : min(n1, j0 + S);
 
 	// the chunk's slots are read once: a thread's first kRedCache keys stay in registers for all three passes (a 2 x 213 k pair has
@@ -1303,8 +1324,40 @@ __global__ void __launch_bounds__(256, 2) k_icp_reduce(unsigned long long *__res
 	}
 	red_block<2>(v, smem);
 	red_store<2>(smem, c, 1, pe);
-	red_arrive_wait(state, nblocks, 1, epoch, pe, true);
-	red_total<2>(part_local, C, 1, smem);
+	red_mark(3);
+	red_arrive(state, nblocks, 1, epoch, pe);
+	// next iteration's packet schedule, built while the first barrier fills (the match stage of this iteration is complete): most
+	// expensive class first, so the match kernel's tail is one cheap packet per warp instead of whatever happened to be drawn
+	// last.  One atomic per class per warp (the lanes of a class are ranked by ballot).
+	{
+		const unsigned np = state->n_packets;
+		unsigned off[8];
+		unsigned run = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) { off[k] = run; run += state->cls_n[k]; }
+		const int lane = threadIdx.x & 31;
+		for (unsigned p0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; p0 < np; p0 += gridDim.x * blockDim.x) {
+			const unsigned p = p0 + lane;
+			const unsigned k = p < np ? pk_cost_class(pk_cost[p], budget) : 8u;
+			const unsigned grp = __match_any_sync(kFull, k);
+			const int leader = __ffs(grp) - 1;
+			unsigned base = 0;
+			if (lane == leader && k < 8u) base = atomicAdd(&state->cls_fill[k], (unsigned)__popc(grp));
+			base = __shfl_sync(kFull, base, leader);
+			if (k < 8u) {
+				unsigned o = 0;
+#pragma unroll
+				for (int kk = 0; kk < 8; kk++) if (k == (unsigned)kk) o = off[kk];
+				const unsigned pos = o + base + __popc(grp & ((1u << lane) - 1u));
+				if (pos < np) sched[pos] = p;
+			}
+		}
+		if (blockIdx.x == 0 && threadIdx.x == 0) state->sched_valid = run == np ? 1u : 0u;     // every packet was classed exactly once
+	}
+	red_wait(state, nblocks, 1, epoch, pe);
+	red_mark(4);
+	red_total<2>(part_local, C, 1, s_cells, smem);
+	red_mark(5);
 	const double cnt = smem[0];
 	const float nf = (float)cnt;                                     // (float)data.size()
 	const float meanf = cnt >= 0.5 ? __fdiv_rn((float)smem[1], nf) : 0.0f;
@@ -1319,8 +1372,12 @@ __global__ void __launch_bounds__(256, 2) k_icp_reduce(unsigned long long *__res
 	}
 	red_block<1>(v, smem);
 	red_store<1>(smem, c, 2, pe);
-	red_arrive_wait(state, nblocks, 2, epoch, pe, true);
-	red_total<1>(part_local, C, 2, smem);
+	red_mark(6);
+	red_arrive(state, nblocks, 2, epoch, pe);
+	red_wait(state, nblocks, 2, epoch, pe);
+	red_mark(7);
+	red_total<1>(part_local, C, 2, s_cells, smem);
+	red_mark(8);
 	const float sigma = cnt >= 0.5 ? sqrtf(__fdiv_rn((float)smem[0], nf)) : 0.0f;
 	const float thr = __fmul_rn(2.5f, sigma);
 
@@ -1348,10 +1405,14 @@ __global__ void __launch_bounds__(256, 2) k_icp_reduce(unsigned long long *__res
 	for (int j = j0 + (int)threadIdx.x + 256 * kRedCache; j < j1; j += 256) take(j, __ldcg(slots + j));
 	red_block<16>(v, smem);
 	red_store<16>(smem, c, 3, pe);
-	red_arrive_wait(state, nblocks, 3, epoch, pe, blockIdx.x == 0);
+	red_mark(9);
+	red_arrive(state, nblocks, 3, epoch, pe);
 	if (blockIdx.x != 0) return;
+	red_wait(state, nblocks, 3, epoch, pe);
+	red_mark(10);
 	// ---- block 0 of every rank: fold, solve, accumulate (identical arithmetic on identical numbers everywhere) ----
-	red_total<16>(part_local, C, 3, smem);
+	red_total<16>(part_local, C, 3, s_cells, smem);
+	red_mark(11);
 	if (threadIdx.x == 0) {
 		if (trace && trace_idx >= 0 && trace_idx < kTraceCap) { trace[trace_idx].n_matched = (int)(cnt + 0.5); trace[trace_idx].sigma = sigma; }
 		double sums[16];
@@ -1365,7 +1426,18 @@ __global__ void __launch_bounds__(256, 2) k_icp_reduce(unsigned long long *__res
 		state->red_bar = 0;
 		state->red_epoch = epoch + 1u;
 	}
+	red_mark(12);
 }
+#ifdef LS3D_RED_TIMING
+extern "C" int ls3d_debug_red_timing(unsigned long long *host16) {
+	unsigned long long *d = nullptr;
+	if (cudaMalloc(&d, 128) != cudaSuccess) return -1;
+	k_red_timing_dump<<<1, 32>>>(d);
+	const cudaError_t e = cudaMemcpy(host16, d, 128, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	return e == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // cross-rank rendezvous (sharded ICP, one block): every rank has reached this point of its stream.  ls3d_icp_set_source ends with
 // it, so no rank's first match kernel can put keys into a peer's dedupe slots before that peer has re-initialised them.
@@ -1675,6 +1747,7 @@ static int icp_launch_match(Ls3dIcp *c, int apply, int search, cudaStream_t st) 
 				!cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_heavy, k_icp_match_heavy, kPkWarps * 32, sizeof(HvBlock)), "occupancy query")) return -1;
 			occ_light = std::max(occ_light, 1);
 			occ_heavy = std::max(occ_heavy, 1);
+			if (getenv("LS3D_PK_OCC")) occ_light = std::max(1, std::min(occ_light, atoi(getenv("LS3D_PK_OCC"))));      // tuning aid: leave SM room for the block-wide stage
 		}
 		const int nb = std::max(1, std::min((n_packets + kPkWarps - 1) / kPkWarps + 8, c->sm_count * occ_light));
 		const unsigned budget = icp_budget();

@@ -114,13 +114,17 @@ def slot_owner(idx, n1: int, world: int):
 
 
 def fold_chunk_partials(partials):
-    """The fixed-order fold every rank applies to the C chunk partials (red_total in csrc/icp.cu): lane l adds chunks l, l+32, ...
-    in increasing order, then a 5-step xor butterfly.  partials: [C] or [C, k] float64 -> scalar or [k]."""
+    """The fixed-order fold every rank applies to the C chunk partials (red_total in csrc/icp.cu): chunk c belongs to column
+    c % 32 and row (c // 32) % 8; a cell adds its chunks in increasing c, a column its 8 cells in row order, the 32 columns are
+    combined by a 5-step xor butterfly.  partials: [C] or [C, k] float64 -> scalar or [k]."""
     p = np.asarray(partials, dtype=np.float64)
     p2 = p.reshape(len(p), -1)
-    acc = np.zeros((32, p2.shape[1]), dtype=np.float64)
+    cells = np.zeros((256, p2.shape[1]), dtype=np.float64)
     for c in range(len(p2)):
-        acc[c % 32] = acc[c % 32] + p2[c]
+        cells[c % 256] = cells[c % 256] + p2[c]
+    acc = np.zeros((32, p2.shape[1]), dtype=np.float64)
+    for w in range(8):
+        acc = acc + cells[w * 32:(w + 1) * 32]
     o = 16
     while o > 0:
         acc = acc + acc[np.arange(32) ^ o]
