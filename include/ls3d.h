@@ -226,6 +226,24 @@ int ls3d_frame_run_peers(Ls3dFrame *f, const void *d_depth_maps, const void *d_d
 int ls3d_frame_run_count(Ls3dFrame *f, const void *d_depth_maps, const void *d_depth_colors, int first_map, int n_run, void *stream);
 int ls3d_frame_merge_peers(Ls3dFrame *f, int first_map, int n_run, int n_peers, void *const *peer_dst_vertices, const int *d_dst_offset, void *stream);
 
+/* The exchange around that pair without any collective library: counts and completion flags travel as NVLink peer stores.
+ * Every rank owns one Ls3dFrameSync block in device memory, zero-initialised once and mapped by all ranks (CUDA IPC);
+ * peer_sync[r] is rank r's block as seen from this process.
+ *   ls3d_frame_publish_counts : after ls3d_frame_run_count — stores this rank's survivor count into every rank's block, waits for
+ *                               all ranks' counts of this frame and leaves this rank's exclusive prefix in its own block's
+ *                               `offset` (pass &block->offset as ls3d_frame_merge_peers' d_dst_offset) and the sum in `total`.
+ *                               f == NULL publishes 0 (a rank that owns no sensor).
+ *   ls3d_frame_wait_peers     : after ls3d_frame_merge_peers — raises this rank's "delivered" word on every rank and waits for
+ *                               everyone's: afterwards this rank's merged buffer holds the whole cloud.
+ * Both are single-block kernels on `stream` (no host synchronisation; capturable in a CUDA graph). */
+typedef struct Ls3dFrameSync {
+	unsigned epoch; int offset; int total; int err;
+	unsigned cnt_tag[8]; int cnt_val[8]; unsigned done_tag[8];
+	unsigned pad[36];
+} Ls3dFrameSync;                               /* 256 bytes */
+int ls3d_frame_publish_counts(Ls3dFrame *f, int rank, int world, void *const *peer_sync, void *stream);
+int ls3d_frame_wait_peers(int rank, int world, void *const *peer_sync, void *stream);
+
 /* The two pre-passes on device-resident buffers, enqueued on `stream` without synchronisation: radial correction of a packed
  * frame in place (same layouts as ls3d_frame_run's inputs, so it chains straight into it), flying-pixel filter from d_in to a
  * distinct d_out.  Return the number of kernels enqueued or -1. */

@@ -1678,6 +1678,89 @@ extern "C" int ls3d_frame_run_peers(Ls3dFrame *f, const void *d_depth_maps, cons
 	return frame_run_impl(f, d_depth_maps, d_depth_colors, first_map, n_run, (uint4 *)peer_dst_vertices[0], d_dst_offset, peers, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// multi-GPU merge without a collective library: survivor counts and completion flags travel as peer stores
+// ------------------------------------------------------------------------------------------------------
+// Every rank owns one Ls3dFrameSync block (include/ls3d.h; 256 bytes of device memory mapped by all ranks).  Per frame:
+//   k_frame_publish_counts  (1 block, after the neighbour count): store this rank's survivor count into EVERY rank's block, tag it
+//                           with the frame number, wait until all ranks' counts of this frame have arrived here, and leave the
+//                           exclusive prefix (where this rank's records start in the merged cloud) in sync->offset — which is
+//                           what the compaction kernel reads as its base (ls3d_frame_merge_peers' d_dst_offset);
+//   k_frame_wait_peers      (1 block, after the compaction): tell every rank that this rank's records have been delivered and
+//                           wait for the same word from all of them: after it, the merged cloud in this rank's buffer is complete.
+// Spins are bounded (kErrScanSpin) so a broken peer cannot hang the GPU.
+struct FrameSync {
+	unsigned epoch;            // frames completed so far
+	int offset;                // exclusive prefix of the survivor counts for this rank
+	int total;                 // sum of all ranks' counts
+	int err;
+	unsigned cnt_tag[kMaxPeers];   // cnt_tag[r] == frame number: cnt_val[r] is rank r's survivor count of that frame
+	int cnt_val[kMaxPeers];
+	unsigned done_tag[kMaxPeers];  // done_tag[r] == frame number: rank r's records of that frame are in this rank's buffer
+	unsigned pad[36];
+};
+static_assert(sizeof(FrameSync) == 256, "Ls3dFrameSync layout");
+struct SyncPeers { int world, rank; FrameSync *p[kMaxPeers]; };
+
+__global__ void k_frame_publish_counts(const FrameCtl *ctl, SyncPeers sp) {
+	if (threadIdx.x != 0) return;
+	FrameSync *me = sp.p[sp.rank];
+	const unsigned e = ld_volatile_u32(&me->epoch) + 1u;
+	const int n = ctl ? ctl->n_kept : 0;
+	for (int r = 0; r < sp.world; r++) *reinterpret_cast<volatile int *>(&sp.p[r]->cnt_val[sp.rank]) = n;
+	__threadfence_system();
+	for (int r = 0; r < sp.world; r++) st_volatile_u32(&sp.p[r]->cnt_tag[sp.rank], e);
+	int off = 0, tot = 0;
+	for (int r = 0; r < sp.world; r++) {
+		unsigned spins = 0;
+		while (ld_volatile_u32(&me->cnt_tag[r]) != e) if (++spins > (1u << 25)) { me->err |= kErrScanSpin; break; }
+		__threadfence_system();
+		const int v = *reinterpret_cast<volatile int *>(&me->cnt_val[r]);
+		if (r < sp.rank) off += v;
+		tot += v;
+	}
+	me->offset = off;
+	me->total = tot;
+}
+
+__global__ void k_frame_wait_peers(SyncPeers sp) {
+	if (threadIdx.x != 0) return;
+	FrameSync *me = sp.p[sp.rank];
+	const unsigned e = ld_volatile_u32(&me->epoch) + 1u;
+	__threadfence_system();                                           // the compaction kernel before us has completed: its peer stores are performed
+	for (int r = 0; r < sp.world; r++) st_volatile_u32(&sp.p[r]->done_tag[sp.rank], e);
+	for (int r = 0; r < sp.world; r++) {
+		unsigned spins = 0;
+		while (ld_volatile_u32(&me->done_tag[r]) != e) if (++spins > (1u << 25)) { me->err |= kErrScanSpin; break; }
+	}
+	__threadfence_system();
+	me->epoch = e;
+}
+
+static bool sync_peers(SyncPeers &sp, int rank, int world, void *const *peer_sync, const char *who) {
+	if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !peer_sync) { set_error("%s: world must be 1..%d, rank inside it, pointer table non-null", who, kMaxPeers); return false; }
+	sp.world = world; sp.rank = rank;
+	for (int r = 0; r < kMaxPeers; r++) sp.p[r] = r < world ? (FrameSync *)peer_sync[r] : nullptr;
+	for (int r = 0; r < world; r++) if (!sp.p[r]) { set_error("%s: missing sync block of rank %d", who, r); return false; }
+	return true;
+}
+
+extern "C" int ls3d_frame_publish_counts(Ls3dFrame *f, int rank, int world, void *const *peer_sync, void *stream) {
+	SyncPeers sp;
+	if (!sync_peers(sp, rank, world, peer_sync, "ls3d_frame_publish_counts")) return -1;
+	k_frame_publish_counts<<<1, 32, 0, (cudaStream_t)stream>>>(f ? f->ctl : nullptr, sp);      // f == NULL: a rank without sensors publishes 0
+	count_launch(1);
+	return cuda_ok(cudaGetLastError(), "k_frame_publish_counts") ? 0 : -1;
+}
+
+extern "C" int ls3d_frame_wait_peers(int rank, int world, void *const *peer_sync, void *stream) {
+	SyncPeers sp;
+	if (!sync_peers(sp, rank, world, peer_sync, "ls3d_frame_wait_peers")) return -1;
+	k_frame_wait_peers<<<1, 32, 0, (cudaStream_t)stream>>>(sp);
+	count_launch(1);
+	return cuda_ok(cudaGetLastError(), "k_frame_wait_peers") ? 0 : -1;
+}
+
 extern "C" void ls3d_frame_enable_timing(Ls3dFrame *f, int on) { if (f) f->timing = on != 0; }
 
 // Stage durations of the last ls3d_frame_run (milliseconds; waits for it to finish); stages that did not run are 0:

@@ -459,6 +459,9 @@ __device__ __forceinline__ void nn_commit(int i, float d2, int idx, const SlotMa
 		unsigned long long *slots = sm.ptr[0];
 		if (sm.world > 1) slots = sm.ptr[min(sm.world - 1, (idx / sm.chunk) / sm.per)];      // the owner's array: a 64-bit atomic over NVLink
 		atomicMin(&slots[idx], key);
+		// a reduction without return value is fire-and-forget: make sure it has been performed at the owner before this thread
+		// goes on (and, eventually, its kernel counts as complete for the peers' hand-shake in k_icp_reduce)
+		if (sm.world > 1) __threadfence_system();
 	}
 }
 // ------------------------------------------------------------------------------------------------------
@@ -1181,6 +1184,8 @@ __device__ __forceinline__ unsigned ld_volatile_sys_u32(const unsigned *p) { uns
 
 // all local blocks have stored (and fenced) their pass-`phase` partials; the last one to arrive raises this rank's flag on every peer
 __device__ __forceinline__ void red_arrive(IcpState *st, unsigned nblocks, unsigned phase, unsigned epoch, const IcpPeers &pe) {
+	// release: everything this block has written so far (partials, slot resets) before its arrival counts
+	if (pe.world > 1) __threadfence_system(); else __threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		const unsigned arrived = atomicAdd(&st->red_bar, 1u) + 1u;

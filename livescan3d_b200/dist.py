@@ -3,10 +3,10 @@
 Two sharded variants, both bit-identical to the single-GPU result:
 
   ShardedFrame  one or more sensor streams per GPU.  Every rank maps, culls and neighbour-counts its own sensors
-                (no communication), the per-rank survivor counts are all-gathered (world ints), and the final
-                compaction kernel stores every surviving 16-byte record straight into EVERY rank's merged buffer at
-                its global offset over NVLink peer stores (CUDA IPC mapped memory): compaction + all-gather in one
-                kernel, no NCCL on the vertex data.  formMesh's order (sensor order, row-major inside a sensor,
+                (no communication), the per-rank survivor counts are exchanged by peer stores inside one single-block
+                kernel (ls3d_frame_publish_counts), and the final compaction kernel stores every surviving 16-byte record
+                straight into EVERY rank's merged buffer at its global offset over NVLink peer stores (CUDA IPC mapped
+                memory): compaction + all-gather in one kernel, no collective library call anywhere.  formMesh's order (sensor order, row-major inside a sensor,
                 depthprocessing.cpp:1594-1608) is kept because ranks own contiguous sensor ranges.
 
   ShardedIcp    the target octree is replicated, the SOURCE points are partitioned, the dedupe slots and the reduction are
@@ -190,54 +190,64 @@ class PeerBuffer:
 # sensor streams sharded over GPUs, merged by peer stores
 # ---------------------------------------------------------------------------------------------------------
 class ShardedFrame:
+    """One rig over the ranks of a node: contiguous sensor ranges per rank, merged by peer stores.  Per frame a rank enqueues
+    (1) everything up to the neighbour count on its own sensors, (2) ls3d_frame_publish_counts — its survivor count goes into every
+    rank's sync block and its exclusive prefix comes back, all inside one single-block kernel, (3) the compaction kernel, whose
+    STG.128s land in EVERY rank's merged buffer at that prefix, (4) ls3d_frame_wait_peers.  No collective library call, no host
+    round trip: the four launches are stream-ordered (and graph-capturable)."""
+
     def __init__(self, widths, heights, group=None):
+        import ctypes as C
         import torch
-        from .device import FramePipeline
+        import torch.distributed as dist
+        from .device import FramePipeline, view
         self.group = group
         self.rank, self.world = _world(group)
         self.fp = FramePipeline(widths, heights)           # descriptors for the whole rig; only this rank's range is run
         self.first, self.n_own = sensor_ranges(self.fp.n_maps, self.world)[self.rank]
         self.merged = PeerBuffer(16 * self.fp.total_px, group)
-        dev = self.fp.device
-        self.kept_all = torch.zeros(self.world, dtype=torch.int32, device=dev)
-        self.kept_own = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.offset = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._fence = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sync = PeerBuffer(256, group)                 # Ls3dFrameSync of every rank, mapped everywhere
+        self._sync_i32 = view(self.sync.local, (64,), "<i4", self.fp.device)
+        self._sync_i32.zero_()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=group)                      # every block is zero before anyone's first publish can reach it
+        self._offset = view(int(self.sync.local) + 4, (1,), "<i4", self.fp.device)          # Ls3dFrameSync.offset
+        self._sync_tbl = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in self.sync.ptrs])
 
     def set_params(self, intr, wt, bounds, filter_k=10, filter_max_dist=0.01):
         self.fp.set_params(intr, wt, bounds, filter_k, filter_max_dist)
 
     def step(self, d_depth, d_colors):
         """Enqueue one frame on the current stream.  d_depth / d_colors use the packed whole-rig layout; only this rank's
-        sensor range has to hold data.  Afterwards every rank's merged buffer holds the whole merged cloud (rows
-        [0, kept_all.sum()))."""
-        import torch.distributed as dist
+        sensor range has to hold data.  Afterwards every rank's merged buffer holds the whole merged cloud."""
+        from . import native
+        from .device import _stream
+        lib = self.fp.lib
         if self.n_own > 0:
             self.fp.run_count(d_depth, d_colors, self.first, self.n_own)
-            self.kept_own.copy_(self.fp.counts[3:4])
-        else:
-            self.kept_own.zero_()
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.kept_all, self.kept_own, group=self.group)
-        else:
-            self.kept_all.copy_(self.kept_own)
-        self.offset.copy_(self.kept_all[: self.rank].sum().to(self.offset.dtype).reshape(1))      # 8 ints: plumbing, not data path
+        native.check(lib.ls3d_frame_publish_counts(self.fp.h if self.n_own > 0 else None, self.rank, self.world, self._sync_tbl, _stream()) == 0, "ls3d_frame_publish_counts")
         if self.n_own > 0:
-            self.fp.merge_peers(self.merged.ptrs, self.offset, self.first, self.n_own)
-        if self.world > 1:
-            dist.all_reduce(self._fence, group=self.group)     # every rank's peer stores are complete once this returns on the stream
+            self.fp.merge_peers(self.merged.ptrs, self._offset, self.first, self.n_own)
+        native.check(lib.ls3d_frame_wait_peers(self.rank, self.world, self._sync_tbl, _stream()) == 0, "ls3d_frame_wait_peers")
 
     def result(self):
         """Synchronise; -> (merged VertexC4ubV3f ndarray, per-rank counts)."""
         import torch
         from .api import VERTEX_DTYPE
+        from .native import Ls3dError
         torch.cuda.current_stream().synchronize()
-        counts = self.kept_all.cpu().numpy()
-        n = int(counts.sum())
+        blk = self._sync_i32.cpu().numpy()
+        if blk[3]:
+            raise Ls3dError(f"sharded frame: peer exchange error flags 0x{int(blk[3]):x}")
+        counts = blk[12:12 + self.world].copy()           # cnt_val
+        n = int(blk[2])                                    # total
+        assert n == int(counts.sum())
         v = self.merged.tensor((self.fp.total_px, 16), "|u1")[:n].cpu().numpy().reshape(-1).view(VERTEX_DTYPE)
         return v, counts
 
     def close(self):
+        self.sync.close()
         self.merged.close()
         self.fp.close()
 
@@ -373,7 +383,7 @@ def bench_sharded(args, rank, world, dev, flush):
     dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
     out["frame_one_rig_over_ranks"] = {"ms_per_step": ms, "clouds_per_s": 1000.0 / ms, "scaling": "strong", "merged": int(counts.sum()),
                                        "per_rank_counts": [int(c) for c in counts], "bit_identical_to_single_gpu_on_every_rank": bool(ok_all.item()),
-                                       "exchange": "all-gather of world ints (NCCL) + peer stores of 16*n_kept bytes to every rank (NVLink, CUDA IPC)"}
+                                       "exchange": "survivor counts and completion flags as peer stores inside two single-block kernels + peer stores of 16*n_kept bytes to every rank (NVLink, CUDA IPC); no collective call"}
     sf.close()
     if not bool(ok_all.item()):
         raise RuntimeError("sharded frame: the merged cloud differs from the single-GPU result on at least one rank")

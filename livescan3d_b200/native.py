@@ -106,6 +106,8 @@ _SIG = {
     "ls3d_icp_set_target": (_i, [_vp, _vp, _i, _vp]),
     "ls3d_icp_set_source": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ls3d_icp_match": (_i, [_vp, _vp]),
+    "ls3d_frame_publish_counts": (_i, [_vp, _i, _i, _vp, _vp]),
+    "ls3d_frame_wait_peers": (_i, [_i, _i, _vp, _vp]),
     "ls3d_icp_reduce": (_i, [_vp, _vp]),
     "ls3d_icp_set_peers": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "ls3d_icp_red_part": (_vp, [_vp]),

@@ -59,7 +59,7 @@ def _run_rank(rank, world, port, q):
 
         A, B = icp_pair(small_frame(S=2, w=128, h=96), synth.SERVER_BOUNDS)
         dA = torch.from_numpy(A).to(dev)
-        # the single-GPU result on this rank, then the sharded call three times (the third replays the captured graph)
+        # the single-GPU result on this rank, then the sharded call a dozen times (a race in the peer protocol shows up as a bit difference)
         from livescan3d_b200.device import IcpSolver
         dB = torch.from_numpy(B).to(dev)
         one = IcpSolver(len(A), len(B))
@@ -68,7 +68,7 @@ def _run_rank(rank, world, port, q):
         res["icp_single"] = (R1, t1, st1.tolist(), dB.cpu().numpy())
         one.close()
         si = ldist.ShardedIcp(len(A), len(B))
-        for rep in range(3):
+        for rep in range(12):                                  # the first is plain launches, the second captures, the rest replay the graph
             dB = torch.from_numpy(B).to(dev)
             si.run(dA, dB, 5)
             R, t, st = si.pose()
@@ -100,7 +100,7 @@ def _check(results, world):
     wv, wR, wt, _ = orc.orc_icp(A, B, max_iter=5)
     R1, t1, st1, v1 = results[0]["icp_single"]
     for r in range(world):
-        for key in ("icp_single", "icp_sharded_0", "icp_sharded_1", "icp_sharded_2"):
+        for key in ["icp_single"] + [f"icp_sharded_{rep}" for rep in range(12)]:
             R, t, st, v2 = results[r][key]
             assert st[0] == 5 and st[1] == 0
             assert rot_err(R, wR) <= 1e-5 and np.max(np.abs(t.astype(np.float64) - wt)) <= 1e-4      # north-star tolerances
