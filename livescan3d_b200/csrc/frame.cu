@@ -1088,7 +1088,7 @@ using namespace ls3d;
 enum { kTsMap = 0, kTsHashClear, kTsInsert, kTsRanges, kTsCount, kTsCompact, kTsOrganized, kTsWhole, kTsTriangles, kTsN };
 enum { kModeAuto = 0, kModeVoxelHash = 1, kModeOrganized = 2 };
 
-constexpr int kMaxChunks = 16, kEvN = 5 * kMaxChunks + 4;
+constexpr int kMaxChunks = 16, kEvN = 5 * kMaxChunks + 5;
 struct HostGraphKey { const void *depth, *colors, *out; int first, n_run, chunks, pull; unsigned long long params_version; };
 struct Ls3dFrame {
 	int device = 0;
@@ -1138,6 +1138,13 @@ struct Ls3dFrame {
 	int hg_launches = 0;
 	unsigned long long params_version = 0;   // bumped whenever frame_set_params changes anything on the device
 	cudaStream_t st_colors = nullptr, st_out = nullptr;     // host path: upload stream, read-back stream
+	// host path, pageable caller buffers: page-locked (mapped) staging the caller's depth / colours are copied into by the host copy
+	// pool, a host flag the merge stream waits on (the colours are still being copied while the neighbour count already runs), and
+	// the device-side count of such waits
+	unsigned char *stage_depth = nullptr, *stage_colors = nullptr;
+	unsigned *stage_flag = nullptr;
+	unsigned stage_seq = 0;
+	DevBuf stage_expect;
 	bool want_triangles = false;   // run the triangle stage after K1 (unfiltered runs only)
 	int *tri_override = nullptr;   // host mesh path: where this run's triangles go (a per-chunk region of `tri`)
 	DevBuf acc;                    // host mesh path: running totals + per-chunk records (k_mesh_chunk_done)
@@ -1181,6 +1188,10 @@ static void frame_free(Ls3dFrame *f) {
 	if (f->st_colors) cudaStreamDestroy(f->st_colors);
 	if (f->st_out) cudaStreamDestroy(f->st_out);
 	if (f->st_merge) cudaStreamDestroy(f->st_merge);
+	if (f->stage_depth) cudaFreeHost(f->stage_depth);
+	if (f->stage_colors) cudaFreeHost(f->stage_colors);
+	if (f->stage_flag) cudaFreeHost(f->stage_flag);
+	f->stage_expect.release();
 	for (cudaEvent_t x : f->ev_tr) if (x) cudaEventDestroy(x);
 	if (f->hg_exec) cudaGraphExecDestroy(f->hg_exec);
 	if (f->hm_exec) cudaGraphExecDestroy(f->hm_exec);
@@ -1480,6 +1491,19 @@ __global__ void __launch_bounds__(256) k_copy_mesh_out(const uint4 *__restrict__
 	} else if (blockIdx.x == 0) {
 		for (long long i = lo + threadIdx.x; i < hi; i += 256) t_host[i] = tris[i - lo] + v0;
 	}
+}
+
+// Host path with pageable caller buffers: the merge stream waits here until the host has finished copying the colours into the
+// page-locked staging block (it bumps *flag once per frame; *expect counts the waits on the device side).  Bounded spin.
+__global__ void k_wait_host_flag(const unsigned *flag, unsigned *expect, FrameCtl *ctl) {
+	if (threadIdx.x != 0) return;
+	const unsigned want = *expect + 1u;
+	unsigned spins = 0;
+	while ((int)(*reinterpret_cast<const volatile unsigned *>(flag) - want) < 0) {
+		if (++spins > (1u << 23)) { atomicOr(&ctl->err, kErrScanSpin); break; }
+		__nanosleep(200);
+	}
+	*expect = want;
 }
 
 // K1 launcher.  keep_px != nullptr: AND the organized neighbour-count mask into the validity test.
@@ -1900,10 +1924,31 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 				return true;
 			};
 			void *col_dev = nullptr;
-			const bool pull = env_mode == 2 && locked(depth_colors, &col_dev);
-			const bool graph_ok = env_graph != 0 && locked(depth_maps, nullptr) && (pull || locked(depth_colors, nullptr));
-			const uint8_t *col_src = pull ? (const uint8_t *)col_dev : dc;
 			bool ok = true;
+			// pageable caller buffers (a P/Invoke caller's GC-pinned byte[], KinectServer.cs:354-374): cudaMemcpyAsync from them would be
+			// staged by the driver on this thread, chunk after chunk, and nothing would overlap.  Instead the host copy pool moves the
+			// depth into page-locked staging, the schedule below starts from there (same pointers every frame: the captured graph is
+			// reused), and the colours are copied while the neighbour count already runs; the merge stream waits on a host flag.
+			static const int env_stage = getenv("LS3D_E2E_STAGE") ? atoi(getenv("LS3D_E2E_STAGE")) : 1;
+			const bool staged = env_stage != 0 && env_mode == 2 && !locked(depth_maps, nullptr);
+			if (staged) {
+				if (!f->stage_depth) {
+					ok = cuda_ok(cudaHostAlloc((void **)&f->stage_depth, std::max<size_t>(f->depth_bytes, 16), cudaHostAllocDefault), "alloc depth staging") &&
+						cuda_ok(cudaHostAlloc((void **)&f->stage_colors, std::max<size_t>(f->color_bytes, 16), cudaHostAllocMapped), "alloc colour staging") &&
+						cuda_ok(cudaHostAlloc((void **)&f->stage_flag, 64, cudaHostAllocMapped), "alloc staging flag") && f->stage_expect.reserve(256, "alloc staging counter") &&
+						cuda_ok(cudaMemset(f->stage_expect.p, 0, 256), "clear staging counter");
+					if (ok) { *f->stage_flag = 0; f->stage_seq = 0; }
+					else { if (f->stage_depth) cudaFreeHost(f->stage_depth); if (f->stage_colors) cudaFreeHost(f->stage_colors); if (f->stage_flag) cudaFreeHost(f->stage_flag); f->stage_depth = f->stage_colors = nullptr; f->stage_flag = nullptr; }
+				}
+				if (!ok) { host_block_free(v); return -1; }
+				parallel_memcpy(f->stage_depth + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off));
+			}
+			const unsigned char *src_depth = staged ? f->stage_depth : depth_maps, *src_colors = staged ? f->stage_colors : depth_colors;
+			void *flag_dev = nullptr;
+			if (staged) ok = cuda_ok(cudaHostGetDevicePointer(&flag_dev, f->stage_flag, 0), "map staging flag");
+			const bool pull = env_mode == 2 && locked(src_colors, &col_dev);
+			const bool graph_ok = env_graph != 0 && locked(src_depth, nullptr) && (pull || locked(src_colors, nullptr));
+			const uint8_t *col_src = pull ? (const uint8_t *)col_dev : dc;
 			for (int i = 0; i < kEvN && ok; i++)
 				if (!f->ev_up[i]) ok = cuda_ok(cudaEventCreateWithFlags(&f->ev_up[i], cudaEventDisableTiming), "create event");
 			for (int i = 0; i < 4 * kMaxChunks + 1 && ok && env_trace; i++)
@@ -1914,17 +1959,23 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 			cudaStream_t sm = f->st_merge, so = f->st_out;
 			auto bound = [&](int c) { return first + (int)((long long)n_run * c / Cn); };      // chunk c = sensors [bound(c), bound(c+1))
 			PeerDst none; none.n = 0;
+			bool wait_issued = false;          // staged: a k_wait_host_flag really is (or will be, via the graph) in flight
 			auto enqueue = [&]() -> bool {
 				bool k = trace(-1, 0, st) && cuda_ok(cudaEventRecord(ev_x[0], st), "fork") && cuda_ok(cudaStreamWaitEvent(up, ev_x[0], 0), "fork") &&
 					cuda_ok(cudaStreamWaitEvent(sm, ev_x[0], 0), "fork") && cuda_ok(cudaStreamWaitEvent(so, ev_x[0], 0), "fork") &&
 					cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block");
+				if (k && staged) {
+					// the merge stream (in order) starts with the wait for the colours; it must also see the cleared control block
+					k = cuda_ok(cudaEventRecord(ev_x[4], st), "order the flag wait") && cuda_ok(cudaStreamWaitEvent(sm, ev_x[4], 0), "order the flag wait");
+					if (k) { k_wait_host_flag<<<1, 32, 0, sm>>>((const unsigned *)flag_dev, f->stage_expect.as<unsigned>(), f->ctl); count_launch(1); k = cuda_ok(cudaGetLastError(), "k_wait_host_flag"); wait_issued = k; }
+				}
 				for (int c = 0; c < Cn && k; c++) {
 					const SensorDesc &ca = f->h_sd[bound(c)], &cz = f->h_sd[bound(c + 1)];
 					const int tlo = ca.tile_begin - a.tile_begin, thi = cz.tile_begin - a.tile_begin;
-					k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off, depth_maps + ca.depth_off, (size_t)(cz.depth_off - ca.depth_off), cudaMemcpyHostToDevice, up), "upload depth") &&
+					k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off, src_depth + ca.depth_off, (size_t)(cz.depth_off - ca.depth_off), cudaMemcpyHostToDevice, up), "upload depth") &&
 						cuda_ok(cudaEventRecord(ev_d[c], up), "record depth upload") && trace(0, c, up);
 					if (k && !pull)
-						k = cuda_ok(cudaMemcpyAsync(dc + ca.color_off, depth_colors + ca.color_off, (size_t)(cz.color_off - ca.color_off), cudaMemcpyHostToDevice, up), "upload colours") &&
+						k = cuda_ok(cudaMemcpyAsync(dc + ca.color_off, src_colors + ca.color_off, (size_t)(cz.color_off - ca.color_off), cudaMemcpyHostToDevice, up), "upload colours") &&
 							cuda_ok(cudaEventRecord(ev_c[c], up), "record colour upload");
 					k = k && cuda_ok(cudaStreamWaitEvent(st, ev_d[c], 0), "wait for the depth upload") && launch_organized_count(f, dd, bound(c), bound(c + 1), st) == 0 && trace(1, c, st) &&
 						cuda_ok(cudaEventRecord(ev_n[c], st), "record count") && cuda_ok(cudaStreamWaitEvent(sm, ev_n[c], 0), "wait for the count") &&
@@ -1947,7 +1998,7 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 			f->last_colors = dc;
 			f->ev_recorded = 0;
 			if (ok && graph_ok && !f->timing) {
-				const HostGraphKey key{depth_maps, depth_colors, v, first, n_run, Cn, pull ? 1 : 0, f->params_version};
+				const HostGraphKey key{src_depth, src_colors, v, first, n_run, Cn, (pull ? 1 : 0) | (staged ? 2 : 0), f->params_version};
 				if (!f->hg_exec || memcmp(&key, &f->hg_key, sizeof(key))) {
 					cudaGraph_t g = nullptr;
 					const long long l0 = g_launches.load();
@@ -1970,10 +2021,18 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 					if (g) cudaGraphDestroy(g);
 					if (ok) f->hg_key = key; else if (f->hg_exec) { cudaGraphExecDestroy(f->hg_exec); f->hg_exec = nullptr; }
 				}
+				wait_issued = false;            // capture only recorded it
 				ok = ok && cuda_ok(cudaGraphLaunch(f->hg_exec, st), "launch the frame graph");
-				if (ok) count_launch(f->hg_launches);
+				if (ok) { count_launch(f->hg_launches); wait_issued = staged; }
 			} else if (ok) {
 				ok = enqueue();
+			}
+			if (staged && wait_issued) {
+				// the device is already counting neighbours on the depth: now the colours, then release the merge stream.  The flag is
+				// bumped exactly when a wait kernel is in flight, so host and device counts never drift apart.
+				if (ok) parallel_memcpy(f->stage_colors + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off));
+				std::atomic_thread_fence(std::memory_order_release);
+				*reinterpret_cast<volatile unsigned *>(f->stage_flag) = ++f->stage_seq;
 			}
 			ok = cuda_ok(cudaStreamSynchronize(st), "frame pipeline") && ok;
 			if (ok && env_trace) {

@@ -31,6 +31,10 @@ void *host_block_alloc(size_t bytes);
 void host_block_free(void *p);
 bool host_block_is_pinned(void *p);     // true: page-locked and mapped, a kernel may store into it
 
+// memcpy spread over a small pool of host threads (the caller takes part): for moving the caller's pageable frame buffers into
+// the library's page-locked staging at more than one core's copy bandwidth.  Small sizes fall through to plain memcpy.
+void parallel_memcpy(void *dst, const void *src, size_t bytes);
+
 // device scratch with grow-only semantics
 struct DevBuf {
 	void *p = nullptr;

@@ -597,8 +597,8 @@ extern "C" void depthMapAndColorSetRadialCorrection(int n_maps, unsigned char *d
 		cuda_ok(cudaStreamSynchronize(st), "radial correction");
 	if (!ok) return;
 	if (*c->pin_err) { set_error("radial correction: device status flags 0x%x", *c->pin_err); return; }
-	memcpy(depth_maps, c->pin_out, 2 * n);
-	memcpy(depth_colors, c->pin_out + 2 * n, 3 * n);
+	parallel_memcpy(depth_maps, c->pin_out, 2 * n);
+	parallel_memcpy(depth_colors, c->pin_out + 2 * n, 3 * n);
 }
 
 // KinectCapture::filterFlyingPixels (kinectCapture.cpp:132-174) on one host depth image, in place.  maxNonFittingNeighbours is accepted and

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <thread>
 #include <vector>
 
 namespace ls3d {
@@ -129,6 +131,89 @@ void host_block_free(void *p) {
 		return;
 	}
 	if (hb.pinned) cudaFreeHost(p); else free(p);
+}
+
+// ---- host copy pool -----------------------------------------------------------------------------------
+// One job at a time (callers hold api_mutex()).  A job is cut into 256 KB slices handed out by an atomic counter; the workers
+// and the caller pull slices until none is left.  After a job the workers keep polling for ~200 us before they go back to
+// sleep on the condition variable, so back-to-back frames do not pay a wake-up each.
+namespace {
+struct CopyPool {
+	std::vector<std::thread> workers;
+	std::mutex m;
+	std::condition_variable cv;
+	std::atomic<unsigned long long> generation{0};
+	std::atomic<bool> stop{false};
+	// job description: atomics, because a worker that is late leaving the previous job may look at them while the next is set up
+	// (it then simply takes part in the next job: `next` is published last, with release semantics)
+	std::atomic<unsigned char *> dst{nullptr};
+	std::atomic<const unsigned char *> src{nullptr};
+	std::atomic<size_t> bytes{0}, n_slices{0};
+	std::atomic<size_t> next{0}, done{0};
+	static constexpr size_t kSlice = 256 * 1024;
+
+	void work() {
+		for (;;) {
+			const size_t i = next.fetch_add(1, std::memory_order_acq_rel);
+			if (i >= n_slices.load(std::memory_order_relaxed)) return;
+			const size_t off = i * kSlice, n = std::min(kSlice, bytes.load(std::memory_order_relaxed) - off);
+			memcpy(dst.load(std::memory_order_relaxed) + off, src.load(std::memory_order_relaxed) + off, n);
+			done.fetch_add(1, std::memory_order_release);
+		}
+	}
+	void worker_main() {
+		unsigned long long seen = 0;
+		for (;;) {
+			// poll briefly, then sleep
+			bool got = false;
+			for (int spin = 0; spin < 20000 && !got; spin++) {
+				if (stop.load(std::memory_order_relaxed)) return;
+				got = generation.load(std::memory_order_acquire) != seen;
+				if (!got) std::this_thread::yield();
+			}
+			if (!got) {
+				std::unique_lock<std::mutex> lk(m);
+				cv.wait(lk, [&] { return stop.load() || generation.load(std::memory_order_acquire) != seen; });
+				if (stop.load()) return;
+			}
+			seen = generation.load(std::memory_order_acquire);
+			work();
+		}
+	}
+	explicit CopyPool(int n) {
+		for (int i = 0; i < n; i++) workers.emplace_back([this] { worker_main(); });
+	}
+	~CopyPool() {
+		{ std::lock_guard<std::mutex> lk(m); stop.store(true); }
+		cv.notify_all();
+		for (auto &t : workers) t.join();
+	}
+	void run(void *d, const void *s, size_t n) {
+		const size_t ns = (n + kSlice - 1) / kSlice;
+		next.store(~(size_t)0 / 2, std::memory_order_relaxed);          // park late workers while the job is being described
+		dst.store((unsigned char *)d); src.store((const unsigned char *)s); bytes.store(n); n_slices.store(ns);
+		done.store(0, std::memory_order_relaxed);
+		next.store(0, std::memory_order_release);
+		{ std::lock_guard<std::mutex> lk(m); generation.fetch_add(1, std::memory_order_release); }
+		cv.notify_all();
+		work();
+		while (done.load(std::memory_order_acquire) < ns) std::this_thread::yield();
+	}
+};
+CopyPool *g_copy_pool = nullptr;
+std::mutex g_copy_mutex;
+}  // namespace
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+	if (bytes < 2 * CopyPool::kSlice) { memcpy(dst, src, bytes); return; }
+	std::lock_guard<std::mutex> lk(g_copy_mutex);
+	if (!g_copy_pool) {
+		static const int env = getenv("LS3D_COPY_THREADS") ? atoi(getenv("LS3D_COPY_THREADS")) : -1;
+		const unsigned hw = std::thread::hardware_concurrency();
+		const int n = env >= 0 ? env : (int)std::max(1u, std::min(6u, hw > 2 ? hw / 2 - 1 : 0u));      // + the caller
+		g_copy_pool = new CopyPool(std::max(0, std::min(n, 16)));      // never destroyed: worker threads must not be joined from a library destructor
+	}
+	g_copy_pool->run(dst, src, bytes);
 }
 
 bool DevBuf::reserve(size_t bytes, const char *what) {

@@ -332,13 +332,53 @@ class ShardedIcp:
 # ---------------------------------------------------------------------------------------------------------
 # bench.py's "sharded" block (N > 1)
 # ---------------------------------------------------------------------------------------------------------
+def refine_poses_sharded(clouds, n_refine_iters: int = 2, n_icp_iters: int = 10, group=None):
+    """LiveScanServer's refine schedule (MainWindowForm.cs:349-375; livescan3d_b200/refine.py) with every ICP call sharded over
+    the ranks: target = the other sensors' clouds (replicated), source = cloud i, searched in slices.  clouds: CUDA tensors,
+    identical on every rank, moved in place.  Returns (Rs, Ts) — the same bits on every rank and as refine_poses_device."""
+    import torch
+    S = len(clouds)
+    n = [int(c.shape[0]) for c in clouds]
+    si = ShardedIcp(max(1, sum(n) - (min(n) if n else 0)), max(1, max(n) if n else 1), group)
+    try:
+        Rs = np.stack([np.eye(3, dtype=np.float32) for _ in range(S)])
+        Ts = np.zeros((S, 3), dtype=np.float32)
+        poses = torch.zeros((S, 12), dtype=torch.float32, device=clouds[0].device)
+        poses[:, 0] = poses[:, 4] = poses[:, 8] = 1.0
+        keep_alive = []
+        for it in range(int(n_refine_iters)):
+            if it > 0:
+                torch.cuda.current_stream().synchronize()
+                rt = poses.cpu().numpy()
+                Rs, Ts = rt[:, :9].reshape(S, 3, 3).copy(), rt[:, 9:].copy()
+                keep_alive.clear()
+            for i in range(S):
+                others = [clouds[j] for j in range(S) if j != i and n[j] > 0]
+                if not others or n[i] == 0:
+                    continue
+                verts1 = torch.cat(others).contiguous()
+                keep_alive.append(verts1)
+                si.run(verts1, clouds[i], n_icp_iters, Rs[i], Ts[i])
+                poses[i].copy_(si.solver.Rt)
+        torch.cuda.current_stream().synchronize()
+        out = poses.cpu().numpy()
+    finally:
+        si.close()
+    return out[:, :9].reshape(S, 3, 3).copy(), out[:, 9:].copy()
+
+
 def bench_sharded(args, rank, world, dev, flush):
-    """Strong-scaling variants: ONE 8-sensor rig split over the ranks (peer-store merge) and ONE ICP pair with the source
-    partitioned.  Checked against this rank's own single-GPU result before timing.  Times are CUDA events, max over ranks."""
+    """Strong-scaling variants, every one checked bit for bit against this rank's own single-GPU result (a mismatch raises, which
+    makes bench.py exit non-zero): ONE rig split over the ranks (peer-store merge) and ONE ICP call with the source partitioned —
+    on the bench sizes (8 x 512x424, 2 x 213 k points), on BASELINE.json configs[4] (8 x 1920x1080; 2 x 2 M points) and on
+    configs[3] (the global refine schedule: 16 ICP calls against the other seven clouds).  Times are CUDA events (the refine: wall
+    clock), max over ranks; the single-GPU time of the same work, measured in the same process, sits beside each."""
+    import os
+    import time
     import torch
     import torch.distributed as dist
     import bench
-    from . import api
+    from . import api, refine, synth
     from .device import FramePipeline, IcpSolver
 
     def max_over_ranks(x):
@@ -346,81 +386,132 @@ def bench_sharded(args, rank, world, dev, flush):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ok(flag: bool) -> bool:
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
     def sync():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
 
+    steps = max(3, args.steps)
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+
+    def timed(fn, prep=None, reps=steps):
+        for _ in range(max(args.warmup, 3)):
+            if prep:
+                prep()
+            fn()
+        sync()
+        for i in range(reps):
+            if prep:
+                prep()
+            flush.zero_()
+            ev_s[i].record()
+            fn()
+            ev_e[i].record()
+        sync()
+        return max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in zip(ev_s[:reps], ev_e[:reps])])))
+
+    def frame_case(frame, bounds, k, md, label):
+        d_depth = torch.from_numpy(frame["depth_maps"]).to(dev)
+        d_colors = torch.from_numpy(frame["depth_colors"]).to(dev)
+        fp = FramePipeline(frame["widths"], frame["heights"])
+        fp.set_params(frame["intr"], frame["wt"], bounds, k, md)
+        one_ms = timed(lambda: fp.run(d_depth, d_colors))
+        want, _ = fp.result()
+        want = want.copy()
+        fp.close()
+        sf = ShardedFrame(frame["widths"], frame["heights"])
+        sf.set_params(frame["intr"], frame["wt"], bounds, k, md)
+        ms = timed(lambda: sf.step(d_depth, d_colors))
+        got, counts = sf.result()
+        same = all_ok(got.tobytes() == want.tobytes())
+        sf.close()
+        del d_depth, d_colors
+        res = {"workload": label, "ms_per_step": ms, "clouds_per_s": 1000.0 / ms, "single_gpu_ms_per_step": one_ms, "speedup_vs_single_gpu": one_ms / ms, "scaling": "strong",
+               "merged": int(counts.sum()), "per_rank_counts": [int(c) for c in counts], "bit_identical_to_single_gpu_on_every_rank": same,
+               "exchange": "survivor counts and completion flags as peer stores inside two single-block kernels + peer stores of 16*n_kept bytes to every rank (NVLink, CUDA IPC); no collective call"}
+        if not same:
+            raise RuntimeError(f"sharded frame ({label}): the merged cloud differs from the single-GPU result on at least one rank")
+        return res
+
+    def icp_case(A, B, label):
+        dA = torch.from_numpy(A).to(dev)
+        dB0 = torch.from_numpy(B).to(dev)
+        dB = dB0.clone()
+        one = IcpSolver(len(A), len(B))
+
+        def run_one():
+            one.set_target(dA); one.set_source(dB); one.run(bench.ICP_ITERS)
+        one_ms = timed(run_one, prep=lambda: dB.copy_(dB0))
+        R1, t1, _ = one.pose()
+        v1 = dB.clone()
+        one.close()
+        si = ShardedIcp(len(A), len(B))
+        ms = timed(lambda: si.run(dA, dB, bench.ICP_ITERS), prep=lambda: dB.copy_(dB0))
+        R, t, st = si.pose()
+        same = all_ok(np.array_equal(R, R1) and np.array_equal(t, t1) and bool(torch.equal(dB, v1)) and int(st[1]) == 0)
+        si.close()
+        res = {"workload": label, "n1": len(A), "n2": len(B), "ms_per_step": ms, "ms_per_iter": ms / bench.ICP_ITERS, "Mpts_iter_per_s": len(B) * bench.ICP_ITERS / (ms / 1000.0) / 1e6,
+               "single_gpu_ms_per_step": one_ms, "speedup_vs_single_gpu": one_ms / ms, "scaling": "strong", "bit_identical_to_single_gpu_on_every_rank": same, "status": [int(x) for x in st],
+               "exchange": "dedupe keys: 64-bit atomicMin into the owner rank's slots over NVLink; partial sums: peer stores + flags inside k_icp_reduce; no collective call in the loop"}
+        del dA, dB, dB0, v1
+        if not same:
+            raise RuntimeError(f"sharded ICP ({label}): R, t or the moved cloud differ from the single-GPU result (status {st}); they must be bit-identical")
+        return res
+
+    xyz = lambda v: np.ascontiguousarray(np.stack([v["X"], v["Y"], v["Z"]], axis=1), dtype=np.float32)
     out = {}
     frame, pair = bench.make_inputs(0)                       # every rank: the SAME rig / pair (rank 0's)
-    d_depth = torch.from_numpy(frame["depth_maps"]).to(dev)
-    d_colors = torch.from_numpy(frame["depth_colors"]).to(dev)
-
-    # ---- frame: single-GPU truth on this rank, then the sharded run
-    fp = FramePipeline(frame["widths"], frame["heights"])
-    fp.set_params(frame["intr"], frame["wt"], bench.FRAME_BOUNDS, bench.FILTER_K, bench.FILTER_MAXDIST)
-    fp.run(d_depth, d_colors)
-    want, _ = fp.result()
-    want = want.copy()
-    fp.close()
-    sf = ShardedFrame(frame["widths"], frame["heights"])
-    sf.set_params(frame["intr"], frame["wt"], bench.FRAME_BOUNDS, bench.FILTER_K, bench.FILTER_MAXDIST)
-    for _ in range(max(args.warmup, 3)):
-        sf.step(d_depth, d_colors)
-    got, counts = sf.result()
-    same = got.tobytes() == want.tobytes()
-    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sync()
-    for i in range(args.steps):
-        flush.zero_()
-        ev_s[i].record()
-        sf.step(d_depth, d_colors)
-        ev_e[i].record()
-    sync()
-    ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / args.steps
-    ok_all = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
-    dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
-    out["frame_one_rig_over_ranks"] = {"ms_per_step": ms, "clouds_per_s": 1000.0 / ms, "scaling": "strong", "merged": int(counts.sum()),
-                                       "per_rank_counts": [int(c) for c in counts], "bit_identical_to_single_gpu_on_every_rank": bool(ok_all.item()),
-                                       "exchange": "survivor counts and completion flags as peer stores inside two single-block kernels + peer stores of 16*n_kept bytes to every rank (NVLink, CUDA IPC); no collective call"}
-    sf.close()
-    if not bool(ok_all.item()):
-        raise RuntimeError("sharded frame: the merged cloud differs from the single-GPU result on at least one rank")
-
-    # ---- ICP: single-GPU truth, then partitioned source
+    out["frame_one_rig_over_ranks"] = frame_case(frame, bench.FRAME_BOUNDS, bench.FILTER_K, bench.FILTER_MAXDIST, "8 x 512x424, cull +-1.5 m, filter (10, 0.01)")
     A, B = bench.icp_clouds(pair, api.generate_vertices_from_depth_map)
-    dA = torch.from_numpy(A).to(dev)
-    dB0 = torch.from_numpy(B).to(dev)
-    dB = dB0.clone()
-    one = IcpSolver(len(A), len(B))
-    one.set_target(dA)
-    one.set_source(dB)
-    one.run(bench.ICP_ITERS)
-    R1, t1, _ = one.pose()
-    one.close()
-    si = ShardedIcp(len(A), len(B))
-    for _ in range(max(args.warmup, 3)):
-        dB.copy_(dB0)
-        si.run(dA, dB, bench.ICP_ITERS)
-    R, t, st = si.pose()
-    sync()
-    for i in range(args.steps):
-        dB.copy_(dB0)
-        flush.zero_()
-        ev_s[i].record()
-        si.run(dA, dB, bench.ICP_ITERS)
-        ev_e[i].record()
-    sync()
-    ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / args.steps
-    dR_s, dt_s = float(np.max(np.abs(R.astype(np.float64) - R1))), float(np.max(np.abs(t.astype(np.float64) - t1)))
-    out["icp_source_partitioned"] = {
-        "ms_per_step": ms, "ms_per_iter": ms / bench.ICP_ITERS, "Mpts_iter_per_s": len(B) * bench.ICP_ITERS / (ms / 1000.0) / 1e6, "scaling": "strong",
-        "max_abs_dR_vs_single_gpu": dR_s, "max_abs_dt_vs_single_gpu_m": dt_s, "status": [int(x) for x in st],
-        "exchange": "dedupe keys: 64-bit atomicMin into the owner rank's slots over NVLink; partial sums: peer stores + flags inside k_icp_reduce; no collective call in the loop"}
-    si.close()
-    bad = torch.tensor([0 if (dR_s == 0.0 and dt_s == 0.0 and int(st[1]) == 0) else 1], dtype=torch.int32, device=dev)
-    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-    if int(bad.item()):
-        raise RuntimeError(f"sharded ICP: pose differs from the single-GPU result (dR={dR_s:.3e}, dt={dt_s:.3e} m, status {st}); it must be bit-identical")
+    out["icp_source_partitioned"] = icp_case(A, B, "bench pair: sensors 0/1 of the 8-ring at 512x424, cull +-5 m")
+    if os.environ.get("LS3D_BENCH_STRESS", "1") != "0":
+        # ---- BASELINE.json configs[3]: the global refine (2 refine iterations x 8 sensors, target = the other 7 clouds, ~1.49 M points)
+        ring = synth.make_frame(8, synth.KINECT_W, synth.KINECT_H)
+        clouds = []
+        for i in range(8):
+            c = xyz(api.generate_vertices_from_depth_map(ring, synth.SERVER_BOUNDS, i))
+            if i:
+                c = synth.perturb(c, deg=0.3 + 0.1 * i, trans_mm=(2.0 * i, -3.0, 1.0 * i))
+            clouds.append(np.ascontiguousarray(c))
+        dev0 = [torch.from_numpy(c).to(dev) for c in clouds]
+
+        def wall(fn, reps=3):
+            ts = []
+            for it in range(reps + 1):
+                dc = [c.clone() for c in dev0]
+                sync()
+                t0 = time.perf_counter()
+                r = fn(dc)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                if it:
+                    ts.append(dt)
+            return max_over_ranks(float(np.median(ts))) * 1000.0, r, dc
+        one_ms, (R1s, T1s), dc1 = wall(lambda dc: refine.refine_poses_device(dc, 2, bench.ICP_ITERS))
+        ms, (Rs, Ts), dcs = wall(lambda dc: refine_poses_sharded(dc, 2, bench.ICP_ITERS))
+        same = all_ok(np.array_equal(Rs, R1s) and np.array_equal(Ts, T1s) and all(bool(torch.equal(a, b)) for a, b in zip(dc1, dcs)))
+        n2_total = 2 * sum(len(c) for c in clouds)
+        out["global_refine_8_sensors"] = {"workload": "BASELINE.json configs[3]: refine schedule of MainWindowForm.cs:349-375, 16 ICP calls x 10 iterations, target = the other 7 clouds",
+                                          "n_target_per_call": int(sum(len(c) for c in clouds) - len(clouds[0])), "ms_per_refine": ms, "single_gpu_ms_per_refine": one_ms, "speedup_vs_single_gpu": one_ms / ms,
+                                          "Mpts_iter_per_s": n2_total * bench.ICP_ITERS / (ms / 1000.0) / 1e6, "bit_identical_to_single_gpu_on_every_rank": same,
+                                          "timing": "wall clock around the whole schedule (device-resident clouds, one host wait per refine iteration), median of 3, max over ranks"}
+        del dev0, dc1, dcs
+        if not same:
+            raise RuntimeError("sharded global refine: poses or clouds differ from the single-GPU schedule")
+        # ---- BASELINE.json configs[4]: 8 x 1920x1080 and the 2 M-point ICP
+        W, H = 1920, 1080
+        big = synth.make_frame(8, W, H)
+        out["stress_frame_one_rig_over_ranks"] = frame_case(big, synth.DEFAULT_BOUNDS, 10, 0.004, "BASELINE.json configs[4]: 8 x 1920x1080, cull +-1.5 m, filter (10, 0.004)")
+        del big
+        pair_big = synth.make_frame(2, W, H, ring=8)
+        A2 = xyz(api.generate_vertices_from_depth_map(pair_big, synth.SERVER_BOUNDS, 0))
+        B2 = synth.perturb(xyz(api.generate_vertices_from_depth_map(pair_big, synth.SERVER_BOUNDS, 1)))
+        torch.cuda.empty_cache()
+        out["stress_icp_source_partitioned"] = icp_case(A2, B2, "BASELINE.json configs[4]: sensors 0/1 of the 8-ring at 1920x1080, cull +-5 m (2 x ~2 M points)")
     return out
