@@ -126,6 +126,14 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 {
 	__shared__ unsigned sm[16];
 	__shared__ int s_tile;
+	// look-back variant: the world positions pass 1 computes are parked here (thread-private slots, [coordinate][pixel][thread]:
+	// conflict-free, no barrier) and read back by pass 2 — 48 shared-memory accesses instead of ~360 instructions of recomputation
+	// per thread, without the 24 live registers that made the first staged version lose a resident block
+	__shared__ float s_pos[kKeepMask ? 1 : 3][kKeepMask ? 1 : 8][kKeepMask ? 1 : kScanThreads];
+	// multi-GPU merge (peers.n > 0; launched with kTile * 16 bytes of dynamic shared memory): a tile's records are staged here
+	// and then copied to every rank's buffer by whole warps — 512 contiguous bytes per store instruction; a thread storing its
+	// own few records one by one over NVLink ran at a fifth of the link rate
+	extern __shared__ __align__(16) uint4 s_stage[];
 
 	const int tile0 = sd[s_first].tile_begin;
 	const int ntiles = sd[s_end].tile_begin - tile0;
@@ -196,7 +204,10 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 #pragma unroll 1
 			for (int j = 0; j < 8; j++) {
 				float wx, wy, wz;
-				if (map_pixel(m, __ldg(xray + x), yn, depth_of(j), wx, wy, wz)) valid |= 1u << j;
+				if (map_pixel(m, __ldg(xray + x), yn, depth_of(j), wx, wy, wz)) {
+					valid |= 1u << j;
+					if (!kKeepMask) { s_pos[0][j][tid] = wx; s_pos[1][j][tid] = wy; s_pos[2][j][tid] = wz; }
+				}
 				if (++x == w) { x = 0; y++; yn = __ldg(yray + min(y, sd[s].h - 1)); }
 			}
 		}
@@ -251,10 +262,14 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 			while (rest) {
 				const int j = __ffs(rest) - 1;
 				rest &= rest - 1;
-				int x = x0 + j, y = y0;
-				while (x >= w) { x -= w; y++; }
 				float wx, wy, wz;
-				map_pixel(m, __ldg(xray + x), __ldg(yray + y), depth_of(j), wx, wy, wz);
+				if (kKeepMask) {
+					int x = x0 + j, y = y0;
+					while (x >= w) { x -= w; y++; }
+					map_pixel(m, __ldg(xray + x), __ldg(yray + y), depth_of(j), wx, wy, wz);
+				} else {
+					wx = s_pos[0][j][tid]; wy = s_pos[1][j][tid]; wz = s_pos[2][j][tid];
+				}
 				// bytes 3j, 3j+1, 3j+2 of the 24-byte colour block -> R,G,B,255
 				const int bi = 3 * j, wi = bi >> 2;
 				const unsigned lo = wi == 0 ? c0 : wi == 1 ? c1 : wi == 2 ? c2 : wi == 3 ? c3 : wi == 4 ? c4 : c5;
@@ -262,9 +277,17 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 				const unsigned rgb = __funnelshift_r(lo, hi, 8 * (bi & 3)) & 0xffffffu;
 				const uint4 rec = make_uint4(rgb | 0xff000000u, __float_as_uint(wx), __float_as_uint(wy), __float_as_uint(wz));
 				if (peers.n == 0) out[o] = rec;
-				else for (int p = 0; p < peers.n; p++) peers.ptr[p][o] = rec;
+				else s_stage[o - ((size_t)out_off + base)] = rec;
 				o++;
 			}
+		}
+		if (peers.n > 0) {
+			__syncthreads();
+			for (int p = 0; p < peers.n; p++) {
+				uint4 *dst = peers.ptr[p] + (size_t)out_off + base;
+				for (unsigned i = tid; i < total; i += kScanThreads) dst[i] = s_stage[i];
+			}
+			__syncthreads();
 		}
 		if (kWriteD2V) {
 			int *dst = d2v + sd[s].pix_begin + p0;
@@ -1521,13 +1544,24 @@ static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, i
 	const float *rays = f->rays.as<float>();
 	const unsigned *tc = reinterpret_cast<const unsigned *>(f->status_b);      // per-tile survivor counts left by the organized count
 	if (f->colors_ready && !cuda_ok(cudaStreamWaitEvent(st, f->colors_ready, 0), "wait for the colour upload")) return -1;
+	const size_t stage_bytes = peers.n > 0 ? (size_t)kTile * sizeof(uint4) : 0;      // 32 KB on top of up to 24 KB static: needs the opt-in
+	if (stage_bytes) {
+		static bool attr = false;
+		if (!attr) {
+			if (!cuda_ok(cudaFuncSetAttribute(k_map_cull_compact<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes), "merge staging") ||
+				!cuda_ok(cudaFuncSetAttribute(k_map_cull_compact<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes), "merge staging") ||
+				!cuda_ok(cudaFuncSetAttribute(k_map_cull_compact<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes), "merge staging") ||
+				!cuda_ok(cudaFuncSetAttribute(k_map_cull_compact<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes), "merge staging")) return -1;
+			attr = true;
+		}
+	}
 	stage_begin(f, kTsMap, st);
 	if (f->want_d2v || f->want_triangles) {
-		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers, tile_lo, tile_hi);
-		else k_map_cull_compact<true, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers, tile_lo, tile_hi);
+		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, stage_bytes, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers, tile_lo, tile_hi);
+		else k_map_cull_compact<true, false><<<blocks, kScanThreads, stage_bytes, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers, tile_lo, tile_hi);
 	} else {
-		if (keep_px) k_map_cull_compact<false, true><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers, tile_lo, tile_hi);
-		else k_map_cull_compact<false, false><<<blocks, kScanThreads, 0, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers, tile_lo, tile_hi);
+		if (keep_px) k_map_cull_compact<false, true><<<blocks, kScanThreads, stage_bytes, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers, tile_lo, tile_hi);
+		else k_map_cull_compact<false, false><<<blocks, kScanThreads, stage_bytes, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers, tile_lo, tile_hi);
 	}
 	stage_end(f, kTsMap, st);
 	count_launch(1);

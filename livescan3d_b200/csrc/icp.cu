@@ -458,10 +458,7 @@ __device__ __forceinline__ void nn_commit(int i, float d2, int idx, const SlotMa
 		const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
 		unsigned long long *slots = sm.ptr[0];
 		if (sm.world > 1) slots = sm.ptr[min(sm.world - 1, (idx / sm.chunk) / sm.per)];      // the owner's array: a 64-bit atomic over NVLink
-		atomicMin(&slots[idx], key);
-		// a reduction without return value is fire-and-forget: make sure it has been performed at the owner before this thread
-		// goes on (and, eventually, its kernel counts as complete for the peers' hand-shake in k_icp_reduce)
-		if (sm.world > 1) __threadfence_system();
+		atomicMin(&slots[idx], key);      // remote ones are ordered system-wide by the block's fence at the end of the match kernels
 	}
 }
 // ------------------------------------------------------------------------------------------------------
@@ -909,7 +906,7 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_
 		__syncwarp();
 	}
 	// the last block to run dry re-arms the packet counter for the next match stage
-	__threadfence();                                                  // this block's results before its arrival
+	if (slotmap.world > 1) __threadfence_system(); else __threadfence();      // this block's results (incl. keys sent to peers) before its arrival
 	__syncthreads();
 	if (threadIdx.x == 0 && atomicAdd(&state->blocks_done, 1u) == gridDim.x - 1) {
 		state->blocks_done = 0;
@@ -1101,6 +1098,7 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_HV_MINBLOCKS) k_icp_match_
 		}
 	}
 	// the last block re-arms the queue for the next match stage
+	if (slotmap.world > 1) __threadfence_system();
 	if (threadIdx.x == 0 && atomicAdd(&state->hq_done, 1u) == gridDim.x - 1) {
 		state->hq_done = 0;
 		state->hq_head = 0;
@@ -1184,10 +1182,12 @@ __device__ __forceinline__ unsigned ld_volatile_sys_u32(const unsigned *p) { uns
 
 // all local blocks have stored (and fenced) their pass-`phase` partials; the last one to arrive raises this rank's flag on every peer
 __device__ __forceinline__ void red_arrive(IcpState *st, unsigned nblocks, unsigned phase, unsigned epoch, const IcpPeers &pe) {
-	// release: everything this block has written so far (partials, slot resets) before its arrival counts
-	if (pe.world > 1) __threadfence_system(); else __threadfence();
+	// release: everything this block has written so far (partials into the peers' tables, slot resets) before its arrival counts.
+	// One fence by the arriving thread after the block barrier is cumulative over the block's writes; a system-scope fence in
+	// every thread (first version) cost ~10 us per pass.
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		if (pe.world > 1) __threadfence_system(); else __threadfence();
 		const unsigned arrived = atomicAdd(&st->red_bar, 1u) + 1u;
 		if (pe.world > 1 && arrived == phase * nblocks) {
 			__threadfence_system();
@@ -1216,7 +1216,6 @@ __device__ __forceinline__ void red_store(const double *smem, int c, int phase, 
 	if (threadIdx.x < NV && c >= 0) {
 		const double v = smem[threadIdx.x];
 		for (int r = 0; r < pe.world; r++) pe.part[r][(size_t)(phase - 1) * kRedPhaseStride + (size_t)c * 16 + threadIdx.x] = v;
-		if (pe.world > 1) __threadfence_system(); else __threadfence();
 	}
 }
 
