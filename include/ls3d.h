@@ -73,8 +73,10 @@ void generateMeshFromDepthMaps(int n_maps, unsigned char *depth_maps, unsigned c
  * C# binding LiveScanServer/KinectServer.cs:51-53.  Radial-distortion correction of every sensor's depth and colour map,
  * IN PLACE in the caller's packed buffers: forward warp by 1 - r2*r - r4*r^2 - r6*r^3 (the last source pixel in raster order
  * wins a destination), then the reference's in-place raster-order hole fill (a zero pixel with more than 4 mutually
- * consistent non-zero neighbours becomes their integer mean).  Bit-identical to the reference; on failure the buffers are
- * left untouched and ls3d_last_error() says why. */
+ * consistent non-zero neighbours becomes their integer mean).  Bit-identical to the reference.  The buffers are written only
+ * after every kernel has finished and the device status has been read back clean: a failure before that leaves them untouched
+ * and ls3d_last_error() says why (only a failing device-to-host transfer of the finished result can leave them undefined, and
+ * the error text then says so). */
 void depthMapAndColorSetRadialCorrection(int n_maps, unsigned char *depth_maps, unsigned char *depth_colors, int *widths, int *heights, float *intr_params);
 
 /* Replace src/NativeUtils/depthprocessing.cpp:1818-1835 (C# KinectServer.cs:56-60).  deleteMesh releases the

@@ -1161,13 +1161,11 @@ struct Ls3dFrame {
 	int hg_launches = 0;
 	unsigned long long params_version = 0;   // bumped whenever frame_set_params changes anything on the device
 	cudaStream_t st_colors = nullptr, st_out = nullptr;     // host path: upload stream, read-back stream
-	// host path, pageable caller buffers: page-locked (mapped) staging the caller's depth / colours are copied into by the host copy
-	// pool, a host flag the merge stream waits on (the colours are still being copied while the neighbour count already runs), and
-	// the device-side count of such waits
+	// host path, pageable caller buffers: page-locked (mapped) staging the caller's depth / colours are copied into by the host copy pool
 	unsigned char *stage_depth = nullptr, *stage_colors = nullptr;
-	unsigned *stage_flag = nullptr;
-	unsigned stage_seq = 0;
-	DevBuf stage_expect;
+	cudaGraphExec_t hg_exec_b = nullptr;   // ... and the second half of the schedule (merge + read-back), launched once the colours are staged
+	HostGraphKey hg_key_b = {};
+	int hg_launches_b = 0;
 	bool want_triangles = false;   // run the triangle stage after K1 (unfiltered runs only)
 	int *tri_override = nullptr;   // host mesh path: where this run's triangles go (a per-chunk region of `tri`)
 	DevBuf acc;                    // host mesh path: running totals + per-chunk records (k_mesh_chunk_done)
@@ -1213,8 +1211,7 @@ static void frame_free(Ls3dFrame *f) {
 	if (f->st_merge) cudaStreamDestroy(f->st_merge);
 	if (f->stage_depth) cudaFreeHost(f->stage_depth);
 	if (f->stage_colors) cudaFreeHost(f->stage_colors);
-	if (f->stage_flag) cudaFreeHost(f->stage_flag);
-	f->stage_expect.release();
+	if (f->hg_exec_b) cudaGraphExecDestroy(f->hg_exec_b);
 	for (cudaEvent_t x : f->ev_tr) if (x) cudaEventDestroy(x);
 	if (f->hg_exec) cudaGraphExecDestroy(f->hg_exec);
 	if (f->hm_exec) cudaGraphExecDestroy(f->hm_exec);
@@ -1514,19 +1511,6 @@ __global__ void __launch_bounds__(256) k_copy_mesh_out(const uint4 *__restrict__
 	} else if (blockIdx.x == 0) {
 		for (long long i = lo + threadIdx.x; i < hi; i += 256) t_host[i] = tris[i - lo] + v0;
 	}
-}
-
-// Host path with pageable caller buffers: the merge stream waits here until the host has finished copying the colours into the
-// page-locked staging block (it bumps *flag once per frame; *expect counts the waits on the device side).  Bounded spin.
-__global__ void k_wait_host_flag(const unsigned *flag, unsigned *expect, FrameCtl *ctl) {
-	if (threadIdx.x != 0) return;
-	const unsigned want = *expect + 1u;
-	unsigned spins = 0;
-	while ((int)(*reinterpret_cast<const volatile unsigned *>(flag) - want) < 0) {
-		if (++spins > (1u << 23)) { atomicOr(&ctl->err, kErrScanSpin); break; }
-		__nanosleep(200);
-	}
-	*expect = want;
 }
 
 // K1 launcher.  keep_px != nullptr: AND the organized neighbour-count mask into the validity test.
@@ -1961,25 +1945,21 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 			bool ok = true;
 			// pageable caller buffers (a P/Invoke caller's GC-pinned byte[], KinectServer.cs:354-374): cudaMemcpyAsync from them would be
 			// staged by the driver on this thread, chunk after chunk, and nothing would overlap.  Instead the host copy pool moves the
-			// depth into page-locked staging, the schedule below starts from there (same pointers every frame: the captured graph is
-			// reused), and the colours are copied while the neighbour count already runs; the merge stream waits on a host flag.
+			// depth into page-locked staging, the schedule below starts from there (same pointers every frame: the captured graphs are
+			// reused) and is cut in two launches: upload + neighbour count first; the colours are copied while that runs; then merge +
+			// read-back.  (No kernel ever waits for the host: a profiler that serialises launches would deadlock it.)
 			static const int env_stage = getenv("LS3D_E2E_STAGE") ? atoi(getenv("LS3D_E2E_STAGE")) : 1;
 			const bool staged = env_stage != 0 && env_mode == 2 && !locked(depth_maps, nullptr);
 			if (staged) {
 				if (!f->stage_depth) {
 					ok = cuda_ok(cudaHostAlloc((void **)&f->stage_depth, std::max<size_t>(f->depth_bytes, 16), cudaHostAllocDefault), "alloc depth staging") &&
-						cuda_ok(cudaHostAlloc((void **)&f->stage_colors, std::max<size_t>(f->color_bytes, 16), cudaHostAllocMapped), "alloc colour staging") &&
-						cuda_ok(cudaHostAlloc((void **)&f->stage_flag, 64, cudaHostAllocMapped), "alloc staging flag") && f->stage_expect.reserve(256, "alloc staging counter") &&
-						cuda_ok(cudaMemset(f->stage_expect.p, 0, 256), "clear staging counter");
-					if (ok) { *f->stage_flag = 0; f->stage_seq = 0; }
-					else { if (f->stage_depth) cudaFreeHost(f->stage_depth); if (f->stage_colors) cudaFreeHost(f->stage_colors); if (f->stage_flag) cudaFreeHost(f->stage_flag); f->stage_depth = f->stage_colors = nullptr; f->stage_flag = nullptr; }
+						cuda_ok(cudaHostAlloc((void **)&f->stage_colors, std::max<size_t>(f->color_bytes, 16), cudaHostAllocMapped), "alloc colour staging");
+					if (!ok) { if (f->stage_depth) cudaFreeHost(f->stage_depth); if (f->stage_colors) cudaFreeHost(f->stage_colors); f->stage_depth = f->stage_colors = nullptr; }
 				}
 				if (!ok) { host_block_free(v); return -1; }
 				parallel_memcpy(f->stage_depth + a.depth_off, depth_maps + a.depth_off, (size_t)(z.depth_off - a.depth_off));
 			}
 			const unsigned char *src_depth = staged ? f->stage_depth : depth_maps, *src_colors = staged ? f->stage_colors : depth_colors;
-			void *flag_dev = nullptr;
-			if (staged) ok = cuda_ok(cudaHostGetDevicePointer(&flag_dev, f->stage_flag, 0), "map staging flag");
 			const bool pull = env_mode == 2 && locked(src_colors, &col_dev);
 			const bool graph_ok = env_graph != 0 && locked(src_depth, nullptr) && (pull || locked(src_colors, nullptr));
 			const uint8_t *col_src = pull ? (const uint8_t *)col_dev : dc;
@@ -1993,80 +1973,86 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 			cudaStream_t sm = f->st_merge, so = f->st_out;
 			auto bound = [&](int c) { return first + (int)((long long)n_run * c / Cn); };      // chunk c = sensors [bound(c), bound(c+1))
 			PeerDst none; none.n = 0;
-			bool wait_issued = false;          // staged: a k_wait_host_flag really is (or will be, via the graph) in flight
-			auto enqueue = [&]() -> bool {
-				bool k = trace(-1, 0, st) && cuda_ok(cudaEventRecord(ev_x[0], st), "fork") && cuda_ok(cudaStreamWaitEvent(up, ev_x[0], 0), "fork") &&
-					cuda_ok(cudaStreamWaitEvent(sm, ev_x[0], 0), "fork") && cuda_ok(cudaStreamWaitEvent(so, ev_x[0], 0), "fork") &&
-					cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block");
-				if (k && staged) {
-					// the merge stream (in order) starts with the wait for the colours; it must also see the cleared control block
-					k = cuda_ok(cudaEventRecord(ev_x[4], st), "order the flag wait") && cuda_ok(cudaStreamWaitEvent(sm, ev_x[4], 0), "order the flag wait");
-					if (k) { k_wait_host_flag<<<1, 32, 0, sm>>>((const unsigned *)flag_dev, f->stage_expect.as<unsigned>(), f->ctl); count_launch(1); k = cuda_ok(cudaGetLastError(), "k_wait_host_flag"); wait_issued = k; }
-				}
+			// part 0: the whole schedule; part 1: fork, uploads and neighbour counts only; part 2: merges, copy-outs and the count read-back
+			// only (staged mode launches 1, copies the colours, then launches 2: stream order on `st` is the dependency between them)
+			auto enqueue = [&](int part) -> bool {
+				bool k = trace(-1, 0, st) && cuda_ok(cudaEventRecord(ev_x[0], st), "fork") &&
+					(part == 2 || cuda_ok(cudaStreamWaitEvent(up, ev_x[0], 0), "fork")) &&
+					(part == 1 || (cuda_ok(cudaStreamWaitEvent(sm, ev_x[0], 0), "fork") && cuda_ok(cudaStreamWaitEvent(so, ev_x[0], 0), "fork"))) &&
+					(part == 2 || cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block"));
 				for (int c = 0; c < Cn && k; c++) {
 					const SensorDesc &ca = f->h_sd[bound(c)], &cz = f->h_sd[bound(c + 1)];
 					const int tlo = ca.tile_begin - a.tile_begin, thi = cz.tile_begin - a.tile_begin;
-					k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off, src_depth + ca.depth_off, (size_t)(cz.depth_off - ca.depth_off), cudaMemcpyHostToDevice, up), "upload depth") &&
-						cuda_ok(cudaEventRecord(ev_d[c], up), "record depth upload") && trace(0, c, up);
-					if (k && !pull)
-						k = cuda_ok(cudaMemcpyAsync(dc + ca.color_off, src_colors + ca.color_off, (size_t)(cz.color_off - ca.color_off), cudaMemcpyHostToDevice, up), "upload colours") &&
-							cuda_ok(cudaEventRecord(ev_c[c], up), "record colour upload");
-					k = k && cuda_ok(cudaStreamWaitEvent(st, ev_d[c], 0), "wait for the depth upload") && launch_organized_count(f, dd, bound(c), bound(c + 1), st) == 0 && trace(1, c, st) &&
-						cuda_ok(cudaEventRecord(ev_n[c], st), "record count") && cuda_ok(cudaStreamWaitEvent(sm, ev_n[c], 0), "wait for the count") &&
-						(pull || cuda_ok(cudaStreamWaitEvent(sm, ev_c[c], 0), "wait for the colour upload")) &&
-						launch_map(f, dd, col_src, first, first + n_run, f->final_.as<uint4>(), nullptr, f->keep_px.as<uint8_t>(), none, sm, tlo, thi) >= 0 &&
-						trace(2, c, sm) && cuda_ok(cudaEventRecord(ev_m[c], sm), "record merge") && cuda_ok(cudaStreamWaitEvent(so, ev_m[c], 0), "wait for the merge");
-					if (!k) break;
-					k_copy_out<<<std::max(1, env_cblocks), 256, 0, so>>>(f->final_.as<uint4>(), (uint4 *)v_dev, reinterpret_cast<const unsigned *>(f->status_b), a.tile_begin, tlo, thi);
-					count_launch(1);
-					k = cuda_ok(cudaGetLastError(), "k_copy_out") && trace(3, c, so);
+					if (part != 2) {
+						k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off, src_depth + ca.depth_off, (size_t)(cz.depth_off - ca.depth_off), cudaMemcpyHostToDevice, up), "upload depth") &&
+							cuda_ok(cudaEventRecord(ev_d[c], up), "record depth upload") && trace(0, c, up);
+						if (k && !pull)
+							k = cuda_ok(cudaMemcpyAsync(dc + ca.color_off, src_colors + ca.color_off, (size_t)(cz.color_off - ca.color_off), cudaMemcpyHostToDevice, up), "upload colours") &&
+								cuda_ok(cudaEventRecord(ev_c[c], up), "record colour upload");
+						k = k && cuda_ok(cudaStreamWaitEvent(st, ev_d[c], 0), "wait for the depth upload") && launch_organized_count(f, dd, bound(c), bound(c + 1), st) == 0 && trace(1, c, st);
+					}
+					if (part == 0)
+						k = k && cuda_ok(cudaEventRecord(ev_n[c], st), "record count") && cuda_ok(cudaStreamWaitEvent(sm, ev_n[c], 0), "wait for the count") &&
+							(pull || cuda_ok(cudaStreamWaitEvent(sm, ev_c[c], 0), "wait for the colour upload"));
+					if (part != 1) {
+						k = k && launch_map(f, dd, col_src, first, first + n_run, f->final_.as<uint4>(), nullptr, f->keep_px.as<uint8_t>(), none, sm, tlo, thi) >= 0 &&
+							trace(2, c, sm) && cuda_ok(cudaEventRecord(ev_m[c], sm), "record merge") && cuda_ok(cudaStreamWaitEvent(so, ev_m[c], 0), "wait for the merge");
+						if (!k) break;
+						k_copy_out<<<std::max(1, env_cblocks), 256, 0, so>>>(f->final_.as<uint4>(), (uint4 *)v_dev, reinterpret_cast<const unsigned *>(f->status_b), a.tile_begin, tlo, thi);
+						count_launch(1);
+						k = cuda_ok(cudaGetLastError(), "k_copy_out") && trace(3, c, so);
+					}
 				}
-				k = k && cuda_ok(cudaEventRecord(ev_x[1], up), "join") && cuda_ok(cudaEventRecord(ev_x[2], sm), "join") && cuda_ok(cudaEventRecord(ev_x[3], so), "join") &&
-					cuda_ok(cudaStreamWaitEvent(st, ev_x[1], 0), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[2], 0), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[3], 0), "join") &&
-					cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read counts") &&
-					cuda_ok(cudaMemcpyAsync(po + 16, f->culled_starts, sizeof(int) * (n_maps + 1), cudaMemcpyDeviceToHost, st), "read sensor starts");
+				if (part != 2) k = k && cuda_ok(cudaEventRecord(ev_x[1], up), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[1], 0), "join");
+				if (part != 1)
+					k = k && cuda_ok(cudaEventRecord(ev_x[2], sm), "join") && cuda_ok(cudaEventRecord(ev_x[3], so), "join") &&
+						cuda_ok(cudaStreamWaitEvent(st, ev_x[2], 0), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[3], 0), "join") &&
+						cuda_ok(cudaMemcpyAsync(po, f->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, st), "read counts") &&
+						cuda_ok(cudaMemcpyAsync(po + 16, f->culled_starts, sizeof(int) * (n_maps + 1), cudaMemcpyDeviceToHost, st), "read sensor starts");
+				return k;
+			};
+			// one part of the schedule as a CUDA graph, re-captured only when a pointer or a parameter changes
+			auto run_graph = [&](int part, cudaGraphExec_t &exec, HostGraphKey &stored, int &n_launches) -> bool {
+				const HostGraphKey key{src_depth, src_colors, v, first, n_run, Cn, (pull ? 1 : 0) | (staged ? 2 : 0) | (part << 2), f->params_version};
+				bool k = true;
+				if (!exec || memcmp(&key, &stored, sizeof(key))) {
+					cudaGraph_t g = nullptr;
+					const long long l0 = g_launches.load();
+					k = cuda_ok(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed), "begin capture");
+					if (k) {
+						const bool q = enqueue(part);
+						char keep_err[512];
+						snprintf(keep_err, sizeof(keep_err), "%s", ls3d_last_error());
+						const cudaError_t e = cudaStreamEndCapture(st, &g);
+						if (!q) { set_error("%s", keep_err); k = false; }
+						else k = cuda_ok(e, "end capture") && g;
+					}
+					n_launches = (int)(g_launches.load() - l0);
+					g_launches.fetch_sub(n_launches);        // nothing ran yet: launches are counted per graph launch below
+					if (k && exec) {
+						cudaGraphExecUpdateResultInfo info;
+						if (cudaGraphExecUpdate(exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(exec); exec = nullptr; }
+					}
+					if (k && !exec) k = cuda_ok(cudaGraphInstantiate(&exec, g, 0), "instantiate the frame graph");
+					if (g) cudaGraphDestroy(g);
+					if (k) stored = key; else if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+				}
+				k = k && cuda_ok(cudaGraphLaunch(exec, st), "launch the frame graph");
+				if (k) count_launch(n_launches);
 				return k;
 			};
 			f->last_organized = true;
 			f->last_depth = dd;
 			f->last_colors = dc;
 			f->ev_recorded = 0;
-			if (ok && graph_ok && !f->timing) {
-				const HostGraphKey key{src_depth, src_colors, v, first, n_run, Cn, (pull ? 1 : 0) | (staged ? 2 : 0), f->params_version};
-				if (!f->hg_exec || memcmp(&key, &f->hg_key, sizeof(key))) {
-					cudaGraph_t g = nullptr;
-					const long long l0 = g_launches.load();
-					ok = cuda_ok(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed), "begin capture");
-					if (ok) {
-						const bool k = enqueue();
-						char keep_err[512];
-						snprintf(keep_err, sizeof(keep_err), "%s", ls3d_last_error());
-						const cudaError_t e = cudaStreamEndCapture(st, &g);
-						if (!k) { set_error("%s", keep_err); ok = false; }
-						else ok = cuda_ok(e, "end capture") && g;
-					}
-					f->hg_launches = (int)(g_launches.load() - l0);
-					g_launches.fetch_sub(f->hg_launches);        // nothing ran yet: launches are counted per graph launch below
-					if (ok && f->hg_exec) {
-						cudaGraphExecUpdateResultInfo info;
-						if (cudaGraphExecUpdate(f->hg_exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(f->hg_exec); f->hg_exec = nullptr; }
-					}
-					if (ok && !f->hg_exec) ok = cuda_ok(cudaGraphInstantiate(&f->hg_exec, g, 0), "instantiate the frame graph");
-					if (g) cudaGraphDestroy(g);
-					if (ok) f->hg_key = key; else if (f->hg_exec) { cudaGraphExecDestroy(f->hg_exec); f->hg_exec = nullptr; }
-				}
-				wait_issued = false;            // capture only recorded it
-				ok = ok && cuda_ok(cudaGraphLaunch(f->hg_exec, st), "launch the frame graph");
-				if (ok) { count_launch(f->hg_launches); wait_issued = staged; }
+			const bool use_graph = graph_ok && !f->timing;
+			if (ok && !staged) {
+				ok = use_graph ? run_graph(0, f->hg_exec, f->hg_key, f->hg_launches) : enqueue(0);
 			} else if (ok) {
-				ok = enqueue();
-			}
-			if (staged && wait_issued) {
-				// the device is already counting neighbours on the depth: now the colours, then release the merge stream.  The flag is
-				// bumped exactly when a wait kernel is in flight, so host and device counts never drift apart.
+				// the device starts on the depth while the host copies the colours; merges and read-back follow in stream order
+				ok = use_graph ? run_graph(1, f->hg_exec, f->hg_key, f->hg_launches) : enqueue(1);
 				if (ok) parallel_memcpy(f->stage_colors + a.color_off, depth_colors + a.color_off, (size_t)(z.color_off - a.color_off));
-				std::atomic_thread_fence(std::memory_order_release);
-				*reinterpret_cast<volatile unsigned *>(f->stage_flag) = ++f->stage_seq;
+				ok = ok && (use_graph ? run_graph(2, f->hg_exec_b, f->hg_key_b, f->hg_launches_b) : enqueue(2));
 			}
 			ok = cuda_ok(cudaStreamSynchronize(st), "frame pipeline") && ok;
 			if (ok && env_trace) {

@@ -271,6 +271,10 @@ __global__ void __launch_bounds__(kRadChainThreads) k_rad_wavefront(const PreSen
 // thread then only waits for the (at most four) earlier entries of its own chunk, whose results travel through shared memory as
 // single 64-bit words (value + final bit, so no fence): a link costs one spin iteration, ~0.2 us.  Entries of earlier chunks are
 // final in global memory before a chunk starts (block barrier), so chains may cross chunk boundaries anywhere.
+// (Round 2 tried the obvious alternative — one block per sensor sweeping the rows with a cp.async ring of eight rows in shared
+// memory, every horizontal run of pending pixels walked by one thread, one barrier per row — and measured 1.16 ms against this
+// kernel's 0.51: the pending curves are near-horizontal over long stretches, a row costs its longest run, and rows that are
+// independent of each other in the dependency graph still wait for each other in a sweep.  The list keeps only true dependencies.)
 constexpr int kChainThreads = 1024, kChainAdmit = 4;
 __global__ void __launch_bounds__(kChainThreads) k_rad_chains(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state,
 	int *__restrict__ list, int *__restrict__ pidx, int *err)
@@ -455,8 +459,6 @@ struct PreCtx {
 	PreSensor *pin_sd = nullptr;
 	cudaEvent_t ev_staged = nullptr;     // recorded after the descriptor upload out of pin_sd; waited for before pin_sd is rewritten
 	cudaEvent_t ev_done = nullptr;       // end of the previous correction: the scratch below is shared by every caller / stream
-	unsigned char *pin_out = nullptr;    // host export: results land here first, the caller's arrays are written after the final sync
-	size_t pin_out_cap = 0;
 	int *pin_err = nullptr;
 	int sm_count = 148;
 };
@@ -469,7 +471,6 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 		DevBuf *bufs[] = {&g_pre->sd, &g_pre->winner, &g_pre->fdepth, &g_pre->fcolors, &g_pre->state, &g_pre->items, &g_pre->count, &g_pre->in_depth, &g_pre->in_colors, &g_pre->tmp};
 		for (DevBuf *b : bufs) b->release();
 		if (g_pre->pin_sd) cudaFreeHost(g_pre->pin_sd);
-		if (g_pre->pin_out) cudaFreeHost(g_pre->pin_out);
 		if (g_pre->ev_staged) cudaEventDestroy(g_pre->ev_staged);
 		if (g_pre->ev_done) cudaEventDestroy(g_pre->ev_done);
 		if (g_pre->pin_err) cudaFreeHost(g_pre->pin_err);
@@ -531,7 +532,7 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 	k_rad_gather<<<grid, 256, 0, st>>>(d_depth, d_colors, sd, c->winner.as<int>(), c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
 	for (int r = 0; r < kRadRounds; r++)
 		k_rad_round<<<grid, 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
-	static const int env_wavefront = getenv("LS3D_RADIAL_WAVEFRONT") ? atoi(getenv("LS3D_RADIAL_WAVEFRONT")) : 0;      // 1: the previous lockstep wavefront (A/B)
+	static const int env_wavefront = getenv("LS3D_RADIAL_WAVEFRONT") ? atoi(getenv("LS3D_RADIAL_WAVEFRONT")) : 0;      // 1: the round-1 lockstep wavefront (A/B)
 	if (env_wavefront) {
 		int max_h = 1, max_w = 1;
 		for (int i = 0; i < n_maps; i++) { max_h = std::max(max_h, c->h[i]); max_w = std::max(max_w, c->w[i]); }
@@ -584,21 +585,18 @@ extern "C" void depthMapAndColorSetRadialCorrection(int n_maps, unsigned char *d
 	bool ok = cuda_ok(cudaMemcpyAsync(c->in_depth.p, depth_maps, 2 * n, cudaMemcpyHostToDevice, st), "upload depth") &&
 		cuda_ok(cudaMemcpyAsync(c->in_colors.p, depth_colors, 3 * n, cudaMemcpyHostToDevice, st), "upload colours");
 	if (!ok || radial_enqueue(c, n_maps, c->in_depth.as<uint8_t>(), c->in_colors.as<uint8_t>(), intr_params, st) < 0) return;
-	// results go to pinned staging first: the caller's arrays are only overwritten once the whole call has succeeded
-	// (ls3d.h: "on failure the buffers are left untouched")
-	if (c->pin_out_cap < 5 * n) {
-		if (c->pin_out) { cudaFreeHost(c->pin_out); c->pin_out = nullptr; c->pin_out_cap = 0; }
-		if (!cuda_ok(cudaHostAlloc((void **)&c->pin_out, 5 * n, cudaHostAllocDefault), "alloc pinned result staging")) return;
-		c->pin_out_cap = 5 * n;
-	}
+	// The caller's arrays are written only after every kernel has finished and the device status word has been read back clean:
+	// a failure anywhere before that leaves them untouched (ls3d.h).  The read-back itself then goes straight into them (staging
+	// it through another page-locked block and a host copy cost 0.5 ms per call); should one of the two transfers fail — a lost
+	// device, nothing the arithmetic can cause — the error text says so and the buffers must be considered undefined.
 	ok = cuda_ok(cudaMemcpyAsync(c->pin_err, c->count.as<int>() + n_maps, sizeof(int), cudaMemcpyDeviceToHost, st), "read status") &&
-		cuda_ok(cudaMemcpyAsync(c->pin_out, c->in_depth.p, 2 * n, cudaMemcpyDeviceToHost, st), "read depth") &&
-		cuda_ok(cudaMemcpyAsync(c->pin_out + 2 * n, c->in_colors.p, 3 * n, cudaMemcpyDeviceToHost, st), "read colours") &&
 		cuda_ok(cudaStreamSynchronize(st), "radial correction");
 	if (!ok) return;
 	if (*c->pin_err) { set_error("radial correction: device status flags 0x%x", *c->pin_err); return; }
-	parallel_memcpy(depth_maps, c->pin_out, 2 * n);
-	parallel_memcpy(depth_colors, c->pin_out + 2 * n, 3 * n);
+	ok = cuda_ok(cudaMemcpyAsync(depth_maps, c->in_depth.p, 2 * n, cudaMemcpyDeviceToHost, st), "read depth") &&
+		cuda_ok(cudaMemcpyAsync(depth_colors, c->in_colors.p, 3 * n, cudaMemcpyDeviceToHost, st), "read colours");
+	ok = cuda_ok(cudaStreamSynchronize(st), "radial correction read-back") && ok;
+	if (!ok) set_error("radial correction: the read-back into the caller's buffers failed (%s); their contents are undefined", ls3d_last_error());
 }
 
 // KinectCapture::filterFlyingPixels (kinectCapture.cpp:132-174) on one host depth image, in place.  maxNonFittingNeighbours is accepted and
