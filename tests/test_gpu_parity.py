@@ -568,13 +568,15 @@ def _check_icp(api, A, B, iters, R0=None, t0=None):
     assert dR <= R_TOL, f"max |dR| = {dR:.3e}"
     assert dt <= T_TOL, f"max |dt| = {dt:.3e} m"
     assert float(np.max(np.abs(gv.astype(np.float64) - wv))) <= 2 * T_TOL
-    # stage level: match / accept counts per iteration (a handful of borderline pairs may flip at the 2.5 sigma gate,
-    # because sigma is an fp64 parallel reduction here and a sequential fp32 sum in the reference)
-    assert gtr[0]["n_matched"] == wtr[0]["n_matched"]
+    # stage level.  The first iteration starts from identical inputs: matches, accepted matches and sigma must agree exactly / to fp32
+    # accumulation noise (sigma is computed in the reference's two-pass form; only the summation order differs).  Later iterations
+    # start from poses that differ by ~1e-7, which can flip a correspondence between two nearly equidistant targets: a few counts of
+    # slack there (tests/test_gpu_icp_fuzz.py checks every iteration exactly, from the oracle's own intermediate states).
+    assert gtr[0]["n_matched"] == wtr[0]["n_matched"] and gtr[0]["n_accepted"] == wtr[0]["n_accepted"]
     for g, w in zip(gtr, wtr):
-        assert abs(g["n_matched"] - w["n_matched"]) <= max(3, w["n_matched"] // 2000)
-        assert abs(g["n_accepted"] - w["n_accepted"]) <= max(3, w["n_matched"] // 500)
-        assert abs(g["sigma"] - w["sigma"]) <= 1e-3 * w["sigma"]
+        assert abs(g["n_matched"] - w["n_matched"]) <= max(2, w["n_matched"] // 20000)
+        assert abs(g["n_accepted"] - w["n_accepted"]) <= max(2, w["n_matched"] // 20000)
+        assert abs(g["sigma"] - w["sigma"]) <= 2e-4 * w["sigma"]
     return dR, dt
 
 
