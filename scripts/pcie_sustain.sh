@@ -1,0 +1,10 @@
+#!/bin/bash
+# What the host side gives N GPUs together: frame-sized copy-engine transfers on 1, 2, 4, 8 devices at once (run under gpurun --gpus 8).
+cd "$(dirname "$0")/.."
+for mode in both h2d d2h; do
+  for n in 1 2 4 8; do
+    echo "== $mode on $n GPUs at once"
+    for ((i = 0; i < n; i++)); do CUDA_VISIBLE_DEVICES=$i timeout 60 scripts/bin/pcie_probe sustain $mode 1.5 & done
+    wait
+  done
+done
