@@ -353,6 +353,13 @@ void ls3d_frames_info_free(Ls3dFramesInfo *info);
 long long ls3d_ply_binary_size(int n_vertices, int n_triangles);
 long long ls3d_write_ply_binary(const VertexC4ubV3f *vertices, int n_vertices, const int *triangles, int n_triangles, unsigned char *out, long long out_cap);
 int ls3d_pack_ply_body_device(const void *d_vertices, int n_vertices, const int *d_triangles, int n_triangles, void *d_out, void *stream);
+/* ASCII PLY, Utils.saveToPly with binary = false (Utils.cs:204-214, :276-289), byte for byte including its quirks: "\r\n" after a
+ * header line that already ends in "\n", a blank before every vertex line's end, face lines "3 " + the three indices written with
+ * nothing between them.  Floats as Single.ToString(InvariantCulture) of .NET Framework 4.5 (7 significant digits, general format).
+ * Host text codec (no device work).  out_cap must be at least ls3d_ply_ascii_bound(); returns the file's length or -1.
+ * n_triangles < 0: the vertex-only overload. */
+long long ls3d_ply_ascii_bound(int n_vertices, int n_triangles);
+long long ls3d_write_ply_ascii(const VertexC4ubV3f *vertices, int n_vertices, const int *triangles, int n_triangles, unsigned char *out, long long out_cap);
 
 /* The mesh frame TransferServer streams to viewers (HoloLens / Unity): formVerticesChunks / formMeshChunks
  * (LiveScanServer/TransferServer.cs:179-271) split the mesh into chunks of at most 64 997 vertices — with triangles, a vertex is

@@ -18,7 +18,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace ls3d;
@@ -415,6 +417,145 @@ extern "C" long long ls3d_write_ply_binary(const VertexC4ubV3f *vertices, int n_
 		cuda_ok(cudaMemcpyAsync(out + h.size(), g_fmt_out.p, (size_t)body, cudaMemcpyDeviceToHost, st), "read PLY body");
 	ok = cuda_ok(cudaStreamSynchronize(st), "ls3d_write_ply_binary") && ok;
 	return ok ? total : -1;
+}
+
+// ---- ASCII PLY (Utils.saveToPly with binary=false, Utils.cs:204-214 / :276-289): text, formatted on the host like the other
+// host codecs of this file.  Quirks kept: the header's first WriteLine already ends in "\n" and gets "\r\n" on top; every vertex
+// line ends in a blank before the line end; a face line is "3 " followed by the three indices with NOTHING between them (:284-287).
+// Numbers are Single.ToString(CultureInfo.InvariantCulture) of the .NET Framework 4.5 the server targets (LiveScanServer.csproj):
+// general format with 7 significant digits — fixed notation for decimal exponents -5 < e < 7, else d.dddE+XX (two exponent digits at
+// least), trailing zeros dropped, "NaN" / "Infinity" / "-Infinity", and "0" for either zero.  The CLR rounds through the C runtime's
+// _ecvt, i.e. half away from zero on the exact value; glibc rounds the same except on an exact tie at the 8th digit (possible only
+// for values such as 1234566.5f), which is detected and rounded by hand.  No .NET runtime exists here: parity unpinned, the format
+// is restated from the documented behaviour and checked against an independent decimal implementation (oracle/formats_oracle.py).
+static int fmt_single_net45(float v, char *o) {
+	if (v != v) { memcpy(o, "NaN", 3); return 3; }
+	if (v == INFINITY) { memcpy(o, "Infinity", 8); return 8; }
+	if (v == -INFINITY) { memcpy(o, "-Infinity", 9); return 9; }
+	if (v == 0.0f) { o[0] = '0'; return 1; }
+	char e[160];
+	snprintf(e, sizeof(e), "%.9E", (double)v);                 // [-]d.dddddddddE±XX
+	const char *m = e + (e[0] == '-' ? 1 : 0);
+	char dig[8];
+	int exp10;
+	if (m[8] == '5' && m[9] == '0' && m[10] == '0') {           // significant digit k >= 2 is m[k]
+		// perhaps an exact tie at the 8th digit: round the exact expansion (a float has at most 112 significant digits) by hand —
+		// a 5 there rounds up whether or not anything follows it
+		snprintf(e, sizeof(e), "%.120E", (double)v);
+		m = e + (e[0] == '-' ? 1 : 0);
+		exp10 = atoi(strchr(m, 'E') + 1);
+		long long d7 = (m[0] - '0');
+		for (int i = 2; i < 8; i++) d7 = d7 * 10 + (m[i] - '0');
+		if (m[8] >= '5') d7++;
+		if (d7 == 10000000) { d7 = 1000000; exp10++; }
+		for (int i = 6; i >= 0; i--) { dig[i] = (char)('0' + d7 % 10); d7 /= 10; }
+	} else {
+		snprintf(e, sizeof(e), "%.6E", (double)v);               // 7 significant digits, correctly rounded
+		m = e + (e[0] == '-' ? 1 : 0);
+		dig[0] = m[0];
+		for (int i = 0; i < 6; i++) dig[1 + i] = m[2 + i];
+		exp10 = atoi(strchr(m, 'E') + 1);
+	}
+	int nd = 7;
+	while (nd > 1 && dig[nd - 1] == '0') nd--;
+	char *q = o;
+	if (v < 0) *q++ = '-';
+	if (exp10 > -5 && exp10 < 7) {
+		if (exp10 >= 0) {
+			for (int i = 0; i <= exp10; i++) *q++ = i < nd ? dig[i] : '0';
+			if (nd > exp10 + 1) { *q++ = '.'; for (int i = exp10 + 1; i < nd; i++) *q++ = dig[i]; }
+		} else {
+			*q++ = '0'; *q++ = '.';
+			for (int i = 0; i < -exp10 - 1; i++) *q++ = '0';
+			for (int i = 0; i < nd; i++) *q++ = dig[i];
+		}
+	} else {
+		*q++ = dig[0];
+		if (nd > 1) { *q++ = '.'; for (int i = 1; i < nd; i++) *q++ = dig[i]; }
+		*q++ = 'E';
+		*q++ = exp10 < 0 ? '-' : '+';
+		const int a = exp10 < 0 ? -exp10 : exp10;
+		if (a >= 100) *q++ = (char)('0' + a / 100);
+		*q++ = (char)('0' + (a / 10) % 10);
+		*q++ = (char)('0' + a % 10);
+	}
+	return (int)(q - o);
+}
+static int fmt_uint(unsigned v, char *o) {
+	char t[12];
+	int n = 0;
+	do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+	for (int i = 0; i < n; i++) o[i] = t[n - 1 - i];
+	return n;
+}
+static int fmt_int(int v, char *o) {
+	if (v >= 0) return fmt_uint((unsigned)v, o);
+	o[0] = '-';
+	return 1 + fmt_uint(0u - (unsigned)v, o + 1);
+}
+
+static std::string ply_ascii_header(int n_vertices, int n_triangles) {
+	std::string h = "ply\nformat ascii 1.0\n\r\n";
+	h += "element vertex " + std::to_string(n_vertices) + "\n";
+	h += "property float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n";
+	if (n_triangles >= 0) {
+		h += "element face " + std::to_string(n_triangles) + "\n";
+		h += "property list uchar int vertex_index\n";
+	}
+	h += "end_header\n";
+	return h;
+}
+constexpr long long kAsciiVertexMax = 64, kAsciiFaceMax = 40;      // "-1.234568E-38 " x 3 + "255 " x 3 + CRLF = 59; "3 " + 3 x 11 + CRLF = 37
+
+extern "C" long long ls3d_ply_ascii_bound(int n_vertices, int n_triangles) {
+	if (n_vertices < 0) return -1;
+	return (long long)ply_ascii_header(n_vertices, n_triangles).size() + kAsciiVertexMax * n_vertices + kAsciiFaceMax * std::max(n_triangles, 0);
+}
+
+extern "C" long long ls3d_write_ply_ascii(const VertexC4ubV3f *vertices, int n_vertices, const int *triangles, int n_triangles, unsigned char *out, long long out_cap) {
+	clear_error();
+	if (n_vertices < 0 || (n_vertices && !vertices) || (n_triangles > 0 && !triangles) || !out) { set_error("ls3d_write_ply_ascii: bad argument"); return -1; }
+	const long long bound = ls3d_ply_ascii_bound(n_vertices, n_triangles);
+	if (out_cap < bound) { set_error("ls3d_write_ply_ascii: need ls3d_ply_ascii_bound() = %lld bytes of output, got %lld", bound, out_cap); return -1; }
+	const std::string h = ply_ascii_header(n_vertices, n_triangles);
+	const int nt = std::max(n_triangles, 0);
+	// lines are formatted by a few host threads, each into its own slice of a scratch buffer (fixed upper bound per line), then packed
+	const int n_thr = (int)std::max(1u, std::min(16u, std::min(std::thread::hardware_concurrency(), (unsigned)(((long long)n_vertices + nt) / 20000 + 1))));
+	const long long items = (long long)n_vertices + nt;
+	std::vector<std::vector<char>> part(n_thr);
+	auto work = [&](int t) {
+		const long long a = items * t / n_thr, b = items * (t + 1) / n_thr;
+		std::vector<char> &buf = part[t];
+		buf.resize((size_t)std::max<long long>(1, (b - a) * kAsciiVertexMax));
+		char *q = buf.data();
+		for (long long i = a; i < b; i++) {
+			if (i < n_vertices) {
+				const VertexC4ubV3f &v = vertices[i];
+				q += fmt_single_net45(v.X, q); *q++ = ' ';
+				q += fmt_single_net45(v.Y, q); *q++ = ' ';
+				q += fmt_single_net45(v.Z, q); *q++ = ' ';
+				q += fmt_uint(v.R, q); *q++ = ' ';
+				q += fmt_uint(v.G, q); *q++ = ' ';
+				q += fmt_uint(v.B, q); *q++ = ' ';
+			} else {
+				const int *tr = triangles + 3 * (i - n_vertices);
+				*q++ = '3'; *q++ = ' ';
+				q += fmt_int(tr[0], q); q += fmt_int(tr[1], q); q += fmt_int(tr[2], q);
+			}
+			*q++ = '\r'; *q++ = '\n';
+		}
+		buf.resize((size_t)(q - buf.data()));
+	};
+	if (n_thr == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for (int t = 0; t < n_thr; t++) th.emplace_back(work, t);
+		for (auto &x : th) x.join();
+	}
+	unsigned char *q = out;
+	memcpy(q, h.data(), h.size()); q += h.size();
+	for (int t = 0; t < n_thr; t++) { memcpy(q, part[t].data(), part[t].size()); q += part[t].size(); }
+	return (long long)(q - out);
 }
 
 // ======================================================================================================

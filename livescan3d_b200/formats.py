@@ -77,6 +77,20 @@ def write_ply_binary(vertices: np.ndarray, triangles: np.ndarray | None) -> byte
     return out.tobytes()
 
 
+def write_ply_ascii(vertices: np.ndarray, triangles: np.ndarray | None) -> bytes:
+    """Utils.saveToPly(..., binary=false) (Utils.cs:204-214, :276-289) -> the file's bytes (host text codec)."""
+    lib = native.load()
+    v = np.ascontiguousarray(vertices)
+    assert v.dtype.itemsize == 16
+    t = None if triangles is None else np.ascontiguousarray(triangles, np.int32).reshape(-1, 3)
+    nt = -1 if t is None else len(t)
+    cap = lib.ls3d_ply_ascii_bound(len(v), nt)
+    out = np.empty(cap, np.uint8)
+    n = lib.ls3d_write_ply_ascii(_ptr(v) if len(v) else None, len(v), None if t is None or not len(t) else _ptr(t), nt, _ptr(out), cap)
+    native.check(n >= 0, "ls3d_write_ply_ascii")
+    return out[:n].tobytes()
+
+
 def write_transfer_frame(vertices: np.ndarray, triangles: np.ndarray | None) -> bytes:
     """formVerticesChunks / formMeshChunks + TransferSocket.SendFrame (TransferServer.cs:179-271, TransferSocket.cs:50-105)."""
     lib = native.load()
@@ -92,4 +106,4 @@ def write_transfer_frame(vertices: np.ndarray, triangles: np.ndarray | None) -> 
     return out.tobytes()
 
 
-__all__ = ["client_frame_pack", "client_frame_unpack", "frames_info_store", "frames_info_load", "write_ply_binary", "write_transfer_frame", "Ls3dError"]
+__all__ = ["client_frame_pack", "client_frame_unpack", "frames_info_store", "frames_info_load", "write_ply_binary", "write_ply_ascii", "write_transfer_frame", "Ls3dError"]

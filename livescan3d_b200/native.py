@@ -68,6 +68,8 @@ _SIG = {
     "ls3d_ply_binary_size": (C.c_longlong, [_i, _i]),
     "ls3d_write_ply_binary": (C.c_longlong, [_vp, _i, _vp, _i, _vp, C.c_longlong]),
     "ls3d_pack_ply_body_device": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "ls3d_ply_ascii_bound": (C.c_longlong, [_i, _i]),
+    "ls3d_write_ply_ascii": (C.c_longlong, [_vp, _i, _vp, _i, _vp, C.c_longlong]),
     "ls3d_transfer_frame_size": (C.c_longlong, [_i, _i, _i]),
     "ls3d_set_transfer_chunk_limit": (_i, [_i]),
     "ls3d_write_transfer_frame": (C.c_longlong, [_vp, _i, _vp, _i, _vp, C.c_longlong]),

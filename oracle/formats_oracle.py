@@ -4,7 +4,7 @@
 Each function follows the reference code it cites line by line, in plain Python / numpy:
   * client frame blob   SerializeFrame, src/LiveScanClient/liveScanClient.cpp:185-290; receiver LiveScanServer/KinectSocket.cs:211-304
   * frames dump         storeAllFramesInformation / loadAllFramesInformation, src/NativeUtils/depthprocessing.cpp:1316-1385
-  * binary PLY          Utils.saveToPly, LiveScanServer/Utils.cs:173-293
+  * binary and ASCII PLY Utils.saveToPly, LiveScanServer/Utils.cs:173-293
   * transfer frame      formVerticesChunks / formMeshChunks, LiveScanServer/TransferServer.cs:179-271; SendFrame, TransferSocket.cs:50-105
 
 Pinning: the frames dump is checked against the reference's own C++ functions compiled into oracle/_ref (tests/test_formats.py).
@@ -161,6 +161,68 @@ def orc_ply_binary(vertices: np.ndarray, triangles) -> bytes:
         f["n"], f["a"], f["b"], f["c"] = 3, t[:, 0], t[:, 1], t[:, 2]
         body += f.tobytes()
     return head.encode("ascii") + body
+
+
+# --------------------------------------------------------------------------------------------------------- ASCII PLY
+def net45_single_to_string(v) -> str:
+    """Single.ToString(CultureInfo.InvariantCulture) on .NET Framework 4.5 (the server's target, LiveScanServer.csproj:12): the
+    general format with 7 significant digits.  Restated with exact decimal arithmetic: the float's exact value is rounded half away
+    from zero to 7 digits (the CLR goes through the C runtime's _ecvt); fixed notation when the decimal exponent e of the ROUNDED
+    number satisfies -5 < e < 7, else d.ddddddE+XX with at least two exponent digits; trailing zeros dropped; both zeros print "0".
+    No .NET runtime is available here: parity unpinned, this follows the documented behaviour."""
+    import decimal
+    import math
+    f = float(np.float32(v))
+    if math.isnan(f):
+        return "NaN"
+    if math.isinf(f):
+        return "Infinity" if f > 0 else "-Infinity"
+    if f == 0.0:
+        return "0"
+    d = decimal.Decimal(f)                       # exact
+    sign, a = ("-" if d < 0 else ""), abs(d)
+    e = a.adjusted()
+    with decimal.localcontext() as ctx:
+        ctx.prec = 200
+        q = (a.scaleb(6 - e)).to_integral_value(rounding=decimal.ROUND_HALF_UP)      # 7-digit integer
+    q = int(q)
+    if q == 10 ** 7:
+        q, e = 10 ** 6, e + 1
+    digits = str(q).rstrip("0") or "0"
+    if -5 < e < 7:
+        if e >= 0:
+            ip = (digits + "0" * 7)[:e + 1]
+            fp = digits[e + 1:]
+            return sign + ip + ("." + fp if fp else "")
+        return sign + "0." + "0" * (-e - 1) + digits
+    mant = digits[0] + ("." + digits[1:] if len(digits) > 1 else "")
+    return sign + mant + "E" + ("-" if e < 0 else "+") + "%02d" % abs(e)
+
+
+def orc_ply_ascii(vertices: np.ndarray, triangles) -> bytes:
+    """Utils.cs:222-293 with binary=false (triangles None: the overload at :173-220).  WriteLine = text + "\r\n"; the header's first
+    WriteLine is given a string that already ends in "\n" (:187/:236); vertex lines end in a blank (:207-211, :279-284); face
+    lines are "3 " followed by the three indices with nothing between them (:285-290) — reproduced as written."""
+    v = np.asarray(vertices)
+    out = ["ply\nformat ascii 1.0\n" + "\r\n", "element vertex " + str(len(v)) + "\n",
+           "property float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n"]
+    t = None
+    if triangles is not None:
+        t = np.asarray(triangles, "<i4").reshape(-1, 3)
+        out.append("element face " + str(len(t)) + "\n")
+        out.append("property list uchar int vertex_index\n")
+    out.append("end_header\n")
+    for r in v:
+        s = ""
+        for k in ("X", "Y", "Z"):
+            s += net45_single_to_string(r[k]) + " "
+        for k in ("R", "G", "B"):
+            s += str(int(r[k])) + " "
+        out.append(s + "\r\n")
+    if t is not None:
+        for a, b, c in t:
+            out.append("3 " + str(int(a)) + str(int(b)) + str(int(c)) + "\r\n")
+    return "".join(out).encode("ascii")
 
 
 # --------------------------------------------------------------------------------------------------------- transfer frame

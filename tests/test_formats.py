@@ -158,6 +158,47 @@ def test_ply_and_transfer_sizes_without_a_device():
     assert lib.ls3d_transfer_frame_size(5, 2, 1) == len(fo.orc_transfer_frame(v, np.array([[0, 1, 2], [2, 3, 4]])))
 
 
+def test_net45_float_text_known_answers():
+    """Documented outputs of Single.ToString() on .NET Framework (general format, 7 significant digits)."""
+    kat = [(0.0, "0"), (-0.0, "0"), (1.0, "1"), (-1.5, "-1.5"), (0.1, "0.1"), (1.0 / 3.0, "0.3333333"), (123456.789, "123456.8"), (1234567.0, "1234567"),
+           (12345678.0, "1.234568E+07"), (1e7, "1E+07"), (9999999.0, "9999999"), (0.0001, "0.0001"), (0.00001, "1E-05"), (1.5e-5, "1.5E-05"),
+           (3.4028235e38, "3.402823E+38"), (1.17549435e-38, "1.175494E-38"), (1e-45, "1.401298E-45"), (float("nan"), "NaN"),
+           (float("inf"), "Infinity"), (float("-inf"), "-Infinity"), (0.5, "0.5"), (100.0, "100"), (-0.00012345678, "-0.0001234568"),
+           (1234566.5, "1234567"), (1234567.5, "1234568"), (0.99999994, "0.9999999")]
+    for x, want in kat:
+        assert fo.net45_single_to_string(np.float32(x)) == want, (x, fo.net45_single_to_string(np.float32(x)), want)
+
+
+def _awkward_floats(n, seed):
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)           # every exponent, NaNs and infinities included
+    f = bits.view(np.float32).copy()
+    special = np.array([0.0, -0.0, 1e7, 9999999.0, 9999999.5, 99999.995, 1234566.5, 1234567.5, 8388607.5, 0.00001, 0.0000099999995, 1e-45, 3.4028235e38,
+                        np.inf, -np.inf, np.nan, 0.1, 1.0 / 3.0, 16777216.0, 1048576.5, 2097151.5, 524287.25, 0.5, 0.25, 0.125], np.float32)
+    f[:len(special)] = special[:min(len(special), n)]
+    near = rng.normal(size=n // 2).astype(np.float32) * np.float32(2.0)                # the coordinates a cloud really has
+    f[n - len(near):] = near
+    return f
+
+
+@pytest.mark.parametrize("n,nt", [(0, 0), (1, -1), (3, 2), (4000, 777), (60000, 30000)])
+def test_ply_ascii_bytes(n, nt):
+    """Host text codec: runs without a device.  Floats of every magnitude, specials, exact ties at the 8th digit."""
+    v = np.zeros(n, VERTEX)
+    rng = np.random.default_rng(n + 7)
+    for k in "RGB":
+        v[k] = rng.integers(0, 256, n)
+    v["A"] = 255
+    for i, k in enumerate("XYZ"):
+        v[k] = _awkward_floats(n, 10 * n + i) if n else 0
+    t = None if nt < 0 else rng.integers(-5, max(n, 1) + 100000, (nt, 3)).astype(np.int32)
+    got = formats.write_ply_ascii(v, t)
+    want = fo.orc_ply_ascii(v, t)
+    assert got == want
+    if nt >= 0:
+        assert formats.write_ply_ascii(v, None) == fo.orc_ply_ascii(v, None)
+
+
 # ------------------------------------------------------------------------------------------------ GPU: re-packing and chunking
 def _random_cloud(n, seed):
     rng = np.random.default_rng(seed)
