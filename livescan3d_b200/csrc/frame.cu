@@ -13,7 +13,7 @@
 //                          compaction through a decoupled look-back scan, 16-byte records out (HBM-bound)
 //   K2 k_voxel_insert      voxel key per point, warp-aggregated insert into a per-sensor open-addressing hash
 //                          whose 64-bit entries hold (key+1)<<24 | count; returns slot and rank per point
-//   K3 k_cell_ranges       one contiguous range of the sorted array per occupied voxel
+//   K3 k_bucket_alloc      one contiguous range of the sorted array per occupied run of 8 voxels
 //   K4 k_cell_scatter      counting-sort scatter of (x,y,z,g) into voxel order
 //   K5 k_neighbour_count   one warp per occupied voxel: 27 hash look-ups by 27 lanes, candidates staged in
 //                          shared memory, count{d2 <= thr} per query by ballot/popc with warp-uniform early
@@ -724,11 +724,33 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K2: voxel hash insert
+// K2-K5: neighbour count on an unorganized cloud — a hash of x-runs of voxels
 // ------------------------------------------------------------------------------------------------------
+// Voxels have edge h >= maxDist, so a point's neighbours lie in its 27 surrounding voxels = 9 rows of 3 voxels along x.  The hash
+// key is a RUN of 8 voxels along x (bucket): one 64-byte slot holds the key, the run's first position in the voxel-sorted array and
+// the 8 voxel counts, so one look-up (two sectors, all loads independent) yields a row's candidates as ONE contiguous range; a row
+// straddles two runs for a quarter of the voxels.  Queries are processed in input order, one lane each, 9-11 look-ups per lane
+// issued three rows at a time, then a private cursor over the ranges.  (Rounds 1-2 hashed single voxels and processed the points in
+// hash-slot order: 27 look-ups of two dependent loads per distinct voxel, 16 voxels per warp one after the other — 263 us for the
+// bench frame's 739 k points, latency-bound; bricks of 4^3 voxels with shared-memory staging were slower still, see DESIGN.md.)
+// The table is never cleared as a whole: k_voxel_cleanup zeroes exactly the slots the run's points touched.
+constexpr int kRunBits = 3;
+struct alignas(64) VoxBucket {
+	unsigned long long word;       // (key + 1) << 24 | points in the run; 0 = free
+	unsigned start, pad0;          // first position of the run's points in the sorted array (k_bucket_alloc)
+	unsigned cnt[8];               // points per voxel of the run
+	unsigned pad1[4];
+};
+__device__ __forceinline__ unsigned long long bucket_key(int cx, int cy, int cz) {
+	return ((unsigned long long)cz << (2 * kCellBits)) | ((unsigned long long)cy << kCellBits) | (unsigned long long)(cx >> kRunBits);
+}
+
+// K2: per point — find or claim its run's slot, add to the run total and to the voxel's count (the old value is the point's rank).
+// Lanes of a warp that share a voxel are aggregated.  slot_of[g] = slot << 3 | voxel-in-run; rank_of[g] bit 31: this point's group
+// was the first to add to its run, so it will allocate the run's range (k_bucket_alloc).
 __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ cloud, const SensorDesc *__restrict__ sd,
 	const int *__restrict__ culled_starts, int s_first, int s_end, FrameCtl *ctl,
-	unsigned long long *table, unsigned *__restrict__ slot_of, unsigned *__restrict__ rank_of)
+	VoxBucket *table, unsigned *__restrict__ slot_of, unsigned *__restrict__ rank_of)
 {
 	const int N = ctl->n_culled;
 	const int lane = threadIdx.x & 31;
@@ -736,15 +758,15 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 		const int g = g0 + lane;
 		const bool active = g < N;
 		unsigned long long key = 0, tag = ~0ull - (unsigned long long)lane;
-		int s = s_first;
+		int s = s_first, cx = 0;
 		if (active) {
 			while (s + 1 < s_end && culled_starts[s + 1] <= g) s++;
 			const uint4 p = cloud[g];
-			const int cx = cell_coord(__uint_as_float(p.y), sd[s].gox, sd[s].ginv_h);
+			cx = cell_coord(__uint_as_float(p.y), sd[s].gox, sd[s].ginv_h);
 			const int cy = cell_coord(__uint_as_float(p.z), sd[s].goy, sd[s].ginv_h);
 			const int cz = cell_coord(__uint_as_float(p.w), sd[s].goz, sd[s].ginv_h);
-			key = ((unsigned long long)cz << (2 * kCellBits)) | ((unsigned long long)cy << kCellBits) | (unsigned long long)cx;
-			tag = key | ((unsigned long long)s << 40);
+			key = bucket_key(cx, cy, cz);
+			tag = (key << 3) | (unsigned long long)(cx & 7) | ((unsigned long long)s << 44);
 		}
 		const unsigned grp = __match_any_sync(kFull, tag);
 		const int leader = __ffs(grp) - 1;
@@ -756,20 +778,21 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 			unsigned h = voxel_hash(key) & tmask;
 			bool found = false;
 			for (unsigned probe = 0; probe <= tmask; probe++) {
-				const unsigned long long w = table[toff + h];
+				const unsigned long long w = table[toff + h].word;
 				const unsigned long long kk = w >> 24;
 				if (kk == want) { found = true; break; }
 				if (kk == 0) {
-					const unsigned long long prev = atomicCAS(&table[toff + h], 0ull, want << 24);
+					const unsigned long long prev = atomicCAS(&table[toff + h].word, 0ull, want << 24);
 					if (prev == 0 || (prev >> 24) == want) { found = true; break; }
 				}
 				h = (h + 1) & tmask;
 			}
 			if (!found) atomicOr(&ctl->err, kErrProbeLimit);
 			else {
-				const unsigned long long old = atomicAdd(&table[toff + h], (unsigned long long)n);
-				base_rank = (unsigned)(old & kCountMask);
-				if (base_rank + n > (unsigned)kCountMask) atomicOr(&ctl->err, kErrCellOverflow);
+				const unsigned long long old = atomicAdd(&table[toff + h].word, (unsigned long long)n);
+				if ((old & kCountMask) + n > kCountMask) atomicOr(&ctl->err, kErrCellOverflow);
+				base_rank = atomicAdd(&table[toff + h].cnt[cx & 7], n);
+				if ((old & kCountMask) == 0) base_rank |= 0x80000000u;
 			}
 			slot = toff + h;
 		}
@@ -777,85 +800,71 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 		slot = __shfl_sync(kFull, slot, leader);
 		base_rank = __shfl_sync(kFull, base_rank, leader);
 		if (active) {
-			slot_of[g] = slot;
-			rank_of[g] = base_rank + __popc(grp & ((1u << lane) - 1u));
+			slot_of[g] = (slot << 3) | (unsigned)(cx & 7);
+			rank_of[g] = lane == leader ? base_rank : (base_rank & 0x7fffffffu) + __popc(grp & ((1u << lane) - 1u));
 		}
 	}
 }
 
-// ------------------------------------------------------------------------------------------------------
-// K3: contiguous range of the sorted array for every occupied voxel
-// ------------------------------------------------------------------------------------------------------
-constexpr int kRangeThreads = 1024;
-__global__ void __launch_bounds__(kRangeThreads) k_cell_ranges(const unsigned long long *__restrict__ table, unsigned *__restrict__ cell_start,
-	unsigned slot_lo, unsigned slot_hi, FrameCtl *ctl)
-{
-	// one atomicAdd on the shared cursor per 1024 slots (ncu: one per warp serialised ~1e5 same-address atomics)
-	__shared__ unsigned s_w[32];
+// K3: every run gets its range of the sorted array (any order will do): the elected points carry their run's total through a
+// block-wide scan, one atomicAdd on the cursor per block
+__global__ void __launch_bounds__(256) k_bucket_alloc(const unsigned *__restrict__ slot_of, const unsigned *__restrict__ rank_of, VoxBucket *table, FrameCtl *ctl) {
+	__shared__ unsigned s_w[8];
 	__shared__ unsigned s_base;
-	const unsigned i = slot_lo + blockIdx.x * kRangeThreads + threadIdx.x;
+	const int N = ctl->n_culled;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned cnt = 0;
-	if (i < slot_hi) {
-		const unsigned long long w = table[i];
-		if (w >> 24) cnt = (unsigned)(w & kCountMask);
+	for (int g0 = blockIdx.x * 256; g0 < N; g0 += gridDim.x * 256) {
+		const int g = g0 + threadIdx.x;
+		unsigned tot = 0, slot = 0;
+		if (g < N && (rank_of[g] & 0x80000000u)) {
+			slot = slot_of[g] >> 3;
+			tot = (unsigned)(table[slot].word & kCountMask);
+		}
+		const unsigned incl = warp_incl_scan(tot, lane);
+		__syncthreads();                      // s_w / s_base of the previous iteration are no longer read
+		if (lane == 31) s_w[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			const unsigned v = lane < 8 ? s_w[lane] : 0u;
+			const unsigned sc = warp_incl_scan(v, lane);
+			if (lane < 8) s_w[lane] = sc - v;
+			if (lane == 31) s_base = sc ? atomicAdd(&ctl->cursor, sc) : 0u;
+		}
+		__syncthreads();
+		if (tot) table[slot].start = s_base + s_w[warp] + incl - tot;
 	}
-	const unsigned incl = warp_incl_scan(cnt, lane);
-	if (lane == 31) s_w[warp] = incl;
-	__syncthreads();
-	if (warp == 0) {
-		const unsigned v = s_w[lane];
-		const unsigned sc = warp_incl_scan(v, lane);
-		s_w[lane] = sc - v;
-		if (lane == 31) s_base = sc ? atomicAdd(&ctl->cursor, sc) : 0u;
-	}
-	__syncthreads();
-	if (cnt) cell_start[i] = s_base + s_w[warp] + incl - cnt;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// K4: scatter into voxel order
-// ------------------------------------------------------------------------------------------------------
+// K4: scatter into run / voxel order
 __global__ void __launch_bounds__(256) k_cell_scatter(const uint4 *__restrict__ cloud, const unsigned *__restrict__ slot_of,
-	const unsigned *__restrict__ rank_of, const unsigned *__restrict__ cell_start, const FrameCtl *ctl, float4 *__restrict__ sorted)
+	const unsigned *__restrict__ rank_of, const VoxBucket *__restrict__ table, const FrameCtl *ctl, float4 *__restrict__ sorted)
 {
 	const int N = ctl->n_culled;
 	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
 		const uint4 p = cloud[g];
-		const unsigned pos = cell_start[slot_of[g]] + rank_of[g];
+		const unsigned sc = slot_of[g], c = sc & 7u;
+		const uint4 *b = reinterpret_cast<const uint4 *>(table + (sc >> 3));
+		const uint4 h = __ldg(b), c0 = __ldg(b + 1), c1 = __ldg(b + 2);
+		const unsigned cn[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+		unsigned pre = 0;
+#pragma unroll
+		for (int j = 0; j < 7; j++) pre += (unsigned)j < c ? cn[j] : 0u;
+		const unsigned pos = h.z + pre + (rank_of[g] & 0x7fffffffu);
 		sorted[pos] = make_float4(__uint_as_float(p.y), __uint_as_float(p.z), __uint_as_float(p.w), __int_as_float(g));
 	}
 }
 
-// ------------------------------------------------------------------------------------------------------
-// K5: neighbour count per point, one warp per occupied voxel
-// ------------------------------------------------------------------------------------------------------
-// neighbour offsets in visiting order: home, 6 faces, 12 edges, 8 corners (nearer voxels first, so the
-// warp-uniform early exit at k fires as soon as possible)
-__constant__ signed char c_nb[27][3] = {
-	{0, 0, 0},
-	{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
-	{-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1}, {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
-	{-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
-
-// One lane per query point, 32 consecutive points of the voxel-sorted array per warp.
-//  1. the distinct voxels among the warp's 32 points (a voxel's points are contiguous) are looked up once each:
-//     27 lanes probe the 27 neighbour voxels in parallel and the non-empty (start, count) ranges are compacted
-//     into shared memory in visiting order (home voxel first);
-//  2. every lane then walks its own voxel's candidate ranges with a private cursor — a flattened loop, so lanes
-//     with different range layouts stay busy — counting d2 <= thr and leaving as soon as it reaches k;
-//  3. lanes that are still undecided after kLaneIters candidates (isolated points in dense surroundings, large
-//     radii) are finished one at a time by the whole warp: candidates in lanes, ballot/popc, warp-uniform exit.
-// (Round-1 profile of the previous one-warp-per-voxel version: 350 M warp instructions for 739 k queries, 75 %
-// issue-bound on per-voxel staging overhead; see profiles/.)
+// K5: neighbour count, one lane per query in input order.
+// rows in visiting order: the query's own row first, then the four face rows, then the four edge rows, plane by plane of three
+__constant__ signed char c_row[9][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
 constexpr int kLaneIters = 96;
+constexpr int kMaxRanges = 18;
 
-__global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const unsigned long long *__restrict__ table,
-	const unsigned *__restrict__ cell_start, const float4 *__restrict__ sorted, const SensorDesc *__restrict__ sd,
+__global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const VoxBucket *__restrict__ table, const uint4 *__restrict__ cloud,
+	const float4 *__restrict__ sorted, const SensorDesc *__restrict__ sd,
 	const int *__restrict__ culled_starts, int s_first, int s_end, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep)
 {
-	__shared__ uint2 s_rng[kCountWarps][32][27];      // [warp][voxel slot][range] = (start, count)
-	__shared__ unsigned char s_nr[kCountWarps][32];
+	__shared__ uint2 s_rng[kCountWarps][kMaxRanges][32];      // [warp][range][lane] = (start, count): conflict-free per-lane lists
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int N = ctl->n_culled;
 	const int nbatches = (N + 31) >> 5;
@@ -865,82 +874,99 @@ __global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const unsi
 		if (lane == 0) b = (int)atomicAdd(&ctl->work_counter, 1u);
 		b = __shfl_sync(kFull, b, 0);
 		if (b >= nbatches) break;
-		const int pos = (b << 5) + lane;
-		const bool valid = pos < N;
-		float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-		int s = s_first, cx = 0, cy = 0, cz = 0;
-		unsigned long long tag = ~0ull - (unsigned long long)lane;
+		const int g = (b << 5) + lane;
+		const bool valid = g < N;
+		float qx = 0.f, qy = 0.f, qz = 0.f;
+		int nr = 0;
+		unsigned tot = 0;
 		if (valid) {
-			q = sorted[pos];
-			const int g = __float_as_int(q.w);
+			int s = s_first;
 			while (s + 1 < s_end && culled_starts[s + 1] <= g) s++;
-			cx = cell_coord(q.x, sd[s].gox, sd[s].ginv_h);
-			cy = cell_coord(q.y, sd[s].goy, sd[s].ginv_h);
-			cz = cell_coord(q.z, sd[s].goz, sd[s].ginv_h);
-			tag = ((unsigned long long)s << 40) | ((unsigned long long)cz << (2 * kCellBits)) | ((unsigned long long)cy << kCellBits) | (unsigned long long)cx;
-		}
-		const unsigned long long prev = __shfl_up_sync(kFull, tag, 1);
-		const bool leader = valid && (lane == 0 || prev != tag);
-		const unsigned lead_mask = __ballot_sync(kFull, leader);
-		const int slot = __popc(lead_mask & (0xffffffffu >> (31 - lane))) - 1;      // this lane's voxel slot (valid lanes only)
-
-		// ---- 1. one cooperative look-up per distinct voxel ----
-		unsigned m = lead_mask;
-		int vs = 0;
-		while (m) {
-			const int l = __ffs(m) - 1;
-			m &= m - 1;
-			const int ls = __shfl_sync(kFull, s, l), lx = __shfl_sync(kFull, cx, l), ly = __shfl_sync(kFull, cy, l), lz = __shfl_sync(kFull, cz, l);
-			unsigned ncnt = 0, nstart = 0;
-			if (lane < 27) {
-				const int nx = lx + c_nb[lane][0], ny = ly + c_nb[lane][1], nz = lz + c_nb[lane][2];
-				if (nx >= 0 && nx <= kCellMax && ny >= 0 && ny <= kCellMax && nz >= 0 && nz <= kCellMax) {
-					const unsigned toff = sd[ls].tbl_off, tmask = sd[ls].tbl_mask;
-					const unsigned long long nkey = ((unsigned long long)nz << (2 * kCellBits)) | ((unsigned long long)ny << kCellBits) | (unsigned long long)nx;
-					unsigned h = voxel_hash(nkey) & tmask;
-					for (unsigned probe = 0; probe <= tmask; probe++) {
-						const unsigned long long w2 = table[toff + h];
-						const unsigned long long kk = w2 >> 24;
-						if (kk == nkey + 1) { ncnt = (unsigned)(w2 & kCountMask); nstart = cell_start[toff + h]; break; }
-						if (kk == 0) break;
-						h = (h + 1) & tmask;
+			const uint4 q = cloud[g];
+			qx = __uint_as_float(q.y); qy = __uint_as_float(q.z); qz = __uint_as_float(q.w);
+			const int cx = cell_coord(qx, sd[s].gox, sd[s].ginv_h), cy = cell_coord(qy, sd[s].goy, sd[s].ginv_h), cz = cell_coord(qz, sd[s].goz, sd[s].ginv_h);
+			const unsigned toff = sd[s].tbl_off, tmask = sd[s].tbl_mask;
+			const int xlo = max(cx - 1, 0), xhi = min(cx + 1, kCellMax);
+			const int blo = xlo >> kRunBits, bhi = xhi >> kRunBits;          // the runs the row touches (one, or two neighbours)
+			// ---- look-ups, three rows at a time (nine 16-byte loads in flight before the first is examined); the second run of a
+			// straddling row in a pass of its own, so the common case keeps its registers ----
+			auto rows3 = [&](int r0, int bx) {
+				uint4 hd[3], ca[3], cb[3];
+				unsigned long long want[3];
+				unsigned hh[3];
+#pragma unroll
+				for (int j = 0; j < 3; j++) {
+					const int y = cy + c_row[r0 + j][0], z = cz + c_row[r0 + j][1];
+					want[j] = 0; hh[j] = 0;
+					hd[j] = ca[j] = cb[j] = make_uint4(0u, 0u, 0u, 0u);
+					if (y >= 0 && y <= kCellMax && z >= 0 && z <= kCellMax) {
+						const unsigned long long key = ((unsigned long long)z << (2 * kCellBits)) | ((unsigned long long)y << kCellBits) | (unsigned long long)bx;
+						want[j] = key + 1;
+						hh[j] = voxel_hash(key) & tmask;
+						const uint4 *bp = reinterpret_cast<const uint4 *>(table + toff + hh[j]);
+						hd[j] = __ldg(bp); ca[j] = __ldg(bp + 1); cb[j] = __ldg(bp + 2);
 					}
 				}
+#pragma unroll
+				for (int j = 0; j < 3; j++) {
+					if (!want[j]) continue;
+					unsigned long long w = ((unsigned long long)hd[j].y << 32) | hd[j].x;
+					if ((w >> 24) != want[j] && (w >> 24) != 0) {
+						// another run sits in the slot: follow the probe sequence (rare at this table's load)
+						unsigned h = hh[j];
+						for (unsigned probe = 0; probe <= tmask; probe++) {
+							h = (h + 1) & tmask;
+							const uint4 *bp = reinterpret_cast<const uint4 *>(table + toff + h);
+							hd[j] = __ldg(bp);
+							w = ((unsigned long long)hd[j].y << 32) | hd[j].x;
+							if ((w >> 24) == want[j]) { ca[j] = __ldg(bp + 1); cb[j] = __ldg(bp + 2); break; }
+							if ((w >> 24) == 0) break;
+						}
+					}
+					if ((w >> 24) != want[j]) continue;
+					// voxels [a, e] of this run belong to the row
+					const int base = bx << kRunBits;
+					const int a = max(xlo - base, 0), e = min(xhi - base, 7);
+					const unsigned cn[8] = {ca[j].x, ca[j].y, ca[j].z, ca[j].w, cb[j].x, cb[j].y, cb[j].z, cb[j].w};
+					unsigned pre = 0, n = 0;
+#pragma unroll
+					for (int v = 0; v < 8; v++) { pre += v < a ? cn[v] : 0u; n += (v >= a && v <= e) ? cn[v] : 0u; }
+					if (n) { s_rng[warp][nr][lane] = make_uint2(hd[j].z + pre, n); nr++; tot += n; }
+				}
+			};
+#pragma unroll 1
+			for (int r0 = 0; r0 < 9; r0 += 3) rows3(r0, blo);
+			if (bhi != blo) {
+#pragma unroll 1
+				for (int r0 = 0; r0 < 9; r0 += 3) rows3(r0, bhi);
 			}
-			const unsigned nz_mask = __ballot_sync(kFull, ncnt != 0);
-			if (ncnt) s_rng[warp][vs][__popc(nz_mask & ((1u << lane) - 1u))] = make_uint2(nstart, ncnt);
-			if (lane == 0) s_nr[warp][vs] = (unsigned char)__popc(nz_mask);
-			vs++;
 		}
 		__syncwarp();
 
-		// ---- 2. private cursors ----
-		int cnt = 0, c = 0, nr = 0;
+		// ---- private cursors (a point with fewer than k candidates in its 27 voxels cannot reach k) ----
+		int cnt = 0, c = 0;
 		unsigned p = 0, e = 0;
-		if (valid) {
-			nr = s_nr[warp][slot];
-			const uint2 r = s_rng[warp][slot][0];        // the home voxel: never empty, it holds the query itself
-			p = r.x; e = r.x + r.y;
-		}
+		if (tot < (unsigned)k) nr = 0;
+		if (nr) { const uint2 r = s_rng[warp][0][lane]; p = r.x; e = r.x + r.y; }
 		for (int it = 0; it < kLaneIters; it++) {
-			const bool act = valid && cnt < k && c < nr;
+			const bool act = cnt < k && c < nr;
 			if (!__any_sync(kFull, act)) break;
 			if (act) {
 				const float4 cd = __ldg(sorted + p);
-				cnt += dist2_ref(q.x, q.y, q.z, cd.x, cd.y, cd.z) <= thr ? 1 : 0;
+				cnt += dist2_ref(qx, qy, qz, cd.x, cd.y, cd.z) <= thr ? 1 : 0;
 				if (++p == e) {
-					if (++c < nr) { const uint2 r = s_rng[warp][slot][c]; p = r.x; e = r.x + r.y; }
+					if (++c < nr) { const uint2 r = s_rng[warp][c][lane]; p = r.x; e = r.x + r.y; }
 				}
 			}
 		}
 
-		// ---- 3. cooperative tail for the undecided lanes ----
-		unsigned rem = __ballot_sync(kFull, valid && cnt < k && c < nr);
+		// ---- cooperative tail for the lanes still undecided (dense surroundings, large radii): candidates in lanes ----
+		unsigned rem = __ballot_sync(kFull, cnt < k && c < nr);
 		while (rem) {
 			const int l = __ffs(rem) - 1;
 			rem &= rem - 1;
-			const float qx = __shfl_sync(kFull, q.x, l), qy = __shfl_sync(kFull, q.y, l), qz = __shfl_sync(kFull, q.z, l);
-			const int lslot = __shfl_sync(kFull, slot, l), lnr = __shfl_sync(kFull, nr, l);
+			const float lx = __shfl_sync(kFull, qx, l), ly = __shfl_sync(kFull, qy, l), lz = __shfl_sync(kFull, qz, l);
+			const int lnr = __shfl_sync(kFull, nr, l);
 			int lc = __shfl_sync(kFull, c, l), lcnt = __shfl_sync(kFull, cnt, l);
 			unsigned lp = __shfl_sync(kFull, p, l), le = __shfl_sync(kFull, e, l);
 			while (lcnt < k && lc < lnr) {
@@ -949,20 +975,31 @@ __global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const unsi
 					bool ok = false;
 					if (pp < le) {
 						const float4 cd = __ldg(sorted + pp);
-						ok = dist2_ref(qx, qy, qz, cd.x, cd.y, cd.z) <= thr;
+						ok = dist2_ref(lx, ly, lz, cd.x, cd.y, cd.z) <= thr;
 					}
 					lcnt += __popc(__ballot_sync(kFull, ok));
 				}
-				if (++lc < lnr) { const uint2 r = s_rng[warp][lslot][lc]; lp = r.x; le = r.x + r.y; }
+				if (++lc < lnr) { const uint2 r = s_rng[warp][lc][l]; lp = r.x; le = r.x + r.y; }
 			}
 			if (lane == l) cnt = lcnt;
 		}
 
 		const bool kept = valid && cnt >= k;
-		if (valid) keep[__float_as_int(q.w)] = (uint8_t)(kept ? 1 : 0);
+		if (valid) keep[g] = (uint8_t)(kept ? 1 : 0);
 		const unsigned km = __ballot_sync(kFull, kept);
 		if (lane == 0 && km) atomicAdd(&ctl->n_kept, __popc(km));
 		__syncwarp();
+	}
+}
+
+// after the count: the slots this run's points touched go back to zero (the table is cleared by its users, not by a memset of
+// all of it: 4 M slots for 0.1 M occupied ones on the bench frame)
+__global__ void __launch_bounds__(256) k_voxel_cleanup(const unsigned *__restrict__ slot_of, VoxBucket *table, const FrameCtl *ctl) {
+	const int N = ctl->n_culled;
+	const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
+		uint4 *b = reinterpret_cast<uint4 *>(table + (slot_of[g] >> 3));
+		b[0] = z; b[1] = z; b[2] = z;
 	}
 }
 
@@ -1149,6 +1186,7 @@ struct Ls3dFrame {
 	int max_w = 0, max_h = 0;
 	size_t depth_bytes = 0, color_bytes = 0;
 	unsigned total_slots = 0;
+	bool table_dirty = true;           // the voxel table is not known to be all zero (see frame_filter_stages)
 	std::vector<SensorDesc> h_sd;       // S+1 entries (sentinel last)
 	SensorDesc *pin_sd = nullptr;       // pinned staging for the descriptor upload
 	float *pin_rays = nullptr;          // pinned staging for the ray tables
@@ -1168,7 +1206,7 @@ struct Ls3dFrame {
 	int sm_count = 148;
 
 	// device memory
-	DevBuf sd, tile_sensor, rays, zero, cloud0, sorted, final_, slot_of, rank_of, keep, keep_px, map, d2v, table, cell_start, in_depth, in_colors, box, tri;
+	DevBuf sd, tile_sensor, rays, zero, cloud0, sorted, final_, slot_of, rank_of, keep, keep_px, map, d2v, table, in_depth, in_colors, box, tri;
 	// carve-outs of `zero` (re-zeroed by one memset per run)
 	FrameCtl *ctl = nullptr;
 	unsigned long long *status_a = nullptr, *status_b = nullptr;
@@ -1223,7 +1261,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static void frame_free(Ls3dFrame *f) {
 	if (!f) return;
 	DevBuf *bufs[] = {&f->sd, &f->tile_sensor, &f->rays, &f->zero, &f->cloud0, &f->sorted, &f->final_, &f->slot_of, &f->rank_of, &f->keep, &f->keep_px, &f->map, &f->d2v,
-		&f->table, &f->cell_start, &f->in_depth, &f->in_colors, &f->box, &f->tri};
+		&f->table, &f->in_depth, &f->in_colors, &f->box, &f->tri};
 	for (DevBuf *b : bufs) b->release();
 	if (f->pin_sd) cudaFreeHost(f->pin_sd);
 	if (f->pin_rays) cudaFreeHost(f->pin_rays);
@@ -1283,7 +1321,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		f->max_w = std::max(f->max_w, d.w);
 		f->max_h = std::max(f->max_h, d.h);
 		unsigned long long cap = 64;
-		while (cap < (unsigned long long)px * 3 / 2) cap <<= 1;
+		while (cap < (unsigned long long)px * 9 / 8 + 64) cap <<= 1;       // runs of 8 voxels: never more of them than points
 		d.tbl_mask = (unsigned)(cap - 1);
 		slot_acc += cap;
 		px_acc += px;
@@ -1295,7 +1333,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		tile_sensor.insert(tile_sensor.end(), nt, (unsigned short)i);
 		tile_acc += nt;
 	}
-	if (px_acc >= (1ll << 31) - kTile || slot_acc >= (1ull << 32)) { set_error("ls3d_frame_create: frame too large"); delete f; return nullptr; }
+	if (px_acc >= (1ll << 31) - kTile || slot_acc >= (1ull << 29)) { set_error("ls3d_frame_create: frame too large"); delete f; return nullptr; }
 	f->total_px = px_acc;
 	f->total_tiles = tile_acc;
 	f->depth_bytes = (size_t)depth_off;
@@ -1313,7 +1351,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 		f->slot_of.reserve(4 * n, "alloc slots") && f->rank_of.reserve(4 * n, "alloc ranks") && f->keep.reserve(align_up(n, 16) + 16, "alloc keep flags") &&
 		f->keep_px.reserve(align_up(n, 16) + 16, "alloc pixel keep flags") &&
 		f->map.reserve(4 * n, "alloc index map") && f->d2v.reserve(4 * n, "alloc pixel map") &&
-		f->table.reserve(8 * (size_t)f->total_slots, "alloc voxel hash") && f->cell_start.reserve(4 * (size_t)f->total_slots, "alloc voxel ranges") &&
+		f->table.reserve(sizeof(VoxBucket) * (size_t)f->total_slots, "alloc voxel hash") &&
 		f->box.reserve(sizeof(FilterBox), "alloc bbox");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_sd, sizeof(SensorDesc) * (n_maps + 1), cudaHostAllocDefault), "alloc pinned descriptors");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&f->pin_rays, sizeof(float) * (f->n_rays + 4), cudaHostAllocDefault), "alloc pinned ray tables");
@@ -1635,31 +1673,36 @@ static int frame_merge_stage(Ls3dFrame *f, int s_first, int s_end, long long n_m
 	return cuda_ok(cudaGetLastError(), "k_filter_compact") ? 1 : -1;
 }
 
-// voxel-hash neighbour count on the culled cloud in cloud0 (4 kernels), optionally followed by the compaction
+// voxel-run neighbour count on the culled cloud in cloud0 (5 kernels), optionally followed by the compaction
 static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n_max, uint4 *dst, const int *d_dst_offset, const PeerDst &peers, cudaStream_t st, int stages = kStageCount | kStageMerge) {
 	const SensorDesc *sd = f->sd.as<SensorDesc>();
-	const unsigned slot_lo = f->h_sd[s_first].tbl_off, slot_hi = f->h_sd[s_end].tbl_off;
+	VoxBucket *table = f->table.as<VoxBucket>();
 	stage_begin(f, kTsHashClear, st);
-	if (!cuda_ok(cudaMemsetAsync(f->table.as<unsigned long long>() + slot_lo, 0, 8 * (size_t)(slot_hi - slot_lo), st), "clear voxel hash")) return -1;
+	if (f->table_dirty) {
+		// first use, or an earlier run was cut short before its clean-up kernel was enqueued
+		if (!cuda_ok(cudaMemsetAsync(table, 0, sizeof(VoxBucket) * (size_t)f->total_slots, st), "clear voxel hash")) return -1;
+	}
+	f->table_dirty = true;
 	stage_end(f, kTsHashClear, st);
-	const int pt_blocks = (int)std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8);
+	const int pt_blocks = (int)std::max<long long>(1, std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8));
 	stage_begin(f, kTsInsert, st);
 	k_voxel_insert<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
-		f->table.as<unsigned long long>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>());
+		table, f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>());
 	stage_end(f, kTsInsert, st);
 	stage_begin(f, kTsRanges, st);
-	k_cell_ranges<<<(slot_hi - slot_lo + kRangeThreads - 1) / kRangeThreads, kRangeThreads, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(), slot_lo, slot_hi, f->ctl);
-	k_cell_scatter<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(),
-		f->cell_start.as<unsigned>(), f->ctl, f->sorted.as<float4>());
+	k_bucket_alloc<<<pt_blocks, 256, 0, st>>>(f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(), table, f->ctl);
+	k_cell_scatter<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(), table, f->ctl, f->sorted.as<float4>());
 	stage_end(f, kTsRanges, st);
 	stage_begin(f, kTsCount, st);
-	k_neighbour_count<<<f->sm_count * 8, kCountWarps * 32, 0, st>>>(f->table.as<unsigned long long>(), f->cell_start.as<unsigned>(),
-		f->sorted.as<float4>(), sd, f->culled_starts, s_first, s_end, f->ctl, f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
+	k_neighbour_count<<<f->sm_count * 8, kCountWarps * 32, 0, st>>>(table, f->cloud0.as<uint4>(), f->sorted.as<float4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
+		f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
+	k_voxel_cleanup<<<pt_blocks, 256, 0, st>>>(f->slot_of.as<unsigned>(), table, f->ctl);
 	stage_end(f, kTsCount, st);
-	count_launch(4);
+	count_launch(5);
 	if (!cuda_ok(cudaGetLastError(), "filter kernels")) return -1;
-	if (!(stages & kStageMerge)) return 4;
-	return frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st) < 0 ? -1 : 5;
+	f->table_dirty = false;                 // everything up to the clean-up is in the stream
+	if (!(stages & kStageMerge)) return 5;
+	return frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st) < 0 ? -1 : 6;
 }
 
 // K1o: per-pixel survivor mask of sensors [s_first, s_end) straight from the depth images (the cloud is only materialised by the
