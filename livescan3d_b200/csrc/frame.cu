@@ -11,13 +11,15 @@
 // Kernels (all sensors of a run are batched into every launch; "g" is a point's index in the culled cloud):
 //   K1 k_map_cull_compact  per 2048-pixel tile: u16 depth + RGB in, pinhole map, +t, R*, strict cull, stable
 //                          compaction through a decoupled look-back scan, 16-byte records out (HBM-bound)
-//   K2 k_voxel_insert      voxel key per point, warp-aggregated insert into a per-sensor open-addressing hash
-//                          whose 64-bit entries hold (key+1)<<24 | count; returns slot and rank per point
-//   K3 k_bucket_alloc      one contiguous range of the sorted array per occupied run of 8 voxels
-//   K4 k_cell_scatter      counting-sort scatter of (x,y,z,g) into voxel order
-//   K5 k_neighbour_count   one warp per occupied voxel: 27 hash look-ups by 27 lanes, candidates staged in
-//                          shared memory, count{d2 <= thr} per query by ballot/popc with warp-uniform early
-//                          exit at k (the filter keeps i  <=>  its k-th NN distance <= thr  <=>  count >= k)
+//   K2 k_voxel_insert      per point: its run of 8 voxels along x (30-bit key) found or claimed in a per-sensor open-addressing
+//                          hash of 64-byte slots, run total and voxel count incremented (warp-aggregated); slot and rank per point
+//   K3 k_bucket_alloc      one contiguous range of the sorted array per occupied run (block scan over the elected points, one
+//                          atomic per block); voxel counts -> inclusive prefix sums in the slot
+//   K4 k_cell_scatter      counting-sort scatter of (x,y,z,g) into run / voxel order
+//   K5 k_neighbour_count   one lane per query, input order: 9 row look-ups (one 32-byte load each; 18 when the row straddles two
+//                          runs), then a private cursor over the contiguous candidate ranges, two candidates per 32-byte load,
+//                          leaving at k (the filter keeps i  <=>  its k-th NN distance <= thr  <=>  count >= k); k_voxel_cleanup
+//                          zeroes the slots the run's points touched (no memset of the table)
 //   K6 k_filter_compact    stable compaction of the survivors (look-back scan again); sensor order is the
 //                          merge order, so the merged cloud is produced here with no extra copy; can store
 //                          to several destinations (peer-mapped buffers) for the multi-GPU merge
@@ -33,17 +35,20 @@
 
 namespace ls3d {
 
-constexpr int kCellBits = 13;                 // voxel coordinate bits per axis
+constexpr int kCellBits = 11;                 // voxel coordinate bits per axis: (z, y, x >> 3) of a run of 8 voxels is a 30-bit key
 constexpr int kCellMax = (1 << kCellBits) - 1;
-constexpr unsigned long long kCountMask = 0xFFFFFFull;
+constexpr unsigned long long kCountMask = 0xFFFFFFull;      // points per run of voxels (and per call)
 constexpr int kCountWarps = 4;                // warps per block in K5
 constexpr int kMaxPeers = 8;
 
 struct PeerDst { int n; uint4 *ptr[kMaxPeers]; };
 
-__device__ __forceinline__ unsigned voxel_hash(unsigned long long key) {
-	return (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 32);
-}
+// hash of a run (bx = x >> 3, y, z): one multiplicative term per axis, so the nine rows around a voxel cost two XORs each once the
+// three y- and three z-terms are known; the final shift-xor spreads the high bits into the table index
+__device__ __forceinline__ unsigned hash_x(int bx) { return (unsigned)bx * 0x9E3779B1u; }
+__device__ __forceinline__ unsigned hash_y(int y) { return (unsigned)y * 0x85EBCA77u; }
+__device__ __forceinline__ unsigned hash_z(int z) { return (unsigned)z * 0xC2B2AE3Du; }
+__device__ __forceinline__ unsigned hash_mix(unsigned h) { return h ^ (h >> 15); }
 __device__ __forceinline__ int cell_coord(float x, float o, float inv_h) {
 	// monotone in x: fp32 subtract, fp32 multiply by a positive constant, floor, clamp
 	float u = floorf(__fmul_rn(__fsub_rn(x, o), inv_h));
@@ -736,13 +741,20 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 // The table is never cleared as a whole: k_voxel_cleanup zeroes exactly the slots the run's points touched.
 constexpr int kRunBits = 3;
 struct alignas(64) VoxBucket {
-	unsigned long long word;       // (key + 1) << 24 | points in the run; 0 = free
-	unsigned start, pad0;          // first position of the run's points in the sorted array (k_bucket_alloc)
-	unsigned cnt[8];               // points per voxel of the run
-	unsigned pad1[4];
+	unsigned long long word;       // (key + 1) << 32 | points in the run; 0 = free
+	unsigned start;                // first position of the run's points in the sorted array (k_bucket_alloc)
+	unsigned wide;                 // 1: more than 65535 points in the run, inc16 is not valid, read cnt
+	unsigned short inc16[8];       // inclusive prefix sums of the voxel counts: with the header, the ONE sector a row look-up reads
+	unsigned cnt[8];               // points per voxel of the run; k_bucket_alloc turns them into the inclusive prefix sums
 };
-__device__ __forceinline__ unsigned long long bucket_key(int cx, int cy, int cz) {
-	return ((unsigned long long)cz << (2 * kCellBits)) | ((unsigned long long)cy << kCellBits) | (unsigned long long)(cx >> kRunBits);
+struct alignas(32) V8 { unsigned v[8]; };
+__device__ __forceinline__ V8 ldg256(const void *p) {          // one 32-byte request per lane (LDG.E.256, sm_100)
+	V8 r;
+	asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ unsigned bucket_key(int bx, int cy, int cz) {       // bx = cx >> kRunBits
+	return ((unsigned)cz << (2 * kCellBits - kRunBits)) | ((unsigned)cy << (kCellBits - kRunBits)) | (unsigned)bx;
 }
 
 // K2: per point — find or claim its run's slot, add to the run total and to the voxel's count (the old value is the point's rank).
@@ -757,7 +769,8 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 	for (int g0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); g0 < N; g0 += gridDim.x * blockDim.x) {
 		const int g = g0 + lane;
 		const bool active = g < N;
-		unsigned long long key = 0, tag = ~0ull - (unsigned long long)lane;
+		unsigned key = 0, h0 = 0;
+		unsigned long long tag = ~0ull - (unsigned long long)lane;
 		int s = s_first, cx = 0;
 		if (active) {
 			while (s + 1 < s_end && culled_starts[s + 1] <= g) s++;
@@ -765,8 +778,9 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 			cx = cell_coord(__uint_as_float(p.y), sd[s].gox, sd[s].ginv_h);
 			const int cy = cell_coord(__uint_as_float(p.z), sd[s].goy, sd[s].ginv_h);
 			const int cz = cell_coord(__uint_as_float(p.w), sd[s].goz, sd[s].ginv_h);
-			key = bucket_key(cx, cy, cz);
-			tag = (key << 3) | (unsigned long long)(cx & 7) | ((unsigned long long)s << 44);
+			key = bucket_key(cx >> kRunBits, cy, cz);
+			h0 = hash_mix(hash_x(cx >> kRunBits) ^ hash_y(cy) ^ hash_z(cz));
+			tag = ((unsigned long long)key << 3) | (unsigned long long)(cx & 7) | ((unsigned long long)s << 40);
 		}
 		const unsigned grp = __match_any_sync(kFull, tag);
 		const int leader = __ffs(grp) - 1;
@@ -774,16 +788,16 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 		if (active && lane == leader) {
 			const unsigned n = __popc(grp);
 			const unsigned toff = sd[s].tbl_off, tmask = sd[s].tbl_mask;
-			const unsigned long long want = key + 1;
-			unsigned h = voxel_hash(key) & tmask;
+			const unsigned long long want = (unsigned long long)key + 1;
+			unsigned h = h0 & tmask;
 			bool found = false;
 			for (unsigned probe = 0; probe <= tmask; probe++) {
 				const unsigned long long w = table[toff + h].word;
-				const unsigned long long kk = w >> 24;
+				const unsigned long long kk = w >> 32;
 				if (kk == want) { found = true; break; }
 				if (kk == 0) {
-					const unsigned long long prev = atomicCAS(&table[toff + h].word, 0ull, want << 24);
-					if (prev == 0 || (prev >> 24) == want) { found = true; break; }
+					const unsigned long long prev = atomicCAS(&table[toff + h].word, 0ull, want << 32);
+					if (prev == 0 || (prev >> 32) == want) { found = true; break; }
 				}
 				h = (h + 1) & tmask;
 			}
@@ -831,7 +845,16 @@ __global__ void __launch_bounds__(256) k_bucket_alloc(const unsigned *__restrict
 			if (lane == 31) s_base = sc ? atomicAdd(&ctl->cursor, sc) : 0u;
 		}
 		__syncthreads();
-		if (tot) table[slot].start = s_base + s_w[warp] + incl - tot;
+		if (tot) {
+			table[slot].start = s_base + s_w[warp] + incl - tot;
+			// voxel counts -> inclusive prefix sums, in place (every rank is out by now): a row's range is two of these values
+			uint4 *cp = reinterpret_cast<uint4 *>(table[slot].cnt);
+			uint4 a = cp[0], b = cp[1];
+			a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
+			cp[0] = a; cp[1] = b;
+			*reinterpret_cast<uint4 *>(table[slot].inc16) = make_uint4((a.x & 0xffffu) | (a.y << 16), (a.z & 0xffffu) | (a.w << 16), (b.x & 0xffffu) | (b.y << 16), (b.z & 0xffffu) | (b.w << 16));
+			table[slot].wide = tot > 0xffffu ? 1u : 0u;
+		}
 	}
 }
 
@@ -843,20 +866,14 @@ __global__ void __launch_bounds__(256) k_cell_scatter(const uint4 *__restrict__ 
 	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
 		const uint4 p = cloud[g];
 		const unsigned sc = slot_of[g], c = sc & 7u;
-		const uint4 *b = reinterpret_cast<const uint4 *>(table + (sc >> 3));
-		const uint4 h = __ldg(b), c0 = __ldg(b + 1), c1 = __ldg(b + 2);
-		const unsigned cn[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-		unsigned pre = 0;
-#pragma unroll
-		for (int j = 0; j < 7; j++) pre += (unsigned)j < c ? cn[j] : 0u;
-		const unsigned pos = h.z + pre + (rank_of[g] & 0x7fffffffu);
+		const VoxBucket *b = table + (sc >> 3);
+		const unsigned pre = c ? __ldg(b->cnt + c - 1) : 0u;
+		const unsigned pos = __ldg(&b->start) + pre + (rank_of[g] & 0x7fffffffu);
 		sorted[pos] = make_float4(__uint_as_float(p.y), __uint_as_float(p.z), __uint_as_float(p.w), __int_as_float(g));
 	}
 }
 
-// K5: neighbour count, one lane per query in input order.
-// rows in visiting order: the query's own row first, then the four face rows, then the four edge rows, plane by plane of three
-__constant__ signed char c_row[9][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
+// K5: neighbour count, one lane per query in input order; rows visited plane by plane (z, z-1, z+1), the query's own row first
 constexpr int kLaneIters = 96;
 constexpr int kMaxRanges = 18;
 
@@ -887,59 +904,62 @@ __global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const VoxB
 			const int cx = cell_coord(qx, sd[s].gox, sd[s].ginv_h), cy = cell_coord(qy, sd[s].goy, sd[s].ginv_h), cz = cell_coord(qz, sd[s].goz, sd[s].ginv_h);
 			const unsigned toff = sd[s].tbl_off, tmask = sd[s].tbl_mask;
 			const int xlo = max(cx - 1, 0), xhi = min(cx + 1, kCellMax);
-			const int blo = xlo >> kRunBits, bhi = xhi >> kRunBits;          // the runs the row touches (one, or two neighbours)
-			// ---- look-ups, three rows at a time (nine 16-byte loads in flight before the first is examined); the second run of a
-			// straddling row in a pass of its own, so the common case keeps its registers ----
-			auto rows3 = [&](int r0, int bx) {
-				uint4 hd[3], ca[3], cb[3];
-				unsigned long long want[3];
+			const int blo = xlo >> kRunBits, bhi = xhi >> kRunBits;          // the runs a row touches (one, or two neighbours)
+			// ---- look-ups: the three rows of a z-plane together (three 32-byte loads in flight before the first is examined); the
+			// second run of a straddling row in a pass of its own, so the common case keeps its registers.  Rows outside the grid (a
+			// voxel on its boundary) are skipped.  Measured and dropped: trimming the voxels the ball cannot reach from the query's
+			// position inside its voxel (27 % fewer candidates, but 108-114 us against 91: more registers, more divergent ranges).
+			const unsigned hy[3] = {hash_y(cy - 1), hash_y(cy), hash_y(cy + 1)};
+			const unsigned kyb = (unsigned)cy << (kCellBits - kRunBits);
+			const unsigned ok_y = (cy > 0 ? 1u : 0u) | 2u | (cy < kCellMax ? 4u : 0u);
+			auto plane = [&](int dz, int bx) {
+				const int z = cz + dz;
+				if (z < 0 || z > kCellMax) return;
+				// voxels [a, e] of run bx belong to the rows: known before anything is loaded
+				const int base = bx << kRunBits;
+				const int a = max(xlo - base, 0), e = min(xhi - base, 7);
+				const unsigned hxz = hash_x(bx) ^ hash_z(z);
+				const unsigned kxz = ((unsigned)z << (2 * kCellBits - kRunBits)) | (unsigned)bx;
+				V8 hd[3];
 				unsigned hh[3];
+				// (the zero fill also keeps ptxas from hoisting all eighteen loads of the six planes to the top: 182 registers without it)
+				const V8 zero8 = {{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
 #pragma unroll
-				for (int j = 0; j < 3; j++) {
-					const int y = cy + c_row[r0 + j][0], z = cz + c_row[r0 + j][1];
-					want[j] = 0; hh[j] = 0;
-					hd[j] = ca[j] = cb[j] = make_uint4(0u, 0u, 0u, 0u);
-					if (y >= 0 && y <= kCellMax && z >= 0 && z <= kCellMax) {
-						const unsigned long long key = ((unsigned long long)z << (2 * kCellBits)) | ((unsigned long long)y << kCellBits) | (unsigned long long)bx;
-						want[j] = key + 1;
-						hh[j] = voxel_hash(key) & tmask;
-						const uint4 *bp = reinterpret_cast<const uint4 *>(table + toff + hh[j]);
-						hd[j] = __ldg(bp); ca[j] = __ldg(bp + 1); cb[j] = __ldg(bp + 2);
-					}
+				for (int j = 0; j < 3; j++) {              // j: dy = 0, -1, +1 (the query's own row first)
+					const int yi = j == 0 ? 1 : (j == 1 ? 0 : 2);
+					hh[j] = hash_mix(hxz ^ hy[yi]) & tmask;
+					hd[j] = zero8;
+					if ((ok_y >> yi) & 1u) hd[j] = ldg256(table + toff + hh[j]);
 				}
 #pragma unroll
 				for (int j = 0; j < 3; j++) {
-					if (!want[j]) continue;
-					unsigned long long w = ((unsigned long long)hd[j].y << 32) | hd[j].x;
-					if ((w >> 24) != want[j] && (w >> 24) != 0) {
+					const int yi = j == 0 ? 1 : (j == 1 ? 0 : 2);
+					const unsigned want = kxz + (kyb + ((unsigned)yi << (kCellBits - kRunBits)) - (1u << (kCellBits - kRunBits))) + 1u;      // key(y = cy + yi - 1) + 1
+					const VoxBucket *bp = table + toff + hh[j];
+					if (hd[j].v[1] != want && hd[j].v[1] != 0u) {
 						// another run sits in the slot: follow the probe sequence (rare at this table's load)
 						unsigned h = hh[j];
 						for (unsigned probe = 0; probe <= tmask; probe++) {
 							h = (h + 1) & tmask;
-							const uint4 *bp = reinterpret_cast<const uint4 *>(table + toff + h);
-							hd[j] = __ldg(bp);
-							w = ((unsigned long long)hd[j].y << 32) | hd[j].x;
-							if ((w >> 24) == want[j]) { ca[j] = __ldg(bp + 1); cb[j] = __ldg(bp + 2); break; }
-							if ((w >> 24) == 0) break;
+							bp = table + toff + h;
+							hd[j] = ldg256(bp);
+							if (hd[j].v[1] == want || hd[j].v[1] == 0u) break;
 						}
 					}
-					if ((w >> 24) != want[j]) continue;
-					// voxels [a, e] of this run belong to the row
-					const int base = bx << kRunBits;
-					const int a = max(xlo - base, 0), e = min(xhi - base, 7);
-					const unsigned cn[8] = {ca[j].x, ca[j].y, ca[j].z, ca[j].w, cb[j].x, cb[j].y, cb[j].z, cb[j].w};
-					unsigned pre = 0, n = 0;
-#pragma unroll
-					for (int v = 0; v < 8; v++) { pre += v < a ? cn[v] : 0u; n += (v >= a && v <= e) ? cn[v] : 0u; }
-					if (n) { s_rng[warp][nr][lane] = make_uint2(hd[j].z + pre, n); nr++; tot += n; }
+					if (hd[j].v[1] != want) continue;
+					// inclusive prefix sums [a - 1] and [e] bound the row's range
+					auto inc = [&](int i) -> unsigned {
+						const unsigned wsel = (i & 4) ? ((i & 2) ? hd[j].v[7] : hd[j].v[6]) : ((i & 2) ? hd[j].v[5] : hd[j].v[4]);
+						return (i & 1) ? (wsel >> 16) : (wsel & 0xffffu);
+					};
+					unsigned pe = inc(e), pa = a ? inc(a - 1) : 0u;
+					if (hd[j].v[3]) { pe = __ldg(bp->cnt + e); pa = a ? __ldg(bp->cnt + a - 1) : 0u; }      // more than 65535 points in the run
+					const unsigned n = pe - pa;
+					if (n) { s_rng[warp][nr][lane] = make_uint2(hd[j].v[2] + pa, n); nr++; tot += n; }
 				}
 			};
-#pragma unroll 1
-			for (int r0 = 0; r0 < 9; r0 += 3) rows3(r0, blo);
-			if (bhi != blo) {
-#pragma unroll 1
-				for (int r0 = 0; r0 < 9; r0 += 3) rows3(r0, bhi);
-			}
+			plane(0, blo); plane(-1, blo); plane(1, blo);
+			if (bhi != blo) { plane(0, bhi); plane(-1, bhi); plane(1, bhi); }
 		}
 		__syncwarp();
 
@@ -952,9 +972,14 @@ __global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const VoxB
 			const bool act = cnt < k && c < nr;
 			if (!__any_sync(kFull, act)) break;
 			if (act) {
-				const float4 cd = __ldg(sorted + p);
-				cnt += dist2_ref(qx, qy, qz, cd.x, cd.y, cd.z) <= thr ? 1 : 0;
-				if (++p == e) {
+				// one aligned 32-byte request per turn = two candidates (the pair that holds position p); counting past k is harmless
+				const unsigned q0 = p & ~1u;
+				const V8 cc = ldg256(sorted + q0);
+				const bool lo_ok = !(p & 1u), hi_ok = q0 + 1u < e;
+				cnt += (lo_ok && dist2_ref(qx, qy, qz, __uint_as_float(cc.v[0]), __uint_as_float(cc.v[1]), __uint_as_float(cc.v[2])) <= thr) ? 1 : 0;
+				cnt += (hi_ok && dist2_ref(qx, qy, qz, __uint_as_float(cc.v[4]), __uint_as_float(cc.v[5]), __uint_as_float(cc.v[6])) <= thr) ? 1 : 0;
+				p = min(q0 + 2u, e);
+				if (p == e) {
 					if (++c < nr) { const uint2 r = s_rng[warp][c][lane]; p = r.x; e = r.x + r.y; }
 				}
 			}
@@ -999,7 +1024,7 @@ __global__ void __launch_bounds__(256) k_voxel_cleanup(const unsigned *__restric
 	const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
 		uint4 *b = reinterpret_cast<uint4 *>(table + (slot_of[g] >> 3));
-		b[0] = z; b[1] = z; b[2] = z;
+		b[0] = z; b[1] = z; b[2] = z; b[3] = z;
 	}
 }
 
@@ -1347,7 +1372,7 @@ extern "C" Ls3dFrame *ls3d_frame_create(int n_maps, const int *widths, const int
 	f->zero_bytes = ctl_b + 2 * st_b + 3 * starts_b;
 	bool ok = f->sd.reserve(sizeof(SensorDesc) * (n_maps + 1), "alloc descriptors") && f->zero.reserve(f->zero_bytes, "alloc control block") &&
 		f->tile_sensor.reserve(sizeof(unsigned short) * (tile_sensor.size() + 1), "alloc tile table") && f->rays.reserve(sizeof(float) * (f->n_rays + 4), "alloc ray tables") &&
-		f->cloud0.reserve(16 * n, "alloc culled cloud") && f->sorted.reserve(16 * n, "alloc sorted cloud") && f->final_.reserve(16 * n, "alloc merged cloud") &&
+		f->cloud0.reserve(16 * n, "alloc culled cloud") && f->sorted.reserve(16 * n + 64, "alloc sorted cloud") && f->final_.reserve(16 * n, "alloc merged cloud") &&
 		f->slot_of.reserve(4 * n, "alloc slots") && f->rank_of.reserve(4 * n, "alloc ranks") && f->keep.reserve(align_up(n, 16) + 16, "alloc keep flags") &&
 		f->keep_px.reserve(align_up(n, 16) + 16, "alloc pixel keep flags") &&
 		f->map.reserve(4 * n, "alloc index map") && f->d2v.reserve(4 * n, "alloc pixel map") &&
@@ -1694,7 +1719,7 @@ static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n
 	k_cell_scatter<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(), table, f->ctl, f->sorted.as<float4>());
 	stage_end(f, kTsRanges, st);
 	stage_begin(f, kTsCount, st);
-	k_neighbour_count<<<f->sm_count * 8, kCountWarps * 32, 0, st>>>(table, f->cloud0.as<uint4>(), f->sorted.as<float4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
+	k_neighbour_count<<<f->sm_count * 12, kCountWarps * 32, 0, st>>>(table, f->cloud0.as<uint4>(), f->sorted.as<float4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
 		f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
 	k_voxel_cleanup<<<pt_blocks, 256, 0, st>>>(f->slot_of.as<unsigned>(), table, f->ctl);
 	stage_end(f, kTsCount, st);

@@ -318,6 +318,40 @@ def test_filter_full_size_sensor(api):
         assert gv.tobytes() == wv.tobytes() and gc.tobytes() == wc.tobytes()
 
 
+def test_filter_shuffled_input(api):
+    """The voxel path processes queries in input order; nothing may depend on that order being a raster scan."""
+    fr = small_frame(S=1, w=200, h=150)
+    xyz, rgba = cloud_of(fr, synth.DEFAULT_BOUNDS, 0)
+    perm = np.random.default_rng(5).permutation(len(xyz))
+    xyz, rgba = np.ascontiguousarray(xyz[perm]), np.ascontiguousarray(rgba[perm])
+    for k, md in [(10, 0.01), (6, 0.03)]:
+        wv, wc, wm = orc.orc_filter(xyz, rgba, k, md)
+        gv, gc, gm = api.filter(xyz, rgba, k, md)
+        assert np.array_equal(gm, wm) and gv.tobytes() == wv.tobytes() and gc.tobytes() == wc.tobytes()
+
+
+def test_filter_run_with_more_than_65535_points(api):
+    """66 000 points inside one voxel (cube edge = maxDist): the run's 16-bit prefix sums overflow and the 32-bit ones are read.
+    k is the median neighbour count, so the decision depends on the exact count (a corner sees 52 % of the cube, the centre all of
+    it).  Truth: brute force in numpy with the reference's fp32 expression (filter.h:38-45) for 3 000 sampled points."""
+    n, md = 66000, np.float32(0.05)
+    rng = np.random.default_rng(11)
+    xyz = (rng.random((n, 3)) * 0.0499 + np.array([0.3, -0.2, 1.0])).astype(np.float32)
+    rgba = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+    thr = np.float32(np.float64(md) ** 2)
+    rows = np.sort(rng.choice(n, 3000, replace=False))
+    counts = np.zeros(len(rows), np.int64)
+    for a in range(0, len(rows), 500):
+        q = xyz[rows[a:a + 500]]
+        d0, d1, d2 = q[:, None, 0] - xyz[None, :, 0], q[:, None, 1] - xyz[None, :, 1], q[:, None, 2] - xyz[None, :, 2]
+        counts[a:a + 500] = (((d0 * d0 + d1 * d1) + d2 * d2) <= thr).sum(axis=1)
+    k = int(np.median(counts))
+    gv, gc, gm = api.filter(xyz, rgba, k, float(md))
+    assert np.array_equal(gm[rows] >= 0, counts >= k), f"{((gm[rows] >= 0) != (counts >= k)).sum()} mask mismatches of {len(rows)}"
+    assert 0.2 < (gm >= 0).mean() < 0.8
+    assert gv.tobytes() == xyz[gm >= 0].tobytes() and np.array_equal(gm[gm >= 0], np.arange(len(gv)))
+
+
 def _pipeline_oracle(fr, bounds, k, md):
     """createVertices -> filter per sensor -> formMesh, composed from the oracle's stages."""
     parts, counts = [], []
