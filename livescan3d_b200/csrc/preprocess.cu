@@ -23,6 +23,8 @@
 #include "ls3d_internal.h"
 #include "../../include/ls3d.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <climits>
 #include <cstdio>
@@ -403,6 +405,161 @@ __global__ void __launch_bounds__(kChainThreads) k_rad_chains(const PreSensor *_
 	}
 }
 
+// What the grid-wide round left pending, finished by FIXPOINT ITERATION instead of along the chains (round 2).  The fill of a hole is
+// a function of its eight neighbours; the four raster-earlier ones may be pending holes themselves, which is what makes the reference's
+// raster-order loop a recurrence.  But the recurrence is over a DAG (a hole only reads raster-earlier holes), so the assignment "every
+// pending hole holds exactly what the fill rule gives for the values its neighbours hold" has ONE solution — the reference's result —
+// and any iteration that ends in a full pass without a change has found it.  So: every pending hole is evaluated at once from the
+// tentative values in place (unfilled = 0 to start with), again and again until a pass changes nothing.  A fill is an average of five to
+// eight values, so a wrong guess upstream reaches the next link divided by n >= 5 and dies out within a few links: the thin hole curves
+// of a warped Kinect frame (chains of ~h links, 0.43 ms in k_rad_chains at ~0.3 us per link) settle in a handful of passes.  Only a
+// chain whose fill DECISIONS hang on one another (each link has exactly four valid fixed neighbours) needs one pass per link, which is
+// what the chain kernel costs anyway.  After the first pass a hole is re-evaluated only if a raster-earlier neighbour changed in the
+// previous pass (two alternating "changed" bits in the state byte); it reads values another thread may be rewriting in the same pass —
+// harmless: whoever changed flags itself, and its readers run again next pass, after the barrier.
+// A CLUSTER of eight 1024-thread blocks per sensor (one block alone is instruction-bound on its SM: 8 holes per thread, 12 us per
+// pass): each block lists the pending holes of its eighth of the image and owns them, about one per thread; a pass ends in a cluster
+// barrier, and the blocks learn from each other's "changed" flags (distributed shared memory) whether another pass is needed.
+// Values other blocks may have rewritten are read with loads that bypass L1.
+constexpr int kFixThreads = 1024, kFixCluster = 8;
+enum : unsigned char { kRadChgA = 4, kRadChgB = 8 };
+__global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThreads) k_rad_fixpoint(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors,
+	unsigned char *state, int *__restrict__ list, int *err)
+{
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster();
+	__shared__ unsigned s_w[32];
+	__shared__ unsigned s_total;
+	__shared__ int s_flag[2];
+	const unsigned rank = cluster.block_rank();
+	const PreSensor s = sd[blockIdx.x / kFixCluster];
+	const int px = s.w * s.h, w = s.w;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	// this block's pixels [r0, r1) and its slice of the list buffer
+	const int r0 = (int)((long long)px * rank / kFixCluster), r1 = (int)((long long)px * (rank + 1) / kFixCluster);
+	int *lst = list + s.pix_begin + r0;
+	unsigned n_pending = 0;
+	for (int base = r0; base < r1; base += kFixThreads * 16) {
+		const int p0 = base + tid * 16;
+		unsigned m = 0;
+#pragma unroll
+		for (int j = 0; j < 16; j++)
+			if (p0 + j < r1 && !(state[s.pix_begin + p0 + j] & kRadDone)) m |= 1u << j;
+		const unsigned cnt = __popc(m), incl = warp_incl_scan(cnt, lane);
+		if (lane == 31) s_w[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			const unsigned v = s_w[lane], sc = warp_incl_scan(v, lane);
+			s_w[lane] = sc - v;
+			if (lane == 31) s_total = sc;
+		}
+		__syncthreads();
+		unsigned o = n_pending + s_w[warp] + incl - cnt;
+		while (m) {
+			const int j = __ffs(m) - 1;
+			m &= m - 1;
+			lst[o++] = p0 + j;
+		}
+		n_pending += s_total;
+		__syncthreads();
+	}
+	const int nb[8] = {-w - 1, -w, -w + 1, -1, 1, w - 1, w, w + 1};      // depthprocessing.cpp:226
+	// Passes are LOCAL to a block (a __syncthreads each, values and flags of its own holes read through its own L1) until the block
+	// sees no change; only then does the cluster meet, and the blocks learn from each other's flags whether anyone changed since the
+	// last meeting.  A hole whose raster-earlier neighbours belong to the block before (pixel < r0 + w + 1) cannot use that block's
+	// "changed" bits — the blocks count their passes independently — so it is simply re-evaluated in the first pass after every
+	// meeting, reading those neighbours past L1.  The last meeting follows a round in which no block changed anything: every such
+	// hole was evaluated in it from values that no longer moved.
+	// A hole only reads holes at most a row back, so a chain cannot be longer than the image has pixels: px + 1 rounds always suffice.
+	const long long own_lo = s.pix_begin + r0;
+	unsigned pass = 0;
+	bool converged = false;
+	for (int round = 0; round <= px + 1; round++) {
+		int any_round = 0;
+		for (bool first = true;; first = false) {
+			const unsigned char bit_cur = (pass & 1u) ? kRadChgB : kRadChgA, bit_prev = (pass & 1u) ? kRadChgA : kRadChgB;
+			int changed = 0;
+			for (unsigned e = tid; e < n_pending; e += kFixThreads) {
+				const int p = lst[e];
+				const long long gp = s.pix_begin + p;
+				const bool border = p < r0 + w + 1;
+				unsigned st[4];
+#pragma unroll
+				for (int i = 0; i < 4; i++) st[i] = (gp + nb[i] >= own_lo) ? ld_vol_u8<true>(state + gp + nb[i]) : ld_vol_u8<false>(state + gp + nb[i]);
+				const unsigned char mine = (unsigned char)ld_vol_u8<true>(state + gp);        // only this thread writes it
+				unsigned moved = 0;
+#pragma unroll
+				for (int i = 0; i < 4; i++) moved |= (gp + nb[i] >= own_lo) ? (st[i] & bit_prev) : 0u;
+				if (!(pass == 0 || moved || (first && border))) {
+					// nothing this hole reads has moved since it was last evaluated
+					if (mine & bit_cur) state[gp] = mine & (unsigned char)~bit_cur;
+					continue;
+				}
+				int val[8];
+				unsigned col[8][3];
+#pragma unroll
+				for (int i = 0; i < 8; i++) {
+					const long long q = gp + nb[i];
+					const uint8_t *c = fcolors + 3 * q;
+					if (i < 4 && (st[i] & kRadHole) && !(st[i] & kRadDone)) {
+						// raster-earlier and pending: its tentative value (another block's: past L1)
+						if (q >= own_lo) {
+							val[i] = (int)ld_vol_u16<true>(fdepth + q);
+							col[i][0] = ld_vol_u8<true>(c); col[i][1] = ld_vol_u8<true>(c + 1); col[i][2] = ld_vol_u8<true>(c + 2);
+						} else {
+							val[i] = (int)ld_vol_u16<false>(fdepth + q);
+							col[i][0] = ld_vol_u8<false>(c); col[i][1] = ld_vol_u8<false>(c + 1); col[i][2] = ld_vol_u8<false>(c + 2);
+						}
+					} else {
+						// final before this kernel started; raster-later: the warped value, which for an original hole is 0 whatever
+						// has been filled into it since
+						val[i] = (i >= 4 && (state[q] & kRadHole)) ? 0 : (int)fdepth[q];
+						col[i][0] = c[0]; col[i][1] = c[1]; col[i][2] = c[2];
+					}
+				}
+				int n = 0, sum = 0, sr = 0, sg = 0, sb = 0, prev = -1;
+#pragma unroll
+				for (int i = 0; i < 8; i++) {
+					if (val[i] > 0 && (prev == -1 || abs(val[i] - prev) < 30)) {       // depthprocessing.cpp:239
+						prev = val[i]; n++; sum += val[i];
+						sr += (int)col[i][0]; sg += (int)col[i][1]; sb += (int)col[i][2];
+					}
+				}
+				unsigned d = 0, cr = 0, cg = 0, cbl = 0;                               // n <= 4: stays as warped, depth 0 and colour 0 (:249)
+				if (n > 4) {
+					// x / n for 5 <= n <= 8 and x < 2^20 as a multiply, exact there (see k_rad_chains)
+					const unsigned rcp = n == 5 ? 858993460u : n == 6 ? 715827883u : n == 7 ? 613566757u : 536870912u;
+					d = __umulhi((unsigned)sum, rcp) & 0xffffu; cr = __umulhi((unsigned)sr, rcp) & 0xffu; cg = __umulhi((unsigned)sg, rcp) & 0xffu; cbl = __umulhi((unsigned)sb, rcp) & 0xffu;
+				}
+				const unsigned od = ld_vol_u16<true>(fdepth + gp);                     // what this hole holds now (this thread wrote it)
+				const unsigned ocr = ld_vol_u8<true>(fcolors + 3 * gp), ocg = ld_vol_u8<true>(fcolors + 3 * gp + 1), ocb = ld_vol_u8<true>(fcolors + 3 * gp + 2);
+				const bool chg = d != od || cr != ocr || cg != ocg || cbl != ocb;
+				if (chg) {
+					fdepth[gp] = (unsigned short)d;
+					fcolors[3 * gp] = (uint8_t)cr; fcolors[3 * gp + 1] = (uint8_t)cg; fcolors[3 * gp + 2] = (uint8_t)cbl;
+					changed = 1;
+				}
+				const unsigned char want = chg ? (unsigned char)(mine | bit_cur) : (unsigned char)(mine & ~bit_cur);
+				if (want != mine) state[gp] = want;
+			}
+			pass++;
+			const int any = __syncthreads_or(changed);
+			any_round |= any;
+			if (!any) break;
+		}
+		if (tid == 0) s_flag[round & 1] = any_round;
+		__threadfence();                                  // this round's values before the meeting (the next block reads them through L2)
+		cluster.sync();
+		int all = 0;
+#pragma unroll
+		for (int r = 0; r < kFixCluster; r++) all |= *cluster.map_shared_rank(&s_flag[round & 1], r);
+		if (!all) { converged = true; break; }
+	}
+	if (!converged && tid == 0) atomicOr(err, 64);
+	for (unsigned e = tid; e < n_pending; e += kFixThreads) state[s.pix_begin + lst[e]] = kRadHole | kRadDone;
+	cluster.sync();                                       // nobody leaves while its flags may still be read
+}
+
 __global__ void __launch_bounds__(256) k_rad_writeback(uint8_t *__restrict__ depth, uint8_t *__restrict__ colors, long long total_px,
 	const unsigned short *__restrict__ fdepth, const uint8_t *__restrict__ fcolors)
 {
@@ -533,6 +690,7 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 	for (int r = 0; r < kRadRounds; r++)
 		k_rad_round<<<grid, 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
 	static const int env_wavefront = getenv("LS3D_RADIAL_WAVEFRONT") ? atoi(getenv("LS3D_RADIAL_WAVEFRONT")) : 0;      // 1: the round-1 lockstep wavefront (A/B)
+	static const int env_chains = getenv("LS3D_RADIAL_CHAINS") ? atoi(getenv("LS3D_RADIAL_CHAINS")) : 0;               // 1: the chain kernel of round 1/2 instead of the fixpoint iteration (A/B)
 	if (env_wavefront) {
 		int max_h = 1, max_w = 1;
 		for (int i = 0; i < n_maps; i++) { max_h = std::max(max_h, c->h[i]); max_w = std::max(max_w, c->w[i]); }
@@ -544,6 +702,8 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 		if (wf_smem > (size_t)smem_budget) { set_error("radial correction: image width %d too large for the wavefront's pending map", max_w); return -1; }
 		if (!cuda_ok(cudaFuncSetAttribute(k_rad_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget), "wavefront shared memory")) return -1;
 		k_rad_wavefront<<<n_maps, rows, wf_smem, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), words_per_row, count + n_maps);
+	} else if (env_chains == 0) {
+		k_rad_fixpoint<<<n_maps * kFixCluster, kFixThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), count + n_maps);
 	} else {
 		// the winner map is free after the gather: it becomes the pixel -> list index map
 		k_rad_chains<<<n_maps, kChainThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps);
