@@ -14,10 +14,13 @@
 //                   values — or even if every unresolved one of them were filled it could not collect more than 4
 //                   neighbours, so it stays 0.  Values are published with "write, fence, flag", so any interleaving of
 //                   threads gives the sequential result.  One grid-wide round settles the vast majority of holes;
-//   k_rad_chains    one block per sensor finishes what hangs on other holes (fill cascades, the thin hole curves of the warp): the
-//                   pending pixels are listed in raster order and resolved chunk by chunk, each entry waiting only for the earlier
-//                   entries it really reads, whose results travel through shared memory (k_rad_wavefront, the lockstep w + 2h step
-//                   version it replaced, is kept behind LS3D_RADIAL_WAVEFRONT=1 for comparison);
+//   k_rad_fixpoint  what hangs on other holes (fill cascades, the thin hole curves of the warp) is settled by fixpoint iteration: a
+//                   cluster of eight blocks per sensor re-evaluates the pending holes from each other's tentative values (64-bit
+//                   words in shared / distributed shared memory) until a pass changes nothing — the recurrence is over a DAG, so
+//                   the fixpoint is unique and is the reference's result; averages of 5-8 values make it contract in 15-30 passes;
+//   k_rad_chains    the chain-by-chain kernel of rounds 1-2 (pending pixels listed in raster order and resolved chunk by chunk, each
+//                   entry waiting for the earlier entries it reads): still runs for a sensor too dense for k_rad_fixpoint's shared
+//                   memory, or with LS3D_RADIAL_CHAINS=1; k_rad_wavefront, the lockstep version before it, behind LS3D_RADIAL_WAVEFRONT=1;
 //   k_rad_writeback results back into the caller's buffers (the reference works in place).
 #include "ls3d_common.cuh"
 #include "ls3d_internal.h"
@@ -279,8 +282,9 @@ __global__ void __launch_bounds__(kRadChainThreads) k_rad_wavefront(const PreSen
 // independent of each other in the dependency graph still wait for each other in a sweep.  The list keeps only true dependencies.)
 constexpr int kChainThreads = 1024, kChainAdmit = 4;
 __global__ void __launch_bounds__(kChainThreads) k_rad_chains(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state,
-	int *__restrict__ list, int *__restrict__ pidx, int *err)
+	int *__restrict__ list, int *__restrict__ pidx, int *err, const int *__restrict__ only_if = nullptr)
 {
+	if (only_if && !only_if[blockIdx.x]) return;              // behind k_rad_fixpoint: only the sensors it left alone
 	__shared__ unsigned long long s_val[kChainThreads];          // entry i of the chunk: depth | r << 16 | g << 24 | b << 32 | final << 63
 	__shared__ unsigned s_w[32];
 	__shared__ unsigned s_total;
@@ -410,33 +414,115 @@ __global__ void __launch_bounds__(kChainThreads) k_rad_chains(const PreSensor *_
 // raster-order loop a recurrence.  But the recurrence is over a DAG (a hole only reads raster-earlier holes), so the assignment "every
 // pending hole holds exactly what the fill rule gives for the values its neighbours hold" has ONE solution — the reference's result —
 // and any iteration that ends in a full pass without a change has found it.  So: every pending hole is evaluated at once from the
-// tentative values in place (unfilled = 0 to start with), again and again until a pass changes nothing.  A fill is an average of five to
+// tentative values (unfilled = 0 to start with), again and again until a pass changes nothing.  A fill is an average of five to
 // eight values, so a wrong guess upstream reaches the next link divided by n >= 5 and dies out within a few links: the thin hole curves
-// of a warped Kinect frame (chains of ~h links, 0.43 ms in k_rad_chains at ~0.3 us per link) settle in a handful of passes.  Only a
-// chain whose fill DECISIONS hang on one another (each link has exactly four valid fixed neighbours) needs one pass per link, which is
-// what the chain kernel costs anyway.  After the first pass a hole is re-evaluated only if a raster-earlier neighbour changed in the
-// previous pass (two alternating "changed" bits in the state byte); it reads values another thread may be rewriting in the same pass —
-// harmless: whoever changed flags itself, and its readers run again next pass, after the barrier.
-// A CLUSTER of eight 1024-thread blocks per sensor (one block alone is instruction-bound on its SM: 8 holes per thread, 12 us per
-// pass): each block lists the pending holes of its eighth of the image and owns them, about one per thread; a pass ends in a cluster
-// barrier, and the blocks learn from each other's "changed" flags (distributed shared memory) whether another pass is needed.
-// Values other blocks may have rewritten are read with loads that bypass L1.
-constexpr int kFixThreads = 1024, kFixCluster = 8;
-enum : unsigned char { kRadChgA = 4, kRadChgB = 8 };
+// of a warped Kinect frame (chains of ~h links, 0.43 ms in k_rad_chains at ~0.3 us per link) settle in 15-30 passes.  Only a chain
+// whose fill DECISIONS hang on one another (each link has exactly four valid fixed neighbours) needs one pass per link, which is what
+// the chain kernel costs anyway.  After the first pass a hole is re-evaluated only if a raster-earlier neighbour changed in the
+// previous pass (two alternating "changed" bits beside the value); it may read a value another thread rewrites in the same pass —
+// harmless: whoever changes flags itself, and its readers run again next pass, after the barrier.
+//
+// A pass must be CHEAP (there are tens of them, one after the other): a cluster of eight 1024-thread blocks per sensor, each owning
+// the pending holes of an eighth of the image, at most two per thread.  A hole's tentative value is one 64-bit word in its owner's
+// shared memory (depth | r | g | b | changed bits: one atomic word, no torn colours); what never changes during the kernel — the
+// four raster-later neighbours, the raster-earlier ones that are not pending — is fetched once, the former parked in shared memory,
+// the latter in registers together with the references (block, index) to the pending ones.  So a pass is at most four shared-memory
+// reads (distributed shared memory for a neighbour in the block before), ~100 instructions and a __syncthreads.  Passes are LOCAL to
+// a block until it sees no change; only then does the cluster meet and the blocks learn from each other's flags whether anyone
+// changed since the last meeting.  The blocks count their passes independently, so a hole with a neighbour in another block cannot
+// use that neighbour's "changed" bits: it is simply re-evaluated in the first pass after every meeting.  The last meeting follows a
+// round in which no block changed anything: every such hole was evaluated in it from values that no longer moved.
+// A sensor with more than 2048 pending holes in one eighth (never seen on warped frames) is left to k_rad_chains (bail flag).
+constexpr int kFixThreads = 1024, kFixCluster = 8, kFixPerThread = 2, kFixCap = kFixThreads * kFixPerThread, kFixRowCap = 1024;
+constexpr unsigned long long kFixRef = 1ull << 63;
+
+__device__ __forceinline__ unsigned long long rad_record(const unsigned short *fdepth, const uint8_t *fcolors, long long q) {
+	const uint8_t *c = fcolors + 3 * q;
+	return (unsigned long long)fdepth[q] | ((unsigned long long)c[0] << 16) | ((unsigned long long)c[1] << 24) | ((unsigned long long)c[2] << 32);
+}
+
 __global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThreads) k_rad_fixpoint(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors,
-	unsigned char *state, int *__restrict__ list, int *err)
+	unsigned char *state, int *__restrict__ list, int *pidx, int *err, int *bail)
 {
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster();
+	extern __shared__ __align__(16) unsigned long long s_fix[];   // 80 KB, opt-in
+	unsigned long long *s_T = s_fix;                              // [kFixCap] tentative value of this block's pending hole e
+	unsigned long long (*s_L)[4] = reinterpret_cast<unsigned long long (*)[4]>(s_fix + kFixCap);      // [kFixCap][4] its four raster-later neighbours (immutable)
+	unsigned char (*s_dirty)[kFixCap] = reinterpret_cast<unsigned char (*)[kFixCap]>(s_fix + 5 * kFixCap);    // [2][kFixCap] "a neighbour you read changed", by pass parity
 	__shared__ unsigned s_w[32];
 	__shared__ unsigned s_total;
-	__shared__ int s_flag[2];
+	__shared__ int s_flag[2], s_over;
 	const unsigned rank = cluster.block_rank();
-	const PreSensor s = sd[blockIdx.x / kFixCluster];
+	const int sensor = blockIdx.x / kFixCluster;
+	const PreSensor s = sd[sensor];
 	const int px = s.w * s.h, w = s.w;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	// ---- bands of whole rows with about the same number of pending holes each (the forward warp leaves most of its holes near the
+	// image border: equal row counts gave the first and last block four times the holes of the middle ones) ----
+	__shared__ unsigned s_rows[kFixRowCap];                    // pending holes per row of this block's EQUAL share of the rows
+	__shared__ unsigned s_pre[kFixThreads + 1];
+	__shared__ int s_bound[kFixCluster + 1];
+	__shared__ unsigned s_carry;
+	const int h = s.h;
+	const int rows_per = (h + kFixCluster - 1) / kFixCluster;
+	if (rows_per > kFixRowCap) {                                // > 8192 rows: not an image this path is for
+		if (rank == 0 && tid == 0) bail[sensor] = 1;
+		return;                                                 // uniform over the cluster: nobody waits at a barrier
+	}
+	for (int j = warp; j < rows_per; j += kFixThreads / 32) {
+		const int y = (int)rank * rows_per + j;
+		unsigned c = 0;
+		if (y < h)
+			for (int x = lane; x < w; x += 32) c += (state[s.pix_begin + (long long)y * w + x] & kRadDone) ? 0u : 1u;
+		c = warp_sum(c);
+		if (lane == 0) s_rows[j] = c;
+	}
+	if (tid <= kFixCluster) s_bound[tid] = tid == 0 ? 0 : h;
+	if (tid == 0) s_carry = 0;
+	cluster.sync();
+	{
+		// exclusive prefix over all h rows (every block computes the same), 1024 rows per turn
+		unsigned total = 0;
+		for (int y = tid; y < h; y += kFixThreads) total += *cluster.map_shared_rank(&s_rows[y % rows_per], (unsigned)(y / rows_per));
+		total = warp_sum(total);
+		if (lane == 0) atomicAdd(&s_carry, total);
+		__syncthreads();
+		total = s_carry;
+		__syncthreads();
+		unsigned carry = 0;
+		for (int base = 0; base < h; base += kFixThreads) {
+			const int y = base + tid;
+			const unsigned c = y < h ? *cluster.map_shared_rank(&s_rows[y % rows_per], (unsigned)(y / rows_per)) : 0u;
+			const unsigned incl = warp_incl_scan(c, lane);
+			if (lane == 31) s_w[warp] = incl;
+			__syncthreads();
+			if (warp == 0) {
+				const unsigned v = s_w[lane], sc = warp_incl_scan(v, lane);
+				s_w[lane] = sc - v;
+				if (lane == 31) s_total = sc;
+			}
+			__syncthreads();
+			const unsigned excl = carry + s_w[warp] + incl - c;
+			s_pre[tid] = excl;                                   // s_pre[kFixThreads]: the previous turn's last row (not used for y = 0)
+			__syncthreads();
+			if (y < h) {
+				const unsigned before = tid ? s_pre[tid - 1] : s_pre[kFixThreads];
+#pragma unroll
+				for (int r = 1; r < kFixCluster; r++) {
+					const unsigned target = (unsigned)((unsigned long long)total * r / kFixCluster);
+					if (excl >= target && (y == 0 || before < target)) s_bound[r] = y;       // first row whose prefix reaches the target
+				}
+			}
+			carry += s_total;
+			__syncthreads();
+			if (tid == kFixThreads - 1) s_pre[kFixThreads] = excl;
+		}
+	}
+	__syncthreads();
+	auto range_lo = [&](unsigned r) { return s_bound[r] * w; };
 	// this block's pixels [r0, r1) and its slice of the list buffer
-	const int r0 = (int)((long long)px * rank / kFixCluster), r1 = (int)((long long)px * (rank + 1) / kFixCluster);
+	const int r0 = range_lo(rank), r1 = range_lo(rank + 1);
 	int *lst = list + s.pix_begin + r0;
 	unsigned n_pending = 0;
 	for (int base = r0; base < r1; base += kFixThreads * 16) {
@@ -458,89 +544,115 @@ __global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThread
 		while (m) {
 			const int j = __ffs(m) - 1;
 			m &= m - 1;
-			lst[o++] = p0 + j;
+			lst[o] = p0 + j;
+			pidx[s.pix_begin + p0 + j] = (int)o;
+			o++;
 		}
 		n_pending += s_total;
 		__syncthreads();
 	}
+	if (tid == 0) s_over = n_pending > (unsigned)kFixCap ? 1 : 0;
+	__threadfence();                                          // the index map before the meeting (other blocks read it through L2)
+	cluster.sync();
+	{
+		int over = 0;
+#pragma unroll
+		for (int r = 0; r < kFixCluster; r++) over |= *cluster.map_shared_rank(&s_over, r);
+		if (over) {
+			if (rank == 0 && tid == 0) bail[sensor] = 1;
+			cluster.sync();                                   // nobody leaves while its flag may still be read
+			return;
+		}
+	}
 	const int nb[8] = {-w - 1, -w, -w + 1, -1, 1, w - 1, w, w + 1};      // depthprocessing.cpp:226
-	// Passes are LOCAL to a block (a __syncthreads each, values and flags of its own holes read through its own L1) until the block
-	// sees no change; only then does the cluster meet, and the blocks learn from each other's flags whether anyone changed since the
-	// last meeting.  A hole whose raster-earlier neighbours belong to the block before (pixel < r0 + w + 1) cannot use that block's
-	// "changed" bits — the blocks count their passes independently — so it is simply re-evaluated in the first pass after every
-	// meeting, reading those neighbours past L1.  The last meeting follows a round in which no block changed anything: every such
-	// hole was evaluated in it from values that no longer moved.
-	// A hole only reads holes at most a row back, so a chain cannot be longer than the image has pixels: px + 1 rounds always suffice.
-	const long long own_lo = s.pix_begin + r0;
+	// ---- per hole: what cannot change, and where the pending neighbours live ----
+	unsigned long long E[kFixPerThread][4];                   // raster-earlier neighbours: a fixed record, or kFixRef | owner << 16 | index
+	unsigned short succ[kFixPerThread][4];                    // the raster-later neighbours that are pending holes of THIS block (0xffff: none): who to wake when this hole changes
+	bool remote[kFixPerThread];
+#pragma unroll
+	for (int j = 0; j < kFixPerThread; j++) {
+		const unsigned e = tid + j * kFixThreads;
+		remote[j] = false;
+#pragma unroll
+		for (int i = 0; i < 4; i++) { E[j][i] = 0; succ[j][i] = 0xffffu; }
+		if (e < kFixCap) { s_dirty[0][e] = 0; s_dirty[1][e] = 0; }
+		if (e < n_pending) {
+			const int p = lst[e];
+			const long long gp = s.pix_begin + p;
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const long long q = gp + nb[i];
+				const unsigned st = state[q];
+				if ((st & kRadHole) && !(st & kRadDone)) {
+					unsigned owner = rank;
+					while (p + nb[i] < range_lo(owner)) owner--;
+					E[j][i] = kFixRef | ((unsigned long long)owner << 16) | (unsigned long long)(unsigned)ld_volatile_u32(reinterpret_cast<const unsigned *>(pidx + q));
+					remote[j] = remote[j] || owner != rank;
+				} else {
+					E[j][i] = rad_record(fdepth, fcolors, q);         // final before this kernel started
+				}
+			}
+#pragma unroll
+			for (int i = 4; i < 8; i++) {
+				const long long q = gp + nb[i];
+				// raster-later: the warped value, which for an original hole is 0 whatever has been filled into it since
+				const unsigned st = state[q];
+				s_L[e][i - 4] = (st & kRadHole) ? 0ull : rad_record(fdepth, fcolors, q);
+				if ((st & kRadHole) && !(st & kRadDone) && p + nb[i] < r1) succ[j][i - 4] = (unsigned short)ld_volatile_u32(reinterpret_cast<const unsigned *>(pidx + q));
+			}
+			s_T[e] = 0ull;                                        // unfilled: depth 0, colour 0 (:249)
+		}
+	}
+	cluster.sync();                                           // every block's tentative values exist before anyone reads them
 	unsigned pass = 0;
 	bool converged = false;
 	for (int round = 0; round <= px + 1; round++) {
 		int any_round = 0;
 		for (bool first = true;; first = false) {
-			const unsigned char bit_cur = (pass & 1u) ? kRadChgB : kRadChgA, bit_prev = (pass & 1u) ? kRadChgA : kRadChgB;
+			const unsigned cur = pass & 1u;
 			int changed = 0;
-			for (unsigned e = tid; e < n_pending; e += kFixThreads) {
-				const int p = lst[e];
-				const long long gp = s.pix_begin + p;
-				const bool border = p < r0 + w + 1;
-				unsigned st[4];
 #pragma unroll
-				for (int i = 0; i < 4; i++) st[i] = (gp + nb[i] >= own_lo) ? ld_vol_u8<true>(state + gp + nb[i]) : ld_vol_u8<false>(state + gp + nb[i]);
-				const unsigned char mine = (unsigned char)ld_vol_u8<true>(state + gp);        // only this thread writes it
-				unsigned moved = 0;
+			for (int j = 0; j < kFixPerThread; j++) {
+				const unsigned e = tid + j * kFixThreads;
+				if (e >= n_pending) continue;
+				// evaluated when a hole it reads (in this block) changed in the previous pass; in the very first pass; and, for a hole
+				// with a neighbour in the block before, in the first pass after every meeting
+				const bool woken = ((volatile unsigned char *)s_dirty[cur])[e] != 0;
+				if (!(woken || pass == 0 || (first && remote[j]))) continue;
+				if (woken) s_dirty[cur][e] = 0;
+				unsigned long long rec[4];
 #pragma unroll
-				for (int i = 0; i < 4; i++) moved |= (gp + nb[i] >= own_lo) ? (st[i] & bit_prev) : 0u;
-				if (!(pass == 0 || moved || (first && border))) {
-					// nothing this hole reads has moved since it was last evaluated
-					if (mine & bit_cur) state[gp] = mine & (unsigned char)~bit_cur;
-					continue;
-				}
-				int val[8];
-				unsigned col[8][3];
-#pragma unroll
-				for (int i = 0; i < 8; i++) {
-					const long long q = gp + nb[i];
-					const uint8_t *c = fcolors + 3 * q;
-					if (i < 4 && (st[i] & kRadHole) && !(st[i] & kRadDone)) {
-						// raster-earlier and pending: its tentative value (another block's: past L1)
-						if (q >= own_lo) {
-							val[i] = (int)ld_vol_u16<true>(fdepth + q);
-							col[i][0] = ld_vol_u8<true>(c); col[i][1] = ld_vol_u8<true>(c + 1); col[i][2] = ld_vol_u8<true>(c + 2);
-						} else {
-							val[i] = (int)ld_vol_u16<false>(fdepth + q);
-							col[i][0] = ld_vol_u8<false>(c); col[i][1] = ld_vol_u8<false>(c + 1); col[i][2] = ld_vol_u8<false>(c + 2);
-						}
-					} else {
-						// final before this kernel started; raster-later: the warped value, which for an original hole is 0 whatever
-						// has been filled into it since
-						val[i] = (i >= 4 && (state[q] & kRadHole)) ? 0 : (int)fdepth[q];
-						col[i][0] = c[0]; col[i][1] = c[1]; col[i][2] = c[2];
+				for (int i = 0; i < 4; i++) {
+					rec[i] = E[j][i];
+					if (rec[i] & kFixRef) {
+						const unsigned owner = (unsigned)(rec[i] >> 16) & 0xffu, idx = (unsigned)rec[i] & 0xffffu;
+						rec[i] = owner == rank ? ((volatile unsigned long long *)s_T)[idx] : *(volatile unsigned long long *)cluster.map_shared_rank(&s_T[idx], owner);
 					}
 				}
 				int n = 0, sum = 0, sr = 0, sg = 0, sb = 0, prev = -1;
 #pragma unroll
 				for (int i = 0; i < 8; i++) {
-					if (val[i] > 0 && (prev == -1 || abs(val[i] - prev) < 30)) {       // depthprocessing.cpp:239
-						prev = val[i]; n++; sum += val[i];
-						sr += (int)col[i][0]; sg += (int)col[i][1]; sb += (int)col[i][2];
+					const unsigned long long r = i < 4 ? rec[i] : s_L[e][i - 4];
+					const int v = (int)(r & 0xffffull);
+					if (v > 0 && (prev == -1 || abs(v - prev) < 30)) {                 // depthprocessing.cpp:239
+						prev = v; n++; sum += v;
+						sr += (int)((r >> 16) & 0xffull); sg += (int)((r >> 24) & 0xffull); sb += (int)((r >> 32) & 0xffull);
 					}
 				}
-				unsigned d = 0, cr = 0, cg = 0, cbl = 0;                               // n <= 4: stays as warped, depth 0 and colour 0 (:249)
+				unsigned long long out = 0ull;                                         // n <= 4: stays as warped, depth 0 and colour 0 (:249)
 				if (n > 4) {
 					// x / n for 5 <= n <= 8 and x < 2^20 as a multiply, exact there (see k_rad_chains)
 					const unsigned rcp = n == 5 ? 858993460u : n == 6 ? 715827883u : n == 7 ? 613566757u : 536870912u;
-					d = __umulhi((unsigned)sum, rcp) & 0xffffu; cr = __umulhi((unsigned)sr, rcp) & 0xffu; cg = __umulhi((unsigned)sg, rcp) & 0xffu; cbl = __umulhi((unsigned)sb, rcp) & 0xffu;
+					out = (unsigned long long)(__umulhi((unsigned)sum, rcp) & 0xffffu) | ((unsigned long long)(__umulhi((unsigned)sr, rcp) & 0xffu) << 16) |
+						((unsigned long long)(__umulhi((unsigned)sg, rcp) & 0xffu) << 24) | ((unsigned long long)(__umulhi((unsigned)sb, rcp) & 0xffu) << 32);
 				}
-				const unsigned od = ld_vol_u16<true>(fdepth + gp);                     // what this hole holds now (this thread wrote it)
-				const unsigned ocr = ld_vol_u8<true>(fcolors + 3 * gp), ocg = ld_vol_u8<true>(fcolors + 3 * gp + 1), ocb = ld_vol_u8<true>(fcolors + 3 * gp + 2);
-				const bool chg = d != od || cr != ocr || cg != ocg || cbl != ocb;
-				if (chg) {
-					fdepth[gp] = (unsigned short)d;
-					fcolors[3 * gp] = (uint8_t)cr; fcolors[3 * gp + 1] = (uint8_t)cg; fcolors[3 * gp + 2] = (uint8_t)cbl;
+				if (out != ((volatile unsigned long long *)s_T)[e]) {
+					((volatile unsigned long long *)s_T)[e] = out;
 					changed = 1;
+#pragma unroll
+					for (int i = 0; i < 4; i++)
+						if (succ[j][i] != 0xffffu) s_dirty[cur ^ 1u][succ[j][i]] = 1;       // its readers run in the next pass
 				}
-				const unsigned char want = chg ? (unsigned char)(mine | bit_cur) : (unsigned char)(mine & ~bit_cur);
-				if (want != mine) state[gp] = want;
 			}
 			pass++;
 			const int any = __syncthreads_or(changed);
@@ -548,7 +660,6 @@ __global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThread
 			if (!any) break;
 		}
 		if (tid == 0) s_flag[round & 1] = any_round;
-		__threadfence();                                  // this round's values before the meeting (the next block reads them through L2)
 		cluster.sync();
 		int all = 0;
 #pragma unroll
@@ -556,8 +667,21 @@ __global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThread
 		if (!all) { converged = true; break; }
 	}
 	if (!converged && tid == 0) atomicOr(err, 64);
-	for (unsigned e = tid; e < n_pending; e += kFixThreads) state[s.pix_begin + lst[e]] = kRadHole | kRadDone;
-	cluster.sync();                                       // nobody leaves while its flags may still be read
+	// ---- the settled values into the image ----
+#pragma unroll
+	for (int j = 0; j < kFixPerThread; j++) {
+		const unsigned e = tid + j * kFixThreads;
+		if (e < n_pending) {
+			const long long gp = s.pix_begin + lst[e];
+			const unsigned long long v = s_T[e];
+			if (v & 0xffffull) {
+				fdepth[gp] = (unsigned short)(v & 0xffffull);
+				fcolors[3 * gp] = (uint8_t)(v >> 16); fcolors[3 * gp + 1] = (uint8_t)(v >> 24); fcolors[3 * gp + 2] = (uint8_t)(v >> 32);
+			}
+			state[gp] = kRadHole | kRadDone;
+		}
+	}
+	cluster.sync();                                           // nobody leaves while its shared memory may still be read
 }
 
 __global__ void __launch_bounds__(256) k_rad_writeback(uint8_t *__restrict__ depth, uint8_t *__restrict__ colors, long long total_px,
@@ -650,7 +774,7 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 	const size_t n = (size_t)acc;
 	bool ok = c->sd.reserve(sizeof(PreSensor) * n_maps, "alloc descriptors") && c->winner.reserve(4 * n, "alloc warp winners") && c->fdepth.reserve(2 * n, "alloc warped depth") &&
 		c->fcolors.reserve(3 * n, "alloc warped colours") && c->state.reserve(n, "alloc hole states") && c->items.reserve(4 * n, "alloc pending lists") &&
-		c->count.reserve(4 * (size_t)n_maps + 4, "alloc worklist counts");
+		c->count.reserve(8 * (size_t)n_maps + 8, "alloc worklist counts");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin_sd, sizeof(PreSensor) * n_maps, cudaHostAllocDefault), "alloc pinned descriptors");
 	ok = ok && cuda_ok(cudaHostAlloc((void **)&c->pin_err, 64, cudaHostAllocDefault), "alloc pinned status");
 	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming), "create staging event") &&
@@ -680,7 +804,7 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 	bool ok = cuda_ok(cudaMemcpyAsync(c->sd.p, c->pin_sd, sizeof(PreSensor) * n_maps, cudaMemcpyHostToDevice, st), "upload descriptors") &&
 		cuda_ok(cudaEventRecord(c->ev_staged, st), "record descriptor upload") &&
 		cuda_ok(cudaMemsetAsync(c->winner.p, 0, 4 * (size_t)c->total_px, st), "clear winners") &&
-		cuda_ok(cudaMemsetAsync(c->count.p, 0, 4 * (size_t)n_maps + 4, st), "clear worklist counts");
+		cuda_ok(cudaMemsetAsync(c->count.p, 0, 8 * (size_t)n_maps + 8, st), "clear worklist counts");
 	if (!ok) return -1;
 	const dim3 grid((unsigned)std::max(1, std::min((max_px + 255) / 256, c->sm_count * 8 / std::max(1, std::min(n_maps, 8)) + 1)), (unsigned)n_maps);
 	const PreSensor *sd = c->sd.as<PreSensor>();
@@ -703,7 +827,17 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 		if (!cuda_ok(cudaFuncSetAttribute(k_rad_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget), "wavefront shared memory")) return -1;
 		k_rad_wavefront<<<n_maps, rows, wf_smem, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), words_per_row, count + n_maps);
 	} else if (env_chains == 0) {
-		k_rad_fixpoint<<<n_maps * kFixCluster, kFixThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), count + n_maps);
+		// the winner map is free after the gather: it becomes the pixel -> list index map; count[n_maps + 1 + i] = sensor i was too dense
+		constexpr size_t fix_smem = sizeof(unsigned long long) * kFixCap * 5 + 2 * kFixCap;
+		static bool fix_attr = false;
+		if (!fix_attr) {
+			if (!cuda_ok(cudaFuncSetAttribute(k_rad_fixpoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fix_smem), "hole fill shared memory")) return -1;
+			fix_attr = true;
+		}
+		k_rad_fixpoint<<<n_maps * kFixCluster, kFixThreads, fix_smem, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(),
+			c->winner.as<int>(), count + n_maps, count + n_maps + 1);
+		k_rad_chains<<<n_maps, kChainThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps,
+			count + n_maps + 1);
 	} else {
 		// the winner map is free after the gather: it becomes the pixel -> list index map
 		k_rad_chains<<<n_maps, kChainThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps);
