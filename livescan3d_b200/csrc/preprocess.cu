@@ -194,8 +194,53 @@ __global__ void __launch_bounds__(256) k_rad_round(const PreSensor *__restrict__
 	const PreSensor s = sd[blockIdx.y];
 	const int px = s.w * s.h;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < px; p += gridDim.x * blockDim.x) {
-		if (ld_vol_u8<false>(state + s.pix_begin + p) & kRadDone) continue;
+		if (state[s.pix_begin + p] & kRadDone) continue;                   // its own flag: nobody else writes it (a plain, coalesced load for the 96 % that are no holes)
 		rad_try_resolve<false>(s, p, fdepth, fcolors, state);
+	}
+}
+
+// The same round under a SNAPSHOT rule: a hole is settled here only from what was final before the kernel started — none of its four
+// raster-earlier neighbours is a hole (or it cannot reach five neighbours whatever they turn out to be).  Nothing it reads can be
+// written concurrently, so there are no fences and no volatile loads (k_rad_round's write-fence-flag protocol lets it also settle
+// holes whose earlier neighbours happen to be finished by another thread in time: 37 us against this kernel's few; the holes it
+// leaves — the thin curves of the warp, every link of which has an earlier hole for a neighbour — are what k_rad_fixpoint is for).
+__global__ void __launch_bounds__(256) k_rad_first(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state)
+{
+	const PreSensor s = sd[blockIdx.y];
+	const int px = s.w * s.h, w = s.w;
+	const int nb[8] = {-w - 1, -w, -w + 1, -1, 1, w - 1, w, w + 1};      // depthprocessing.cpp:226
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < px; p += gridDim.x * blockDim.x) {
+		const long long gp = s.pix_begin + p;
+		if (state[gp] & kRadDone) continue;
+		int val[8];
+		bool earlier_hole = false;
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			const bool hole = (state[gp + nb[i]] & kRadHole) != 0;          // immutable
+			if (i < 4) { earlier_hole = earlier_hole || hole; val[i] = hole ? -1 : (int)fdepth[gp + nb[i]]; }
+			else val[i] = hole ? 0 : (int)fdepth[gp + nb[i]];                // the reference has not reached it yet: still 0
+		}
+		if (earlier_hole) {
+			int possible = 0;
+#pragma unroll
+			for (int i = 0; i < 8; i++) possible += val[i] != 0 ? 1 : 0;    // unknown (-1) counts as "might be filled"
+			if (possible <= 4) state[gp] = kRadHole | kRadDone;             // cannot reach n > 4: stays 0 (depthprocessing.cpp:249)
+			continue;
+		}
+		int n = 0, sum = 0, sr = 0, sg = 0, sb = 0, prev = -1;
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			if (val[i] > 0 && (prev == -1 || abs(val[i] - prev) < 30)) {       // :239
+				const uint8_t *c = fcolors + 3 * (gp + nb[i]);
+				prev = val[i]; n++; sum += val[i];
+				sr += (int)c[0]; sg += (int)c[1]; sb += (int)c[2];
+			}
+		}
+		if (n > 4) {
+			fcolors[3 * gp] = (uint8_t)(sr / n); fcolors[3 * gp + 1] = (uint8_t)(sg / n); fcolors[3 * gp + 2] = (uint8_t)(sb / n);
+			fdepth[gp] = (unsigned short)(sum / n);
+		}
+		state[gp] = kRadHole | kRadDone;
 	}
 }
 
@@ -473,8 +518,15 @@ __global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThread
 	for (int j = warp; j < rows_per; j += kFixThreads / 32) {
 		const int y = (int)rank * rows_per + j;
 		unsigned c = 0;
-		if (y < h)
-			for (int x = lane; x < w; x += 32) c += (state[s.pix_begin + (long long)y * w + x] & kRadDone) ? 0u : 1u;
+		if (y < h) {
+			const unsigned char *rp = state + s.pix_begin + (long long)y * w;
+			if ((w & 3) == 0 && (((uintptr_t)rp) & 3) == 0) {
+				// four flags per load: a pending pixel has bit 0 (kRadDone) clear
+				for (int x = 4 * lane; x < w; x += 128) c += 4u - (unsigned)__popc(*reinterpret_cast<const unsigned *>(rp + x) & 0x01010101u);
+			} else {
+				for (int x = lane; x < w; x += 32) c += (rp[x] & kRadDone) ? 0u : 1u;
+			}
+		}
 		c = warp_sum(c);
 		if (lane == 0) s_rows[j] = c;
 	}
@@ -528,9 +580,19 @@ __global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThread
 	for (int base = r0; base < r1; base += kFixThreads * 16) {
 		const int p0 = base + tid * 16;
 		unsigned m = 0;
+		const unsigned char *sp = state + s.pix_begin + p0;
+		if (p0 + 16 <= r1 && (((uintptr_t)sp) & 15) == 0) {
+			// 16 flags in one load; bit 0 of every byte is kRadDone
+			const uint4 f = *reinterpret_cast<const uint4 *>(sp);
+			const unsigned wd[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-		for (int j = 0; j < 16; j++)
-			if (p0 + j < r1 && !(state[s.pix_begin + p0 + j] & kRadDone)) m |= 1u << j;
+			for (int j = 0; j < 16; j++)
+				if (!((wd[j >> 2] >> (8 * (j & 3))) & kRadDone)) m |= 1u << j;
+		} else {
+#pragma unroll
+			for (int j = 0; j < 16; j++)
+				if (p0 + j < r1 && !(sp[j] & kRadDone)) m |= 1u << j;
+		}
 		const unsigned cnt = __popc(m), incl = warp_incl_scan(cnt, lane);
 		if (lane == 31) s_w[warp] = incl;
 		__syncthreads();
@@ -811,8 +873,11 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 	int *count = c->count.as<int>();
 	k_rad_scatter<<<grid, 256, 0, st>>>(d_depth, sd, c->winner.as<int>());
 	k_rad_gather<<<grid, 256, 0, st>>>(d_depth, d_colors, sd, c->winner.as<int>(), c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
-	for (int r = 0; r < kRadRounds; r++)
-		k_rad_round<<<grid, 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+	static const int env_snapshot = getenv("LS3D_RADIAL_SNAPSHOT") ? atoi(getenv("LS3D_RADIAL_SNAPSHOT")) : 1;         // 0: the fenced round of rounds 1-2 (A/B)
+	for (int r = 0; r < kRadRounds; r++) {
+		if (env_snapshot && r == 0) k_rad_first<<<dim3((unsigned)((max_px + 255) / 256), (unsigned)n_maps), 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+		else k_rad_round<<<grid, 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+	}
 	static const int env_wavefront = getenv("LS3D_RADIAL_WAVEFRONT") ? atoi(getenv("LS3D_RADIAL_WAVEFRONT")) : 0;      // 1: the round-1 lockstep wavefront (A/B)
 	static const int env_chains = getenv("LS3D_RADIAL_CHAINS") ? atoi(getenv("LS3D_RADIAL_CHAINS")) : 0;               // 1: the chain kernel of round 1/2 instead of the fixpoint iteration (A/B)
 	if (env_wavefront) {
