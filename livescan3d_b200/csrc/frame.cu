@@ -1200,7 +1200,7 @@ using namespace ls3d;
 enum { kTsMap = 0, kTsHashClear, kTsInsert, kTsRanges, kTsCount, kTsCompact, kTsOrganized, kTsWhole, kTsTriangles, kTsN };
 enum { kModeAuto = 0, kModeVoxelHash = 1, kModeOrganized = 2 };
 
-constexpr int kMaxChunks = 16, kEvN = 6 * kMaxChunks + 8;
+constexpr int kMaxChunks = 16, kEvN = 5 * kMaxChunks + 5;
 struct HostGraphKey { const void *depth, *colors, *out; int first, n_run, chunks, pull; unsigned long long params_version; };
 struct Ls3dFrame {
 	int device = 0;
@@ -1244,7 +1244,7 @@ struct Ls3dFrame {
 	cudaEvent_t colors_ready = nullptr;
 	cudaEvent_t ev_colors = nullptr, ev_count = nullptr;
 	cudaEvent_t ev_up[kEvN] = {};      // host path: per chunk depth-landed / colours-landed / counted / merged, then fork + 3 joins
-	cudaStream_t st_merge = nullptr, st_pull = nullptr, st_up2 = nullptr;
+	cudaStream_t st_merge = nullptr;
 	cudaEvent_t ev_tr[4 * kMaxChunks + 1] = {};    // LS3D_E2E_TRACE only: timed events (external records, so they also work inside the graph)
 	cudaGraphExec_t hg_exec = nullptr;  // host path: the captured per-frame schedule, valid for hg_key
 	HostGraphKey hg_key = {};
@@ -1299,8 +1299,6 @@ static void frame_free(Ls3dFrame *f) {
 	if (f->st_colors) cudaStreamDestroy(f->st_colors);
 	if (f->st_out) cudaStreamDestroy(f->st_out);
 	if (f->st_merge) cudaStreamDestroy(f->st_merge);
-	if (f->st_pull) cudaStreamDestroy(f->st_pull);
-	if (f->st_up2) cudaStreamDestroy(f->st_up2);
 	if (f->stage_depth) cudaFreeHost(f->stage_depth);
 	if (f->stage_colors) cudaFreeHost(f->stage_colors);
 	if (f->hg_exec_b) cudaGraphExecDestroy(f->hg_exec_b);
@@ -1565,50 +1563,6 @@ __global__ void __launch_bounds__(256) k_copy_out(const uint4 *__restrict__ src,
 #pragma unroll
 	for (int i = 0; i < 8; i++) { begin += s_part[0][i]; n += s_part[1][i]; }
 	for (unsigned i = blockIdx.x * 256 + tid; i < n; i += gridDim.x * 256) dst[begin + i] = src[begin + i];
-}
-
-// Host path: the colour bytes under the survivors of tiles [tile_lo, tile_hi) come out of the caller's page-locked buffer (mapped) into
-// the device colour image, as whole 128-byte lines requested by 16-byte lanes — the same lines k_map_cull_compact then stages.  Measured
-// on the bench frame's link (scripts/pcie_probe.cu): line requests move 38-47 GB/s where 32-byte sector requests move 20 GB/s, and the
-// rate does not depend on how many blocks ask; but a kernel that only touches device memory runs 2-3x slower while every SM has
-// host reads in flight.  Hence a small grid of its own instead of loads inside the merge kernel.
-__global__ void __launch_bounds__(256) k_pull_colors(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const uint8_t *__restrict__ keep_px,
-	const SensorDesc *__restrict__ sd, const unsigned short *__restrict__ tile_sensor, int tile0, int tile_lo, int tile_hi)
-{
-	const int lane = threadIdx.x & 31;
-	const int warps = gridDim.x * 8;
-	const int n_groups = (tile_hi - tile_lo) * (kTile / 256);          // a warp takes 256 pixels (768 colour bytes) at a time
-	for (int g = blockIdx.x * 8 + (threadIdx.x >> 5); g < n_groups; g += warps) {
-		const int tile = tile_lo + g / (kTile / 256);
-		const int s = tile_sensor[tile + tile0];
-		const int px = sd[s].px;
-		const int g0 = (tile + tile0 - sd[s].tile_begin) * kTile + (g % (kTile / 256)) * 256;      // the group's first pixel
-		const int p0 = g0 + lane * 8, rem = px - p0;
-		unsigned any = 0;
-		const uint8_t *kp = keep_px + sd[s].pix_begin + p0;
-		if (rem >= 8 && (((uintptr_t)kp) & 7) == 0) {
-			const uint2 f = __ldg(reinterpret_cast<const uint2 *>(kp));
-			any = f.x | f.y;
-		} else {
-			for (int j = 0; j < 8 && j < rem; j++) any |= __ldg(kp + j);
-		}
-		const unsigned act = __ballot_sync(kFull, any != 0);
-		if (!act) continue;
-		const long long off = sd[s].color_off + 3ll * g0;
-		if (px - g0 >= 256 && ((((uintptr_t)(src + off)) | ((uintptr_t)(dst + off))) & 15) == 0) {
-			const uint4 *a = reinterpret_cast<const uint4 *>(src + off);
-			uint4 *b = reinterpret_cast<uint4 *>(dst + off);
-			const bool w0 = (act & color_line_mask(lane >> 3)) != 0, w1 = lane < 16 && (act & color_line_mask(4 + (lane >> 3))) != 0;
-			uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-			if (w0) v0 = __ldg(a + lane);
-			if (w1) v1 = __ldg(a + 32 + lane);
-			if (w0) b[lane] = v0;
-			if (w1) b[32 + lane] = v1;
-		} else if (any) {
-			const long long o = off + 24ll * lane;
-			for (int j = 0; j < 24 && j < 3 * rem; j++) dst[o + j] = __ldg(src + o + j);
-		}
-	}
 }
 
 // Host mesh path (unfiltered frame + triangles, sensors processed in chunks): after a chunk's K1 + triangle kernels, record where its
@@ -2049,7 +2003,7 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 			!cuda_ok(cudaEventCreateWithFlags(&f->ev_colors, cudaEventDisableTiming), "create event") ||
 			!cuda_ok(cudaEventCreateWithFlags(&f->ev_count, cudaEventDisableTiming), "create event")) return -1;
 	}
-	struct ColorsGuard { Ls3dFrame *f; ~ColorsGuard() { f->colors_ready = nullptr; if (f->st_colors) cudaStreamSynchronize(f->st_colors); if (f->st_out) cudaStreamSynchronize(f->st_out); if (f->st_merge) cudaStreamSynchronize(f->st_merge); if (f->st_pull) cudaStreamSynchronize(f->st_pull); if (f->st_up2) cudaStreamSynchronize(f->st_up2); } } guard{f};
+	struct ColorsGuard { Ls3dFrame *f; ~ColorsGuard() { f->colors_ready = nullptr; if (f->st_colors) cudaStreamSynchronize(f->st_colors); if (f->st_out) cudaStreamSynchronize(f->st_out); if (f->st_merge) cudaStreamSynchronize(f->st_merge); } } guard{f};
 	f->filter_mode = g_default_filter_mode;
 	f->want_triangles = with_triangles && !(filter_k > 0 && filter_maxDist > 0);
 	if (frame_set_params(f, n_maps, intr_params, wtransform_params, bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5], filter_k, filter_maxDist, st) < 0) return -1;
@@ -2065,10 +2019,6 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 	static const int env_cblocks = getenv("LS3D_E2E_COPY_BLOCKS") ? atoi(getenv("LS3D_E2E_COPY_BLOCKS")) : 16;
 	static const int env_trace = getenv("LS3D_E2E_TRACE") ? atoi(getenv("LS3D_E2E_TRACE")) : 0;    // 1: timed events in the schedule, timeline printed to stderr
 	static const int env_direct = getenv("LS3D_E2E_DIRECT") ? atoi(getenv("LS3D_E2E_DIRECT")) : 1;  // 1: the merge kernel stores its tiles into the host block itself
-	static const int env_pullk = getenv("LS3D_E2E_PULL_KERNEL") ? atoi(getenv("LS3D_E2E_PULL_KERNEL")) : 0;  // 1: a small kernel fetches the survivors' colour lines; 0: the merge kernel loads them from the host itself
-	static const int env_pullb = getenv("LS3D_E2E_PULL_BLOCKS") ? atoi(getenv("LS3D_E2E_PULL_BLOCKS")) : 64;
-	static const int env_up2 = getenv("LS3D_E2E_UP2") ? atoi(getenv("LS3D_E2E_UP2")) : 0;           // 1: every depth chunk is uploaded as two halves on two streams (two copy engines)
-	static const int env_taper = getenv("LS3D_E2E_TAPER") ? atoi(getenv("LS3D_E2E_TAPER")) : 0;     // 1: the last chunk gives a sensor to the first
 	if (env_mode != 0 && frame_will_use_organized(f)) {
 		// Pipelined over chunks of sensors on four streams (upload, count, merge, read-back): a chunk's neighbour count starts when
 		// its depth has landed; its map/merge kernel places the survivors at the base the per-tile survivor counts give it; a copy
@@ -2110,23 +2060,18 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 			const unsigned char *src_depth = staged ? f->stage_depth : depth_maps, *src_colors = staged ? f->stage_colors : depth_colors;
 			const bool pull = env_mode == 2 && locked(src_colors, &col_dev);
 			const bool graph_ok = env_graph != 0 && locked(src_depth, nullptr) && (pull || locked(src_colors, nullptr));
-			const bool pull_kernel = pull && env_pullk != 0;
-			const uint8_t *col_src = (pull && !pull_kernel) ? (const uint8_t *)col_dev : dc;
+			const uint8_t *col_src = pull ? (const uint8_t *)col_dev : dc;
 			for (int i = 0; i < kEvN && ok; i++)
 				if (!f->ev_up[i]) ok = cuda_ok(cudaEventCreateWithFlags(&f->ev_up[i], cudaEventDisableTiming), "create event");
 			for (int i = 0; i < 4 * kMaxChunks + 1 && ok && env_trace; i++)
 				if (!f->ev_tr[i]) ok = cuda_ok(cudaEventCreate(&f->ev_tr[i]), "create trace event");
 			auto trace = [&](int kind, int c, cudaStream_t s_) { return !env_trace || cuda_ok(cudaEventRecordWithFlags(f->ev_tr[kind < 0 ? 4 * kMaxChunks : kind * kMaxChunks + c], s_, cudaEventRecordExternal), "trace"); };
 			if (!f->st_merge) ok = ok && cuda_ok(cudaStreamCreateWithFlags(&f->st_merge, cudaStreamNonBlocking), "create merge stream");
-			if (!f->st_pull) ok = ok && cuda_ok(cudaStreamCreateWithFlags(&f->st_pull, cudaStreamNonBlocking), "create colour fetch stream");
-			if (!f->st_up2) ok = ok && cuda_ok(cudaStreamCreateWithFlags(&f->st_up2, cudaStreamNonBlocking), "create second upload stream");
-			cudaEvent_t *ev_d = f->ev_up, *ev_c = ev_d + kMaxChunks, *ev_n = ev_c + kMaxChunks, *ev_m = ev_n + kMaxChunks, *ev_p = ev_m + kMaxChunks, *ev_d2 = ev_p + kMaxChunks,
-				*ev_x = ev_d2 + kMaxChunks;   // ev_x: fork + joins
-			cudaStream_t sm = f->st_merge, so = f->st_out, sp = f->st_pull, up2 = f->st_up2;
-			// chunk c = sensors [bound(c), bound(c+1)).  What follows the last upload (that chunk's count, merge and read-back) is exposed
-			// time, so the last chunk is the smallest: it hands one sensor to the first, whose longer upload only delays idle kernels.
-			const bool taper = env_taper != 0 && Cn >= 3 && n_run / Cn >= 2;
-			auto bound = [&](int c) { const int even = (int)((long long)n_run * c / Cn); return first + even + ((taper && c > 0 && c < Cn) ? 1 : 0); };
+			cudaEvent_t *ev_d = f->ev_up, *ev_c = ev_d + kMaxChunks, *ev_n = ev_c + kMaxChunks, *ev_m = ev_n + kMaxChunks, *ev_x = ev_m + 2 * kMaxChunks;   // ev_x: fork + 3 joins
+			cudaStream_t sm = f->st_merge, so = f->st_out;
+			// chunk c = sensors [bound(c), bound(c+1))   (measured and dropped: a smaller last chunk, 3 / 5 / 6 / 8 chunks, depth halves on two
+			// copy engines, the colour fetch as a kernel of its own — all within 3 % or slower)
+			auto bound = [&](int c) { return first + (int)((long long)n_run * c / Cn); };
 			PeerDst none; none.n = 0;
 			// the merge kernel stages a tile's records in shared memory and stores them into the page-locked output block by whole warps
 			// (the multi-GPU merge's peer-store path with the host block as the only "peer"): no device copy of the result, no copy kernel
@@ -2136,35 +2081,22 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 			auto enqueue = [&](int part) -> bool {
 				bool k = trace(-1, 0, st) && cuda_ok(cudaEventRecord(ev_x[0], st), "fork") &&
 					(part == 2 || cuda_ok(cudaStreamWaitEvent(up, ev_x[0], 0), "fork")) &&
-					(part == 2 || !env_up2 || cuda_ok(cudaStreamWaitEvent(up2, ev_x[0], 0), "fork")) &&
-					(part == 1 || (cuda_ok(cudaStreamWaitEvent(sm, ev_x[0], 0), "fork") && cuda_ok(cudaStreamWaitEvent(so, ev_x[0], 0), "fork") &&
-						(!pull_kernel || cuda_ok(cudaStreamWaitEvent(sp, ev_x[0], 0), "fork")))) &&
+					(part == 1 || (cuda_ok(cudaStreamWaitEvent(sm, ev_x[0], 0), "fork") && cuda_ok(cudaStreamWaitEvent(so, ev_x[0], 0), "fork"))) &&
 					(part == 2 || cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block"));
 				for (int c = 0; c < Cn && k; c++) {
 					const SensorDesc &ca = f->h_sd[bound(c)], &cz = f->h_sd[bound(c + 1)];
 					const int tlo = ca.tile_begin - a.tile_begin, thi = cz.tile_begin - a.tile_begin;
 					if (part != 2) {
-						const size_t dbytes = (size_t)(cz.depth_off - ca.depth_off), dhalf = env_up2 ? (dbytes / 2) & ~(size_t)255 : dbytes;
-						k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off, src_depth + ca.depth_off, dhalf, cudaMemcpyHostToDevice, up), "upload depth") &&
+						k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off, src_depth + ca.depth_off, (size_t)(cz.depth_off - ca.depth_off), cudaMemcpyHostToDevice, up), "upload depth") &&
 							cuda_ok(cudaEventRecord(ev_d[c], up), "record depth upload") && trace(0, c, up);
-						if (k && dhalf < dbytes)
-							k = cuda_ok(cudaMemcpyAsync(dd + ca.depth_off + dhalf, src_depth + ca.depth_off + dhalf, dbytes - dhalf, cudaMemcpyHostToDevice, up2), "upload depth") &&
-								cuda_ok(cudaEventRecord(ev_d2[c], up2), "record depth upload") && cuda_ok(cudaStreamWaitEvent(st, ev_d2[c], 0), "wait for the depth upload");
 						if (k && !pull)
 							k = cuda_ok(cudaMemcpyAsync(dc + ca.color_off, src_colors + ca.color_off, (size_t)(cz.color_off - ca.color_off), cudaMemcpyHostToDevice, up), "upload colours") &&
 								cuda_ok(cudaEventRecord(ev_c[c], up), "record colour upload");
 						k = k && cuda_ok(cudaStreamWaitEvent(st, ev_d[c], 0), "wait for the depth upload") && launch_organized_count(f, dd, bound(c), bound(c + 1), st) == 0 && trace(1, c, st);
 					}
 					if (part == 0)
-						k = k && cuda_ok(cudaEventRecord(ev_n[c], st), "record count") && cuda_ok(cudaStreamWaitEvent(pull_kernel ? sp : sm, ev_n[c], 0), "wait for the count") &&
+						k = k && cuda_ok(cudaEventRecord(ev_n[c], st), "record count") && cuda_ok(cudaStreamWaitEvent(sm, ev_n[c], 0), "wait for the count") &&
 							(pull || cuda_ok(cudaStreamWaitEvent(sm, ev_c[c], 0), "wait for the colour upload"));
-					if (part != 1 && pull_kernel) {
-						// the colour lines under this chunk's survivors, host -> device colour image, on a stream of its own
-						k_pull_colors<<<std::max(1, env_pullb), 256, 0, sp>>>((const uint8_t *)col_dev, dc, f->keep_px.as<uint8_t>(), f->sd.as<SensorDesc>(), f->tile_sensor.as<unsigned short>(),
-							a.tile_begin, tlo, thi);
-						count_launch(1);
-						k = k && cuda_ok(cudaGetLastError(), "k_pull_colors") && cuda_ok(cudaEventRecord(ev_p[c], sp), "record colour fetch") && cuda_ok(cudaStreamWaitEvent(sm, ev_p[c], 0), "wait for the colour fetch");
-					}
 					if (part != 1) {
 						k = k && launch_map(f, dd, col_src, first, first + n_run, f->final_.as<uint4>(), nullptr, f->keep_px.as<uint8_t>(), env_direct ? host_dst : none, sm, tlo, thi) >= 0 &&
 							trace(2, c, sm) && cuda_ok(cudaEventRecord(ev_m[c], sm), "record merge") && cuda_ok(cudaStreamWaitEvent(so, ev_m[c], 0), "wait for the merge");
@@ -2177,9 +2109,7 @@ static int host_frame(int n_maps, unsigned char *depth_maps, unsigned char *dept
 						k = k && trace(3, c, so);
 					}
 				}
-				if (part != 2) k = k && cuda_ok(cudaEventRecord(ev_x[1], up), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[1], 0), "join") &&
-					(!env_up2 || (cuda_ok(cudaEventRecord(ev_x[5], up2), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[5], 0), "join")));
-				if (part != 1 && pull_kernel) k = k && cuda_ok(cudaEventRecord(ev_x[4], sp), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[4], 0), "join");
+				if (part != 2) k = k && cuda_ok(cudaEventRecord(ev_x[1], up), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[1], 0), "join");
 				if (part != 1)
 					k = k && cuda_ok(cudaEventRecord(ev_x[2], sm), "join") && cuda_ok(cudaEventRecord(ev_x[3], so), "join") &&
 						cuda_ok(cudaStreamWaitEvent(st, ev_x[2], 0), "join") && cuda_ok(cudaStreamWaitEvent(st, ev_x[3], 0), "join") &&
