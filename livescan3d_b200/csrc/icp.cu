@@ -768,9 +768,9 @@ __device__ __forceinline__ void pk_search(const IcpGrid &g, const unsigned *__re
 #define LS3D_PK_BUDGET 64
 #endif
 constexpr unsigned kPkBudget = LS3D_PK_BUDGET;
-#ifndef LS3D_PK_BUDGET0_FACTOR
-#define LS3D_PK_BUDGET0_FACTOR 1u       // measured on the bench pair: 1 -> 1.54 ms per call, 2 -> 1.79, 4 -> 1.59
-#endif
+#ifndef LS3D_PK_BUDGET0_PCT
+#define LS3D_PK_BUDGET0_PCT 75u         // first match stage of a call, in % of the budget.  Measured on the bench pair: 200 -> 1.79 ms per
+#endif                                  // call, 400 -> 1.59, 100 -> 1.54; its first iteration alone takes 269 us at 100 and 229 us at 75
 
 // this lane's query of packet `pd`: position (after the pending update when apply != 0, which is also written back), home cell,
 // and the previous nearest neighbour as the first candidate
@@ -838,8 +838,8 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_PK_MINBLOCKS) k_icp_match_
 	const f32x2 one2 = pk2(one, one);
 	const int n_packets = (int)state->n_packets;
 	const bool use_sched = state->sched_valid != 0;
-	// first match stage of a call: no seeds and no cost history yet, walks are ~40 % longer (a larger budget there did not pay)
-	const unsigned walk_budget = use_sched ? budget : budget * LS3D_PK_BUDGET0_FACTOR;
+	// first match stage of a call: no seeds and no cost history yet, walks are ~40 % longer — more of them go to the block-wide stage
+	const unsigned walk_budget = (use_sched || budget >= 0x3fffffffu) ? budget : (unsigned)((unsigned long long)budget * LS3D_PK_BUDGET0_PCT / 100u);
 	for (;;) {
 		int pk = 0;
 		if (lane == 0) {
@@ -1094,7 +1094,13 @@ __global__ void __launch_bounds__(kPkWarps * 32, LS3D_HV_MINBLOCKS) k_icp_match_
 				nn_commit(i, q.d2, q.valid ? q.idx : -1, slotmap, nn_idx, nn_d2);
 				if (dbg) { dbg[3 * (size_t)i] = hb.steps; dbg[3 * (size_t)i + 1] = hb.scanned; dbg[3 * (size_t)i + 2] = 1u; }
 			}
-			if (lane == 0) { pk_cost[pk] = max(hb.steps, budget + 1u); atomicAdd(&state->cls_n[0], 1u); }      // stays with the block-wide stage for the rest of the call
+			// stays with the block-wide stage for the rest of the call — except after the first match stage, whose warps gave up earlier
+			// than they will from now on (LS3D_PK_BUDGET0_PCT) and without seeds: those packets get one more try in the first wave
+			if (lane == 0) {
+				const bool first_stage = ld_volatile_u32(&state->sched_valid) == 0u && budget < 0x3fffffffu;
+				pk_cost[pk] = first_stage ? budget : max(hb.steps, budget + 1u);
+				atomicAdd(&state->cls_n[first_stage ? pk_cost_class(budget, budget) : 0u], 1u);
+			}
 		}
 	}
 	// the last block re-arms the queue for the next match stage
