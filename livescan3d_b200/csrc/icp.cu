@@ -476,7 +476,10 @@ __device__ __forceinline__ void nn_commit(int i, float d2, int idx, const SlotMa
 // boundary have nothing behind them), so the result is exact at any distance like nanoflann's; ties resolve to the smallest
 // target index.  `best` starts from last iteration's neighbour (a real candidate, so exactness is untouched).
 constexpr int kPkWarps = 8;
-constexpr int kPkDone = 4;             // home cells scanned up front (and skipped by the walk)
+#ifndef LS3D_PK_DONE
+#define LS3D_PK_DONE 4
+#endif
+constexpr int kPkDone = LS3D_PK_DONE;             // home cells scanned up front (and skipped by the walk)
 
 struct PkWarp {
 	float4 lo[8][8], hi[8][8];      // [level t-1][child]: point boxes of the children of the node being iterated at level t, decoded
@@ -770,7 +773,7 @@ __device__ __forceinline__ void pk_search(const IcpGrid &g, const unsigned *__re
 constexpr unsigned kPkBudget = LS3D_PK_BUDGET;
 #ifndef LS3D_PK_BUDGET0_PCT
 #define LS3D_PK_BUDGET0_PCT 75u         // first match stage of a call, in % of the budget.  Measured on the bench pair: 200 -> 1.79 ms per
-#endif                                  // call, 400 -> 1.59, 100 -> 1.54; its first iteration alone takes 269 us at 100 and 229 us at 75
+#endif                                  // call, 400 -> 1.59, 100 -> 1.54, 50 -> 1.60; 62 / 75 / 88 -> 1.50-1.55 (run-to-run spread of the same size)
 
 // this lane's query of packet `pd`: position (after the pending update when apply != 0, which is also written back), home cell,
 // and the previous nearest neighbour as the first candidate
