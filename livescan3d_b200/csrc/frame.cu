@@ -111,6 +111,47 @@ __device__ __forceinline__ bool map_pixel(const PixelXform &m, float xn, float y
 
 struct Bounds6 { float v[6]; };
 
+// ---- packed-fp32 variant (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issue slot) ----
+// The tile is kept as three float planes, so one LDS.64 yields the same coordinate of two horizontally adjacent candidates;
+// the query is broadcast into both halves and every step of d0*d0 + d1*d1 + d2*d2 runs on the pair: 3 FADD2 (differences),
+// 3 FMUL2 (squares), 2 adds.  Each half is rounded exactly like the scalar sequence, so the masks stay bit-exact.  The adds are
+// issued as fma(a, 1.0f, b) == fl(a + b) with the 1.0f taken from a kernel argument: ptxas contracts a packed mul.rn + add.rn
+// into FFMA2 even under --fmad=false (checked in SASS), which would skip the rounding of the product; it cannot do that to an
+// fma whose multiplier it does not know.  Pairs start at even columns, so a window of reach HX is covered by HX+1 pairs (one
+// extra real candidate on one side, which keeps the count exact); the halo is staged one column wider for it.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// map_pixel for two horizontally adjacent pixels of one row at once: dpair = their two u16 depths (low half = left pixel), xn2 their two
+// ray-table entries.  Every half is rounded exactly like map_pixel's scalar sequence (the two FMAs of div1000_u16 are FMAs there too;
+// -q0 * 1000 == q0 * -1000 exactly), so the positions are bit-identical; a sum that follows a product is again fma(a, 1.0f, b) with the
+// opaque 1.0f.  Returns bit 0 / bit 1 = the left / right pixel yields a vertex.  The halo staging of the organized count runs on this:
+// a third of the instructions per staged pixel.
+__device__ __forceinline__ unsigned map_pixel_pair(const PixelXform &m, f32x2 xn2, float yn, unsigned dpair, f32x2 one2, f32x2 &wx, f32x2 &wy, f32x2 &wz) {
+	const float r = 1.0f / 1000.0f;
+	const f32x2 v = pk((float)(dpair & 0xffffu), (float)(dpair >> 16));
+	const f32x2 q0 = mul2(v, pk(r, r));
+	const f32x2 rem = fma2(q0, pk(-1000.0f, -1000.0f), v);
+	f32x2 Z = fma2(rem, pk(r, r), q0);
+	f32x2 X = mul2(xn2, Z), Y = mul2(pk(yn, yn), Z);
+	X = fma2(X, one2, pk(m.t0, m.t0)); Y = fma2(Y, one2, pk(m.t1, m.t1)); Z = fma2(Z, one2, pk(m.t2, m.t2));
+	wx = fma2(fma2(mul2(X, pk(m.r0, m.r0)), one2, mul2(Y, pk(m.r1, m.r1))), one2, mul2(Z, pk(m.r2, m.r2)));
+	wy = fma2(fma2(mul2(X, pk(m.r3, m.r3)), one2, mul2(Y, pk(m.r4, m.r4))), one2, mul2(Z, pk(m.r5, m.r5)));
+	wz = fma2(fma2(mul2(X, pk(m.r6, m.r6)), one2, mul2(Y, pk(m.r7, m.r7))), one2, mul2(Z, pk(m.r8, m.r8)));
+	float x0, x1, y0, y1, z0, z1;
+	upk(wx, x0, x1); upk(wy, y0, y1); upk(wz, z0, z1);
+	unsigned ok = 0;
+	if ((dpair & 0xffffu) && !(x0 < m.minX || x0 > m.maxX || y0 < m.minY || y0 > m.maxY || z0 < m.minZ || z0 > m.maxZ)) ok |= 1u;
+	if ((dpair >> 16) && !(x1 < m.minX || x1 > m.maxX || y1 < m.minY || y1 > m.maxY || z1 < m.minZ || z1 > m.maxZ)) ok |= 2u;
+	return ok;
+}
+
+
 __device__ __forceinline__ unsigned color_line_mask(int k) {          // threads (8 pixels = 24 bytes each) of a warp whose bytes touch line k of its 768
 	const int lo = 128 * k / 24, hi = (128 * k + 127) / 24;
 	return ((2u << hi) - 1u) & ~((1u << lo) - 1u);
@@ -127,12 +168,15 @@ __device__ __forceinline__ unsigned color_line_mask(int k) {          // threads
 // kKeepMask: AND the organized neighbour count's per-pixel mask into the validity test.  In that mode the count kernel
 // has already left every tile's survivor count in tile_count[], so a tile's base is a plain sum over its predecessors
 // (no inter-block dependency at all) and tiles are assigned statically; otherwise the base comes from the look-back scan.
+#ifndef LS3D_MAP_PAIRS
+#define LS3D_MAP_PAIRS 1
+#endif
 template <bool kWriteD2V, bool kKeepMask>
 __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 	const uint8_t *__restrict__ depth, const uint8_t *__restrict__ colors, const SensorDesc *__restrict__ sd, const unsigned short *__restrict__ tile_sensor,
 	const float *__restrict__ rays, int s_first, int s_end, Bounds6 bnd, FrameCtl *ctl, unsigned long long *status, int *culled_starts,
 	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ d2v, const uint8_t *__restrict__ keep_px,
-	const unsigned *__restrict__ tile_count, PeerDst peers, int tile_lo, int tile_hi)
+	const unsigned *__restrict__ tile_count, PeerDst peers, int tile_lo, int tile_hi, float one)
 {
 	__shared__ unsigned sm[16];
 	__shared__ int s_tile;
@@ -156,6 +200,7 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 	// kKeepMask only: this launch places tiles [tile_lo, tile_hi) of the run (bases still count from the run's first tile), so
 	// the host path can merge sensor by sensor as the colours arrive; the look-back variant always walks the whole run
 	int static_tile = tile_lo + blockIdx.x;
+	bool waited = false;
 
 	for (;;) {
 		int tile;
@@ -174,6 +219,26 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 		const int rem = px - p0;
 		const PixelXform m = load_xform(sd, s, bnd.v);
 
+		// ---- 8 u16 depths: one LDG.128 (kept packed in 4 registers), issued before the keep mask is looked at: an input, not something the
+		// count kernel wrote, so with a programmatic launch it is already on its way while that kernel's last blocks finish ----
+		uint4 dq = make_uint4(0u, 0u, 0u, 0u);
+		const uint8_t *dp = depth + sd[s].depth_off + 2ll * p0;
+		{
+			if (rem >= 8 && (((uintptr_t)dp) & 15) == 0) {
+				dq = __ldg(reinterpret_cast<const uint4 *>(dp));
+			} else {
+				unsigned t[8];
+#pragma unroll
+				for (int j = 0; j < 8; j++) t[j] = (j < rem) ? (unsigned)__ldg(reinterpret_cast<const unsigned short *>(dp) + j) : 0u;
+				dq = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
+			}
+		}
+		if (kKeepMask && !waited) {
+			// launched programmatically behind k_organized_count (launch_map): everything above ran beside its tail; its keep bytes and
+			// tile counts are visible from here on.  A no-op for a plain launch.
+			asm volatile("griddepcontrol.wait;" ::: "memory");
+			waited = true;
+		}
 		// ---- the organized count's verdicts for the 8 pixels: one LDG.64, bytes (0/1) -> bits by a multiply ----
 		unsigned keepm = 0xffu;
 		if (kKeepMask) {
@@ -186,19 +251,6 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 			} else {
 #pragma unroll
 				for (int j = 0; j < 8; j++) if (j < rem && __ldg(kp + j)) keepm |= 1u << j;
-			}
-		}
-		// ---- 8 u16 depths: one LDG.128 (kept packed in 4 registers); with a keep mask only threads that emit something need them ----
-		uint4 dq = make_uint4(0u, 0u, 0u, 0u);
-		const uint8_t *dp = depth + sd[s].depth_off + 2ll * p0;
-		if (!kKeepMask || keepm) {
-			if (rem >= 8 && (((uintptr_t)dp) & 15) == 0) {
-				dq = __ldg(reinterpret_cast<const uint4 *>(dp));
-			} else {
-				unsigned t[8];
-#pragma unroll
-				for (int j = 0; j < 8; j++) t[j] = (j < rem) ? (unsigned)__ldg(reinterpret_cast<const unsigned short *>(dp) + j) : 0u;
-				dq = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
 			}
 		}
 		auto depth_of = [&](int j) -> unsigned {
@@ -289,20 +341,8 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 				c0 = cw[0]; c1 = cw[1]; c2 = cw[2]; c3 = cw[3]; c4 = cw[4]; c5 = cw[5];
 			}
 			size_t o = (size_t)out_off + base + off;
-			unsigned rest = valid;
-#pragma unroll 1
-			while (rest) {
-				const int j = __ffs(rest) - 1;
-				rest &= rest - 1;
-				float wx, wy, wz;
-				if (kKeepMask) {
-					int x = x0 + j, y = y0;
-					while (x >= w) { x -= w; y++; }
-					map_pixel(m, __ldg(xray + x), __ldg(yray + y), depth_of(j), wx, wy, wz);
-				} else {
-					wx = s_pos[0][j][tid]; wy = s_pos[1][j][tid]; wz = s_pos[2][j][tid];
-				}
-				// bytes 3j, 3j+1, 3j+2 of the 24-byte colour block -> R,G,B,255
+			// bytes 3j, 3j+1, 3j+2 of the 24-byte colour block -> R,G,B,255, then the record goes to its final place (or to the staging tile)
+			auto emit = [&](int j, float wx, float wy, float wz) {
 				const int bi = 3 * j, wi = bi >> 2;
 				const unsigned lo = wi == 0 ? c0 : wi == 1 ? c1 : wi == 2 ? c2 : wi == 3 ? c3 : wi == 4 ? c4 : c5;
 				const unsigned hi = wi == 0 ? c1 : wi == 1 ? c2 : wi == 2 ? c3 : wi == 3 ? c4 : c5;
@@ -311,6 +351,41 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 				if (peers.n == 0) out[o] = rec;
 				else s_stage[o - ((size_t)out_off + base)] = rec;
 				o++;
+			};
+			if (LS3D_MAP_PAIRS && kKeepMask && !(w & 1) && w >= 8 && rem >= 8) {
+				// even width: pixels 2q, 2q+1 of the thread share a row and an 8-byte aligned ray pair -> four packed pair evaluations,
+				// unrolled (constant j: the depth and colour selections are one instruction each), bit-identical to map_pixel
+				const f32x2 one2 = pk(one, one);
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					if (valid & (3u << (2 * q))) {
+						int x = x0 + 2 * q, y = y0;
+						if (x >= w) { x -= w; y++; }
+						const float2 xn = __ldg(reinterpret_cast<const float2 *>(xray + x));
+						f32x2 ax, ay, az;
+						map_pixel_pair(m, pk(xn.x, xn.y), __ldg(yray + y), q == 0 ? dq.x : q == 1 ? dq.y : q == 2 ? dq.z : dq.w, one2, ax, ay, az);
+						float a0, a1, b0, b1, g0, g1;
+						upk(ax, a0, a1); upk(ay, b0, b1); upk(az, g0, g1);
+						if (valid & (1u << (2 * q))) emit(2 * q, a0, b0, g0);
+						if (valid & (2u << (2 * q))) emit(2 * q + 1, a1, b1, g1);
+					}
+				}
+			} else {
+				unsigned rest = valid;
+#pragma unroll 1
+				while (rest) {
+					const int j = __ffs(rest) - 1;
+					rest &= rest - 1;
+					float wx, wy, wz;
+					if (kKeepMask) {
+						int x = x0 + j, y = y0;
+						while (x >= w) { x -= w; y++; }
+						map_pixel(m, __ldg(xray + x), __ldg(yray + y), depth_of(j), wx, wy, wz);
+					} else {
+						wx = s_pos[0][j][tid]; wy = s_pos[1][j][tid]; wz = s_pos[2][j][tid];
+					}
+					emit(j, wx, wy, wz);
+				}
 			}
 		}
 		if (peers.n > 0) {
@@ -526,22 +601,6 @@ __device__ __forceinline__ int org_count_dispatch(int hx, const float4 *__restri
 	}
 }
 
-// ---- packed-fp32 variant (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issue slot) ----
-// The tile is kept as three float planes, so one LDS.64 yields the same coordinate of two horizontally adjacent candidates;
-// the query is broadcast into both halves and every step of d0*d0 + d1*d1 + d2*d2 runs on the pair: 3 FADD2 (differences),
-// 3 FMUL2 (squares), 2 adds.  Each half is rounded exactly like the scalar sequence, so the masks stay bit-exact.  The adds are
-// issued as fma(a, 1.0f, b) == fl(a + b) with the 1.0f taken from a kernel argument: ptxas contracts a packed mul.rn + add.rn
-// into FFMA2 even under --fmad=false (checked in SASS), which would skip the rounding of the product; it cannot do that to an
-// fma whose multiplier it does not know.  Pairs start at even columns, so a window of reach HX is covered by HX+1 pairs (one
-// extra real candidate on one side, which keeps the count exact); the halo is staged one column wider for it.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
 template <int HX>
 __device__ __forceinline__ int org_count_rows2(const float *__restrict__ tx, const float *__restrict__ ty, const float *__restrict__ tz,
 	int ci, int rv, float qx, float qy, float qz, int k, float thr, f32x2 one2) {
@@ -586,6 +645,9 @@ __device__ __forceinline__ int org_count_dispatch2(int hx, const float *__restri
 #ifndef LS3D_ORG_PACKED
 #define LS3D_ORG_PACKED 1
 #endif
+#ifndef LS3D_ORG_PAIRSTAGE
+#define LS3D_ORG_PAIRSTAGE 1
+#endif
 #ifndef LS3D_ORG_MINBLOCKS
 #define LS3D_ORG_MINBLOCKS 6
 #endif
@@ -603,6 +665,9 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 #endif
 	__shared__ unsigned s_kept;
 	__shared__ int s_hx, s_hy;
+	// the map kernel behind us (launch_map, after_count) may move into the SMs as soon as every block of this grid has started: it
+	// waits for this grid's completion (griddepcontrol.wait) before it touches anything written here
+	asm volatile("griddepcontrol.launch_dependents;");
 	const int s = s_first + blockIdx.z;
 	const int w = sd[s].w, h = sd[s].h;
 	const int tx0 = blockIdx.x * kOrgTW, ty0 = blockIdx.y * kOrgTH;
@@ -666,6 +731,48 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 		}
 		put(r * kOrgSW + c, wx, wy, wz);
 	};
+#if LS3D_ORG_PACKED && LS3D_ORG_PAIRSTAGE
+	// The ring as a flat list of even-aligned pixel PAIRS (2 hy band rows of 16 + hxe pairs, then hxe pairs beside each of the 16 tile
+	// rows; hxe = hx rounded up to even), dealt out evenly to the 256 threads and mapped two pixels at a time with packed fp32: one
+	// 32-bit depth load, one 64-bit ray load and three 64-bit shared-memory stores per pair.  (Until round 2 every thread staged single
+	// pixels in a row loop x column loop whose second trips kept a third of the lanes busy: 41 % of the kernel's instructions.)
+	// Needs an even image width and a 4-byte aligned image (block-uniform test); other images take the scalar loops below.
+	if ((hx | hy) && !(w & 1) && !(reinterpret_cast<uintptr_t>(dimg) & 3)) {
+		const int hxe = (hx + 1) & ~1;                                   // 2..8
+		const int pw = kOrgTW / 2 + hxe;                                 // pairs per band row: 18..24
+		const int nband = 2 * hy * pw, ntot = nband + kOrgTH * hxe;
+		const unsigned inv_pw = 65536u / (unsigned)pw + 1u, inv_hx = 65536u / (unsigned)hxe + 1u;      // (i * inv) >> 16 == i / d for i < 2048
+		const f32x2 one2 = pk(one, one);
+		for (int i = tid; i < ntot; i += kOrgTW * kOrgRows) {
+			int r, c;                                                    // tile coordinates of the pair's left (even) column
+			if (i < nband) {
+				const int br = (int)(((unsigned)i * inv_pw) >> 16), bc = i - br * pw;
+				r = br < hy ? kOrgHalo - hy + br : kOrgHalo + kOrgTH - hy + br;
+				c = kOrgHalo - hxe + 2 * bc;
+			} else {
+				const int j = i - nband;
+				const int sr = (int)(((unsigned)j * inv_hx) >> 16), sc = j - sr * hxe;      // hxe / 2 pairs left of the tile, hxe / 2 right of it
+				r = kOrgHalo + sr;
+				c = 2 * sc < hxe ? kOrgHalo - hxe + 2 * sc : kOrgHalo + kOrgTW - hxe + 2 * sc;
+			}
+			const int gx = tx0 - kOrgHalo + c, gy = ty0 - kOrgHalo + r;         // gx is even and w is even: both pixels are inside or both outside
+			f32x2 sx = pk(qnan, qnan), sy = sx, sz = sx;
+			if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+				const unsigned dp = __ldg(reinterpret_cast<const unsigned *>(dimg + (size_t)gy * w + gx));
+				const float2 xn = __ldg(reinterpret_cast<const float2 *>(xray + gx));
+				f32x2 ax;
+				const unsigned ok = map_pixel_pair(m, pk(xn.x, xn.y), __ldg(yray + gy), dp, one2, ax, sy, sz);
+				float a0, a1;
+				upk(ax, a0, a1);
+				sx = pk((ok & 1u) ? a0 : qnan, (ok & 2u) ? a1 : qnan);      // a NaN x is enough to fail every distance test
+			}
+			const int idx = r * kOrgSW + c;
+			*reinterpret_cast<f32x2 *>(tile_x + idx) = sx;
+			*reinterpret_cast<f32x2 *>(tile_y + idx) = sy;
+			*reinterpret_cast<f32x2 *>(tile_z + idx) = sz;
+		}
+	} else
+#endif
 	if (hx | hy) {
 		for (int r = ly; r < 2 * hy; r += kOrgRows) {
 			const int row = r < hy ? kOrgHalo - hy + r : kOrgHalo + kOrgTH + (r - hy);
@@ -1603,9 +1710,33 @@ __global__ void __launch_bounds__(256) k_copy_mesh_out(const uint4 *__restrict__
 	}
 }
 
-// K1 launcher.  keep_px != nullptr: AND the organized neighbour-count mask into the validity test.
+static bool frame_use_pdl() {
+	static const int v = getenv("LS3D_FRAME_PDL") ? atoi(getenv("LS3D_FRAME_PDL")) : 1;
+	return v != 0;
+}
+
+// kernel launch, optionally with the programmatic-stream-serialization attribute: the kernel may then become resident while its
+// predecessor in the stream (which has executed griddepcontrol.launch_dependents) still runs, and orders itself with griddepcontrol.wait
+template <typename... KArgs, typename... Args>
+static void launch_ex(bool programmatic, void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = dim3(block);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = programmatic && frame_use_pdl() ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);          // errors are picked up by the caller's cudaGetLastError
+}
+
+// K1 launcher.  keep_px != nullptr: AND the organized neighbour-count mask into the validity test.  after_count: the organized count
+// of the same sensors is the previous launch in this stream (nothing in between) — K1 is then launched programmatically: its blocks
+// move in as the count's last blocks leave, fetch their depths, and wait for the count's results only then.
 static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, int s_first, int s_end, uint4 *out, const int *d_off,
-	const uint8_t *keep_px, const PeerDst &peers, cudaStream_t st, int tile_lo = 0, int tile_hi = -1)
+	const uint8_t *keep_px, const PeerDst &peers, cudaStream_t st, int tile_lo = 0, int tile_hi = -1, bool after_count = false)
 {
 	const int ntiles = f->h_sd[s_end].tile_begin - f->h_sd[s_first].tile_begin;
 	if (tile_hi < 0) tile_hi = ntiles;
@@ -1631,11 +1762,11 @@ static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, i
 	}
 	stage_begin(f, kTsMap, st);
 	if (f->want_d2v || f->want_triangles) {
-		if (keep_px) k_map_cull_compact<true, true><<<blocks, kScanThreads, stage_bytes, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers, tile_lo, tile_hi);
-		else k_map_cull_compact<true, false><<<blocks, kScanThreads, stage_bytes, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers, tile_lo, tile_hi);
+		if (keep_px) launch_ex(after_count, k_map_cull_compact<true, true>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers, tile_lo, tile_hi, 1.0f);
+		else launch_ex(false, k_map_cull_compact<true, false>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers, tile_lo, tile_hi, 1.0f);
 	} else {
-		if (keep_px) k_map_cull_compact<false, true><<<blocks, kScanThreads, stage_bytes, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers, tile_lo, tile_hi);
-		else k_map_cull_compact<false, false><<<blocks, kScanThreads, stage_bytes, st>>>(dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers, tile_lo, tile_hi);
+		if (keep_px) launch_ex(after_count, k_map_cull_compact<false, true>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers, tile_lo, tile_hi, 1.0f);
+		else launch_ex(false, k_map_cull_compact<false, false>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers, tile_lo, tile_hi, 1.0f);
 	}
 	stage_end(f, kTsMap, st);
 	count_launch(1);
@@ -1752,7 +1883,8 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 		int r;
 		if (f->filter_on && f->last_organized) {
 			if (!f->last_depth) { set_error("ls3d_frame_merge: no count stage has run"); return -1; }
-			r = launch_map(f, f->last_depth, f->last_colors, s_first, s_end, dst, d_dst_offset, f->keep_px.as<uint8_t>(), peers, st);
+			r = launch_map(f, f->last_depth, f->last_colors, s_first, s_end, dst, d_dst_offset, f->keep_px.as<uint8_t>(), peers, st, 0, -1,
+				(stages & kStageCount) && !f->timing && !f->colors_ready);      // straight behind the count kernel in this stream
 		} else if (f->filter_on || !(stages & kStageCount)) {
 			r = frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st);
 		} else {

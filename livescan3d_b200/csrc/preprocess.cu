@@ -74,7 +74,17 @@ __device__ __forceinline__ int c_float_to_int(float f) {
 	return (f > -2147483904.0f && f < 2147483648.0f) ? __float2int_rz(f) : INT_MIN;
 }
 
+// The correction is a chain of short kernels; from the gather on each is launched programmatically behind its predecessor
+// (launch_chain): its blocks may move into the SMs while the predecessor's last blocks run, and the first thing they do is wait for
+// that grid — and with it every earlier one — to complete.  Same ordering as a plain stream, minus the launch latencies.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_enter() {
+	asm volatile("griddepcontrol.launch_dependents;");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256) k_rad_scatter(const uint8_t *__restrict__ depth, const PreSensor *__restrict__ sd, int *winner) {
+	pdl_trigger();
 	const PreSensor s = sd[blockIdx.y];
 	const unsigned short *dm = reinterpret_cast<const unsigned short *>(depth) + s.pix_begin;
 	const int px = s.w * s.h;
@@ -97,6 +107,7 @@ __global__ void __launch_bounds__(256) k_rad_scatter(const uint8_t *__restrict__
 __global__ void __launch_bounds__(256) k_rad_gather(const uint8_t *__restrict__ depth, const uint8_t *__restrict__ colors, const PreSensor *__restrict__ sd,
 	const int *__restrict__ winner, unsigned short *__restrict__ fdepth, uint8_t *__restrict__ fcolors, unsigned char *__restrict__ state)
 {
+	pdl_enter();
 	const PreSensor s = sd[blockIdx.y];
 	const unsigned short *dm = reinterpret_cast<const unsigned short *>(depth) + s.pix_begin;
 	const uint8_t *cm = colors + 3 * s.pix_begin;
@@ -191,6 +202,7 @@ __device__ __forceinline__ bool rad_try_resolve(const PreSensor &s, int p, unsig
 // one grid-wide round: settles every hole whose outcome does not hang on another undecided hole (the vast majority)
 __global__ void __launch_bounds__(256) k_rad_round(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state)
 {
+	pdl_enter();
 	const PreSensor s = sd[blockIdx.y];
 	const int px = s.w * s.h;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < px; p += gridDim.x * blockDim.x) {
@@ -206,6 +218,7 @@ __global__ void __launch_bounds__(256) k_rad_round(const PreSensor *__restrict__
 // leaves — the thin curves of the warp, every link of which has an earlier hole for a neighbour — are what k_rad_fixpoint is for).
 __global__ void __launch_bounds__(256) k_rad_first(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state)
 {
+	pdl_enter();
 	const PreSensor s = sd[blockIdx.y];
 	const int px = s.w * s.h, w = s.w;
 	const int nb[8] = {-w - 1, -w, -w + 1, -1, 1, w - 1, w, w + 1};      // depthprocessing.cpp:226
@@ -329,6 +342,7 @@ constexpr int kChainThreads = 1024, kChainAdmit = 4;
 __global__ void __launch_bounds__(kChainThreads) k_rad_chains(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors, unsigned char *state,
 	int *__restrict__ list, int *__restrict__ pidx, int *err, const int *__restrict__ only_if = nullptr)
 {
+	pdl_enter();
 	if (only_if && !only_if[blockIdx.x]) return;              // behind k_rad_fixpoint: only the sensors it left alone
 	__shared__ unsigned long long s_val[kChainThreads];          // entry i of the chunk: depth | r << 16 | g << 24 | b << 32 | final << 63
 	__shared__ unsigned s_w[32];
@@ -489,6 +503,7 @@ __device__ __forceinline__ unsigned long long rad_record(const unsigned short *f
 __global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThreads) k_rad_fixpoint(const PreSensor *__restrict__ sd, unsigned short *fdepth, uint8_t *fcolors,
 	unsigned char *state, int *__restrict__ list, int *pidx, int *err, int *bail)
 {
+	pdl_enter();
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster();
 	extern __shared__ __align__(16) unsigned long long s_fix[];   // 80 KB, opt-in
@@ -749,6 +764,7 @@ __global__ void __cluster_dims__(kFixCluster, 1, 1) __launch_bounds__(kFixThread
 __global__ void __launch_bounds__(256) k_rad_writeback(uint8_t *__restrict__ depth, uint8_t *__restrict__ colors, long long total_px,
 	const unsigned short *__restrict__ fdepth, const uint8_t *__restrict__ fcolors)
 {
+	pdl_enter();
 	unsigned short *dm = reinterpret_cast<unsigned short *>(depth);
 	for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total_px; p += (long long)gridDim.x * blockDim.x) {
 		dm[p] = fdepth[p];
@@ -804,6 +820,7 @@ struct PreCtx {
 	cudaEvent_t ev_done = nullptr;       // end of the previous correction: the scratch below is shared by every caller / stream
 	int *pin_err = nullptr;
 	int sm_count = 148;
+	std::vector<PreSensor> last_sd;     // what the device copy of the descriptors holds (empty: nothing uploaded yet)
 };
 
 PreCtx *g_pre = nullptr;
@@ -846,16 +863,33 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 	return c;
 }
 
+// launch behind the previous kernel of the stream with the programmatic-stream-serialization attribute (see pdl_enter)
+template <typename... KArgs, typename... Args>
+static void launch_chain(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+	static const int use = getenv("LS3D_RADIAL_PDL") ? atoi(getenv("LS3D_RADIAL_PDL")) : 1;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = dim3(block);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = use ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);          // errors are picked up by the cudaGetLastError at the end of the chain
+}
+
 // enqueue the whole correction on st for device-resident packed buffers (in place); err word = count[n_maps]
 int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, const float *intr_params, cudaStream_t st) {
 	long long acc = 0;
 	int max_px = 1;
-	// the previous call's descriptor upload must have left the pinned block before it is rewritten, and — the scratch buffers are
-	// one set per process — a correction enqueued on ANOTHER stream must not start before the previous one has finished
-	if (!cuda_ok(cudaEventSynchronize(c->ev_staged), "wait for the previous descriptor upload") ||
-		!cuda_ok(cudaStreamWaitEvent(st, c->ev_done, 0), "order after the previous correction")) return -1;
+	// the scratch buffers are one set per process: a correction enqueued on ANOTHER stream must not start before the previous one
+	// has finished
+	if (!cuda_ok(cudaStreamWaitEvent(st, c->ev_done, 0), "order after the previous correction")) return -1;
+	std::vector<PreSensor> now((size_t)n_maps);
 	for (int i = 0; i < n_maps; i++) {
-		PreSensor &s = c->pin_sd[i];
+		PreSensor &s = now[i];
 		memset(&s, 0, sizeof(s));
 		s.w = c->w[i]; s.h = c->h[i]; s.pix_begin = acc;
 		const float *ip = intr_params + 7 * i;
@@ -863,20 +897,28 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 		acc += (long long)s.w * s.h;
 		max_px = std::max(max_px, s.w * s.h);
 	}
-	bool ok = cuda_ok(cudaMemcpyAsync(c->sd.p, c->pin_sd, sizeof(PreSensor) * n_maps, cudaMemcpyHostToDevice, st), "upload descriptors") &&
-		cuda_ok(cudaEventRecord(c->ev_staged, st), "record descriptor upload") &&
-		cuda_ok(cudaMemsetAsync(c->winner.p, 0, 4 * (size_t)c->total_px, st), "clear winners") &&
+	bool ok = true;
+	if (c->last_sd.size() != now.size() || memcmp(c->last_sd.data(), now.data(), sizeof(PreSensor) * now.size()) != 0) {
+		// new intrinsics (normally once per rig): the previous upload must have left the pinned block before it is rewritten
+		c->last_sd.clear();
+		if (!cuda_ok(cudaEventSynchronize(c->ev_staged), "wait for the previous descriptor upload")) return -1;
+		memcpy(c->pin_sd, now.data(), sizeof(PreSensor) * now.size());
+		ok = cuda_ok(cudaMemcpyAsync(c->sd.p, c->pin_sd, sizeof(PreSensor) * n_maps, cudaMemcpyHostToDevice, st), "upload descriptors") &&
+			cuda_ok(cudaEventRecord(c->ev_staged, st), "record descriptor upload");
+		if (ok) c->last_sd = now;
+	}
+	ok = ok && cuda_ok(cudaMemsetAsync(c->winner.p, 0, 4 * (size_t)c->total_px, st), "clear winners") &&
 		cuda_ok(cudaMemsetAsync(c->count.p, 0, 8 * (size_t)n_maps + 8, st), "clear worklist counts");
 	if (!ok) return -1;
 	const dim3 grid((unsigned)std::max(1, std::min((max_px + 255) / 256, c->sm_count * 8 / std::max(1, std::min(n_maps, 8)) + 1)), (unsigned)n_maps);
 	const PreSensor *sd = c->sd.as<PreSensor>();
 	int *count = c->count.as<int>();
 	k_rad_scatter<<<grid, 256, 0, st>>>(d_depth, sd, c->winner.as<int>());
-	k_rad_gather<<<grid, 256, 0, st>>>(d_depth, d_colors, sd, c->winner.as<int>(), c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+	launch_chain(k_rad_gather, grid, 256, 0, st, d_depth, d_colors, sd, c->winner.as<int>(), c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
 	static const int env_snapshot = getenv("LS3D_RADIAL_SNAPSHOT") ? atoi(getenv("LS3D_RADIAL_SNAPSHOT")) : 1;         // 0: the fenced round of rounds 1-2 (A/B)
 	for (int r = 0; r < kRadRounds; r++) {
-		if (env_snapshot && r == 0) k_rad_first<<<dim3((unsigned)((max_px + 255) / 256), (unsigned)n_maps), 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
-		else k_rad_round<<<grid, 256, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+		if (env_snapshot && r == 0) launch_chain(k_rad_first, dim3((unsigned)((max_px + 255) / 256), (unsigned)n_maps), 256, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+		else launch_chain(k_rad_round, grid, 256, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
 	}
 	static const int env_wavefront = getenv("LS3D_RADIAL_WAVEFRONT") ? atoi(getenv("LS3D_RADIAL_WAVEFRONT")) : 0;      // 1: the round-1 lockstep wavefront (A/B)
 	static const int env_chains = getenv("LS3D_RADIAL_CHAINS") ? atoi(getenv("LS3D_RADIAL_CHAINS")) : 0;               // 1: the chain kernel of round 1/2 instead of the fixpoint iteration (A/B)
@@ -899,15 +941,15 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 			if (!cuda_ok(cudaFuncSetAttribute(k_rad_fixpoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fix_smem), "hole fill shared memory")) return -1;
 			fix_attr = true;
 		}
-		k_rad_fixpoint<<<n_maps * kFixCluster, kFixThreads, fix_smem, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(),
+		launch_chain(k_rad_fixpoint, dim3((unsigned)(n_maps * kFixCluster)), kFixThreads, fix_smem, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(),
 			c->winner.as<int>(), count + n_maps, count + n_maps + 1);
-		k_rad_chains<<<n_maps, kChainThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps,
+		launch_chain(k_rad_chains, dim3((unsigned)n_maps), kChainThreads, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps,
 			count + n_maps + 1);
 	} else {
 		// the winner map is free after the gather: it becomes the pixel -> list index map
-		k_rad_chains<<<n_maps, kChainThreads, 0, st>>>(sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps);
+		launch_chain(k_rad_chains, dim3((unsigned)n_maps), kChainThreads, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps, nullptr);
 	}
-	k_rad_writeback<<<(unsigned)std::max<long long>(1, std::min<long long>((c->total_px + 255) / 256, (long long)c->sm_count * 8)), 256, 0, st>>>(d_depth, d_colors, c->total_px,
+	launch_chain(k_rad_writeback, dim3((unsigned)std::max<long long>(1, std::min<long long>((c->total_px + 255) / 256, (long long)c->sm_count * 8))), 256, 0, st, d_depth, d_colors, c->total_px,
 		c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>());
 	count_launch(4 + kRadRounds);
 	if (!cuda_ok(cudaEventRecord(c->ev_done, st), "record end of correction")) return -1;
