@@ -571,6 +571,7 @@ extern "C" int ls3d_set_transfer_chunk_limit(int limit) { if (limit < 1) { set_e
 // indices are the scan values (repeat occurrences follow prev[] back to the first one inside the chunk).  Chunks are resolved
 // one after the other (each needs the previous end), every chunk with grid-wide kernels.
 __global__ void __launch_bounds__(256) k_occ_count(const int *__restrict__ tri, long long m, int n_vertices, unsigned *__restrict__ cnt, int *err) {
+	pdl_enter();
 	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < m; i += 256ll * gridDim.x) {
 		const int v = __ldg(tri + i);
 		if (v < 0 || v >= n_vertices) { atomicOr(err, 1); continue; }
@@ -579,6 +580,7 @@ __global__ void __launch_bounds__(256) k_occ_count(const int *__restrict__ tri, 
 }
 // exclusive scan of cnt[0..n) into start[0..n] by a single block (n <= a few million: tens of microseconds)
 __global__ void __launch_bounds__(1024) k_scan_single(const unsigned *__restrict__ cnt, unsigned *__restrict__ start, long long n) {
+	pdl_enter();
 	__shared__ unsigned s_w[32];
 	__shared__ unsigned s_carry;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -603,6 +605,7 @@ __global__ void __launch_bounds__(1024) k_scan_single(const unsigned *__restrict
 // the same exclusive scan, grid-wide (decoupled look-back over 2048-element tiles, tiles handed out by ticket): the single-block
 // version above needs ~1 us per 1024 elements, i.e. 0.7 ms for the 739 k vertices of an 8-sensor mesh
 __global__ void __launch_bounds__(kScanThreads) k_scan_excl(const unsigned *__restrict__ cnt, unsigned *__restrict__ start, long long n, unsigned long long *status, unsigned *ticket, int *err) {
+	pdl_enter();
 	__shared__ unsigned sm[16];
 	__shared__ int s_tile;
 	const int tid = threadIdx.x;
@@ -626,6 +629,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_excl(const unsigned *__re
 	}
 }
 __global__ void __launch_bounds__(256) k_occ_fill(const int *__restrict__ tri, long long m, int n_vertices, const unsigned *__restrict__ start, unsigned *__restrict__ cursor, unsigned *__restrict__ pos) {
+	pdl_enter();
 	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < m; i += 256ll * gridDim.x) {
 		const int v = __ldg(tri + i);
 		if (v < 0 || v >= n_vertices) continue;
@@ -634,6 +638,7 @@ __global__ void __launch_bounds__(256) k_occ_fill(const int *__restrict__ tri, l
 }
 // per vertex: sort its (short) occurrence list, then link each occurrence to the one before it
 __global__ void __launch_bounds__(256) k_occ_link(int n_vertices, const unsigned *__restrict__ start, unsigned *__restrict__ pos, int *__restrict__ prev) {
+	pdl_enter();
 	for (int v = blockIdx.x * 256 + threadIdx.x; v < n_vertices; v += 256 * gridDim.x) {
 		const unsigned a = start[v], b = start[v + 1];
 		for (unsigned i = a + 1; i < b; i++) {          // insertion sort: a grid mesh vertex has at most 6 occurrences
@@ -666,6 +671,7 @@ struct ChunkCtl {
 __global__ void __launch_bounds__(kScanThreads) k_chunk_scan(const int *__restrict__ prev, long long m, long long s, long long span,
 	unsigned long long *status, ChunkCtl *ctl, unsigned *__restrict__ incl_out, int limit)
 {
+	pdl_enter();
 	__shared__ unsigned sm[16];
 	__shared__ int s_tile;
 	const int tid = threadIdx.x;
@@ -706,6 +712,7 @@ __global__ void __launch_bounds__(kScanThreads) k_chunk_scan(const int *__restri
 __global__ void __launch_bounds__(256) k_chunk_emit(const int *__restrict__ tri, const int *__restrict__ prev, long long s, long long e,
 	const unsigned *__restrict__ incl, const uint4 *__restrict__ verts, unsigned vbase, int *__restrict__ new_tri, uint4 *__restrict__ new_verts, const ChunkCtl *ctl)
 {
+	pdl_enter();
 	if (ctl) {                         // device-driven loop: the range k_chunk_close resolved
 		if (ctl->done) return;
 		s = ctl->emit_s; e = ctl->emit_e; vbase = ctl->emit_vbase;
@@ -725,6 +732,7 @@ __global__ void __launch_bounds__(256) k_chunk_emit(const int *__restrict__ tri,
 // turns the scan's result into the chunk's sizes, the range k_chunk_emit writes, and the next start.  A chunk longer than the scan
 // window raises `overflow` and the host loop below takes over (its window grows on demand).
 __global__ void __launch_bounds__(256) k_chunk_begin(ChunkCtl *ctl, unsigned long long *status, long long m, long long span_max) {
+	pdl_enter();
 	if (ctl->done) return;
 	const long long s = ctl->s;
 	if (s >= m) { if (blockIdx.x == 0 && threadIdx.x == 0) ctl->done = 1; return; }
@@ -733,6 +741,7 @@ __global__ void __launch_bounds__(256) k_chunk_begin(ChunkCtl *ctl, unsigned lon
 	if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->tile_counter = 0; ctl->end = 0x7fffffffffffffffll; }
 }
 __global__ void k_chunk_close(ChunkCtl *ctl, const unsigned *__restrict__ incl, long long m, long long span_max, int *chunk_v, int *chunk_t) {
+	pdl_enter();
 	if (ctl->done) return;
 	const long long s = ctl->s, span = min(span_max, m - s);
 	const bool closed = ctl->end != 0x7fffffffffffffffll;
@@ -786,14 +795,14 @@ static int transfer_chunk_device(const uint4 *d_verts, int n_vertices, const int
 	if (!cuda_ok(cudaMemsetAsync(b + o_cnt, 0, o_start - o_cnt, st), "clear counters") || !cuda_ok(cudaMemsetAsync(ctl, 0, sizeof(ChunkCtl), st), "clear control")) return -1;
 	k_occ_count<<<grid, 256, 0, st>>>(d_tri, m, n_vertices, cnt, &ctl->err);
 	if (n_vertices <= 8192) {
-		k_scan_single<<<1, 1024, 0, st>>>(cnt, start, n_vertices);
+		launch_chain(true, k_scan_single, dim3((unsigned)(1)), 1024, 0, st, cnt, start, n_vertices);
 	} else {
 		const int tiles = (int)(((long long)n_vertices + kTile - 1) / kTile);
 		if (!cuda_ok(cudaMemsetAsync(status, 0, 8 * (size_t)tiles, st), "clear scan status")) return -1;
-		k_scan_excl<<<std::max(1, std::min(tiles, 148 * 8)), kScanThreads, 0, st>>>(cnt, start, n_vertices, status, &ctl->tile_counter, &ctl->err);
+		launch_chain(true, k_scan_excl, dim3((unsigned)(std::max(1, std::min(tiles, 148 * 8)))), kScanThreads, 0, st, cnt, start, n_vertices, status, &ctl->tile_counter, &ctl->err);
 	}
-	k_occ_fill<<<grid, 256, 0, st>>>(d_tri, m, n_vertices, start, cur, pos);
-	k_occ_link<<<pack_grid(16ll * n_vertices), 256, 0, st>>>(n_vertices, start, pos, prev);
+	launch_chain(true, k_occ_fill, dim3((unsigned)(grid)), 256, 0, st, d_tri, m, n_vertices, start, cur, pos);
+	launch_chain(true, k_occ_link, dim3((unsigned)(pack_grid(16ll * n_vertices))), 256, 0, st, n_vertices, start, pos, prev);
 	count_launch(4);
 	if (!cuda_ok(cudaGetLastError(), "occurrence lists")) return -1;
 	ChunkCtl h;
@@ -820,10 +829,10 @@ static int transfer_chunk_device(const uint4 *d_verts, int n_vertices, const int
 			const ChunkCtl *hc = reinterpret_cast<const ChunkCtl *>(pin);
 			for (int batch = 0; ok; batch++) {
 				for (int i = 0; i < 16; i++) {
-					k_chunk_begin<<<32, 256, 0, st>>>(ctl, status, m, span_max);
-					k_chunk_scan<<<scan_grid, kScanThreads, 0, st>>>(prev, m, -1, span_max, status, ctl, incl, kChunkLimit);
-					k_chunk_close<<<1, 1, 0, st>>>(ctl, incl, m, span_max, cv, ct);
-					k_chunk_emit<<<pack_grid(4 * std::min(span_max, m)), 256, 0, st>>>(d_tri, prev, 0, -1, incl, d_verts, 0u, new_tri, new_verts, ctl);
+					launch_chain(true, k_chunk_begin, dim3((unsigned)(32)), 256, 0, st, ctl, status, m, span_max);
+					launch_chain(true, k_chunk_scan, dim3((unsigned)(scan_grid)), kScanThreads, 0, st, prev, m, -1, span_max, status, ctl, incl, kChunkLimit);
+					launch_chain(true, k_chunk_close, dim3((unsigned)(1)), 1, 0, st, ctl, incl, m, span_max, cv, ct);
+					launch_chain(true, k_chunk_emit, dim3((unsigned)(pack_grid(4 * std::min(span_max, m)))), 256, 0, st, d_tri, prev, 0, -1, incl, d_verts, 0u, new_tri, new_verts, ctl);
 				}
 				count_launch(64);
 				ok = cuda_ok(cudaGetLastError(), "chunk loop") && cuda_ok(cudaMemcpyAsync(pin, ctl, sizeof(ChunkCtl), cudaMemcpyDeviceToHost, st), "read control") &&
@@ -854,7 +863,7 @@ static int transfer_chunk_device(const uint4 *d_verts, int n_vertices, const int
 			ChunkCtl init; memset(&init, 0, sizeof(init)); init.end = 0x7fffffffffffffffll;
 			if (!cuda_ok(cudaMemcpyAsync(ctl, &init, sizeof(init), cudaMemcpyHostToDevice, st), "reset control") ||
 				!cuda_ok(cudaMemsetAsync(status, 0, 8 * (size_t)tiles, st), "clear scan status")) return -1;
-			k_chunk_scan<<<std::max(1, std::min(tiles, 148 * 8)), kScanThreads, 0, st>>>(prev, m, s, span, status, ctl, incl, kChunkLimit);
+			launch_chain(true, k_chunk_scan, dim3((unsigned)(std::max(1, std::min(tiles, 148 * 8)))), kScanThreads, 0, st, prev, m, s, span, status, ctl, incl, kChunkLimit);
 			count_launch(1);
 			if (!cuda_ok(cudaGetLastError(), "k_chunk_scan") || !cuda_ok(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st), "read control") ||
 				!cuda_ok(cudaStreamSynchronize(st), "chunk scan")) return -1;
@@ -866,7 +875,7 @@ static int transfer_chunk_device(const uint4 *d_verts, int n_vertices, const int
 		const long long e = closed ? h.end : m - 1;
 		unsigned n_new = 0;
 		if (!cuda_ok(cudaMemcpyAsync(&n_new, incl + (e - s), 4, cudaMemcpyDeviceToHost, st), "read chunk size")) return -1;
-		k_chunk_emit<<<pack_grid(4 * (e - s + 1)), 256, 0, st>>>(d_tri, prev, s, e, incl, d_verts, vbase, new_tri, new_verts, nullptr);
+		launch_chain(true, k_chunk_emit, dim3((unsigned)(pack_grid(4 * (e - s + 1)))), 256, 0, st, d_tri, prev, s, e, incl, d_verts, vbase, new_tri, new_verts, nullptr);
 		count_launch(1);
 		if (!cuda_ok(cudaGetLastError(), "k_chunk_emit") || !cuda_ok(cudaStreamSynchronize(st), "chunk emit")) return -1;
 		v_sizes.push_back((int)n_new);

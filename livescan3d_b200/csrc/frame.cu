@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 	// times the bytes per outstanding read of the 8-byte-per-thread gather this replaces (7 GB/s measured for that one)
 	__shared__ __align__(16) uint4 s_col[kTile * 3 / 16];
 
+	pdl_trigger();             // a kernel chained behind this one (k_voxel_insert, k_triangles) may move in; it waits for our completion
 	const int tile0 = sd[s_first].tile_begin;
 	const int ntiles = sd[s_end].tile_begin - tile0;
 	const int out_off = d_out_offset ? *d_out_offset : 0;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 		if (kKeepMask && !waited) {
 			// launched programmatically behind k_organized_count (launch_map): everything above ran beside its tail; its keep bytes and
 			// tile counts are visible from here on.  A no-op for a plain launch.
-			asm volatile("griddepcontrol.wait;" ::: "memory");
+			pdl_wait();
 			waited = true;
 		}
 		// ---- the organized count's verdicts for the 8 pixels: one LDG.64, bytes (0/1) -> bits by a multiply ----
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(kScanThreads) k_triangles(const uint8_t *__res
 	const unsigned short *__restrict__ tile_sensor, const int *__restrict__ d2v, int s_first, int s_end, FrameCtl *ctl,
 	unsigned long long *status, int *tri_starts, int *__restrict__ tri)
 {
+	pdl_enter();
 	extern __shared__ unsigned short s_depth[];        // kTile + 3 * max_w + 4 values
 	__shared__ unsigned s_seg[64], s_base, s_total;
 	__shared__ int s_tile;
@@ -667,7 +669,7 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 	__shared__ int s_hx, s_hy;
 	// the map kernel behind us (launch_map, after_count) may move into the SMs as soon as every block of this grid has started: it
 	// waits for this grid's completion (griddepcontrol.wait) before it touches anything written here
-	asm volatile("griddepcontrol.launch_dependents;");
+	pdl_trigger();
 	const int s = s_first + blockIdx.z;
 	const int w = sd[s].w, h = sd[s].h;
 	const int tx0 = blockIdx.x * kOrgTW, ty0 = blockIdx.y * kOrgTH;
@@ -871,6 +873,7 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 	const int *__restrict__ culled_starts, int s_first, int s_end, FrameCtl *ctl,
 	VoxBucket *table, unsigned *__restrict__ slot_of, unsigned *__restrict__ rank_of)
 {
+	pdl_enter();
 	const int N = ctl->n_culled;
 	const int lane = threadIdx.x & 31;
 	for (int g0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); g0 < N; g0 += gridDim.x * blockDim.x) {
@@ -930,6 +933,7 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const uint4 *__restrict__ 
 // K3: every run gets its range of the sorted array (any order will do): the elected points carry their run's total through a
 // block-wide scan, one atomicAdd on the cursor per block
 __global__ void __launch_bounds__(256) k_bucket_alloc(const unsigned *__restrict__ slot_of, const unsigned *__restrict__ rank_of, VoxBucket *table, FrameCtl *ctl) {
+	pdl_enter();
 	__shared__ unsigned s_w[8];
 	__shared__ unsigned s_base;
 	const int N = ctl->n_culled;
@@ -969,6 +973,7 @@ __global__ void __launch_bounds__(256) k_bucket_alloc(const unsigned *__restrict
 __global__ void __launch_bounds__(256) k_cell_scatter(const uint4 *__restrict__ cloud, const unsigned *__restrict__ slot_of,
 	const unsigned *__restrict__ rank_of, const VoxBucket *__restrict__ table, const FrameCtl *ctl, float4 *__restrict__ sorted)
 {
+	pdl_enter();
 	const int N = ctl->n_culled;
 	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
 		const uint4 p = cloud[g];
@@ -988,6 +993,7 @@ __global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const VoxB
 	const float4 *__restrict__ sorted, const SensorDesc *__restrict__ sd,
 	const int *__restrict__ culled_starts, int s_first, int s_end, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep)
 {
+	pdl_enter();
 	__shared__ uint2 s_rng[kCountWarps][kMaxRanges][32];      // [warp][range][lane] = (start, count): conflict-free per-lane lists
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int N = ctl->n_culled;
@@ -1127,6 +1133,7 @@ __global__ void __launch_bounds__(kCountWarps * 32) k_neighbour_count(const VoxB
 // after the count: the slots this run's points touched go back to zero (the table is cleared by its users, not by a memset of
 // all of it: 4 M slots for 0.1 M occupied ones on the bench frame)
 __global__ void __launch_bounds__(256) k_voxel_cleanup(const unsigned *__restrict__ slot_of, VoxBucket *table, const FrameCtl *ctl) {
+	pdl_enter();
 	const int N = ctl->n_culled;
 	const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
@@ -1142,6 +1149,7 @@ __global__ void __launch_bounds__(kScanThreads) k_filter_compact(const uint4 *__
 	const int *__restrict__ culled_starts, int s_first, int s_end, FrameCtl *ctl, unsigned long long *status, int *final_starts,
 	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ old_to_new, PeerDst peers)
 {
+	pdl_enter();
 	__shared__ uint4 stage[kTile];
 	__shared__ unsigned sm[16];
 	__shared__ int s_tile;
@@ -1710,28 +1718,6 @@ __global__ void __launch_bounds__(256) k_copy_mesh_out(const uint4 *__restrict__
 	}
 }
 
-static bool frame_use_pdl() {
-	static const int v = getenv("LS3D_FRAME_PDL") ? atoi(getenv("LS3D_FRAME_PDL")) : 1;
-	return v != 0;
-}
-
-// kernel launch, optionally with the programmatic-stream-serialization attribute: the kernel may then become resident while its
-// predecessor in the stream (which has executed griddepcontrol.launch_dependents) still runs, and orders itself with griddepcontrol.wait
-template <typename... KArgs, typename... Args>
-static void launch_ex(bool programmatic, void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = grid;
-	cfg.blockDim = dim3(block);
-	cfg.dynamicSmemBytes = smem;
-	cfg.stream = st;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = 1;
-	cfg.attrs = attr;
-	cfg.numAttrs = programmatic && frame_use_pdl() ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);          // errors are picked up by the caller's cudaGetLastError
-}
-
 // K1 launcher.  keep_px != nullptr: AND the organized neighbour-count mask into the validity test.  after_count: the organized count
 // of the same sensors is the previous launch in this stream (nothing in between) — K1 is then launched programmatically: its blocks
 // move in as the count's last blocks leave, fetch their depths, and wait for the count's results only then.
@@ -1762,11 +1748,11 @@ static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, i
 	}
 	stage_begin(f, kTsMap, st);
 	if (f->want_d2v || f->want_triangles) {
-		if (keep_px) launch_ex(after_count, k_map_cull_compact<true, true>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers, tile_lo, tile_hi, 1.0f);
-		else launch_ex(false, k_map_cull_compact<true, false>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers, tile_lo, tile_hi, 1.0f);
+		if (keep_px) launch_chain(after_count, k_map_cull_compact<true, true>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), keep_px, tc, peers, tile_lo, tile_hi, 1.0f);
+		else launch_chain(false, k_map_cull_compact<true, false>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, f->d2v.as<int>(), nullptr, nullptr, peers, tile_lo, tile_hi, 1.0f);
 	} else {
-		if (keep_px) launch_ex(after_count, k_map_cull_compact<false, true>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers, tile_lo, tile_hi, 1.0f);
-		else launch_ex(false, k_map_cull_compact<false, false>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers, tile_lo, tile_hi, 1.0f);
+		if (keep_px) launch_chain(after_count, k_map_cull_compact<false, true>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, keep_px, tc, peers, tile_lo, tile_hi, 1.0f);
+		else launch_chain(false, k_map_cull_compact<false, false>, dim3(blocks), kScanThreads, stage_bytes, st, dd, dc, sd, ts, rays, s_first, s_end, b, f->ctl, f->status_a, f->culled_starts, out, d_off, nullptr, nullptr, nullptr, peers, tile_lo, tile_hi, 1.0f);
 	}
 	stage_end(f, kTsMap, st);
 	count_launch(1);
@@ -1776,7 +1762,7 @@ static int launch_map(Ls3dFrame *f, const void *d_depth, const void *d_colors, i
 static int frame_merge_stage(Ls3dFrame *f, int s_first, int s_end, long long n_max, uint4 *dst, const int *d_dst_offset, const PeerDst &peers, cudaStream_t st) {
 	const int tiles = (int)((n_max + kTile - 1) / kTile);
 	stage_begin(f, kTsCompact, st);
-	k_filter_compact<<<std::max(1, std::min(tiles, f->sm_count * 6)), kScanThreads, 0, st>>>(f->cloud0.as<uint4>(), f->keep.as<uint8_t>(),
+	launch_chain(!f->timing, k_filter_compact, dim3((unsigned)(std::max(1, std::min(tiles, f->sm_count * 6)))), kScanThreads, 0, st, f->cloud0.as<uint4>(), f->keep.as<uint8_t>(),
 		f->culled_starts, s_first, s_end, f->ctl, f->status_b, f->final_starts, dst, d_dst_offset, f->map.as<int>(), peers);
 	stage_end(f, kTsCompact, st);
 	count_launch(1);
@@ -1796,17 +1782,17 @@ static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n
 	stage_end(f, kTsHashClear, st);
 	const int pt_blocks = (int)std::max<long long>(1, std::min<long long>((n_max + 255) / 256, (long long)f->sm_count * 8));
 	stage_begin(f, kTsInsert, st);
-	k_voxel_insert<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
+	launch_chain(!f->timing, k_voxel_insert, dim3((unsigned)(pt_blocks)), 256, 0, st, f->cloud0.as<uint4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
 		table, f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>());
 	stage_end(f, kTsInsert, st);
 	stage_begin(f, kTsRanges, st);
-	k_bucket_alloc<<<pt_blocks, 256, 0, st>>>(f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(), table, f->ctl);
-	k_cell_scatter<<<pt_blocks, 256, 0, st>>>(f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(), table, f->ctl, f->sorted.as<float4>());
+	launch_chain(!f->timing, k_bucket_alloc, dim3((unsigned)(pt_blocks)), 256, 0, st, f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(), table, f->ctl);
+	launch_chain(!f->timing, k_cell_scatter, dim3((unsigned)(pt_blocks)), 256, 0, st, f->cloud0.as<uint4>(), f->slot_of.as<unsigned>(), f->rank_of.as<unsigned>(), table, f->ctl, f->sorted.as<float4>());
 	stage_end(f, kTsRanges, st);
 	stage_begin(f, kTsCount, st);
-	k_neighbour_count<<<f->sm_count * 12, kCountWarps * 32, 0, st>>>(table, f->cloud0.as<uint4>(), f->sorted.as<float4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
+	launch_chain(!f->timing, k_neighbour_count, dim3((unsigned)(f->sm_count * 12)), kCountWarps * 32, 0, st, table, f->cloud0.as<uint4>(), f->sorted.as<float4>(), sd, f->culled_starts, s_first, s_end, f->ctl,
 		f->filter_k, f->filter_thr, f->keep.as<uint8_t>());
-	k_voxel_cleanup<<<pt_blocks, 256, 0, st>>>(f->slot_of.as<unsigned>(), table, f->ctl);
+	launch_chain(!f->timing, k_voxel_cleanup, dim3((unsigned)(pt_blocks)), 256, 0, st, f->slot_of.as<unsigned>(), table, f->ctl);
 	stage_end(f, kTsCount, st);
 	count_launch(5);
 	if (!cuda_ok(cudaGetLastError(), "filter kernels")) return -1;
@@ -1899,7 +1885,7 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 				const size_t tri_smem = sizeof(unsigned short) * ((size_t)kTile + 3 * (size_t)mw + 4);
 				if (tri_smem > 200 * 1024) { set_error("triangle stage: image width %d too large for the staged depth rows", mw); return -1; }
 				if (tri_smem > 48 * 1024 && !cuda_ok(cudaFuncSetAttribute(k_triangles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem), "triangle stage shared memory")) return -1;
-				k_triangles<<<std::max(1, std::min(ntiles, f->sm_count * 8)), kScanThreads, tri_smem, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->tile_sensor.as<unsigned short>(),
+				launch_chain(!f->timing, k_triangles, dim3((unsigned)(std::max(1, std::min(ntiles, f->sm_count * 8)))), kScanThreads, tri_smem, st, (const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->tile_sensor.as<unsigned short>(),
 					f->d2v.as<int>(), s_first, s_end, f->ctl, f->status_b, f->tri_starts, f->tri_override ? f->tri_override : f->tri.as<int>());
 				stage_end(f, kTsTriangles, st);
 				count_launch(1);

@@ -50,6 +50,15 @@ struct FrameCtl {
 	int pad[3];
 };
 
+// Programmatic dependent launch (launch_chain in ls3d_internal.h).  A chain of short kernels pays a launch latency per link when each
+// waits for its predecessor to drain before it is even scheduled; launched programmatically, a kernel's blocks may move into the SMs
+// once every block of the predecessor has STARTED (pdl_trigger), and the first thing they do is wait for that grid — and with it
+// every earlier one — to complete and flush (griddepcontrol.wait).  Same ordering as a plain stream, minus the launch latencies;
+// both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
 	unsigned long long v;
 	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));

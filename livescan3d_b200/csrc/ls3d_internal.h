@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstddef>
+#include <cstdlib>
 #include <mutex>
 
 namespace ls3d {
@@ -34,6 +35,28 @@ bool host_block_is_pinned(void *p);     // true: page-locked and mapped, a kerne
 // memcpy spread over a small pool of host threads (the caller takes part): for moving the caller's pageable frame buffers into
 // the library's page-locked staging at more than one core's copy bandwidth.  Small sizes fall through to plain memcpy.
 void parallel_memcpy(void *dst, const void *src, size_t bytes);
+
+// Kernel launch, optionally with the programmatic-stream-serialization attribute (see pdl_enter in ls3d_common.cuh): the kernel may
+// become resident while its predecessor in the stream still runs and orders itself with griddepcontrol.wait.  LS3D_PDL=0 turns every
+// such launch into a plain one (A/B).  Errors are picked up by the caller's cudaGetLastError.
+inline bool pdl_enabled() {
+	static const int v = getenv("LS3D_PDL") ? atoi(getenv("LS3D_PDL")) : 1;
+	return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_chain(bool programmatic, void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = dim3(block);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = programmatic && pdl_enabled() ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // device scratch with grow-only semantics
 struct DevBuf {

@@ -74,15 +74,7 @@ __device__ __forceinline__ int c_float_to_int(float f) {
 	return (f > -2147483904.0f && f < 2147483648.0f) ? __float2int_rz(f) : INT_MIN;
 }
 
-// The correction is a chain of short kernels; from the gather on each is launched programmatically behind its predecessor
-// (launch_chain): its blocks may move into the SMs while the predecessor's last blocks run, and the first thing they do is wait for
-// that grid — and with it every earlier one — to complete.  Same ordering as a plain stream, minus the launch latencies.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
-__device__ __forceinline__ void pdl_enter() {
-	asm volatile("griddepcontrol.launch_dependents;");
-	asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
+// The correction is a chain of short kernels: from the gather on each is launched programmatically behind its predecessor (pdl_enter).
 __global__ void __launch_bounds__(256) k_rad_scatter(const uint8_t *__restrict__ depth, const PreSensor *__restrict__ sd, int *winner) {
 	pdl_trigger();
 	const PreSensor s = sd[blockIdx.y];
@@ -863,25 +855,9 @@ PreCtx *pre_ctx(int n_maps, const int *widths, const int *heights) {
 	return c;
 }
 
-// launch behind the previous kernel of the stream with the programmatic-stream-serialization attribute (see pdl_enter)
-template <typename... KArgs, typename... Args>
-static void launch_chain(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
-	static const int use = getenv("LS3D_RADIAL_PDL") ? atoi(getenv("LS3D_RADIAL_PDL")) : 1;
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = grid;
-	cfg.blockDim = dim3(block);
-	cfg.dynamicSmemBytes = smem;
-	cfg.stream = st;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = 1;
-	cfg.attrs = attr;
-	cfg.numAttrs = use ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);          // errors are picked up by the cudaGetLastError at the end of the chain
-}
-
 // enqueue the whole correction on st for device-resident packed buffers (in place); err word = count[n_maps]
 int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, const float *intr_params, cudaStream_t st) {
+	static const bool rad_pdl = getenv("LS3D_RADIAL_PDL") ? atoi(getenv("LS3D_RADIAL_PDL")) != 0 : true;
 	long long acc = 0;
 	int max_px = 1;
 	// the scratch buffers are one set per process: a correction enqueued on ANOTHER stream must not start before the previous one
@@ -914,11 +890,11 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 	const PreSensor *sd = c->sd.as<PreSensor>();
 	int *count = c->count.as<int>();
 	k_rad_scatter<<<grid, 256, 0, st>>>(d_depth, sd, c->winner.as<int>());
-	launch_chain(k_rad_gather, grid, 256, 0, st, d_depth, d_colors, sd, c->winner.as<int>(), c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+	launch_chain(rad_pdl, k_rad_gather, grid, 256, 0, st, d_depth, d_colors, sd, c->winner.as<int>(), c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
 	static const int env_snapshot = getenv("LS3D_RADIAL_SNAPSHOT") ? atoi(getenv("LS3D_RADIAL_SNAPSHOT")) : 1;         // 0: the fenced round of rounds 1-2 (A/B)
 	for (int r = 0; r < kRadRounds; r++) {
-		if (env_snapshot && r == 0) launch_chain(k_rad_first, dim3((unsigned)((max_px + 255) / 256), (unsigned)n_maps), 256, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
-		else launch_chain(k_rad_round, grid, 256, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+		if (env_snapshot && r == 0) launch_chain(rad_pdl, k_rad_first, dim3((unsigned)((max_px + 255) / 256), (unsigned)n_maps), 256, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
+		else launch_chain(rad_pdl, k_rad_round, grid, 256, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>());
 	}
 	static const int env_wavefront = getenv("LS3D_RADIAL_WAVEFRONT") ? atoi(getenv("LS3D_RADIAL_WAVEFRONT")) : 0;      // 1: the round-1 lockstep wavefront (A/B)
 	static const int env_chains = getenv("LS3D_RADIAL_CHAINS") ? atoi(getenv("LS3D_RADIAL_CHAINS")) : 0;               // 1: the chain kernel of round 1/2 instead of the fixpoint iteration (A/B)
@@ -941,15 +917,15 @@ int radial_enqueue(PreCtx *c, int n_maps, uint8_t *d_depth, uint8_t *d_colors, c
 			if (!cuda_ok(cudaFuncSetAttribute(k_rad_fixpoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fix_smem), "hole fill shared memory")) return -1;
 			fix_attr = true;
 		}
-		launch_chain(k_rad_fixpoint, dim3((unsigned)(n_maps * kFixCluster)), kFixThreads, fix_smem, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(),
+		launch_chain(rad_pdl, k_rad_fixpoint, dim3((unsigned)(n_maps * kFixCluster)), kFixThreads, fix_smem, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(),
 			c->winner.as<int>(), count + n_maps, count + n_maps + 1);
-		launch_chain(k_rad_chains, dim3((unsigned)n_maps), kChainThreads, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps,
+		launch_chain(rad_pdl, k_rad_chains, dim3((unsigned)n_maps), kChainThreads, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps,
 			count + n_maps + 1);
 	} else {
 		// the winner map is free after the gather: it becomes the pixel -> list index map
-		launch_chain(k_rad_chains, dim3((unsigned)n_maps), kChainThreads, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps, nullptr);
+		launch_chain(rad_pdl, k_rad_chains, dim3((unsigned)n_maps), kChainThreads, 0, st, sd, c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>(), c->state.as<unsigned char>(), c->items.as<int>(), c->winner.as<int>(), count + n_maps, nullptr);
 	}
-	launch_chain(k_rad_writeback, dim3((unsigned)std::max<long long>(1, std::min<long long>((c->total_px + 255) / 256, (long long)c->sm_count * 8))), 256, 0, st, d_depth, d_colors, c->total_px,
+	launch_chain(rad_pdl, k_rad_writeback, dim3((unsigned)std::max<long long>(1, std::min<long long>((c->total_px + 255) / 256, (long long)c->sm_count * 8))), 256, 0, st, d_depth, d_colors, c->total_px,
 		c->fdepth.as<unsigned short>(), c->fcolors.as<uint8_t>());
 	count_launch(4 + kRadRounds);
 	if (!cuda_ok(cudaEventRecord(c->ev_done, st), "record end of correction")) return -1;
