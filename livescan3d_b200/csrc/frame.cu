@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 	pdl_trigger();             // a kernel chained behind this one (k_voxel_insert, k_triangles) may move in; it waits for our completion
 	const int tile0 = sd[s_first].tile_begin;
 	const int ntiles = sd[s_end].tile_begin - tile0;
-	const int out_off = d_out_offset ? *d_out_offset : 0;
+	// the output offset may come from the kernel right before us (the multi-GPU count exchange): with a keep mask it is read behind the wait
+	int out_off = (!kKeepMask && d_out_offset) ? *d_out_offset : 0;
 	const int tid = threadIdx.x;
 	// kKeepMask only: this launch places tiles [tile_lo, tile_hi) of the run (bases still count from the run's first tile), so
 	// the host path can merge sensor by sensor as the colours arrive; the look-back variant always walks the whole run
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 			// tile counts are visible from here on.  A no-op for a plain launch.
 			pdl_wait();
 			waited = true;
+			if (d_out_offset) out_off = *d_out_offset;
 		}
 		// ---- the organized count's verdicts for the 8 pixels: one LDG.64, bytes (0/1) -> bits by a multiply ----
 		unsigned keepm = 0xffu;
@@ -265,6 +267,22 @@ __global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
 		unsigned valid = 0;
 		if (kKeepMask) {
 			valid = keepm;            // the count kernel only keeps pixels that have a vertex
+		} else if (LS3D_MAP_PAIRS && !(w & 1) && w >= 8 && rem >= 8) {
+			// even width: four packed pair evaluations (see pass 2 of the keep-mask variant), bit-identical to map_pixel
+			const f32x2 one2 = pk(one, one);
+#pragma unroll 1
+			for (int q = 0; q < 4; q++) {
+				int x = x0 + 2 * q, y = y0;
+				if (x >= w) { x -= w; y++; }
+				const float2 xn = __ldg(reinterpret_cast<const float2 *>(xray + x));
+				f32x2 ax, ay, az;
+				const unsigned ok = map_pixel_pair(m, pk(xn.x, xn.y), __ldg(yray + y), q == 0 ? dq.x : q == 1 ? dq.y : q == 2 ? dq.z : dq.w, one2, ax, ay, az);
+				float a0, a1, b0, b1, g0, g1;
+				upk(ax, a0, a1); upk(ay, b0, b1); upk(az, g0, g1);
+				if (ok & 1u) { s_pos[0][2 * q][tid] = a0; s_pos[1][2 * q][tid] = b0; s_pos[2][2 * q][tid] = g0; }
+				if (ok & 2u) { s_pos[0][2 * q + 1][tid] = a1; s_pos[1][2 * q + 1][tid] = b1; s_pos[2][2 * q + 1][tid] = g1; }
+				valid |= ok << (2 * q);
+			}
 		} else if (rem > 0) {
 			int x = x0, y = y0;
 			float yn = __ldg(yray + y);
@@ -1870,7 +1888,7 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 		if (f->filter_on && f->last_organized) {
 			if (!f->last_depth) { set_error("ls3d_frame_merge: no count stage has run"); return -1; }
 			r = launch_map(f, f->last_depth, f->last_colors, s_first, s_end, dst, d_dst_offset, f->keep_px.as<uint8_t>(), peers, st, 0, -1,
-				(stages & kStageCount) && !f->timing && !f->colors_ready);      // straight behind the count kernel in this stream
+				((stages & kStageCount) || peers.n > 0) && !f->timing && !f->colors_ready);      // straight behind the count kernel (or the count exchange) in this stream
 		} else if (f->filter_on || !(stages & kStageCount)) {
 			r = frame_merge_stage(f, s_first, s_end, n_max, dst, d_dst_offset, peers, st);
 		} else {
@@ -1960,6 +1978,7 @@ static_assert(sizeof(FrameSync) == 256, "Ls3dFrameSync layout");
 struct SyncPeers { int world, rank; FrameSync *p[kMaxPeers]; };
 
 __global__ void k_frame_publish_counts(const FrameCtl *ctl, SyncPeers sp) {
+	pdl_enter();
 	if (threadIdx.x != 0) return;
 	FrameSync *me = sp.p[sp.rank];
 	const unsigned e = ld_volatile_u32(&me->epoch) + 1u;
@@ -1981,6 +2000,7 @@ __global__ void k_frame_publish_counts(const FrameCtl *ctl, SyncPeers sp) {
 }
 
 __global__ void k_frame_wait_peers(SyncPeers sp) {
+	pdl_enter();
 	if (threadIdx.x != 0) return;
 	FrameSync *me = sp.p[sp.rank];
 	const unsigned e = ld_volatile_u32(&me->epoch) + 1u;
@@ -2005,7 +2025,7 @@ static bool sync_peers(SyncPeers &sp, int rank, int world, void *const *peer_syn
 extern "C" int ls3d_frame_publish_counts(Ls3dFrame *f, int rank, int world, void *const *peer_sync, void *stream) {
 	SyncPeers sp;
 	if (!sync_peers(sp, rank, world, peer_sync, "ls3d_frame_publish_counts")) return -1;
-	k_frame_publish_counts<<<1, 32, 0, (cudaStream_t)stream>>>(f ? f->ctl : nullptr, sp);      // f == NULL: a rank without sensors publishes 0
+	launch_chain(true, k_frame_publish_counts, dim3(1), 32, 0, (cudaStream_t)stream, f ? f->ctl : (FrameCtl *)nullptr, sp);      // f == NULL: a rank without sensors publishes 0
 	count_launch(1);
 	return cuda_ok(cudaGetLastError(), "k_frame_publish_counts") ? 0 : -1;
 }
@@ -2013,7 +2033,7 @@ extern "C" int ls3d_frame_publish_counts(Ls3dFrame *f, int rank, int world, void
 extern "C" int ls3d_frame_wait_peers(int rank, int world, void *const *peer_sync, void *stream) {
 	SyncPeers sp;
 	if (!sync_peers(sp, rank, world, peer_sync, "ls3d_frame_wait_peers")) return -1;
-	k_frame_wait_peers<<<1, 32, 0, (cudaStream_t)stream>>>(sp);
+	launch_chain(true, k_frame_wait_peers, dim3(1), 32, 0, (cudaStream_t)stream, sp);
 	count_launch(1);
 	return cuda_ok(cudaGetLastError(), "k_frame_wait_peers") ? 0 : -1;
 }
