@@ -132,13 +132,13 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm(
 // -q0 * 1000 == q0 * -1000 exactly), so the positions are bit-identical; a sum that follows a product is again fma(a, 1.0f, b) with the
 // opaque 1.0f.  Returns bit 0 / bit 1 = the left / right pixel yields a vertex.  The halo staging of the organized count runs on this:
 // a third of the instructions per staged pixel.
-__device__ __forceinline__ unsigned map_pixel_pair(const PixelXform &m, f32x2 xn2, float yn, unsigned dpair, f32x2 one2, f32x2 &wx, f32x2 &wy, f32x2 &wz) {
+__device__ __forceinline__ unsigned map_pixel_pair_xy(const PixelXform &m, f32x2 xn2, f32x2 yn2, unsigned dpair, f32x2 one2, f32x2 &wx, f32x2 &wy, f32x2 &wz) {
 	const float r = 1.0f / 1000.0f;
 	const f32x2 v = pk((float)(dpair & 0xffffu), (float)(dpair >> 16));
 	const f32x2 q0 = mul2(v, pk(r, r));
 	const f32x2 rem = fma2(q0, pk(-1000.0f, -1000.0f), v);
 	f32x2 Z = fma2(rem, pk(r, r), q0);
-	f32x2 X = mul2(xn2, Z), Y = mul2(pk(yn, yn), Z);
+	f32x2 X = mul2(xn2, Z), Y = mul2(yn2, Z);
 	X = fma2(X, one2, pk(m.t0, m.t0)); Y = fma2(Y, one2, pk(m.t1, m.t1)); Z = fma2(Z, one2, pk(m.t2, m.t2));
 	wx = fma2(fma2(mul2(X, pk(m.r0, m.r0)), one2, mul2(Y, pk(m.r1, m.r1))), one2, mul2(Z, pk(m.r2, m.r2)));
 	wy = fma2(fma2(mul2(X, pk(m.r3, m.r3)), one2, mul2(Y, pk(m.r4, m.r4))), one2, mul2(Z, pk(m.r5, m.r5)));
@@ -149,6 +149,9 @@ __device__ __forceinline__ unsigned map_pixel_pair(const PixelXform &m, f32x2 xn
 	if ((dpair & 0xffffu) && !(x0 < m.minX || x0 > m.maxX || y0 < m.minY || y0 > m.maxY || z0 < m.minZ || z0 > m.maxZ)) ok |= 1u;
 	if ((dpair >> 16) && !(x1 < m.minX || x1 > m.maxX || y1 < m.minY || y1 > m.maxY || z1 < m.minZ || z1 > m.maxZ)) ok |= 2u;
 	return ok;
+}
+__device__ __forceinline__ unsigned map_pixel_pair(const PixelXform &m, f32x2 xn2, float yn, unsigned dpair, f32x2 one2, f32x2 &wx, f32x2 &wy, f32x2 &wz) {
+	return map_pixel_pair_xy(m, xn2, pk(yn, yn), dpair, one2, wx, wy, wz);
 }
 
 
@@ -168,11 +171,14 @@ __device__ __forceinline__ unsigned color_line_mask(int k) {          // threads
 // kKeepMask: AND the organized neighbour count's per-pixel mask into the validity test.  In that mode the count kernel
 // has already left every tile's survivor count in tile_count[], so a tile's base is a plain sum over its predecessors
 // (no inter-block dependency at all) and tiles are assigned statically; otherwise the base comes from the look-back scan.
+#ifndef LS3D_MAP_MINBLOCKS
+#define LS3D_MAP_MINBLOCKS 6
+#endif
 #ifndef LS3D_MAP_PAIRS
 #define LS3D_MAP_PAIRS 1
 #endif
 template <bool kWriteD2V, bool kKeepMask>
-__global__ void __launch_bounds__(kScanThreads, 6) k_map_cull_compact(
+__global__ void __launch_bounds__(kScanThreads, LS3D_MAP_MINBLOCKS) k_map_cull_compact(
 	const uint8_t *__restrict__ depth, const uint8_t *__restrict__ colors, const SensorDesc *__restrict__ sd, const unsigned short *__restrict__ tile_sensor,
 	const float *__restrict__ rays, int s_first, int s_end, Bounds6 bnd, FrameCtl *ctl, unsigned long long *status, int *culled_starts,
 	uint4 *__restrict__ out, const int *__restrict__ d_out_offset, int *__restrict__ d2v, const uint8_t *__restrict__ keep_px,
@@ -584,7 +590,10 @@ __global__ void __launch_bounds__(kScanThreads) k_triangles(const uint8_t *__res
 // d2 <= thr over its window, leaving at k; pixels whose window exceeds the halo (very near depth, large radii)
 // walk the window in global memory instead, recomputing candidates from the depth image.  Same fp32 expressions,
 // same count >= k decision as the voxel-hash path and the reference — only the candidate enumeration differs.
-constexpr int kOrgTW = 32, kOrgRows = 8, kOrgPPT = 2, kOrgTH = kOrgRows * kOrgPPT, kOrgHalo = 8;   // 32x16 pixel tile, 256 threads, 2 pixels (rows ly, ly+8) per thread
+#ifndef LS3D_ORG_PPT
+#define LS3D_ORG_PPT 2
+#endif
+constexpr int kOrgTW = 32, kOrgRows = 8, kOrgPPT = LS3D_ORG_PPT, kOrgTH = kOrgRows * kOrgPPT, kOrgHalo = 8;   // 32x16 pixel tile, 256 threads, 2 pixels (rows ly, ly+8) per thread
 constexpr int kOrgSW = kOrgTW + 2 * kOrgHalo, kOrgSH = kOrgTH + 2 * kOrgHalo;
 
 // count{d2 <= thr} over rows ci + dy*kOrgSW (dy = 0, -1, +1, -2, ... up to +-rv: centre rows first, so an inlier reaches k
@@ -621,6 +630,27 @@ __device__ __forceinline__ int org_count_dispatch(int hx, const float4 *__restri
 	}
 }
 
+#ifndef LS3D_ORG_PACKED
+#define LS3D_ORG_PACKED 1
+#endif
+#ifndef LS3D_ORG_ONEARRAY
+#define LS3D_ORG_ONEARRAY 1
+#endif
+#ifndef LS3D_ORG_OWNPAIR
+#define LS3D_ORG_OWNPAIR 1
+#endif
+#ifndef LS3D_ORG_PAIRSTAGE
+#define LS3D_ORG_PAIRSTAGE 1
+#endif
+#ifndef LS3D_ORG_MINBLOCKS
+#define LS3D_ORG_MINBLOCKS 5
+#endif
+#ifndef LS3D_ORG_ROWS2
+#define LS3D_ORG_ROWS2 1
+#endif
+#ifndef LS3D_ORG_NOBAR1
+#define LS3D_ORG_NOBAR1 1
+#endif
 template <int HX>
 __device__ __forceinline__ int org_count_rows2(const float *__restrict__ tx, const float *__restrict__ ty, const float *__restrict__ tz,
 	int ci, int rv, float qx, float qy, float qz, int k, float thr, f32x2 one2) {
@@ -629,10 +659,7 @@ __device__ __forceinline__ int org_count_rows2(const float *__restrict__ tx, con
 	const float kf = (float)k;
 	f32x2 acc = pk(0.0f, 0.0f);
 	float cnt = 0.0f;
-#pragma unroll 1
-	for (int j = 0; j <= 2 * rv && cnt < kf; j++) {
-		const int dy = (j & 1) ? -((j + 1) >> 1) : (j >> 1);
-		const int b = c0 + dy * kOrgSW;
+	auto row = [&](int b) {
 #pragma unroll
 		for (int p = 0; p <= HX; p++) {
 			const f32x2 X = *reinterpret_cast<const f32x2 *>(tx + b + 2 * p), Y = *reinterpret_cast<const f32x2 *>(ty + b + 2 * p), Z = *reinterpret_cast<const f32x2 *>(tz + b + 2 * p);
@@ -642,10 +669,29 @@ __device__ __forceinline__ int org_count_rows2(const float *__restrict__ tx, con
 			upk(s, lo, hi);
 			acc = add2(acc, pk(lo <= thr ? 1.0f : 0.0f, hi <= thr ? 1.0f : 0.0f));
 		}
+	};
+#if LS3D_ORG_ROWS2
+	// the centre row, then rows -r and +r together: one exit test per two rows (same rows as below, so the same decision)
+	row(c0);
+	{ float a0, a1; upk(acc, a0, a1); cnt = a0 + a1; }
+#pragma unroll 1
+	for (int r = 1; r <= rv && cnt < kf; r++) {
+		row(c0 - r * kOrgSW);
+		row(c0 + r * kOrgSW);
 		float a0, a1;
 		upk(acc, a0, a1);
 		cnt = a0 + a1;
 	}
+#else
+#pragma unroll 1
+	for (int j = 0; j <= 2 * rv && cnt < kf; j++) {
+		const int dy = (j & 1) ? -((j + 1) >> 1) : (j >> 1);
+		row(c0 + dy * kOrgSW);
+		float a0, a1;
+		upk(acc, a0, a1);
+		cnt = a0 + a1;
+	}
+#endif
 	return (int)cnt;
 }
 
@@ -662,20 +708,25 @@ __device__ __forceinline__ int org_count_dispatch2(int hx, const float *__restri
 	}
 }
 
-#ifndef LS3D_ORG_PACKED
-#define LS3D_ORG_PACKED 1
-#endif
-#ifndef LS3D_ORG_PAIRSTAGE
-#define LS3D_ORG_PAIRSTAGE 1
-#endif
-#ifndef LS3D_ORG_MINBLOCKS
-#define LS3D_ORG_MINBLOCKS 6
-#endif
+// the per-run control block cleared by a kernel instead of a memset node, so that the organized count can be chained behind it
+// programmatically (its blocks start while this one runs; they wait for it before their first write)
+__global__ void __launch_bounds__(256) k_zero_control(uint4 *p, int n16) {
+	pdl_trigger();
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organized_count(const uint8_t *__restrict__ depth, const SensorDesc *__restrict__ sd,
 	const float *__restrict__ rays, int s_first, Bounds6 bnd, FrameCtl *ctl, int k, float thr, uint8_t *__restrict__ keep_px, unsigned *tile_count, float one)
 {
 #if LS3D_ORG_PACKED
+#if LS3D_ORG_ONEARRAY
+	// one array, three planes: a candidate's y and z are its x address plus a constant (immediate offsets instead of three address computations per row)
+	__shared__ __align__(16) float tile_xyz[3 * kOrgSH * kOrgSW];
+	float *const tile_x = tile_xyz, *const tile_y = tile_xyz + kOrgSH * kOrgSW, *const tile_z = tile_xyz + 2 * kOrgSH * kOrgSW;
+#else
 	__shared__ __align__(16) float tile_x[kOrgSH * kOrgSW], tile_y[kOrgSH * kOrgSW], tile_z[kOrgSH * kOrgSW];
+#endif
 	auto put = [&](int i, float a, float b, float c) { tile_x[i] = a; tile_y[i] = b; tile_z[i] = c; };
 	constexpr int kReachX = kOrgHalo - 1;       // pairs start at even columns: one halo column is spent on the alignment
 #else
@@ -697,8 +748,13 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 	const float *xray = rays + sd[s].ray_off, *yray = xray + w;
 	const float *xreach = yray + h, *yreach = xreach + w;     // fx*sqrt(1+xn^2), fy*sqrt(1+yn^2): the window reach per unit of r'/(Z-r')
 	const int tid = threadIdx.x;
+#if LS3D_ORG_NOBAR1
+	__shared__ int s_wx[kOrgRows], s_wy[kOrgRows];      // every warp's reach: no initialisation, so no barrier before phase 0
+	if (tid == 0) s_kept = 0;                          // first used behind the barriers below
+#else
 	if (tid == 0) { s_kept = 0; s_hx = 0; s_hy = 0; }
 	__syncthreads();
+#endif
 
 	// ---- phase 0: this thread's own pixels -> world positions into the tile centre, and how far their windows reach ----
 	const int lx = tid & (kOrgTW - 1), ly = tid / kOrgTW;
@@ -709,6 +765,46 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 	int ru[kOrgPPT], rv[kOrgPPT];
 	bool has[kOrgPPT], in_halo[kOrgPPT];
 	int mu = 0, mv = 0;
+#if LS3D_ORG_PACKED && LS3D_ORG_OWNPAIR && (LS3D_ORG_PPT % 2 == 0)
+	// the thread's pixels two at a time (same column, rows 8 apart) through the packed pair map: bit-identical positions
+	unsigned dd[kOrgPPT];
+	{
+		const float xn = x < w ? __ldg(xray + x) : 0.0f;
+		const f32x2 one2 = pk(one, one);
+#pragma unroll
+		for (int p = 0; p < kOrgPPT; p += 2) {
+			const int ya = ty0 + ly + kOrgRows * p, yb = ya + kOrgRows;
+			const bool ina = x < w && ya < h, inb = x < w && yb < h;
+			dd[p] = ina ? (unsigned)__ldg(dimg + (size_t)ya * w + x) : 0u;
+			dd[p + 1] = inb ? (unsigned)__ldg(dimg + (size_t)yb * w + x) : 0u;
+			f32x2 ax, ay, az;
+			const unsigned ok = map_pixel_pair_xy(m, pk(xn, xn), pk(ina ? __ldg(yray + ya) : 0.0f, inb ? __ldg(yray + yb) : 0.0f), dd[p] | (dd[p + 1] << 16), one2, ax, ay, az);
+			float a0, a1, b0, b1, g0, g1;
+			upk(ax, a0, a1); upk(ay, b0, b1); upk(az, g0, g1);
+			has[p] = (ok & 1u) != 0; has[p + 1] = (ok & 2u) != 0;
+			qx[p] = has[p] ? a0 : qnan; qy[p] = has[p] ? b0 : qnan; qz[p] = has[p] ? g0 : qnan;
+			qx[p + 1] = has[p + 1] ? a1 : qnan; qy[p + 1] = has[p + 1] ? b1 : qnan; qz[p + 1] = has[p + 1] ? g1 : qnan;
+		}
+	}
+#pragma unroll
+	for (int p = 0; p < kOrgPPT; p++) {
+		const int y = ty0 + ly + kOrgRows * p;
+		ru[p] = 0; rv[p] = 0;
+		if (has[p]) {
+			const float den = (float)dd[p] * 0.001f - rp;
+			ru[p] = 1 << 28; rv[p] = 1 << 28;
+			if (den > 1e-6f) {
+				const float g = __fdividef(rp, den) * 1.002f;
+				const float fu = __ldg(xreach + x) * g + 1e-2f, fv = __ldg(yreach + y) * g + 1e-2f;
+				if (fu < 1e8f) ru[p] = (int)ceilf(fu);
+				if (fv < 1e8f) rv[p] = (int)ceilf(fv);
+			}
+		}
+		put((ly + kOrgRows * p + kOrgHalo) * kOrgSW + lx + kOrgHalo, qx[p], qy[p], qz[p]);
+		in_halo[p] = has[p] && ru[p] <= kReachX && rv[p] <= kOrgHalo;
+		if (in_halo[p]) { mu = max(mu, ru[p]); mv = max(mv, rv[p]); }
+	}
+#else
 #pragma unroll
 	for (int p = 0; p < kOrgPPT; p++) {
 		const int y = ty0 + ly + kOrgRows * p;
@@ -735,11 +831,19 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 		in_halo[p] = has[p] && ru[p] <= kReachX && rv[p] <= kOrgHalo;
 		if (in_halo[p]) { mu = max(mu, ru[p]); mv = max(mv, rv[p]); }
 	}
+#endif
 	const int hxw = __reduce_max_sync(kFull, mu), hyw = __reduce_max_sync(kFull, mv);      // this warp's reach
+#if LS3D_ORG_NOBAR1
+	if ((tid & 31) == 0) { s_wx[tid >> 5] = hxw; s_wy[tid >> 5] = hyw; }
+	__syncthreads();
+	const int bhx = __reduce_max_sync(kFull, s_wx[tid & (kOrgRows - 1)]), bhy = __reduce_max_sync(kFull, s_wy[tid & (kOrgRows - 1)]);
+#else
 	if ((tid & 31) == 0 && (hxw | hyw)) { atomicMax(&s_hx, hxw); atomicMax(&s_hy, hyw); }
 	__syncthreads();
-	const int hy = s_hy;                      // block-uniform reach of the shared-memory windows (0,0: nobody needs the halo)
-	const int hx = (LS3D_ORG_PACKED && (s_hx | s_hy)) ? max(s_hx, 1) + 1 : s_hx;      // packed: dispatch floor 1, one column more for the pair alignment
+	const int bhx = s_hx, bhy = s_hy;
+#endif
+	const int hy = bhy;                       // block-uniform reach of the shared-memory windows (0,0: nobody needs the halo)
+	const int hx = (LS3D_ORG_PACKED && (bhx | bhy)) ? max(bhx, 1) + 1 : bhx;      // packed: dispatch floor 1, one column more for the pair alignment
 
 	// ---- phase 1: stage only the halo ring that some window reaches: hy rows above/below, hx columns left/right ----
 	auto stage = [&](int r, int c) {          // tile coordinates
@@ -807,6 +911,7 @@ __global__ void __launch_bounds__(kOrgTW * kOrgRows, LS3D_ORG_MINBLOCKS) k_organ
 	__syncthreads();
 
 	// ---- phase 2: count ----
+	pdl_wait();          // chained behind k_zero_control: the tile counts and the control block are clear before anything is written
 	unsigned kept_total = 0;
 #pragma unroll
 	for (int p = 0; p < kOrgPPT; p++) {
@@ -1821,13 +1926,13 @@ static int frame_filter_stages(Ls3dFrame *f, int s_first, int s_end, long long n
 
 // K1o: per-pixel survivor mask of sensors [s_first, s_end) straight from the depth images (the cloud is only materialised by the
 // merge stage); adds to ctl->n_kept and the per-tile survivor counts, which the caller has zeroed
-static int launch_organized_count(Ls3dFrame *f, const void *d_depth, int s_first, int s_end, cudaStream_t st) {
+static int launch_organized_count(Ls3dFrame *f, const void *d_depth, int s_first, int s_end, cudaStream_t st, bool chained = false) {
 	Bounds6 b;
 	memcpy(b.v, f->bounds, sizeof(b.v));
 	int mw = 0, mh = 0;
 	for (int i = s_first; i < s_end; i++) { mw = std::max(mw, f->w[i]); mh = std::max(mh, f->h[i]); }
 	const dim3 grid((mw + kOrgTW - 1) / kOrgTW, (mh + kOrgTH - 1) / kOrgTH, s_end - s_first);
-	k_organized_count<<<grid, kOrgTW * kOrgRows, 0, st>>>((const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->rays.as<float>(), s_first, b, f->ctl, f->filter_k, f->filter_thr,
+	launch_chain(chained, k_organized_count, grid, kOrgTW * kOrgRows, 0, st, (const uint8_t *)d_depth, f->sd.as<SensorDesc>(), f->rays.as<float>(), s_first, b, f->ctl, f->filter_k, f->filter_thr,
 		f->keep_px.as<uint8_t>(), reinterpret_cast<unsigned *>(f->status_b), 1.0f);
 	count_launch(1);
 	return cuda_ok(cudaGetLastError(), "k_organized_count") ? 0 : -1;
@@ -1860,12 +1965,17 @@ static int frame_run_impl(Ls3dFrame *f, const void *d_depth, const void *d_color
 		f->last_colors = d_colors;
 		f->ev_recorded = 0;
 		stage_begin(f, kTsWhole, st);
-		if (!cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block")) return -1;
+		const bool chain0 = organized && !f->timing && pdl_enabled() && f->zero_bytes % 16 == 0;
+		if (chain0) {
+			const int n16 = (int)(f->zero_bytes / 16);
+			k_zero_control<<<(n16 + 255) / 256, 256, 0, st>>>(f->zero.as<uint4>(), n16);
+			count_launch(1);
+		} else if (!cuda_ok(cudaMemsetAsync(f->zero.p, 0, f->zero_bytes, st), "clear control block")) return -1;
 		// (Measured and dropped: merging the first sensors on a second stream beside the count of the last ones — 67.7-69.6 us per
 		// frame against 60.5 serial; two more launches and two cross-stream waits cost more than the overlap returns.)
 		if (organized) {
 			stage_begin(f, kTsOrganized, st);
-			if (launch_organized_count(f, d_depth, s_first, s_end, st) < 0) return -1;
+			if (launch_organized_count(f, d_depth, s_first, s_end, st, chain0) < 0) return -1;
 			stage_end(f, kTsOrganized, st);
 			launched += 1;
 		} else if (f->filter_on) {
