@@ -432,7 +432,7 @@ def run_ours(args, rank, local_rank, world):
     ncu_name = {"organized_neighbour_count": "k_organized_count", "map_cull_compact": "k_map_cull_compact<0, 1>", "voxel_neighbour_count": "k_neighbour_count"}
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak,
                 "traffic": ncu_traffic(ncu_name.get(dom["kernel"], dom["kernel"]))[0], "traffic_source": ncu_traffic(ncu_name.get(dom["kernel"], dom["kernel"]))[1], "peak_source": peak_src,
-                "note": "the neighbour count tests ~40 shared-memory candidates per surviving pixel with exact fp32 d2 (two per instruction, FADD2/FMUL2/FFMA2) after staging tile + halo: issue-bound (ncu r02 frame v2: 74.5 % issue slots, 25.1 M warp instructions of which about half are the distance tests, 0 % tensor pipe); its HBM traffic is below the algorithmic bytes because it never touches the colours; map_cull_compact is the streaming kernel (see profiles/)",
+                "note": "the neighbour count tests ~40 shared-memory candidates per surviving pixel with exact fp32 d2 (two per instruction, FADD2/FMUL2/FFMA2) after staging tile + halo: issue-bound (ncu r02 frame v3: 70 % issue slots, 21.3 M warp instructions of which about half are the distance tests, 0 % tensor pipe); its HBM traffic is below the algorithmic bytes because it never touches the colours; map_cull_compact is the streaming kernel (see profiles/)",
                 "whole_pipeline": {"alg_bytes": whole_alg, "achieved": whole_alg / ms_per_step / 1e6, "frac": whole_alg / ms_per_step / 1e6 / hbm_peak},
                 "stages": stages}
 
