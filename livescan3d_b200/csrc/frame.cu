@@ -9,6 +9,11 @@
 //   filter / KNNeighbors      src/LiveScanClient/filter.cpp:36-81 / :19-34
 //
 // Kernels (all sensors of a run are batched into every launch; "g" is a point's index in the culled cloud):
+//   K1o k_organized_count the filter's verdict per PIXEL for clouds that come from depth images (see its header): 32x16 pixel tiles,
+//                          world positions of tile + halo staged in shared memory (two pixels per packed-fp32 evaluation), packed
+//                          distance tests; leaves keep bytes and per-tile survivor counts for K1.  The normal frame is
+//                          k_zero_control -> K1o -> K1, chained as programmatic dependent launches (launch_chain): each kernel's
+//                          blocks move in while its predecessor's last blocks run and wait for it before they consume its output
 //   K1 k_map_cull_compact  per 2048-pixel tile: u16 depth + RGB in, pinhole map, +t, R*, strict cull, stable
 //                          compaction through a decoupled look-back scan, 16-byte records out (HBM-bound)
 //   K2 k_voxel_insert      per point: its run of 8 voxels along x (30-bit key) found or claimed in a per-sensor open-addressing
