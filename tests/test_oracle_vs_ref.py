@@ -152,6 +152,23 @@ def test_icp_vs_reference():
     assert np.array_equal(rR.view(np.uint32), oR.view(np.uint32)) and np.array_equal(rt.view(np.uint32), ot.view(np.uint32))
 
 
+@needs_ref
+@pytest.mark.parametrize("seed,w,h,stride,iters", [(11, 48, 36, 1, 3), (12, 64, 48, 3, 4), (13, 40, 30, 7, 2), (14, 96, 72, 5, 6), (15, 33, 27, 2, 5),
+                                                  (16, 64, 48, 29, 3), (17, 80, 60, 113, 2)])
+def test_nn_and_icp_seeded_sweep_vs_reference(seed, w, h, stride, iters):
+    """More rigs, sizes (down to 15 points) and iteration counts: NN indices / d2 bits and the whole ICP call, oracle vs the compiled reference."""
+    fr = small_frame(S=2, w=w, h=h, seed_base=seed)
+    A, B = icp_pair(fr, synth.DEFAULT_BOUNDS, stride=stride)
+    assert len(A) > 0 and len(B) > 0
+    ri, rd = orc.ref_find_closest(A, B)
+    oi, od = orc.orc_find_closest(A, B)
+    assert np.array_equal(ri, oi) and np.array_equal(rd.view(np.uint32), od.view(np.uint32))
+    rv, rR, rt = orc.ref_icp(A, B, max_iter=iters)
+    ov, oR, ot, _ = orc.orc_icp(A, B, max_iter=iters)
+    assert np.array_equal(rR.view(np.uint32), oR.view(np.uint32)) and np.array_equal(rt.view(np.uint32), ot.view(np.uint32))
+    assert rv.tobytes() == ov.tobytes()
+
+
 def test_icp_recovers_known_offset():
     """Sanity of the oracle itself: ICP reduces the known 1.5 deg / (8,-5,6) mm perturbation (point-to-point ICP
     slides along the scene's planes, so 10 iterations only take part of it back)."""
