@@ -109,6 +109,21 @@ def test_filter_bit_exact_vs_reference(k, md):
 
 
 @needs_ref
+@pytest.mark.parametrize("seed,w,h,bi,k,md", [(21, 37, 29, 0, 3, 0.12), (22, 5, 5, 1, 1, 0.5), (23, 97, 61, 2, 7, 0.06), (24, 128, 96, 0, 29, 0.09),
+                                             (25, 64, 48, 1, 10, 0.1), (27, 31, 201, 1, 5, 0.08)])
+def test_filter_seeded_sweep_vs_reference(seed, w, h, bi, k, md):
+    """More rigs (odd and extreme aspect ratios, all three bounds presets, k up to 29) with partial survival: masks, vertices, colours."""
+    fr = small_frame(S=2, w=w, h=h, seed_base=seed)
+    for idx in (0, 1):
+        xyz, rgba = cloud_of(fr, BOUNDS[bi], idx)
+        assert len(xyz) > 0
+        rv, rc, rm = orc.ref_filter(xyz, rgba, k, md)
+        ov, oc, om = orc.orc_filter(xyz, rgba, k, md)
+        assert np.array_equal(rm, om)
+        assert rv.tobytes() == ov.tobytes() and rc.tobytes() == oc.tobytes()
+
+
+@needs_ref
 def test_filter_edge_cases_vs_reference():
     fr = small_frame(S=1, w=64, h=48)
     xyz, rgba = cloud_of(fr, synth.SERVER_BOUNDS, 0)
